@@ -1,0 +1,226 @@
+"""ctypes driver for oracle/_ref/libqref.so -- the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; never from qunundrum_b200/.
+
+libqref.so is the reference's own hot-path translation units (built by
+oracle/Makefile from /root/reference/src, see oracle/ref_capi.cpp for the list
+and file:line citations) behind a plain-C handle API.  The built library
+travels to the GPU box with the snapshot; /root/reference itself is not needed
+at run time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libqref.so")
+
+# Slice flag constants (reference: src/common.h:226-257).
+SLICE_FLAGS_ERROR_BOUND_WARNING = 0x00000001
+SLICE_FLAGS_METHOD_SIMPSON = 0x00020000
+SLICE_FLAGS_METHOD_RICHARDSON = 0x00080000
+
+METHOD_HEURISTIC_SIGMA = 0
+METHOD_OPTIMAL_LOCAL_SIGMA = 1
+METHOD_QUICK = 2
+TARGET_D = 0
+TARGET_R = 1
+
+_lib = None
+
+
+def build(reference_root: str = "/root/reference") -> bool:
+    """Compile _ref/libqref.so if the reference sources are present."""
+    if not os.path.isdir(os.path.join(reference_root, "src")):
+        return os.path.exists(LIB_PATH)
+    subprocess.check_call(
+        ["make", "-s", "-j8", "-C", _HERE, f"REF={reference_root}", "ref"])
+    return os.path.exists(LIB_PATH)
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `make -C oracle ref` where "
+            "/root/reference is mounted")
+    L = C.CDLL(LIB_PATH)
+    u32, i32, vp, cp, sz = C.c_uint32, C.c_int32, C.c_void_p, C.c_char_p, C.c_size_t
+    ldp = C.c_void_p  # long double * (numpy longdouble buffers)
+    L.qref_version.restype = cp
+    L.qref_deterministic_d_r.argtypes = [u32, cp, cp, sz]
+    L.qref_deterministic_d_r.restype = C.c_int
+    L.qref_parameters_new.argtypes = [u32, u32, u32, u32, cp, cp]
+    L.qref_parameters_new.restype = vp
+    L.qref_parameters_free.argtypes = [vp]
+    L.qref_parameters_get.argtypes = [vp, C.POINTER(u32)]
+    L.qref_diagonal_parameters_new.argtypes = [u32, u32, u32, u32, u32, u32, cp, cp]
+    L.qref_diagonal_parameters_new.restype = vp
+    L.qref_diagonal_parameters_free.argtypes = [vp]
+    L.qref_distribution_slice_compute.argtypes = [
+        vp, C.c_int, C.c_int, u32, i32, i32, ldp, ldp, ldp, C.POINTER(u32)]
+    L.qref_linear_distribution_slice_compute.argtypes = [
+        vp, C.c_int, C.c_int, u32, i32, ldp, ldp, ldp, C.POINTER(u32)]
+    L.qref_diagonal_distribution_slice_compute.argtypes = [
+        vp, C.c_int, u32, i32, i32, ldp, ldp, ldp, C.POINTER(u32)]
+    L.qref_probability_approx.argtypes = [vp, u32, cp, cp, cp, cp, sz]
+    L.qref_probability_approx.restype = C.c_int
+    L.qref_probability_approx_quick.argtypes = [vp, cp, cp, cp, sz]
+    L.qref_linear_probability.argtypes = [vp, C.c_int, cp, cp, sz]
+    L.qref_diagonal_probability_f_eta.argtypes = [vp, cp, i32, u32, cp, sz]
+    _lib = L
+    return L
+
+
+def deterministic_d_r(m: int) -> tuple[int, int]:
+    """parameters_selection_deterministic_d_r (src/parameters_selection.cpp:21)."""
+    cap = 4096
+    d = C.create_string_buffer(cap)
+    r = C.create_string_buffer(cap)
+    if lib().qref_deterministic_d_r(m, d, r, cap) != 0:
+        raise RuntimeError("buffer too small")
+    return int(d.value), int(r.value)
+
+
+class RefParameters:
+    """Parameters (src/parameters.h:33-114) owned by the reference library."""
+
+    def __init__(self, m: int, s: int, d: int, r: int, t: int = 30, l: int = 0):
+        self.h = lib().qref_parameters_new(
+            m, s, l, t, str(d).encode(), str(r).encode())
+        if not self.h:
+            raise ValueError("bad d/r")
+        out = (C.c_uint32 * 8)()
+        lib().qref_parameters_get(self.h, out)
+        (self.m, self.l, self.s, self.t, self.min_alpha_d, self.max_alpha_d,
+         self.min_alpha_r, self.max_alpha_r) = [int(x) for x in out]
+        self.d, self.r = d, r
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qref_parameters_free(self.h)
+            self.h = None
+
+
+class RefDiagonalParameters:
+    """Diagonal_Parameters (src/diagonal_parameters.h:32-106)."""
+
+    def __init__(self, m: int, sigma: int, s: int, d: int, r: int,
+                 eta_bound: int = 0, t: int = 30, l: int = 0):
+        self.h = lib().qref_diagonal_parameters_new(
+            m, sigma, s, l, eta_bound, t, str(d).encode(), str(r).encode())
+        if not self.h:
+            raise ValueError("bad d/r")
+        self.m, self.sigma, self.s, self.t, self.eta_bound = m, sigma, s, t, eta_bound
+        self.d, self.r = d, r
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qref_diagonal_parameters_free(self.h)
+            self.h = None
+
+
+class RefSlice:
+    def __init__(self, cells, total_probability, total_error, flags):
+        self.cells = cells  # np.longdouble
+        self.total_probability = total_probability
+        self.total_error = total_error
+        self.flags = flags
+
+
+def _ld1():
+    return np.zeros(1, dtype=np.longdouble)
+
+
+def distribution_slice_compute(params: RefParameters, dimension: int,
+                               min_log_alpha_d: int, min_log_alpha_r: int,
+                               method: int = METHOD_HEURISTIC_SIGMA,
+                               richardson: bool = True) -> RefSlice:
+    """cells[i_d + dimension * j_r] as the reference stores them."""
+    cells = np.zeros(dimension * dimension, dtype=np.longdouble)
+    tp, te = _ld1(), _ld1()
+    fl = C.c_uint32(0)
+    lib().qref_distribution_slice_compute(
+        params.h, int(richardson), method, dimension, min_log_alpha_d,
+        min_log_alpha_r, cells.ctypes.data, tp.ctypes.data, te.ctypes.data,
+        C.byref(fl))
+    return RefSlice(cells, tp[0], te[0], fl.value)
+
+
+def linear_distribution_slice_compute(params: RefParameters, dimension: int,
+                                      min_log_alpha: int, target: int,
+                                      richardson: bool = True) -> RefSlice:
+    cells = np.zeros(dimension, dtype=np.longdouble)
+    tp, te = _ld1(), _ld1()
+    fl = C.c_uint32(0)
+    lib().qref_linear_distribution_slice_compute(
+        params.h, int(richardson), target, dimension, min_log_alpha,
+        cells.ctypes.data, tp.ctypes.data, te.ctypes.data, C.byref(fl))
+    return RefSlice(cells, tp[0], te[0], fl.value)
+
+
+def diagonal_distribution_slice_compute(params: RefDiagonalParameters,
+                                        dimension: int, min_log_alpha_r: int,
+                                        eta: int,
+                                        richardson: bool = True) -> RefSlice:
+    cells = np.zeros(dimension, dtype=np.longdouble)
+    tp, te = _ld1(), _ld1()
+    fl = C.c_uint32(0)
+    lib().qref_diagonal_distribution_slice_compute(
+        params.h, int(richardson), dimension, min_log_alpha_r, eta,
+        cells.ctypes.data, tp.ctypes.data, te.ctypes.data, C.byref(fl))
+    return RefSlice(cells, tp[0], te[0], fl.value)
+
+
+_CAP = 256
+
+
+def probability_approx(params: RefParameters, sigma: int, theta_d: str,
+                       theta_r: str) -> tuple[str, str, bool]:
+    n = C.create_string_buffer(_CAP)
+    e = C.create_string_buffer(_CAP)
+    b = lib().qref_probability_approx(
+        params.h, sigma, theta_d.encode(), theta_r.encode(), n, e, _CAP)
+    return n.value.decode(), e.value.decode(), bool(b)
+
+
+def probability_approx_quick(params: RefParameters, theta_d: str,
+                             theta_r: str) -> str:
+    n = C.create_string_buffer(_CAP)
+    lib().qref_probability_approx_quick(
+        params.h, theta_d.encode(), theta_r.encode(), n, _CAP)
+    return n.value.decode()
+
+
+def linear_probability(params: RefParameters, target: int, theta: str) -> str:
+    n = C.create_string_buffer(_CAP)
+    lib().qref_linear_probability(params.h, target, theta.encode(), n, _CAP)
+    return n.value.decode()
+
+
+def diagonal_probability_f_eta(params: RefDiagonalParameters, alpha_r: int,
+                               eta: int, theta_precision: int = 0) -> str:
+    n = C.create_string_buffer(_CAP)
+    lib().qref_diagonal_probability_f_eta(
+        params.h, str(alpha_r).encode(), eta, theta_precision, n, _CAP)
+    return n.value.decode()
+
+
+def heuristic_sigma(l: int) -> int:
+    """sigma = round((l + tau + 4 - 1.6515) / 2), tau = 11, in float32 as the
+    reference (src/distribution_slice_compute.cpp:149-158)."""
+    f = np.float32
+    v = (f(l) + f(11) + f(4) - f(1.6515)) / f(2.0)
+    # C round(): half away from zero.
+    return int(np.floor(float(v) + 0.5))
