@@ -1,0 +1,161 @@
+// hostconst.cpp -- see hostconst.hpp.
+#include "hostconst.hpp"
+
+#include <cmath>
+
+#include "bigint.hpp"
+
+namespace qb200 {
+
+namespace {
+
+const size_t kMpfrPrec = 192;  // PRECISION, src/common.h:13
+
+double bf_to_double(const BigFloat& v) {
+  if (v.mant.is_zero()) return 0.0;
+  const BigFloat r = v.rounded(53);
+  const uint64_t mant = r.mant.w.empty() ? 0 : r.mant.w[0];  // <= 2^53
+  return std::ldexp((double)mant, (int)r.exp);
+}
+
+// Exact a - b; returns magnitude, sets neg.
+BigFloat bf_sub(const BigFloat& a, const BigFloat& b, bool* neg) {
+  const long e = a.exp < b.exp ? a.exp : b.exp;
+  const BigUInt am = a.mant.shl((size_t)(a.exp - e));
+  const BigUInt bm = b.mant.shl((size_t)(b.exp - e));
+  if (BigUInt::cmp(am, bm) >= 0) {
+    *neg = false;
+    return BigFloat(BigUInt::sub(am, bm), e);
+  }
+  *neg = true;
+  return BigFloat(BigUInt::sub(bm, am), e);
+}
+
+BigFloat bf_from_double(double x) {  // x >= 0
+  if (x == 0.0) return BigFloat();
+  int e;
+  const double f = std::frexp(x, &e);  // x = f * 2^e, f in [0.5, 1)
+  const uint64_t mant = (uint64_t)std::ldexp(f, 53);
+  return BigFloat(BigUInt(mant), (long)e - 53);
+}
+
+// Non-negative big float -> double-double (hi = nearest double, lo = nearest
+// double of the remainder).
+DD bf_to_dd(const BigFloat& v, bool negative = false) {
+  DD r;
+  r.hi = bf_to_double(v);
+  bool neg = false;
+  const BigFloat rem = bf_sub(v, bf_from_double(r.hi), &neg);
+  r.lo = bf_to_double(rem);
+  if (neg) r.lo = -r.lo;
+  if (negative) {
+    r.hi = -r.hi;
+    r.lo = -r.lo;
+  }
+  return r;
+}
+
+// a / b as a 256-bit-accurate big float (for plain rational constants).
+BigFloat bf_ratio(const BigUInt& a, long ea, const BigUInt& b) {
+  return BigFloat::div_rounded(a, ea, b, 256);
+}
+
+}  // namespace
+
+int host_consts_compute(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d_be,
+                        size_t d_len, const uint8_t* r_be, size_t r_len, HostConsts* out) {
+  if (m == 0 || m > 65536 || l == 0 || l > 65536 || sigma > 65536) return -3;
+  const BigUInt d = BigUInt::from_bytes_be(d_be, d_len);
+  const BigUInt r = BigUInt::from_bytes_be(r_be, r_len);
+  if (d.is_zero() || r.is_zero()) return -1;
+  if (d.bit_length() > m || r.bit_length() > m) return -2;
+
+  out->m = m;
+  out->l = l;
+  out->sigma = sigma;
+
+  // K_sigma = ceil(rnd(rnd(-2^sigma * d) / r))        src/probability.cpp:165-170
+  //         = -floor(rnd(rnd(2^sigma d) / r))         (round-to-nearest is symmetric)
+  {
+    const BigFloat t = BigFloat(d, (long)sigma).rounded(kMpfrPrec);
+    const BigFloat q = BigFloat::div_rounded(t.mant, t.exp, r, kMpfrPrec);
+    const BigUInt k = q.floor_int();
+    out->kappa = bf_to_dd(BigFloat(k, -(long)sigma), /*negative=*/true);
+  }
+  // quick: theta_r * d / r with both operations rounded  src/probability.cpp:302-304
+  {
+    const BigFloat t = BigFloat(d, 0).rounded(kMpfrPrec);
+    const BigFloat q = BigFloat::div_rounded(t.mant, t.exp, r, kMpfrPrec);
+    out->kappa_q = bf_to_dd(q, /*negative=*/true);
+  }
+  // Q = rnd(2^(m+l) / r); C = ceil(Q), N = floor(Q)     src/probability.cpp:216-220,
+  //                                                     src/linear_probability.cpp:194-197
+  {
+    const BigFloat q = BigFloat::div_rounded(BigUInt(1), (long)(m + l), r, kMpfrPrec);
+    const BigUInt c = q.ceil_int();
+    const BigUInt n = q.floor_int();
+    out->c_over_L = bf_to_dd(BigFloat(c, -(long)l));
+    out->n_over_L = bf_to_dd(BigFloat(n, -(long)l));
+    // mpfr_add_ui(tmp, N, 1): rounded to 192 bits       src/linear_probability.cpp:200,217
+    const BigFloat n1 = BigFloat(BigUInt::add(n, BigUInt(1)), 0).rounded(kMpfrPrec);
+    out->n1_over_L = bf_to_dd(BigFloat(n1.mant, n1.exp - (long)l));
+  }
+  // beta = 2^(l+m) mod r (exact)                        src/linear_probability.cpp:190-192
+  {
+    BigUInt q, beta;
+    BigUInt::divmod(BigUInt::pow2((uint64_t)m + l), r, q, beta);
+    out->beta_m = bf_to_dd(BigFloat(beta, -(long)m));
+    out->rbeta_m = bf_to_dd(BigFloat(BigUInt::sub(r, beta), -(long)m));
+  }
+  out->r_m = bf_to_dd(BigFloat(r, -(long)m));
+  out->d_m = bf_to_dd(BigFloat(d, -(long)m));
+  out->rho = bf_to_dd(bf_ratio(BigUInt(1), (long)m, r));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// 2^(i/n) table. 256-bit fixed point; g = 2^(1/n) from the exponential series,
+// then table[i] = table[i-1] * g. The accumulated error is below n * 2^-254.
+// The reference forms the same grid by repeated 192-bit multiplication with
+// exp2(1/dimension) (src/distribution_slice_compute.cpp:110-113, 196-212).
+// ---------------------------------------------------------------------------
+namespace {
+
+const size_t kFix = 256;
+
+BigUInt fix_mul(const BigUInt& a, const BigUInt& b) { return BigUInt::mul(a, b).shr(kFix); }
+
+BigUInt fix_ln2() {
+  // floor(ln 2 * 2^320)
+  static const uint64_t limbs[5] = {0xe7b876206debac98ull, 0x8a0d175b8baafa2bull,
+                                    0x40f343267298b62dull, 0xc9e3b39803f2f6afull,
+                                    0xb17217f7d1cf79abull};
+  BigUInt v;
+  v.w.assign(limbs, limbs + 5);
+  return v.shr(320 - kFix);
+}
+
+}  // namespace
+
+void exp2_table_dd(uint32_t n, DD* table) {
+  BigUInt q, rem;
+  BigUInt::divmod(fix_ln2(), BigUInt(n), q, rem);  // t = ln2 / n
+  const BigUInt t = q;
+  const BigUInt one = BigUInt::pow2(kFix);
+  BigUInt g = one, term = one;
+  for (uint64_t k = 1; k < 200; k++) {
+    term = fix_mul(term, t);
+    BigUInt::divmod(term, BigUInt(k), q, rem);
+    term = q;
+    if (term.is_zero()) break;
+    g = BigUInt::add(g, term);
+  }
+  BigUInt cur = one;
+  for (uint32_t i = 0; i <= n; i++) {
+    if (i == n) cur = BigUInt::pow2(kFix + 1);  // exactly 2
+    table[i] = bf_to_dd(BigFloat(cur, -(long)kFix));
+    cur = fix_mul(cur, g);
+  }
+}
+
+}  // namespace qb200

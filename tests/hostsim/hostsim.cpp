@@ -1,0 +1,169 @@
+// tests/hostsim/hostsim.cpp -- TEST-ONLY CPU twin of the device functions.
+//
+// Compiles the __host__ __device__ bodies of qunundrum_b200/csrc (qmath.cuh,
+// integrands.cuh, slice_cells.cuh) and the host planner (plan.hpp) with g++ and
+// drives them with plain loops, so the mathematics of the kernels can be
+// checked against the oracle on a machine without a GPU (`pytest -m "not gpu"`).
+// It is NOT part of the product: libqunundrum_b200.so contains no such loops,
+// no CPU path, and nothing under qunundrum_b200/ references this file.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../qunundrum_b200/csrc/plan.hpp"
+
+using namespace qb200;
+
+static std::string g_err;
+
+static ParamsView view(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d, size_t dn,
+                       const uint8_t* r, size_t rn) {
+  ParamsView p;
+  p.m = m;
+  p.l = l;
+  p.sigma = sigma;
+  p.d_be = d;
+  p.d_len = dn;
+  p.r_be = r;
+  p.r_len = rn;
+  return p;
+}
+
+extern "C" {
+
+const char* hostsim_last_error() { return g_err.c_str(); }
+
+int hostsim_host_consts(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d, size_t dn,
+                        const uint8_t* r, size_t rn, double* out20) {
+  HostConsts h;
+  const int rc = host_consts_compute(m, l, sigma, d, dn, r, rn, &h);
+  if (rc) return rc;
+  const DD* v[10] = {&h.kappa, &h.kappa_q, &h.c_over_L, &h.n_over_L, &h.n1_over_L,
+                     &h.beta_m, &h.rbeta_m, &h.r_m, &h.d_m, &h.rho};
+  for (int i = 0; i < 10; i++) {
+    out20[2 * i] = v[i]->hi;
+    out20[2 * i + 1] = v[i]->lo;
+  }
+  return 0;
+}
+
+void hostsim_exp2_table(uint32_t n, double* out_hi_lo) {
+  std::vector<DD> t((size_t)n + 1);
+  exp2_table_dd(n, t.data());
+  for (uint32_t i = 0; i <= n; i++) {
+    out_hi_lo[2 * i] = t[i].hi;
+    out_hi_lo[2 * i + 1] = t[i].lo;
+  }
+}
+
+uint32_t hostsim_heuristic_sigma(uint32_t l) { return heuristic_sigma(l); }
+
+int hostsim_slice2d(uint32_t m, uint32_t l, const uint8_t* d, size_t dn, const uint8_t* r,
+                    size_t rn, int method, int richardson, uint32_t D, uint32_t n,
+                    const int32_t* a_d, const int32_t* a_r, double* cells,
+                    long double* total_probability, long double* total_error,
+                    uint32_t* flags) {
+  Plan plan;
+  const int rc = plan_2d(view(m, l, 0, d, dn, r, rn), method, richardson, D, n, a_d, a_r,
+                         &plan, &g_err);
+  if (rc) return rc;
+  const Geometry geo = make_geometry((int)D);
+  const int NP = table_points((int)D);
+  std::vector<AxisD> ta(plan.tabs_a.size() * (size_t)NP);
+  std::vector<AxisR> tb(plan.tabs_b.size() * (size_t)NP);
+  for (size_t t = 0; t < plan.tabs_a.size(); t++)
+    for (int i = 0; i < NP; i++)
+      axis_d_point(plan.c, make_dd(geo.gx[i].hi, geo.gx[i].lo), plan.tabs_a[t],
+                   &ta[t * NP + i]);
+  for (size_t t = 0; t < plan.tabs_b.size(); t++)
+    for (int i = 0; i < NP; i++)
+      axis_r_point(plan.c, make_dd(geo.gx[i].hi, geo.gx[i].lo), plan.tabs_b[t],
+                   &tb[t * NP + i]);
+  const int Dc = (int)D;
+  std::vector<double> fine((size_t)4 * Dc * Dc);
+  for (uint32_t s = 0; s < n; s++) {
+    const SliceDesc& sd = plan.slices[s];
+    double* out = cells + (size_t)s * Dc * Dc;
+    double M1[2] = {0, 0}, M2[2] = {0, 0};
+    bool bounded = true;
+    for (int pass = 0; pass <= plan.richardson; pass++) {
+      const int Dp = pass ? 2 * Dc : Dc;
+      const AxisD* td = &ta[(size_t)sd.tab_a * NP + pass_offset(Dc, pass)];
+      const AxisR* tr = &tb[(size_t)sd.tab_b * NP + pass_offset(Dc, pass)];
+      const double* gw = geo.gw.data() + width_offset(Dc, pass);
+      double* dst = pass ? fine.data() : out;
+      for (int J = 0; J < Dp; J++)
+        for (int I = 0; I < Dp; I++) {
+          double mass, m1, m2;
+          bool ok;
+          pass2d_cell(plan.c, td, tr, gw[I] * sd.scale_a, gw[J] * sd.scale_b, I, J,
+                      plan.with_error, &mass, &m1, &m2, &ok);
+          dst[I + (size_t)Dp * J] = mass;
+          M1[pass] += m1;
+          M2[pass] += m2;
+          if (pass == 0) bounded = bounded && ok;
+        }
+    }
+    long double tp = 0;
+    if (plan.richardson) {
+      for (int i = 0; i < Dc; i++)
+        for (int j = 0; j < Dc; j++) {
+          const size_t F = (size_t)2 * Dc;
+          const double f = fine[F * (2 * j) + 2 * i] + fine[F * (2 * j) + 2 * i + 1] +
+                           fine[F * (2 * j + 1) + 2 * i] + fine[F * (2 * j + 1) + 2 * i + 1];
+          out[(size_t)Dc * j + i] = 2.0 * f - out[(size_t)Dc * j + i];
+          tp += out[(size_t)Dc * j + i];
+        }
+      total_error[s] =
+          total_error_2d(plan, s, 2.0 * M1[1] - M1[0], 2.0 * M2[1] - M2[0]);
+    } else {
+      for (size_t i = 0; i < (size_t)Dc * Dc; i++) tp += out[i];
+      total_error[s] = total_error_2d(plan, s, M1[0], M2[0]);
+    }
+    total_probability[s] = tp;
+    flags[s] = kFlagMethodSimpson | (plan.richardson ? kFlagMethodRichardson : 0u) |
+               ((plan.with_error && !bounded) ? kFlagErrorBoundWarning : 0u);
+  }
+  return 0;
+}
+
+int hostsim_slice1d(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d, size_t dn,
+                    const uint8_t* r, size_t rn, int kind, int richardson, uint32_t D,
+                    uint32_t n, const int32_t* a, const int32_t* eta, double* cells,
+                    long double* total_probability, uint32_t* flags) {
+  Plan plan;
+  const int rc = plan_1d(view(m, l, sigma, d, dn, r, rn), kind, richardson, D, n, a, eta,
+                         &plan, &g_err);
+  if (rc) return rc;
+  const Geometry geo = make_geometry((int)D);
+  const int NP = table_points((int)D);
+  const int Dc = (int)D;
+  std::vector<double> v((size_t)NP);
+  for (uint32_t s = 0; s < n; s++) {
+    const SliceDesc& sd = plan.slices[s];
+    for (int i = 0; i < NP; i++)
+      v[i] = value_1d(plan.c, kind, make_dd(geo.gx[i].hi, geo.gx[i].lo),
+                      plan.tabs_a[sd.tab_a], sd.eta_shift);
+    double* out = cells + (size_t)s * Dc;
+    long double tp = 0;
+    for (int I = 0; I < Dc; I++) {
+      const double coarse = pass1d_cell(v.data(), geo.gw[I] * sd.scale_a, I);
+      double res = coarse;
+      if (plan.richardson) {
+        const double* vf = v.data() + pass_offset(Dc, 1);
+        const double* wf = geo.gw.data() + width_offset(Dc, 1);
+        const double f = pass1d_cell(vf, wf[2 * I] * sd.scale_a, 2 * I) +
+                         pass1d_cell(vf, wf[2 * I + 1] * sd.scale_a, 2 * I + 1);
+        res = 2.0 * f - coarse;
+      }
+      out[I] = res;
+      tp += res;
+    }
+    total_probability[s] = tp;
+    flags[s] = kFlagMethodSimpson | (plan.richardson ? kFlagMethodRichardson : 0u);
+  }
+  return 0;
+}
+
+}  // extern "C"
