@@ -1,0 +1,172 @@
+/* qunundrum_b200.h -- C ABI of the B200 slice integrators.
+ *
+ * Drop-in boundary for the slice-integration hot path of ekera/qunundrum.
+ * Every entry point below replaces (a batch of calls to) one of the
+ * reference's six C++ entry points; the reference-side forwarding TU a
+ * maintainer adds is shown in INTEGRATION.md and built in
+ * qunundrum_b200/csrc/dropin.cpp.
+ *
+ *   entry point here                         replaces (reference file:line)
+ *   qb200_slice2d_compute                    distribution_slice_compute            src/distribution_slice_compute.cpp:38
+ *                                            distribution_slice_compute_richardson src/distribution_slice_compute_richardson.cpp:17
+ *   qb200_slice1d_compute (LINEAR_D / _R)    linear_distribution_slice_compute            src/linear_distribution_slice_compute.cpp:30
+ *                                            linear_distribution_slice_compute_richardson src/linear_distribution_slice_compute_richardson.cpp:17
+ *   qb200_slice1d_compute (DIAGONAL)         diagonal_distribution_slice_compute            src/diagonal_distribution_slice_compute.cpp:30
+ *                                            diagonal_distribution_slice_compute_richardson src/diagonal_distribution_slice_compute_richardson.cpp:17
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all buffers are caller-owned;
+ *  - d and r (Parameters::d, Parameters::r, src/parameters.h:60-72) travel as
+ *    big-endian magnitude bytes, i.e. what mpz_export(buf, &n, 1, 1, 1, 0, z)
+ *    writes;
+ *  - cells are IEEE doubles in the reference's own index order
+ *    (2D: index = i_d + dimension * j_r, src/distribution_slice_compute.cpp:401);
+ *    the binding widens them to the long double norm_matrix / norm_vector;
+ *  - flags are the bits the reference ORs into slice->flags after clearing
+ *    SLICE_FLAGS_MASK_METHOD (src/common.h:226-257): SIMPSON, RICHARDSON and the
+ *    ERROR_BOUND_WARNING bit;
+ *  - every function returns 0 on success and a negative code on failure, with
+ *    qb200_last_error() giving the message; the reference convention (errors
+ *    are fatal, critical() -> exit, src/errors.c) is applied by the binding;
+ *  - there is no CPU path: without a CUDA device qb200_create() fails.
+ */
+#ifndef QUNUNDRUM_B200_H
+#define QUNUNDRUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_VERSION 1
+
+/* Distribution_Slice_Compute_Method, src/distribution_slice.h:31-78. */
+#define QB200_METHOD_HEURISTIC_SIGMA 0
+#define QB200_METHOD_OPTIMAL_LOCAL_SIGMA 1 /* rejected: not implemented */
+#define QB200_METHOD_QUICK 2
+
+/* One-dimensional integrands. LINEAR_D / LINEAR_R are
+ * Linear_Distribution_Slice_Compute_Target, src/linear_distribution_slice.h:30-40. */
+#define QB200_KIND_LINEAR_D 0
+#define QB200_KIND_LINEAR_R 1
+#define QB200_KIND_DIAGONAL 2
+
+/* Slice flag bits, src/common.h:226-257. */
+#define QB200_FLAG_ERROR_BOUND_WARNING 0x00000001u
+#define QB200_FLAG_METHOD_SIMPSON 0x00020000u
+#define QB200_FLAG_METHOD_RICHARDSON 0x00080000u
+
+/* The fields of Parameters (src/parameters.h:33-114) / Diagonal_Parameters
+ * (src/diagonal_parameters.h:32-106) that the integrators read. */
+typedef struct {
+  uint32_t m;
+  uint32_t l;
+  uint32_t sigma; /* Diagonal_Parameters::sigma; ignored otherwise */
+  const uint8_t *d_be;
+  size_t d_len;
+  const uint8_t *r_be;
+  size_t r_len;
+} qb200_params;
+
+typedef struct qb200_context qb200_context;
+typedef struct qb200_plan qb200_plan;
+
+int qb200_version(void);
+
+/* Message of the last failure on this thread (never NULL). */
+const char *qb200_last_error(void);
+
+/* Number of CUDA devices visible (0 if none / no driver). */
+int qb200_device_count(void);
+
+/* One context per MPI worker rank; device = (rank - 1) mod qb200_device_count(). */
+int qb200_create(int device, qb200_context **ctx);
+void qb200_destroy(qb200_context *ctx);
+
+/* Kernel launches issued by this context so far (for accounting). */
+uint64_t qb200_launch_count(const qb200_context *ctx);
+
+/* Pinned host memory for result buffers (optional; plain malloc works too). */
+void *qb200_host_alloc(size_t bytes);
+void qb200_host_free(void *p);
+
+/* ---- synchronous, host buffers in, host buffers out ----------------------- */
+
+/* n two-dimensional slices of dimension `dimension` with coordinates
+ * (min_log_alpha_d[i], min_log_alpha_r[i]).
+ *   cells             n * dimension^2 doubles
+ *   total_probability n long doubles (sum of the slice's cells)
+ *   total_error       n long doubles (0 for the quick method)
+ *   flags             n words
+ * richardson = 0: distribution_slice_compute; 1: ..._compute_richardson. */
+int qb200_slice2d_compute(qb200_context *ctx, const qb200_params *params, int method,
+                          int richardson, uint32_t dimension, uint32_t n,
+                          const int32_t *min_log_alpha_d, const int32_t *min_log_alpha_r,
+                          double *cells, long double *total_probability,
+                          long double *total_error, uint32_t *flags);
+
+/* n one-dimensional slices. eta is read for QB200_KIND_DIAGONAL only (may be
+ * NULL otherwise). cells: n * dimension doubles. */
+int qb200_slice1d_compute(qb200_context *ctx, const qb200_params *params, int kind,
+                          int richardson, uint32_t dimension, uint32_t n,
+                          const int32_t *min_log_alpha, const int32_t *eta, double *cells,
+                          long double *total_probability, uint32_t *flags);
+
+/* ---- planned, device-resident execution ----------------------------------- */
+
+/* A plan holds the batch's constants, coordinates and axis-table descriptors
+ * in device memory. qb200_plan_run() enqueues all kernels of one pass over the
+ * batch on `stream` (a cudaStream_t, NULL = the context's own stream) and
+ * returns without synchronising:
+ *   d_cells    device, n * dimension^(1|2) doubles
+ *   d_summary  device, n * QB200_SUMMARY_STRIDE doubles (see below)
+ * qb200_plan_finish() turns a host copy of the summary into the reference's
+ * per-slice scalars. */
+#define QB200_SUMMARY_STRIDE 8 /* tp_hi, tp_lo, m1, m2, bounded, 0, 0, 0 */
+
+int qb200_plan2d_create(qb200_context *ctx, const qb200_params *params, int method,
+                        int richardson, uint32_t dimension, uint32_t n,
+                        const int32_t *min_log_alpha_d, const int32_t *min_log_alpha_r,
+                        qb200_plan **plan);
+int qb200_plan1d_create(qb200_context *ctx, const qb200_params *params, int kind,
+                        int richardson, uint32_t dimension, uint32_t n,
+                        const int32_t *min_log_alpha, const int32_t *eta,
+                        qb200_plan **plan);
+void qb200_plan_destroy(qb200_plan *plan);
+
+/* Number of cells one run produces, and kernel launches per run. */
+uint64_t qb200_plan_cells(const qb200_plan *plan);
+uint32_t qb200_plan_launches(const qb200_plan *plan);
+
+/* algo: 0 = automatic, 1 = plain kernels (one thread per cell), 2 = fused
+ * kernel (fails if the plan does not meet its preconditions). */
+int qb200_plan_set_algorithm(qb200_plan *plan, int algo);
+int qb200_plan_algorithm(const qb200_plan *plan);
+
+int qb200_plan_run(qb200_plan *plan, void *stream, double *d_cells, double *d_summary);
+int qb200_plan_finish(const qb200_plan *plan, const double *h_summary,
+                      long double *total_probability, long double *total_error,
+                      uint32_t *flags);
+
+/* ---- introspection (host logic; usable without a GPU) --------------------- */
+
+/* sigma chosen by QB200_METHOD_HEURISTIC_SIGMA for this l
+ * (src/distribution_slice_compute.cpp:149-158). */
+uint32_t qb200_heuristic_sigma(uint32_t l);
+
+/* The double-double constants derived from (m, l, sigma, d, r), as 10 (hi, lo)
+ * pairs: kappa, kappa_quick, C/L, N/L, (N+1)/L, beta/2^m, (r-beta)/2^m, r/2^m,
+ * d/2^m, 2^m/r. */
+int qb200_host_constants(const qb200_params *params, double *out20);
+
+/* Measured FP64 FMA throughput of the device (flop/s, FMA = 2), from a
+ * register-resident DFMA loop; used as the roofline denominator. */
+int qb200_measure_fp64_peak(qb200_context *ctx, double *flops_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QUNUNDRUM_B200_H */

@@ -1,0 +1,42 @@
+"""qunundrum_b200 -- B200-native slice integrators behind the reference's interface.
+
+The package is a thin host-side mirror (same names, argument meaning and error
+behaviour) of the six entry points of ekera/qunundrum's slice-integration path,
+over the C ABI declared in include/qunundrum_b200.h and implemented by
+hand-written sm_100a CUDA kernels in qunundrum_b200/csrc.
+
+There is NO CPU path: importing works anywhere (so that the host logic can be
+unit-tested), but every compute call needs libqunundrum_b200.so and a CUDA
+device and raises otherwise.
+"""
+from .host import (  # noqa: F401
+    CriticalError,
+    Context,
+    Diagonal_Distribution_Slice,
+    Diagonal_Parameters,
+    Distribution_Slice,
+    Linear_Distribution_Slice,
+    Parameters,
+    DISTRIBUTION_SLICE_COMPUTE_METHOD_HEURISTIC_SIGMA,
+    DISTRIBUTION_SLICE_COMPUTE_METHOD_OPTIMAL_LOCAL_SIGMA,
+    DISTRIBUTION_SLICE_COMPUTE_METHOD_QUICK,
+    LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_D,
+    LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_R,
+    SLICE_FLAGS_ERROR_BOUND_WARNING,
+    SLICE_FLAGS_METHOD_RICHARDSON,
+    SLICE_FLAGS_METHOD_SIMPSON,
+    SLICE_FLAGS_MASK_METHOD,
+    default_context,
+    diagonal_distribution_slice_compute,
+    diagonal_distribution_slice_compute_richardson,
+    distribution_slice_compute,
+    distribution_slice_compute_richardson,
+    heuristic_sigma,
+    host_constants,
+    lib,
+    lib_path,
+    linear_distribution_slice_compute,
+    linear_distribution_slice_compute_richardson,
+)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

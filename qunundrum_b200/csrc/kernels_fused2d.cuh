@@ -1,0 +1,620 @@
+// kernels_fused2d.cuh -- the fused two-dimensional Richardson slice kernel.
+//
+// Replaces, for one batch of slices, what the reference does in
+// distribution_slice_compute_richardson (src/distribution_slice_compute_richardson.cpp:17-73):
+// two calls of distribution_slice_compute (src/distribution_slice_compute.cpp:38-453)
+// at dimensions D and 2 D, each a (2 D' + 1)^2 grid of probability_approx
+// (src/probability.cpp:150-288) evaluations followed by 3 x 3 Simpson sums, and
+// the combination 2 * (four fine cells) - coarse cell.
+//
+// Work decomposition (B200: 148 SMs x 4 sub-partitions, FP64 pipe bound):
+//   * a WARP owns a tile of 32 x 32 coarse cells of one slice; lane <-> coarse
+//     row I (alpha_d, the fast index of norm_matrix, so stores coalesce), and the
+//     warp marches over the tile's alpha_r columns;
+//   * per lane, the alpha_d-only quantities of its five abscissae (four fine
+//     points of the cell and the coarse mid point) live in registers; the
+//     alpha_r-only quantities of the current column (including the whole second
+//     factor T2 of the approximation, folded with the Simpson weight) are one
+//     warp-uniform 80-byte record read through L1;
+//   * sin(pi u), u = x_d + kappa x_r, is NOT evaluated per point: with
+//     sin/cos(pi x_d) per row and sin/cos(pi kappa x_r) per column (double-double
+//     reduced, in the axis tables) it is one multiply and one FMA,
+//     sin(pi u) = sin(pi x_d) cos(pi y) + cos(pi x_d) sin(pi y);
+//     near the ridge (|u| < 1/16), where that would lose relative accuracy, the
+//     point falls back to a polynomial in u^2 (u itself is exact there);
+//   * 1 / u^2 is MUFU.RCP64H plus one cubic Newton step (3 DFMA);
+//   * every integrand value is computed once: the fine-grid row shared by
+//     vertically adjacent cells comes from the neighbouring lane by shuffle, the
+//     column shared by horizontally adjacent cells is applied twice with two
+//     weights, and coarse main points reuse the fine values. 19 evaluations per
+//     output cell instead of the reference's 20.09;
+//   * the only redundancy is the one halo row below lane 31, evaluated in a
+//     lanes<->columns pre-pass (1 % of the tile's work), which keeps warps fully
+//     independent: no __syncthreads, no inter-warp traffic.
+//
+// Outputs per tile: 32 x 32 cells (coalesced 256-byte row segments) and a
+// 4-double partial (mass, error moments, bound flag) summed per slice in a
+// fixed order by k_fused_final => bitwise reproducible results.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels_plain.cuh"
+#include "plan.hpp"
+
+namespace qb200 {
+
+#define QB_FUSED_REC 10         // doubles per column record
+#define QB_FUSED_PART_STRIDE 4  // doubles per tile partial
+#define QB_FUSED_WARPS 4
+
+struct FusedItem {  // kept for ABI stability of qb200_plan; tiles are indexed arithmetically
+  int unused;
+};
+
+struct FusedConst {
+  double c1, c2, c3;   // 1/sinc^2(z) = 1 + c1 w + c2 w^2 + c3 w^3, w = u^2, z = pi u / Lambda
+  double cs, e0s, r_m; // error bound pieces (src/probability.cpp:252-281)
+  int D, nb, NP, ncol; // nb = D / 32, ncol = 5 D + 1 records per alpha_r table
+  unsigned n_tiles;
+};
+
+struct FusedPlan2D {
+  std::vector<FusedItem> items;  // unused (empty)
+  FusedConst k;
+  int mode = 0;        // 0: Lambda sin(pi u / Lambda) == pi u; 1: series correction
+  bool has_err = false, has_m2 = false, has_bound = false;
+  std::vector<unsigned char> host_unbounded;  // per slice, when the bound is decided on the host
+  size_t cols_bytes = 0;
+  void* d_cols = nullptr;   // column records, owned
+  ~FusedPlan2D() {
+    if (d_cols) cudaFree(d_cols);
+  }
+};
+
+// ---- column records ---------------------------------------------------------
+// For alpha_r table t and record R = 5 J + k:
+//   k = 0      fine main column h = 4 J  (also coarse main column)
+//   k = 1,2,3  fine columns h = 4 J + k
+//   k = 4      coarse mid column of cell J
+//   R = 5 D    the last main column h = 4 D
+// Fields: yh, yl, sr, cr, wF, wF2, wC, wC2, b, t2p.
+//   wF  : fine Simpson weight of the column within cell J   (x T2 / pi^2)
+//   wF2 : fine weight of the column as LAST column of cell J - 1 (k = 0 only)
+//   wC / wC2 : the same for the coarse pass
+__global__ void k_fused_cols(int D, int m, const TabDesc* __restrict__ desc_b,
+                             const AxisR* __restrict__ tab_b, const double* __restrict__ gw,
+                             double* __restrict__ cols) {
+  const int R = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncol = 5 * D + 1;
+  if (R >= ncol) return;
+  const int t = blockIdx.y;
+  const int NP = table_points(D);
+  const AxisR* tc = tab_b + (size_t)t * NP;       // coarse interleaved
+  const AxisR* tf = tc + pass_offset(D, 1);       // fine interleaved
+  const double* wc = gw;                          // coarse widths [D]
+  const double* wf = gw + width_offset(D, 1);     // fine widths [2 D]
+  const double sb = pow2i(desc_b[t].k_abs - m) / 6.0;
+  const double inv_pi2 = 0.101321183642337771443879463209;  // 1 / pi^2
+  const int J = R / 5, k = R % 5;
+  AxisR a;
+  double wF = 0.0, wF2 = 0.0, wC = 0.0, wC2 = 0.0;
+  if (k == 4) {
+    a = tc[2 * J + 1];
+    wC = 4.0 * wc[J];
+  } else {
+    a = tf[4 * J + k];
+    if (k == 0) {
+      if (J < D) {
+        wF = wf[2 * J];
+        wC = wc[J];
+      }
+      if (J >= 1) {
+        wF2 = wf[2 * J - 1];
+        wC2 = wc[J - 1];
+      }
+    } else if (k == 1) {
+      wF = 4.0 * wf[2 * J];
+    } else if (k == 2) {
+      wF = wf[2 * J] + wf[2 * J + 1];
+    } else {
+      wF = 4.0 * wf[2 * J + 1];
+    }
+  }
+  const double t2p = a.t2 * inv_pi2;
+  const double f = sb * t2p;
+  double* o = cols + ((size_t)t * ncol + R) * QB_FUSED_REC;
+  o[0] = a.yh;
+  o[1] = a.yl;
+  o[2] = a.sr;
+  o[3] = a.cr;
+  o[4] = wF * f;
+  o[5] = wF2 * f;
+  o[6] = wC * f;
+  o[7] = wC2 * f;
+  o[8] = a.b;
+  o[9] = t2p;
+}
+
+// ---- device helpers ---------------------------------------------------------
+struct ColRec {
+  double yh, yl, sr, cr, wF, wF2, wC, wC2, b, t2p;
+};
+
+__device__ __forceinline__ ColRec load_col(const double* __restrict__ p) {
+  const double2 a = __ldg((const double2*)p);
+  const double2 b = __ldg((const double2*)p + 1);
+  const double2 c = __ldg((const double2*)p + 2);
+  const double2 d = __ldg((const double2*)p + 3);
+  const double2 e = __ldg((const double2*)p + 4);
+  ColRec r;
+  r.yh = a.x; r.yl = a.y; r.sr = b.x; r.cr = b.y;
+  r.wF = c.x; r.wF2 = c.y; r.wC = d.x; r.wC2 = d.y;
+  r.b = e.x; r.t2p = e.y;
+  return r;
+}
+
+struct RowReg {
+  double xh, xl, sd, cd;
+};
+
+__device__ __forceinline__ RowReg load_row(const AxisD* __restrict__ p) {
+  const double2 a = __ldg((const double2*)p);
+  const double2 b = __ldg((const double2*)p + 1);
+  RowReg r;
+  r.xh = a.x; r.xl = a.y; r.sd = b.x; r.cd = b.y;
+  return r;
+}
+
+__device__ __forceinline__ double rcp_seed(double w) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+  return r;
+}
+
+// pi^2 * T1 at one point: (sin(pi u) / u)^2 [* 1 / sinc^2(pi u / Lambda)].
+template <int MODE>
+__device__ __forceinline__ double eval_t1(const RowReg& r, const ColRec& c, const FusedConst& k) {
+  const double S = fma(r.sd, c.cr, r.cd * c.sr);
+  const double u = (r.xh + c.yh) + (r.xl + c.yl);
+  const double w = u * u;
+  double T;
+  if ((__double2hiint(u) & 0x7fffffff) < 0x3FB00000) {  // |u| < 1/16
+    // pi sinc(pi u) = sum (-1)^k pi^(2k+1) / (2k+1)! w^k
+    double p = 4.6630280576761256442e-4;
+    p = fma(p, w, -7.3704309457143507773e-3);
+    p = fma(p, w, 8.2145886611128228799e-2);
+    p = fma(p, w, -5.9926452932079207689e-1);
+    p = fma(p, w, 2.5501640398773454439);
+    p = fma(p, w, -5.1677127800499700292);
+    p = fma(p, w, 3.1415926535897932385);
+    T = p * p;
+  } else {
+    const double r0 = rcp_seed(w);
+    const double e = fma(-w, r0, 1.0);
+    const double rr = fma(r0, fma(e, e, e), r0);
+    T = (S * S) * rr;
+  }
+  if (MODE == 1) T *= fma(w, fma(w, fma(w, k.c3, k.c2), k.c1), 1.0);
+  return T;
+}
+
+struct FusedArgs {
+  FusedConst k;
+  const DevSlice* slices;
+  const AxisD* tab_a;
+  const double* cols;
+  const double* gw;
+  double* out;
+  double* part;
+};
+
+template <int MODE, bool HAS_ERR, bool HAS_M2, bool HAS_BOUND>
+__global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a) {
+  __shared__ double s_halo[QB_FUSED_WARPS][2][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const unsigned tile = blockIdx.x * QB_FUSED_WARPS + warp;
+  if (tile >= a.k.n_tiles) return;
+  const FusedConst& k = a.k;
+  const int D = k.D, nb = k.nb;
+  const unsigned per_slice = (unsigned)(nb * nb);
+  const unsigned sidx = tile / per_slice;
+  const unsigned rem = tile - sidx * per_slice;
+  const int jc = (int)(rem / (unsigned)nb), ib = (int)(rem - (unsigned)jc * nb);
+  const int I0 = ib * 32, J0 = jc * 32, I = I0 + lane;
+  const DevSlice s = a.slices[sidx];
+  const AxisD* tdc = a.tab_a + (size_t)s.tab_a * k.NP;
+  const AxisD* tdf = tdc + (2 * D + 1);
+  const double* cols = a.cols + (size_t)s.tab_b * k.ncol * QB_FUSED_REC;
+  const double* gwc = a.gw;
+  const double* gwf = a.gw + D;
+
+  // alpha_d rows of this lane: fine h = 4 I .. 4 I + 3 and the coarse mid point.
+  const RowReg r0 = load_row(tdf + 4 * I);
+  const RowReg r1 = load_row(tdf + 4 * I + 1);
+  const RowReg r2 = load_row(tdf + 4 * I + 2);
+  const RowReg r3 = load_row(tdf + 4 * I + 3);
+  const RowReg rc = load_row(tdc + 2 * I + 1);
+  const double fd = s.scale_a * k.r_m / 6.0;
+  const double d0 = __ldg(gwf + 2 * I), d1 = __ldg(gwf + 2 * I + 1), dC = __ldg(gwc + I);
+  // fine weights of rows p = 0..4 and coarse weights of (c0, cm, c2)
+  const double WF0 = fd * d0, WF1 = 4.0 * WF0, WF3 = 4.0 * fd * d1, WF4 = fd * d1;
+  const double WF2 = WF0 + WF4;
+  const double WC0 = fd * dC, WC1 = 4.0 * WC0;
+
+  double err1 = 0.0, err2 = 0.0;  // Richardson-combined error moments of this lane
+  int ok = 1;
+
+  // ---- halo row h = 4 (I0 + 32): lanes <-> columns pre-pass -------------------
+  {
+    const RowReg rh = load_row(tdf + 4 * (I0 + 32));
+    const int J = J0 + lane;
+    const double* cp = cols + (size_t)(5 * J) * QB_FUSED_REC;
+    const ColRec c0 = load_col(cp);
+    const ColRec c1 = load_col(cp + QB_FUSED_REC);
+    const ColRec c2 = load_col(cp + 2 * QB_FUSED_REC);
+    const ColRec c3 = load_col(cp + 3 * QB_FUSED_REC);
+    const ColRec cm = load_col(cp + 4 * QB_FUSED_REC);
+    const ColRec c4 = load_col(cp + 5 * QB_FUSED_REC);
+    const double T0 = eval_t1<MODE>(rh, c0, k), T1 = eval_t1<MODE>(rh, c1, k);
+    const double T2 = eval_t1<MODE>(rh, c2, k), T3 = eval_t1<MODE>(rh, c3, k);
+    const double Tm = eval_t1<MODE>(rh, cm, k), T4 = eval_t1<MODE>(rh, c4, k);
+    const double HF = fma(c4.wF2, T4, fma(c3.wF, T3, fma(c2.wF, T2, fma(c1.wF, T1, c0.wF * T0))));
+    const double HC = fma(c4.wC2, T4, fma(cm.wC, Tm, c0.wC * T0));
+    s_halo[warp][0][lane] = HF;
+    s_halo[warp][1][lane] = HC;
+    if (HAS_ERR) {
+      // weights of this row as p = 4 / c2 of lane 31's cell
+      const double wf4 = fd * __ldg(gwf + 2 * (I0 + 31) + 1);
+      const double wc2 = fd * __ldg(gwc + I0 + 31);
+      const double ah = fabs(rh.xh);
+      const double HFB = fma(c4.wF2 * c4.b, T4,
+                             fma(c3.wF * c3.b, T3,
+                                 fma(c2.wF * c2.b, T2, fma(c1.wF * c1.b, T1, (c0.wF * c0.b) * T0))));
+      const double HCB = fma(c4.wC2 * c4.b, T4, fma(cm.wC * cm.b, Tm, (c0.wC * c0.b) * T0));
+      err1 = 2.0 * wf4 * fma(ah, HF, HFB) - wc2 * fma(ah, HC, HCB);
+      if (HAS_M2) {
+        const double HFBB =
+            fma(c4.wF2 * c4.b * c4.b, T4,
+                fma(c3.wF * c3.b * c3.b, T3,
+                    fma(c2.wF * c2.b * c2.b, T2,
+                        fma(c1.wF * c1.b * c1.b, T1, (c0.wF * c0.b * c0.b) * T0))));
+        const double HCBB =
+            fma(c4.wC2 * c4.b * c4.b, T4, fma(cm.wC * cm.b * cm.b, Tm, (c0.wC * c0.b * c0.b) * T0));
+        err2 = 2.0 * wf4 * fma(ah * ah, HF, fma(2.0 * ah, HFB, HFBB)) -
+               wc2 * fma(ah * ah, HC, fma(2.0 * ah, HCB, HCBB));
+      }
+    }
+    if (HAS_BOUND) {
+      const double ah = fabs(rh.xh);
+      const double Tt[3] = {T0, Tm, T4};
+      const double bb[3] = {c0.b, cm.b, c4.b};
+      const double tt[3] = {c0.t2p, cm.t2p, c4.t2p};
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const double sv = k.cs * (ah + bb[q]);
+        const double room = QB_ERROR_BOUND - sv * (2.0 + sv);
+        ok &= (room >= 0.0) && (k.e0s <= room * (Tt[q] * tt[q]) * k.r_m);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- main march over the tile's columns --------------------------------------
+  // composite alpha_d weights of rows 0 and c0 for the error totals: the row is
+  // also row 4 / c2 of the lane above (the tile above handles lane 0's share).
+  const double a0 = fabs(r0.xh), a1 = fabs(r1.xh), a2 = fabs(r2.xh), a3 = fabs(r3.xh);
+  const double am = fabs(rc.xh);
+  double EW0 = WF0, EC0 = WC0;
+  if (HAS_ERR && lane > 0) {
+    EW0 += fd * __ldg(gwf + 2 * I - 1);
+    EC0 += fd * __ldg(gwc + I - 1);
+  }
+
+  double sF0, sF1, sF2, sF3, sC0, sCm;                 // per-cell row sums
+  double tF0 = 0, tF1 = 0, tF2 = 0, tF3 = 0, tC0 = 0, tCm = 0;  // tile totals of the row sums
+  double bF0 = 0, bF1 = 0, bF2 = 0, bF3 = 0, bC0 = 0, bCm = 0;  // ... weighted by b
+  double qF0 = 0, qF1 = 0, qF2 = 0, qF3 = 0, qC0 = 0, qCm = 0;  // ... weighted by b^2
+  double tp = 0.0;
+
+#define QB_BOUND_TEST(T_, arow_, col_)                                              \
+  if (HAS_BOUND) {                                                                  \
+    const double sv_ = k.cs * ((arow_) + (col_).b);                                 \
+    const double room_ = QB_ERROR_BOUND - sv_ * (2.0 + sv_);                        \
+    ok &= (room_ >= 0.0) && (k.e0s <= room_ * ((T_) * (col_).t2p) * k.r_m);         \
+  }
+
+  const double* cp = cols + (size_t)(5 * J0) * QB_FUSED_REC;
+  {
+    // first column of the tile: starts cell J0
+    const ColRec c = load_col(cp);
+    const double T0 = eval_t1<MODE>(r0, c, k), T1 = eval_t1<MODE>(r1, c, k);
+    const double T2 = eval_t1<MODE>(r2, c, k), T3 = eval_t1<MODE>(r3, c, k);
+    const double Tm = eval_t1<MODE>(rc, c, k);
+    sF0 = c.wF * T0; sF1 = c.wF * T1; sF2 = c.wF * T2; sF3 = c.wF * T3;
+    sC0 = c.wC * T0; sCm = c.wC * Tm;
+    if (HAS_ERR) {
+      const double wb = c.wF * c.b, wcb = c.wC * c.b;
+      bF0 = wb * T0; bF1 = wb * T1; bF2 = wb * T2; bF3 = wb * T3;
+      bC0 = wcb * T0; bCm = wcb * Tm;
+      if (HAS_M2) {
+        const double wbb = wb * c.b, wcbb = wcb * c.b;
+        qF0 = wbb * T0; qF1 = wbb * T1; qF2 = wbb * T2; qF3 = wbb * T3;
+        qC0 = wcbb * T0; qCm = wcbb * Tm;
+      }
+    }
+    QB_BOUND_TEST(T0, a0, c)
+    QB_BOUND_TEST(Tm, am, c)
+  }
+  double* outp = a.out + (size_t)sidx * D * D + (size_t)J0 * D + I;
+
+  for (int jj = 0; jj < 32; jj++) {
+    cp += QB_FUSED_REC;
+#pragma unroll
+    for (int q = 1; q <= 3; q++) {  // fine interior columns
+      const ColRec c = load_col(cp);
+      cp += QB_FUSED_REC;
+      const double T0 = eval_t1<MODE>(r0, c, k), T1 = eval_t1<MODE>(r1, c, k);
+      const double T2 = eval_t1<MODE>(r2, c, k), T3 = eval_t1<MODE>(r3, c, k);
+      sF0 = fma(c.wF, T0, sF0); sF1 = fma(c.wF, T1, sF1);
+      sF2 = fma(c.wF, T2, sF2); sF3 = fma(c.wF, T3, sF3);
+      if (HAS_ERR) {
+        const double wb = c.wF * c.b;
+        bF0 = fma(wb, T0, bF0); bF1 = fma(wb, T1, bF1);
+        bF2 = fma(wb, T2, bF2); bF3 = fma(wb, T3, bF3);
+        if (HAS_M2) {
+          const double wbb = wb * c.b;
+          qF0 = fma(wbb, T0, qF0); qF1 = fma(wbb, T1, qF1);
+          qF2 = fma(wbb, T2, qF2); qF3 = fma(wbb, T3, qF3);
+        }
+      }
+    }
+    {  // coarse mid column
+      const ColRec c = load_col(cp);
+      cp += QB_FUSED_REC;
+      const double T0 = eval_t1<MODE>(r0, c, k), Tm = eval_t1<MODE>(rc, c, k);
+      sC0 = fma(c.wC, T0, sC0); sCm = fma(c.wC, Tm, sCm);
+      if (HAS_ERR) {
+        const double wcb = c.wC * c.b;
+        bC0 = fma(wcb, T0, bC0); bCm = fma(wcb, Tm, bCm);
+        if (HAS_M2) {
+          const double wcbb = wcb * c.b;
+          qC0 = fma(wcbb, T0, qC0); qCm = fma(wcbb, Tm, qCm);
+        }
+      }
+      QB_BOUND_TEST(T0, a0, c)
+      QB_BOUND_TEST(Tm, am, c)
+    }
+    {  // boundary column: closes cell J0 + jj, opens the next one
+      const ColRec c = load_col(cp);
+      const double T0 = eval_t1<MODE>(r0, c, k), T1 = eval_t1<MODE>(r1, c, k);
+      const double T2 = eval_t1<MODE>(r2, c, k), T3 = eval_t1<MODE>(r3, c, k);
+      const double Tm = eval_t1<MODE>(rc, c, k);
+      sF0 = fma(c.wF2, T0, sF0); sF1 = fma(c.wF2, T1, sF1);
+      sF2 = fma(c.wF2, T2, sF2); sF3 = fma(c.wF2, T3, sF3);
+      sC0 = fma(c.wC2, T0, sC0); sCm = fma(c.wC2, Tm, sCm);
+      QB_BOUND_TEST(T0, a0, c)
+      QB_BOUND_TEST(Tm, am, c)
+      // rows 4 / c2 of this lane are rows 0 / c0 of the lane below
+      double nF = __shfl_down_sync(0xffffffffu, sF0, 1);
+      double nC = __shfl_down_sync(0xffffffffu, sC0, 1);
+      if (lane == 31) {
+        nF = s_halo[warp][0][jj];
+        nC = s_halo[warp][1][jj];
+      }
+      const double fine = fma(WF4, nF, fma(WF3, sF3, fma(WF2, sF2, fma(WF1, sF1, WF0 * sF0))));
+      const double coarse = fma(WC0, nC, fma(WC1, sCm, WC0 * sC0));
+      const double cell = fma(2.0, fine, -coarse);
+      outp[(size_t)jj * D] = cell;
+      tp += cell;
+      if (HAS_ERR) {
+        tF0 += sF0; tF1 += sF1; tF2 += sF2; tF3 += sF3;
+        tC0 += sC0; tCm += sCm;
+        // the boundary column carries both weights, except on the tile's last column
+        const double wsum = (jj == 31) ? 0.0 : c.wF;
+        const double wcsum = (jj == 31) ? 0.0 : c.wC;
+        const double wb = (c.wF2 + wsum) * c.b, wcb = (c.wC2 + wcsum) * c.b;
+        bF0 = fma(wb, T0, bF0); bF1 = fma(wb, T1, bF1);
+        bF2 = fma(wb, T2, bF2); bF3 = fma(wb, T3, bF3);
+        bC0 = fma(wcb, T0, bC0); bCm = fma(wcb, Tm, bCm);
+        if (HAS_M2) {
+          const double wbb = wb * c.b, wcbb = wcb * c.b;
+          qF0 = fma(wbb, T0, qF0); qF1 = fma(wbb, T1, qF1);
+          qF2 = fma(wbb, T2, qF2); qF3 = fma(wbb, T3, qF3);
+          qC0 = fma(wcbb, T0, qC0); qCm = fma(wcbb, Tm, qCm);
+        }
+      }
+      sF0 = c.wF * T0; sF1 = c.wF * T1; sF2 = c.wF * T2; sF3 = c.wF * T3;
+      sC0 = c.wC * T0; sCm = c.wC * Tm;
+    }
+  }
+#undef QB_BOUND_TEST
+
+  if (HAS_ERR) {
+    // sum over the lane's rows of weight * (a^n * rowsum + ...), fine counted twice
+    double e1 = EW0 * fma(a0, tF0, bF0);
+    e1 = fma(WF1, fma(a1, tF1, bF1), e1);
+    e1 = fma(WF2, fma(a2, tF2, bF2), e1);
+    e1 = fma(WF3, fma(a3, tF3, bF3), e1);
+    double e1c = EC0 * fma(a0, tC0, bC0);
+    e1c = fma(WC1, fma(am, tCm, bCm), e1c);
+    err1 += fma(2.0, e1, -e1c);
+    if (HAS_M2) {
+      double e2 = EW0 * fma(a0 * a0, tF0, fma(2.0 * a0, bF0, qF0));
+      e2 = fma(WF1, fma(a1 * a1, tF1, fma(2.0 * a1, bF1, qF1)), e2);
+      e2 = fma(WF2, fma(a2 * a2, tF2, fma(2.0 * a2, bF2, qF2)), e2);
+      e2 = fma(WF3, fma(a3 * a3, tF3, fma(2.0 * a3, bF3, qF3)), e2);
+      double e2c = EC0 * fma(a0 * a0, tC0, fma(2.0 * a0, bC0, qC0));
+      e2c = fma(WC1, fma(am * am, tCm, fma(2.0 * am, bCm, qCm)), e2c);
+      err2 += fma(2.0, e2, -e2c);
+    }
+  }
+
+  // warp reduction in a fixed order
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    tp += __shfl_down_sync(0xffffffffu, tp, off);
+    err1 += __shfl_down_sync(0xffffffffu, err1, off);
+    err2 += __shfl_down_sync(0xffffffffu, err2, off);
+    ok &= __shfl_down_sync(0xffffffffu, ok, off);
+  }
+  if (lane == 0) {
+    double* p = a.part + (size_t)tile * QB_FUSED_PART_STRIDE;
+    p[0] = tp;
+    p[1] = err1;
+    p[2] = err2;
+    p[3] = (double)ok;
+  }
+}
+
+// One thread per slice: tile partials -> summary, in tile order.
+__global__ void k_fused_final(unsigned n, unsigned per_slice, const double* __restrict__ part,
+                              double* __restrict__ summary) {
+  const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  dd tp = make_dd(0.0, 0.0);
+  double m1 = 0.0, m2 = 0.0;
+  int ok = 1;
+  for (unsigned t = 0; t < per_slice; t++) {
+    const double* p = part + ((size_t)s * per_slice + t) * QB_FUSED_PART_STRIDE;
+    tp = dd_add_d(tp, p[0]);
+    m1 += p[1];
+    m2 += p[2];
+    ok &= (p[3] != 0.0);
+  }
+  double* o = summary + (size_t)s * 8;
+  o[0] = tp.hi;
+  o[1] = tp.lo;
+  o[2] = m1;
+  o[3] = m2;
+  o[4] = (double)ok;
+  o[5] = o[6] = o[7] = 0.0;
+}
+
+// ---- host side ----------------------------------------------------------------
+
+// Decide whether the fused kernel applies and which variant.
+inline bool fused2d_prepare(const Plan& h, int sm_count, FusedPlan2D* f, std::string* why) {
+  (void)sm_count;
+  if (h.kind >= 0) {
+    *why = "not a two-dimensional plan";
+    return false;
+  }
+  if (!h.richardson) {
+    *why = "single-pass (non-Richardson) request";
+    return false;
+  }
+  if (h.D % 32 != 0) {
+    *why = "dimension is not a multiple of 32";
+    return false;
+  }
+  if ((size_t)h.slices.size() * (size_t)(h.D / 32) * (h.D / 32) >= (size_t(1) << 31)) {
+    *why = "too many tiles";
+    return false;
+  }
+  const DevConsts& c = h.c;
+  int rel_max = -100000;
+  for (size_t i = 0; i < h.slices.size(); i++) {
+    rel_max = std::max(rel_max, (int)std::labs((long)h.k_a[i]) - c.m);
+    rel_max = std::max(rel_max, (int)std::labs((long)h.k_b[i]) - c.m);
+  }
+  if (h.slices.empty()) rel_max = 0;
+  // |u| <= |x_d| + |kappa| |x_r| < 2^(rel_max + 1) * (1 + |kappa|)
+  const int log_u = rel_max + 1 + (int)std::ceil(std::log2(1.0 + std::fabs(c.kappa.hi)));
+  if (c.lam_exp - log_u >= 29) {
+    f->mode = 0;
+  } else if (c.lam_exp - log_u >= 10) {
+    f->mode = 1;
+  } else {
+    *why = "l - sigma too small for the sinc expansion of the inner sine";
+    return false;
+  }
+  // Lambda sin(z)/... : 1 / sinc^2(z) = 1 + z^2/3 + z^4/15 + 2 z^6/189, z^2 = (pi/Lambda)^2 w
+  const double q = std::ldexp(9.86960440108935861883, -2 * std::min(c.lam_exp, 500));
+  f->k.c1 = q / 3.0;
+  f->k.c2 = q * q / 15.0;
+  f->k.c3 = q * q * q * (2.0 / 189.0);
+  f->k.cs = c.cs;
+  f->k.e0s = c.e0s;
+  f->k.r_m = c.r_m;
+  f->k.D = h.D;
+  f->k.nb = h.D / 32;
+  f->k.NP = table_points(h.D);
+  f->k.ncol = 5 * h.D + 1;
+  f->k.n_tiles = (unsigned)(h.slices.size() * (size_t)f->k.nb * f->k.nb);
+  f->has_err = h.with_error;
+  // second moment: relative size cs * h_max / 2 versus the first
+  const double csh = c.cs * std::ldexp(1.0, rel_max + 2);
+  f->has_m2 = h.with_error && (csh > 1e-13);
+  // The bound test needs the per-point norm only while e0s can matter:
+  // T1 T2 r/2^m is never below ~1e-90 at double precision, so for e0s < 2^-330
+  // the test is s (2 + s) <= bound, monotone in h => decided at the far corner.
+  f->has_bound = h.with_error && (c.e0s >= std::ldexp(1.0, -330));
+  f->host_unbounded.assign(h.slices.size(), 0);
+  if (h.with_error && !f->has_bound) {
+    for (size_t i = 0; i < h.slices.size(); i++) {
+      const double hmax = 2.0 * (h.slices[i].scale_a + h.slices[i].scale_b);
+      const double sv = c.cs * hmax;
+      f->host_unbounded[i] = (QB_ERROR_BOUND - sv * (2.0 + sv) >= 0.0) ? 0 : 1;
+    }
+  }
+  const size_t bytes = std::max<size_t>(1, h.tabs_b.size()) * (size_t)f->k.ncol * QB_FUSED_REC *
+                       sizeof(double);
+  if (f->d_cols) cudaFree(f->d_cols);
+  f->d_cols = nullptr;
+  if (cudaMalloc(&f->d_cols, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    *why = "out of device memory for the column records";
+    return false;
+  }
+  f->cols_bytes = bytes;
+  return true;
+}
+
+inline uint32_t fused2d_launches(const FusedPlan2D&) { return 4; }  // axis, cols, fused, final
+
+template <int MODE>
+inline void fused2d_launch_variant(const FusedPlan2D& f, const FusedArgs& args, unsigned blocks,
+                                   cudaStream_t st) {
+  const int v = (f.has_err ? 1 : 0) | (f.has_m2 ? 2 : 0) | (f.has_bound ? 4 : 0);
+  const dim3 g(blocks), b(QB_FUSED_WARPS * 32);
+  switch (v) {
+    case 0: k_fused2d<MODE, false, false, false><<<g, b, 0, st>>>(args); break;
+    case 1: k_fused2d<MODE, true, false, false><<<g, b, 0, st>>>(args); break;
+    case 3: k_fused2d<MODE, true, true, false><<<g, b, 0, st>>>(args); break;
+    case 5: k_fused2d<MODE, true, false, true><<<g, b, 0, st>>>(args); break;
+    default: k_fused2d<MODE, true, true, true><<<g, b, 0, st>>>(args); break;
+  }
+}
+
+// Enqueues k_fused_cols, k_fused2d and k_fused_final (k_axis2d is enqueued by the caller).
+inline int fused2d_run(const FusedPlan2D& f, const Plan& h, cudaStream_t st,
+                       const DevSlice* slices, const AxisD* tab_a, const AxisR* tab_b,
+                       const double* gw, const FusedItem*, double* part, double* d_cells,
+                       double* d_summary, const TabDesc* desc_b) {
+  const int D = h.D;
+  const unsigned n = (unsigned)h.slices.size();
+  k_fused_cols<<<dim3((f.k.ncol + 127) / 128, (unsigned)h.tabs_b.size()), 128, 0, st>>>(
+      D, h.c.m, desc_b, tab_b, gw, (double*)f.d_cols);
+  FusedArgs args;
+  args.k = f.k;
+  args.slices = slices;
+  args.tab_a = tab_a;
+  args.cols = (const double*)f.d_cols;
+  args.gw = gw;
+  args.out = d_cells;
+  args.part = part;
+  const unsigned blocks = (f.k.n_tiles + QB_FUSED_WARPS - 1) / QB_FUSED_WARPS;
+  if (f.mode == 0)
+    fused2d_launch_variant<0>(f, args, blocks, st);
+  else
+    fused2d_launch_variant<1>(f, args, blocks, st);
+  k_fused_final<<<(n + 127) / 128, 128, 0, st>>>(n, (unsigned)(f.k.nb * f.k.nb), part, d_summary);
+  return cudaGetLastError() == cudaSuccess ? 0 : -100;
+}
+
+}  // namespace qb200

@@ -1,0 +1,543 @@
+// qb200.cu -- the C ABI (include/qunundrum_b200.h) over the CUDA kernels.
+//
+// One qb200_context per worker process / GPU. A plan owns the device copies of
+// a batch's descriptors and scratch; qb200_plan_run() only enqueues kernels.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/qunundrum_b200.h"
+#include "kernels_fused2d.cuh"
+#include "kernels_plain.cuh"
+#include "plan.hpp"
+
+using namespace qb200;
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define QB_CUDA(call)                                                                   \
+  do {                                                                                  \
+    const cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(-100, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int reserve(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    QB_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return 0;
+  }
+  template <class T>
+  T* as() const {
+    return (T*)p;
+  }
+};
+
+struct DevGeometry {
+  DevBuf gx, gw;
+};
+
+}  // namespace
+
+struct qb200_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  uint64_t launches = 0;
+  std::map<int, std::unique_ptr<DevGeometry>> geo;
+  // staging for the synchronous host API
+  DevBuf out_cells, out_summary;
+  void* h_summary = nullptr;
+  size_t h_summary_bytes = 0;
+};
+
+struct qb200_plan {
+  qb200_context* ctx = nullptr;
+  Plan host;
+  int algo = 0;        // resolved: 1 plain, 2 fused
+  int fused_ok = 0;
+  std::string fused_why;
+  uint32_t n = 0;
+  DevGeometry* geo = nullptr;
+  DevBuf desc_a, desc_b, slices, tab_a, tab_b;
+  // plain path scratch (per chunk of slices)
+  uint32_t chunk = 0;
+  DevBuf cells_c, cells_f, part_c, part_f, part_tp, values;
+  // fused path
+  FusedPlan2D fused;
+  DevBuf fused_part;
+};
+
+namespace {
+
+int get_geometry(qb200_context* ctx, int D, DevGeometry** out) {
+  auto it = ctx->geo.find(D);
+  if (it != ctx->geo.end()) {
+    *out = it->second.get();
+    return 0;
+  }
+  const Geometry g = make_geometry(D);
+  std::unique_ptr<DevGeometry> dg(new DevGeometry);
+  if (int rc = dg->gx.reserve(g.gx.size() * sizeof(DD))) return rc;
+  if (int rc = dg->gw.reserve(g.gw.size() * sizeof(double))) return rc;
+  QB_CUDA(cudaMemcpy(dg->gx.p, g.gx.data(), g.gx.size() * sizeof(DD), cudaMemcpyHostToDevice));
+  QB_CUDA(cudaMemcpy(dg->gw.p, g.gw.data(), g.gw.size() * sizeof(double),
+                     cudaMemcpyHostToDevice));
+  *out = dg.get();
+  ctx->geo[D] = std::move(dg);
+  return 0;
+}
+
+ParamsView view_of(const qb200_params* p) {
+  ParamsView v;
+  v.m = p->m;
+  v.l = p->l;
+  v.sigma = p->sigma;
+  v.d_be = p->d_be;
+  v.d_len = p->d_len;
+  v.r_be = p->r_be;
+  v.r_len = p->r_len;
+  return v;
+}
+
+int upload_plan(qb200_plan* pl) {
+  const Plan& h = pl->host;
+  const uint32_t n = (uint32_t)h.slices.size();
+  pl->n = n;
+  const int D = h.D;
+  const int NP = table_points(D);
+  if (int rc = get_geometry(pl->ctx, D, &pl->geo)) return rc;
+  std::vector<DevSlice> ds(n);
+  for (uint32_t i = 0; i < n; i++) {
+    ds[i].tab_a = h.slices[i].tab_a;
+    ds[i].tab_b = h.slices[i].tab_b;
+    ds[i].scale_a = h.slices[i].scale_a;
+    ds[i].scale_b = h.slices[i].scale_b;
+    ds[i].eta_shift = h.slices[i].eta_shift;
+  }
+  if (int rc = pl->slices.reserve(std::max<size_t>(1, n) * sizeof(DevSlice))) return rc;
+  if (n) QB_CUDA(cudaMemcpy(pl->slices.p, ds.data(), n * sizeof(DevSlice), cudaMemcpyHostToDevice));
+  if (int rc = pl->desc_a.reserve(std::max<size_t>(1, h.tabs_a.size()) * sizeof(TabDesc))) return rc;
+  if (!h.tabs_a.empty())
+    QB_CUDA(cudaMemcpy(pl->desc_a.p, h.tabs_a.data(), h.tabs_a.size() * sizeof(TabDesc),
+                       cudaMemcpyHostToDevice));
+  if (h.kind < 0) {
+    if (int rc = pl->desc_b.reserve(std::max<size_t>(1, h.tabs_b.size()) * sizeof(TabDesc))) return rc;
+    if (!h.tabs_b.empty())
+      QB_CUDA(cudaMemcpy(pl->desc_b.p, h.tabs_b.data(), h.tabs_b.size() * sizeof(TabDesc),
+                         cudaMemcpyHostToDevice));
+    if (int rc = pl->tab_a.reserve(std::max<size_t>(1, h.tabs_a.size()) * NP * sizeof(AxisD))) return rc;
+    if (int rc = pl->tab_b.reserve(std::max<size_t>(1, h.tabs_b.size()) * NP * sizeof(AxisR))) return rc;
+  }
+  return 0;
+}
+
+// Scratch for the plain path: chunks of at most ~1 GiB of pass cells.
+int reserve_plain(qb200_plan* pl) {
+  const Plan& h = pl->host;
+  const size_t D = (size_t)h.D;
+  if (h.kind < 0) {
+    const size_t per_slice = 5 * D * D * sizeof(double);
+    size_t chunk = std::max<size_t>(1, (size_t(1) << 30) / per_slice);
+    chunk = std::min<size_t>(chunk, std::max<uint32_t>(1, pl->n));
+    chunk = std::min<size_t>(chunk, 65535);
+    pl->chunk = (uint32_t)chunk;
+    const size_t nb_c = (D * D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+    const size_t nb_f = (4 * D * D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+    if (int rc = pl->cells_c.reserve(chunk * D * D * sizeof(double))) return rc;
+    if (h.richardson)
+      if (int rc = pl->cells_f.reserve(chunk * 4 * D * D * sizeof(double))) return rc;
+    if (int rc = pl->part_c.reserve(chunk * nb_c * 3 * sizeof(double))) return rc;
+    if (int rc = pl->part_f.reserve(chunk * nb_f * 3 * sizeof(double))) return rc;
+    if (int rc = pl->part_tp.reserve(chunk * nb_c * 2 * sizeof(double))) return rc;
+  } else {
+    const size_t NP = (size_t)table_points(h.D);
+    size_t chunk = std::max<size_t>(1, (size_t(1) << 28) / (NP * sizeof(double)));
+    chunk = std::min<size_t>(chunk, std::max<uint32_t>(1, pl->n));
+    chunk = std::min<size_t>(chunk, 65535);
+    pl->chunk = (uint32_t)chunk;
+    const size_t nb = (D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+    if (int rc = pl->values.reserve(chunk * NP * sizeof(double))) return rc;
+    if (int rc = pl->part_tp.reserve(chunk * nb * 2 * sizeof(double))) return rc;
+  }
+  return 0;
+}
+
+int run_plain_2d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_summary) {
+  const Plan& h = pl->host;
+  qb200_context* ctx = pl->ctx;
+  const int D = h.D;
+  const int NP = table_points(D);
+  const int n_a = (int)h.tabs_a.size(), n_b = (int)h.tabs_b.size();
+  if (pl->n == 0) return 0;
+  {
+    dim3 grid((NP + 127) / 128, n_a + n_b);
+    k_axis2d<<<grid, 128, 0, st>>>(h.c, NP, n_a, pl->desc_a.as<TabDesc>(), pl->desc_b.as<TabDesc>(),
+                                   pl->geo->gx.as<dd>(), pl->tab_a.as<AxisD>(),
+                                   pl->tab_b.as<AxisR>());
+    ctx->launches++;
+  }
+  const int nb_c = (D * D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+  const int nb_f = (4 * D * D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+  for (uint32_t s0 = 0; s0 < pl->n; s0 += pl->chunk) {
+    const uint32_t ns = std::min(pl->chunk, pl->n - s0);
+    const DevSlice* sl = pl->slices.as<DevSlice>() + s0;
+    k_pass2d<<<dim3(nb_c, ns), QB_PLAIN_BLOCK, 0, st>>>(
+        h.c, D, 0, h.with_error ? 1 : 0, sl, pl->tab_a.as<AxisD>(), pl->tab_b.as<AxisR>(),
+        pl->geo->gw.as<double>(), pl->cells_c.as<double>(), pl->part_c.as<double>());
+    ctx->launches++;
+    if (h.richardson) {
+      k_pass2d<<<dim3(nb_f, ns), QB_PLAIN_BLOCK, 0, st>>>(
+          h.c, D, 1, h.with_error ? 1 : 0, sl, pl->tab_a.as<AxisD>(), pl->tab_b.as<AxisR>(),
+          pl->geo->gw.as<double>(), pl->cells_f.as<double>(), pl->part_f.as<double>());
+      ctx->launches++;
+    }
+    k_rich2d<<<dim3(nb_c, ns), QB_PLAIN_BLOCK, 0, st>>>(
+        D, h.richardson, pl->cells_c.as<double>(), pl->cells_f.as<double>(),
+        d_cells + (size_t)s0 * D * D, pl->part_tp.as<double>());
+    ctx->launches++;
+    k_final2d<<<(ns + 127) / 128, 128, 0, st>>>(
+        (int)ns, h.richardson, nb_c, nb_f, nb_c, pl->part_c.as<double>(), pl->part_f.as<double>(),
+        pl->part_tp.as<double>(), d_summary + (size_t)s0 * QB200_SUMMARY_STRIDE);
+    ctx->launches++;
+  }
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int run_plain_1d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_summary) {
+  const Plan& h = pl->host;
+  qb200_context* ctx = pl->ctx;
+  const int D = h.D;
+  const int NP = table_points(D);
+  const int nb = (D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+  for (uint32_t s0 = 0; s0 < pl->n; s0 += pl->chunk) {
+    const uint32_t ns = std::min(pl->chunk, pl->n - s0);
+    const DevSlice* sl = pl->slices.as<DevSlice>() + s0;
+    k_vals1d<<<dim3((NP + 127) / 128, ns), 128, 0, st>>>(
+        h.c, h.kind, NP, sl, pl->desc_a.as<TabDesc>(), pl->geo->gx.as<dd>(),
+        pl->values.as<double>());
+    k_cells1d<<<dim3(nb, ns), QB_PLAIN_BLOCK, 0, st>>>(
+        D, h.richardson, sl, pl->values.as<double>(), pl->geo->gw.as<double>(),
+        d_cells + (size_t)s0 * D, pl->part_tp.as<double>());
+    k_final1d<<<(ns + 127) / 128, 128, 0, st>>>(
+        (int)ns, nb, pl->part_tp.as<double>(), d_summary + (size_t)s0 * QB200_SUMMARY_STRIDE);
+    ctx->launches += 3;
+  }
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+uint32_t plain_launches(const qb200_plan* pl) {
+  const uint32_t chunks = pl->n ? (pl->n + pl->chunk - 1) / pl->chunk : 0;
+  if (pl->host.kind < 0) return (pl->n ? 1 : 0) + chunks * (pl->host.richardson ? 4 : 3);
+  return chunks * 3;
+}
+
+int finish_common(qb200_plan* pl) {
+  if (int rc = upload_plan(pl)) return rc;
+  if (int rc = reserve_plain(pl)) return rc;
+  pl->fused_ok = 0;
+  if (pl->host.kind < 0) {
+    pl->fused_ok = fused2d_prepare(pl->host, pl->ctx->sm_count, &pl->fused, &pl->fused_why) ? 1 : 0;
+    if (pl->fused_ok) {
+      if (int rc = pl->fused_part.reserve(std::max<size_t>(1, pl->fused.k.n_tiles) *
+                                          QB_FUSED_PART_STRIDE * sizeof(double)))
+        return rc;
+    }
+  }
+  pl->algo = pl->fused_ok ? 2 : 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qb200_version(void) { return QB200_VERSION; }
+const char* qb200_last_error(void) { return g_err.c_str(); }
+
+int qb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int qb200_create(int device, qb200_context** out) {
+  *out = nullptr;
+  const int n = qb200_device_count();
+  if (n <= 0)
+    return fail(-101, "no CUDA device: the slice integrators have no CPU path");
+  if (device < 0 || device >= n) return fail(-102, "bad device index");
+  QB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  QB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(-103, std::string("built for sm_100a (B200); found ") + prop.name);
+  qb200_context* ctx = new qb200_context;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  const cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(-100, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return 0;
+}
+
+void qb200_destroy(qb200_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
+  delete ctx;
+}
+
+uint64_t qb200_launch_count(const qb200_context* ctx) { return ctx ? ctx->launches : 0; }
+
+void* qb200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void qb200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int qb200_plan2d_create(qb200_context* ctx, const qb200_params* params, int method,
+                        int richardson, uint32_t dimension, uint32_t n,
+                        const int32_t* a_d, const int32_t* a_r, qb200_plan** out) {
+  *out = nullptr;
+  if (!ctx || !params) return fail(-1, "null argument");
+  QB_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<qb200_plan> pl(new qb200_plan);
+  pl->ctx = ctx;
+  std::string err;
+  if (int rc = plan_2d(view_of(params), method, richardson, dimension, n, a_d, a_r, &pl->host, &err))
+    return fail(rc, err);
+  if (int rc = finish_common(pl.get())) return rc;
+  *out = pl.release();
+  return 0;
+}
+
+int qb200_plan1d_create(qb200_context* ctx, const qb200_params* params, int kind, int richardson,
+                        uint32_t dimension, uint32_t n, const int32_t* a, const int32_t* eta,
+                        qb200_plan** out) {
+  *out = nullptr;
+  if (!ctx || !params) return fail(-1, "null argument");
+  QB_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<qb200_plan> pl(new qb200_plan);
+  pl->ctx = ctx;
+  std::string err;
+  if (int rc = plan_1d(view_of(params), kind, richardson, dimension, n, a, eta, &pl->host, &err))
+    return fail(rc, err);
+  if (int rc = finish_common(pl.get())) return rc;
+  *out = pl.release();
+  return 0;
+}
+
+void qb200_plan_destroy(qb200_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->ctx->device);
+  delete plan;
+}
+
+uint64_t qb200_plan_cells(const qb200_plan* plan) {
+  const uint64_t D = (uint64_t)plan->host.D;
+  return (uint64_t)plan->n * (plan->host.kind < 0 ? D * D : D);
+}
+
+uint32_t qb200_plan_launches(const qb200_plan* plan) {
+  if (plan->algo == 2) return fused2d_launches(plan->fused);
+  return plain_launches(plan);
+}
+
+int qb200_plan_set_algorithm(qb200_plan* plan, int algo) {
+  if (algo == 0) {
+    plan->algo = plan->fused_ok ? 2 : 1;
+    return 0;
+  }
+  if (algo == 1) {
+    plan->algo = 1;
+    return 0;
+  }
+  if (algo == 2) {
+    if (!plan->fused_ok) return fail(-20, "fused kernel not applicable: " + plan->fused_why);
+    plan->algo = 2;
+    return 0;
+  }
+  return fail(-21, "unknown algorithm");
+}
+
+int qb200_plan_algorithm(const qb200_plan* plan) { return plan->algo; }
+
+int qb200_plan_run(qb200_plan* plan, void* stream, double* d_cells, double* d_summary) {
+  qb200_context* ctx = plan->ctx;
+  QB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  if (plan->host.kind >= 0) return run_plain_1d(plan, st, d_cells, d_summary);
+  if (plan->algo == 2) {
+    if (plan->n == 0) return 0;
+    const Plan& h = plan->host;
+    const int NP = table_points(h.D);
+    const int n_a = (int)h.tabs_a.size(), n_b = (int)h.tabs_b.size();
+    dim3 grid((NP + 127) / 128, n_a + n_b);
+    k_axis2d<<<grid, 128, 0, st>>>(h.c, NP, n_a, plan->desc_a.as<TabDesc>(),
+                                   plan->desc_b.as<TabDesc>(), plan->geo->gx.as<dd>(),
+                                   plan->tab_a.as<AxisD>(), plan->tab_b.as<AxisR>());
+    ctx->launches++;
+    const int rc = fused2d_run(plan->fused, h, st, plan->slices.as<DevSlice>(),
+                               plan->tab_a.as<AxisD>(), plan->tab_b.as<AxisR>(),
+                               plan->geo->gw.as<double>(), nullptr,
+                               plan->fused_part.as<double>(), d_cells, d_summary,
+                               plan->desc_b.as<TabDesc>());
+    ctx->launches += fused2d_launches(plan->fused) - 1;
+    if (rc) return fail(rc, "fused kernel launch failed");
+    QB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  return run_plain_2d(plan, st, d_cells, d_summary);
+}
+
+int qb200_plan_finish(const qb200_plan* plan, const double* hs, long double* tp, long double* te,
+                      uint32_t* flags) {
+  const Plan& h = plan->host;
+  for (uint32_t i = 0; i < plan->n; i++) {
+    const double* s = hs + (size_t)i * QB200_SUMMARY_STRIDE;
+    if (tp) tp[i] = (long double)s[0] + (long double)s[1];
+    if (te) te[i] = h.kind < 0 ? total_error_2d(h, i, s[2], s[3]) : 0.0L;
+    if (flags) {
+      uint32_t f = kFlagMethodSimpson | (h.richardson ? kFlagMethodRichardson : 0u);
+      if (h.kind < 0 && h.with_error) {
+        // Coarse-pass points only decide the warning
+        // (src/distribution_slice_compute_richardson.cpp:28-44, 69-72).
+        if (s[4] == 0.0) f |= kFlagErrorBoundWarning;
+        if (plan->algo == 2 && !plan->fused.has_bound && plan->fused.host_unbounded[i])
+          f |= kFlagErrorBoundWarning;
+      }
+      flags[i] = f;
+    }
+  }
+  return 0;
+}
+
+static int run_sync(qb200_context* ctx, qb200_plan* pl, double* cells, long double* tp,
+                    long double* te, uint32_t* flags) {
+  const uint64_t ncells = qb200_plan_cells(pl);
+  const size_t sum_bytes = (size_t)pl->n * QB200_SUMMARY_STRIDE * sizeof(double);
+  if (int rc = ctx->out_cells.reserve(std::max<size_t>(8, ncells * sizeof(double)))) return rc;
+  if (int rc = ctx->out_summary.reserve(std::max<size_t>(8, sum_bytes))) return rc;
+  if (ctx->h_summary_bytes < sum_bytes) {
+    if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
+    ctx->h_summary = nullptr;
+    ctx->h_summary_bytes = 0;
+    QB_CUDA(cudaHostAlloc(&ctx->h_summary, sum_bytes, cudaHostAllocDefault));
+    ctx->h_summary_bytes = sum_bytes;
+  }
+  if (int rc = qb200_plan_run(pl, ctx->stream, ctx->out_cells.as<double>(),
+                              ctx->out_summary.as<double>()))
+    return rc;
+  if (ncells)
+    QB_CUDA(cudaMemcpyAsync(cells, ctx->out_cells.p, ncells * sizeof(double),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  if (sum_bytes)
+    QB_CUDA(cudaMemcpyAsync(ctx->h_summary, ctx->out_summary.p, sum_bytes,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  QB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return qb200_plan_finish(pl, (const double*)ctx->h_summary, tp, te, flags);
+}
+
+int qb200_slice2d_compute(qb200_context* ctx, const qb200_params* params, int method,
+                          int richardson, uint32_t dimension, uint32_t n, const int32_t* a_d,
+                          const int32_t* a_r, double* cells, long double* tp, long double* te,
+                          uint32_t* flags) {
+  qb200_plan* pl = nullptr;
+  if (int rc = qb200_plan2d_create(ctx, params, method, richardson, dimension, n, a_d, a_r, &pl))
+    return rc;
+  const int rc = run_sync(ctx, pl, cells, tp, te, flags);
+  qb200_plan_destroy(pl);
+  return rc;
+}
+
+int qb200_slice1d_compute(qb200_context* ctx, const qb200_params* params, int kind,
+                          int richardson, uint32_t dimension, uint32_t n, const int32_t* a,
+                          const int32_t* eta, double* cells, long double* tp, uint32_t* flags) {
+  qb200_plan* pl = nullptr;
+  if (int rc = qb200_plan1d_create(ctx, params, kind, richardson, dimension, n, a, eta, &pl))
+    return rc;
+  const int rc = run_sync(ctx, pl, cells, tp, nullptr, flags);
+  qb200_plan_destroy(pl);
+  return rc;
+}
+
+uint32_t qb200_heuristic_sigma(uint32_t l) { return heuristic_sigma(l); }
+
+int qb200_host_constants(const qb200_params* p, double* out20) {
+  HostConsts h;
+  const int rc = host_consts_compute(p->m, p->l, p->sigma, p->d_be, p->d_len, p->r_be, p->r_len, &h);
+  if (rc) return fail(rc, "bad parameters");
+  const DD* v[10] = {&h.kappa, &h.kappa_q, &h.c_over_L, &h.n_over_L, &h.n1_over_L,
+                     &h.beta_m, &h.rbeta_m, &h.r_m, &h.d_m, &h.rho};
+  for (int i = 0; i < 10; i++) {
+    out20[2 * i] = v[i]->hi;
+    out20[2 * i + 1] = v[i]->lo;
+  }
+  return 0;
+}
+
+int qb200_measure_fp64_peak(qb200_context* ctx, double* flops) {
+  QB_CUDA(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+  DevBuf out;
+  if (int rc = out.reserve((size_t)blocks * threads * sizeof(double))) return rc;
+  cudaEvent_t e0, e1;
+  QB_CUDA(cudaEventCreate(&e0));
+  QB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    QB_CUDA(cudaEventRecord(e0, ctx->stream));
+    k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(out.as<double>(), iters, 0.999999, 1e-9);
+    ctx->launches++;
+    QB_CUDA(cudaEventRecord(e1, ctx->stream));
+    QB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    QB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3);
+    if (rep > 0 && fl > best) best = fl;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *flops = best;
+  return 0;
+}
+
+}  // extern "C"

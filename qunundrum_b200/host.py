@@ -1,0 +1,486 @@
+"""Host-side mirror of the reference's slice-integration interface (ctypes over the C ABI).
+
+Names follow the reference:
+
+  Parameters / Diagonal_Parameters            src/parameters.h:33-114, src/diagonal_parameters.h:32-106
+  Distribution_Slice                          src/distribution_slice.h:86-139
+  Linear_Distribution_Slice                   src/linear_distribution_slice.h:48-91
+  Diagonal_Distribution_Slice                 src/diagonal_distribution_slice.h:32-83
+  distribution_slice_compute[_richardson]     src/distribution_slice.h:364-392
+  linear_distribution_slice_compute[_richardson]
+  diagonal_distribution_slice_compute[_richardson]
+
+Semantics kept: the caller creates the slice with its dimension, the callee
+fills the cells, total_probability, total_error, coordinates (and eta) and
+REPLACES the method bits of flags; parameters are read-only; errors are fatal
+(the reference calls critical() -> exit(-1), src/errors.c; here CriticalError).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+DISTRIBUTION_SLICE_COMPUTE_METHOD_HEURISTIC_SIGMA = 0
+DISTRIBUTION_SLICE_COMPUTE_METHOD_OPTIMAL_LOCAL_SIGMA = 1
+DISTRIBUTION_SLICE_COMPUTE_METHOD_QUICK = 2
+LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_D = 0
+LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_R = 1
+KIND_DIAGONAL = 2
+
+SLICE_FLAGS_ERROR_BOUND_WARNING = 0x00000001
+SLICE_FLAGS_METHOD_SIMPSON = 0x00020000
+SLICE_FLAGS_METHOD_RICHARDSON = 0x00080000
+SLICE_FLAGS_MASK_METHOD = 0x000F0000
+
+SUMMARY_STRIDE = 8
+
+
+class CriticalError(RuntimeError):
+    """The reference's critical(): unrecoverable error in a slice computation."""
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libqunundrum_b200.so")
+
+
+class _Params(C.Structure):
+    _fields_ = [("m", C.c_uint32), ("l", C.c_uint32), ("sigma", C.c_uint32),
+                ("d_be", C.c_char_p), ("d_len", C.c_size_t),
+                ("r_be", C.c_char_p), ("r_len", C.c_size_t)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libqunundrum_b200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise CriticalError(
+            f"{path} is missing: build it with `python -m qunundrum_b200.build` "
+            "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u32, i32p = C.c_void_p, C.c_uint32, C.c_void_p
+    PP = C.POINTER(_Params)
+    L.qb200_version.restype = C.c_int
+    L.qb200_last_error.restype = C.c_char_p
+    L.qb200_device_count.restype = C.c_int
+    L.qb200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.qb200_destroy.argtypes = [vp]
+    L.qb200_launch_count.argtypes = [vp]
+    L.qb200_launch_count.restype = C.c_uint64
+    L.qb200_host_alloc.argtypes = [C.c_size_t]
+    L.qb200_host_alloc.restype = vp
+    L.qb200_host_free.argtypes = [vp]
+    L.qb200_slice2d_compute.argtypes = [vp, PP, C.c_int, C.c_int, u32, u32, i32p, i32p,
+                                        vp, vp, vp, vp]
+    L.qb200_slice1d_compute.argtypes = [vp, PP, C.c_int, C.c_int, u32, u32, i32p, i32p,
+                                        vp, vp, vp]
+    L.qb200_plan2d_create.argtypes = [vp, PP, C.c_int, C.c_int, u32, u32, i32p, i32p,
+                                      C.POINTER(vp)]
+    L.qb200_plan1d_create.argtypes = [vp, PP, C.c_int, C.c_int, u32, u32, i32p, i32p,
+                                      C.POINTER(vp)]
+    L.qb200_plan_destroy.argtypes = [vp]
+    L.qb200_plan_cells.argtypes = [vp]
+    L.qb200_plan_cells.restype = C.c_uint64
+    L.qb200_plan_launches.argtypes = [vp]
+    L.qb200_plan_launches.restype = C.c_uint32
+    L.qb200_plan_set_algorithm.argtypes = [vp, C.c_int]
+    L.qb200_plan_algorithm.argtypes = [vp]
+    L.qb200_plan_run.argtypes = [vp, vp, vp, vp]
+    L.qb200_plan_finish.argtypes = [vp, vp, vp, vp, vp]
+    L.qb200_heuristic_sigma.argtypes = [u32]
+    L.qb200_heuristic_sigma.restype = u32
+    L.qb200_host_constants.argtypes = [PP, vp]
+    L.qb200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _err() -> str:
+    return lib().qb200_last_error().decode(errors="replace")
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise CriticalError(f"{what}: {_err()} (code {rc})")
+
+
+def _be(x: int) -> bytes:
+    if x < 0:
+        raise CriticalError("d and r must be non-negative")
+    return x.to_bytes(max(1, (x.bit_length() + 7) // 8), "big")
+
+
+# --------------------------------------------------------------------------- #
+# Parameters                                                                  #
+# --------------------------------------------------------------------------- #
+
+@dataclass
+class Parameters:
+    """Parameters (src/parameters.h:33-114); regions as parameters_setup_regions
+    (src/parameters.cpp:30-51). Give s (l = ceil(m / s), parameters_explicit_m_s)
+    or l (parameters_explicit_m_l, s = 0)."""
+    m: int
+    s: int
+    d: int
+    r: int
+    t: int = 30
+    l: int = 0
+
+    def __post_init__(self):
+        if self.l == 0:
+            if self.s <= 0:
+                raise CriticalError("Parameters: s or l must be given")
+            self.l = int(math.ceil(self.m / self.s))
+        else:
+            self.s = 0
+        self.min_alpha_d = 0 if self.t > self.m else self.m - self.t
+        self.max_alpha_d = (self.m + self.l - 2 if self.t >= self.l
+                            else self.m + self.t - 1)
+        self.min_alpha_r = self.min_alpha_d
+        self.max_alpha_r = self.max_alpha_d
+
+    def _c(self, sigma: int = 0):
+        db, rb = _be(self.d), _be(self.r)
+        p = _Params(self.m, self.l, sigma, db, len(db), rb, len(rb))
+        p._keep = (db, rb)
+        return p
+
+
+@dataclass
+class Diagonal_Parameters:
+    """Diagonal_Parameters (src/diagonal_parameters.h:32-106)."""
+    m: int
+    sigma: int
+    s: int
+    d: int
+    r: int
+    eta_bound: int = 0
+    t: int = 30
+    l: int = 0
+
+    def __post_init__(self):
+        if self.l == 0:
+            if self.s <= 0:
+                raise CriticalError("Diagonal_Parameters: s or l must be given")
+            self.l = int(math.ceil(self.m / self.s))
+        else:
+            self.s = 0
+        self.min_alpha_r = 0 if self.t > self.m else self.m - self.t
+        self.max_alpha_r = (self.m + self.sigma - 2 if self.t >= self.sigma
+                            else self.m + self.t - 1)
+
+    def _c(self):
+        db, rb = _be(self.d), _be(self.r)
+        p = _Params(self.m, self.l, self.sigma, db, len(db), rb, len(rb))
+        p._keep = (db, rb)
+        return p
+
+
+# --------------------------------------------------------------------------- #
+# Slices                                                                      #
+# --------------------------------------------------------------------------- #
+
+@dataclass
+class Distribution_Slice:
+    """Distribution_Slice (src/distribution_slice.h:86-139);
+    norm_matrix[i_d + dimension * j_r]."""
+    dimension: int
+    min_log_alpha_d: int = 0
+    min_log_alpha_r: int = 0
+    total_probability: np.longdouble = np.longdouble(0)
+    total_error: np.longdouble = np.longdouble(0)
+    flags: int = 0
+    norm_matrix: np.ndarray = field(default=None, repr=False)
+
+    def __post_init__(self):
+        if self.norm_matrix is None:
+            self.norm_matrix = np.zeros(self.dimension * self.dimension, dtype=np.longdouble)
+
+
+@dataclass
+class Linear_Distribution_Slice:
+    """Linear_Distribution_Slice (src/linear_distribution_slice.h:48-91)."""
+    dimension: int
+    min_log_alpha: int = 0
+    total_probability: np.longdouble = np.longdouble(0)
+    total_error: np.longdouble = np.longdouble(0)
+    flags: int = 0
+    norm_vector: np.ndarray = field(default=None, repr=False)
+
+    def __post_init__(self):
+        if self.norm_vector is None:
+            self.norm_vector = np.zeros(self.dimension, dtype=np.longdouble)
+
+
+@dataclass
+class Diagonal_Distribution_Slice:
+    """Diagonal_Distribution_Slice (src/diagonal_distribution_slice.h:32-83)."""
+    dimension: int
+    min_log_alpha_r: int = 0
+    eta: int = 0
+    total_probability: np.longdouble = np.longdouble(0)
+    total_error: np.longdouble = np.longdouble(0)
+    flags: int = 0
+    norm_vector: np.ndarray = field(default=None, repr=False)
+
+    def __post_init__(self):
+        if self.norm_vector is None:
+            self.norm_vector = np.zeros(self.dimension, dtype=np.longdouble)
+
+
+# --------------------------------------------------------------------------- #
+# Context and batch API                                                       #
+# --------------------------------------------------------------------------- #
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Plan:
+    """A batch resident on the device (qb200_plan)."""
+
+    def __init__(self, ctx: "Context", handle, n: int, dimension: int, two_d: bool):
+        self.ctx, self.h, self.n, self.dimension, self.two_d = ctx, handle, n, dimension, two_d
+
+    @property
+    def cells(self) -> int:
+        return int(lib().qb200_plan_cells(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().qb200_plan_launches(self.h))
+
+    @property
+    def algorithm(self) -> int:
+        return int(lib().qb200_plan_algorithm(self.h))
+
+    def set_algorithm(self, algo: int):
+        _check(lib().qb200_plan_set_algorithm(self.h, algo), "qb200_plan_set_algorithm")
+
+    def run(self, d_cells_ptr: int, d_summary_ptr: int, stream: int = 0):
+        """Enqueue one pass over the batch; pointers are device addresses."""
+        _check(lib().qb200_plan_run(self.h, C.c_void_p(stream), C.c_void_p(d_cells_ptr),
+                                    C.c_void_p(d_summary_ptr)), "qb200_plan_run")
+
+    def finish(self, h_summary: np.ndarray):
+        h_summary = np.ascontiguousarray(h_summary, dtype=np.float64)
+        tp = np.zeros(self.n, dtype=np.longdouble)
+        te = np.zeros(self.n, dtype=np.longdouble)
+        fl = np.zeros(self.n, dtype=np.uint32)
+        _check(lib().qb200_plan_finish(self.h, h_summary.ctypes.data, tp.ctypes.data,
+                                       te.ctypes.data, fl.ctypes.data), "qb200_plan_finish")
+        return tp, te, fl
+
+    def close(self):
+        if self.h:
+            lib().qb200_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU (qb200_context). In an MPI farm: one per worker rank,
+    device = (rank - 1) mod device_count."""
+
+    def __init__(self, device: int = 0):
+        self.h = C.c_void_p()
+        _check(lib().qb200_create(device, C.byref(self.h)), "qb200_create")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().qb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().qb200_launch_count(self.h))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0)
+        _check(lib().qb200_measure_fp64_peak(self.h, C.byref(v)), "qb200_measure_fp64_peak")
+        return v.value
+
+    # ---- synchronous batches (host buffers) ---------------------------------
+    def slice2d_batch(self, params: Parameters, method: int, richardson: bool,
+                      dimension: int, min_log_alpha_d, min_log_alpha_r, out=None):
+        a_d, a_r = _i32(min_log_alpha_d), _i32(min_log_alpha_r)
+        n = len(a_d)
+        if len(a_r) != n:
+            raise CriticalError("coordinate arrays differ in length")
+        cells = out if out is not None else np.empty((n, dimension * dimension))
+        tp = np.zeros(n, dtype=np.longdouble)
+        te = np.zeros(n, dtype=np.longdouble)
+        fl = np.zeros(n, dtype=np.uint32)
+        p = params._c()
+        _check(lib().qb200_slice2d_compute(
+            self.h, C.byref(p), method, int(bool(richardson)), dimension, n,
+            a_d.ctypes.data, a_r.ctypes.data, cells.ctypes.data, tp.ctypes.data,
+            te.ctypes.data, fl.ctypes.data), "qb200_slice2d_compute")
+        return cells, tp, te, fl
+
+    def slice1d_batch(self, params, kind: int, richardson: bool, dimension: int,
+                      min_log_alpha, eta=None, out=None):
+        a = _i32(min_log_alpha)
+        n = len(a)
+        e = _i32(eta) if eta is not None else None
+        cells = out if out is not None else np.empty((n, dimension))
+        tp = np.zeros(n, dtype=np.longdouble)
+        fl = np.zeros(n, dtype=np.uint32)
+        p = params._c()
+        _check(lib().qb200_slice1d_compute(
+            self.h, C.byref(p), kind, int(bool(richardson)), dimension, n, a.ctypes.data,
+            e.ctypes.data if e is not None else None, cells.ctypes.data, tp.ctypes.data,
+            fl.ctypes.data), "qb200_slice1d_compute")
+        return cells, tp, fl
+
+    # ---- device-resident plans ------------------------------------------------
+    def plan2d(self, params: Parameters, method: int, richardson: bool, dimension: int,
+               min_log_alpha_d, min_log_alpha_r) -> Plan:
+        a_d, a_r = _i32(min_log_alpha_d), _i32(min_log_alpha_r)
+        h = C.c_void_p()
+        p = params._c()
+        _check(lib().qb200_plan2d_create(
+            self.h, C.byref(p), method, int(bool(richardson)), dimension, len(a_d),
+            a_d.ctypes.data, a_r.ctypes.data, C.byref(h)), "qb200_plan2d_create")
+        return Plan(self, h, len(a_d), dimension, True)
+
+    def plan1d(self, params, kind: int, richardson: bool, dimension: int, min_log_alpha,
+               eta=None) -> Plan:
+        a = _i32(min_log_alpha)
+        e = _i32(eta) if eta is not None else None
+        h = C.c_void_p()
+        p = params._c()
+        _check(lib().qb200_plan1d_create(
+            self.h, C.byref(p), kind, int(bool(richardson)), dimension, len(a),
+            a.ctypes.data, e.ctypes.data if e is not None else None, C.byref(h)),
+            "qb200_plan1d_create")
+        return Plan(self, h, len(a), dimension, False)
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+def heuristic_sigma(l: int) -> int:
+    return int(lib().qb200_heuristic_sigma(l))
+
+
+def host_constants(m: int, l: int, sigma: int, d: int, r: int) -> dict:
+    db, rb = _be(d), _be(r)
+    p = _Params(m, l, sigma, db, len(db), rb, len(rb))
+    out = np.zeros(20)
+    _check(lib().qb200_host_constants(C.byref(p), out.ctypes.data), "qb200_host_constants")
+    names = ["kappa", "kappa_q", "c_over_L", "n_over_L", "n1_over_L", "beta_m", "rbeta_m",
+             "r_m", "d_m", "rho"]
+    return {k: (out[2 * i], out[2 * i + 1]) for i, k in enumerate(names)}
+
+
+# --------------------------------------------------------------------------- #
+# The reference's six entry points                                            #
+# --------------------------------------------------------------------------- #
+
+def _apply_flags(old: int, new_bits: int) -> int:
+    # slice->flags &= ~MASK_METHOD; |= SIMPSON [| RICHARDSON] [| WARNING]
+    # (src/distribution_slice_compute.cpp:413-418, ..._richardson.cpp:69)
+    return (old & ~SLICE_FLAGS_MASK_METHOD) | int(new_bits)
+
+
+def _compute_2d(slice_, parameters, method, a_d, a_r, richardson, ctx):
+    ctx = ctx or default_context()
+    cells, tp, te, fl = ctx.slice2d_batch(parameters, int(method), richardson,
+                                          slice_.dimension, [a_d], [a_r])
+    slice_.norm_matrix[:] = cells[0].astype(np.longdouble)
+    slice_.total_probability = tp[0]
+    slice_.total_error = te[0]
+    slice_.min_log_alpha_d = int(a_d)
+    slice_.min_log_alpha_r = int(a_r)
+    slice_.flags = _apply_flags(slice_.flags, fl[0])
+
+
+def distribution_slice_compute(slice, parameters, method, min_log_alpha_d,
+                               min_log_alpha_r, ctx=None):
+    """src/distribution_slice_compute.cpp:38."""
+    _compute_2d(slice, parameters, method, min_log_alpha_d, min_log_alpha_r, False, ctx)
+
+
+def distribution_slice_compute_richardson(slice, parameters, method, min_log_alpha_d,
+                                          min_log_alpha_r, ctx=None):
+    """src/distribution_slice_compute_richardson.cpp:17."""
+    _compute_2d(slice, parameters, method, min_log_alpha_d, min_log_alpha_r, True, ctx)
+
+
+def _compute_linear(slice_, parameters, target, a, richardson, ctx):
+    if target not in (LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_D,
+                      LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_R):
+        raise CriticalError("linear_distribution_slice_compute(): Unknown target.")
+    ctx = ctx or default_context()
+    cells, tp, fl = ctx.slice1d_batch(parameters, int(target), richardson,
+                                      slice_.dimension, [a])
+    slice_.norm_vector[:] = cells[0].astype(np.longdouble)
+    slice_.total_probability = tp[0]
+    slice_.total_error = np.longdouble(0)
+    slice_.min_log_alpha = int(a)
+    slice_.flags = _apply_flags(slice_.flags, fl[0])
+
+
+def linear_distribution_slice_compute(slice, parameters, target, min_log_alpha, ctx=None):
+    """src/linear_distribution_slice_compute.cpp:30."""
+    _compute_linear(slice, parameters, target, min_log_alpha, False, ctx)
+
+
+def linear_distribution_slice_compute_richardson(slice, parameters, target, min_log_alpha,
+                                                 ctx=None):
+    """src/linear_distribution_slice_compute_richardson.cpp:17."""
+    _compute_linear(slice, parameters, target, min_log_alpha, True, ctx)
+
+
+def _compute_diagonal(slice_, parameters, a_r, eta, richardson, ctx):
+    ctx = ctx or default_context()
+    cells, tp, fl = ctx.slice1d_batch(parameters, KIND_DIAGONAL, richardson,
+                                      slice_.dimension, [a_r], [eta])
+    slice_.norm_vector[:] = cells[0].astype(np.longdouble)
+    slice_.total_probability = tp[0]
+    slice_.total_error = np.longdouble(0)
+    slice_.min_log_alpha_r = int(a_r)
+    slice_.eta = int(eta)
+    slice_.flags = _apply_flags(slice_.flags, fl[0])
+
+
+def diagonal_distribution_slice_compute(slice, parameters, min_log_alpha_r, eta, ctx=None):
+    """src/diagonal_distribution_slice_compute.cpp:30."""
+    _compute_diagonal(slice, parameters, min_log_alpha_r, eta, False, ctx)
+
+
+def diagonal_distribution_slice_compute_richardson(slice, parameters, min_log_alpha_r, eta,
+                                                   ctx=None):
+    """src/diagonal_distribution_slice_compute_richardson.cpp:17."""
+    _compute_diagonal(slice, parameters, min_log_alpha_r, eta, True, ctx)
