@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- slice cells integrated per second at m = 2048 on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8(d) "T2D"): the slice set
+of one two-dimensional Ekera distribution, m = 2048, s = 1 (l = 2048, heuristic
+sigma = 1031), t = 30, synthetic d and r (random.seed(20482048 + rank)); the 3362
+coordinates the generator client integrates (|alpha| from m - 30 to m + 10, both
+signs of alpha_d) in enumerator order, at `-dim 256` (dimension D = 128 with the
+Richardson pass at 256): 16,384 cells and 329,218 reference integrand
+evaluations per slice; 55.08 M cells per step and per GPU.
+
+A step is one pass of the hot path over that batch. Slices are independent, so
+for N > 1 every rank integrates one such distribution (weak scaling, no
+data-path collective); only the per-slice summaries are gathered on rank 0.
+
+`value`   : device-resident throughput (descriptors and tables in HBM, results
+            left in HBM), CUDA events on the launching stream, max over ranks.
+`e2e`     : the same through the synchronous C-ABI call with host buffers:
+            coordinates H2D, kernels, all cells + summaries D2H into pinned host
+            memory, inside the timed region.
+`roofline`: FP64-pipe bound. achieved = cells/s x 1600 algorithmic FP64 flop per
+            cell (20.09 evaluations x 80 flop) over the
+            FP64 FMA peak measured on the same GPU by a register-resident DFMA
+            loop (MEASURED_PEAKS.json holds no FP64 figure). The kernel executes
+            fewer flops than the canonical count (separable angle addition, see
+            DESIGN.md), so `frac` can exceed 1; `executed_frac` is the share of
+            the FP64 pipe actually used (from the committed ncu capture).
+`cpu_baseline` / --impl reference: the UNMODIFIED reference
+            (oracle/_ref/libqref.so, distribution_slice_compute_richardson with
+            192-bit MPFR) on the host cores, one slice per worker process.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+M, S, T_PARAM, DIM = 2048, 1, 30, 128
+FLOP_PER_CELL = 1600.0
+EVALS_PER_SLICE_REF = (2 * DIM + 1) ** 2 + (4 * DIM + 1) ** 2
+METRIC = "slice cells integrated/sec at m=2048"
+
+
+def synthetic_d_r(seed: int):
+    rnd = random.Random(seed)
+    r = 2 ** (M - 1) + 1 + rnd.randrange(2 ** (M - 1) - 1)
+    d = r // 2 + rnd.randrange(r // 2)
+    return d, r
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": ("generate_distribution (2D alpha_d, alpha_r), heuristic sigma, Richardson: "
+                     "m=2048 s=1 l=2048 sigma=1031 t=30, 3362 slices (|alpha| in [m-30, m+10], "
+                     "both signs of alpha_d) at -dim 256 (D=128 + 256): 55,083,008 cells per "
+                     "step per GPU"),
+        "cells_per_step_per_gpu": 3362 * DIM * DIM,
+        "slices_per_step_per_gpu": 3362,
+        "dimension": DIM,
+        "sharding": f"one distribution per rank x {n_gpus} ranks, no data-path collective",
+        "l2": ("results 440.7 MB per step exceed the 126 MB L2; inputs are ~5 MB of axis "
+               "tables rebuilt on the device every step"),
+    }
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference (oracle/_ref) farm -- the ONLY place bench.py touches oracle/
+# --------------------------------------------------------------------------------------
+def _ref_worker(args):
+    seed, coords = args
+    from oracle import ref
+    d, r = synthetic_d_r(seed)
+    P = ref.RefParameters(M, S, d, r, T_PARAM)
+    t0 = time.perf_counter()
+    n = 0
+    for (a, b) in coords:
+        sl = ref.distribution_slice_compute(P, DIM, a, b)
+        n += sl.cells.size
+    return n, time.perf_counter() - t0
+
+
+def reference_cpu_pass(pool, cores, coords, slices_per_core=1):
+    """One bounded sample: every worker integrates `slices_per_core` slices of the
+    workload (in enumerator order) with the reference's own code."""
+    jobs = []
+    for k in range(cores):
+        sl = coords[k * slices_per_core:(k + 1) * slices_per_core]
+        jobs.append((20482048, sl))
+    t0 = time.perf_counter()
+    res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall
+
+
+def host_cores():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get("QB200_CPU_CORES", "256"))))
+
+
+def run_reference_arm(args, rank):
+    import multiprocessing as mp
+    from oracle import ref
+    from qunundrum_b200 import shard
+    if rank != 0:
+        return
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "oracle/_ref/libqref.so was not built (no /root/reference at build time)"}))
+        return
+    coords = shard.enumerate_2d(M)
+    cores = host_cores()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pass  # nothing to warm: every slice is an independent cold computation
+        t0 = time.perf_counter()
+        cells = 0
+        for _ in range(args.steps):
+            c, _ = reference_cpu_pass(pool, cores, coords, 1)
+            cells += c
+        wall = time.perf_counter() - t0
+    value = cells / wall
+    sample = (f"{cores} slices per step (one per worker process, first {cores} of the enumerator "
+              f"order) x {args.steps} steps, D=128 Richardson, 192-bit MPFR")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall / max(1, args.steps) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "mpfr192", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "reference",
+                         "sample": sample, "cells_per_s_per_core": value / cores},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def profile_constants():
+    """DRAM traffic and FP64-pipe share of the dominant kernel from the committed ncu
+    capture (profiles/fused2d_latest.json), or None."""
+    p = os.path.join(ROOT, "profiles", "fused2d_latest.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import qunundrum_b200 as qb
+    from qunundrum_b200 import shard
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the slice integrators have no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ctx = qb.Context(local_rank)
+    d, r = synthetic_d_r(20482048 + rank)
+    P = qb.Parameters(M, S, d, r, T_PARAM)
+    coords = shard.enumerate_2d(M)
+    a_d = np.array([c[0] for c in coords], dtype=np.int32)
+    a_r = np.array([c[1] for c in coords], dtype=np.int32)
+    n = len(coords)
+
+    # ---- device-resident timing --------------------------------------------------------
+    plan = ctx.plan2d(P, qb.DISTRIBUTION_SLICE_COMPUTE_METHOD_HEURISTIC_SIGMA, True, DIM, a_d, a_r)
+    if plan.algorithm != 2:
+        raise SystemExit("bench.py: the fused kernel was not selected")
+    cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
+    summ = torch.empty(n * 8, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    peak_flops = ctx.measure_fp64_peak()
+    for _ in range(max(3, args.warmup)):
+        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    # keep the clocks record meaningful for short runs: sample a little longer under load
+    t_end = time.perf_counter() + 0.6
+    while time.perf_counter() < t_end:
+        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    total_cells = plan.cells * world
+    value = total_cells / (ms_per_step * 1e-3)
+
+    # results sanity (and the only cross-rank traffic): gather the slice summaries
+    table = shard.gather_summaries(np.arange(n), summ.cpu().numpy().reshape(n, 8), n)
+    tp, te, fl = plan.finish(summ.cpu().numpy())
+    mass = float(tp.sum())
+    if not (0.4999 < mass < 0.5):
+        raise SystemExit(f"bench.py: captured mass {mass} is wrong")
+
+    # ---- end to end through the synchronous C ABI with host buffers ------------------
+    import ctypes as C
+    L = qb.lib()
+    nbytes = plan.cells * 8
+    hptr = L.qb200_host_alloc(nbytes)
+    if not hptr:
+        raise SystemExit("bench.py: pinned host allocation failed")
+    h_cells = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(n, DIM * DIM))
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(2):
+        ctx.slice2d_batch(P, 0, True, DIM, a_d, a_r, out=h_cells)
+    barrier()
+    l1 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _, tp2, te2, fl2 = ctx.slice2d_batch(P, 0, True, DIM, a_d, a_r, out=h_cells)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    e2e_launches = ctx.launch_count - l1
+    tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    e2e_value = total_cells * e2e_steps / wall
+    if abs(float(tp2.sum()) - mass) > 1e-13 or abs(h_cells.sum() - mass) > 1e-9:
+        raise SystemExit("bench.py: end-to-end results differ from the device-resident run")
+    h2d = a_d.nbytes + a_r.nbytes + 2 * ((M + 7) // 8) + 3362 * 40  # coords, d, r, descriptors
+    d2h = nbytes + n * 8 * 8
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import multiprocessing as mp
+            from oracle import ref
+            if ref.available():
+                cores = host_cores()
+                with mp.get_context("fork").Pool(cores) as pool:
+                    c, w = reference_cpu_pass(pool, cores, coords, 1)
+                cpu = {"value": c / w, "unit": "cells/s", "cores": cores, "kind": "reference",
+                       "sample": (f"{cores} slices (one per worker process; the first {cores} of the "
+                                  f"enumerator order), D=128 Richardson, 192-bit MPFR, {w:.1f} s wall"),
+                       "cells_per_s_per_core": c / w / cores}
+        except Exception as exc:  # pragma: no cover
+            cpu = {"value": None, "unit": "cells/s", "cores": 0, "kind": "reference",
+                   "sample": f"failed: {exc}"}
+
+    L.qb200_host_free(C.c_void_p(hptr))
+    if dist is not None:
+        dist.barrier()
+
+    if rank == 0:
+        prof = profile_constants() or {}
+        achieved = (plan.cells / (ms_per_step * 1e-3)) * FLOP_PER_CELL / 1e12  # per GPU
+        peak = peak_flops / 1e12
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        out_gbs = nbytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world),
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
+                "kernel": "k_fused2d<0,1,0,0>",
+                "flop_per_cell": FLOP_PER_CELL,
+                "peak_source": "DFMA microkernel measured in this run on this GPU "
+                               "(MEASURED_PEAKS.json has no FP64 entry)",
+                "executed_frac": prof.get("fp64_pipe_active_frac"),
+                "executed_fp64_inst_per_cell": prof.get("fp64_inst_per_cell"),
+                "hbm": {"algorithmic_gbs": out_gbs, "peak_gbs": hbm_peak, "frac": out_gbs / hbm_peak,
+                        "peak_source": hbm_src},
+                "note": "per GPU; step time includes the three small table/summary kernels (<1.5%)",
+            },
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "ms_per_step": wall / e2e_steps * 1e3,
+                    "api": "qb200_slice2d_compute (synchronous C ABI, pinned host result buffer)"},
+            "gpu_launches": int(launches),
+            "e2e_gpu_launches": int(e2e_launches),
+            "clocks": clocks,
+            "captured_mass_per_distribution": mass,
+            "gathered_summaries": None if table is None else int(table.shape[0]),
+        }
+        print(json.dumps(line))
+    plan.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch ourselves under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        if args.no_cpu_baseline:
+            cmd.append("--no-cpu-baseline")
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

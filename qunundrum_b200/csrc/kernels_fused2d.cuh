@@ -176,31 +176,82 @@ __device__ __forceinline__ double rcp_seed(double w) {
 }
 
 // pi^2 * T1 at one point: (sin(pi u) / u)^2 [* 1 / sinc^2(pi u / Lambda)].
+// Branch-free main path (valid for |u| >= 1/16); the caller patches the rare
+// small-|u| points with eval_small(), one test per column, so that the
+// independent evaluations of a column interleave in the FP64 pipe.
 template <int MODE>
-__device__ __forceinline__ double eval_t1(const RowReg& r, const ColRec& c, const FusedConst& k) {
+__device__ __forceinline__ double eval_main(const RowReg& r, const ColRec& c, const FusedConst& k,
+                                            double& u_out) {
   const double S = fma(r.sd, c.cr, r.cd * c.sr);
   const double u = (r.xh + c.yh) + (r.xl + c.yl);
-  const double w = u * u;
-  double T;
-  if ((__double2hiint(u) & 0x7fffffff) < 0x3FB00000) {  // |u| < 1/16
-    // pi sinc(pi u) = sum (-1)^k pi^(2k+1) / (2k+1)! w^k
-    double p = 4.6630280576761256442e-4;
-    p = fma(p, w, -7.3704309457143507773e-3);
-    p = fma(p, w, 8.2145886611128228799e-2);
-    p = fma(p, w, -5.9926452932079207689e-1);
-    p = fma(p, w, 2.5501640398773454439);
-    p = fma(p, w, -5.1677127800499700292);
-    p = fma(p, w, 3.1415926535897932385);
-    T = p * p;
-  } else {
-    const double r0 = rcp_seed(w);
-    const double e = fma(-w, r0, 1.0);
-    const double rr = fma(r0, fma(e, e, e), r0);
-    T = (S * S) * rr;
+  const double r0 = rcp_seed(u);
+  const double e = fma(-u, r0, 1.0);
+  const double rr = fma(r0, fma(e, e, e), r0);
+  const double q = S * rr;
+  double T = q * q;
+  if (MODE == 1) {
+    const double w = u * u;
+    T *= fma(w, fma(w, fma(w, k.c3, k.c2), k.c1), 1.0);
   }
+  u_out = u;
+  return T;
+}
+
+__device__ __forceinline__ unsigned abs_hi(double u) {
+  return (unsigned)__double2hiint(u) & 0x7fffffffu;
+}
+#define QB_SMALL_U 0x3FB00000u  // |u| < 1/16
+
+template <int MODE>
+__device__ __forceinline__ double eval_small(double u, const FusedConst& k) {
+  // pi sinc(pi u) = sum (-1)^k pi^(2k+1) / (2k+1)! w^k, |u| < 1/16
+  const double w = u * u;
+  double p = 4.6630280576761256442e-4;
+  p = fma(p, w, -7.3704309457143507773e-3);
+  p = fma(p, w, 8.2145886611128228799e-2);
+  p = fma(p, w, -5.9926452932079207689e-1);
+  p = fma(p, w, 2.5501640398773454439);
+  p = fma(p, w, -5.1677127800499700292);
+  p = fma(p, w, 3.1415926535897932385);
+  double T = p * p;
   if (MODE == 1) T *= fma(w, fma(w, fma(w, k.c3, k.c2), k.c1), 1.0);
   return T;
 }
+
+// Evaluate one column against up to five rows.
+#define QB_EVAL4(c_, T0, T1, T2, T3)                                                      \
+  double T0, T1, T2, T3;                                                                  \
+  {                                                                                       \
+    double u0_, u1_, u2_, u3_;                                                            \
+    T0 = eval_main<MODE>(r0, c_, k, u0_);                                                 \
+    T1 = eval_main<MODE>(r1, c_, k, u1_);                                                 \
+    T2 = eval_main<MODE>(r2, c_, k, u2_);                                                 \
+    T3 = eval_main<MODE>(r3, c_, k, u3_);                                                 \
+    if (min(min(abs_hi(u0_), abs_hi(u1_)), min(abs_hi(u2_), abs_hi(u3_))) < QB_SMALL_U) { \
+      if (abs_hi(u0_) < QB_SMALL_U) T0 = eval_small<MODE>(u0_, k);                        \
+      if (abs_hi(u1_) < QB_SMALL_U) T1 = eval_small<MODE>(u1_, k);                        \
+      if (abs_hi(u2_) < QB_SMALL_U) T2 = eval_small<MODE>(u2_, k);                        \
+      if (abs_hi(u3_) < QB_SMALL_U) T3 = eval_small<MODE>(u3_, k);                        \
+    }                                                                                     \
+  }
+#define QB_EVAL1(row_, c_, T)                                        \
+  double T;                                                          \
+  {                                                                  \
+    double u_;                                                       \
+    T = eval_main<MODE>(row_, c_, k, u_);                            \
+    if (abs_hi(u_) < QB_SMALL_U) T = eval_small<MODE>(u_, k);        \
+  }
+#define QB_EVAL2(rowa_, rowb_, c_, Ta, Tb)                            \
+  double Ta, Tb;                                                      \
+  {                                                                   \
+    double ua_, ub_;                                                  \
+    Ta = eval_main<MODE>(rowa_, c_, k, ua_);                          \
+    Tb = eval_main<MODE>(rowb_, c_, k, ub_);                          \
+    if (min(abs_hi(ua_), abs_hi(ub_)) < QB_SMALL_U) {                 \
+      if (abs_hi(ua_) < QB_SMALL_U) Ta = eval_small<MODE>(ua_, k);    \
+      if (abs_hi(ub_) < QB_SMALL_U) Tb = eval_small<MODE>(ub_, k);    \
+    }                                                                 \
+  }
 
 struct FusedArgs {
   FusedConst k;
@@ -260,9 +311,12 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
     const ColRec c3 = load_col(cp + 3 * QB_FUSED_REC);
     const ColRec cm = load_col(cp + 4 * QB_FUSED_REC);
     const ColRec c4 = load_col(cp + 5 * QB_FUSED_REC);
-    const double T0 = eval_t1<MODE>(rh, c0, k), T1 = eval_t1<MODE>(rh, c1, k);
-    const double T2 = eval_t1<MODE>(rh, c2, k), T3 = eval_t1<MODE>(rh, c3, k);
-    const double Tm = eval_t1<MODE>(rh, cm, k), T4 = eval_t1<MODE>(rh, c4, k);
+    QB_EVAL1(rh, c0, T0)
+    QB_EVAL1(rh, c1, T1)
+    QB_EVAL1(rh, c2, T2)
+    QB_EVAL1(rh, c3, T3)
+    QB_EVAL1(rh, cm, Tm)
+    QB_EVAL1(rh, c4, T4)
     const double HF = fma(c4.wF2, T4, fma(c3.wF, T3, fma(c2.wF, T2, fma(c1.wF, T1, c0.wF * T0))));
     const double HC = fma(c4.wC2, T4, fma(cm.wC, Tm, c0.wC * T0));
     s_halo[warp][0][lane] = HF;
@@ -332,9 +386,8 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
   {
     // first column of the tile: starts cell J0
     const ColRec c = load_col(cp);
-    const double T0 = eval_t1<MODE>(r0, c, k), T1 = eval_t1<MODE>(r1, c, k);
-    const double T2 = eval_t1<MODE>(r2, c, k), T3 = eval_t1<MODE>(r3, c, k);
-    const double Tm = eval_t1<MODE>(rc, c, k);
+    QB_EVAL4(c, T0, T1, T2, T3)
+    QB_EVAL1(rc, c, Tm)
     sF0 = c.wF * T0; sF1 = c.wF * T1; sF2 = c.wF * T2; sF3 = c.wF * T3;
     sC0 = c.wC * T0; sCm = c.wC * Tm;
     if (HAS_ERR) {
@@ -358,8 +411,7 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
     for (int q = 1; q <= 3; q++) {  // fine interior columns
       const ColRec c = load_col(cp);
       cp += QB_FUSED_REC;
-      const double T0 = eval_t1<MODE>(r0, c, k), T1 = eval_t1<MODE>(r1, c, k);
-      const double T2 = eval_t1<MODE>(r2, c, k), T3 = eval_t1<MODE>(r3, c, k);
+      QB_EVAL4(c, T0, T1, T2, T3)
       sF0 = fma(c.wF, T0, sF0); sF1 = fma(c.wF, T1, sF1);
       sF2 = fma(c.wF, T2, sF2); sF3 = fma(c.wF, T3, sF3);
       if (HAS_ERR) {
@@ -376,7 +428,7 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
     {  // coarse mid column
       const ColRec c = load_col(cp);
       cp += QB_FUSED_REC;
-      const double T0 = eval_t1<MODE>(r0, c, k), Tm = eval_t1<MODE>(rc, c, k);
+      QB_EVAL2(r0, rc, c, T0, Tm)
       sC0 = fma(c.wC, T0, sC0); sCm = fma(c.wC, Tm, sCm);
       if (HAS_ERR) {
         const double wcb = c.wC * c.b;
@@ -391,9 +443,8 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
     }
     {  // boundary column: closes cell J0 + jj, opens the next one
       const ColRec c = load_col(cp);
-      const double T0 = eval_t1<MODE>(r0, c, k), T1 = eval_t1<MODE>(r1, c, k);
-      const double T2 = eval_t1<MODE>(r2, c, k), T3 = eval_t1<MODE>(r3, c, k);
-      const double Tm = eval_t1<MODE>(rc, c, k);
+      QB_EVAL4(c, T0, T1, T2, T3)
+      QB_EVAL1(rc, c, Tm)
       sF0 = fma(c.wF2, T0, sF0); sF1 = fma(c.wF2, T1, sF1);
       sF2 = fma(c.wF2, T2, sF2); sF3 = fma(c.wF2, T3, sF3);
       sC0 = fma(c.wC2, T0, sC0); sCm = fma(c.wC2, Tm, sCm);

@@ -84,6 +84,7 @@ struct qb200_plan {
   DevBuf desc_a, desc_b, slices, tab_a, tab_b;
   // plain path scratch (per chunk of slices)
   uint32_t chunk = 0;
+  bool plain_ready = false;
   DevBuf cells_c, cells_f, part_c, part_f, part_tp, values;
   // fused path
   FusedPlan2D fused;
@@ -186,6 +187,10 @@ int reserve_plain(qb200_plan* pl) {
 }
 
 int run_plain_2d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_summary) {
+  if (!pl->plain_ready) {
+    if (int rc = reserve_plain(pl)) return rc;
+    pl->plain_ready = true;
+  }
   const Plan& h = pl->host;
   qb200_context* ctx = pl->ctx;
   const int D = h.D;
@@ -228,6 +233,10 @@ int run_plain_2d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_sum
 }
 
 int run_plain_1d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_summary) {
+  if (!pl->plain_ready) {
+    if (int rc = reserve_plain(pl)) return rc;
+    pl->plain_ready = true;
+  }
   const Plan& h = pl->host;
   qb200_context* ctx = pl->ctx;
   const int D = h.D;
@@ -250,15 +259,26 @@ int run_plain_1d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_sum
   return 0;
 }
 
+uint32_t plain_chunk(const qb200_plan* pl) {
+  const Plan& h = pl->host;
+  const size_t D = (size_t)h.D;
+  const size_t per_slice = h.kind < 0 ? 5 * D * D * sizeof(double)
+                                      : (size_t)table_points(h.D) * sizeof(double);
+  const size_t budget = h.kind < 0 ? (size_t(1) << 30) : (size_t(1) << 28);
+  size_t chunk = std::max<size_t>(1, budget / per_slice);
+  chunk = std::min<size_t>(chunk, std::max<uint32_t>(1, pl->n));
+  return (uint32_t)std::min<size_t>(chunk, 65535);
+}
+
 uint32_t plain_launches(const qb200_plan* pl) {
-  const uint32_t chunks = pl->n ? (pl->n + pl->chunk - 1) / pl->chunk : 0;
+  const uint32_t ch = plain_chunk(pl);
+  const uint32_t chunks = pl->n ? (pl->n + ch - 1) / ch : 0;
   if (pl->host.kind < 0) return (pl->n ? 1 : 0) + chunks * (pl->host.richardson ? 4 : 3);
   return chunks * 3;
 }
 
 int finish_common(qb200_plan* pl) {
   if (int rc = upload_plan(pl)) return rc;
-  if (int rc = reserve_plain(pl)) return rc;
   pl->fused_ok = 0;
   if (pl->host.kind < 0) {
     pl->fused_ok = fused2d_prepare(pl->host, pl->ctx->sm_count, &pl->fused, &pl->fused_why) ? 1 : 0;

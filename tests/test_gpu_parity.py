@@ -1,0 +1,217 @@
+"""Parity of the CUDA path (through the C ABI) with the reference -- needs a B200.
+
+ * every cell of every committed golden slice (tests/golden/slices.npz, produced by
+   the UNMODIFIED reference): <= 1e-9 relative per cell, <= 1e-12 on the slice's
+   probability mass, total_error <= 1e-9 relative, flags exact;
+ * the same against the reference itself run on this box when oracle/_ref travelled;
+ * the fused kernel against the plain one-thread-per-cell kernels;
+ * at BASELINE.json's full size (the 3362-slice m = 2048 set at dimension 128):
+   determinism, batch-composition invariance, Richardson identity, captured mass.
+"""
+import numpy as np
+import pytest
+
+import qunundrum_b200 as qb
+from qunundrum_b200 import shard
+from tests.conftest import golden_slices, ref_or_none
+from tests.util import CELL_RTOL, assert_slice_matches, cell_errors, group_by
+
+pytestmark = pytest.mark.gpu
+
+G = golden_slices()
+G2D = group_by([g for g in G if g.meta["kind"] == "2d"], ["m", "s", "l", "D", "richardson", "method", "d", "r"])
+GLIN = group_by([g for g in G if g.meta["kind"] == "lin"], ["m", "s", "l", "D", "richardson", "target", "d", "r"])
+GDIAG = group_by([g for g in G if g.meta["kind"] == "diag"], ["m", "s", "l", "sigma", "D", "richardson", "d", "r"])
+
+
+def _run_plan(plan, algo):
+    import torch
+    plan.set_algorithm(algo)
+    cells = torch.empty(max(1, plan.cells), dtype=torch.float64, device="cuda")
+    summ = torch.empty(max(1, plan.n * 8), dtype=torch.float64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        plan.run(cells.data_ptr(), summ.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    tp, te, fl = plan.finish(summ.cpu().numpy()[:plan.n * 8])
+    return cells.cpu().numpy()[:plan.cells].reshape(plan.n, -1), tp, te, fl
+
+
+def test_extension_is_loaded_and_device_is_blackwell(gpu_ctx):
+    assert qb.lib().qb200_device_count() >= 1
+    assert gpu_ctx.measure_fp64_peak() > 1e12
+
+
+@pytest.mark.parametrize("key", list(G2D), ids=lambda k: f"m{k[0]}-s{k[1]}-D{k[3]}-R{k[4]}-meth{k[5]}")
+def test_2d_golden(gpu_ctx, key):
+    m, s, l, D, rich, method, d, r = key
+    gs = G2D[key]
+    P = qb.Parameters(m, s, int(d), int(r), l=0 if s else l)
+    cells, tp, te, fl = gpu_ctx.slice2d_batch(P, method, bool(rich), D,
+                                              [g.meta["a_d"] for g in gs], [g.meta["a_r"] for g in gs])
+    for i, g in enumerate(gs):
+        assert_slice_matches(cells[i], tp[i], te[i], fl[i], g)
+
+
+@pytest.mark.parametrize("key", [k for k in G2D if k[4] == 1 and k[3] % 32 == 0],
+                         ids=lambda k: f"m{k[0]}-s{k[1]}-D{k[3]}-meth{k[5]}")
+def test_2d_fused_and_plain_agree_with_golden(gpu_ctx, key):
+    m, s, l, D, rich, method, d, r = key
+    gs = G2D[key]
+    P = qb.Parameters(m, s, int(d), int(r))
+    plan = gpu_ctx.plan2d(P, method, True, D, [g.meta["a_d"] for g in gs], [g.meta["a_r"] for g in gs])
+    assert plan.algorithm == 2, "the fused kernel must be the default for these shapes"
+    outs = {algo: _run_plan(plan, algo) for algo in (1, 2)}
+    for algo, (cells, tp, te, fl) in outs.items():
+        for i, g in enumerate(gs):
+            assert_slice_matches(cells[i], tp[i], te[i], fl[i], g)
+    assert cell_errors(outs[2][0], outs[1][0]) <= 1e-10
+    plan.close()
+
+
+@pytest.mark.parametrize("key", list(GLIN), ids=lambda k: f"m{k[0]}-s{k[1]}-D{k[3]}-R{k[4]}-t{k[5]}")
+def test_linear_golden(gpu_ctx, key):
+    m, s, l, D, rich, target, d, r = key
+    gs = GLIN[key]
+    P = qb.Parameters(m, s, int(d), int(r))
+    cells, tp, fl = gpu_ctx.slice1d_batch(P, target, bool(rich), D, [g.meta["a"] for g in gs])
+    for i, g in enumerate(gs):
+        assert_slice_matches(cells[i], tp[i], 0, fl[i], g)
+
+
+@pytest.mark.parametrize("key", list(GDIAG), ids=lambda k: f"m{k[0]}-sigma{k[3]}-D{k[4]}")
+def test_diagonal_golden(gpu_ctx, key):
+    m, s, l, sigma, D, rich, d, r = key
+    gs = GDIAG[key]
+    P = qb.Diagonal_Parameters(m, sigma, s, int(d), int(r), eta_bound=25)
+    cells, tp, fl = gpu_ctx.slice1d_batch(P, 2, bool(rich), D, [g.meta["a"] for g in gs],
+                                          [g.meta["eta"] for g in gs])
+    for i, g in enumerate(gs):
+        assert_slice_matches(cells[i], tp[i], 0, fl[i], g)
+
+
+def test_reference_entry_points(gpu_ctx):
+    """The six entry points with the reference's calling convention (host mirror)."""
+    g = next(x for x in G if x.meta["name"].startswith("2d/c1/130_129"))
+    P = qb.Parameters(g.meta["m"], g.meta["s"], g.d, g.r)
+    sl = qb.Distribution_Slice(g.meta["D"])
+    sl.flags = 0x00000100 | 0x00040000  # other bits survive, stale method bits do not
+    qb.distribution_slice_compute_richardson(sl, P, 0, 130, 129, ctx=gpu_ctx)
+    assert sl.flags == (0x00000100 | g.flags) and (sl.min_log_alpha_d, sl.min_log_alpha_r) == (130, 129)
+    assert cell_errors(sl.norm_matrix, g.cells) <= CELL_RTOL
+    assert sl.norm_matrix.dtype == np.longdouble
+    assert abs(float(sl.total_probability - np.sum(sl.norm_matrix))) < 1e-15
+
+    g = next(x for x in G if x.meta["name"] == "2d/c2s/2040_2041")      # single pass
+    sl = qb.Distribution_Slice(g.meta["D"])
+    qb.distribution_slice_compute(sl, qb.Parameters(2048, 1, g.d, g.r), 0, 2040, 2041, ctx=gpu_ctx)
+    assert sl.flags == g.flags == qb.SLICE_FLAGS_METHOD_SIMPSON
+    assert cell_errors(sl.norm_matrix, g.cells) <= CELL_RTOL
+
+    g = next(x for x in G if x.meta["name"] == "lin/c1/t0/-130")
+    ls = qb.Linear_Distribution_Slice(g.meta["D"])
+    qb.linear_distribution_slice_compute_richardson(ls, qb.Parameters(128, 2, g.d, g.r), 0, -130, ctx=gpu_ctx)
+    assert cell_errors(ls.norm_vector, g.cells) <= CELL_RTOL and ls.total_error == 0 and ls.min_log_alpha == -130
+    g = next(x for x in G if x.meta["name"] == "lin/single/t1/127")
+    ls = qb.Linear_Distribution_Slice(g.meta["D"])
+    qb.linear_distribution_slice_compute(ls, qb.Parameters(128, 2, g.d, g.r), 1, 127, ctx=gpu_ctx)
+    assert cell_errors(ls.norm_vector, g.cells) <= CELL_RTOL and ls.flags == g.flags
+
+    g = next(x for x in G if x.meta["name"] == "diag/m128/126_-1")
+    ds = qb.Diagonal_Distribution_Slice(g.meta["D"])
+    qb.diagonal_distribution_slice_compute_richardson(
+        ds, qb.Diagonal_Parameters(128, 5, 1, g.d, g.r, eta_bound=25), 126, -1, ctx=gpu_ctx)
+    assert cell_errors(ds.norm_vector, g.cells) <= CELL_RTOL and ds.eta == -1 and ds.min_log_alpha_r == 126
+
+    with pytest.raises(qb.CriticalError, match="OPTIMAL_LOCAL_SIGMA"):
+        qb.distribution_slice_compute_richardson(qb.Distribution_Slice(32), P, 1, 130, 129, ctx=gpu_ctx)
+    with pytest.raises(qb.CriticalError, match="Unknown target"):
+        qb.linear_distribution_slice_compute(qb.Linear_Distribution_Slice(32), P, 3, 128, ctx=gpu_ctx)
+
+
+def test_against_reference_on_this_box(gpu_ctx):
+    """oracle/_ref travels with the snapshot: fresh coordinates, not in the fixtures."""
+    ref = ref_or_none()
+    if ref is None:
+        pytest.skip("oracle/_ref/libqref.so not present")
+    rng = np.random.default_rng(7)
+    for (m, s, D) in ((2048, 1, 32), (128, 2, 32), (3072, 4, 32), (512, 3, 20)):
+        d, r = ref.deterministic_d_r(m)
+        P, RP = qb.Parameters(m, s, d, r), ref.RefParameters(m, s, d, r)
+        ad = [int(x) for x in rng.integers(m - 12, m + 11, 3) * rng.choice([-1, 1], 3)]
+        ar = [int(x) for x in rng.integers(m - 12, m + 11, 3)]
+        cells, tp, te, fl = gpu_ctx.slice2d_batch(P, 0, True, D, ad, ar)
+        for i in range(3):
+            R = ref.distribution_slice_compute(RP, D, ad[i], ar[i])
+            assert cell_errors(cells[i], R.cells) <= CELL_RTOL, (m, ad[i], ar[i])
+            assert abs(float(tp[i] - R.total_probability)) <= 1e-12
+            assert abs(float((te[i] - R.total_error) / R.total_error)) <= 1e-9
+            assert int(fl[i]) == R.flags
+        a1 = [int(x) for x in rng.integers(m - 25, m + 11, 3) * rng.choice([-1, 1], 3)]
+        for target in (1,) if m > 1024 else (0, 1):
+            c1, tp1, f1 = gpu_ctx.slice1d_batch(P, target, True, 64, a1)
+            for i in range(3):
+                R = ref.linear_distribution_slice_compute(RP, 64, a1[i], target)
+                assert cell_errors(c1[i], R.cells) <= CELL_RTOL and abs(float(tp1[i] - R.total_probability)) <= 1e-12
+
+
+# ---- full-size properties --------------------------------------------------------------
+
+def _t2d_params():
+    import random
+    rnd = random.Random(20482048)
+    m = 2048
+    r = 2 ** (m - 1) + 1 + rnd.randrange(2 ** (m - 1) - 1)
+    d = r // 2 + rnd.randrange(r // 2)
+    return qb.Parameters(m, 1, d, r)
+
+
+def test_full_size_properties(gpu_ctx):
+    P = _t2d_params()
+    coords = shard.enumerate_2d(2048)
+    ad = [c[0] for c in coords]
+    ar = [c[1] for c in coords]
+    D = 128
+    plan = gpu_ctx.plan2d(P, 0, True, D, ad, ar)
+    assert plan.cells == 3362 * D * D and plan.algorithm == 2
+    c_a, tp_a, te_a, fl_a = _run_plan(plan, 2)
+    c_b, tp_b, te_b, fl_b = _run_plan(plan, 2)
+    # determinism: bit-identical re-run
+    assert np.array_equal(c_a, c_b) and np.array_equal(tp_a, tp_b) and np.array_equal(te_a, te_b)
+    # the slice's total is the sum of its cells
+    assert np.max(np.abs(c_a.sum(axis=1) - tp_a.astype(np.float64))) < 1e-15
+    # captured mass: alpha_r > 0 half of the distribution
+    mass = float(tp_a.sum())
+    assert 0.4999 < mass < 0.5, mass
+    assert np.all(fl_a == (qb.SLICE_FLAGS_METHOD_SIMPSON | qb.SLICE_FLAGS_METHOD_RICHARDSON))
+    assert np.all(te_a > 0) and np.all(np.isfinite(c_a))
+    # batch-composition invariance (bit-exact) and fused == plain on a sample
+    sample = list(range(0, len(coords), 97))
+    sub = gpu_ctx.plan2d(P, 0, True, D, [ad[i] for i in sample], [ar[i] for i in sample])
+    c_s, tp_s, te_s, _ = _run_plan(sub, 2)
+    assert np.array_equal(c_s, c_a[sample]) and np.array_equal(tp_s, tp_a[sample])
+    c_p, tp_p, te_p, _ = _run_plan(sub, 1)
+    assert cell_errors(c_s, c_p) <= 1e-10
+    assert np.max(np.abs((tp_s - tp_p).astype(np.float64))) <= 1e-14
+    assert np.max(np.abs(((te_s - te_p) / te_p).astype(np.float64))) <= 1e-10
+    # Richardson identity from two single passes (src/distribution_slice_compute_richardson.cpp:47-64)
+    k = sample[3]
+    co, _, _, _ = gpu_ctx.slice2d_batch(P, 0, False, D, [ad[k]], [ar[k]])
+    fi, _, _, _ = gpu_ctx.slice2d_batch(P, 0, False, 2 * D, [ad[k]], [ar[k]])
+    f = fi[0].reshape(2 * D, 2 * D)
+    four = f[0::2, 0::2] + f[0::2, 1::2] + f[1::2, 0::2] + f[1::2, 1::2]
+    rich = 2 * four.reshape(-1) - co[0]
+    assert cell_errors(c_a[k], rich) <= 1e-10
+    plan.close()
+    sub.close()
+
+
+def test_empty_and_ragged_batches(gpu_ctx):
+    P = _t2d_params()
+    cells, tp, te, fl = gpu_ctx.slice2d_batch(P, 0, True, 32, [], [])
+    assert cells.shape == (0, 1024) and len(tp) == 0
+    # one slice, odd dimension, single pass and Richardson agree with the plain identity
+    c1, tp1, _, _ = gpu_ctx.slice2d_batch(P, 2, True, 7, [2048], [2047])
+    assert c1.shape == (1, 49) and abs(float(tp1[0]) - c1.sum()) < 1e-16
+    c2, tp2, f2 = gpu_ctx.slice1d_batch(P, 1, True, 1, [2048])
+    assert c2.shape == (1, 1) and float(tp2[0]) == c2[0, 0]

@@ -27,7 +27,9 @@ def run_plan(plan, algo):
     plan.set_algorithm(algo)
     cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
     summ = torch.empty(plan.n * 8, dtype=torch.float64, device="cuda")
-    plan.run(cells.data_ptr(), summ.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    s_ = torch.cuda.Stream()
+    with torch.cuda.stream(s_):
+        plan.run(cells.data_ptr(), summ.data_ptr(), s_.cuda_stream)
     torch.cuda.synchronize()
     tp, te, fl = plan.finish(summ.cpu().numpy())
     return cells.cpu().numpy().reshape(plan.n, -1), tp, te, fl
@@ -110,7 +112,9 @@ out["plan_create_s"] = time.time() - t0
 print("plan create", out["plan_create_s"], "algo", plan.algorithm, "cells", plan.cells, flush=True)
 cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
 summ = torch.empty(plan.n * 8, dtype=torch.float64, device="cuda")
-st = torch.cuda.current_stream().cuda_stream
+tstream = torch.cuda.Stream()
+torch.cuda.set_stream(tstream)
+st = tstream.cuda_stream
 for algo in (2,):
     plan.set_algorithm(algo)
     for _ in range(3):
