@@ -59,20 +59,36 @@ struct FusedConst {
   double c1, c2, c3;   // 1/sinc^2(z) = 1 + c1 w + c2 w^2 + c3 w^3, w = u^2, z = pi u / Lambda
   double cs, e0s, r_m; // error bound pieces (src/probability.cpp:252-281)
   int D, nb, NP, ncol; // nb = D / 32, ncol = 5 D + 1 records per alpha_r table
-  unsigned n_tiles;
+  unsigned n_tiles;    // all classes
+  unsigned tile_base, tile_end;  // the range this launch covers
+};
+
+// A slice as the fused kernel sees it. Slices are sorted by class so that each
+// class is one contiguous tile range and one launch; `slot` is the position in
+// the caller's order (where the cells and the summary go).
+struct FusedSlice {
+  int tab_a, tab_b;
+  int slot, cls;
+  double scale_a;
+};
+
+// A contiguous range of the caller's slices, integrated by at most three
+// launches (one per class present). Device-resident runs use a single chunk;
+// the synchronous host API uses several so that the device-to-host copy of
+// chunk c overlaps the kernels of chunk c + 1.
+struct FusedChunk {
+  unsigned slot_begin, slot_end;
+  unsigned class_tiles[4];  // tile_base of class 0, 1, 2 and the end, in sorted order
 };
 
 struct FusedPlan2D {
-  std::vector<FusedItem> items;  // unused (empty)
   FusedConst k;
   int mode = 0;        // 0: Lambda sin(pi u / Lambda) == pi u; 1: series correction
   bool has_err = false, has_m2 = false, has_bound = false;
   std::vector<unsigned char> host_unbounded;  // per slice, when the bound is decided on the host
-  size_t cols_bytes = 0;
-  void* d_cols = nullptr;   // column records, owned
-  ~FusedPlan2D() {
-    if (d_cols) cudaFree(d_cols);
-  }
+  std::vector<FusedSlice> fslices;            // sorted by (chunk, class)
+  std::vector<FusedChunk> chunks;
+  size_t cols_bytes = 0;                      // size of the column-record buffer
 };
 
 // ---- column records ---------------------------------------------------------
@@ -176,9 +192,21 @@ __device__ __forceinline__ double rcp_seed(double w) {
 }
 
 // pi^2 * T1 at one point: (sin(pi u) / u)^2 [* 1 / sinc^2(pi u / Lambda)].
-// Branch-free main path (valid for |u| >= 1/16); the caller patches the rare
-// small-|u| points with eval_small(), one test per column, so that the
-// independent evaluations of a column interleave in the FP64 pipe.
+//
+// Slice classes (decided on the host from the slice coordinates):
+//   CLS 0  general: branch-free main path (valid for |u| >= 1/16); the caller
+//          patches the rare small-|u| points (the ridge) with eval_small(), one
+//          test per column, so that the independent evaluations of a column
+//          interleave in the FP64 pipe;
+//   CLS 1  every |u| of the slice is below 1/16  -> 7-term polynomial only;
+//   CLS 2  every |u| of the slice is below 2^-9  -> 3-term polynomial only.
+// (Slices far below the diagonal, |alpha| << 2^m, are entirely in class 1 / 2:
+// 40 % of the slices of a default m + 10 ... m - 30 distribution.)
+template <int MODE>
+__device__ __forceinline__ double series_corr(double w, const FusedConst& k) {
+  return MODE == 1 ? fma(w, fma(w, fma(w, k.c3, k.c2), k.c1), 1.0) : 1.0;
+}
+
 template <int MODE>
 __device__ __forceinline__ double eval_main(const RowReg& r, const ColRec& c, const FusedConst& k,
                                             double& u_out) {
@@ -189,10 +217,7 @@ __device__ __forceinline__ double eval_main(const RowReg& r, const ColRec& c, co
   const double rr = fma(r0, fma(e, e, e), r0);
   const double q = S * rr;
   double T = q * q;
-  if (MODE == 1) {
-    const double w = u * u;
-    T *= fma(w, fma(w, fma(w, k.c3, k.c2), k.c1), 1.0);
-  }
+  if (MODE == 1) T *= series_corr<MODE>(u * u, k);
   u_out = u;
   return T;
 }
@@ -202,9 +227,9 @@ __device__ __forceinline__ unsigned abs_hi(double u) {
 }
 #define QB_SMALL_U 0x3FB00000u  // |u| < 1/16
 
+// pi sinc(pi u) = sum (-1)^k pi^(2k+1) / (2k+1)! w^k
 template <int MODE>
-__device__ __forceinline__ double eval_small(double u, const FusedConst& k) {
-  // pi sinc(pi u) = sum (-1)^k pi^(2k+1) / (2k+1)! w^k, |u| < 1/16
+__device__ __forceinline__ double eval_small(double u, const FusedConst& k) {  // |u| < 1/16
   const double w = u * u;
   double p = 4.6630280576761256442e-4;
   p = fma(p, w, -7.3704309457143507773e-3);
@@ -213,49 +238,71 @@ __device__ __forceinline__ double eval_small(double u, const FusedConst& k) {
   p = fma(p, w, 2.5501640398773454439);
   p = fma(p, w, -5.1677127800499700292);
   p = fma(p, w, 3.1415926535897932385);
-  double T = p * p;
-  if (MODE == 1) T *= fma(w, fma(w, fma(w, k.c3, k.c2), k.c1), 1.0);
-  return T;
+  return (p * p) * series_corr<MODE>(w, k);
+}
+template <int MODE>
+__device__ __forceinline__ double eval_tiny(double u, const FusedConst& k) {  // |u| < 2^-9
+  const double w = u * u;
+  double p = 2.5501640398773454439;
+  p = fma(p, w, -5.1677127800499700292);
+  p = fma(p, w, 3.1415926535897932385);
+  return (p * p) * series_corr<MODE>(w, k);
+}
+
+template <int MODE, int CLS>
+__device__ __forceinline__ double eval_cls(const RowReg& r, const ColRec& c, const FusedConst& k) {
+  const double u = (r.xh + c.yh) + (r.xl + c.yl);
+  return CLS == 1 ? eval_small<MODE>(u, k) : eval_tiny<MODE>(u, k);
 }
 
 // Evaluate one column against up to five rows.
-#define QB_EVAL4(c_, T0, T1, T2, T3)                                                      \
-  double T0, T1, T2, T3;                                                                  \
-  {                                                                                       \
-    double u0_, u1_, u2_, u3_;                                                            \
-    T0 = eval_main<MODE>(r0, c_, k, u0_);                                                 \
-    T1 = eval_main<MODE>(r1, c_, k, u1_);                                                 \
-    T2 = eval_main<MODE>(r2, c_, k, u2_);                                                 \
-    T3 = eval_main<MODE>(r3, c_, k, u3_);                                                 \
-    if (min(min(abs_hi(u0_), abs_hi(u1_)), min(abs_hi(u2_), abs_hi(u3_))) < QB_SMALL_U) { \
-      if (abs_hi(u0_) < QB_SMALL_U) T0 = eval_small<MODE>(u0_, k);                        \
-      if (abs_hi(u1_) < QB_SMALL_U) T1 = eval_small<MODE>(u1_, k);                        \
-      if (abs_hi(u2_) < QB_SMALL_U) T2 = eval_small<MODE>(u2_, k);                        \
-      if (abs_hi(u3_) < QB_SMALL_U) T3 = eval_small<MODE>(u3_, k);                        \
-    }                                                                                     \
+#define QB_EVAL4(c_, T0, T1, T2, T3)                                                        \
+  double T0, T1, T2, T3;                                                                    \
+  if (CLS == 0) {                                                                           \
+    double u0_, u1_, u2_, u3_;                                                              \
+    T0 = eval_main<MODE>(r0, c_, k, u0_);                                                   \
+    T1 = eval_main<MODE>(r1, c_, k, u1_);                                                   \
+    T2 = eval_main<MODE>(r2, c_, k, u2_);                                                   \
+    T3 = eval_main<MODE>(r3, c_, k, u3_);                                                   \
+    if (min(min(abs_hi(u0_), abs_hi(u1_)), min(abs_hi(u2_), abs_hi(u3_))) < QB_SMALL_U) {   \
+      if (abs_hi(u0_) < QB_SMALL_U) T0 = eval_small<MODE>(u0_, k);                          \
+      if (abs_hi(u1_) < QB_SMALL_U) T1 = eval_small<MODE>(u1_, k);                          \
+      if (abs_hi(u2_) < QB_SMALL_U) T2 = eval_small<MODE>(u2_, k);                          \
+      if (abs_hi(u3_) < QB_SMALL_U) T3 = eval_small<MODE>(u3_, k);                          \
+    }                                                                                       \
+  } else {                                                                                  \
+    T0 = eval_cls<MODE, CLS>(r0, c_, k);                                                    \
+    T1 = eval_cls<MODE, CLS>(r1, c_, k);                                                    \
+    T2 = eval_cls<MODE, CLS>(r2, c_, k);                                                    \
+    T3 = eval_cls<MODE, CLS>(r3, c_, k);                                                    \
   }
-#define QB_EVAL1(row_, c_, T)                                        \
-  double T;                                                          \
-  {                                                                  \
-    double u_;                                                       \
-    T = eval_main<MODE>(row_, c_, k, u_);                            \
-    if (abs_hi(u_) < QB_SMALL_U) T = eval_small<MODE>(u_, k);        \
+#define QB_EVAL1(row_, c_, T)                                          \
+  double T;                                                            \
+  if (CLS == 0) {                                                      \
+    double u_;                                                         \
+    T = eval_main<MODE>(row_, c_, k, u_);                              \
+    if (abs_hi(u_) < QB_SMALL_U) T = eval_small<MODE>(u_, k);          \
+  } else {                                                             \
+    T = eval_cls<MODE, CLS>(row_, c_, k);                              \
   }
-#define QB_EVAL2(rowa_, rowb_, c_, Ta, Tb)                            \
-  double Ta, Tb;                                                      \
-  {                                                                   \
-    double ua_, ub_;                                                  \
-    Ta = eval_main<MODE>(rowa_, c_, k, ua_);                          \
-    Tb = eval_main<MODE>(rowb_, c_, k, ub_);                          \
-    if (min(abs_hi(ua_), abs_hi(ub_)) < QB_SMALL_U) {                 \
-      if (abs_hi(ua_) < QB_SMALL_U) Ta = eval_small<MODE>(ua_, k);    \
-      if (abs_hi(ub_) < QB_SMALL_U) Tb = eval_small<MODE>(ub_, k);    \
-    }                                                                 \
+#define QB_EVAL2(rowa_, rowb_, c_, Ta, Tb)                              \
+  double Ta, Tb;                                                        \
+  if (CLS == 0) {                                                       \
+    double ua_, ub_;                                                    \
+    Ta = eval_main<MODE>(rowa_, c_, k, ua_);                            \
+    Tb = eval_main<MODE>(rowb_, c_, k, ub_);                            \
+    if (min(abs_hi(ua_), abs_hi(ub_)) < QB_SMALL_U) {                   \
+      if (abs_hi(ua_) < QB_SMALL_U) Ta = eval_small<MODE>(ua_, k);      \
+      if (abs_hi(ub_) < QB_SMALL_U) Tb = eval_small<MODE>(ub_, k);      \
+    }                                                                   \
+  } else {                                                              \
+    Ta = eval_cls<MODE, CLS>(rowa_, c_, k);                             \
+    Tb = eval_cls<MODE, CLS>(rowb_, c_, k);                             \
   }
 
 struct FusedArgs {
   FusedConst k;
-  const DevSlice* slices;
+  const FusedSlice* slices;
   const AxisD* tab_a;
   const double* cols;
   const double* gw;
@@ -263,26 +310,56 @@ struct FusedArgs {
   double* part;
 };
 
-template <int MODE, bool HAS_ERR, bool HAS_M2, bool HAS_BOUND>
-__global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a) {
-  __shared__ double s_halo[QB_FUSED_WARPS][2][32];
+#ifndef QB_FUSED_MIN_CTAS
+#define QB_FUSED_MIN_CTAS 3
+#endif
+#define QB_TILE_RECS 161  // 5 * 32 + 1 column records per tile
+#define QB_FUSED_SMEM_BYTES \
+  (QB_FUSED_WARPS * (QB_TILE_RECS * QB_FUSED_REC + 2 * 32) * (int)sizeof(double))
+
+__device__ __forceinline__ ColRec load_col_s(const double* p) {
+  const double2 a = *(const double2*)p;
+  const double2 b = *((const double2*)p + 1);
+  const double2 c = *((const double2*)p + 2);
+  const double2 d = *((const double2*)p + 3);
+  const double2 e = *((const double2*)p + 4);
+  ColRec r;
+  r.yh = a.x; r.yl = a.y; r.sr = b.x; r.cr = b.y;
+  r.wF = c.x; r.wF2 = c.y; r.wC = d.x; r.wC2 = d.y;
+  r.b = e.x; r.t2p = e.y;
+  return r;
+}
+
+template <int MODE, int CLS, bool HAS_ERR, bool HAS_M2, bool HAS_BOUND>
+__global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fused2d(FusedArgs a) {
+  extern __shared__ __align__(16) double s_dyn[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const unsigned tile = blockIdx.x * QB_FUSED_WARPS + warp;
-  if (tile >= a.k.n_tiles) return;
   const FusedConst& k = a.k;
+  const unsigned tile = k.tile_base + blockIdx.x * QB_FUSED_WARPS + warp;
+  if (tile >= k.tile_end) return;
+  double* s_cols = s_dyn + warp * (QB_TILE_RECS * QB_FUSED_REC + 2 * 32);
+  double* s_halo = s_cols + QB_TILE_RECS * QB_FUSED_REC;  // [2][32]
   const int D = k.D, nb = k.nb;
   const unsigned per_slice = (unsigned)(nb * nb);
   const unsigned sidx = tile / per_slice;
   const unsigned rem = tile - sidx * per_slice;
   const int jc = (int)(rem / (unsigned)nb), ib = (int)(rem - (unsigned)jc * nb);
   const int I0 = ib * 32, J0 = jc * 32, I = I0 + lane;
-  const DevSlice s = a.slices[sidx];
+  const FusedSlice s = a.slices[sidx];
   const AxisD* tdc = a.tab_a + (size_t)s.tab_a * k.NP;
   const AxisD* tdf = tdc + (2 * D + 1);
-  const double* cols = a.cols + (size_t)s.tab_b * k.ncol * QB_FUSED_REC;
   const double* gwc = a.gw;
   const double* gwf = a.gw + D;
+
+  // ---- stage the tile's 161 column records in shared memory (per warp) ---------
+  {
+    const double2* g =
+        (const double2*)(a.cols + ((size_t)s.tab_b * k.ncol + (size_t)5 * J0) * QB_FUSED_REC);
+    double2* sh = (double2*)s_cols;
+#pragma unroll 4
+    for (int i = lane; i < QB_TILE_RECS * QB_FUSED_REC / 2; i += 32) sh[i] = __ldg(g + i);
+  }
 
   // alpha_d rows of this lane: fine h = 4 I .. 4 I + 3 and the coarse mid point.
   const RowReg r0 = load_row(tdf + 4 * I);
@@ -291,26 +368,31 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
   const RowReg r3 = load_row(tdf + 4 * I + 3);
   const RowReg rc = load_row(tdc + 2 * I + 1);
   const double fd = s.scale_a * k.r_m / 6.0;
-  const double d0 = __ldg(gwf + 2 * I), d1 = __ldg(gwf + 2 * I + 1), dC = __ldg(gwc + I);
-  // fine weights of rows p = 0..4 and coarse weights of (c0, cm, c2)
-  const double WF0 = fd * d0, WF1 = 4.0 * WF0, WF3 = 4.0 * fd * d1, WF4 = fd * d1;
-  const double WF2 = WF0 + WF4;
-  const double WC0 = fd * dC, WC1 = 4.0 * WC0;
+  // Simpson weights along alpha_d: fine rows (D0, 4 D0, D0 + D1, 4 D1, D1), coarse DC (1, 4, 1)
+  const double D0 = fd * __ldg(gwf + 2 * I), D1 = fd * __ldg(gwf + 2 * I + 1);
+  const double DC = fd * __ldg(gwc + I);
 
   double err1 = 0.0, err2 = 0.0;  // Richardson-combined error moments of this lane
   int ok = 1;
+  __syncwarp();
+
+#define QB_BOUND_TEST(T_, arow_, col_)                                              \
+  if (HAS_BOUND) {                                                                  \
+    const double sv_ = k.cs * ((arow_) + (col_).b);                                 \
+    const double room_ = QB_ERROR_BOUND - sv_ * (2.0 + sv_);                        \
+    ok &= (room_ >= 0.0) && (k.e0s <= room_ * ((T_) * (col_).t2p) * k.r_m);         \
+  }
 
   // ---- halo row h = 4 (I0 + 32): lanes <-> columns pre-pass -------------------
   {
     const RowReg rh = load_row(tdf + 4 * (I0 + 32));
-    const int J = J0 + lane;
-    const double* cp = cols + (size_t)(5 * J) * QB_FUSED_REC;
-    const ColRec c0 = load_col(cp);
-    const ColRec c1 = load_col(cp + QB_FUSED_REC);
-    const ColRec c2 = load_col(cp + 2 * QB_FUSED_REC);
-    const ColRec c3 = load_col(cp + 3 * QB_FUSED_REC);
-    const ColRec cm = load_col(cp + 4 * QB_FUSED_REC);
-    const ColRec c4 = load_col(cp + 5 * QB_FUSED_REC);
+    const double* cp = s_cols + (size_t)(5 * lane) * QB_FUSED_REC;
+    const ColRec c0 = load_col_s(cp);
+    const ColRec c1 = load_col_s(cp + QB_FUSED_REC);
+    const ColRec c2 = load_col_s(cp + 2 * QB_FUSED_REC);
+    const ColRec c3 = load_col_s(cp + 3 * QB_FUSED_REC);
+    const ColRec cm = load_col_s(cp + 4 * QB_FUSED_REC);
+    const ColRec c4 = load_col_s(cp + 5 * QB_FUSED_REC);
     QB_EVAL1(rh, c0, T0)
     QB_EVAL1(rh, c1, T1)
     QB_EVAL1(rh, c2, T2)
@@ -319,8 +401,8 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
     QB_EVAL1(rh, c4, T4)
     const double HF = fma(c4.wF2, T4, fma(c3.wF, T3, fma(c2.wF, T2, fma(c1.wF, T1, c0.wF * T0))));
     const double HC = fma(c4.wC2, T4, fma(cm.wC, Tm, c0.wC * T0));
-    s_halo[warp][0][lane] = HF;
-    s_halo[warp][1][lane] = HC;
+    s_halo[lane] = HF;
+    s_halo[32 + lane] = HC;
     if (HAS_ERR) {
       // weights of this row as p = 4 / c2 of lane 31's cell
       const double wf4 = fd * __ldg(gwf + 2 * (I0 + 31) + 1);
@@ -345,47 +427,24 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
     }
     if (HAS_BOUND) {
       const double ah = fabs(rh.xh);
-      const double Tt[3] = {T0, Tm, T4};
-      const double bb[3] = {c0.b, cm.b, c4.b};
-      const double tt[3] = {c0.t2p, cm.t2p, c4.t2p};
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        const double sv = k.cs * (ah + bb[q]);
-        const double room = QB_ERROR_BOUND - sv * (2.0 + sv);
-        ok &= (room >= 0.0) && (k.e0s <= room * (Tt[q] * tt[q]) * k.r_m);
-      }
+      QB_BOUND_TEST(T0, ah, c0)
+      QB_BOUND_TEST(Tm, ah, cm)
+      QB_BOUND_TEST(T4, ah, c4)
     }
     __syncwarp();
   }
 
   // ---- main march over the tile's columns --------------------------------------
-  // composite alpha_d weights of rows 0 and c0 for the error totals: the row is
-  // also row 4 / c2 of the lane above (the tile above handles lane 0's share).
-  const double a0 = fabs(r0.xh), a1 = fabs(r1.xh), a2 = fabs(r2.xh), a3 = fabs(r3.xh);
-  const double am = fabs(rc.xh);
-  double EW0 = WF0, EC0 = WC0;
-  if (HAS_ERR && lane > 0) {
-    EW0 += fd * __ldg(gwf + 2 * I - 1);
-    EC0 += fd * __ldg(gwc + I - 1);
-  }
-
-  double sF0, sF1, sF2, sF3, sC0, sCm;                 // per-cell row sums
+  double sF0, sF1, sF2, sF3, sC0, sCm;                          // per-cell row sums
   double tF0 = 0, tF1 = 0, tF2 = 0, tF3 = 0, tC0 = 0, tCm = 0;  // tile totals of the row sums
   double bF0 = 0, bF1 = 0, bF2 = 0, bF3 = 0, bC0 = 0, bCm = 0;  // ... weighted by b
   double qF0 = 0, qF1 = 0, qF2 = 0, qF3 = 0, qC0 = 0, qCm = 0;  // ... weighted by b^2
   double tp = 0.0;
 
-#define QB_BOUND_TEST(T_, arow_, col_)                                              \
-  if (HAS_BOUND) {                                                                  \
-    const double sv_ = k.cs * ((arow_) + (col_).b);                                 \
-    const double room_ = QB_ERROR_BOUND - sv_ * (2.0 + sv_);                        \
-    ok &= (room_ >= 0.0) && (k.e0s <= room_ * ((T_) * (col_).t2p) * k.r_m);         \
-  }
-
-  const double* cp = cols + (size_t)(5 * J0) * QB_FUSED_REC;
+  const double* cp = s_cols;
   {
     // first column of the tile: starts cell J0
-    const ColRec c = load_col(cp);
+    const ColRec c = load_col_s(cp);
     QB_EVAL4(c, T0, T1, T2, T3)
     QB_EVAL1(rc, c, Tm)
     sF0 = c.wF * T0; sF1 = c.wF * T1; sF2 = c.wF * T2; sF3 = c.wF * T3;
@@ -400,16 +459,16 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
         qC0 = wcbb * T0; qCm = wcbb * Tm;
       }
     }
-    QB_BOUND_TEST(T0, a0, c)
-    QB_BOUND_TEST(Tm, am, c)
+    QB_BOUND_TEST(T0, fabs(r0.xh), c)
+    QB_BOUND_TEST(Tm, fabs(rc.xh), c)
   }
-  double* outp = a.out + (size_t)sidx * D * D + (size_t)J0 * D + I;
+  double* outp = a.out + (size_t)s.slot * D * D + (size_t)J0 * D + I;
 
   for (int jj = 0; jj < 32; jj++) {
     cp += QB_FUSED_REC;
 #pragma unroll
     for (int q = 1; q <= 3; q++) {  // fine interior columns
-      const ColRec c = load_col(cp);
+      const ColRec c = load_col_s(cp);
       cp += QB_FUSED_REC;
       QB_EVAL4(c, T0, T1, T2, T3)
       sF0 = fma(c.wF, T0, sF0); sF1 = fma(c.wF, T1, sF1);
@@ -426,7 +485,7 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
       }
     }
     {  // coarse mid column
-      const ColRec c = load_col(cp);
+      const ColRec c = load_col_s(cp);
       cp += QB_FUSED_REC;
       QB_EVAL2(r0, rc, c, T0, Tm)
       sC0 = fma(c.wC, T0, sC0); sCm = fma(c.wC, Tm, sCm);
@@ -438,27 +497,29 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
           qC0 = fma(wcbb, T0, qC0); qCm = fma(wcbb, Tm, qCm);
         }
       }
-      QB_BOUND_TEST(T0, a0, c)
-      QB_BOUND_TEST(Tm, am, c)
+      QB_BOUND_TEST(T0, fabs(r0.xh), c)
+      QB_BOUND_TEST(Tm, fabs(rc.xh), c)
     }
     {  // boundary column: closes cell J0 + jj, opens the next one
-      const ColRec c = load_col(cp);
+      const ColRec c = load_col_s(cp);
       QB_EVAL4(c, T0, T1, T2, T3)
       QB_EVAL1(rc, c, Tm)
       sF0 = fma(c.wF2, T0, sF0); sF1 = fma(c.wF2, T1, sF1);
       sF2 = fma(c.wF2, T2, sF2); sF3 = fma(c.wF2, T3, sF3);
       sC0 = fma(c.wC2, T0, sC0); sCm = fma(c.wC2, Tm, sCm);
-      QB_BOUND_TEST(T0, a0, c)
-      QB_BOUND_TEST(Tm, am, c)
+      QB_BOUND_TEST(T0, fabs(r0.xh), c)
+      QB_BOUND_TEST(Tm, fabs(rc.xh), c)
       // rows 4 / c2 of this lane are rows 0 / c0 of the lane below
       double nF = __shfl_down_sync(0xffffffffu, sF0, 1);
       double nC = __shfl_down_sync(0xffffffffu, sC0, 1);
       if (lane == 31) {
-        nF = s_halo[warp][0][jj];
-        nC = s_halo[warp][1][jj];
+        nF = s_halo[jj];
+        nC = s_halo[32 + jj];
       }
-      const double fine = fma(WF4, nF, fma(WF3, sF3, fma(WF2, sF2, fma(WF1, sF1, WF0 * sF0))));
-      const double coarse = fma(WC0, nC, fma(WC1, sCm, WC0 * sC0));
+      const double f0 = fma(4.0, sF1, sF0) + sF2;   // fine cell 2 I    (times D0)
+      const double f1 = fma(4.0, sF3, sF2) + nF;    // fine cell 2 I + 1 (times D1)
+      const double fine = fma(D1, f1, D0 * f0);
+      const double coarse = DC * (fma(4.0, sCm, sC0) + nC);
       const double cell = fma(2.0, fine, -coarse);
       outp[(size_t)jj * D] = cell;
       tp += cell;
@@ -486,19 +547,29 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
 #undef QB_BOUND_TEST
 
   if (HAS_ERR) {
-    // sum over the lane's rows of weight * (a^n * rowsum + ...), fine counted twice
+    // Composite alpha_d weights for the error totals: rows 0 / c0 are also rows
+    // 4 / c2 of the lane above (the tile above accounts for lane 0's share in its
+    // halo pre-pass).
+    const double a0 = fabs(r0.xh), a1 = fabs(r1.xh), a2 = fabs(r2.xh), a3 = fabs(r3.xh);
+    const double am = fabs(rc.xh);
+    double EW0 = D0, EC0 = DC;
+    if (lane > 0) {
+      EW0 += fd * __ldg(gwf + 2 * I - 1);
+      EC0 += fd * __ldg(gwc + I - 1);
+    }
+    const double W1 = 4.0 * D0, W2 = D0 + D1, W3 = 4.0 * D1, WC1 = 4.0 * DC;
     double e1 = EW0 * fma(a0, tF0, bF0);
-    e1 = fma(WF1, fma(a1, tF1, bF1), e1);
-    e1 = fma(WF2, fma(a2, tF2, bF2), e1);
-    e1 = fma(WF3, fma(a3, tF3, bF3), e1);
+    e1 = fma(W1, fma(a1, tF1, bF1), e1);
+    e1 = fma(W2, fma(a2, tF2, bF2), e1);
+    e1 = fma(W3, fma(a3, tF3, bF3), e1);
     double e1c = EC0 * fma(a0, tC0, bC0);
     e1c = fma(WC1, fma(am, tCm, bCm), e1c);
     err1 += fma(2.0, e1, -e1c);
     if (HAS_M2) {
       double e2 = EW0 * fma(a0 * a0, tF0, fma(2.0 * a0, bF0, qF0));
-      e2 = fma(WF1, fma(a1 * a1, tF1, fma(2.0 * a1, bF1, qF1)), e2);
-      e2 = fma(WF2, fma(a2 * a2, tF2, fma(2.0 * a2, bF2, qF2)), e2);
-      e2 = fma(WF3, fma(a3 * a3, tF3, fma(2.0 * a3, bF3, qF3)), e2);
+      e2 = fma(W1, fma(a1 * a1, tF1, fma(2.0 * a1, bF1, qF1)), e2);
+      e2 = fma(W2, fma(a2 * a2, tF2, fma(2.0 * a2, bF2, qF2)), e2);
+      e2 = fma(W3, fma(a3 * a3, tF3, fma(2.0 * a3, bF3, qF3)), e2);
       double e2c = EC0 * fma(a0 * a0, tC0, fma(2.0 * a0, bC0, qC0));
       e2c = fma(WC1, fma(am * am, tCm, fma(2.0 * am, bCm, qCm)), e2c);
       err2 += fma(2.0, e2, -e2c);
@@ -514,7 +585,7 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, 3) k_fused2d(FusedArgs a)
     ok &= __shfl_down_sync(0xffffffffu, ok, off);
   }
   if (lane == 0) {
-    double* p = a.part + (size_t)tile * QB_FUSED_PART_STRIDE;
+    double* p = a.part + ((size_t)s.slot * per_slice + rem) * QB_FUSED_PART_STRIDE;
     p[0] = tp;
     p[1] = err1;
     p[2] = err2;
@@ -548,9 +619,8 @@ __global__ void k_fused_final(unsigned n, unsigned per_slice, const double* __re
 
 // ---- host side ----------------------------------------------------------------
 
-// Decide whether the fused kernel applies and which variant.
-inline bool fused2d_prepare(const Plan& h, int sm_count, FusedPlan2D* f, std::string* why) {
-  (void)sm_count;
+// Decide whether the fused kernel applies and which variants; sort the slices by class.
+inline bool fused2d_prepare(const Plan& h, unsigned n_chunks, FusedPlan2D* f, std::string* why) {
   if (h.kind >= 0) {
     *why = "not a two-dimensional plan";
     return false;
@@ -568,6 +638,7 @@ inline bool fused2d_prepare(const Plan& h, int sm_count, FusedPlan2D* f, std::st
     return false;
   }
   const DevConsts& c = h.c;
+  const double akappa = std::fabs(c.kappa.hi) * (1.0 + 1e-12) + 1e-300;
   int rel_max = -100000;
   for (size_t i = 0; i < h.slices.size(); i++) {
     rel_max = std::max(rel_max, (int)std::labs((long)h.k_a[i]) - c.m);
@@ -575,7 +646,7 @@ inline bool fused2d_prepare(const Plan& h, int sm_count, FusedPlan2D* f, std::st
   }
   if (h.slices.empty()) rel_max = 0;
   // |u| <= |x_d| + |kappa| |x_r| < 2^(rel_max + 1) * (1 + |kappa|)
-  const int log_u = rel_max + 1 + (int)std::ceil(std::log2(1.0 + std::fabs(c.kappa.hi)));
+  const int log_u = rel_max + 1 + (int)std::ceil(std::log2(1.0 + akappa));
   if (c.lam_exp - log_u >= 29) {
     f->mode = 0;
   } else if (c.lam_exp - log_u >= 10) {
@@ -584,7 +655,7 @@ inline bool fused2d_prepare(const Plan& h, int sm_count, FusedPlan2D* f, std::st
     *why = "l - sigma too small for the sinc expansion of the inner sine";
     return false;
   }
-  // Lambda sin(z)/... : 1 / sinc^2(z) = 1 + z^2/3 + z^4/15 + 2 z^6/189, z^2 = (pi/Lambda)^2 w
+  // 1 / sinc^2(z) = 1 + z^2/3 + z^4/15 + 2 z^6/189, z^2 = (pi/Lambda)^2 w
   const double q = std::ldexp(9.86960440108935861883, -2 * std::min(c.lam_exp, 500));
   f->k.c1 = q / 3.0;
   f->k.c2 = q * q / 15.0;
@@ -596,7 +667,10 @@ inline bool fused2d_prepare(const Plan& h, int sm_count, FusedPlan2D* f, std::st
   f->k.nb = h.D / 32;
   f->k.NP = table_points(h.D);
   f->k.ncol = 5 * h.D + 1;
-  f->k.n_tiles = (unsigned)(h.slices.size() * (size_t)f->k.nb * f->k.nb);
+  const unsigned per_slice = (unsigned)(f->k.nb * f->k.nb);
+  f->k.n_tiles = (unsigned)h.slices.size() * per_slice;
+  f->k.tile_base = 0;
+  f->k.tile_end = f->k.n_tiles;
   f->has_err = h.with_error;
   // second moment: relative size cs * h_max / 2 versus the first
   const double csh = c.cs * std::ldexp(1.0, rel_max + 2);
@@ -613,59 +687,125 @@ inline bool fused2d_prepare(const Plan& h, int sm_count, FusedPlan2D* f, std::st
       f->host_unbounded[i] = (QB_ERROR_BOUND - sv * (2.0 + sv) >= 0.0) ? 0 : 1;
     }
   }
-  const size_t bytes = std::max<size_t>(1, h.tabs_b.size()) * (size_t)f->k.ncol * QB_FUSED_REC *
-                       sizeof(double);
-  if (f->d_cols) cudaFree(f->d_cols);
-  f->d_cols = nullptr;
-  if (cudaMalloc(&f->d_cols, bytes) != cudaSuccess) {
-    cudaGetLastError();
-    *why = "out of device memory for the column records";
-    return false;
+  // classes: an upper bound of |u| over every abscissa of the slice (the last
+  // main points sit at 2 * 2^(k - m))
+  const unsigned n = (unsigned)h.slices.size();
+  n_chunks = std::max(1u, std::min(n_chunks, std::max(1u, n)));
+  f->fslices.clear();
+  f->chunks.clear();
+  unsigned base = 0;
+  for (unsigned ch = 0; ch < n_chunks; ch++) {
+    FusedChunk fc;
+    fc.slot_begin = (unsigned)((uint64_t)n * ch / n_chunks);
+    fc.slot_end = (unsigned)((uint64_t)n * (ch + 1) / n_chunks);
+    std::vector<FusedSlice> by_cls[3];
+    for (unsigned i = fc.slot_begin; i < fc.slot_end; i++) {
+      const double umax = 2.0 * (h.slices[i].scale_a + akappa * h.slices[i].scale_b);
+      FusedSlice fs;
+      fs.tab_a = h.slices[i].tab_a;
+      fs.tab_b = h.slices[i].tab_b;
+      fs.slot = (int)i;
+      fs.scale_a = h.slices[i].scale_a;
+      fs.cls = umax < 0.001953124 ? 2 : (umax < 0.062499 ? 1 : 0);
+      by_cls[fs.cls].push_back(fs);
+    }
+    for (int cl = 0; cl < 3; cl++) {
+      fc.class_tiles[cl] = base;
+      f->fslices.insert(f->fslices.end(), by_cls[cl].begin(), by_cls[cl].end());
+      base += (unsigned)by_cls[cl].size() * per_slice;
+    }
+    fc.class_tiles[3] = base;
+    f->chunks.push_back(fc);
   }
-  f->cols_bytes = bytes;
+  f->cols_bytes = std::max<size_t>(1, h.tabs_b.size()) * (size_t)f->k.ncol * QB_FUSED_REC *
+                  sizeof(double);
   return true;
 }
 
-inline uint32_t fused2d_launches(const FusedPlan2D&) { return 4; }  // axis, cols, fused, final
-
-template <int MODE>
-inline void fused2d_launch_variant(const FusedPlan2D& f, const FusedArgs& args, unsigned blocks,
-                                   cudaStream_t st) {
-  const int v = (f.has_err ? 1 : 0) | (f.has_m2 ? 2 : 0) | (f.has_bound ? 4 : 0);
-  const dim3 g(blocks), b(QB_FUSED_WARPS * 32);
-  switch (v) {
-    case 0: k_fused2d<MODE, false, false, false><<<g, b, 0, st>>>(args); break;
-    case 1: k_fused2d<MODE, true, false, false><<<g, b, 0, st>>>(args); break;
-    case 3: k_fused2d<MODE, true, true, false><<<g, b, 0, st>>>(args); break;
-    case 5: k_fused2d<MODE, true, false, true><<<g, b, 0, st>>>(args); break;
-    default: k_fused2d<MODE, true, true, true><<<g, b, 0, st>>>(args); break;
-  }
+inline uint32_t fused2d_launches(const FusedPlan2D& f) {
+  uint32_t n = 3;  // axis tables, column records, final summary
+  for (const FusedChunk& c : f.chunks)
+    for (int cl = 0; cl < 3; cl++) n += c.class_tiles[cl + 1] > c.class_tiles[cl] ? 1 : 0;
+  return n;
 }
 
-// Enqueues k_fused_cols, k_fused2d and k_fused_final (k_axis2d is enqueued by the caller).
-inline int fused2d_run(const FusedPlan2D& f, const Plan& h, cudaStream_t st,
-                       const DevSlice* slices, const AxisD* tab_a, const AxisR* tab_b,
-                       const double* gw, const FusedItem*, double* part, double* d_cells,
-                       double* d_summary, const TabDesc* desc_b) {
-  const int D = h.D;
-  const unsigned n = (unsigned)h.slices.size();
-  k_fused_cols<<<dim3((f.k.ncol + 127) / 128, (unsigned)h.tabs_b.size()), 128, 0, st>>>(
-      D, h.c.m, desc_b, tab_b, gw, (double*)f.d_cols);
+template <int MODE, int CLS>
+inline cudaError_t fused2d_launch_variant(const FusedPlan2D& f, const FusedArgs& args,
+                                          unsigned blocks, cudaStream_t st) {
+  const int v = (f.has_err ? 1 : 0) | (f.has_m2 ? 2 : 0) | (f.has_bound ? 4 : 0);
+  const dim3 g(blocks), b(QB_FUSED_WARPS * 32);
+  const size_t sm = QB_FUSED_SMEM_BYTES;
+#define QB_LAUNCH(E, M2, B)                                                                   \
+  {                                                                                           \
+    auto kern = k_fused2d<MODE, CLS, E, M2, B>;                                               \
+    static bool once = false;                                                                 \
+    if (!once) {                                                                              \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);       \
+      once = true;                                                                            \
+    }                                                                                         \
+    kern<<<g, b, sm, st>>>(args);                                                             \
+  }
+  switch (v) {
+    case 0: QB_LAUNCH(false, false, false) break;
+    case 1: QB_LAUNCH(true, false, false) break;
+    case 3: QB_LAUNCH(true, true, false) break;
+    case 5: QB_LAUNCH(true, false, true) break;
+    default: QB_LAUNCH(true, true, true) break;
+  }
+#undef QB_LAUNCH
+  return cudaGetLastError();
+}
+
+// Enqueue the fused kernel for one chunk (one launch per slice class present).
+inline int fused2d_launch_chunk(const FusedPlan2D& f, FusedArgs args, size_t chunk,
+                                cudaStream_t st) {
+  const FusedChunk& c = f.chunks[chunk];
+  for (int cl = 0; cl < 3; cl++) {
+    const unsigned lo = c.class_tiles[cl], hi = c.class_tiles[cl + 1];
+    if (lo >= hi) continue;
+    args.k.tile_base = lo;
+    args.k.tile_end = hi;
+    const unsigned blocks = (hi - lo + QB_FUSED_WARPS - 1) / QB_FUSED_WARPS;
+    cudaError_t e;
+    if (f.mode == 0) {
+      e = cl == 0 ? fused2d_launch_variant<0, 0>(f, args, blocks, st)
+                  : cl == 1 ? fused2d_launch_variant<0, 1>(f, args, blocks, st)
+                            : fused2d_launch_variant<0, 2>(f, args, blocks, st);
+    } else {
+      e = cl == 0 ? fused2d_launch_variant<1, 0>(f, args, blocks, st)
+                  : cl == 1 ? fused2d_launch_variant<1, 1>(f, args, blocks, st)
+                            : fused2d_launch_variant<1, 2>(f, args, blocks, st);
+    }
+    if (e != cudaSuccess) return -100;
+  }
+  return 0;
+}
+
+inline FusedArgs fused2d_args(const FusedPlan2D& f, const FusedSlice* d_fslices,
+                              const double* d_cols, const AxisD* tab_a, const double* gw,
+                              double* part, double* d_cells) {
   FusedArgs args;
   args.k = f.k;
-  args.slices = slices;
+  args.slices = d_fslices;
   args.tab_a = tab_a;
-  args.cols = (const double*)f.d_cols;
+  args.cols = d_cols;
   args.gw = gw;
   args.out = d_cells;
   args.part = part;
-  const unsigned blocks = (f.k.n_tiles + QB_FUSED_WARPS - 1) / QB_FUSED_WARPS;
-  if (f.mode == 0)
-    fused2d_launch_variant<0>(f, args, blocks, st);
-  else
-    fused2d_launch_variant<1>(f, args, blocks, st);
+  return args;
+}
+
+inline void fused2d_launch_cols(const FusedPlan2D& f, const Plan& h, cudaStream_t st,
+                                const TabDesc* desc_b, const AxisR* tab_b, const double* gw,
+                                double* d_cols) {
+  k_fused_cols<<<dim3((f.k.ncol + 127) / 128, (unsigned)h.tabs_b.size()), 128, 0, st>>>(
+      h.D, h.c.m, desc_b, tab_b, gw, d_cols);
+}
+
+inline void fused2d_launch_final(const FusedPlan2D& f, const Plan& h, cudaStream_t st,
+                                 const double* part, double* d_summary) {
+  const unsigned n = (unsigned)h.slices.size();
   k_fused_final<<<(n + 127) / 128, 128, 0, st>>>(n, (unsigned)(f.k.nb * f.k.nb), part, d_summary);
-  return cudaGetLastError() == cudaSuccess ? 0 : -100;
 }
 
 }  // namespace qb200

@@ -34,17 +34,50 @@ int fail(int code, const std::string& msg) {
       return fail(-100, std::string(#call) + ": " + cudaGetErrorString(e_));            \
   } while (0)
 
+// Device buffers come from a per-context pool: a plan returns its buffers to
+// the pool when it is destroyed, so the synchronous API (one plan per call)
+// does not pay cudaMalloc / cudaFree on every call.
+struct Pool {
+  std::vector<std::pair<void*, size_t>> free_;
+  ~Pool() {
+    for (auto& e : free_) cudaFree(e.first);
+  }
+  bool take(size_t n, void** p, size_t* got) {
+    size_t best = free_.size();
+    for (size_t i = 0; i < free_.size(); i++)
+      if (free_[i].second >= n && free_[i].second <= 4 * n + 4096 &&
+          (best == free_.size() || free_[i].second < free_[best].second))
+        best = i;
+    if (best == free_.size()) return false;
+    *p = free_[best].first;
+    *got = free_[best].second;
+    free_.erase(free_.begin() + (long)best);
+    return true;
+  }
+  void give(void* p, size_t n) { free_.emplace_back(p, n); }
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  ~DevBuf() {
-    if (p) cudaFree(p);
+  Pool* pool = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (!p) return;
+    if (pool)
+      pool->give(p, bytes);
+    else
+      cudaFree(p);
+    p = nullptr;
+    bytes = 0;
   }
   int reserve(size_t n) {
     if (n <= bytes) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
+    release();
+    if (pool && pool->take(n, &p, &bytes)) return 0;
     QB_CUDA(cudaMalloc(&p, n));
     bytes = n;
     return 0;
@@ -63,7 +96,9 @@ struct DevGeometry {
 
 struct qb200_context {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_stream = nullptr;  // device-to-host copies of the synchronous API
+  std::vector<cudaEvent_t> events;
   int sm_count = 0;
   uint64_t launches = 0;
   std::map<int, std::unique_ptr<DevGeometry>> geo;
@@ -71,6 +106,7 @@ struct qb200_context {
   DevBuf out_cells, out_summary;
   void* h_summary = nullptr;
   size_t h_summary_bytes = 0;
+  Pool pool;  // declared last: destroyed first is fine, plans never outlive their context
 };
 
 struct qb200_plan {
@@ -80,6 +116,7 @@ struct qb200_plan {
   int fused_ok = 0;
   std::string fused_why;
   uint32_t n = 0;
+  std::vector<DevSlice> h_slices;
   DevGeometry* geo = nullptr;
   DevBuf desc_a, desc_b, slices, tab_a, tab_b;
   // plain path scratch (per chunk of slices)
@@ -88,7 +125,12 @@ struct qb200_plan {
   DevBuf cells_c, cells_f, part_c, part_f, part_tp, values;
   // fused path
   FusedPlan2D fused;
-  DevBuf fused_part;
+  DevBuf fused_part, fused_cols, fused_slices;
+  void bind_pool(Pool* pool) {
+    DevBuf* all[] = {&desc_a, &desc_b, &slices, &tab_a, &tab_b, &cells_c, &cells_f, &part_c,
+                     &part_f, &part_tp, &values, &fused_part, &fused_cols, &fused_slices};
+    for (DevBuf* b : all) b->pool = pool;
+  }
 };
 
 namespace {
@@ -130,7 +172,8 @@ int upload_plan(qb200_plan* pl) {
   const int D = h.D;
   const int NP = table_points(D);
   if (int rc = get_geometry(pl->ctx, D, &pl->geo)) return rc;
-  std::vector<DevSlice> ds(n);
+  std::vector<DevSlice>& ds = pl->h_slices;
+  ds.resize(n);
   for (uint32_t i = 0; i < n; i++) {
     ds[i].tab_a = h.slices[i].tab_a;
     ds[i].tab_b = h.slices[i].tab_b;
@@ -139,16 +182,18 @@ int upload_plan(qb200_plan* pl) {
     ds[i].eta_shift = h.slices[i].eta_shift;
   }
   if (int rc = pl->slices.reserve(std::max<size_t>(1, n) * sizeof(DevSlice))) return rc;
-  if (n) QB_CUDA(cudaMemcpy(pl->slices.p, ds.data(), n * sizeof(DevSlice), cudaMemcpyHostToDevice));
+  if (n)
+    QB_CUDA(cudaMemcpyAsync(pl->slices.p, ds.data(), n * sizeof(DevSlice), cudaMemcpyHostToDevice,
+                            pl->ctx->stream));
   if (int rc = pl->desc_a.reserve(std::max<size_t>(1, h.tabs_a.size()) * sizeof(TabDesc))) return rc;
   if (!h.tabs_a.empty())
-    QB_CUDA(cudaMemcpy(pl->desc_a.p, h.tabs_a.data(), h.tabs_a.size() * sizeof(TabDesc),
-                       cudaMemcpyHostToDevice));
+    QB_CUDA(cudaMemcpyAsync(pl->desc_a.p, h.tabs_a.data(), h.tabs_a.size() * sizeof(TabDesc),
+                            cudaMemcpyHostToDevice, pl->ctx->stream));
   if (h.kind < 0) {
     if (int rc = pl->desc_b.reserve(std::max<size_t>(1, h.tabs_b.size()) * sizeof(TabDesc))) return rc;
     if (!h.tabs_b.empty())
-      QB_CUDA(cudaMemcpy(pl->desc_b.p, h.tabs_b.data(), h.tabs_b.size() * sizeof(TabDesc),
-                         cudaMemcpyHostToDevice));
+      QB_CUDA(cudaMemcpyAsync(pl->desc_b.p, h.tabs_b.data(), h.tabs_b.size() * sizeof(TabDesc),
+                              cudaMemcpyHostToDevice, pl->ctx->stream));
     if (int rc = pl->tab_a.reserve(std::max<size_t>(1, h.tabs_a.size()) * NP * sizeof(AxisD))) return rc;
     if (int rc = pl->tab_b.reserve(std::max<size_t>(1, h.tabs_b.size()) * NP * sizeof(AxisR))) return rc;
   }
@@ -277,17 +322,66 @@ uint32_t plain_launches(const qb200_plan* pl) {
   return chunks * 3;
 }
 
-int finish_common(qb200_plan* pl) {
-  if (int rc = upload_plan(pl)) return rc;
+int setup_fused(qb200_plan* pl, unsigned n_chunks) {
   pl->fused_ok = 0;
-  if (pl->host.kind < 0) {
-    pl->fused_ok = fused2d_prepare(pl->host, pl->ctx->sm_count, &pl->fused, &pl->fused_why) ? 1 : 0;
-    if (pl->fused_ok) {
-      if (int rc = pl->fused_part.reserve(std::max<size_t>(1, pl->fused.k.n_tiles) *
-                                          QB_FUSED_PART_STRIDE * sizeof(double)))
-        return rc;
-    }
-  }
+  if (pl->host.kind >= 0) return 0;
+  if (!fused2d_prepare(pl->host, n_chunks, &pl->fused, &pl->fused_why)) return 0;
+  if (int rc = pl->fused_part.reserve(std::max<size_t>(1, pl->fused.k.n_tiles) *
+                                      QB_FUSED_PART_STRIDE * sizeof(double)))
+    return rc;
+  if (int rc = pl->fused_cols.reserve(pl->fused.cols_bytes)) return rc;
+  const size_t fb = std::max<size_t>(1, pl->fused.fslices.size()) * sizeof(FusedSlice);
+  if (int rc = pl->fused_slices.reserve(fb)) return rc;
+  if (!pl->fused.fslices.empty())
+    QB_CUDA(cudaMemcpyAsync(pl->fused_slices.p, pl->fused.fslices.data(),
+                            pl->fused.fslices.size() * sizeof(FusedSlice), cudaMemcpyHostToDevice,
+                            pl->ctx->stream));
+  pl->fused_ok = 1;
+  return 0;
+}
+
+int enqueue_fused_prologue(qb200_plan* plan, cudaStream_t st) {
+  const Plan& h = plan->host;
+  const int NP = table_points(h.D);
+  const int n_a = (int)h.tabs_a.size(), n_b = (int)h.tabs_b.size();
+  dim3 grid((NP + 127) / 128, n_a + n_b);
+  k_axis2d<<<grid, 128, 0, st>>>(h.c, NP, n_a, plan->desc_a.as<TabDesc>(),
+                                 plan->desc_b.as<TabDesc>(), plan->geo->gx.as<dd>(),
+                                 plan->tab_a.as<AxisD>(), plan->tab_b.as<AxisR>());
+  fused2d_launch_cols(plan->fused, h, st, plan->desc_b.as<TabDesc>(), plan->tab_b.as<AxisR>(),
+                      plan->geo->gw.as<double>(), plan->fused_cols.as<double>());
+  plan->ctx->launches += 2;
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+FusedArgs fused_args_of(qb200_plan* plan, double* d_cells) {
+  return fused2d_args(plan->fused, plan->fused_slices.as<FusedSlice>(),
+                      plan->fused_cols.as<double>(), plan->tab_a.as<AxisD>(),
+                      plan->geo->gw.as<double>(), plan->fused_part.as<double>(), d_cells);
+}
+
+int enqueue_fused_chunk(qb200_plan* plan, const FusedArgs& args, size_t c, cudaStream_t st) {
+  if (fused2d_launch_chunk(plan->fused, args, c, st)) return fail(-100, "fused kernel launch failed");
+  const FusedChunk& fc = plan->fused.chunks[c];
+  for (int cl = 0; cl < 3; cl++)
+    plan->ctx->launches += fc.class_tiles[cl + 1] > fc.class_tiles[cl] ? 1 : 0;
+  return 0;
+}
+
+int enqueue_fused_epilogue(qb200_plan* plan, cudaStream_t st, double* d_summary) {
+  fused2d_launch_final(plan->fused, plan->host, st, plan->fused_part.as<double>(), d_summary);
+  plan->ctx->launches += 1;
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int finish_common(qb200_plan* pl, unsigned n_chunks = 1) {
+  if (int rc = upload_plan(pl)) return rc;
+  if (int rc = setup_fused(pl, n_chunks)) return rc;
+  // uploads above are asynchronous on the context stream from pageable vectors owned by
+  // the plan (or already consumed): make them visible to any stream the caller runs on
+  QB_CUDA(cudaStreamSynchronize(pl->ctx->stream));
   pl->algo = pl->fused_ok ? 2 : 1;
   return 0;
 }
@@ -322,11 +416,13 @@ int qb200_create(int device, qb200_context** out) {
   qb200_context* ctx = new qb200_context;
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  const cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete ctx;
     return fail(-100, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
   }
+  ctx->out_cells.pool = nullptr;
   *out = ctx;
   return 0;
 }
@@ -335,6 +431,8 @@ void qb200_destroy(qb200_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
   if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
   delete ctx;
 }
@@ -353,20 +451,27 @@ void qb200_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+static int create_plan2d(qb200_context* ctx, const qb200_params* params, int method,
+                         int richardson, uint32_t dimension, uint32_t n, const int32_t* a_d,
+                         const int32_t* a_r, unsigned n_chunks, qb200_plan** out) {
+  std::unique_ptr<qb200_plan> pl(new qb200_plan);
+  pl->ctx = ctx;
+  pl->bind_pool(&ctx->pool);
+  std::string err;
+  if (int rc = plan_2d(view_of(params), method, richardson, dimension, n, a_d, a_r, &pl->host, &err))
+    return fail(rc, err);
+  if (int rc = finish_common(pl.get(), n_chunks)) return rc;
+  *out = pl.release();
+  return 0;
+}
+
 int qb200_plan2d_create(qb200_context* ctx, const qb200_params* params, int method,
                         int richardson, uint32_t dimension, uint32_t n,
                         const int32_t* a_d, const int32_t* a_r, qb200_plan** out) {
   *out = nullptr;
   if (!ctx || !params) return fail(-1, "null argument");
   QB_CUDA(cudaSetDevice(ctx->device));
-  std::unique_ptr<qb200_plan> pl(new qb200_plan);
-  pl->ctx = ctx;
-  std::string err;
-  if (int rc = plan_2d(view_of(params), method, richardson, dimension, n, a_d, a_r, &pl->host, &err))
-    return fail(rc, err);
-  if (int rc = finish_common(pl.get())) return rc;
-  *out = pl.release();
-  return 0;
+  return create_plan2d(ctx, params, method, richardson, dimension, n, a_d, a_r, 1, out);
 }
 
 int qb200_plan1d_create(qb200_context* ctx, const qb200_params* params, int kind, int richardson,
@@ -377,6 +482,7 @@ int qb200_plan1d_create(qb200_context* ctx, const qb200_params* params, int kind
   QB_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<qb200_plan> pl(new qb200_plan);
   pl->ctx = ctx;
+  pl->bind_pool(&ctx->pool);
   std::string err;
   if (int rc = plan_1d(view_of(params), kind, richardson, dimension, n, a, eta, &pl->host, &err))
     return fail(rc, err);
@@ -427,23 +533,11 @@ int qb200_plan_run(qb200_plan* plan, void* stream, double* d_cells, double* d_su
   if (plan->host.kind >= 0) return run_plain_1d(plan, st, d_cells, d_summary);
   if (plan->algo == 2) {
     if (plan->n == 0) return 0;
-    const Plan& h = plan->host;
-    const int NP = table_points(h.D);
-    const int n_a = (int)h.tabs_a.size(), n_b = (int)h.tabs_b.size();
-    dim3 grid((NP + 127) / 128, n_a + n_b);
-    k_axis2d<<<grid, 128, 0, st>>>(h.c, NP, n_a, plan->desc_a.as<TabDesc>(),
-                                   plan->desc_b.as<TabDesc>(), plan->geo->gx.as<dd>(),
-                                   plan->tab_a.as<AxisD>(), plan->tab_b.as<AxisR>());
-    ctx->launches++;
-    const int rc = fused2d_run(plan->fused, h, st, plan->slices.as<DevSlice>(),
-                               plan->tab_a.as<AxisD>(), plan->tab_b.as<AxisR>(),
-                               plan->geo->gw.as<double>(), nullptr,
-                               plan->fused_part.as<double>(), d_cells, d_summary,
-                               plan->desc_b.as<TabDesc>());
-    ctx->launches += fused2d_launches(plan->fused) - 1;
-    if (rc) return fail(rc, "fused kernel launch failed");
-    QB_CUDA(cudaGetLastError());
-    return 0;
+    if (int rc = enqueue_fused_prologue(plan, st)) return rc;
+    const FusedArgs args = fused_args_of(plan, d_cells);
+    for (size_t c = 0; c < plan->fused.chunks.size(); c++)
+      if (int rc = enqueue_fused_chunk(plan, args, c, st)) return rc;
+    return enqueue_fused_epilogue(plan, st, d_summary);
   }
   return run_plain_2d(plan, st, d_cells, d_summary);
 }
@@ -483,16 +577,41 @@ static int run_sync(qb200_context* ctx, qb200_plan* pl, double* cells, long doub
     QB_CUDA(cudaHostAlloc(&ctx->h_summary, sum_bytes, cudaHostAllocDefault));
     ctx->h_summary_bytes = sum_bytes;
   }
-  if (int rc = qb200_plan_run(pl, ctx->stream, ctx->out_cells.as<double>(),
-                              ctx->out_summary.as<double>()))
-    return rc;
-  if (ncells)
-    QB_CUDA(cudaMemcpyAsync(cells, ctx->out_cells.p, ncells * sizeof(double),
-                            cudaMemcpyDeviceToHost, ctx->stream));
+  double* d_cells = ctx->out_cells.as<double>();
+  double* d_summary = ctx->out_summary.as<double>();
+  if (pl->host.kind < 0 && pl->algo == 2 && pl->n > 0) {
+    // Pipelined: the copy of chunk c runs on the copy stream while chunk c + 1 computes.
+    const size_t nch = pl->fused.chunks.size();
+    while (ctx->events.size() < nch) {
+      cudaEvent_t ev;
+      QB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      ctx->events.push_back(ev);
+    }
+    if (int rc = enqueue_fused_prologue(pl, ctx->stream)) return rc;
+    const FusedArgs args = fused_args_of(pl, d_cells);
+    const size_t per = (size_t)pl->host.D * pl->host.D;
+    for (size_t c = 0; c < nch; c++) {
+      if (int rc = enqueue_fused_chunk(pl, args, c, ctx->stream)) return rc;
+      QB_CUDA(cudaEventRecord(ctx->events[c], ctx->stream));
+      QB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0));
+      const FusedChunk& fc = pl->fused.chunks[c];
+      const size_t off = (size_t)fc.slot_begin * per, cnt = (size_t)(fc.slot_end - fc.slot_begin) * per;
+      if (cnt)
+        QB_CUDA(cudaMemcpyAsync(cells + off, d_cells + off, cnt * sizeof(double),
+                                cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    if (int rc = enqueue_fused_epilogue(pl, ctx->stream, d_summary)) return rc;
+  } else {
+    if (int rc = qb200_plan_run(pl, ctx->stream, d_cells, d_summary)) return rc;
+    if (ncells)
+      QB_CUDA(cudaMemcpyAsync(cells, d_cells, ncells * sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+  }
   if (sum_bytes)
-    QB_CUDA(cudaMemcpyAsync(ctx->h_summary, ctx->out_summary.p, sum_bytes,
-                            cudaMemcpyDeviceToHost, ctx->stream));
+    QB_CUDA(cudaMemcpyAsync(ctx->h_summary, d_summary, sum_bytes, cudaMemcpyDeviceToHost,
+                            ctx->stream));
   QB_CUDA(cudaStreamSynchronize(ctx->stream));
+  QB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   return qb200_plan_finish(pl, (const double*)ctx->h_summary, tp, te, flags);
 }
 
@@ -500,8 +619,13 @@ int qb200_slice2d_compute(qb200_context* ctx, const qb200_params* params, int me
                           int richardson, uint32_t dimension, uint32_t n, const int32_t* a_d,
                           const int32_t* a_r, double* cells, long double* tp, long double* te,
                           uint32_t* flags) {
+  if (!ctx || !params) return fail(-1, "null argument");
+  QB_CUDA(cudaSetDevice(ctx->device));
   qb200_plan* pl = nullptr;
-  if (int rc = qb200_plan2d_create(ctx, params, method, richardson, dimension, n, a_d, a_r, &pl))
+  // chunks of ~32 MB of results so that copies overlap compute
+  const uint64_t bytes = (uint64_t)n * dimension * dimension * sizeof(double);
+  const unsigned n_chunks = (unsigned)std::min<uint64_t>(16, std::max<uint64_t>(1, bytes >> 25));
+  if (int rc = create_plan2d(ctx, params, method, richardson, dimension, n, a_d, a_r, n_chunks, &pl))
     return rc;
   const int rc = run_sync(ctx, pl, cells, tp, te, flags);
   qb200_plan_destroy(pl);
