@@ -311,7 +311,7 @@ struct FusedArgs {
 };
 
 #ifndef QB_FUSED_MIN_CTAS
-#define QB_FUSED_MIN_CTAS 3
+#define QB_FUSED_MIN_CTAS 4
 #endif
 #define QB_TILE_RECS 161  // 5 * 32 + 1 column records per tile
 #define QB_FUSED_SMEM_BYTES \

@@ -46,7 +46,8 @@ class CriticalError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libqunundrum_b200.so")
+    # QB200_LIB: development override (A/B-testing kernel builds); the default is the in-tree build
+    return os.environ.get("QB200_LIB") or os.path.join(_HERE, "libqunundrum_b200.so")
 
 
 class _Params(C.Structure):
