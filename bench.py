@@ -286,7 +286,9 @@ def run_ours(args, rank, world, local_rank):
     value = total_cells / (ms_per_step * 1e-3)
 
     # results sanity (and the only cross-rank traffic): gather the slice summaries
-    table = shard.gather_summaries(np.arange(n), summ.cpu().numpy().reshape(n, 8), n)
+    # (weak scaling: rank k owns entries [k n, (k + 1) n) of the n * world slice table)
+    table = shard.gather_summaries(rank * n + np.arange(n), summ.cpu().numpy().reshape(n, 8),
+                                   n * world)
     tp, te, fl = plan.finish(summ.cpu().numpy())
     mass = float(tp.sum())
     if not (0.4999 < mass < 0.5):
