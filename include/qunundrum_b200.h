@@ -44,7 +44,7 @@ extern "C" {
 
 /* Distribution_Slice_Compute_Method, src/distribution_slice.h:31-78. */
 #define QB200_METHOD_HEURISTIC_SIGMA 0
-#define QB200_METHOD_OPTIMAL_LOCAL_SIGMA 1 /* rejected: not implemented */
+#define QB200_METHOD_OPTIMAL_LOCAL_SIGMA 1
 #define QB200_METHOD_QUICK 2
 
 /* One-dimensional integrands. LINEAR_D / LINEAR_R are

@@ -198,6 +198,46 @@ def probability_approx(sigma: int, theta_d, theta_r, p: Parameters):
         return norm, error, bounded
 
 
+def probability_approx_optimal_sigma(theta_d, theta_r, p: Parameters):
+    """src/probability.cpp:102-148. Returns (norm, error, sigma, bounded)."""
+    with mp.workprec(PRECISION):
+        best_norm = mp.nan
+        best_error = mp.mpf(1)
+        best_sigma = 0
+        best_bounded = False
+        for sigma in range(1, p.l - 1):
+            norm, error, bounded = probability_approx(sigma, theta_d, theta_r, p)
+            if error < best_error:
+                best_error, best_norm, best_sigma, best_bounded = error, norm, sigma, bounded
+        return best_norm, best_error, best_sigma, best_bounded
+
+
+def probability_approx_adjust_sigma(best_sigma: int, theta_d, theta_r, p: Parameters):
+    """src/probability.cpp:20-100. Returns (norm, error, sigma, bounded).
+
+    Note the reference's control flow: the first non-improving DECREASE returns
+    at once (`best_sigma != sigma` always holds there, :59-67), so the increasing
+    search (:77-93) only runs when sigma has walked down to 1."""
+    with mp.workprec(PRECISION):
+        norm, error, bounded = probability_approx(best_sigma, theta_d, theta_r, p)
+        best_norm, best_error, best_bounded = norm, error, bounded
+        sigma = best_sigma - 1
+        while sigma >= 1:
+            norm, error, bounded = probability_approx(sigma, theta_d, theta_r, p)
+            if error >= best_error:
+                return best_norm, best_error, best_sigma, best_bounded
+            best_norm, best_error, best_bounded, best_sigma = norm, error, bounded, sigma
+            sigma -= 1
+        sigma = best_sigma + 1
+        while sigma < p.l - 1:
+            norm, error, bounded = probability_approx(sigma, theta_d, theta_r, p)
+            if error >= best_error:
+                break
+            best_norm, best_error, best_bounded, best_sigma = norm, error, bounded, sigma
+            sigma += 1
+        return best_norm, best_error, best_sigma, best_bounded
+
+
 def probability_approx_quick(theta_d, theta_r, p: Parameters):
     """src/probability.cpp:290-372."""
     with mp.workprec(PRECISION):
@@ -418,11 +458,12 @@ class Slice:
 def distribution_slice_compute(p: Parameters, dimension: int,
                                min_log_alpha_d: int, min_log_alpha_r: int,
                                method: int = METHOD_HEURISTIC_SIGMA) -> Slice:
-    """src/distribution_slice_compute.cpp:38-453 (heuristic-sigma and quick
-    methods; the sigma-optimal hill climb is not restated)."""
-    if method not in (METHOD_HEURISTIC_SIGMA, METHOD_QUICK):
-        raise NotImplementedError("sigma-optimal method is not restated")
+    """src/distribution_slice_compute.cpp:38-453. For the sigma-optimal method the
+    sigma chosen at every point is kept in the returned slice's `sigmas`."""
+    if method not in (METHOD_HEURISTIC_SIGMA, METHOD_OPTIMAL_LOCAL_SIGMA, METHOD_QUICK):
+        raise ValueError("unknown method")
     sl = Slice(dimension, 2)
+    sl.sigmas = []
     n = 2 * dimension + 1
     with mp.workprec(PRECISION):
         scale = 2 * mp.pi / _pow2(p.l + p.m)
@@ -439,6 +480,14 @@ def distribution_slice_compute(p: Parameters, dimension: int,
                 theta_r = ar[j] * scale
                 if method == METHOD_QUICK:
                     norm[i][j] = probability_approx_quick(theta_d, theta_r, p)
+                elif method == METHOD_OPTIMAL_LOCAL_SIGMA:
+                    if i == 0 and j == 0:
+                        nn, ee, sigma, bb = probability_approx_optimal_sigma(theta_d, theta_r, p)
+                    else:
+                        nn, ee, sigma, bb = probability_approx_adjust_sigma(sigma, theta_d, theta_r, p)
+                    norm[i][j], err[i][j] = nn, ee
+                    bounded = bounded and bb
+                    sl.sigmas.append(sigma)
                 else:
                     nn, ee, bb = probability_approx(sigma, theta_d, theta_r, p)
                     norm[i][j], err[i][j] = nn, ee

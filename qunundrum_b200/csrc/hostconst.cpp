@@ -85,8 +85,15 @@ int host_consts_compute(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d
   // quick: theta_r * d / r with both operations rounded  src/probability.cpp:302-304
   {
     const BigFloat t = BigFloat(d, 0).rounded(kMpfrPrec);
-    const BigFloat q = BigFloat::div_rounded(t.mant, t.exp, r, kMpfrPrec);
+    BigFloat q = BigFloat::div_rounded(t.mant, t.exp, r, kMpfrPrec);
     out->kappa_q = bf_to_dd(q, /*negative=*/true);
+    // the same Q serves every sigma: rnd(rnd(2^sigma d) / r) == Q * 2^sigma exactly
+    while (q.mant.bit_length() > kMpfrPrec) {  // rounding carried into bit 192
+      q.mant = q.mant.shr(1);
+      q.exp += 1;
+    }
+    for (int i = 0; i < 3; i++) out->q_mant[i] = (size_t)i < q.mant.w.size() ? q.mant.w[i] : 0;
+    out->q_exp = (int)q.exp;
   }
   // Q = rnd(2^(m+l) / r); C = ceil(Q), N = floor(Q)     src/probability.cpp:216-220,
   //                                                     src/linear_probability.cpp:194-197

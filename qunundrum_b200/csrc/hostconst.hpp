@@ -39,6 +39,11 @@ struct HostConsts {
   DD r_m;        // r / 2^m
   DD d_m;        // d / 2^m
   DD rho;        // 2^m / r
+  // Q = rnd(rnd(d) / r) at 192 bits as mant * 2^q_exp (mant < 2^192, little-endian limbs):
+  // K_sigma = -floor(Q * 2^sigma) for EVERY sigma (the scaling by 2^sigma is exact in MPFR),
+  // which is what the sigma-optimal method needs (src/probability.cpp:20-148, 165-170).
+  uint64_t q_mant[3];
+  int q_exp;
 };
 
 // d, r: big-endian magnitude bytes (what mpz_export(buf, &n, 1, 1, 1, 0, z)

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "hostconst.hpp"
+#include "sigma_opt.cuh"
 #include "slice_cells.cuh"
 
 namespace qb200 {
@@ -48,8 +49,16 @@ inline uint32_t heuristic_sigma(uint32_t l) {
 
 inline dd to_dd(DD v) { return make_dd(v.hi, v.lo); }
 
-inline int make_dev_consts(const ParamsView& p, int method_2d, DevConsts* c, std::string* err) {
+inline int make_dev_consts(const ParamsView& p, int method_2d, DevConsts* c, std::string* err,
+                           SigmaOptConsts* so = nullptr) {
   uint32_t sigma = p.sigma;
+  if (method_2d == kMethodOptimalLocalSigma) {
+    sigma = 1;  // per-point sigma; the constants below that depend on sigma are not used
+    if (p.l < 4) {
+      *err = "l is too small for the sigma-optimal method";
+      return -3;
+    }
+  }
   if (method_2d == kMethodHeuristicSigma) {
     sigma = heuristic_sigma(p.l);
     if (sigma >= p.l) {
@@ -80,6 +89,10 @@ inline int make_dev_consts(const ParamsView& p, int method_2d, DevConsts* c, std
   c->lam_exp = method_2d == kMethodQuick ? (int)p.l : (int)p.l - (int)sigma;
   c->cs = std::ldexp(3.14159265358979323846, (int)sigma - (int)p.l);
   c->e0s = std::ldexp(1.0, 4 - (int)sigma) + std::ldexp(1.0, 3 - (int)p.l);
+  if (so) {
+    for (int i = 0; i < 3; i++) so->q_mant[i] = h.q_mant[i];
+    so->q_exp = h.q_exp;
+  }
   return 0;
 }
 
@@ -132,6 +145,7 @@ struct Plan {
   int kind = -1;       // -1: two-dimensional; else Kind1D
   int method = 0;      // 2D only
   bool with_error = false;  // 2D error-bounded approximation
+  SigmaOptConsts so;        // method == kMethodOptimalLocalSigma only
   std::vector<TabDesc> tabs_a, tabs_b;
   std::vector<SliceDesc> slices;
   std::vector<int> k_a, k_b;  // signed coordinates as given
@@ -164,11 +178,8 @@ inline int intern_table(std::map<std::pair<int, int>, int>& index, std::vector<T
 
 inline int plan_2d(const ParamsView& p, int method, int richardson, uint32_t D, uint32_t n,
                    const int32_t* a_d, const int32_t* a_r, Plan* plan, std::string* err) {
-  if (method == kMethodOptimalLocalSigma) {
-    *err = "DISTRIBUTION_SLICE_COMPUTE_METHOD_OPTIMAL_LOCAL_SIGMA is not implemented on the GPU";
-    return -10;
-  }
-  if (method != kMethodHeuristicSigma && method != kMethodQuick) {
+  if (method != kMethodHeuristicSigma && method != kMethodQuick &&
+      method != kMethodOptimalLocalSigma) {
     *err = "unknown method specified for computing the slice";
     return -11;
   }
@@ -176,13 +187,13 @@ inline int plan_2d(const ParamsView& p, int method, int richardson, uint32_t D, 
     *err = "bad slice dimension";
     return -12;
   }
-  const int rc = make_dev_consts(p, method, &plan->c, err);
+  const int rc = make_dev_consts(p, method, &plan->c, err, &plan->so);
   if (rc != 0) return rc;
   plan->D = (int)D;
   plan->richardson = richardson ? 1 : 0;
   plan->kind = -1;
   plan->method = method;
-  plan->with_error = (method == kMethodHeuristicSigma);
+  plan->with_error = (method != kMethodQuick);
   std::map<std::pair<int, int>, int> ia, ib;
   plan->slices.resize(n);
   plan->k_a.assign(a_d, a_d + n);
@@ -251,6 +262,24 @@ inline int plan_1d(const ParamsView& p, int kind, int richardson, uint32_t D, ui
 //   sum over cells of Simpson(error) * widths / 2^m, error as in
 //   src/probability.cpp:252-277, Richardson-combined as
 //   src/distribution_slice_compute_richardson.cpp:66.
+// sigma-optimal: every point has its own sigma; the device returns, per pass,
+//   A = sum w pi h n r/2^m (2 + s) 2^(sigma_p - sigma_0),  C = sum w 2^(sigma_0 - sigma_p)
+// (weights include the cell widths), and sigma_0 of the pass (kernels_sigma_opt.cuh).
+inline long double total_error_sigma_opt(const Plan& plan, size_t i, const double* s) {
+  const DevConsts& c = plan.c;
+  const int ka = (int)std::labs((long)plan.k_a[i]) - c.m;
+  const int kb = (int)std::labs((long)plan.k_b[i]) - c.m;
+  const int packed = (int)s[7];
+  const int s0c = packed % 65536, s0f = packed / 65536;
+  const long double konst = ldexpl(1.0L, 3 - c.l + ka + kb);
+  const long double ec =
+      ldexpl((long double)s[2], s0c - c.l) + ldexpl((long double)s[3], 4 - s0c) + konst;
+  if (!plan.richardson) return ec;
+  const long double ef =
+      ldexpl((long double)s[5], s0f - c.l) + ldexpl((long double)s[6], 4 - s0f) + konst;
+  return 2.0L * ef - ec;
+}
+
 inline long double total_error_2d(const Plan& plan, size_t i, double m1, double m2) {
   if (!plan.with_error) return 0.0L;
   const DevConsts& c = plan.c;

@@ -14,6 +14,7 @@
 #include "../../include/qunundrum_b200.h"
 #include "kernels_fused2d.cuh"
 #include "kernels_plain.cuh"
+#include "kernels_sigma_opt.cuh"
 #include "plan.hpp"
 
 using namespace qb200;
@@ -126,9 +127,13 @@ struct qb200_plan {
   // fused path
   FusedPlan2D fused;
   DevBuf fused_part, fused_cols, fused_slices;
+  // sigma-optimal scratch
+  DevBuf so_sigma, so_guess, so_norm, so_erra, so_sigma0, so_status, so_changed;
   void bind_pool(Pool* pool) {
     DevBuf* all[] = {&desc_a, &desc_b, &slices, &tab_a, &tab_b, &cells_c, &cells_f, &part_c,
-                     &part_f, &part_tp, &values, &fused_part, &fused_cols, &fused_slices};
+                     &part_f, &part_tp, &values, &fused_part, &fused_cols, &fused_slices,
+                     &so_sigma, &so_guess, &so_norm, &so_erra, &so_sigma0, &so_status,
+                     &so_changed};
     for (DevBuf* b : all) b->pool = pool;
   }
 };
@@ -231,7 +236,96 @@ int reserve_plain(qb200_plan* pl) {
   return 0;
 }
 
+// The sigma-optimal method: fixed-point iteration of the reference's serial walk (see
+// kernels_sigma_opt.cuh). Synchronises `st` between iterations (convergence flag).
+int run_sigma_opt_2d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_summary) {
+  const Plan& h = pl->host;
+  qb200_context* ctx = pl->ctx;
+  if (pl->n == 0) return 0;
+  const int D = h.D;
+  SoLayout L;
+  L.D = D;
+  L.passes = h.richardson ? 2 : 1;
+  L.n_c = (2 * D + 1) * (2 * D + 1);
+  L.n_f = h.richardson ? (4 * D + 1) * (4 * D + 1) : 0;
+  L.stride = L.n_c + L.n_f;
+  const size_t per_slice = (size_t)L.stride * 24 + (size_t)5 * D * D * 8;
+  uint32_t chunk = (uint32_t)std::max<size_t>(1, (size_t(1) << 29) / per_slice);
+  chunk = std::min<uint32_t>(std::min<uint32_t>(chunk, pl->n), 16384);
+  const int nb_c = (D * D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+  const int nb_f = (4 * D * D + QB_PLAIN_BLOCK - 1) / QB_PLAIN_BLOCK;
+  const size_t pts = (size_t)chunk * L.stride;
+  if (int rc = pl->so_sigma.reserve(pts * sizeof(int))) return rc;
+  if (int rc = pl->so_guess.reserve(pts * sizeof(int))) return rc;
+  if (int rc = pl->so_norm.reserve(pts * sizeof(double))) return rc;
+  if (int rc = pl->so_erra.reserve(pts * sizeof(double))) return rc;
+  if (int rc = pl->so_sigma0.reserve((size_t)chunk * 2 * sizeof(int))) return rc;
+  if (int rc = pl->so_status.reserve((size_t)chunk * 2 * sizeof(int))) return rc;
+  if (int rc = pl->so_changed.reserve(sizeof(int))) return rc;
+  if (int rc = pl->cells_c.reserve((size_t)chunk * D * D * sizeof(double))) return rc;
+  if (h.richardson)
+    if (int rc = pl->cells_f.reserve((size_t)chunk * 4 * D * D * sizeof(double))) return rc;
+  if (int rc = pl->part_c.reserve((size_t)chunk * nb_c * 3 * sizeof(double))) return rc;
+  if (int rc = pl->part_f.reserve((size_t)chunk * nb_f * 3 * sizeof(double))) return rc;
+  if (int rc = pl->part_tp.reserve((size_t)chunk * nb_c * 2 * sizeof(double))) return rc;
+
+  const int NP = table_points(D);
+  const int n_a = (int)h.tabs_a.size(), n_b = (int)h.tabs_b.size();
+  k_axis2d<<<dim3((NP + 127) / 128, n_a + n_b), 128, 0, st>>>(
+      h.c, NP, n_a, pl->desc_a.as<TabDesc>(), pl->desc_b.as<TabDesc>(), pl->geo->gx.as<dd>(),
+      pl->tab_a.as<AxisD>(), pl->tab_b.as<AxisR>());
+  ctx->launches++;
+  const TabDesc* da = pl->desc_a.as<TabDesc>();
+  const TabDesc* db = pl->desc_b.as<TabDesc>();
+  const dd* gx = pl->geo->gx.as<dd>();
+  const AxisR* tb = pl->tab_b.as<AxisR>();
+  int* sigma0 = pl->so_sigma0.as<int>();
+  int* status = pl->so_status.as<int>();
+  int* changed = pl->so_changed.as<int>();
+  for (uint32_t s0 = 0; s0 < pl->n; s0 += chunk) {
+    const uint32_t ns = std::min(chunk, pl->n - s0);
+    const DevSlice* sl = pl->slices.as<DevSlice>() + s0;
+    const unsigned pairs = ns * (unsigned)L.passes;
+    QB_CUDA(cudaMemsetAsync(status, 0, pairs * sizeof(int), st));
+    k_so_first<<<pairs, 256, 0, st>>>(h.c, h.so, L, sl, da, db, gx, tb, sigma0);
+    const size_t npts = (size_t)ns * L.stride;
+    k_so_fill<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(npts, L, sigma0, pl->so_guess.as<int>());
+    ctx->launches += 2;
+    const int max_pts = h.richardson ? L.n_f : L.n_c;
+    int iter = 0, moved = 1;
+    while (moved) {
+      if (++iter > 4096) return fail(-30, "sigma-optimal walk did not converge");
+      QB_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+      k_so_step<<<dim3((max_pts + 127) / 128, pairs), 128, 0, st>>>(
+          h.c, h.so, L, sl, da, db, gx, tb, sigma0, pl->so_guess.as<int>(), pl->so_sigma.as<int>(),
+          pl->so_norm.as<double>(), pl->so_erra.as<double>(), status);
+      k_so_scan<<<pairs, 1024, 0, st>>>(L, pl->so_sigma.as<int>(), pl->so_guess.as<int>(), changed);
+      ctx->launches += 2;
+      QB_CUDA(cudaMemcpyAsync(&moved, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+      QB_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int pass = 0; pass < L.passes; pass++) {
+      k_so_cells<<<dim3(pass ? nb_f : nb_c, ns), QB_PLAIN_BLOCK, 0, st>>>(
+          h.c, L, pass, sl, pl->geo->gw.as<double>(), sigma0, pl->so_sigma.as<int>(),
+          pl->so_norm.as<double>(), pl->so_erra.as<double>(),
+          pass ? pl->cells_f.as<double>() : pl->cells_c.as<double>(),
+          pass ? pl->part_f.as<double>() : pl->part_c.as<double>());
+      ctx->launches++;
+    }
+    k_rich2d<<<dim3(nb_c, ns), QB_PLAIN_BLOCK, 0, st>>>(
+        D, h.richardson, pl->cells_c.as<double>(), pl->cells_f.as<double>(),
+        d_cells + (size_t)s0 * D * D, pl->part_tp.as<double>());
+    k_so_final<<<(ns + 127) / 128, 128, 0, st>>>(
+        (int)ns, L, nb_c, nb_f, nb_c, pl->part_c.as<double>(), pl->part_f.as<double>(),
+        pl->part_tp.as<double>(), sigma0, status, d_summary + (size_t)s0 * QB200_SUMMARY_STRIDE);
+    ctx->launches += 2;
+  }
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int run_plain_2d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_summary) {
+  if (pl->host.method == kMethodOptimalLocalSigma) return run_sigma_opt_2d(pl, st, d_cells, d_summary);
   if (!pl->plain_ready) {
     if (int rc = reserve_plain(pl)) return rc;
     pl->plain_ready = true;
@@ -325,6 +419,10 @@ uint32_t plain_launches(const qb200_plan* pl) {
 int setup_fused(qb200_plan* pl, unsigned n_chunks) {
   pl->fused_ok = 0;
   if (pl->host.kind >= 0) return 0;
+  if (pl->host.method == kMethodOptimalLocalSigma) {
+    pl->fused_why = "the sigma-optimal method runs on the point-array kernels";
+    return 0;
+  }
   if (!fused2d_prepare(pl->host, n_chunks, &pl->fused, &pl->fused_why)) return 0;
   if (int rc = pl->fused_part.reserve(std::max<size_t>(1, pl->fused.k.n_tiles) *
                                       QB_FUSED_PART_STRIDE * sizeof(double)))
@@ -548,7 +646,13 @@ int qb200_plan_finish(const qb200_plan* plan, const double* hs, long double* tp,
   for (uint32_t i = 0; i < plan->n; i++) {
     const double* s = hs + (size_t)i * QB200_SUMMARY_STRIDE;
     if (tp) tp[i] = (long double)s[0] + (long double)s[1];
-    if (te) te[i] = h.kind < 0 ? total_error_2d(h, i, s[2], s[3]) : 0.0L;
+    const bool so = h.kind < 0 && h.method == kMethodOptimalLocalSigma;
+    if (so && s[4] < 0.0)
+      return fail(-31,
+                  "sigma-optimal method: no admissible sigma at the first point, or the walk "
+                  "reached sigma = 1 (increasing search); not supported on the GPU");
+    if (te) te[i] = so ? total_error_sigma_opt(h, i, s)
+                       : (h.kind < 0 ? total_error_2d(h, i, s[2], s[3]) : 0.0L);
     if (flags) {
       uint32_t f = kFlagMethodSimpson | (h.richardson ? kFlagMethodRichardson : 0u);
       if (h.kind < 0 && h.with_error) {

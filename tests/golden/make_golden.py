@@ -75,6 +75,11 @@ def main():
         ("c4", 3072, 4, "det", 32, 1, 0, [(3075, 3074), (-3060, 3082), (3072, 3072)]),
         ("odd", 256, 3, "det", 12, 1, 0, [(256, 257), (-250, 255)]),
         ("c2d64", 2048, 1, "syn", 64, 1, 0, [(2049, 2049)]),
+        # sigma-optimal method (-sigma-optimal; docs/pages/info-distribution.md uses it at s = 30)
+        ("c1o", 128, 2, "det", 32, 1, 1, [(130, 129), (128, 128), (-127, 126), (136, 135)]),
+        ("s30o", 2048, 30, "det", 32, 1, 1, [(2049, 2047), (-2048, 2048), (2040, 2044)]),
+        ("c2o", 2048, 1, "syn", 8, 1, 1, [(2048, 2048), (-2050, 2049)]),
+        ("c1os", 128, 2, "det", 16, 0, 1, [(129, 128)]),
     ]
     for tag, m, s, src, D, rich, method, coords in cases2d:
         d, r = synthetic_d_r(m, 20482048) if src == "syn" else ref.deterministic_d_r(m)

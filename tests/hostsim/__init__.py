@@ -16,7 +16,7 @@ _LIB = os.path.join(_HERE, "_build", "libhostsim.so")
 _SRCS = [os.path.join(_HERE, "hostsim.cpp"),
          os.path.join(_ROOT, "qunundrum_b200", "csrc", "hostconst.cpp")]
 _DEPS = _SRCS + [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
-                 ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "plan.hpp",
+                 ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "sigma_opt.cuh", "plan.hpp",
                   "hostconst.hpp", "bigint.hpp")]
 _lib = None
 

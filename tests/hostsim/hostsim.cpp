@@ -82,6 +82,104 @@ int hostsim_slice2d(uint32_t m, uint32_t l, const uint8_t* d, size_t dn, const u
                    &tb[t * NP + i]);
   const int Dc = (int)D;
   std::vector<double> fine((size_t)4 * Dc * Dc);
+  if (method == kMethodOptimalLocalSigma) {
+    // Serial walk of the reference (src/distribution_slice_compute.cpp:265-287) with the same
+    // per-point functions the kernels use (sigma_opt.cuh).
+    for (uint32_t s = 0; s < n; s++) {
+      const SliceDesc& sd = plan.slices[s];
+      double* out = cells + (size_t)s * Dc * Dc;
+      double summ[8] = {0, 0, 0, 0, 1, 0, 0, 0};
+      int s0[2] = {0, 0};
+      bool bounded = true;
+      for (int pass = 0; pass <= plan.richardson; pass++) {
+        const int Dp = pass ? 2 * Dc : Dc, side = 2 * Dp + 1, off = pass_offset(Dc, pass);
+        std::vector<double> nrm((size_t)side * side), era((size_t)side * side);
+        std::vector<int> sg((size_t)side * side);
+        std::vector<char> okp((size_t)side * side);
+        int sigma = 0;
+        for (int i = 0; i < side; i++)
+          for (int j = 0; j < side; j++) {
+            SoPoint pt;
+            pt.xd_ = grid_x(make_dd(geo.gx[off + i].hi, geo.gx[off + i].lo),
+                            plan.tabs_a[sd.tab_a].k_abs, plan.tabs_a[sd.tab_a].sign, plan.c.m);
+            pt.xr_ = grid_x(make_dd(geo.gx[off + j].hi, geo.gx[off + j].lo),
+                            plan.tabs_b[sd.tab_b].k_abs, plan.tabs_b[sd.tab_b].sign, plan.c.m);
+            pt.t2 = tb[(size_t)sd.tab_b * NP + off + j].t2;
+            pt.h = fabs(pt.xd_.hi) + fabs(pt.xr_.hi);
+            double nn;
+            xd ee;
+            if (i == 0 && j == 0) {
+              xd best = xd_make(1.0, plan.c.m);
+              for (int t = 1; t < plan.c.l - 1; t++) {
+                so_eval(plan.c, plan.so, pt, t, &nn, &ee);
+                if (xd_less(ee, best)) {
+                  best = ee;
+                  sigma = t;
+                }
+              }
+              if (sigma == 0) {
+                g_err = "no admissible sigma";
+                return -31;
+              }
+              s0[pass] = sigma;
+              so_eval(plan.c, plan.so, pt, sigma, &nn, &ee);
+            } else {
+              bool inc;
+              sigma = so_adjust(plan.c, plan.so, pt, sigma, &nn, &ee, &inc);
+            }
+            const size_t p = (size_t)i * side + j;
+            const int sl = sigma - plan.c.l;
+            const double ph = 3.14159265358979323846 * pt.h;
+            const double sv = sl > -1000 ? ldexp(ph, sl) : 0.0;
+            nrm[p] = nn;
+            era[p] = ldexp(ph * (2.0 + sv) * nn * plan.c.r_m, sigma - s0[pass]);
+            sg[p] = sigma;
+            okp[p] = so_bounded(plan.c, nn, ee);
+          }
+        const double* gw = geo.gw.data() + width_offset(Dc, pass);
+        double* dst = pass ? fine.data() : out;
+        double A = 0, Cc = 0;
+        const double w3[3] = {1.0, 4.0, 1.0};
+        for (int J = 0; J < Dp; J++)
+          for (int I = 0; I < Dp; I++) {
+            double acc = 0, a_ = 0, c_ = 0;
+            for (int a = 0; a < 3; a++)
+              for (int b = 0; b < 3; b++) {
+                const size_t p = (size_t)(2 * I + a) * side + (2 * J + b);
+                acc += w3[a] * w3[b] * nrm[p];
+                a_ += w3[a] * w3[b] * era[p];
+                c_ += w3[a] * w3[b] * ldexp(1.0, s0[pass] - sg[p]);
+                if (pass == 0) bounded = bounded && okp[p];
+              }
+            const double f = (gw[I] * sd.scale_a) * (gw[J] * sd.scale_b) / 36.0;
+            dst[I + (size_t)Dp * J] = acc * f * plan.c.r_m;
+            A += a_ * f;
+            Cc += c_ * f;
+          }
+        summ[pass ? 5 : 2] = A;
+        summ[pass ? 6 : 3] = Cc;
+      }
+      summ[7] = (double)(s0[0] + 65536 * s0[1]);
+      long double tp = 0;
+      if (plan.richardson) {
+        for (int i = 0; i < Dc; i++)
+          for (int j = 0; j < Dc; j++) {
+            const size_t F = (size_t)2 * Dc;
+            const double f = fine[F * (2 * j) + 2 * i] + fine[F * (2 * j) + 2 * i + 1] +
+                             fine[F * (2 * j + 1) + 2 * i] + fine[F * (2 * j + 1) + 2 * i + 1];
+            out[(size_t)Dc * j + i] = 2.0 * f - out[(size_t)Dc * j + i];
+            tp += out[(size_t)Dc * j + i];
+          }
+      } else {
+        for (size_t i = 0; i < (size_t)Dc * Dc; i++) tp += out[i];
+      }
+      total_probability[s] = tp;
+      total_error[s] = total_error_sigma_opt(plan, s, summ);
+      flags[s] = kFlagMethodSimpson | (plan.richardson ? kFlagMethodRichardson : 0u) |
+                 (!bounded ? kFlagErrorBoundWarning : 0u);
+    }
+    return 0;
+  }
   for (uint32_t s = 0; s < n; s++) {
     const SliceDesc& sd = plan.slices[s];
     double* out = cells + (size_t)s * Dc * Dc;

@@ -123,8 +123,8 @@ def test_reference_entry_points(gpu_ctx):
         ds, qb.Diagonal_Parameters(128, 5, 1, g.d, g.r, eta_bound=25), 126, -1, ctx=gpu_ctx)
     assert cell_errors(ds.norm_vector, g.cells) <= CELL_RTOL and ds.eta == -1 and ds.min_log_alpha_r == 126
 
-    with pytest.raises(qb.CriticalError, match="OPTIMAL_LOCAL_SIGMA"):
-        qb.distribution_slice_compute_richardson(qb.Distribution_Slice(32), P, 1, 130, 129, ctx=gpu_ctx)
+    with pytest.raises(qb.CriticalError, match="[Uu]nknown method"):
+        qb.distribution_slice_compute_richardson(qb.Distribution_Slice(32), P, 7, 130, 129, ctx=gpu_ctx)
     with pytest.raises(qb.CriticalError, match="Unknown target"):
         qb.linear_distribution_slice_compute(qb.Linear_Distribution_Slice(32), P, 3, 128, ctx=gpu_ctx)
 
@@ -204,6 +204,25 @@ def test_full_size_properties(gpu_ctx):
     assert cell_errors(c_a[k], rich) <= 1e-10
     plan.close()
     sub.close()
+
+
+def test_sigma_optimal_matches_reference_on_this_box(gpu_ctx):
+    """-sigma-optimal: the parallel fixed-point solution of the reference's serial walk."""
+    ref = ref_or_none()
+    if ref is None:
+        pytest.skip("oracle/_ref/libqref.so not present")
+    for (m, s, D, coords) in ((2048, 30, 16, [(2050, 2049), (-2047, 2046), (2056, 2057)]),
+                              (256, 3, 12, [(256, 255), (-259, 258)])):
+        d, r = ref.deterministic_d_r(m)
+        P, RP = qb.Parameters(m, s, d, r), ref.RefParameters(m, s, d, r)
+        ad, ar = [c[0] for c in coords], [c[1] for c in coords]
+        cells, tp, te, fl = gpu_ctx.slice2d_batch(P, 1, True, D, ad, ar)
+        for i in range(len(coords)):
+            R = ref.distribution_slice_compute(RP, D, ad[i], ar[i], method=1)
+            assert cell_errors(cells[i], R.cells) <= CELL_RTOL, (m, coords[i])
+            assert abs(float(tp[i] - R.total_probability)) <= 1e-12
+            assert abs(float((te[i] - R.total_error) / R.total_error)) <= 1e-9
+            assert int(fl[i]) == R.flags
 
 
 def test_empty_and_ragged_batches(gpu_ctx):
