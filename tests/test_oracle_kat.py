@@ -150,7 +150,7 @@ def test_restatement_matches_golden_slices():
     done = 0
     for g in golden_slices():
         k = g.meta
-        if k["kind"] == "2d" and k["D"] <= 16:
+        if k["kind"] == "2d" and k["D"] <= 16 and not (k["method"] == 1 and k["m"] > 1024):
             P = rs.Parameters(k["m"], k["s"], g.d, g.r)
             f = rs.distribution_slice_compute_richardson if k["richardson"] else rs.distribution_slice_compute
             sl = f(P, k["D"], k["a_d"], k["a_r"], k["method"])
