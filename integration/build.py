@@ -1,0 +1,93 @@
+"""Build the reference's own generator executables, unmodified, in two flavours:
+
+  integration/_build/ref/generate_*   the reference's slice integrators (MPFR, CPU)
+  integration/_build/gpu/generate_*   the six integrator TUs replaced by
+                                      qunundrum_b200/dropin/dropin.cpp + libqunundrum_b200.so
+
+INTEGRATION-TEST INFRASTRUCTURE. Sources are compiled where they lie under /root/reference/src
+(never copied); neither OpenMPI nor fpLLL nor the GMP/MPFR development headers exist in this
+image, so the build uses integration/minimpi (a minimal single-node MPI over socket pairs),
+integration/stubs (a compile-only fpLLL stand-in: generation never reduces a lattice) and the
+declaration shims of oracle/shims. With the real toolchain a maintainer follows INTEGRATION.md
+instead. The built binaries travel to the GPU box; /root/reference is not needed at run time.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(HERE, "_build")
+LIBDIR = "/lib/x86_64-linux-gnu"
+
+COMMON_CPP = """math rsa parameters diagonal_parameters parameters_selection sample
+ probability linear_probability diagonal_probability
+ distribution distribution_enumerator distribution_info distribution_mpi distribution_slice
+ distribution_slice_mpi distribution_slice_import_export
+ linear_distribution linear_distribution_enumerator linear_distribution_info linear_distribution_mpi
+ linear_distribution_slice linear_distribution_slice_mpi linear_distribution_slice_import_export
+ diagonal_distribution diagonal_distribution_enumerator diagonal_distribution_info
+ diagonal_distribution_mpi diagonal_distribution_slice diagonal_distribution_slice_mpi
+ diagonal_distribution_slice_import_export""".split()
+COMMON_C = "errors random keccak keccak_random gmp_mpi mpfr_mpi string_utilities thread_pool debug_common".split()
+INTEGRATORS = """distribution_slice_compute distribution_slice_compute_richardson
+ linear_distribution_slice_compute linear_distribution_slice_compute_richardson
+ diagonal_distribution_slice_compute diagonal_distribution_slice_compute_richardson""".split()
+MAINS = ["generate_distribution", "generate_linear_distribution", "generate_linear_distribution_rsa",
+         "generate_diagonal_distribution"]
+
+
+def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
+    src = os.path.join(reference_root, "src")
+    done = os.path.join(OUT, ".done")
+    if not os.path.isdir(src):
+        return os.path.exists(done)
+    deps = [os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin.cpp"),
+            os.path.join(HERE, "minimpi", "minimpi.c"), os.path.join(HERE, "minimpi", "mpi.h"),
+            os.path.join(HERE, "build.py"), os.path.join(ROOT, "include", "qunundrum_b200.h")]
+    if not force and os.path.exists(done) and all(
+            os.path.getmtime(d) <= os.path.getmtime(done) for d in deps):
+        return True
+    obj = os.path.join(OUT, "obj")
+    for d in (obj, os.path.join(OUT, "ref"), os.path.join(OUT, "gpu")):
+        os.makedirs(d, exist_ok=True)
+    inc = ["-I", os.path.join(HERE, "minimpi"), "-I", os.path.join(HERE, "stubs"),
+           "-I", os.path.join(ROOT, "oracle", "shims"), "-I", os.path.join(ROOT, "include"),
+           "-iquote", src]
+    jobs = []
+    for f in COMMON_CPP + INTEGRATORS + ["main_" + m for m in MAINS]:
+        jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *inc, "-c",
+                     os.path.join(src, f + ".cpp"), "-o", os.path.join(obj, f + ".o")])
+    for f in COMMON_C:
+        jobs.append(["gcc", "-O2", "-w", *inc, "-c", os.path.join(src, f + ".c"),
+                     "-o", os.path.join(obj, f + ".o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
+                 os.path.join(HERE, "stubs", "lattice_stub.cpp"), "-o", os.path.join(obj, "lattice_stub.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
+                 os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin.cpp"),
+                 "-o", os.path.join(obj, "dropin.o")])
+    jobs.append(["gcc", "-O2", "-c", os.path.join(HERE, "minimpi", "minimpi.c"),
+                 "-o", os.path.join(obj, "minimpi.o")])
+    with ThreadPoolExecutor(8) as ex:
+        list(ex.map(subprocess.check_call, jobs))
+    subprocess.check_call(["gcc", "-O2", os.path.join(HERE, "minimpi", "minimpirun.c"),
+                           "-o", os.path.join(OUT, "minimpirun")])
+    common = [os.path.join(obj, f + ".o") for f in COMMON_CPP + COMMON_C + ["lattice_stub", "minimpi"]]
+    libs = [os.path.join(LIBDIR, "libmpfr.so.6"), os.path.join(LIBDIR, "libgmp.so.10"), "-lpthread", "-lm"]
+    for m in MAINS:
+        main_o = os.path.join(obj, "main_" + m + ".o")
+        subprocess.check_call(["g++", main_o, *common, *[os.path.join(obj, f + ".o") for f in INTEGRATORS],
+                               *libs, "-o", os.path.join(OUT, "ref", m)])
+        subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "dropin.o"),
+                               "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
+                               "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
+                               "-o", os.path.join(OUT, "gpu", m)])
+    open(done, "w").write("ok\n")
+    return True
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

@@ -71,6 +71,11 @@ void __gmpz_sub(mpz_ptr, mpz_srcptr, mpz_srcptr);
 void __gmpz_sub_ui(mpz_ptr, mpz_srcptr, unsigned long);
 #define mpz_mul __gmpz_mul
 void __gmpz_mul(mpz_ptr, mpz_srcptr, mpz_srcptr);
+#define mpz_mul_si __gmpz_mul_si
+void __gmpz_mul_si(mpz_ptr, mpz_srcptr, long);
+#define mpz_div __gmpz_fdiv_q
+#define mpz_invert __gmpz_invert
+int __gmpz_invert(mpz_ptr, mpz_srcptr, mpz_srcptr);
 #define mpz_mul_ui __gmpz_mul_ui
 void __gmpz_mul_ui(mpz_ptr, mpz_srcptr, unsigned long);
 #define mpz_mul_2exp __gmpz_mul_2exp

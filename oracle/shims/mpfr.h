@@ -81,6 +81,20 @@ int mpfr_div(mpfr_ptr, mpfr_srcptr, mpfr_srcptr, mpfr_rnd_t);
 int mpfr_div_ui(mpfr_ptr, mpfr_srcptr, unsigned long, mpfr_rnd_t);
 int mpfr_div_z(mpfr_ptr, mpfr_srcptr, mpz_srcptr, mpfr_rnd_t);
 int mpfr_sqrt(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);
+int mpfr_add_z(mpfr_ptr, mpfr_srcptr, mpz_srcptr, mpfr_rnd_t);
+int mpfr_sub_z(mpfr_ptr, mpfr_srcptr, mpz_srcptr, mpfr_rnd_t);
+int mpfr_mul_d(mpfr_ptr, mpfr_srcptr, double, mpfr_rnd_t);
+int mpfr_div_d(mpfr_ptr, mpfr_srcptr, double, mpfr_rnd_t);
+int mpfr_add_d(mpfr_ptr, mpfr_srcptr, double, mpfr_rnd_t);
+int mpfr_sub_d(mpfr_ptr, mpfr_srcptr, double, mpfr_rnd_t);
+int mpfr_fmod(mpfr_ptr, mpfr_srcptr, mpfr_srcptr, mpfr_rnd_t);
+void mpfr_set_inf(mpfr_ptr, int);
+void mpfr_set_nan(mpfr_ptr);
+void mpfr_set_zero(mpfr_ptr, int);
+int mpfr_printf(const char *, ...);
+int mpfr_fprintf(FILE *, const char *, ...);
+int mpfr_sprintf(char *, const char *, ...);
+int mpfr_snprintf(char *, size_t, const char *, ...);
 
 int mpfr_sin(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);
 int mpfr_cos(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);

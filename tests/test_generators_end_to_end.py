@@ -1,0 +1,87 @@
+"""The reference's own, unmodified generator executables (argv parsing, MPI master-worker
+protocol, enumerators, containers, sort, text export) with the six slice-integration TUs
+replaced by the drop-in, against the same executables with the reference's integrators:
+the .txt distribution files must agree slice for slice.
+
+Binaries are built by integration/build.py where /root/reference is mounted and travel to the
+GPU box; MPI is integration/minimpi (no MPI implementation is installed in this image)."""
+import os
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B = os.path.join(ROOT, "integration", "_build")
+
+
+def _have():
+    return os.path.exists(os.path.join(B, ".done"))
+
+
+def _run(flavour, exe, args, np_, cwd, env=None):
+    os.makedirs(os.path.join(cwd, "distributions"), exist_ok=True)
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([os.path.join(B, "minimpirun"), "-np", str(np_), os.path.join(B, flavour, exe), *args],
+                       cwd=cwd, env=e, capture_output=True, text=True, timeout=3000)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def _files(cwd):
+    d = os.path.join(cwd, "distributions")
+    return sorted(f for f in os.listdir(d) if f.endswith(".txt"))
+
+
+def test_minimpi_runs_the_reference_generator_on_cpu():
+    """BASELINE config 0 shape (linear, m = 128, s = 2, MPI world_size = 2), reference integrators,
+    small dimension so that it takes a second: protocol + export work under integration/minimpi."""
+    if not _have():
+        pytest.skip("integration/_build missing (needs /root/reference at build time)")
+    from integration import distfile
+    with tempfile.TemporaryDirectory() as t:
+        out = _run("ref", "generate_linear_distribution", ["-d", "-dim", "64", "-det", "128", "2"], 2, t)
+        assert "Stopping node 1" in out
+        f = _files(t)
+        assert f == ["linear-distribution-det-dim-64-d-m-128-s-2.txt"]
+        d = distfile.read(os.path.join(t, "distributions", f[0]), "linear")
+        assert d.header["m"] == 128 and d.header["l"] == 64 and len(d.slices) == 82
+        mass = float(sum(s["cells"].sum() for s in d.slices.values()))
+        assert abs(mass - 0.9999038946) < 1e-4    # docs/pages/info-linear-distribution.md (dimension 2048)
+
+
+CASES = [
+    # exe, args, kind, ranks  (ranks = 1 server + clients, all clients share cuda:0 here)
+    ("generate_linear_distribution", ["-d", "-dim", "2048", "-det", "128", "2"], "linear", 2),
+    ("generate_linear_distribution", ["-r", "-dim", "512", "-det", "128", "2"], "linear", 3),
+    ("generate_diagonal_distribution", ["-dim", "512", "-det", "-eta-bound", "1", "128", "5", "2"], "diagonal", 3),
+    ("generate_distribution", ["-det", "-dim", "16", "128", "2"], "2d", 3),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe,args,kind,ranks", CASES, ids=[c[0] + "-" + c[2] + str(i) for i, c in enumerate(CASES)])
+def test_generator_with_dropin_matches_reference_generator(exe, args, kind, ranks):
+    if not _have():
+        pytest.skip("integration/_build missing")
+    from integration import distfile
+    ta, tb = tempfile.mkdtemp(), tempfile.mkdtemp()
+    try:
+        _run("gpu", exe, args, ranks, ta, env={"QB200_DEVICE": "0"})
+        _run("ref", exe, args, 9, tb)
+        fa, fb = _files(ta), _files(tb)
+        assert fa == fb and len(fa) >= 1
+        for f in fa:
+            # collapsed-d / collapsed-r marginals of a 2D distribution are linear distributions;
+            # filtered-* files hold the slices that survive the error filter (selection parity)
+            k = "linear" if f.startswith("collapsed-") else kind
+            a = distfile.read(os.path.join(ta, "distributions", f), k)
+            b = distfile.read(os.path.join(tb, "distributions", f), k)
+            rep = distfile.compare(a, b)
+            print(f, rep)
+            assert rep["slices"] > 10
+    finally:
+        shutil.rmtree(ta, ignore_errors=True)
+        shutil.rmtree(tb, ignore_errors=True)
