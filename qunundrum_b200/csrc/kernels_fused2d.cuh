@@ -264,7 +264,7 @@ __device__ __forceinline__ double eval_cls(const RowReg& r, const ColRec& c, con
     T1 = eval_main<MODE>(r1, c_, k, u1_);                                                   \
     T2 = eval_main<MODE>(r2, c_, k, u2_);                                                   \
     T3 = eval_main<MODE>(r3, c_, k, u3_);                                                   \
-    if (min(min(abs_hi(u0_), abs_hi(u1_)), min(abs_hi(u2_), abs_hi(u3_))) < QB_SMALL_U) {   \
+    if (RIDGE && min(min(abs_hi(u0_), abs_hi(u1_)), min(abs_hi(u2_), abs_hi(u3_))) < QB_SMALL_U) { \
       if (abs_hi(u0_) < QB_SMALL_U) T0 = eval_small<MODE>(u0_, k);                          \
       if (abs_hi(u1_) < QB_SMALL_U) T1 = eval_small<MODE>(u1_, k);                          \
       if (abs_hi(u2_) < QB_SMALL_U) T2 = eval_small<MODE>(u2_, k);                          \
@@ -281,7 +281,7 @@ __device__ __forceinline__ double eval_cls(const RowReg& r, const ColRec& c, con
   if (CLS == 0) {                                                      \
     double u_;                                                         \
     T = eval_main<MODE>(row_, c_, k, u_);                              \
-    if (abs_hi(u_) < QB_SMALL_U) T = eval_small<MODE>(u_, k);          \
+    if (RIDGE && abs_hi(u_) < QB_SMALL_U) T = eval_small<MODE>(u_, k); \
   } else {                                                             \
     T = eval_cls<MODE, CLS>(row_, c_, k);                              \
   }
@@ -291,7 +291,7 @@ __device__ __forceinline__ double eval_cls(const RowReg& r, const ColRec& c, con
     double ua_, ub_;                                                    \
     Ta = eval_main<MODE>(rowa_, c_, k, ua_);                            \
     Tb = eval_main<MODE>(rowb_, c_, k, ub_);                            \
-    if (min(abs_hi(ua_), abs_hi(ub_)) < QB_SMALL_U) {                   \
+    if (RIDGE && min(abs_hi(ua_), abs_hi(ub_)) < QB_SMALL_U) {          \
       if (abs_hi(ua_) < QB_SMALL_U) Ta = eval_small<MODE>(ua_, k);      \
       if (abs_hi(ub_) < QB_SMALL_U) Tb = eval_small<MODE>(ub_, k);      \
     }                                                                   \
@@ -330,52 +330,6 @@ __device__ __forceinline__ ColRec load_col_s(const double* p) {
   return r;
 }
 
-template <int MODE, int CLS, bool HAS_ERR, bool HAS_M2, bool HAS_BOUND>
-__global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fused2d(FusedArgs a) {
-  extern __shared__ __align__(16) double s_dyn[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const FusedConst& k = a.k;
-  const unsigned tile = k.tile_base + blockIdx.x * QB_FUSED_WARPS + warp;
-  if (tile >= k.tile_end) return;
-  double* s_cols = s_dyn + warp * (QB_TILE_RECS * QB_FUSED_REC + 2 * 32);
-  double* s_halo = s_cols + QB_TILE_RECS * QB_FUSED_REC;  // [2][32]
-  const int D = k.D, nb = k.nb;
-  const unsigned per_slice = (unsigned)(nb * nb);
-  const unsigned sidx = tile / per_slice;
-  const unsigned rem = tile - sidx * per_slice;
-  const int jc = (int)(rem / (unsigned)nb), ib = (int)(rem - (unsigned)jc * nb);
-  const int I0 = ib * 32, J0 = jc * 32, I = I0 + lane;
-  const FusedSlice s = a.slices[sidx];
-  const AxisD* tdc = a.tab_a + (size_t)s.tab_a * k.NP;
-  const AxisD* tdf = tdc + (2 * D + 1);
-  const double* gwc = a.gw;
-  const double* gwf = a.gw + D;
-
-  // ---- stage the tile's 161 column records in shared memory (per warp) ---------
-  {
-    const double2* g =
-        (const double2*)(a.cols + ((size_t)s.tab_b * k.ncol + (size_t)5 * J0) * QB_FUSED_REC);
-    double2* sh = (double2*)s_cols;
-#pragma unroll 4
-    for (int i = lane; i < QB_TILE_RECS * QB_FUSED_REC / 2; i += 32) sh[i] = __ldg(g + i);
-  }
-
-  // alpha_d rows of this lane: fine h = 4 I .. 4 I + 3 and the coarse mid point.
-  const RowReg r0 = load_row(tdf + 4 * I);
-  const RowReg r1 = load_row(tdf + 4 * I + 1);
-  const RowReg r2 = load_row(tdf + 4 * I + 2);
-  const RowReg r3 = load_row(tdf + 4 * I + 3);
-  const RowReg rc = load_row(tdc + 2 * I + 1);
-  const double fd = s.scale_a * k.r_m / 6.0;
-  // Simpson weights along alpha_d: fine rows (D0, 4 D0, D0 + D1, 4 D1, D1), coarse DC (1, 4, 1)
-  const double D0 = fd * __ldg(gwf + 2 * I), D1 = fd * __ldg(gwf + 2 * I + 1);
-  const double DC = fd * __ldg(gwc + I);
-
-  double err1 = 0.0, err2 = 0.0;  // Richardson-combined error moments of this lane
-  int ok = 1;
-  __syncwarp();
-
 #define QB_BOUND_TEST(T_, arow_, col_)                                              \
   if (HAS_BOUND) {                                                                  \
     const double sv_ = k.cs * ((arow_) + (col_).b);                                 \
@@ -383,63 +337,23 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fuse
     ok &= (room_ >= 0.0) && (k.e0s <= room_ * ((T_) * (col_).t2p) * k.r_m);         \
   }
 
-  // ---- halo row h = 4 (I0 + 32): lanes <-> columns pre-pass -------------------
-  {
-    const RowReg rh = load_row(tdf + 4 * (I0 + 32));
-    const double* cp = s_cols + (size_t)(5 * lane) * QB_FUSED_REC;
-    const ColRec c0 = load_col_s(cp);
-    const ColRec c1 = load_col_s(cp + QB_FUSED_REC);
-    const ColRec c2 = load_col_s(cp + 2 * QB_FUSED_REC);
-    const ColRec c3 = load_col_s(cp + 3 * QB_FUSED_REC);
-    const ColRec cm = load_col_s(cp + 4 * QB_FUSED_REC);
-    const ColRec c4 = load_col_s(cp + 5 * QB_FUSED_REC);
-    QB_EVAL1(rh, c0, T0)
-    QB_EVAL1(rh, c1, T1)
-    QB_EVAL1(rh, c2, T2)
-    QB_EVAL1(rh, c3, T3)
-    QB_EVAL1(rh, cm, Tm)
-    QB_EVAL1(rh, c4, T4)
-    const double HF = fma(c4.wF2, T4, fma(c3.wF, T3, fma(c2.wF, T2, fma(c1.wF, T1, c0.wF * T0))));
-    const double HC = fma(c4.wC2, T4, fma(cm.wC, Tm, c0.wC * T0));
-    s_halo[lane] = HF;
-    s_halo[32 + lane] = HC;
-    if (HAS_ERR) {
-      // weights of this row as p = 4 / c2 of lane 31's cell
-      const double wf4 = fd * __ldg(gwf + 2 * (I0 + 31) + 1);
-      const double wc2 = fd * __ldg(gwc + I0 + 31);
-      const double ah = fabs(rh.xh);
-      const double HFB = fma(c4.wF2 * c4.b, T4,
-                             fma(c3.wF * c3.b, T3,
-                                 fma(c2.wF * c2.b, T2, fma(c1.wF * c1.b, T1, (c0.wF * c0.b) * T0))));
-      const double HCB = fma(c4.wC2 * c4.b, T4, fma(cm.wC * cm.b, Tm, (c0.wC * c0.b) * T0));
-      err1 = 2.0 * wf4 * fma(ah, HF, HFB) - wc2 * fma(ah, HC, HCB);
-      if (HAS_M2) {
-        const double HFBB =
-            fma(c4.wF2 * c4.b * c4.b, T4,
-                fma(c3.wF * c3.b * c3.b, T3,
-                    fma(c2.wF * c2.b * c2.b, T2,
-                        fma(c1.wF * c1.b * c1.b, T1, (c0.wF * c0.b * c0.b) * T0))));
-        const double HCBB =
-            fma(c4.wC2 * c4.b * c4.b, T4, fma(cm.wC * cm.b * cm.b, Tm, (c0.wC * c0.b * c0.b) * T0));
-        err2 = 2.0 * wf4 * fma(ah * ah, HF, fma(2.0 * ah, HFB, HFBB)) -
-               wc2 * fma(ah * ah, HC, fma(2.0 * ah, HCB, HCBB));
-      }
-    }
-    if (HAS_BOUND) {
-      const double ah = fabs(rh.xh);
-      QB_BOUND_TEST(T0, ah, c0)
-      QB_BOUND_TEST(Tm, ah, cm)
-      QB_BOUND_TEST(T4, ah, c4)
-    }
-    __syncwarp();
-  }
-
+// The march of one warp over the 161 columns of its tile. RIDGE = false is used when no point
+// of the tile can have |u| < 1/16 (decided once per tile from the tile's corner values): the
+// loop is then free of tests and branches. Class 1 / 2 tiles never test.
+template <int MODE, int CLS, bool RIDGE, bool HAS_ERR, bool HAS_M2, bool HAS_BOUND>
+__device__ __forceinline__ void fused_march(const FusedConst& k, const RowReg& r0, const RowReg& r1,
+                                            const RowReg& r2, const RowReg& r3, const RowReg& rc,
+                                            const double D0, const double D1, const double DC,
+                                            const double fd, const double* s_cols,
+                                            const double* s_halo, double* outp, const int D,
+                                            const int I, const int lane, const double* gwc,
+                                            const double* gwf, double& tp, double& err1,
+                                            double& err2, int& ok) {
   // ---- main march over the tile's columns --------------------------------------
   double sF0, sF1, sF2, sF3, sC0, sCm;                          // per-cell row sums
   double tF0 = 0, tF1 = 0, tF2 = 0, tF3 = 0, tC0 = 0, tCm = 0;  // tile totals of the row sums
   double bF0 = 0, bF1 = 0, bF2 = 0, bF3 = 0, bC0 = 0, bCm = 0;  // ... weighted by b
   double qF0 = 0, qF1 = 0, qF2 = 0, qF3 = 0, qC0 = 0, qCm = 0;  // ... weighted by b^2
-  double tp = 0.0;
 
   const double* cp = s_cols;
   {
@@ -462,7 +376,6 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fuse
     QB_BOUND_TEST(T0, fabs(r0.xh), c)
     QB_BOUND_TEST(Tm, fabs(rc.xh), c)
   }
-  double* outp = a.out + (size_t)s.slot * D * D + (size_t)J0 * D + I;
 
   for (int jj = 0; jj < 32; jj++) {
     cp += QB_FUSED_REC;
@@ -544,7 +457,6 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fuse
       sC0 = c.wC * T0; sCm = c.wC * Tm;
     }
   }
-#undef QB_BOUND_TEST
 
   if (HAS_ERR) {
     // Composite alpha_d weights for the error totals: rows 0 / c0 are also rows
@@ -575,6 +487,133 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fuse
       err2 += fma(2.0, e2, -e2c);
     }
   }
+
+}
+
+template <int MODE, int CLS, bool HAS_ERR, bool HAS_M2, bool HAS_BOUND>
+__global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fused2d(FusedArgs a) {
+  extern __shared__ __align__(16) double s_dyn[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const FusedConst& k = a.k;
+  const unsigned tile = k.tile_base + blockIdx.x * QB_FUSED_WARPS + warp;
+  if (tile >= k.tile_end) return;
+  double* s_cols = s_dyn + warp * (QB_TILE_RECS * QB_FUSED_REC + 2 * 32);
+  double* s_halo = s_cols + QB_TILE_RECS * QB_FUSED_REC;  // [2][32]
+  const int D = k.D, nb = k.nb;
+  const unsigned per_slice = (unsigned)(nb * nb);
+  const unsigned sidx = tile / per_slice;
+  const unsigned rem = tile - sidx * per_slice;
+  const int jc = (int)(rem / (unsigned)nb), ib = (int)(rem - (unsigned)jc * nb);
+  const int I0 = ib * 32, J0 = jc * 32, I = I0 + lane;
+  const FusedSlice s = a.slices[sidx];
+  const AxisD* tdc = a.tab_a + (size_t)s.tab_a * k.NP;
+  const AxisD* tdf = tdc + (2 * D + 1);
+  const double* gwc = a.gw;
+  const double* gwf = a.gw + D;
+
+  // ---- stage the tile's 161 column records in shared memory (per warp) ---------
+  // (cp.async: all 26 16-byte copies of a lane are in flight at once and overlap the row loads)
+  {
+    const double2* g =
+        (const double2*)(a.cols + ((size_t)s.tab_b * k.ncol + (size_t)5 * J0) * QB_FUSED_REC);
+    const unsigned sh = (unsigned)__cvta_generic_to_shared(s_cols);
+#pragma unroll 1
+    for (int i = lane; i < QB_TILE_RECS * QB_FUSED_REC / 2; i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sh + 16u * (unsigned)i),
+                   "l"(g + i)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // alpha_d rows of this lane: fine h = 4 I .. 4 I + 3 and the coarse mid point.
+  const RowReg r0 = load_row(tdf + 4 * I);
+  const RowReg r1 = load_row(tdf + 4 * I + 1);
+  const RowReg r2 = load_row(tdf + 4 * I + 2);
+  const RowReg r3 = load_row(tdf + 4 * I + 3);
+  const RowReg rc = load_row(tdc + 2 * I + 1);
+  const double fd = s.scale_a * k.r_m / 6.0;
+  // Simpson weights along alpha_d: fine rows (D0, 4 D0, D0 + D1, 4 D1, D1), coarse DC (1, 4, 1)
+  const double D0 = fd * __ldg(gwf + 2 * I), D1 = fd * __ldg(gwf + 2 * I + 1);
+  const double DC = fd * __ldg(gwc + I);
+
+  double err1 = 0.0, err2 = 0.0;  // Richardson-combined error moments of this lane
+  double tp = 0.0;
+  int ok = 1;
+  const bool RIDGE = true;  // the pre-pass below always tests (six evaluations per lane)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  // ---- halo row h = 4 (I0 + 32): lanes <-> columns pre-pass -------------------
+  {
+    const RowReg rh = load_row(tdf + 4 * (I0 + 32));
+    const double* cp = s_cols + (size_t)(5 * lane) * QB_FUSED_REC;
+    const ColRec c0 = load_col_s(cp);
+    const ColRec c1 = load_col_s(cp + QB_FUSED_REC);
+    const ColRec c2 = load_col_s(cp + 2 * QB_FUSED_REC);
+    const ColRec c3 = load_col_s(cp + 3 * QB_FUSED_REC);
+    const ColRec cm = load_col_s(cp + 4 * QB_FUSED_REC);
+    const ColRec c4 = load_col_s(cp + 5 * QB_FUSED_REC);
+    QB_EVAL1(rh, c0, T0)
+    QB_EVAL1(rh, c1, T1)
+    QB_EVAL1(rh, c2, T2)
+    QB_EVAL1(rh, c3, T3)
+    QB_EVAL1(rh, cm, Tm)
+    QB_EVAL1(rh, c4, T4)
+    const double HF = fma(c4.wF2, T4, fma(c3.wF, T3, fma(c2.wF, T2, fma(c1.wF, T1, c0.wF * T0))));
+    const double HC = fma(c4.wC2, T4, fma(cm.wC, Tm, c0.wC * T0));
+    s_halo[lane] = HF;
+    s_halo[32 + lane] = HC;
+    if (HAS_ERR) {
+      // weights of this row as p = 4 / c2 of lane 31's cell
+      const double wf4 = fd * __ldg(gwf + 2 * (I0 + 31) + 1);
+      const double wc2 = fd * __ldg(gwc + I0 + 31);
+      const double ah = fabs(rh.xh);
+      const double HFB = fma(c4.wF2 * c4.b, T4,
+                             fma(c3.wF * c3.b, T3,
+                                 fma(c2.wF * c2.b, T2, fma(c1.wF * c1.b, T1, (c0.wF * c0.b) * T0))));
+      const double HCB = fma(c4.wC2 * c4.b, T4, fma(cm.wC * cm.b, Tm, (c0.wC * c0.b) * T0));
+      err1 = 2.0 * wf4 * fma(ah, HF, HFB) - wc2 * fma(ah, HC, HCB);
+      if (HAS_M2) {
+        const double HFBB =
+            fma(c4.wF2 * c4.b * c4.b, T4,
+                fma(c3.wF * c3.b * c3.b, T3,
+                    fma(c2.wF * c2.b * c2.b, T2,
+                        fma(c1.wF * c1.b * c1.b, T1, (c0.wF * c0.b * c0.b) * T0))));
+        const double HCBB =
+            fma(c4.wC2 * c4.b * c4.b, T4, fma(cm.wC * cm.b * cm.b, Tm, (c0.wC * c0.b * c0.b) * T0));
+        err2 = 2.0 * wf4 * fma(ah * ah, HF, fma(2.0 * ah, HFB, HFBB)) -
+               wc2 * fma(ah * ah, HC, fma(2.0 * ah, HCB, HCBB));
+      }
+    }
+    if (HAS_BOUND) {
+      const double ah = fabs(rh.xh);
+      QB_BOUND_TEST(T0, ah, c0)
+      QB_BOUND_TEST(Tm, ah, cm)
+      QB_BOUND_TEST(T4, ah, c4)
+    }
+    __syncwarp();
+  }
+
+  double* outp = a.out + (size_t)s.slot * D * D + (size_t)J0 * D + I;
+  // u = x_d + y is monotone in both indices: its range over the tile (rows I0 .. I0 + 32,
+  // columns J0 .. J0 + 32) is spanned by the corner sums. Warp-uniform.
+  bool ridge = false;
+  if (CLS == 0) {
+    const double xa = __shfl_sync(0xffffffffu, r0.xh, 0);
+    const double xb = __ldg(&tdf[4 * (I0 + 32)].xh);
+    const double ya = s_cols[0], yb = s_cols[(QB_TILE_RECS - 1) * QB_FUSED_REC];
+    const double lo = fmin(xa, xb) + fmin(ya, yb), hi = fmax(xa, xb) + fmax(ya, yb);
+    ridge = !(lo > 0.0626 || hi < -0.0626);
+  }
+  if (CLS == 0 && ridge)
+    fused_march<MODE, CLS, true, HAS_ERR, HAS_M2, HAS_BOUND>(k, r0, r1, r2, r3, rc, D0, D1, DC, fd, s_cols,
+                                                        s_halo, outp, D, I, lane, gwc, gwf, tp,
+                                                        err1, err2, ok);
+  else
+    fused_march<MODE, CLS, false, HAS_ERR, HAS_M2, HAS_BOUND>(k, r0, r1, r2, r3, rc, D0, D1, DC, fd, s_cols,
+                                                         s_halo, outp, D, I, lane, gwc, gwf, tp,
+                                                         err1, err2, ok);
 
   // warp reduction in a fixed order
 #pragma unroll
