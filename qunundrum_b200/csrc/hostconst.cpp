@@ -145,9 +145,17 @@ BigUInt fix_ln2() {
 }  // namespace
 
 void exp2_table_dd(uint32_t n, DD* table) {
+  // The reference's step is the DOUBLE 1.0 / dimension (src/distribution_slice_compute.cpp:48,
+  // 110-113: mpfr_set_d(pow_2step, step); exp2), exact only for powers of two; its grid is
+  // (2^step)^i. Reproduce that: t = ln2 * fl(1/n) with fl(1/n) taken exactly.
+  const double step = (double)1 / (double)n;
+  int e2;
+  const double fr = std::frexp(step, &e2);                 // step = fr * 2^e2, fr in [0.5, 1)
+  const uint64_t mant = (uint64_t)std::ldexp(fr, 53);      // exact 53-bit integer
+  // step in 256-bit fixed point: mant * 2^(e2 - 53 + kFix)
+  const BigUInt step_fix = BigUInt(mant).shl((size_t)((long)kFix + e2 - 53));
+  const BigUInt t = fix_mul(fix_ln2(), step_fix);
   BigUInt q, rem;
-  BigUInt::divmod(fix_ln2(), BigUInt(n), q, rem);  // t = ln2 / n
-  const BigUInt t = q;
   const BigUInt one = BigUInt::pow2(kFix);
   BigUInt g = one, term = one;
   for (uint64_t k = 1; k < 200; k++) {
@@ -157,9 +165,10 @@ void exp2_table_dd(uint32_t n, DD* table) {
     if (term.is_zero()) break;
     g = BigUInt::add(g, term);
   }
+  const bool pow2 = (n & (n - 1)) == 0;
   BigUInt cur = one;
   for (uint32_t i = 0; i <= n; i++) {
-    if (i == n) cur = BigUInt::pow2(kFix + 1);  // exactly 2
+    if (i == n && pow2) cur = BigUInt::pow2(kFix + 1);  // exactly 2 when the step is exact
     table[i] = bf_to_dd(BigFloat(cur, -(long)kFix));
     cur = fix_mul(cur, g);
   }

@@ -52,7 +52,8 @@ struct HostConsts {
 int host_consts_compute(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d_be,
                         size_t d_len, const uint8_t* r_be, size_t r_len, HostConsts* out);
 
-// 2^(i / n) for i = 0..n as double-double (table[i] in [1, 2]); n >= 1.
+// (2^fl(1/n))^i for i = 0..n as double-double, fl(1/n) the double the reference uses as its
+// step (equal to 2^(i/n) when n is a power of two); n >= 1.
 void exp2_table_dd(uint32_t n, DD* table);
 
 }  // namespace qb200

@@ -61,8 +61,10 @@ inline int make_dev_consts(const ParamsView& p, int method_2d, DevConsts* c, std
   }
   if (method_2d == kMethodHeuristicSigma) {
     sigma = heuristic_sigma(p.l);
-    if (sigma >= p.l) {
-      *err = "heuristic sigma >= l: l is too small for the error-bounded approximation";
+    if (sigma > p.l) {
+      // the reference forms 2^(l - sigma) with an unsigned difference (src/probability.cpp:178)
+      // and returns NaN cells here; refuse instead
+      *err = "heuristic sigma > l: l is too small for the error-bounded approximation";
       return -3;
     }
   }
