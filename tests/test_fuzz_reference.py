@@ -113,3 +113,65 @@ def test_cuda_vs_reference_random(gpu_ctx):
             P = qb.Parameters(c["m"], c["s"], c["d"], c["r"])
             cells, tp, fl = gpu_ctx.slice1d_batch(P, 0 if c["kind"] == "lin_d" else 1, True, c["D"], [c["a"]])
             check(c, cells[0], tp[0], 0, fl[0])
+
+
+@pytest.mark.gpu
+def test_fused_kernel_random(gpu_ctx):
+    """The fused kernel (dimension a multiple of 32, Richardson) on random parameters: against the
+    reference on a few slices, and against the plain kernels (validated above) on many, with
+    coordinates over the whole region so that all slice classes, both modes of the inner-sine
+    treatment, the bound-test and second-moment variants are hit."""
+    import torch
+    import qunundrum_b200 as qb
+
+    def run(plan, algo):
+        plan.set_algorithm(algo)
+        cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
+        summ = torch.empty(plan.n * 8, dtype=torch.float64, device="cuda")
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            plan.run(cells.data_ptr(), summ.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        tp, te, fl = plan.finish(summ.cpu().numpy())
+        return cells.cpu().numpy().reshape(plan.n, -1), tp, te, fl
+
+    rnd = random.Random(77)
+    n_ref = 0
+    for it in range(24):
+        m = rnd.choice([64, 128, 200, 256, 513, 1024, 2048, 3072])
+        s = rnd.choice([1, 1, 2, 3, 4, 8, 20, 30])
+        l = math.ceil(m / s)
+        if l < 24:
+            continue
+        r = 2 ** (m - 1) + 1 + rnd.randrange(2 ** (m - 1) - 1)
+        d = r // 2 + rnd.randrange(r // 2)
+        method = rnd.choice([0, 0, 2])
+        D = rnd.choice([32, 32, 64])
+        lo, hi = max(1, m - 30), min(m + 29, m + l - 2)
+        n = 12
+        a_d = [rnd.randint(lo, hi) * rnd.choice([1, -1]) for _ in range(n)]
+        a_r = [rnd.randint(lo, hi) * rnd.choice([1, 1, -1]) for _ in range(n)]
+        a_d[0], a_r[0] = m, m                      # the ridge
+        a_d[1], a_r[1] = -(m + 1), m + 1
+        P = qb.Parameters(m, s, d, r)
+        plan = gpu_ctx.plan2d(P, method, True, D, a_d, a_r)
+        if plan.algorithm != 2:                    # l - sigma too small for the fused kernel
+            plan.close()
+            continue
+        c2, tp2, te2, fl2 = run(plan, 2)
+        c1, tp1, te1, fl1 = run(plan, 1)
+        plan.close()
+        assert cell_errors(c2, c1) <= 1e-10, (m, s, method, D)
+        for i in range(n):
+            assert abs(float(tp2[i] - tp1[i])) <= 1e-13 * max(1.0, abs(float(tp1[i]))), (m, s, i)
+            if te1[i] != 0:
+                assert abs(float((te2[i] - te1[i]) / te1[i])) <= 1e-10, (m, s, method, i)
+        assert np.array_equal(fl1, fl2), (m, s, method, fl1, fl2)
+        if D == 32 and n_ref < 6:                  # and the reference itself on the first two slices
+            RP = REF.RefParameters(m, s, d, r)
+            for i in range(2):
+                R = REF.distribution_slice_compute(RP, D, a_d[i], a_r[i], method=method)
+                assert cell_errors(c2[i], R.cells) <= CELL_RTOL, (m, s, method, i)
+                assert int(fl2[i]) == R.flags
+            n_ref += 1
+    assert n_ref >= 3
