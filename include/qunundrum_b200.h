@@ -150,6 +150,48 @@ int qb200_plan_finish(const qb200_plan *plan, const double *h_summary,
                       long double *total_probability, long double *total_error,
                       uint32_t *flags);
 
+/* ---- text export: "%.24Lg\n" lines ------------------------------------------
+ *
+ * SURVEY.md section 8(f) #1. Every cell of a stored slice is written by
+ *   fprintf(file, "%.24Lg\n", slice->norm_matrix[i]);   (then total_error likewise)
+ * in distribution_slice_export          src/distribution_slice_import_export.cpp:89-103
+ *    linear_distribution_slice_export   src/linear_distribution_slice_import_export.cpp:82-97
+ *    diagonal_distribution_slice_export src/diagonal_distribution_slice_import_export.cpp:87-103
+ * -- 1.05e8 calls, 3.1 GB of text and 87 % of the wall clock of one m = 2048
+ * distribution once the integration runs on the GPU. The entry points below
+ * produce the same bytes (glibc semantics: exact value, round-half-even, %g
+ * style selection, trailing zeros removed, inf / nan / signed zero) with one
+ * kernel launch per call. */
+#define QB200_TEXT_X87 0 /* x86-64 long double: 64-bit mantissa, 16-byte stride */
+#define QB200_TEXT_F64 1 /* IEEE double, printed as (long double)x */
+
+/* Largest possible text of n values (33 bytes each). */
+size_t qb200_text_bound(size_t n);
+
+/* n values followed by the optional `tail` value (a slice's total_error; NULL
+ * for none), one line each. *text points into pinned host memory owned by the
+ * context, valid until the next text call on it; *len is its length (no NUL). */
+int qb200_text_format_ld(qb200_context *ctx, const long double *values, size_t n,
+                         const long double *tail, const char **text, size_t *len);
+int qb200_text_format_f64(qb200_context *ctx, const double *values, size_t n,
+                          const double *tail, const char **text, size_t *len);
+
+/* Device-resident form: enqueues one launch on `stream` (a cudaStream_t, NULL =
+ * the context's own) and returns without synchronising. d_text has room for
+ * cap bytes (qb200_text_bound(n) always suffices); *d_len (device) receives
+ * the text length. kind = QB200_TEXT_X87 / QB200_TEXT_F64. */
+int qb200_text_format_device(qb200_context *ctx, int kind, const void *d_values, size_t n,
+                             char *d_text, size_t cap, uint64_t *d_len, void *stream);
+
+/* Introspection / test hooks (host logic; qb200_text_pow10 needs no GPU):
+ * the 192-bit table entry of 10^k (little-endian 32-bit limbs, value =
+ * T * 2^(e2 - 191), truncated; exact = 1 if nothing was cut off); a switch that
+ * sends every value through the exact rounding decision; and the number of
+ * values of the last call that needed it. */
+int qb200_text_pow10(int k, uint32_t w[6], int32_t *e2, uint32_t *exact);
+int qb200_text_set_force_exact(qb200_context *ctx, int on);
+uint64_t qb200_text_exact_count(qb200_context *ctx);
+
 /* ---- introspection (host logic; usable without a GPU) --------------------- */
 
 /* sigma chosen by QB200_METHOD_HEURISTIC_SIGMA for this l

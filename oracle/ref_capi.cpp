@@ -23,6 +23,9 @@
  *   linear_probability_d / linear_probability_r          src/linear_probability.cpp:21,170
  *   diagonal_probability_approx_f_eta                    src/diagonal_probability.cpp:18
  *   parameters_selection_deterministic_d_r               src/parameters_selection.cpp:21
+ *   distribution_slice_export / _import                  src/distribution_slice_import_export.cpp:89,55
+ *   linear_distribution_slice_export / _import           src/linear_distribution_slice_import_export.cpp:82,50
+ *   diagonal_distribution_slice_export / _import         src/diagonal_distribution_slice_import_export.cpp:87,55
  */
 
 #include "common.h"
@@ -253,6 +256,100 @@ void qref_diagonal_distribution_slice_compute(void *dparams, int richardson,
   *total_error = slice.total_error;
   *flags = slice.flags;
   diagonal_distribution_slice_clear(&slice);
+}
+
+/* ---- Slice text export / import (memory streams) ---------------------------- */
+
+/* kind: 0 two-dimensional (c0 = min_log_alpha_d, c1 = min_log_alpha_r),
+ *       1 linear (c0 = min_log_alpha), 2 diagonal (c0 = min_log_alpha_r, c1 = eta).
+ * Returns the number of bytes the reference's exporter wrote (<= cap), or
+ * (size_t)-1 if cap is too small. */
+size_t qref_slice_export(int kind, uint32_t dimension, int32_t c0, int32_t c1,
+                         uint32_t flags, const long double *cells,
+                         long double total_error, char *out, size_t cap) {
+  char *buf = NULL;
+  size_t len = 0;
+  FILE *f = open_memstream(&buf, &len);
+  if (kind == 0) {
+    Distribution_Slice slice;
+    distribution_slice_init(&slice, dimension);
+    memcpy(slice.norm_matrix, cells, sizeof(long double) * (size_t)dimension * dimension);
+    slice.min_log_alpha_d = c0;
+    slice.min_log_alpha_r = c1;
+    slice.flags = flags;
+    slice.total_error = total_error;
+    distribution_slice_export(&slice, f);
+    distribution_slice_clear(&slice);
+  } else if (kind == 1) {
+    Linear_Distribution_Slice slice;
+    linear_distribution_slice_init(&slice, dimension);
+    memcpy(slice.norm_vector, cells, sizeof(long double) * (size_t)dimension);
+    slice.min_log_alpha = c0;
+    slice.flags = flags;
+    slice.total_error = total_error;
+    linear_distribution_slice_export(&slice, f);
+    linear_distribution_slice_clear(&slice);
+  } else {
+    Diagonal_Distribution_Slice slice;
+    diagonal_distribution_slice_init(&slice, dimension);
+    memcpy(slice.norm_vector, cells, sizeof(long double) * (size_t)dimension);
+    slice.min_log_alpha_r = c0;
+    slice.eta = c1;
+    slice.flags = flags;
+    slice.total_error = total_error;
+    diagonal_distribution_slice_export(&slice, f);
+    diagonal_distribution_slice_clear(&slice);
+  }
+  fclose(f);
+  size_t ret = (size_t)-1;
+  if (len <= cap) {
+    memcpy(out, buf, len);
+    ret = len;
+  }
+  free(buf);
+  return ret;
+}
+
+/* The reference's importer on a text held in memory. cells must have room for
+ * dimension^2 (kind 0) / dimension values; head receives dimension, c0, c1, flags.
+ * Returns 0 on success. */
+int qref_slice_import(int kind, const char *text, size_t len, uint32_t max_cells,
+                      uint32_t *head4, long double *cells, long double *total_probability,
+                      long double *total_error) {
+  FILE *f = fmemopen((void *)text, len, "rb");
+  if (!f) return -1;
+  int rc = 0;
+  if (kind == 0) {
+    Distribution_Slice slice;
+    distribution_slice_init_import(&slice, f);
+    const size_t n = (size_t)slice.dimension * slice.dimension;
+    if (n > max_cells) rc = -2;
+    else memcpy(cells, slice.norm_matrix, sizeof(long double) * n);
+    head4[0] = slice.dimension; head4[1] = (uint32_t)slice.min_log_alpha_d;
+    head4[2] = (uint32_t)slice.min_log_alpha_r; head4[3] = slice.flags;
+    *total_probability = slice.total_probability; *total_error = slice.total_error;
+    distribution_slice_clear(&slice);
+  } else if (kind == 1) {
+    Linear_Distribution_Slice slice;
+    linear_distribution_slice_init_import(&slice, f);
+    if (slice.dimension > max_cells) rc = -2;
+    else memcpy(cells, slice.norm_vector, sizeof(long double) * slice.dimension);
+    head4[0] = slice.dimension; head4[1] = (uint32_t)slice.min_log_alpha;
+    head4[2] = 0; head4[3] = slice.flags;
+    *total_probability = slice.total_probability; *total_error = slice.total_error;
+    linear_distribution_slice_clear(&slice);
+  } else {
+    Diagonal_Distribution_Slice slice;
+    diagonal_distribution_slice_init_import(&slice, f);
+    if (slice.dimension > max_cells) rc = -2;
+    else memcpy(cells, slice.norm_vector, sizeof(long double) * slice.dimension);
+    head4[0] = slice.dimension; head4[1] = (uint32_t)slice.min_log_alpha_r;
+    head4[2] = (uint32_t)slice.eta; head4[3] = slice.flags;
+    *total_probability = slice.total_probability; *total_error = slice.total_error;
+    diagonal_distribution_slice_clear(&slice);
+  }
+  fclose(f);
+  return rc;
 }
 
 /* ---- Point-wise integrands (known-answer tests) ---------------------------- */

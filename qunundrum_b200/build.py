@@ -19,12 +19,13 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # FMAs are explicit; error-free transforms must not be contracted
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
-    "-shared",
 ]
+OBJ = os.path.join(HERE, "_obj")
 
 
 def sources():
-    return [os.path.join(CSRC, "qb200.cu"), os.path.join(CSRC, "hostconst.cpp")]
+    return [os.path.join(CSRC, f) for f in
+            ("qb200.cu", "qb200_text.cu", "hostconst.cpp", "text_tables.cpp")]
 
 
 def deps():
@@ -42,11 +43,40 @@ def nvcc_path() -> str:
     return p
 
 
+def _includes(src: str) -> list[str]:
+    """Headers of csrc/ a source file includes, transitively (quoted includes only)."""
+    import re
+    seen, todo = set(), [src]
+    while todo:
+        f = todo.pop()
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.add(f)
+        for inc in re.findall(r'#include\s+"([^"]+)"', open(f).read()):
+            todo.append(os.path.normpath(os.path.join(os.path.dirname(f), inc)))
+    return sorted(seen)
+
+
 def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
-    stale = force or not os.path.exists(LIB) or any(
-        os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps())
-    if stale:
-        cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), *sources(), "-o", LIB]
+    """One object per source (rebuilt only when it or a header it includes changed,
+    in parallel), then one link."""
+    os.makedirs(OBJ, exist_ok=True)
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ, os.path.basename(src) + ".o")
+        objs.append(obj)
+        stale = force or not os.path.exists(obj) or any(
+            os.path.getmtime(d) > os.path.getmtime(obj) for d in _includes(src) + [__file__])
+        if stale:
+            cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), "-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    if procs or not os.path.exists(LIB):
+        cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)

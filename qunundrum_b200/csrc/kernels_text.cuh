@@ -1,0 +1,170 @@
+// kernels_text.cuh -- the text exporter's kernel: n values -> "%.24Lg\n" lines,
+// contiguous, in order, in ONE pass.
+//
+// One thread per value (textfmt.cuh does the arithmetic), 256 values per tile.
+// Line lengths vary (2..33 bytes), so tile t's text starts at the sum of all
+// earlier tiles' lengths: tiles take tickets in launch order and chain their
+// lengths through a decoupled look-back (one 64-bit status word per tile: flag
+// in the top two bits, byte count below), so the text is written once, to its
+// final place, with no second pass and no scratch copy. HBM-bound by design:
+// 16 B read + ~31 B written per value; the 316 KB table of powers of ten stays
+// in L1/L2.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "textfmt.cuh"
+
+namespace qb200 {
+namespace text {
+
+constexpr int TB = 256;                          // values per tile = threads per block
+constexpr int STAGE_BYTES = TB * MAX_TEXT + 32;  // tile text staged in shared memory
+
+constexpr unsigned long long ST_FLAG_AGG = 1ULL << 62;     // tile length published
+constexpr unsigned long long ST_FLAG_PREFIX = 2ULL << 62;  // inclusive prefix published
+constexpr unsigned long long ST_VALUE = (1ULL << 62) - 1;
+
+enum : int { SRC_X87 = 0, SRC_F64 = 1 };
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// status: n_tiles words, zeroed before the launch; ticket: one zeroed word.
+// out: the text (capacity cap bytes); total_out: total text length (written by the
+// last tile even if it exceeds cap, in which case nothing beyond cap is stored).
+template <int SRC>
+__global__ void __launch_bounds__(TB)
+    k_text_format(const void* __restrict__ in, unsigned long long n,
+                  const Pow10Entry* __restrict__ tab, unsigned char* __restrict__ out,
+                  unsigned long long cap, unsigned long long* __restrict__ status,
+                  unsigned int* __restrict__ ticket, unsigned long long* __restrict__ total_out,
+                  unsigned long long* __restrict__ n_exact, int force_band) {
+  __shared__ __align__(16) unsigned char stage[STAGE_BYTES];
+  __shared__ uint32_t big[BIG_LIMBS];
+  __shared__ uint32_t warp_sum[TB / 32];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const unsigned long long i = (unsigned long long)tile * TB + tid;
+
+  Piece p;
+  Dec24 d;
+  uint64_t Mn = 0;
+  int qn = 0;
+  bool number = false;
+  d.undecided = 0;
+  d.up = 0;
+  if (i < n) {
+    if (SRC == SRC_X87) {
+      const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(in) + i);
+      number = classify_x87(v.x, (uint32_t)v.y & 0xffffu, &p, &Mn, &qn);
+    } else {
+      const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long*>(in) + i);
+      number = classify_f64(v, &p, &Mn, &qn);
+    }
+    if (number) digits24(Mn, qn, tab, &d, force_band != 0);
+  }
+  // Undecided roundings (true ties of values >= 1, or a remainder inside the
+  // 2^-107 error band): exact integer arithmetic, one thread at a time on the
+  // block's scratch. Never taken for probabilities; kept for exactness.
+  if (__syncthreads_or((int)d.undecided)) {
+    for (int t = 0; t < TB; t++) {
+      if (t == tid && d.undecided) {
+        d.up = exact_round_up(Mn, qn, d.x, d.c0, d.c1, d.c2, big) ? 1u : 0u;
+        if (n_exact) atomicAdd(n_exact, 1ULL);
+      }
+      __syncthreads();
+    }
+  }
+  int len = 0;
+  if (i < n) {
+    if (number) {
+      round_digits(&d, d.up != 0);
+      piece_from_digits(d, &p);
+    }
+    len = piece_length(p);
+  }
+  // exclusive scan of the line lengths over the tile
+  const int lane = tid & 31, warp = tid >> 5;
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sum[warp] = (uint32_t)incl;
+  __syncthreads();
+  uint32_t before = 0, tile_len = 0;
+#pragma unroll
+  for (int w = 0; w < TB / 32; w++) {
+    const uint32_t s = warp_sum[w];
+    if (w < warp) before += s;
+    tile_len += s;
+  }
+  const uint32_t off = before + (uint32_t)(incl - len);
+  if (i < n) piece_render(p, stage + off);
+
+  // decoupled look-back over the tiles before this one (warp 0)
+  if (warp == 0) {
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st_status(status, ST_FLAG_PREFIX | tile_len);
+    } else {
+      if (lane == 0) st_status(status + tile, ST_FLAG_AGG | tile_len);
+      long long j0 = (long long)tile - 1;  // lane l looks at tile j0 - l
+      while (true) {
+        const long long j = j0 - lane;
+        unsigned long long v = ST_FLAG_PREFIX;  // before tile 0: an empty prefix
+        if (j >= 0) {
+          do {
+            v = ld_status(status + j);
+          } while ((v >> 62) == 0);
+        }
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first = has_prefix ? (__ffs(has_prefix) - 1) : 32;  // nearest tile with a prefix
+        unsigned long long part = (lane <= first) ? (v & ST_VALUE) : 0ULL;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        excl += part;
+        if (has_prefix) break;
+        j0 -= 32;
+      }
+      if (lane == 0) st_status(status + tile, ST_FLAG_PREFIX | (excl + tile_len));
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if ((unsigned long long)(tile + 1) * TB >= n) *total_out = excl + tile_len;
+    }
+  }
+  __syncthreads();
+
+  // stage -> out + base (destination arbitrarily aligned): 4-byte words, coalesced
+  const unsigned long long base = s_base;
+  if (base + tile_len > cap) return;
+  unsigned char* dst = out + base;
+  const uint32_t head0 = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;
+  const uint32_t head = head0 < tile_len ? head0 : tile_len;
+  if ((uint32_t)tid < head) dst[tid] = stage[tid];
+  const uint32_t nwords = (tile_len - head) >> 2;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
+  const uint32_t sel = 0x3210u + 0x1111u * head;  // bytes head .. head+3 of (hi:lo)
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  for (uint32_t w = tid; w < nwords; w += TB) dw[w] = __byte_perm(sw[w], sw[w + 1], sel);
+  const uint32_t done = head + 4u * nwords;
+  if (done + tid < tile_len) dst[done + tid] = stage[done + tid];
+}
+
+}  // namespace text
+}  // namespace qb200

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/qunundrum_b200.h"
+#include "ctx_access.hpp"
 #include "kernels_fused2d.cuh"
 #include "kernels_plain.cuh"
 #include "kernels_sigma_opt.cuh"
@@ -107,6 +108,7 @@ struct qb200_context {
   DevBuf out_cells, out_summary;
   void* h_summary = nullptr;
   size_t h_summary_bytes = 0;
+  qb200::TextState* text = nullptr;  // text exporter / importer state (qb200_text.cu)
   Pool pool;  // declared last: destroyed first is fine, plans never outlive their context
 };
 
@@ -137,6 +139,13 @@ struct qb200_plan {
     for (DevBuf* b : all) b->pool = pool;
   }
 };
+
+namespace qb200 {
+CtxView ctx_view(qb200_context* ctx) {
+  return CtxView{ctx->device, ctx->sm_count, ctx->stream, &ctx->launches, &ctx->text};
+}
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace qb200
 
 namespace {
 
@@ -532,6 +541,7 @@ void qb200_destroy(qb200_context* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
   if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
+  if (ctx->text) qb200::text_state_destroy(ctx->text);
   delete ctx;
 }
 

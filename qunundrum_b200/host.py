@@ -103,6 +103,17 @@ def lib():
     L.qb200_heuristic_sigma.restype = u32
     L.qb200_host_constants.argtypes = [PP, vp]
     L.qb200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.qb200_text_bound.argtypes = [C.c_size_t]
+    L.qb200_text_bound.restype = C.c_size_t
+    L.qb200_text_format_ld.argtypes = [vp, vp, C.c_size_t, vp, C.POINTER(vp),
+                                       C.POINTER(C.c_size_t)]
+    L.qb200_text_format_f64.argtypes = [vp, vp, C.c_size_t, vp, C.POINTER(vp),
+                                        C.POINTER(C.c_size_t)]
+    L.qb200_text_format_device.argtypes = [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, vp]
+    L.qb200_text_pow10.argtypes = [C.c_int, vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
+    L.qb200_text_set_force_exact.argtypes = [vp, C.c_int]
+    L.qb200_text_exact_count.argtypes = [vp]
+    L.qb200_text_exact_count.restype = C.c_uint64
     _lib = L
     return L
 
@@ -357,6 +368,35 @@ class Context:
             fl.ctypes.data), "qb200_slice1d_compute")
         return cells, tp, fl
 
+    # ---- text export ----------------------------------------------------------
+    def text_format(self, values, tail=None) -> bytes:
+        """One '%.24Lg\\n' line per value (then `tail`), as the reference's slice
+        exporters print them. values: long double (x87) or float64 array."""
+        v = np.ascontiguousarray(values)
+        if v.dtype == np.float64:
+            fn, dt = lib().qb200_text_format_f64, np.float64
+        else:
+            v = np.ascontiguousarray(v, dtype=np.longdouble)
+            fn, dt = lib().qb200_text_format_ld, np.longdouble
+        t = None if tail is None else np.array([tail], dtype=dt)
+        text, n = C.c_void_p(), C.c_size_t()
+        _check(fn(self.h, v.ctypes.data, v.size, t.ctypes.data if t is not None else None,
+                  C.byref(text), C.byref(n)), "qb200_text_format")
+        return C.string_at(text, n.value) if n.value else b""
+
+    def text_format_device(self, kind: int, d_values_ptr: int, n: int, d_text_ptr: int,
+                           cap: int, d_len_ptr: int, stream: int = 0):
+        """Enqueue one formatting launch on device-resident values."""
+        _check(lib().qb200_text_format_device(self.h, kind, d_values_ptr, n, d_text_ptr, cap,
+                                              d_len_ptr, stream), "qb200_text_format_device")
+
+    def text_set_force_exact(self, on: bool):
+        _check(lib().qb200_text_set_force_exact(self.h, int(bool(on))), "qb200_text_set_force_exact")
+
+    @property
+    def text_exact_count(self) -> int:
+        return int(lib().qb200_text_exact_count(self.h))
+
     # ---- device-resident plans ------------------------------------------------
     def plan2d(self, params: Parameters, method: int, richardson: bool, dimension: int,
                min_log_alpha_d, min_log_alpha_r) -> Plan:
@@ -485,3 +525,41 @@ def diagonal_distribution_slice_compute_richardson(slice, parameters, min_log_al
                                                    ctx=None):
     """src/diagonal_distribution_slice_compute_richardson.cpp:17."""
     _compute_diagonal(slice, parameters, min_log_alpha_r, eta, True, ctx)
+
+
+# --------------------------------------------------------------------------- #
+# The reference's slice exporters                                             #
+# --------------------------------------------------------------------------- #
+
+TEXT_X87, TEXT_F64 = 0, 1
+
+
+def text_pow10(k: int):
+    """(T, e2, exact): 10^k ~ T * 2^(e2 - 191), the table the text kernels use (host logic)."""
+    w = (C.c_uint32 * 6)()
+    e2, ex = C.c_int32(), C.c_uint32()
+    _check(lib().qb200_text_pow10(k, w, C.byref(e2), C.byref(ex)), "qb200_text_pow10")
+    return sum(int(w[i]) << (32 * i) for i in range(6)), e2.value, bool(ex.value)
+
+
+def distribution_slice_export(slice, file, ctx=None):
+    """src/distribution_slice_import_export.cpp:89-103; file: a binary file object."""
+    ctx = ctx or default_context()
+    file.write(b"%u\n%d\n%d\n%.8x\n" % (slice.dimension, slice.min_log_alpha_d,
+                                       slice.min_log_alpha_r, slice.flags))
+    file.write(ctx.text_format(slice.norm_matrix, slice.total_error))
+
+
+def linear_distribution_slice_export(slice, file, ctx=None):
+    """src/linear_distribution_slice_import_export.cpp:82-97."""
+    ctx = ctx or default_context()
+    file.write(b"%u\n%d\n%.8x\n" % (slice.dimension, slice.min_log_alpha, slice.flags))
+    file.write(ctx.text_format(slice.norm_vector, slice.total_error))
+
+
+def diagonal_distribution_slice_export(slice, file, ctx=None):
+    """src/diagonal_distribution_slice_import_export.cpp:87-103."""
+    ctx = ctx or default_context()
+    file.write(b"%u\n%d\n%d\n%.8x\n" % (slice.dimension, slice.min_log_alpha_r, slice.eta,
+                                       slice.flags))
+    file.write(ctx.text_format(slice.norm_vector, slice.total_error))

@@ -14,10 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "_build", "libhostsim.so")
 _SRCS = [os.path.join(_HERE, "hostsim.cpp"),
-         os.path.join(_ROOT, "qunundrum_b200", "csrc", "hostconst.cpp")]
+         os.path.join(_ROOT, "qunundrum_b200", "csrc", "hostconst.cpp"),
+         os.path.join(_ROOT, "qunundrum_b200", "csrc", "text_tables.cpp")]
 _DEPS = _SRCS + [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
                  ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "sigma_opt.cuh", "plan.hpp",
-                  "hostconst.hpp", "bigint.hpp")]
+                  "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "text_tables.hpp")]
 _lib = None
 
 
@@ -106,3 +107,31 @@ def slice1d(m, l, sigma, d, r, kind, richardson, D, a, eta=None):
     if rc:
         raise ValueError(lib().hostsim_last_error().decode())
     return cells, tp, fl
+
+
+# ---- text formatter ----------------------------------------------------------------
+
+def pow10_entry(k):
+    w = (C.c_uint32 * 6)()
+    e2 = C.c_int32()
+    ex = C.c_uint32()
+    if lib().hostsim_pow10_entry(C.c_int(k), w, C.byref(e2), C.byref(ex)):
+        raise ValueError(k)
+    T = sum(int(w[i]) << (32 * i) for i in range(6))
+    return T, e2.value, bool(ex.value)
+
+
+def floor_log10_pow2(n):
+    lib().hostsim_floor_log10_pow2.restype = C.c_int32
+    return int(lib().hostsim_floor_log10_pow2(C.c_int32(n)))
+
+
+def text_format_ld(values, force_band=False):
+    """'%.24Lg\\n' per value through the CPU compile of textfmt.cuh; returns (bytes, n_exact)."""
+    v = np.ascontiguousarray(values, dtype=np.longdouble)
+    out = C.create_string_buffer(34 * max(1, v.size))
+    nx = C.c_uint64()
+    lib().hostsim_text_format_ld.restype = C.c_size_t
+    n = lib().hostsim_text_format_ld(v.ctypes.data_as(C.c_void_p), C.c_size_t(v.size), out,
+                                     C.c_int(1 if force_band else 0), C.byref(nx))
+    return out.raw[:n], nx.value

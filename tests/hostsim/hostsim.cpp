@@ -265,3 +265,65 @@ int hostsim_slice1d(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d, si
 }
 
 }  // extern "C"
+
+// ---- text formatter (textfmt.cuh) -----------------------------------------------
+#include "../../qunundrum_b200/csrc/text_tables.hpp"
+
+namespace {
+std::vector<text::Pow10Entry>& pow10_table() {
+  static std::vector<text::Pow10Entry> t;
+  if (t.empty()) text::build_pow10_table(t);
+  return t;
+}
+}  // namespace
+
+extern "C" {
+
+int hostsim_pow10_entry(int k, uint32_t* w6, int32_t* e2, uint32_t* exact) {
+  if (k < text::K_MIN || k > text::K_MAX) return -1;
+  const text::Pow10Entry& e = pow10_table()[(size_t)(k - text::K_MIN)];
+  for (int i = 0; i < 6; i++) w6[i] = e.w[i];
+  *e2 = e.e2;
+  *exact = e.exact;
+  return 0;
+}
+
+int32_t hostsim_floor_log10_pow2(int32_t n) { return text::floor_log10_pow2(n); }
+
+// The loop a slice exporter runs: "%.24Lg\n" per value. force_band = 1 sends every
+// value through the exact rounding decision. Returns the text length; *n_exact
+// counts the values that took the exact path.
+size_t hostsim_text_format_ld(const long double* v, size_t n, char* out, int force_band,
+                              uint64_t* n_exact) {
+  const text::Pow10Entry* tab = pow10_table().data();
+  std::vector<uint32_t> scratch(text::BIG_LIMBS);
+  size_t pos = 0;
+  uint64_t slow = 0;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t mant;
+    uint16_t se;
+    memcpy(&mant, (const char*)&v[i], 8);
+    memcpy(&se, (const char*)&v[i] + 8, 2);
+    text::Piece p;
+    uint64_t Mn;
+    int qn;
+    if (text::classify_x87(mant, se, &p, &Mn, &qn)) {
+      text::Dec24 d;
+      text::digits24(Mn, qn, tab, &d, force_band != 0);
+      bool up = d.up != 0;
+      if (d.undecided) {
+        up = text::exact_round_up(Mn, qn, d.x, d.c0, d.c1, d.c2, scratch.data());
+        slow++;
+      }
+      text::round_digits(&d, up);
+      text::piece_from_digits(d, &p);
+    }
+    const int len = text::piece_length(p);
+    text::piece_render(p, out + pos);
+    pos += (size_t)len;
+  }
+  if (n_exact) *n_exact = slow;
+  return pos;
+}
+
+}  // extern "C"
