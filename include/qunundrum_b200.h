@@ -183,6 +183,32 @@ int qb200_text_format_f64(qb200_context *ctx, const double *values, size_t n,
 int qb200_text_format_device(qb200_context *ctx, int kind, const void *d_values, size_t n,
                              char *d_text, size_t cap, uint64_t *d_len, void *stream);
 
+/* ---- text import: "%Lg" numbers ------------------------------------------------
+ *
+ * The importers read every cell back with
+ *   fscanf(file, "%Lg\n", &slice->norm_matrix[i])
+ * (distribution_slice_import_common, src/distribution_slice_import_export.cpp:18-52;
+ * linear: src/linear_distribution_slice_import_export.cpp:18-47; diagonal:
+ * src/diagonal_distribution_slice_import_export.cpp:18-52). qb200_text_parse_ld
+ * converts the first n white-space separated numbers of text[0, len) to x87 long
+ * doubles, correctly rounded (nearest, ties to even -- what glibc's strtold
+ * returns), including inf / nan, denormals, overflow and underflow. *consumed
+ * (may be NULL) receives the offset of the byte after the n-th number and the
+ * white space that follows it, i.e. where the reference's FILE position would be.
+ * Errors: -20 fewer than n numbers, -21 a malformed number, -22 an unsupported
+ * form (hexadecimal floats; more than 28 significant digits exactly on a rounding
+ * boundary). text needs no terminating NUL. */
+int qb200_text_parse_ld(qb200_context *ctx, const char *text, size_t len, size_t n,
+                        long double *values, size_t *consumed);
+
+/* Device-resident form. d_text must be readable up to the next multiple of 16
+ * bytes past len (any content). d_values: n x 16 bytes. d_info: 5 uint64 on the
+ * device: numbers found, status (0 ok, 1 malformed, 2 unsupported), index of the
+ * first bad number, numbers that needed the exact decision, offset of number n
+ * (len if there is none). Two launches on `stream`, no synchronisation. */
+int qb200_text_parse_device(qb200_context *ctx, const char *d_text, size_t len, size_t n,
+                            void *d_values, uint64_t *d_info, void *stream);
+
 /* Introspection / test hooks (host logic; qb200_text_pow10 needs no GPU):
  * the 192-bit table entry of 10^k (little-endian 32-bit limbs, value =
  * T * 2^(e2 - 191), truncated; exact = 1 if nothing was cut off); a switch that

@@ -2,7 +2,12 @@
 
   integration/_build/ref/generate_*   the reference's slice integrators (MPFR, CPU)
   integration/_build/gpu/generate_*   the six integrator TUs replaced by
-                                      qunundrum_b200/dropin/dropin.cpp + libqunundrum_b200.so
+                                      qunundrum_b200/dropin/dropin.cpp, the three
+                                      *_slice_import_export TUs by dropin_text.cpp,
+                                      + libqunundrum_b200.so
+
+plus, in both flavours, the importing executables filter_distribution, info_distribution and
+compare_[linear_|diagonal_]distributions (they load stored distributions: the importer path).
 
 INTEGRATION-TEST INFRASTRUCTURE. Sources are compiled where they lie under /root/reference/src
 (never copied); neither OpenMPI nor fpLLL nor the GMP/MPFR development headers exist in this
@@ -26,18 +31,20 @@ LIBDIR = "/lib/x86_64-linux-gnu"
 COMMON_CPP = """math rsa parameters diagonal_parameters parameters_selection sample
  probability linear_probability diagonal_probability
  distribution distribution_enumerator distribution_info distribution_mpi distribution_slice
- distribution_slice_mpi distribution_slice_import_export
+ distribution_slice_mpi
  linear_distribution linear_distribution_enumerator linear_distribution_info linear_distribution_mpi
- linear_distribution_slice linear_distribution_slice_mpi linear_distribution_slice_import_export
+ linear_distribution_slice linear_distribution_slice_mpi
  diagonal_distribution diagonal_distribution_enumerator diagonal_distribution_info
- diagonal_distribution_mpi diagonal_distribution_slice diagonal_distribution_slice_mpi
+ diagonal_distribution_mpi diagonal_distribution_slice diagonal_distribution_slice_mpi""".split()
+TEXT_IO = """distribution_slice_import_export linear_distribution_slice_import_export
  diagonal_distribution_slice_import_export""".split()
 COMMON_C = "errors random keccak keccak_random gmp_mpi mpfr_mpi string_utilities thread_pool debug_common".split()
 INTEGRATORS = """distribution_slice_compute distribution_slice_compute_richardson
  linear_distribution_slice_compute linear_distribution_slice_compute_richardson
  diagonal_distribution_slice_compute diagonal_distribution_slice_compute_richardson""".split()
 MAINS = ["generate_distribution", "generate_linear_distribution", "generate_linear_distribution_rsa",
-         "generate_diagonal_distribution"]
+         "generate_diagonal_distribution", "filter_distribution", "info_distribution",
+         "compare_distributions", "compare_linear_distributions", "compare_diagonal_distributions"]
 
 
 def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
@@ -46,6 +53,7 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     if not os.path.isdir(src):
         return os.path.exists(done)
     deps = [os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin.cpp"),
+            os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
             os.path.join(HERE, "minimpi", "minimpi.c"), os.path.join(HERE, "minimpi", "mpi.h"),
             os.path.join(HERE, "build.py"), os.path.join(ROOT, "include", "qunundrum_b200.h")]
     if not force and os.path.exists(done) and all(
@@ -58,7 +66,7 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
            "-I", os.path.join(ROOT, "oracle", "shims"), "-I", os.path.join(ROOT, "include"),
            "-iquote", src]
     jobs = []
-    for f in COMMON_CPP + INTEGRATORS + ["main_" + m for m in MAINS]:
+    for f in COMMON_CPP + INTEGRATORS + TEXT_IO + ["main_" + m for m in MAINS]:
         jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *inc, "-c",
                      os.path.join(src, f + ".cpp"), "-o", os.path.join(obj, f + ".o")])
     for f in COMMON_C:
@@ -69,6 +77,9 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
                  os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin.cpp"),
                  "-o", os.path.join(obj, "dropin.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
+                 os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
+                 "-o", os.path.join(obj, "dropin_text.o")])
     jobs.append(["gcc", "-O2", "-c", os.path.join(HERE, "minimpi", "minimpi.c"),
                  "-o", os.path.join(obj, "minimpi.o")])
     with ThreadPoolExecutor(8) as ex:
@@ -79,9 +90,11 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     libs = [os.path.join(LIBDIR, "libmpfr.so.6"), os.path.join(LIBDIR, "libgmp.so.10"), "-lpthread", "-lm"]
     for m in MAINS:
         main_o = os.path.join(obj, "main_" + m + ".o")
-        subprocess.check_call(["g++", main_o, *common, *[os.path.join(obj, f + ".o") for f in INTEGRATORS],
+        subprocess.check_call(["g++", main_o, *common,
+                               *[os.path.join(obj, f + ".o") for f in INTEGRATORS + TEXT_IO],
                                *libs, "-o", os.path.join(OUT, "ref", m)])
         subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "dropin.o"),
+                               os.path.join(obj, "dropin_text.o"),
                                "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
                                "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
                                "-o", os.path.join(OUT, "gpu", m)])

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "textfmt.cuh"
+#include "textparse.cuh"
 
 namespace qb200 {
 namespace text {
@@ -35,6 +36,42 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
 }
 __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of `tile_len` over the tiles before `tile` (all lanes of one
+// warp call this; every lane returns the sum). Tiles take their numbers from a
+// ticket counter, so every earlier tile is already running and publishes at least
+// its own length without waiting for anyone: no deadlock.
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* status,
+                                                                 unsigned int tile,
+                                                                 unsigned long long tile_len,
+                                                                 int lane) {
+  if (tile == 0) {
+    if (lane == 0) st_status(status, ST_FLAG_PREFIX | tile_len);
+    return 0;
+  }
+  if (lane == 0) st_status(status + tile, ST_FLAG_AGG | tile_len);
+  unsigned long long excl = 0;
+  long long j0 = (long long)tile - 1;  // lane l looks at tile j0 - l
+  while (true) {
+    const long long j = j0 - lane;
+    unsigned long long v = ST_FLAG_PREFIX;  // before tile 0: an empty prefix
+    if (j >= 0) {
+      do {
+        v = ld_status(status + j);
+      } while ((v >> 62) == 0);
+    }
+    const unsigned has_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+    const int first = has_prefix ? (__ffs(has_prefix) - 1) : 32;  // nearest tile with a prefix
+    unsigned long long part = (lane <= first) ? (v & ST_VALUE) : 0ULL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    excl += part;
+    if (has_prefix) break;
+    j0 -= 32;
+  }
+  if (lane == 0) st_status(status + tile, ST_FLAG_PREFIX | (excl + tile_len));
+  return excl;
 }
 
 // status: n_tiles words, zeroed before the launch; ticket: one zeroed word.
@@ -118,31 +155,7 @@ __global__ void __launch_bounds__(TB)
 
   // decoupled look-back over the tiles before this one (warp 0)
   if (warp == 0) {
-    unsigned long long excl = 0;
-    if (tile == 0) {
-      if (lane == 0) st_status(status, ST_FLAG_PREFIX | tile_len);
-    } else {
-      if (lane == 0) st_status(status + tile, ST_FLAG_AGG | tile_len);
-      long long j0 = (long long)tile - 1;  // lane l looks at tile j0 - l
-      while (true) {
-        const long long j = j0 - lane;
-        unsigned long long v = ST_FLAG_PREFIX;  // before tile 0: an empty prefix
-        if (j >= 0) {
-          do {
-            v = ld_status(status + j);
-          } while ((v >> 62) == 0);
-        }
-        const unsigned has_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-        const int first = has_prefix ? (__ffs(has_prefix) - 1) : 32;  // nearest tile with a prefix
-        unsigned long long part = (lane <= first) ? (v & ST_VALUE) : 0ULL;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        excl += part;
-        if (has_prefix) break;
-        j0 -= 32;
-      }
-      if (lane == 0) st_status(status + tile, ST_FLAG_PREFIX | (excl + tile_len));
-    }
+    const unsigned long long excl = lookback_exclusive(status, tile, tile_len, lane);
     if (lane == 0) {
       s_base = excl;
       if ((unsigned long long)(tile + 1) * TB >= n) *total_out = excl + tile_len;
@@ -164,6 +177,124 @@ __global__ void __launch_bounds__(TB)
   for (uint32_t w = tid; w < nwords; w += TB) dw[w] = __byte_perm(sw[w], sw[w + 1], sel);
   const uint32_t done = head + 4u * nwords;
   if (done + tid < tile_len) dst[done + tid] = stage[done + tid];
+}
+
+// ---- importer: text -> values ------------------------------------------------------
+
+constexpr int TOK_BYTES = 16;            // text bytes per thread in the tokenizer
+constexpr int MAX_TOKEN = 256;           // longer tokens are reported as malformed
+
+// info words written by the two parser kernels
+enum : int { INFO_TOKENS = 0, INFO_STATUS = 1, INFO_FIRST_BAD = 2, INFO_EXACT = 3, INFO_WORDS = 4 };
+
+// Pass 1: token starts. A token starts at a non-space byte that follows a space (or
+// the beginning); fscanf("%Lg\n") skips any white space between numbers. starts[i]
+// receives the byte offset of token i for i <= n (entry n, if present, is where the
+// reference's file position would be after reading n numbers). text is padded to a
+// multiple of 16 bytes with spaces.
+__global__ void __launch_bounds__(TB)
+    k_text_tokenize(const unsigned char* __restrict__ text, unsigned long long len,
+                    unsigned long long n, unsigned long long* __restrict__ starts,
+                    unsigned long long* __restrict__ status, unsigned int* __restrict__ ticket,
+                    unsigned long long* __restrict__ info) {
+  __shared__ uint32_t warp_sum[TB / 32];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const unsigned long long pos = ((unsigned long long)tile * TB + tid) * TOK_BYTES;
+  uint32_t start_mask = 0;
+  if (pos < len) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + pos));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t space_mask = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+      if (is_space(c) || pos + j >= len) space_mask |= 1u << j;
+    }
+    const bool prev_space = pos == 0 ? true : is_space(__ldg(text + pos - 1));
+    start_mask = ~space_mask & ((space_mask << 1) | (prev_space ? 1u : 0u)) & 0xffffu;
+  }
+  const int cnt = __popc(start_mask);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sum[warp] = (uint32_t)incl;
+  __syncthreads();
+  uint32_t before = 0, tile_cnt = 0;
+#pragma unroll
+  for (int w = 0; w < TB / 32; w++) {
+    const uint32_t s = warp_sum[w];
+    if (w < warp) before += s;
+    tile_cnt += s;
+  }
+  if (warp == 0) {
+    const unsigned long long excl = lookback_exclusive(status, tile, tile_cnt, lane);
+    if (lane == 0) {
+      s_base = excl;
+      if (((unsigned long long)tile + 1) * TB * TOK_BYTES >= len) info[INFO_TOKENS] = excl + tile_cnt;
+    }
+  }
+  __syncthreads();
+  unsigned long long idx = s_base + before + (uint32_t)(incl - cnt);
+  while (start_mask) {
+    const int j = __ffs(start_mask) - 1;
+    start_mask &= start_mask - 1;
+    if (idx <= n) starts[idx] = pos + j;
+    idx++;
+  }
+}
+
+// Pass 2: one thread per token.
+__global__ void __launch_bounds__(TB)
+    k_text_parse(const unsigned char* __restrict__ text, unsigned long long len,
+                 unsigned long long n, const unsigned long long* __restrict__ starts,
+                 const Pow10Entry* __restrict__ tab, ulonglong2* __restrict__ values,
+                 unsigned long long* __restrict__ info, int force_band) {
+  __shared__ uint32_t big[BIG_LIMBS];
+  const int tid = threadIdx.x;
+  const unsigned long long i = (unsigned long long)blockIdx.x * TB + tid;
+  uint32_t undecided = 0;
+  Decimal dec;
+  uint64_t mant = 0;
+  uint32_t se = 0;
+  int q = 0;
+  if (i < n) {
+    const unsigned long long b = starts[i];
+    int tlen = 0;
+    while (tlen < MAX_TOKEN && b + tlen < len && !is_space(__ldg(text + b + tlen))) tlen++;
+    uint32_t st = tlen >= MAX_TOKEN ? (uint32_t)PARSE_MALFORMED : parse_token(text + b, tlen, &dec);
+    if (st == PARSE_OK) {
+      if (dec.special) {
+        mant = dec.special == 2 ? (1ULL << 63) : (3ULL << 62);
+        se = 0x7fffu;
+      } else {
+        const uint32_t r = decimal_to_x87(dec, tab, &mant, &se, &q, force_band != 0);
+        if (r == 1) undecided = 1;
+        if (r == 2) st = PARSE_UNSUPPORTED;
+      }
+    }
+    if (st != PARSE_OK) {
+      atomicMax(info + INFO_STATUS, (unsigned long long)st);
+      atomicMin(info + INFO_FIRST_BAD, i);
+    }
+  }
+  if (__syncthreads_or((int)undecided)) {
+    for (int t = 0; t < TB; t++) {
+      if (t == tid && undecided) {
+        finish_exact(dec, mant, q, big, &mant, &se);
+        atomicAdd(info + INFO_EXACT, 1ULL);
+      }
+      __syncthreads();
+    }
+  }
+  if (i < n) values[i] = make_ulonglong2(mant, (unsigned long long)(se | (dec.neg << 15)));
 }
 
 }  // namespace text

@@ -62,6 +62,8 @@ struct TextState {
   Pow10Entry* d_tab = nullptr;
   unsigned long long* d_scalars = nullptr;  // [0] total length, [1] exact-path count
   GrowBuf d_in, d_text, d_status;
+  GrowBuf d_ptext, d_starts, d_values;       // importer
+  unsigned long long* d_info = nullptr;      // importer: INFO_WORDS + 1 (starts[n])
   GrowBuf h_text, h_scalars;
   int force_exact = 0;
   uint64_t exact_total = 0;
@@ -78,6 +80,10 @@ void text_state_destroy(TextState* st) {
   st->d_in.release();
   st->d_text.release();
   st->d_status.release();
+  st->d_ptext.release();
+  st->d_starts.release();
+  st->d_values.release();
+  if (st->d_info) cudaFree(st->d_info);
   st->h_text.release();
   st->h_scalars.release();
   delete st;
@@ -103,6 +109,7 @@ int get_state(qb200_context* ctx, CtxView* view, TextState** out) {
     const std::vector<Pow10Entry>& t = host_table();
     cudaError_t e = cudaMalloc(&st->d_tab, t.size() * sizeof(Pow10Entry));
     if (e == cudaSuccess) e = cudaMalloc(&st->d_scalars, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&st->d_info, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess)
       e = cudaMemcpy(st->d_tab, t.data(), t.size() * sizeof(Pow10Entry), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(st->d_scalars, 0, 2 * sizeof(unsigned long long));
@@ -183,6 +190,43 @@ int format_host(qb200_context* ctx, int kind, const void* values, size_t n, cons
   return 0;
 }
 
+// Enqueue the two parser passes. d_info: INFO_WORDS words + one for starts[n].
+int enqueue_parse(const CtxView& view, TextState* st, const char* d_text, size_t len, size_t n,
+                  void* d_values, unsigned long long* d_info, cudaStream_t stream) {
+  const unsigned long long init[INFO_WORDS + 1] = {0, 0, ~0ULL, 0, (unsigned long long)len};
+  QT_CUDA(cudaMemcpyAsync(d_info, init, sizeof init, cudaMemcpyHostToDevice, stream));
+  if (len == 0) return 0;
+  const size_t per_tile = (size_t)TB * TOK_BYTES;
+  const size_t n_tiles = (len + per_tile - 1) / per_tile;
+  if (n_tiles > 0xffffffffULL) return set_error(-2, "text too large for one call");
+  const size_t st_bytes = (n_tiles + 1) * sizeof(unsigned long long);
+  if (int rc = st->d_status.reserve(st_bytes)) return rc;
+  if (int rc = st->d_starts.reserve((n + 2) * sizeof(unsigned long long))) return rc;
+  QT_CUDA(cudaMemsetAsync(st->d_status.p, 0, st_bytes, stream));
+  unsigned long long* status = (unsigned long long*)st->d_status.p;
+  unsigned int* ticket = (unsigned int*)(status + n_tiles);
+  unsigned long long* starts = (unsigned long long*)st->d_starts.p;
+  // starts[n] defaults to len: "everything consumed" when no further number follows
+  QT_CUDA(cudaMemcpyAsync(starts + n, &init[INFO_WORDS], sizeof(unsigned long long),
+                          cudaMemcpyHostToDevice, stream));
+  k_text_tokenize<<<(unsigned)n_tiles, TB, 0, stream>>>((const unsigned char*)d_text, len, n, starts,
+                                                        status, ticket, d_info);
+  QT_CUDA(cudaGetLastError());
+  (*view.launches)++;
+  if (n) {
+    // tokens beyond those present leave their entries untouched: the host checks the count first
+    k_text_parse<<<(unsigned)((n + TB - 1) / TB), TB, 0, stream>>>(
+        (const unsigned char*)d_text, len, n, starts, st->d_tab, (ulonglong2*)d_values, d_info,
+        st->force_exact);
+    QT_CUDA(cudaGetLastError());
+    (*view.launches)++;
+  }
+  // starts[n] (the position after the n-th number and the white space behind it)
+  QT_CUDA(cudaMemcpyAsync(d_info + INFO_WORDS, starts + n, sizeof(unsigned long long),
+                          cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -208,6 +252,52 @@ int qb200_text_format_device(qb200_context* ctx, int kind, const void* d_values,
   if (int rc = get_state(ctx, &view, &st)) return rc;
   return enqueue_format(view, st, kind, d_values, n, d_text, cap, (unsigned long long*)d_len,
                         stream ? (cudaStream_t)stream : view.stream);
+}
+
+int qb200_text_parse_ld(qb200_context* ctx, const char* text, size_t len, size_t n,
+                        long double* values, size_t* consumed) {
+  if ((len && !text) || (n && !values)) return set_error(-1, "null argument");
+  CtxView view;
+  TextState* st = nullptr;
+  if (int rc = get_state(ctx, &view, &st)) return rc;
+  const size_t padded = (len + 15) / 16 * 16 + 16;
+  if (int rc = st->d_ptext.reserve(padded)) return rc;
+  if (int rc = st->d_values.reserve(std::max<size_t>(16, n * 16))) return rc;
+  if (int rc = st->d_starts.reserve((n + 2) * sizeof(unsigned long long))) return rc;
+  if (len) {
+    QT_CUDA(cudaMemcpyAsync(st->d_ptext.p, text, len, cudaMemcpyHostToDevice, view.stream));
+    QT_CUDA(cudaMemsetAsync((char*)st->d_ptext.p + len, ' ', padded - len, view.stream));
+  }
+  if (int rc = enqueue_parse(view, st, (const char*)st->d_ptext.p, len, n, st->d_values.p,
+                             st->d_info, view.stream))
+    return rc;
+  unsigned long long* hs = (unsigned long long*)st->h_scalars.p;
+  QT_CUDA(cudaMemcpyAsync(hs, st->d_info, (INFO_WORDS + 1) * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, view.stream));
+  QT_CUDA(cudaStreamSynchronize(view.stream));
+  st->exact_total = hs[INFO_EXACT];
+  if (hs[INFO_TOKENS] < n)
+    return set_error(-20, "text holds " + std::to_string(hs[INFO_TOKENS]) + " numbers, " +
+                              std::to_string(n) + " expected");
+  if (hs[INFO_STATUS] != 0)
+    return set_error(hs[INFO_STATUS] == 1 ? -21 : -22,
+                     std::string(hs[INFO_STATUS] == 1 ? "malformed number" : "unsupported number form") +
+                         " (number " + std::to_string(hs[INFO_FIRST_BAD]) + " of the text)");
+  if (n) {
+    QT_CUDA(cudaMemcpyAsync(values, st->d_values.p, n * 16, cudaMemcpyDeviceToHost, view.stream));
+    QT_CUDA(cudaStreamSynchronize(view.stream));
+  }
+  if (consumed) *consumed = hs[INFO_TOKENS] > n ? (size_t)hs[INFO_WORDS] : len;
+  return 0;
+}
+
+int qb200_text_parse_device(qb200_context* ctx, const char* d_text, size_t len, size_t n,
+                            void* d_values, uint64_t* d_info, void* stream) {
+  CtxView view;
+  TextState* st = nullptr;
+  if (int rc = get_state(ctx, &view, &st)) return rc;
+  return enqueue_parse(view, st, d_text, len, n, d_values, (unsigned long long*)d_info,
+                       stream ? (cudaStream_t)stream : view.stream);
 }
 
 int qb200_text_pow10(int k, uint32_t w[6], int32_t* e2, uint32_t* exact) {

@@ -38,11 +38,11 @@
 namespace qb200 {
 namespace text {
 
-constexpr int K_MIN = -4936;       // powers of ten tabulated: 10^K_MIN .. 10^K_MAX
-constexpr int K_MAX = 4953;
+constexpr int K_MIN = -5000;       // powers of ten tabulated: 10^K_MIN .. 10^K_MAX
+constexpr int K_MAX = 4970;        // (formatter: -4934..4951; parser: -4992..4940)
 constexpr int K_EXACT_MAX = 82;    // 5^82 < 2^191: 10^k is exact in 192 bits for 0 <= k <= 82
 constexpr int MAX_TEXT = 33;       // "-d.ddddddddddddddddddddddde-4932\n"
-constexpr int BIG_LIMBS = 376;     // exact path: (96 + log2(5) * 4975) / 32 limbs
+constexpr int BIG_LIMBS = 376;     // exact path: (96 + log2(5) * 5000) / 32 = 366 limbs
 
 // 10^k ~ T * 2^(e2 - 191), T = w[5]..w[0] (little-endian 32-bit limbs), 2^191 <= T < 2^192,
 // T = floor(true): exact iff 0 <= k <= K_EXACT_MAX.
@@ -105,7 +105,7 @@ QT_HD int trailing_zeros8(uint64_t a) {
 }
 
 // Sign of (z0 * 5^n  -  other * 2^t) by exact integer arithmetic; z0, other < 2^96
-// (three limbs, little-endian), 0 <= n <= 4975, any t. scratch: BIG_LIMBS words.
+// (three limbs, little-endian), 0 <= n <= 5000, any t. scratch: BIG_LIMBS words.
 QT_HD_NOINLINE int cmp_pow5(const uint32_t z0[3], int n, const uint32_t other[3], int t,
                             uint32_t* Z) {
   int len = 3;

@@ -1,0 +1,220 @@
+// dropin_text.cpp -- the reference-side forwarding translation unit for the slice
+// TEXT FORMAT.
+//
+// This file is what a maintainer of ekera/qunundrum adds to the reference's src/
+// directory IN PLACE OF the three translation units
+//
+//   distribution_slice_import_export.cpp
+//   linear_distribution_slice_import_export.cpp
+//   diagonal_distribution_slice_import_export.cpp
+//
+// It defines the same nine functions (*_slice_import, *_slice_init_import,
+// *_slice_export) with the same C++ signatures. The header fields keep going
+// through fscanf / fprintf exactly as in the reference; the cells and the total
+// error -- one "%.24Lg\n" / "%Lg\n" per value, 65,537 per stored two-dimensional
+// slice -- go through the C ABI of libqunundrum_b200.so (qb200_text_format_ld,
+// qb200_text_parse_ld), which produces the very same bytes / bits on the GPU.
+// distribution_export(), distribution_import(), the .txt layout, the MPI
+// protocol and every caller are untouched.
+//
+// Conventions kept: callers own the slice and the FILE; the importers re-init
+// the slice when the stored dimension differs; total_probability is the running
+// long double sum in index order (src/distribution_slice_import_export.cpp:38-46);
+// errors are fatal (critical(), src/errors.c). The importers need a seekable
+// FILE (a regular file, as every caller in the reference passes): the numbers
+// are read in one block and the position is then set to where fscanf would have
+// left it.
+#include "common.h"
+#include "diagonal_distribution_slice.h"
+#include "distribution_slice.h"
+#include "errors.h"
+#include "linear_distribution_slice.h"
+
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "qunundrum_b200.h"
+
+namespace {
+
+qb200_context* g_text_ctx = NULL;
+std::mutex g_text_mutex;  // the server exports from worker threads (main_server_export_distribution)
+
+qb200_context* text_context() {
+  if (g_text_ctx) return g_text_ctx;
+  const int n = qb200_device_count();
+  if (n <= 0) critical("qunundrum_b200: no CUDA device (there is no CPU path).");
+  const char* v = getenv("QB200_TEXT_DEVICE");
+  if (!v || !*v) v = getenv("QB200_DEVICE");
+  int device = (v && *v) ? atoi(v) : 0;
+  device = ((device % n) + n) % n;
+  if (0 != qb200_create(device, &g_text_ctx)) critical("qunundrum_b200: %s", qb200_last_error());
+  return g_text_ctx;
+}
+
+// The exporter's value loop: n cells, then the total error.
+void export_values(FILE* const file, const long double* const values, const size_t n,
+                   const long double total_error, const char* who) {
+  std::lock_guard<std::mutex> lock(g_text_mutex);
+  const char* text = NULL;
+  size_t len = 0;
+  if (0 != qb200_text_format_ld(text_context(), values, n, &total_error, &text, &len)) {
+    critical("%s(): %s", who, qb200_last_error());
+  }
+  if (len != fwrite(text, 1, len, file)) {
+    critical("%s(): Failed to write to the file.", who);
+  }
+}
+
+// The importer's value loop: n cells into values (summed into *total_probability
+// in index order), then the total error.
+void import_values(FILE* const file, long double* const values, const size_t n,
+                   long double* const total_probability, long double* const total_error,
+                   const char* who) {
+  std::lock_guard<std::mutex> lock(g_text_mutex);
+  const long pos = ftell(file);
+  if (pos < 0) critical("%s(): The file is not seekable.", who);
+  std::vector<char> buf;
+  std::vector<long double> parsed(n + 1);
+  size_t want = 40 * (n + 1) + 64, used = 0;
+  for (;;) {
+    buf.resize(want);
+    const size_t got = fread(buf.data(), 1, want, file);
+    const int rc = qb200_text_parse_ld(text_context(), buf.data(), got, n + 1, parsed.data(), &used);
+    if (0 == rc) break;
+    if (-20 == rc && got == want) {  // the block ended before the last number: read more
+      if (0 != fseek(file, pos, SEEK_SET)) critical("%s(): The file is not seekable.", who);
+      want *= 2;
+      continue;
+    }
+    critical("%s(): Failed to import an element: %s", who, qb200_last_error());
+  }
+  if (0 != fseek(file, pos + (long)used, SEEK_SET)) critical("%s(): The file is not seekable.", who);
+  *total_probability = 0;
+  for (size_t i = 0; i < n; i++) {
+    values[i] = parsed[i];
+    *total_probability += values[i];
+  }
+  *total_error = parsed[n];
+}
+
+uint32_t import_dimension(FILE* const file, const char* who) {
+  uint32_t dimension;
+  if (1 != fscanf(file, "%u\n", &dimension)) critical("%s(): Failed to import the dimension.", who);
+  return dimension;
+}
+
+void import_common_2d(Distribution_Slice* const slice, FILE* const file) {
+  const char* who = "distribution_slice_import_common";
+  if (1 != fscanf(file, "%d\n", &(slice->min_log_alpha_d))) critical("%s(): Failed to import min_log_alpha_d.", who);
+  if (1 != fscanf(file, "%d\n", &(slice->min_log_alpha_r))) critical("%s(): Failed to import min_log_alpha_r.", who);
+  if (1 != fscanf(file, "%x\n", &(slice->flags))) critical("%s(): Failed to import flags.", who);
+  import_values(file, slice->norm_matrix, (size_t)slice->dimension * slice->dimension,
+                &slice->total_probability, &slice->total_error, who);
+}
+
+void import_common_linear(Linear_Distribution_Slice* const slice, FILE* const file) {
+  const char* who = "linear_distribution_slice_import";
+  if (1 != fscanf(file, "%d\n", &(slice->min_log_alpha))) critical("%s(): Failed to import min_log_alpha.", who);
+  if (1 != fscanf(file, "%x\n", &(slice->flags))) critical("%s(): Failed to import flags.", who);
+  import_values(file, slice->norm_vector, slice->dimension, &slice->total_probability,
+                &slice->total_error, who);
+}
+
+void import_common_diagonal(Diagonal_Distribution_Slice* const slice, FILE* const file) {
+  const char* who = "diagonal_distribution_slice_import_common";
+  if (1 != fscanf(file, "%d\n", &(slice->min_log_alpha_r))) critical("%s(): Failed to import min_log_alpha_r.", who);
+  if (1 != fscanf(file, "%d\n", &(slice->eta))) critical("%s(): Failed to import eta.", who);
+  if (1 != fscanf(file, "%x\n", &(slice->flags))) critical("%s(): Failed to import flags.", who);
+  import_values(file, slice->norm_vector, slice->dimension, &slice->total_probability,
+                &slice->total_error, who);
+}
+
+}  // namespace
+
+/* ---- two-dimensional slices (src/distribution_slice_import_export.cpp) ---------- */
+
+void distribution_slice_import(Distribution_Slice* const slice, FILE* const file) {
+  const uint32_t dimension = import_dimension(file, "distribution_slice_import");
+  if (dimension != slice->dimension) {
+    distribution_slice_clear(slice);
+    distribution_slice_init(slice, dimension);
+  }
+  import_common_2d(slice, file);
+}
+
+void distribution_slice_init_import(Distribution_Slice* const slice, FILE* const file) {
+  const uint32_t dimension = import_dimension(file, "distribution_slice_init_import");
+  distribution_slice_init(slice, dimension);
+  import_common_2d(slice, file);
+}
+
+void distribution_slice_export(const Distribution_Slice* const slice, FILE* const file) {
+  fprintf(file, "%u\n", slice->dimension);
+  fprintf(file, "%d\n", slice->min_log_alpha_d);
+  fprintf(file, "%d\n", slice->min_log_alpha_r);
+  fprintf(file, "%.8x\n", slice->flags);
+  export_values(file, slice->norm_matrix, (size_t)slice->dimension * slice->dimension,
+                slice->total_error, "distribution_slice_export");
+}
+
+/* ---- linear slices (src/linear_distribution_slice_import_export.cpp) ------------ */
+
+void linear_distribution_slice_import(Linear_Distribution_Slice* const slice, FILE* const file) {
+  const uint32_t dimension = import_dimension(file, "linear_distribution_slice_import");
+  if (dimension != slice->dimension) {
+    linear_distribution_slice_clear(slice);
+    linear_distribution_slice_init(slice, dimension);
+  }
+  import_common_linear(slice, file);
+}
+
+void linear_distribution_slice_init_import(Linear_Distribution_Slice* const slice,
+                                           FILE* const file) {
+  const uint32_t dimension = import_dimension(file, "linear_distribution_slice_init_import");
+  linear_distribution_slice_init(slice, dimension);
+  import_common_linear(slice, file);
+}
+
+void linear_distribution_slice_export(const Linear_Distribution_Slice* const slice,
+                                      FILE* const file) {
+  fprintf(file, "%u\n", slice->dimension);
+  fprintf(file, "%d\n", slice->min_log_alpha);
+  fprintf(file, "%.8x\n", slice->flags);
+  export_values(file, slice->norm_vector, slice->dimension, slice->total_error,
+                "linear_distribution_slice_export");
+}
+
+/* ---- diagonal slices (src/diagonal_distribution_slice_import_export.cpp) --------- */
+
+void diagonal_distribution_slice_import(Diagonal_Distribution_Slice* const slice,
+                                        FILE* const file) {
+  const uint32_t dimension = import_dimension(file, "diagonal_distribution_slice_import");
+  if (dimension != slice->dimension) {
+    diagonal_distribution_slice_clear(slice);
+    diagonal_distribution_slice_init(slice, dimension);
+  }
+  import_common_diagonal(slice, file);
+}
+
+void diagonal_distribution_slice_init_import(Diagonal_Distribution_Slice* const slice,
+                                             FILE* const file) {
+  const uint32_t dimension = import_dimension(file, "diagonal_distribution_slice_init_import");
+  diagonal_distribution_slice_init(slice, dimension);
+  import_common_diagonal(slice, file);
+}
+
+void diagonal_distribution_slice_export(const Diagonal_Distribution_Slice* const slice,
+                                        FILE* const file) {
+  fprintf(file, "%u\n", slice->dimension);
+  fprintf(file, "%d\n", slice->min_log_alpha_r);
+  fprintf(file, "%d\n", slice->eta);
+  fprintf(file, "%.8x\n", slice->flags);
+  export_values(file, slice->norm_vector, slice->dimension, slice->total_error,
+                "diagonal_distribution_slice_export");
+}

@@ -110,6 +110,9 @@ def lib():
     L.qb200_text_format_f64.argtypes = [vp, vp, C.c_size_t, vp, C.POINTER(vp),
                                         C.POINTER(C.c_size_t)]
     L.qb200_text_format_device.argtypes = [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, vp]
+    L.qb200_text_parse_ld.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_size_t, vp,
+                                      C.POINTER(C.c_size_t)]
+    L.qb200_text_parse_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp, vp, vp]
     L.qb200_text_pow10.argtypes = [C.c_int, vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
     L.qb200_text_set_force_exact.argtypes = [vp, C.c_int]
     L.qb200_text_exact_count.argtypes = [vp]
@@ -390,6 +393,20 @@ class Context:
         _check(lib().qb200_text_format_device(self.h, kind, d_values_ptr, n, d_text_ptr, cap,
                                               d_len_ptr, stream), "qb200_text_format_device")
 
+    def text_parse(self, text: bytes, n: int):
+        """The first n white-space separated '%Lg' numbers of text as long doubles,
+        and the offset where the reference's FILE position would be afterwards."""
+        v = np.zeros(max(n, 1), dtype=np.longdouble)
+        used = C.c_size_t()
+        _check(lib().qb200_text_parse_ld(self.h, text, len(text), n, v.ctypes.data,
+                                         C.byref(used)), "qb200_text_parse_ld")
+        return v[:n], used.value
+
+    def text_parse_device(self, d_text_ptr: int, length: int, n: int, d_values_ptr: int,
+                          d_info_ptr: int, stream: int = 0):
+        _check(lib().qb200_text_parse_device(self.h, d_text_ptr, length, n, d_values_ptr,
+                                             d_info_ptr, stream), "qb200_text_parse_device")
+
     def text_set_force_exact(self, on: bool):
         _check(lib().qb200_text_set_force_exact(self.h, int(bool(on))), "qb200_text_set_force_exact")
 
@@ -563,3 +580,76 @@ def diagonal_distribution_slice_export(slice, file, ctx=None):
     file.write(b"%u\n%d\n%d\n%.8x\n" % (slice.dimension, slice.min_log_alpha_r, slice.eta,
                                        slice.flags))
     file.write(ctx.text_format(slice.norm_vector, slice.total_error))
+
+
+# --------------------------------------------------------------------------- #
+# The reference's slice importers                                             #
+# --------------------------------------------------------------------------- #
+
+def _import_numbers(file, n: int, ctx):
+    """n numbers from the current position of a seekable binary file; leaves the
+    position where fscanf("%Lg\\n") x n would (after the white space that follows)."""
+    pos = file.tell()
+    want = 40 * n + 64
+    while True:
+        chunk = file.read(want)
+        try:
+            values, used = ctx.text_parse(chunk, n)
+            break
+        except CriticalError as e:      # -20: the chunk ended before the n-th number
+            if len(chunk) < want or "(code -20)" not in str(e):
+                raise
+            file.seek(pos)
+            want *= 2
+    file.seek(pos + used)
+    return values
+
+
+def _import_common(file, n_head: int):
+    head = []
+    for i in range(n_head):
+        line = file.readline()
+        if not line.strip():
+            raise CriticalError("slice import: failed to import a header field")
+        head.append(int(line, 16) if i == n_head - 1 else int(line))
+    return head
+
+
+def distribution_slice_import(file, ctx=None) -> Distribution_Slice:
+    """distribution_slice_init_import (src/distribution_slice_import_export.cpp:72-87):
+    dimension, min_log_alpha_d, min_log_alpha_r, flags, dimension^2 cells, total_error;
+    total_probability is the running long double sum of the cells (:38-46)."""
+    ctx = ctx or default_context()
+    dimension, a_d, a_r, flags = _import_common(file, 4)
+    v = _import_numbers(file, dimension * dimension + 1, ctx)
+    s = Distribution_Slice(dimension, a_d, a_r, flags=flags, norm_matrix=v[:-1].copy(),
+                           total_error=v[-1])
+    s.total_probability = _sequential_sum(s.norm_matrix)
+    return s
+
+
+def linear_distribution_slice_import(file, ctx=None) -> Linear_Distribution_Slice:
+    """linear_distribution_slice_init_import (src/linear_distribution_slice_import_export.cpp:67-80)."""
+    ctx = ctx or default_context()
+    dimension, a, flags = _import_common(file, 3)
+    v = _import_numbers(file, dimension + 1, ctx)
+    s = Linear_Distribution_Slice(dimension, a, flags=flags, norm_vector=v[:-1].copy(),
+                                  total_error=v[-1])
+    s.total_probability = _sequential_sum(s.norm_vector)
+    return s
+
+
+def diagonal_distribution_slice_import(file, ctx=None) -> Diagonal_Distribution_Slice:
+    """diagonal_distribution_slice_init_import (src/diagonal_distribution_slice_import_export.cpp:72-85)."""
+    ctx = ctx or default_context()
+    dimension, a_r, eta, flags = _import_common(file, 4)
+    v = _import_numbers(file, dimension + 1, ctx)
+    s = Diagonal_Distribution_Slice(dimension, a_r, eta, flags=flags, norm_vector=v[:-1].copy(),
+                                    total_error=v[-1])
+    s.total_probability = _sequential_sum(s.norm_vector)
+    return s
+
+
+def _sequential_sum(v) -> np.longdouble:
+    # the reference accumulates in index order in long double; np.cumsum does exactly that
+    return np.cumsum(np.asarray(v, dtype=np.longdouble))[-1] if len(v) else np.longdouble(0)

@@ -18,7 +18,7 @@ _SRCS = [os.path.join(_HERE, "hostsim.cpp"),
          os.path.join(_ROOT, "qunundrum_b200", "csrc", "text_tables.cpp")]
 _DEPS = _SRCS + [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
                  ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "sigma_opt.cuh", "plan.hpp",
-                  "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "text_tables.hpp")]
+                  "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "textparse.cuh", "text_tables.hpp")]
 _lib = None
 
 
@@ -135,3 +135,17 @@ def text_format_ld(values, force_band=False):
     n = lib().hostsim_text_format_ld(v.ctypes.data_as(C.c_void_p), C.c_size_t(v.size), out,
                                      C.c_int(1 if force_band else 0), C.byref(nx))
     return out.raw[:n], nx.value
+
+
+def text_parse_ld(text: bytes, n: int, force_band=False):
+    """The first n numbers of text through the CPU compile of textparse.cuh:
+    (values, consumed, n_exact); raises ValueError(code) on a parse error."""
+    v = np.zeros(max(n, 1), dtype=np.longdouble)
+    used = C.c_size_t()
+    nx = C.c_uint64()
+    rc = lib().hostsim_text_parse_ld(text, C.c_size_t(len(text)), C.c_size_t(n),
+                                     v.ctypes.data_as(C.c_void_p), C.byref(used),
+                                     C.c_int(1 if force_band else 0), C.byref(nx))
+    if rc:
+        raise ValueError(rc)
+    return v[:n], used.value, nx.value

