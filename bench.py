@@ -29,6 +29,13 @@ data-path collective); only the per-slice summaries are gathered on rank 0.
             fewer flops than the canonical count (separable angle addition, see
             DESIGN.md), so `frac` can exceed 1; `executed_frac` is the share of
             the FP64 pipe actually used (from the committed ncu capture).
+`text`    : SURVEY.md section 8(f) #1, the slice text format: the cells of this very
+            step (doubles, 2^24 of them) through the exporter kernel ("%.24Lg\\n"
+            per value) and the text back through the importer kernels, device
+            resident, CUDA events; HBM-roofline fraction from the algorithmic bytes
+            (value in + text out); the synchronous host call on one stored slice
+            (65,536 cells + total error); libc's fprintf / fscanf on one host core
+            beside it. Byte / bit parity is asserted on a sample in the run.
 `cpu_baseline` / --impl reference: the UNMODIFIED reference
             (oracle/_ref/libqref.so, distribution_slice_compute_richardson with
             192-bit MPFR) on the host cores, one slice per worker process.
@@ -219,6 +226,97 @@ def profile_constants():
         return None
 
 
+def text_section(ctx, qb, torch, stream, cells, hbm_peak):
+    """Exporter / importer kernels on the step's own cells (rank 0, N = 1)."""
+    from oracle import text as ot          # checker + libc baseline only
+    n = min(1 << 24, cells.numel())
+    cap = 33 * n
+    d_text = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_vals = torch.empty(2 * n, dtype=torch.int64, device="cuda")
+    d_info = torch.zeros(8, dtype=torch.int64, device="cuda")
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    reps = 10
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    l0 = ctx.launch_count
+    ms_f = timed(lambda: ctx.text_format_device(qb.host.TEXT_F64, cells.data_ptr(), n,
+                                                d_text.data_ptr(), cap, d_len.data_ptr(),
+                                                stream.cuda_stream))
+    length = int(d_len.item())
+    ms_p = timed(lambda: ctx.text_parse_device(d_text.data_ptr(), length, n, d_vals.data_ptr(),
+                                               d_info.data_ptr(), stream.cuda_stream))
+    launches = ctx.launch_count - l0
+    info = d_info.cpu().numpy()
+    if int(info[0]) != n or int(info[1]) != 0:
+        raise SystemExit(f"bench.py: importer status {info}")
+    # parity on a sample: bytes against libc, and the importer's bits against libc's
+    k = 200000
+    h = cells[:k].cpu().numpy().astype(np.longdouble)
+    t0 = time.perf_counter()
+    want = ot.format_ld24(h)
+    t_fmt = time.perf_counter() - t0
+    got = bytes(d_text[:len(want)].cpu().numpy().tobytes())
+    if got != want:
+        raise SystemExit("bench.py: exporter text differs from libc")
+    t0 = time.perf_counter()
+    back = ot.parse_ld(want, k)
+    t_par = time.perf_counter() - t0
+    m_ref, s_ref = ot.ld_fields(back)
+    raw = d_vals[:2 * k].cpu().numpy().view(np.uint64).reshape(k, 2)
+    if not (np.array_equal(raw[:, 0], m_ref) and np.array_equal(raw[:, 1].astype(np.uint16), s_ref)):
+        raise SystemExit("bench.py: importer values differ from libc")
+    # the synchronous host call on one stored slice (256 x 256 cells + total error)
+    one = cells[:65536].cpu().numpy().astype(np.longdouble)
+    tail = np.longdouble("2.5e-307")
+    text1 = ctx.text_format(one, tail)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.text_format(one, tail)
+    ms_host_f = (time.perf_counter() - t0) / 20 * 1e3
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.text_parse(text1, 65537)
+    ms_host_p = (time.perf_counter() - t0) / 20 * 1e3
+    bytes_f = 8 * n + length          # doubles in, text out
+    bytes_p = length + 16 * n         # text in, x87 values out
+    return {
+        "values": n, "text_bytes": length, "bytes_per_value": length / n,
+        "export": {"values_per_s": n / (ms_f * 1e-3), "ms": ms_f,
+                   "roofline": {"bound": "hbm", "achieved": bytes_f / (ms_f * 1e-3) / 1e9,
+                                "peak": hbm_peak, "unit": "GB/s",
+                                "frac": bytes_f / (ms_f * 1e-3) / 1e9 / hbm_peak},
+                   "kernel": "k_text_format<F64>",
+                   "host_call_ms_per_slice": ms_host_f,
+                   "host_call_values_per_s": 65537 / (ms_host_f * 1e-3)},
+        "import": {"values_per_s": n / (ms_p * 1e-3), "ms": ms_p,
+                   "roofline": {"bound": "hbm", "achieved": bytes_p / (ms_p * 1e-3) / 1e9,
+                                "peak": hbm_peak, "unit": "GB/s",
+                                "frac": bytes_p / (ms_p * 1e-3) / 1e9 / hbm_peak},
+                   "kernels": "k_text_tokenize + k_text_parse",
+                   "host_call_ms_per_slice": ms_host_p,
+                   "host_call_values_per_s": 65537 / (ms_host_p * 1e-3)},
+        "cpu_baseline": {"kind": "reference", "cores": 1,
+                         "export_values_per_s": k / t_fmt, "import_values_per_s": k / t_par,
+                         "sample": f"{k} cells of the step through libc fprintf(\"%.24Lg\\n\") / "
+                                   f"fscanf(\"%Lg\\n\") ({ot.libc_version()}), the calls the "
+                                   "reference's slice exporters / importers make"},
+        "parity": f"first {k} values: text byte-identical to libc, parsed bits identical to libc",
+        "gpu_launches": int(launches),
+    }
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import qunundrum_b200 as qb
@@ -345,15 +443,21 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
 
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    text = None
+    if world == 1 and not args.no_text:
+        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)   # the step's own cells
+        torch.cuda.synchronize()
+        text = text_section(ctx, qb, torch, stream, cells, hbm_peak)
+
     if rank == 0:
         prof = profile_constants() or {}
         achieved = (plan.cells / (ms_per_step * 1e-3)) * FLOP_PER_CELL / 1e12  # per GPU
         peak = peak_flops / 1e12
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-            hbm_src = "measured (MEASURED_PEAKS.json)"
-        except Exception:
-            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         out_gbs = nbytes / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world,
@@ -374,6 +478,7 @@ def run_ours(args, rank, world, local_rank):
                 "note": "per GPU; step time includes the three small table/summary kernels (<1.5%)",
             },
             "cpu_baseline": cpu,
+            "text": text,
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "ms_per_step": wall / e2e_steps * 1e3,
@@ -398,6 +503,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -413,6 +519,8 @@ def main():
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
+        if args.no_text:
+            cmd.append("--no-text")
         raise SystemExit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

@@ -37,6 +37,17 @@ from .host import (  # noqa: F401
     lib_path,
     linear_distribution_slice_compute,
     linear_distribution_slice_compute_richardson,
+    # the slice text format
+    TEXT_F64,
+    TEXT_X87,
+    diagonal_distribution_slice_export,
+    diagonal_distribution_slice_import,
+    distribution_slice_export,
+    distribution_slice_import,
+    linear_distribution_slice_export,
+    linear_distribution_slice_import,
+    text_pow10,
 )
+from . import host  # noqa: F401,E402
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -134,7 +134,7 @@ int enqueue_format(const CtxView& view, TextState* st, int kind, const void* d_v
     QT_CUDA(cudaMemsetAsync(d_len, 0, sizeof(unsigned long long), stream));
     return 0;
   }
-  const size_t n_tiles = (n + TB - 1) / TB;
+  const size_t n_tiles = (n + TILE - 1) / TILE;
   if (n_tiles > 0xffffffffULL) return set_error(-2, "too many values for one call");
   const size_t st_bytes = (n_tiles + 1) * sizeof(unsigned long long);
   if (int rc = st->d_status.reserve(st_bytes)) return rc;
@@ -142,11 +142,11 @@ int enqueue_format(const CtxView& view, TextState* st, int kind, const void* d_v
   unsigned long long* status = (unsigned long long*)st->d_status.p;
   unsigned int* ticket = (unsigned int*)(status + n_tiles);
   if (kind == QB200_TEXT_X87)
-    k_text_format<SRC_X87><<<(unsigned)n_tiles, TB, 0, stream>>>(
+    k_text_format<SRC_X87><<<(unsigned)n_tiles, TEXT_THREADS, 0, stream>>>(
         d_values, n, st->d_tab, (unsigned char*)d_text, cap, status, ticket, d_len,
         st->d_scalars + 1, st->force_exact);
   else
-    k_text_format<SRC_F64><<<(unsigned)n_tiles, TB, 0, stream>>>(
+    k_text_format<SRC_F64><<<(unsigned)n_tiles, TEXT_THREADS, 0, stream>>>(
         d_values, n, st->d_tab, (unsigned char*)d_text, cap, status, ticket, d_len,
         st->d_scalars + 1, st->force_exact);
   QT_CUDA(cudaGetLastError());
@@ -196,7 +196,7 @@ int enqueue_parse(const CtxView& view, TextState* st, const char* d_text, size_t
   const unsigned long long init[INFO_WORDS + 1] = {0, 0, ~0ULL, 0, (unsigned long long)len};
   QT_CUDA(cudaMemcpyAsync(d_info, init, sizeof init, cudaMemcpyHostToDevice, stream));
   if (len == 0) return 0;
-  const size_t per_tile = (size_t)TB * TOK_BYTES;
+  const size_t per_tile = (size_t)TOK_TILE_BYTES;
   const size_t n_tiles = (len + per_tile - 1) / per_tile;
   if (n_tiles > 0xffffffffULL) return set_error(-2, "text too large for one call");
   const size_t st_bytes = (n_tiles + 1) * sizeof(unsigned long long);
@@ -313,7 +313,7 @@ int qb200_text_set_force_exact(qb200_context* ctx, int on) {
   CtxView view;
   TextState* st = nullptr;
   if (int rc = get_state(ctx, &view, &st)) return rc;
-  st->force_exact = on ? 1 : 0;
+  st->force_exact = on;  // 1: exact decision for every value; 2: timing experiment (no chain)
   return 0;
 }
 

@@ -86,16 +86,18 @@ QT_HD uint32_t frac_mul(uint32_t (&F)[10], uint32_t c) {
   return carry;
 }
 
+// Four decimal digits of h < 10^4 as ASCII, first digit in the lowest byte.
+QT_HD uint32_t ascii4(uint32_t h) {
+  const uint32_t q = (h * 5243u) >> 19;          // h / 100
+  const uint32_t y = q | ((h - q * 100u) << 16);  // two 2-digit numbers in 16-bit lanes
+  const uint32_t tens = ((y * 103u) >> 10) & 0x000F000Fu;
+  return tens | ((y - tens * 10u) << 8) | 0x30303030u;
+}
+
 // Eight decimal digits of c < 10^8 as ASCII, first digit in the lowest byte.
 QT_HD uint64_t ascii8(uint32_t c) {
   const uint32_t hi = c / 10000u, lo = c - hi * 10000u;
-  const uint64_t x = ((uint64_t)lo << 32) | hi;
-  const uint64_t q100 = ((x * 5243u) >> 19) & 0x0000007F0000007FULL;
-  const uint64_t r100 = x - q100 * 100u;
-  const uint64_t y = q100 | (r100 << 16);
-  const uint64_t tens = ((y * 103u) >> 10) & 0x000F000F000F000FULL;
-  const uint64_t ones = y - tens * 10u;
-  return tens | (ones << 8) | 0x3030303030303030ULL;
+  return (uint64_t)ascii4(hi) | ((uint64_t)ascii4(lo) << 32);
 }
 
 // Number of trailing '0' characters of an ascii8 group (8 if all).
@@ -323,7 +325,23 @@ QT_HD int piece_length(const Piece& p) {
 
 QT_HD char piece_digit(const Piece& p, int j) {
   const uint64_t a = j < 8 ? p.a0 : (j < 16 ? p.a1 : p.a2);
-  return (char)((a >> (8 * (j & 7))) & 0xff);
+  const uint32_t w = (j & 4) ? (uint32_t)(a >> 32) : (uint32_t)a;
+  return (char)(w >> (8 * (j & 3)));
+}
+
+// "e+XX\n" / "e-XXXX\n" at out[pos...]
+template <class Ptr>
+QT_HD void render_exponent(Ptr out, int pos, int x) {
+  const uint32_t ax = (uint32_t)(x < 0 ? -x : x);  // < 5000
+  out[pos++] = 'e';
+  out[pos++] = x < 0 ? '-' : '+';
+  const uint32_t hi2 = (ax * 5243u) >> 19, lo2 = ax - hi2 * 100u;
+  const uint32_t t1 = (hi2 * 103u) >> 10, t0 = (lo2 * 103u) >> 10;
+  if (ax >= 1000u) out[pos++] = (char)('0' + t1);
+  if (ax >= 100u) out[pos++] = (char)('0' + (hi2 - t1 * 10u));
+  out[pos++] = (char)('0' + t0);
+  out[pos++] = (char)('0' + (lo2 - t0 * 10u));
+  out[pos] = '\n';
 }
 
 // Writes piece_length(p) characters to out.
@@ -331,6 +349,25 @@ template <class Ptr>
 QT_HD void piece_render(const Piece& p, Ptr out) {
   int pos = 0;
   if (p.neg) out[pos++] = '-';
+  const int x = p.x;
+  const bool estyle = !p.special && (x < -4 || x >= 24);
+#if defined(__CUDA_ARCH__)
+  // warp-uniform choice: no divergence between the two digit loops
+  const bool fast = __all_sync(__activemask(), estyle) != 0;
+#else
+  const bool fast = estyle;
+#endif
+  if (fast) {
+    // d[.ddd]e+XX with every digit offset a compile-time constant
+    const int nd = p.ndig;
+    out[pos] = piece_digit(p, 0);
+    if (nd > 1) out[pos + 1] = '.';
+#pragma unroll
+    for (int j = 1; j < 24; j++)
+      if (j < nd) out[pos + 1 + j] = piece_digit(p, j);
+    render_exponent(out, pos + nd + (nd > 1 ? 1 : 0), x);
+    return;
+  }
   if (p.special) {
     if (p.special == 1) {
       out[pos++] = '0';
@@ -343,8 +380,6 @@ QT_HD void piece_render(const Piece& p, Ptr out) {
     out[pos] = '\n';
     return;
   }
-  const int x = p.x;
-  const bool estyle = x < -4 || x >= 24;
   int nd = p.ndig, point = 1;
   if (!estyle) {
     if (x >= 0) {
@@ -360,28 +395,16 @@ QT_HD void piece_render(const Piece& p, Ptr out) {
     }
   }
   const bool has_point = nd > point;
+  const int pos1 = pos + (has_point ? 1 : 0);
 #pragma unroll
   for (int j = 0; j < 24; j++)
-    if (j < nd) out[pos + j + ((has_point && j >= point) ? 1 : 0)] = piece_digit(p, j);
+    if (j < nd) out[(j >= point ? pos1 : pos) + j] = piece_digit(p, j);
   if (has_point) out[pos + point] = '.';
   pos += nd + (has_point ? 1 : 0);
-  if (estyle) {
-    int ax = x < 0 ? -x : x;
-    out[pos++] = 'e';
-    out[pos++] = x < 0 ? '-' : '+';
-    if (ax >= 1000) {
-      out[pos++] = (char)('0' + ax / 1000);
-      ax %= 1000;
-      out[pos++] = (char)('0' + ax / 100);
-      ax %= 100;
-    } else if (ax >= 100) {
-      out[pos++] = (char)('0' + ax / 100);
-      ax %= 100;
-    }
-    out[pos++] = (char)('0' + ax / 10);
-    out[pos++] = (char)('0' + ax % 10);
-  }
-  out[pos] = '\n';
+  if (estyle)
+    render_exponent(out, pos, x);
+  else
+    out[pos] = '\n';
 }
 
 // Classify an x87 extended value (mant with explicit integer bit, se = sign | exponent).

@@ -408,7 +408,7 @@ class Context:
                                              d_info_ptr, stream), "qb200_text_parse_device")
 
     def text_set_force_exact(self, on: bool):
-        _check(lib().qb200_text_set_force_exact(self.h, int(bool(on))), "qb200_text_set_force_exact")
+        _check(lib().qb200_text_set_force_exact(self.h, int(on)), "qb200_text_set_force_exact")
 
     @property
     def text_exact_count(self) -> int:

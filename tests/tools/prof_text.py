@@ -57,3 +57,28 @@ for _ in range(50):
     ctx.text_format(v1[:-1], v1[-1])
 t1 = time.time()
 print(f"host API, 65536 cells + total_error per call: {(t1 - t0) / 50 * 1e3:.3f} ms/call")
+# ---- importer: the text just written, back to values -------------------------------
+d_vals = torch.empty(2 * n, dtype=torch.int64, device="cuda")
+d_info = torch.zeros(8, dtype=torch.int64, device="cuda")
+for _ in range(2):
+    ctx.text_parse_device(d_text.data_ptr(), L, n, d_vals.data_ptr(), d_info.data_ptr(), ts.cuda_stream)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(steps):
+    ctx.text_parse_device(d_text.data_ptr(), L, n, d_vals.data_ptr(), d_info.data_ptr(), ts.cuda_stream)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+info = d_info.cpu().numpy()
+assert info[0] == n and info[1] == 0, info
+assert torch.equal(d_vals.view(torch.uint8).view(-1, 16)[:, :10], d_in.view(-1, 16)[:, :10]), "round trip differs"
+print(f"parse: ms/step {ms:.4f} values/s {n / ms * 1e3:.4e} algorithmic GB/s {(16 * n + L) / ms * 1e-6:.1f} "
+      f"(round trip bit-exact)")
+t0 = time.time(); ot.parse_ld(t[:len(want)], k); t1 = time.time()
+print(f"libc fscanf on this host: {k / (t1 - t0):.3e} values/s (1 core)")
+text1 = ctx.text_format(v1[:-1], v1[-1])
+t0 = time.time()
+for _ in range(50):
+    ctx.text_parse(text1, 65537)
+t1 = time.time()
+print(f"host API parse, 65537 numbers per call: {(t1 - t0) / 50 * 1e3:.3f} ms/call")
