@@ -38,7 +38,9 @@
 #include <gmp.h>
 
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <vector>
 
@@ -47,6 +49,37 @@
 namespace {
 
 qb200_context* g_ctx = NULL;
+
+// QB200_DROPIN_STATS=1: print, at exit, how many slices this process integrated and
+// the wall time spent inside the C ABI calls (to tell GPU time from protocol time).
+struct Stats {
+  double seconds;
+  unsigned long calls;
+  bool on;
+} g_stats = {0.0, 0, false};
+
+double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+void print_stats() {
+  if (g_stats.on && g_stats.calls)
+    fprintf(stderr, "qunundrum_b200 drop-in: %lu slice calls, %.3f s inside the drop-in functions (%.1f us per call)\n",
+            g_stats.calls, g_stats.seconds, 1e6 * g_stats.seconds / (double)g_stats.calls);
+}
+
+struct Timed {
+  double t0;
+  Timed() : t0(g_stats.on ? now_s() : 0.0) {}
+  ~Timed() {
+    if (g_stats.on) {
+      g_stats.seconds += now_s() - t0;
+      g_stats.calls++;
+    }
+  }
+};
 
 int env_int(const char* name, int fallback) {
   const char* v = getenv(name);
@@ -67,6 +100,11 @@ qb200_context* context() {
   }
   if (0 != qb200_create(device, &g_ctx)) {
     critical("qunundrum_b200: %s", qb200_last_error());
+  }
+  const char* st = getenv("QB200_DROPIN_STATS");
+  if (st && *st && *st != '0') {
+    g_stats.on = true;
+    atexit(print_stats);
   }
   return g_ctx;
 }
@@ -104,7 +142,9 @@ void compute_2d(Distribution_Slice* const slice, const Parameters* const paramet
   std::vector<double> cells((size_t)dimension * dimension);
   long double total_probability = 0, total_error = 0;
   uint32_t flags = 0;
-  if (0 != qb200_slice2d_compute(context(), &e.p, (int)method, richardson, dimension, 1,
+  qb200_context* const ctx = context();
+  Timed timed;
+  if (0 != qb200_slice2d_compute(ctx, &e.p, (int)method, richardson, dimension, 1,
                                  &min_log_alpha_d, &min_log_alpha_r, cells.data(),
                                  &total_probability, &total_error, &flags)) {
     critical("%s(): %s", who, qb200_last_error());
@@ -138,7 +178,9 @@ void compute_1d(long double* const norm_vector, const uint32_t dimension, const 
                 const char* who) {
   std::vector<double> cells(dimension);
   long double tp = 0;
-  if (0 != qb200_slice1d_compute(context(), &p, kind, richardson, dimension, 1, &min_log_alpha,
+  qb200_context* const ctx = context();
+  Timed timed;
+  if (0 != qb200_slice1d_compute(ctx, &p, kind, richardson, dimension, 1, &min_log_alpha,
                                  &eta, cells.data(), &tp, flags)) {
     critical("%s(): %s", who, qb200_last_error());
   }
