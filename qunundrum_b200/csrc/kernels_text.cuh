@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(TB)
   if (i < n) {
     const unsigned long long b = starts[i];
     int tlen = 0;
-    while (tlen < MAX_TOKEN && b + tlen < len && !is_space(__ldg(text + b + tlen))) tlen++;
-    uint32_t st = tlen >= MAX_TOKEN ? (uint32_t)PARSE_MALFORMED : parse_token(text + b, tlen, &dec);
+    uint32_t st = parse_number(text + b, (long)(len - b), &dec, &tlen);
+    if (tlen >= MAX_TOKEN) st = PARSE_MALFORMED;
     if (st == PARSE_OK) {
       if (dec.special) {
         mant = dec.special == 2 ? (1ULL << 63) : (3ULL << 62);

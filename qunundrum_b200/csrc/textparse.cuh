@@ -47,93 +47,132 @@ struct Decimal {
 QT_HD bool is_space(uint32_t c) { return c == ' ' || (c >= 9 && c <= 13); }
 QT_HD uint32_t lower(uint32_t c) { return (c >= 'A' && c <= 'Z') ? c + 32 : c; }
 
-// Parse the token s[0 .. len). Returns a ParseStatus.
+QT_HD uint32_t pow10_u32(int k) {  // 10^k, 0 <= k <= 9
+  uint32_t r = 1;
+#pragma unroll
+  for (int j = 0; j < 9; j++)
+    if (j < k) r *= 10u;
+  return r;
+}
+
+// D = D * mul + add on three limbs.
+QT_HD void muladd96(uint32_t (&d)[3], uint32_t mul, uint32_t add) {
+  uint32_t carry = add;
+#pragma unroll
+  for (int j = 0; j < 3; j++) d[j] = mulhi_lo(d[j], mul, carry, &carry);
+}
+
+// Parse ONE number starting at s[0]; it ends at the first white-space byte or after
+// `avail` bytes (the end of the text). Single pass. Digits are gathered nine at a time
+// in a 32-bit accumulator (one multiply-add per digit) and the groups are combined
+// into the 96-bit D at the end. Returns a ParseStatus; *used = length of the token.
 template <class Ptr>
-QT_HD uint32_t parse_token(Ptr s, int len, Decimal* out) {
-  int i = 0;
+QT_HD uint32_t parse_number(Ptr s, long avail, Decimal* out, int* used) {
+  long i = 0;
+  uint32_t c = avail > 0 ? (uint32_t)(unsigned char)s[0] : 32u;
+#define QT_NEXT() (c = (++i < avail) ? (uint32_t)(unsigned char)s[i] : 32u)
   out->neg = 0;
   out->sticky = 0;
   out->special = 0;
   out->k = 0;
   out->ndig = 0;
   out->d[0] = out->d[1] = out->d[2] = 0;
-  if (len <= 0) return PARSE_MALFORMED;
-  if (s[0] == '+' || s[0] == '-') {
-    out->neg = s[0] == '-';
-    i = 1;
+  if (c == '+' || c == '-') {
+    out->neg = c == '-';
+    QT_NEXT();
   }
-  if (i >= len) return PARSE_MALFORMED;
-  const uint32_t c0 = lower(s[i]);
-  if (c0 == 'i' || c0 == 'n') {
-    // inf, infinity, nan, nan(chars)
-    const int rest = len - i;
-    if (c0 == 'i') {
-      const char* w = "infinity";
-      if (rest != 3 && rest != 8) return PARSE_MALFORMED;
-      for (int j = 0; j < rest; j++)
-        if (lower(s[i + j]) != (uint32_t)w[j]) return PARSE_MALFORMED;
+  uint32_t status = PARSE_OK;
+  if (lower(c) == 'i' || lower(c) == 'n') {
+    // inf, infinity, nan, nan(chars): gather up to the white space
+    char w[12];
+    int m = 0;
+    char last = 0;
+    while (!is_space(c)) {
+      if (m < 12) w[m] = (char)lower(c);
+      last = (char)c;
+      m++;
+      QT_NEXT();
+    }
+    const char* inf = "infinity";
+    bool ok;
+    if (w[0] == 'i') {
+      ok = m == 3 || m == 8;
+      for (int j = 0; ok && j < m; j++) ok = w[j] == inf[j];
       out->special = 2;
-      return PARSE_OK;
-    }
-    if (rest < 3 || lower(s[i + 1]) != 'a' || lower(s[i + 2]) != 'n') return PARSE_MALFORMED;
-    if (rest > 3 && !(s[i + 3] == '(' && s[len - 1] == ')')) return PARSE_MALFORMED;
-    out->special = 3;
-    return PARSE_OK;
-  }
-  if (c0 == '0' && i + 1 < len && lower(s[i + 1]) == 'x') return PARSE_UNSUPPORTED;
-  uint32_t d0 = 0, d1 = 0, d2 = 0;
-  int nd = 0, any_digit = 0, frac_digits = 0, dropped = 0;
-  bool point = false;
-  for (; i < len; i++) {
-    const uint32_t c = s[i];
-    if (c == '.') {
-      if (point) return PARSE_MALFORMED;
-      point = true;
-      continue;
-    }
-    if (c < '0' || c > '9') break;
-    any_digit = 1;
-    const uint32_t v = c - '0';
-    if (nd == 0 && v == 0) {  // leading zero
-      if (point) frac_digits++;
-      continue;
-    }
-    if (nd < MAX_SIG_DIGITS) {
-      uint32_t carry = v;
-      d0 = mulhi_lo(d0, 10u, carry, &carry);
-      d1 = mulhi_lo(d1, 10u, carry, &carry);
-      d2 = mulhi_lo(d2, 10u, carry, &carry);
-      nd++;
-      if (point) frac_digits++;
     } else {
-      if (v) out->sticky = 1;
-      if (!point) dropped++;
+      ok = m >= 3 && w[1] == 'a' && w[2] == 'n' && (m == 3 || (w[3] == '(' && last == ')'));
+      out->special = 3;
     }
+    *used = (int)(i > 0x7fffffffL ? 0x7fffffffL : i);
+    return ok ? PARSE_OK : PARSE_MALFORMED;
   }
-  if (!any_digit) return PARSE_MALFORMED;
-  int ex = 0;
-  if (i < len) {
-    if (lower(s[i]) != 'e') return PARSE_MALFORMED;
-    i++;
-    bool eneg = false;
-    if (i < len && (s[i] == '+' || s[i] == '-')) {
-      eneg = s[i] == '-';
-      i++;
+  uint32_t qa = 0, qb = 0, qc = 0, cur = 0;  // full groups of nine digits (oldest first), current group
+  int cnt = 0, nsig = 0, adj = 0;
+  uint32_t sticky = 0;
+  bool point = false, any = false, hex = false;
+  if (c == '0' && i + 1 < avail && lower((uint32_t)(unsigned char)s[i + 1]) == 'x') hex = true;
+  for (;;) {
+    const uint32_t v = c - '0';
+    if (v <= 9u) {
+      any = true;
+      if (nsig < MAX_SIG_DIGITS) {
+        if ((nsig | (int)v) != 0) {  // significant (not a leading zero)
+          cur = cur * 10u + v;
+          nsig++;
+          if (++cnt == 9) {
+            qa = qb;
+            qb = qc;
+            qc = cur;
+            cur = 0;
+            cnt = 0;
+          }
+        }
+        if (point) adj--;
+      } else {
+        sticky |= v;
+        if (!point) adj++;
+      }
+    } else if (c == '.' && !point) {
+      point = true;
+    } else {
+      break;
     }
-    if (i >= len) return PARSE_MALFORMED;
-    for (; i < len; i++) {
-      const uint32_t c = s[i];
-      if (c < '0' || c > '9') return PARSE_MALFORMED;
+    QT_NEXT();
+  }
+  if (!any) status = PARSE_MALFORMED;
+  int ex = 0;
+  if (status == PARSE_OK && lower(c) == 'e') {
+    QT_NEXT();
+    bool eneg = false;
+    if (c == '+' || c == '-') {
+      eneg = c == '-';
+      QT_NEXT();
+    }
+    if (c - '0' > 9u) status = PARSE_MALFORMED;
+    while (c - '0' <= 9u) {
       if (ex < 100000) ex = ex * 10 + (int)(c - '0');
+      QT_NEXT();
     }
     if (eneg) ex = -ex;
   }
-  out->d[0] = d0;
-  out->d[1] = d1;
-  out->d[2] = d2;
-  out->ndig = nd;
-  out->k = ex - frac_digits + dropped;
-  return PARSE_OK;
+  if (!is_space(c)) {  // trailing garbage: skip to the end of the token
+    status = hex ? PARSE_UNSUPPORTED : PARSE_MALFORMED;
+    while (!is_space(c) && i < 0x7fffffffL) QT_NEXT();
+  }
+#undef QT_NEXT
+  *used = (int)(i > 0x7fffffffL ? 0x7fffffffL : i);
+  // D = ((qa * 10^9 + qb) * 10^9 + qc) * 10^cnt + cur
+  uint32_t d[3] = {qa, 0, 0};
+  muladd96(d, 1000000000u, qb);
+  muladd96(d, 1000000000u, qc);
+  muladd96(d, pow10_u32(cnt), cur);
+  out->d[0] = d[0];
+  out->d[1] = d[1];
+  out->d[2] = d[2];
+  out->ndig = nsig;
+  out->sticky = sticky ? 1u : 0u;
+  out->k = ex + adj;
+  return status;
 }
 
 // Round the 288-bit P (9 limbs, top bit 287 set) after dropping `drop` low bits

@@ -345,11 +345,11 @@ int hostsim_text_parse_ld(const char* textp, size_t len, size_t n, long double* 
   while (found < n) {
     while (pos < len && text::is_space(s[pos])) pos++;
     if (pos >= len) return -20;
-    size_t end = pos;
-    while (end < len && !text::is_space(s[end])) end++;
     text::Decimal dec;
-    if (end - pos >= 256) return -21;
-    const uint32_t st = text::parse_token(s + pos, (int)(end - pos), &dec);
+    int tlen = 0;
+    const uint32_t st = text::parse_number(s + pos, (long)(len - pos), &dec, &tlen);
+    const size_t end = pos + (size_t)tlen;
+    if (tlen >= 256) return -21;
     if (st != text::PARSE_OK) return st == text::PARSE_MALFORMED ? -21 : -22;
     uint64_t mant = 0;
     uint32_t se = 0;
