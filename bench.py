@@ -291,19 +291,32 @@ def text_section(ctx, qb, torch, stream, cells, hbm_peak):
     ms_host_p = (time.perf_counter() - t0) / 20 * 1e3
     bytes_f = 8 * n + length          # doubles in, text out
     bytes_p = length + 16 * n         # text in, x87 values out
+    try:                               # DRAM traffic per launch from the committed ncu capture
+        tl = json.load(open(os.path.join(ROOT, "profiles", "text_latest.json")))
+    except Exception:
+        tl = {}
     return {
         "values": n, "text_bytes": length, "bytes_per_value": length / n,
         "export": {"values_per_s": n / (ms_f * 1e-3), "ms": ms_f,
                    "roofline": {"bound": "hbm", "achieved": bytes_f / (ms_f * 1e-3) / 1e9,
                                 "peak": hbm_peak, "unit": "GB/s",
-                                "frac": bytes_f / (ms_f * 1e-3) / 1e9 / hbm_peak},
+                                "frac": bytes_f / (ms_f * 1e-3) / 1e9 / hbm_peak,
+                                "traffic": tl.get("format", {}).get("dram_bytes_per_launch"),
+                                "traffic_note": "ncu capture on 2^24 x87 values (16 B in): 715 MB "
+                                                "against 772 MB algorithmic",
+                                "limiter": "integer issue slots: ~830 thread instructions per value, "
+                                           "issue active 67 % (profiles/r01_text_format_ncu_full.txt)"},
                    "kernel": "k_text_format<F64>",
                    "host_call_ms_per_slice": ms_host_f,
                    "host_call_values_per_s": 65537 / (ms_host_f * 1e-3)},
         "import": {"values_per_s": n / (ms_p * 1e-3), "ms": ms_p,
                    "roofline": {"bound": "hbm", "achieved": bytes_p / (ms_p * 1e-3) / 1e9,
                                 "peak": hbm_peak, "unit": "GB/s",
-                                "frac": bytes_p / (ms_p * 1e-3) / 1e9 / hbm_peak},
+                                "frac": bytes_p / (ms_p * 1e-3) / 1e9 / hbm_peak,
+                                "traffic": (tl.get("tokenize", {}).get("dram_bytes_per_launch", 0) +
+                                            tl.get("parse", {}).get("dram_bytes_per_launch", 0)) or None,
+                                "limiter": "k_text_parse: integer issue slots (~1900 thread "
+                                           "instructions per value, issue active 91 %)"},
                    "kernels": "k_text_tokenize + k_text_parse",
                    "host_call_ms_per_slice": ms_host_p,
                    "host_call_values_per_s": 65537 / (ms_host_p * 1e-3)},

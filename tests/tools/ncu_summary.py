@@ -38,6 +38,11 @@ KEYS = {
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio": "stall_branch",
     "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio": "stall_no_inst",
     "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio": "stall_dispatch",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio": "stall_mio_throttle",
+    "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_warp_inst",
+    "launch__shared_mem_per_block_static": "smem_static",
+    "launch__block_size": "block",
 }
 UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9,
         "s": 1.0, "Ghz": 1e9, "Mhz": 1e6, "cycle": 1.0}
