@@ -216,6 +216,36 @@ def run_reference_arm(args, rank):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def bind_near_gpu(local_rank: int):
+    """Pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE any
+    pinned host buffer is allocated (first touch puts the pages on that node): with one
+    rank per GPU the end-to-end device-to-host streams then stay on their own socket.
+    Best effort; returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"numa: node {node} has no allowed cpu"
+        os.sched_setaffinity(0, allowed)
+        return f"numa: gpu {local_rank} ({bus}) -> node {node}, {len(allowed)} cpus"
+    except Exception as exc:  # pragma: no cover
+        return f"numa: not bound ({type(exc).__name__})"
+
+
 def profile_constants():
     """DRAM traffic and FP64-pipe share of the dominant kernel from the committed ncu
     capture (profiles/fused2d_latest.json), or None."""
@@ -337,12 +367,26 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the slice integrators have no CPU path")
+    numa = bind_near_gpu(local_rank) if world > 1 else "numa: single rank, not bound"
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: NCCL's banner (NCCL_DEBUG=VERSION on the GPU
+        # boxes) goes to stderr instead -- stdout is pointed at stderr while the communicator
+        # is created
         import torch.distributed as dist
-        dist.init_process_group("nccl", rank=rank, world_size=world,
-                                device_id=torch.device("cuda", local_rank))
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         torch.cuda.synchronize()
@@ -495,7 +539,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "ms_per_step": wall / e2e_steps * 1e3,
-                    "api": "qb200_slice2d_compute (synchronous C ABI, pinned host result buffer)"},
+                    "api": "qb200_slice2d_compute (synchronous C ABI, pinned host result buffer)",
+                    "host_placement": numa},
             "gpu_launches": int(launches),
             "e2e_gpu_launches": int(e2e_launches),
             "clocks": clocks,
