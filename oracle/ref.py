@@ -158,6 +158,19 @@ def distribution_slice_compute(params: RefParameters, dimension: int,
     return RefSlice(cells, tp[0], te[0], fl.value)
 
 
+def distribution_slice_copy_scale(cells, src_dimension: int, flags: int, dst_dimension: int):
+    """distribution_slice_copy_scale (src/distribution_slice.cpp:229-264): (cells, flags)."""
+    L = lib()
+    L.qref_distribution_slice_copy_scale.restype = C.c_uint32
+    L.qref_distribution_slice_copy_scale.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32,
+                                                     C.c_uint32, C.c_void_p]
+    src = np.ascontiguousarray(cells, dtype=np.longdouble)
+    dst = np.zeros(dst_dimension * dst_dimension, dtype=np.longdouble)
+    fl = L.qref_distribution_slice_copy_scale(src_dimension, src.ctypes.data, flags, dst_dimension,
+                                              dst.ctypes.data)
+    return dst, int(fl)
+
+
 def linear_distribution_slice_compute(params: RefParameters, dimension: int,
                                       min_log_alpha: int, target: int,
                                       richardson: bool = True) -> RefSlice:

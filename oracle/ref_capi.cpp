@@ -258,6 +258,24 @@ void qref_diagonal_distribution_slice_compute(void *dparams, int richardson,
   diagonal_distribution_slice_clear(&slice);
 }
 
+/* distribution_slice_copy_scale (src/distribution_slice.cpp:229-264): what a client does to
+ * a slice above MAX_SLICE_DIMENSION before sending it. Returns the scaled flags. */
+uint32_t qref_distribution_slice_copy_scale(uint32_t src_dimension, const long double *src_cells,
+                                            uint32_t src_flags, uint32_t dst_dimension,
+                                            long double *dst_cells) {
+  Distribution_Slice src, dst;
+  distribution_slice_init(&src, src_dimension);
+  distribution_slice_init(&dst, dst_dimension);
+  memcpy(src.norm_matrix, src_cells, sizeof(long double) * (size_t)src_dimension * src_dimension);
+  src.flags = src_flags;
+  distribution_slice_copy_scale(&dst, &src);
+  memcpy(dst_cells, dst.norm_matrix, sizeof(long double) * (size_t)dst_dimension * dst_dimension);
+  const uint32_t flags = dst.flags;
+  distribution_slice_clear(&src);
+  distribution_slice_clear(&dst);
+  return flags;
+}
+
 /* ---- Slice text export / import (memory streams) ---------------------------- */
 
 /* kind: 0 two-dimensional (c0 = min_log_alpha_d, c1 = min_log_alpha_r),
