@@ -58,6 +58,8 @@ CASES = [
     ("generate_linear_distribution", ["-r", "-dim", "512", "-det", "128", "2"], "linear", 3),
     ("generate_diagonal_distribution", ["-dim", "512", "-det", "-eta-bound", "1", "128", "5", "2"], "diagonal", 3),
     ("generate_distribution", ["-det", "-dim", "16", "128", "2"], "2d", 3),
+    # BASELINE config 3 shape: Ekera-Hastad factoring, m = n / 2 - 1, l = m - 20, always target d
+    ("generate_linear_distribution_rsa", ["-dim", "256", "-max", "256"], "linear", 2),
 ]
 
 
@@ -85,3 +87,26 @@ def test_generator_with_dropin_matches_reference_generator(exe, args, kind, rank
     finally:
         shutil.rmtree(ta, ignore_errors=True)
         shutil.rmtree(tb, ignore_errors=True)
+
+
+FULL = [
+    # BASELINE config 4 shape: two-dimensional, m = 3072, s = 4 (l = 768, sigma = 391), Richardson
+    ["--m", "3072", "--s", "4", "--dim", "64", "--sample", "16", "--clients", "2"],
+    # config 1 / 2 shape at a size the reference finishes quickly, dimension heuristic (upgrades)
+    ["--m", "256", "--s", "2", "--dim", "0", "--sample", "12", "--clients", "2"],
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", FULL, ids=["m3072-s4-dim64", "m256-s2-heuristic"])
+def test_full_distribution_sampled_against_reference(args):
+    """A complete two-dimensional distribution from the reference's generator with both drop-ins;
+    a random sample of its slices is re-derived with the reference itself (oracle/_ref) on the
+    host cores, following the client's dimension heuristic where no -dim is given."""
+    from oracle import ref
+    if not _have() or not ref.available():
+        pytest.skip("integration/_build or oracle/_ref missing")
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "full_distribution.py"), *args],
+                       capture_output=True, text=True, timeout=3000)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
