@@ -533,6 +533,12 @@ def run_ours(args, rank, world, local_rank):
                 "hbm": {"algorithmic_gbs": out_gbs, "peak_gbs": hbm_peak, "frac": out_gbs / hbm_peak,
                         "peak_source": hbm_src},
                 "note": "per GPU; step time includes the three small table/summary kernels (<1.5%)",
+                "frac_note": ("frac uses the contract's canonical 1600 FP64 flop per cell (SURVEY.md "
+                              "section 8(d): 20.09 integrand evaluations x 80 flop). The kernel does "
+                              "the same integration with ~500 flop per cell -- sin(pi u) by angle "
+                              "addition from per-row / per-column tables instead of one sine per point, "
+                              "19 instead of 20.09 evaluations -- so frac exceeds 1; executed_frac is "
+                              "the measured FP64-pipe utilisation (ncu), the kernel-quality number"),
             },
             "cpu_baseline": cpu,
             "text": text,

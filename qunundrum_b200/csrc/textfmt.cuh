@@ -395,10 +395,16 @@ QT_HD void piece_render(const Piece& p, Ptr out) {
     }
   }
   const bool has_point = nd > point;
-  const int pos1 = pos + (has_point ? 1 : 0);
+  // digits before the point at pos + j, after it at pos + 1 + j: two predicated stores
+  // with compile-time offsets per digit
+  const int before = nd < point ? nd : point;
+  const unsigned after = has_point ? (unsigned)(nd - point) : 0u;
 #pragma unroll
-  for (int j = 0; j < 24; j++)
-    if (j < nd) out[(j >= point ? pos1 : pos) + j] = piece_digit(p, j);
+  for (int j = 0; j < 24; j++) {
+    const char c = piece_digit(p, j);
+    if (j < before) out[pos + j] = c;
+    if ((unsigned)(j - point) < after) out[pos + 1 + j] = c;
+  }
   if (has_point) out[pos + point] = '.';
   pos += nd + (has_point ? 1 : 0);
   if (estyle)
