@@ -258,6 +258,7 @@ def profile_constants():
 
 def text_section(ctx, qb, torch, stream, cells, hbm_peak):
     """Exporter / importer kernels on the step's own cells (rank 0, N = 1)."""
+    import ctypes as C
     from oracle import text as ot          # checker + libc baseline only
     n = min(1 << 24, cells.numel())
     cap = 33 * n
@@ -319,6 +320,34 @@ def text_section(ctx, qb, torch, stream, cells, hbm_peak):
     for _ in range(20):
         ctx.text_parse(text1, 65537)
     ms_host_p = (time.perf_counter() - t0) / 20 * 1e3
+    # ... and on the whole sample in one call (pinned host input, text left in the context's
+    # pinned buffer; values pageable on the way back): transfer bound
+    hp = qb.lib().qb200_host_alloc(8 * n)
+    big = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_double)), shape=(n,))
+    big[:] = cells[:n].cpu().numpy()
+    ctx.text_format_view(big)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        addr, blen = ctx.text_format_view(big)
+    ms_big_f = (time.perf_counter() - t0) / 3 * 1e3
+    L = qb.lib()
+    ht = L.qb200_host_alloc(blen)
+    hv = L.qb200_host_alloc(16 * n)
+    C.memmove(ht, addr, blen)
+    used = C.c_size_t()
+
+    def parse_big():
+        rc = L.qb200_text_parse_ld(ctx.h, C.cast(ht, C.c_char_p), blen, n, hv, C.byref(used))
+        if rc != 0 or used.value != blen:
+            raise SystemExit(f"bench.py: qb200_text_parse_ld rc={rc} used={used.value}/{blen}")
+
+    parse_big()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        parse_big()
+    ms_big_p = (time.perf_counter() - t0) / 3 * 1e3
+    for ptr in (hp, ht, hv):
+        L.qb200_host_free(C.c_void_p(ptr))
     bytes_f = 8 * n + length          # doubles in, text out
     bytes_p = length + 16 * n         # text in, x87 values out
     try:                               # DRAM traffic per launch from the committed ncu capture
@@ -338,7 +367,10 @@ def text_section(ctx, qb, torch, stream, cells, hbm_peak):
                                            "issue active 67 % (profiles/r01_text_format_ncu_full.txt)"},
                    "kernel": "k_text_format<F64>",
                    "host_call_ms_per_slice": ms_host_f,
-                   "host_call_values_per_s": 65537 / (ms_host_f * 1e-3)},
+                   "host_call_values_per_s": 65537 / (ms_host_f * 1e-3),
+                   "e2e": {"value": n / (ms_big_f * 1e-3), "unit": "values/s",
+                           "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": length,
+                           "api": "qb200_text_format_f64, one call, pinned host buffers"}},
         "import": {"values_per_s": n / (ms_p * 1e-3), "ms": ms_p,
                    "roofline": {"bound": "hbm", "achieved": bytes_p / (ms_p * 1e-3) / 1e9,
                                 "peak": hbm_peak, "unit": "GB/s",
@@ -349,7 +381,10 @@ def text_section(ctx, qb, torch, stream, cells, hbm_peak):
                                            "instructions per value, issue active 91 %)"},
                    "kernels": "k_text_tokenize + k_text_parse",
                    "host_call_ms_per_slice": ms_host_p,
-                   "host_call_values_per_s": 65537 / (ms_host_p * 1e-3)},
+                   "host_call_values_per_s": 65537 / (ms_host_p * 1e-3),
+                   "e2e": {"value": n / (ms_big_p * 1e-3), "unit": "values/s",
+                           "h2d_bytes_per_step": length, "d2h_bytes_per_step": 16 * n,
+                           "api": "qb200_text_parse_ld, one call, pinned host buffers"}},
         "cpu_baseline": {"kind": "reference", "cores": 1,
                          "export_values_per_s": k / t_fmt, "import_values_per_s": k / t_par,
                          "sample": f"{k} cells of the step through libc fprintf(\"%.24Lg\\n\") / "

@@ -23,7 +23,10 @@ namespace qb200 {
 namespace text {
 
 constexpr int TB = 256;                            // worker threads per block
-constexpr int SUB = 4;                             // values per worker thread (sub-tiles per tile)
+#ifndef QB_TEXT_SUB
+#define QB_TEXT_SUB 4
+#endif
+constexpr int SUB = QB_TEXT_SUB;                             // values per worker thread (sub-tiles per tile)
 constexpr int TILE = TB * SUB;                     // values per tile
 constexpr int STAGE_BYTES = TILE * MAX_TEXT + 32;  // tile text staged in shared memory
 

@@ -303,8 +303,35 @@ QT_HD uint32_t decimal_to_x87(const Decimal& dec, const Pow10Entry* __restrict__
   if (e < 1) drop = 224 + (1 - e);  // denormal: fewer mantissa bits
   const bool exact = (dec.k >= 0 && dec.k <= K_EXACT_MAX) && !dec.sticky;
   uint32_t carry = 0;
-  uint64_t M = round288(P, drop, &carry);
+  uint64_t M;
   uint32_t status = 0;
+  if (drop == 224 && !dec.sticky && !force_band) {
+    // The common case (a normal number, no dropped digits) without the generic bit loops:
+    // 64 kept bits, the rounding bit is the top bit of P[6].
+    const uint64_t kept = ((uint64_t)P[8] << 32) | P[7];
+    const uint32_t half = P[6] >> 31;
+    uint32_t rest = P[6] & 0x7fffffffu;
+#pragma unroll
+    for (int i = 0; i < 6; i++) rest |= P[i];
+    bool up;
+    if (exact) {
+      up = half && (rest || (kept & 1ULL));
+    } else {
+      // true remainder in (r, r + 2^98), strictly above r: undecided iff r in [half - 2^98, half);
+      // r >= half rounds up (r == half is not a tie: the true value lies above it)
+      const bool below = P[6] == 0x7fffffffu && P[5] == 0xffffffffu && P[4] == 0xffffffffu &&
+                         (P[3] >> 2) == 0x3fffffffu;
+      if (below) {
+        *mant = kept;
+        *q_out = pe + 224;
+        return 1;
+      }
+      up = half != 0;
+    }
+    M = kept + (up ? 1ULL : 0ULL);
+    if (up && M == 0) carry = 1;
+  } else {
+  M = round288(P, drop, &carry);
   if (!exact || force_band) {
     // upper end of the interval the true product lies in
     uint32_t Q[9];
@@ -348,6 +375,7 @@ QT_HD uint32_t decimal_to_x87(const Decimal& dec, const Pow10Entry* __restrict__
       status = 1;
       return status;
     }
+  }
   }
   // assemble
   int ee = e < 1 ? 0 : e;

@@ -387,6 +387,21 @@ class Context:
                   C.byref(text), C.byref(n)), "qb200_text_format")
         return C.string_at(text, n.value) if n.value else b""
 
+    def text_format_view(self, values, tail=None):
+        """As text_format, without copying the text out of the context's pinned buffer:
+        (address, length), valid until the next text call on this context."""
+        v = np.ascontiguousarray(values)
+        if v.dtype == np.float64:
+            fn, dt = lib().qb200_text_format_f64, np.float64
+        else:
+            v = np.ascontiguousarray(v, dtype=np.longdouble)
+            fn, dt = lib().qb200_text_format_ld, np.longdouble
+        t = None if tail is None else np.array([tail], dtype=dt)
+        text, n = C.c_void_p(), C.c_size_t()
+        _check(fn(self.h, v.ctypes.data, v.size, t.ctypes.data if t is not None else None,
+                  C.byref(text), C.byref(n)), "qb200_text_format")
+        return text.value, n.value
+
     def text_format_device(self, kind: int, d_values_ptr: int, n: int, d_text_ptr: int,
                            cap: int, d_len_ptr: int, stream: int = 0):
         """Enqueue one formatting launch on device-resident values."""
