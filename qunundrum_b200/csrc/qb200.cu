@@ -483,12 +483,14 @@ int enqueue_fused_epilogue(qb200_plan* plan, cudaStream_t st, double* d_summary)
   return 0;
 }
 
-int finish_common(qb200_plan* pl, unsigned n_chunks = 1) {
+// same_stream: the caller runs the plan on the context's own stream right away (the
+// synchronous host API), so stream order already makes the uploads visible.
+int finish_common(qb200_plan* pl, unsigned n_chunks = 1, bool same_stream = false) {
   if (int rc = upload_plan(pl)) return rc;
   if (int rc = setup_fused(pl, n_chunks)) return rc;
   // uploads above are asynchronous on the context stream from pageable vectors owned by
   // the plan (or already consumed): make them visible to any stream the caller runs on
-  QB_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+  if (!same_stream) QB_CUDA(cudaStreamSynchronize(pl->ctx->stream));
   pl->algo = pl->fused_ok ? 2 : 1;
   return 0;
 }
@@ -561,14 +563,15 @@ void qb200_host_free(void* p) {
 
 static int create_plan2d(qb200_context* ctx, const qb200_params* params, int method,
                          int richardson, uint32_t dimension, uint32_t n, const int32_t* a_d,
-                         const int32_t* a_r, unsigned n_chunks, qb200_plan** out) {
+                         const int32_t* a_r, unsigned n_chunks, qb200_plan** out,
+                         bool same_stream = false) {
   std::unique_ptr<qb200_plan> pl(new qb200_plan);
   pl->ctx = ctx;
   pl->bind_pool(&ctx->pool);
   std::string err;
   if (int rc = plan_2d(view_of(params), method, richardson, dimension, n, a_d, a_r, &pl->host, &err))
     return fail(rc, err);
-  if (int rc = finish_common(pl.get(), n_chunks)) return rc;
+  if (int rc = finish_common(pl.get(), n_chunks, same_stream)) return rc;
   *out = pl.release();
   return 0;
 }
@@ -693,7 +696,7 @@ static int run_sync(qb200_context* ctx, qb200_plan* pl, double* cells, long doub
   }
   double* d_cells = ctx->out_cells.as<double>();
   double* d_summary = ctx->out_summary.as<double>();
-  if (pl->host.kind < 0 && pl->algo == 2 && pl->n > 0) {
+  if (pl->host.kind < 0 && pl->algo == 2 && pl->n > 0 && pl->fused.chunks.size() > 1) {
     // Pipelined: the copy of chunk c runs on the copy stream while chunk c + 1 computes.
     const size_t nch = pl->fused.chunks.size();
     while (ctx->events.size() < nch) {
@@ -739,7 +742,8 @@ int qb200_slice2d_compute(qb200_context* ctx, const qb200_params* params, int me
   // chunks of ~32 MB of results so that copies overlap compute
   const uint64_t bytes = (uint64_t)n * dimension * dimension * sizeof(double);
   const unsigned n_chunks = (unsigned)std::min<uint64_t>(16, std::max<uint64_t>(1, bytes >> 25));
-  if (int rc = create_plan2d(ctx, params, method, richardson, dimension, n, a_d, a_r, n_chunks, &pl))
+  if (int rc = create_plan2d(ctx, params, method, richardson, dimension, n, a_d, a_r, n_chunks, &pl,
+                             /*same_stream=*/true))
     return rc;
   const int rc = run_sync(ctx, pl, cells, tp, te, flags);
   qb200_plan_destroy(pl);

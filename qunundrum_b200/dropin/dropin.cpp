@@ -139,7 +139,8 @@ void compute_2d(Distribution_Slice* const slice, const Parameters* const paramet
   const uint32_t dimension = slice->dimension;
   Exported e;
   fill(e, parameters->m, parameters->l, 0, parameters->d, parameters->r);
-  std::vector<double> cells((size_t)dimension * dimension);
+  static std::vector<double> cells;  // reused across calls (one integrating thread per rank)
+  if (cells.size() < (size_t)dimension * dimension) cells.resize((size_t)dimension * dimension);
   long double total_probability = 0, total_error = 0;
   uint32_t flags = 0;
   qb200_context* const ctx = context();
