@@ -34,6 +34,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <mutex>
 #include <vector>
@@ -45,8 +46,34 @@ namespace {
 qb200_context* g_text_ctx = NULL;
 std::mutex g_text_mutex;  // the server exports from worker threads (main_server_export_distribution)
 
+// QB200_DROPIN_STATS=1: at exit, the time spent in the C ABI calls and in fwrite / fread.
+struct TextStats {
+  double abi_s, io_s;
+  unsigned long exports, imports;
+  bool on;
+} g_tstats = {0.0, 0.0, 0, 0, false};
+
+double tnow() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+void print_text_stats() {
+  if (g_tstats.on && (g_tstats.exports || g_tstats.imports))
+    fprintf(stderr,
+            "qunundrum_b200 text drop-in: %lu slice exports, %lu slice imports, %.3f s inside the C ABI, "
+            "%.3f s in fwrite / fread\n",
+            g_tstats.exports, g_tstats.imports, g_tstats.abi_s, g_tstats.io_s);
+}
+
 qb200_context* text_context() {
   if (g_text_ctx) return g_text_ctx;
+  const char* st = getenv("QB200_DROPIN_STATS");
+  if (st && *st && *st != '0') {
+    g_tstats.on = true;
+    atexit(print_text_stats);
+  }
   const int n = qb200_device_count();
   if (n <= 0) critical("qunundrum_b200: no CUDA device (there is no CPU path).");
   const char* v = getenv("QB200_TEXT_DEVICE");
@@ -63,11 +90,19 @@ void export_values(FILE* const file, const long double* const values, const size
   std::lock_guard<std::mutex> lock(g_text_mutex);
   const char* text = NULL;
   size_t len = 0;
-  if (0 != qb200_text_format_ld(text_context(), values, n, &total_error, &text, &len)) {
+  qb200_context* const ctx = text_context();
+  const double t0 = g_tstats.on ? tnow() : 0.0;
+  if (0 != qb200_text_format_ld(ctx, values, n, &total_error, &text, &len)) {
     critical("%s(): %s", who, qb200_last_error());
   }
+  const double t1 = g_tstats.on ? tnow() : 0.0;
   if (len != fwrite(text, 1, len, file)) {
     critical("%s(): Failed to write to the file.", who);
+  }
+  if (g_tstats.on) {
+    g_tstats.abi_s += t1 - t0;
+    g_tstats.io_s += tnow() - t1;
+    g_tstats.exports++;
   }
 }
 
@@ -82,10 +117,17 @@ void import_values(FILE* const file, long double* const values, const size_t n,
   std::vector<char> buf;
   std::vector<long double> parsed(n + 1);
   size_t want = 40 * (n + 1) + 64, used = 0;
+  qb200_context* const ctx = text_context();
   for (;;) {
     buf.resize(want);
+    const double t0 = g_tstats.on ? tnow() : 0.0;
     const size_t got = fread(buf.data(), 1, want, file);
-    const int rc = qb200_text_parse_ld(text_context(), buf.data(), got, n + 1, parsed.data(), &used);
+    const double t1 = g_tstats.on ? tnow() : 0.0;
+    const int rc = qb200_text_parse_ld(ctx, buf.data(), got, n + 1, parsed.data(), &used);
+    if (g_tstats.on) {
+      g_tstats.io_s += t1 - t0;
+      g_tstats.abi_s += tnow() - t1;
+    }
     if (0 == rc) break;
     if (-20 == rc && got == want) {  // the block ended before the last number: read more
       if (0 != fseek(file, pos, SEEK_SET)) critical("%s(): The file is not seekable.", who);
@@ -101,6 +143,7 @@ void import_values(FILE* const file, long double* const values, const size_t n,
     *total_probability += values[i];
   }
   *total_error = parsed[n];
+  if (g_tstats.on) g_tstats.imports++;
 }
 
 uint32_t import_dimension(FILE* const file, const char* who) {
