@@ -8,17 +8,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 B = os.path.join(ROOT, "integration", "_build")
 clients = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 run_ref = "--no-ref" not in sys.argv
+pin = "--pin" in sys.argv        # one visible GPU per rank (integration/pin_gpu.sh)
 rnd = random.Random(20482048); m = 2048
 r = 2 ** (m - 1) + 1 + rnd.randrange(2 ** (m - 1) - 1); d = r // 2 + rnd.randrange(r // 2)
 t = tempfile.mkdtemp(); os.makedirs(t + "/distributions")
-cmd = [B + "/minimpirun", "-np", str(clients + 1), B + "/gpu/generate_distribution", "-exp", str(d), str(r),
-       "-dim", "256", "2048", "1"]
-rep = {"clients": clients}
+cmd = [B + "/minimpirun", "-np", str(clients + 1),
+       *([os.path.join(ROOT, "integration", "pin_gpu.sh")] if pin else []),
+       B + "/gpu/generate_distribution", "-exp", str(d), str(r), "-dim", "256", "2048", "1"]
+rep = {"clients": clients, "one_visible_gpu_per_rank": pin}
 t0 = time.time()
 p = subprocess.Popen(["stdbuf", "-oL"] + cmd, cwd=t, stdout=subprocess.PIPE, text=True)
 marks = {}
 for line in p.stdout:
-    for key in ("Processing slice: 1 /", "Stopping node", "Sorting the slices", "Exporting distribution information",
+    for key in ("Processing slice: 1 /", "Processing slice: 100 /", "Stopping node", "Sorting the slices", "Exporting distribution information",
                 "Exporting the distribution to", "Finished exporting"):
         if key in line and key not in marks:
             marks[key] = round(time.time() - t0, 2)
