@@ -28,7 +28,9 @@
  *  - every function returns 0 on success and a negative code on failure, with
  *    qb200_last_error() giving the message; the reference convention (errors
  *    are fatal, critical() -> exit, src/errors.c) is applied by the binding;
- *  - there is no CPU path: without a CUDA device qb200_create() fails.
+ *  - there is no CPU path: without a CUDA device qb200_create() fails;
+ *  - a context is not thread-safe: use it from one thread at a time (one context
+ *    per MPI rank / per exporting thread, or a lock as in dropin_text.cpp).
  */
 #ifndef QUNUNDRUM_B200_H
 #define QUNUNDRUM_B200_H
@@ -195,9 +197,10 @@ int qb200_text_format_device(qb200_context *ctx, int kind, const void *d_values,
  * returns), including inf / nan, denormals, overflow and underflow. *consumed
  * (may be NULL) receives the offset of the byte after the n-th number and the
  * white space that follows it, i.e. where the reference's FILE position would be.
- * Errors: -20 fewer than n numbers, -21 a malformed number, -22 an unsupported
- * form (hexadecimal floats; more than 28 significant digits exactly on a rounding
- * boundary). text needs no terminating NUL. */
+ * Errors: -20 fewer than n numbers, -21 a malformed number (or one longer than 255
+ * characters), -22 an unsupported form (hexadecimal floats; more than 28
+ * significant digits exactly on a rounding boundary). text needs no terminating
+ * NUL. */
 int qb200_text_parse_ld(qb200_context *ctx, const char *text, size_t len, size_t n,
                         long double *values, size_t *consumed);
 

@@ -139,14 +139,21 @@ void compute_2d(Distribution_Slice* const slice, const Parameters* const paramet
   const uint32_t dimension = slice->dimension;
   Exported e;
   fill(e, parameters->m, parameters->l, 0, parameters->d, parameters->r);
-  static std::vector<double> cells;  // reused across calls (one integrating thread per rank)
-  if (cells.size() < (size_t)dimension * dimension) cells.resize((size_t)dimension * dimension);
+  // pinned result buffer, reused across calls (one integrating thread per rank)
+  static double* cells = NULL;
+  static size_t cells_cap = 0;
+  if (cells_cap < (size_t)dimension * dimension) {
+    qb200_host_free(cells);
+    cells_cap = (size_t)dimension * dimension;
+    cells = (double*)qb200_host_alloc(cells_cap * sizeof(double));
+    if (NULL == cells) critical("%s(): Failed to allocate memory.", who);
+  }
   long double total_probability = 0, total_error = 0;
   uint32_t flags = 0;
   qb200_context* const ctx = context();
   Timed timed;
   if (0 != qb200_slice2d_compute(ctx, &e.p, (int)method, richardson, dimension, 1,
-                                 &min_log_alpha_d, &min_log_alpha_r, cells.data(),
+                                 &min_log_alpha_d, &min_log_alpha_r, cells,
                                  &total_probability, &total_error, &flags)) {
     critical("%s(): %s", who, qb200_last_error());
   }
