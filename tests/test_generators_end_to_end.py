@@ -58,6 +58,9 @@ CASES = [
     ("generate_linear_distribution", ["-r", "-dim", "512", "-det", "128", "2"], "linear", 3),
     ("generate_diagonal_distribution", ["-dim", "512", "-det", "-eta-bound", "1", "128", "5", "2"], "diagonal", 3),
     ("generate_distribution", ["-det", "-dim", "16", "128", "2"], "2d", 3),
+    # the other two slice methods of the two-dimensional generator (src/distribution_slice.h:31-78)
+    ("generate_distribution", ["-det", "-approx-quick", "-dim", "16", "128", "2"], "2d", 3),
+    ("generate_distribution", ["-det", "-sigma-optimal", "-dim", "16", "64", "2"], "2d", 3),
     # BASELINE config 3 shape: Ekera-Hastad factoring, m = n / 2 - 1, l = m - 20, always target d
     ("generate_linear_distribution_rsa", ["-dim", "256", "-max", "256"], "linear", 2),
 ]
