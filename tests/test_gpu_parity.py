@@ -234,3 +234,46 @@ def test_empty_and_ragged_batches(gpu_ctx):
     assert c1.shape == (1, 49) and abs(float(tp1[0]) - c1.sum()) < 1e-16
     c2, tp2, f2 = gpu_ctx.slice1d_batch(P, 1, True, 1, [2048])
     assert c2.shape == (1, 1) and float(tp2[0]) == c2[0, 0]
+
+
+@pytest.mark.gpu
+def test_reference_unit_tests_linear_and_diagonal_totals(gpu_ctx):
+    """The reference's own slice-level unit tests, through the CUDA path and the reference-named
+    entry points: test_linear_distribution() (src/test/test_linear_distribution.cpp: m = 128,
+    s = 1, deterministic d and r, dimension 2048, 16 offsets x 2 signs x 2 targets) and
+    test_diagonal_distribution() (src/test/test_diagonal_distribution.cpp: sigma = 5, 9 offsets x
+    7 eta x 2 signs) against the Mathematica totals they quote, with their tolerance
+    (test_cmp_ld, src/test/test_common.cpp:75-93)."""
+    import json
+    import os
+    import qunundrum_b200 as qb
+    from oracle import restate as rs
+    from tests.conftest import GOLDEN
+    totals = json.load(open(os.path.join(GOLDEN, "mathematica_totals.json")))
+
+    def close(a, b, tol):
+        a, b = float(a), float(b)
+        return a > 0 and b > 0 and abs(a - b) / min(a, b) <= tol
+
+    m = 128
+    d, r = rs.deterministic_d_r(m)
+    P = qb.Parameters(m, 1, d, r)
+    for target in (qb.LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_D, qb.LINEAR_DISTRIBUTION_SLICE_COMPUTE_TARGET_R):
+        vals = totals["linear"][target]["values"]
+        for i, off in enumerate(range(-5, 11)):
+            for sign in (1, -1):
+                s = qb.Linear_Distribution_Slice(2048)
+                qb.linear_distribution_slice_compute_richardson(s, P, target, sign * (m + off), ctx=gpu_ctx)
+                tol = 1e-4 if (target == 1 and off >= 10) else 1e-6
+                assert close(s.total_probability, vals[i], tol), (target, off, sign)
+                assert s.flags & qb.SLICE_FLAGS_METHOD_RICHARDSON and s.min_log_alpha == sign * (m + off)
+    DP = qb.Diagonal_Parameters(m, 5, 1, d, r, eta_bound=25)
+    pos, neg = totals["diagonal"][0]["values"], totals["diagonal"][1]["values"]
+    offsets, etas = list(range(-5, 4)), [0, 1, -1, 2, -2, 25, -25]
+    for i in range(63):
+        off, eta = offsets[i % 9], etas[i // 9]
+        for sign, want in ((1, pos[i]), (-1, neg[i])):
+            s = qb.Diagonal_Distribution_Slice(2048)
+            qb.diagonal_distribution_slice_compute_richardson(s, DP, sign * (m + off), eta, ctx=gpu_ctx)
+            assert close(s.total_probability, want, 1e-6), (off, eta, sign)
+            assert s.eta == eta
