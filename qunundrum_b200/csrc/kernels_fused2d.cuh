@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fuse
     fused_march<MODE, CLS, true, false, HAS_ERR, HAS_M2, HAS_BOUND>(
         k, r0, r1, r2, r3, rc, D0, D1, DC, fd, s_cols, s_halo, outp, D, I, lane, gwc, gwf, tp, err1,
         err2, ok);
-  else if (same)
+  else if (CLS == 0 && same)  // (measured: not worth a second instantiation for classes 1 / 2)
     fused_march<MODE, CLS, false, true, HAS_ERR, HAS_M2, HAS_BOUND>(
         k, r0, r1, r2, r3, rc, D0, D1, DC, fd, s_cols, s_halo, outp, D, I, lane, gwc, gwf, tp, err1,
         err2, ok);
