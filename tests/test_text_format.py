@@ -410,3 +410,20 @@ def test_gpu_slice_importers_match_the_reference(gpu_ctx):
             kind = {"2d": 0, "linear": 1, "diagonal": 2}[name]
             head, rcells, rtp, rte = ot.ref_slice_import(kind, gold, cells.size)
             assert same_bits(rcells, cells) and same_bits(np.array([rtp]), np.array([s.total_probability]))
+
+
+@pytest.mark.gpu
+def test_gpu_slice_importer_reads_more_when_the_block_is_short(gpu_ctx):
+    """Numbers separated by a lot of white space: the importer's first block (40 bytes per
+    number) ends before the last number and it has to read on -- same result, same position."""
+    from qunundrum_b200 import host
+    rng = np.random.default_rng(3)
+    vals = rand_ld(rng, 64 * 64 + 1, 16383 - 200, 16383)
+    lines = ot.format_ld24(vals).split(b"\n")[:-1]
+    body = b"".join(b" " * 70 + ln + b"\n" for ln in lines)
+    f = io.BytesIO(b"64\n2040\n-2041\n000a0000\n" + body + b"777\n")
+    s = host.distribution_slice_import(f, gpu_ctx)
+    assert s.dimension == 64 and s.min_log_alpha_d == 2040 and s.min_log_alpha_r == -2041
+    assert s.flags == 0xA0000
+    assert same_bits(s.norm_matrix, vals[:-1]) and same_bits(np.array([s.total_error]), vals[-1:])
+    assert f.read() == b"777\n"
