@@ -200,7 +200,10 @@ int qb200_text_format_device(qb200_context *ctx, int kind, const void *d_values,
  * Errors: -20 fewer than n numbers, -21 a malformed number (or one longer than 255
  * characters), -22 an unsupported form (hexadecimal floats; more than 28
  * significant digits exactly on a rounding boundary). text needs no terminating
- * NUL. */
+ * NUL. text[0, len) is taken to be complete: a number that ends exactly at
+ * text + len is converted as it stands, so a caller that passes a block of a
+ * larger file must make sure that something follows the last number it needs
+ * (*consumed < len) or that the block reaches the end of the file. */
 int qb200_text_parse_ld(qb200_context *ctx, const char *text, size_t len, size_t n,
                         long double *values, size_t *consumed);
 

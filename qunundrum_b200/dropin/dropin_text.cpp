@@ -128,8 +128,11 @@ void import_values(FILE* const file, long double* const values, const size_t n,
       g_tstats.io_s += t1 - t0;
       g_tstats.abi_s += tnow() - t1;
     }
-    if (0 == rc) break;
-    if (-20 == rc && got == want) {  // the block ended before the last number: read more
+    // A block that is not the rest of the file may end inside the last number: the result
+    // only counts if something follows that number in the block (used < got) or the block
+    // reached the end of the file (got < want).
+    if (0 == rc && (used < got || got < want)) break;
+    if ((0 == rc || -20 == rc) && got == want) {  // the block was too short: read more
       if (0 != fseek(file, pos, SEEK_SET)) critical("%s(): The file is not seekable.", who);
       want *= 2;
       continue;

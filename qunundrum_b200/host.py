@@ -610,12 +610,15 @@ def _import_numbers(file, n: int, ctx):
         chunk = file.read(want)
         try:
             values, used = ctx.text_parse(chunk, n)
-            break
+            # a block that is not the rest of the file may end inside the n-th number: accept
+            # only if something follows it in the block, or the block reached the end of file
+            if used < len(chunk) or len(chunk) < want:
+                break
         except CriticalError as e:      # -20: the chunk ended before the n-th number
             if len(chunk) < want or "(code -20)" not in str(e):
                 raise
-            file.seek(pos)
-            want *= 2
+        file.seek(pos)
+        want *= 2
     file.seek(pos + used)
     return values
 

@@ -427,3 +427,21 @@ def test_gpu_slice_importer_reads_more_when_the_block_is_short(gpu_ctx):
     assert s.flags == 0xA0000
     assert same_bits(s.norm_matrix, vals[:-1]) and same_bits(np.array([s.total_error]), vals[-1:])
     assert f.read() == b"777\n"
+
+
+@pytest.mark.gpu
+def test_gpu_slice_importer_never_takes_a_number_cut_by_the_block_end(gpu_ctx):
+    """Line lengths around the importer's block size (40 bytes per number): for some paddings the
+    first block ends inside, or right behind, the last number of the slice. The number must not
+    be taken as it stands; the importer reads on."""
+    from qunundrum_b200 import host
+    rng = np.random.default_rng(4)
+    vals = rand_ld(rng, 32 * 32 + 1, 16383 - 200, 16383 - 20)
+    lines = ot.format_ld24(vals).split(b"\n")[:-1]
+    for pad in range(0, 24):
+        body = b"".join(b" " * pad + ln + b"\n" for ln in lines)
+        f = io.BytesIO(b"32\n2040\n2041\n000a0000\n" + body + b"777\n" + b"1.5\n" * 4000)
+        s = host.distribution_slice_import(f, gpu_ctx)
+        assert same_bits(s.norm_matrix, vals[:-1]), pad
+        assert same_bits(np.array([s.total_error]), vals[-1:]), pad
+        assert f.read(4) == b"777\n", pad
