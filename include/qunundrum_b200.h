@@ -218,8 +218,11 @@ int qb200_text_parse_device(qb200_context *ctx, const char *d_text, size_t len, 
 /* Introspection / test hooks (host logic; qb200_text_pow10 needs no GPU):
  * the 192-bit table entry of 10^k (little-endian 32-bit limbs, value =
  * T * 2^(e2 - 191), truncated; exact = 1 if nothing was cut off); a switch that
- * sends every value through the exact rounding decision; and the number of
- * values of the last call that needed it. */
+ * sends every value through the exact rounding decision (on = 1; on = 2 is a
+ * profiling-only mode of the exporter that writes every tile at a fixed stride
+ * instead of its chained offset -- the text is then NOT contiguous -- to time the
+ * kernel without the look-back chain); and the number of values of the last call
+ * that needed the exact decision. */
 int qb200_text_pow10(int k, uint32_t w[6], int32_t *e2, uint32_t *exact);
 int qb200_text_set_force_exact(qb200_context *ctx, int on);
 uint64_t qb200_text_exact_count(qb200_context *ctx);
