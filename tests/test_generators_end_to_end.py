@@ -61,6 +61,9 @@ CASES = [
     # the other two slice methods of the two-dimensional generator (src/distribution_slice.h:31-78)
     ("generate_distribution", ["-det", "-approx-quick", "-dim", "16", "128", "2"], "2d", 3),
     ("generate_distribution", ["-det", "-sigma-optimal", "-dim", "16", "64", "2"], "2d", 3),
+    # two distributions in one run, explicit l (parameters_explicit_m_l): the drop-in sees the
+    # parameter set change between calls
+    ("generate_distribution", ["-det", "-dim", "16", "-l", "64", "40", "96", "50"], "2d", 3),
     # BASELINE config 3 shape: Ekera-Hastad factoring, m = n / 2 - 1, l = m - 20, always target d
     ("generate_linear_distribution_rsa", ["-dim", "256", "-max", "256"], "linear", 2),
 ]
