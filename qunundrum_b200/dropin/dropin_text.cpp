@@ -117,6 +117,7 @@ void import_values(FILE* const file, long double* const values, const size_t n,
   std::vector<char> buf;
   std::vector<long double> parsed(n + 1);
   size_t want = 40 * (n + 1) + 64, used = 0;
+  int malformed_attempts = 0;
   qb200_context* const ctx = text_context();
   for (;;) {
     buf.resize(want);
@@ -132,7 +133,12 @@ void import_values(FILE* const file, long double* const values, const size_t n,
     // only counts if something follows that number in the block (used < got) or the block
     // reached the end of the file (got < want).
     if (0 == rc && (used < got || got < want)) break;
-    if ((0 == rc || -20 == rc) && got == want) {  // the block was too short: read more
+    // Any failure on a block that is not the rest of the file may come from a number cut by the
+    // block end (too few numbers, or a malformed stump such as "1.5e-"): read more. A file that
+    // really is malformed fails once the block reaches the end of the file.
+    // (A stump is cured by the next, twice as large block; two more attempts are allowed.)
+    if (0 != rc && -20 != rc) malformed_attempts++;
+    if (got == want && malformed_attempts <= 2) {
       if (0 != fseek(file, pos, SEEK_SET)) critical("%s(): The file is not seekable.", who);
       want *= 2;
       continue;

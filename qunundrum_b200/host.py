@@ -606,6 +606,7 @@ def _import_numbers(file, n: int, ctx):
     position where fscanf("%Lg\\n") x n would (after the white space that follows)."""
     pos = file.tell()
     want = 40 * n + 64
+    malformed_attempts = 0
     while True:
         chunk = file.read(want)
         try:
@@ -614,8 +615,13 @@ def _import_numbers(file, n: int, ctx):
             # only if something follows it in the block, or the block reached the end of file
             if used < len(chunk) or len(chunk) < want:
                 break
-        except CriticalError as e:      # -20: the chunk ended before the n-th number
-            if len(chunk) < want or "(code -20)" not in str(e):
+        except CriticalError as e:
+            # too few numbers, or a malformed stump of a number cut by the block end ("1.5e-"):
+            # read more (a stump is cured by the next, twice as large block); a file that really
+            # is malformed fails after two more attempts or when the block reaches its end
+            if "(code -20)" not in str(e):
+                malformed_attempts += 1
+            if len(chunk) < want or malformed_attempts > 2:
                 raise
         file.seek(pos)
         want *= 2

@@ -342,6 +342,16 @@ int hostsim_text_parse_ld(const char* textp, size_t len, size_t n, long double* 
   std::vector<uint32_t> scratch(text::BIG_LIMBS);
   size_t pos = 0, found = 0;
   uint64_t slow = 0;
+  {  // as the CUDA path: "fewer than n numbers" takes precedence over a malformed number
+    size_t cnt = 0;
+    bool in = false;
+    for (size_t i = 0; i < len && cnt < n; i++) {
+      const bool sp = text::is_space(s[i]);
+      if (!sp && !in) cnt++;
+      in = !sp;
+    }
+    if (cnt < n) return -20;
+  }
   while (found < n) {
     while (pos < len && text::is_space(s[pos])) pos++;
     if (pos >= len) return -20;
