@@ -13,7 +13,7 @@ INTEGRATION-TEST INFRASTRUCTURE. Sources are compiled where they lie under /root
 (never copied); neither OpenMPI nor fpLLL nor the GMP/MPFR development headers exist in this
 image, so the build uses integration/minimpi (a minimal single-node MPI over socket pairs),
 integration/stubs (a compile-only fpLLL stand-in: generation never reduces a lattice) and the
-declaration shims of oracle/shims. With the real toolchain a maintainer follows INTEGRATION.md
+declaration shims of integration/shims. With the real toolchain a maintainer follows INTEGRATION.md
 instead. The built binaries travel to the GPU box; /root/reference is not needed at run time.
 """
 from __future__ import annotations
@@ -56,10 +56,7 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
             os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
             os.path.join(HERE, "minimpi", "minimpi.c"), os.path.join(HERE, "minimpi", "mpi.h"),
             os.path.join(HERE, "build.py"), os.path.join(ROOT, "include", "qunundrum_b200.h"),
-            os.path.join(ROOT, "tests", "hostsim", "abi_shim.cpp"),
-            os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp"),
-            os.path.join(ROOT, "qunundrum_b200", "csrc", "textfmt.cuh"),
-            os.path.join(ROOT, "qunundrum_b200", "csrc", "textparse.cuh")]
+            ]
     if not force and os.path.exists(done) and all(
             os.path.getmtime(d) <= os.path.getmtime(done) for d in deps):
         return True
@@ -67,7 +64,7 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     for d in (obj, os.path.join(OUT, "ref"), os.path.join(OUT, "gpu")):
         os.makedirs(d, exist_ok=True)
     inc = ["-I", os.path.join(HERE, "minimpi"), "-I", os.path.join(HERE, "stubs"),
-           "-I", os.path.join(ROOT, "oracle", "shims"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(HERE, "shims"), "-I", os.path.join(ROOT, "include"),
            "-iquote", src]
     jobs = []
     for f in COMMON_CPP + INTEGRATORS + TEXT_IO + ["main_" + m for m in MAINS]:
@@ -102,24 +99,6 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
                                "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
                                "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
                                "-o", os.path.join(OUT, "gpu", m)])
-    # "shim" flavour (TEST-ONLY, tests/test_text_dropin_host_logic.py): the importing executables
-    # with the reference's integrators, dropin_text.cpp and a CPU stand-in for the text entry
-    # points (tests/hostsim/abi_shim.cpp), so that the drop-in's host logic runs without a GPU
-    os.makedirs(os.path.join(OUT, "shim"), exist_ok=True)
-    shim = os.path.join(OUT, "shim", "libqb200_textshim.so")
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-x", "c++",
-                           os.path.join(ROOT, "tests", "hostsim", "abi_shim.cpp"),
-                           os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp"),
-                           os.path.join(ROOT, "qunundrum_b200", "csrc", "hostconst.cpp"),
-                           os.path.join(ROOT, "qunundrum_b200", "csrc", "text_tables.cpp"),
-                           "-o", shim])
-    for m in ("filter_distribution", "compare_distributions", "compare_linear_distributions",
-              "compare_diagonal_distributions", "info_distribution"):
-        main_o = os.path.join(obj, "main_" + m + ".o")
-        subprocess.check_call(["g++", main_o, *common,
-                               *[os.path.join(obj, f + ".o") for f in INTEGRATORS],
-                               os.path.join(obj, "dropin_text.o"), shim, "-Wl,-rpath,$ORIGIN", *libs,
-                               "-o", os.path.join(OUT, "shim", m)])
     open(done, "w").write("ok\n")
     return True
 

@@ -2,7 +2,7 @@
 
 Needs the reference's headers (/root/reference/src, used in place, never copied)
 and -- only because this image lacks libgmp-dev -- the declaration shim
-oracle/shims/gmp.h. Output: qunundrum_b200/dropin/libqunundrum_dropin.so, which
+integration/shims/gmp.h. Output: qunundrum_b200/dropin/libqunundrum_dropin.so, which
 exports the six C++ entry points of the reference with their mangled names and
 depends on ../libqunundrum_b200.so and libgmp. It also compiles the reference's
 src/errors.c (critical()) in place so that the test library is self-contained.
@@ -32,7 +32,8 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> str |
                            os.path.join(src, "errors.c"), "-o", obj])
     subprocess.check_call(
         ["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-w",
-         "-I", os.path.join(ROOT, "oracle", "shims"), "-I", os.path.join(ROOT, "include"),
+         "-I", os.path.join(ROOT, "integration", "shims"), "-I", os.path.join(ROOT, "integration", "minimpi"),
+         "-I", os.path.join(ROOT, "include"),
          "-iquote", src, os.path.join(HERE, "dropin.cpp"), obj,
          "-o", LIB, "-L", PKG, "-lqunundrum_b200", "-Wl,-rpath,$ORIGIN/..", gmp])
     os.remove(obj)

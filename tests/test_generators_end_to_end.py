@@ -113,7 +113,7 @@ def test_full_distribution_sampled_against_reference(args):
     if not _have() or not ref.available():
         pytest.skip("integration/_build or oracle/_ref missing")
     import sys
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "full_distribution.py"), *args],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "full_distribution.py"), *args],
                        capture_output=True, text=True, timeout=3000)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
 
@@ -123,11 +123,11 @@ def test_full_distribution_sampled_against_reference(args):
 def test_one_dimensional_baseline_configs_at_full_size(config):
     """BASELINE configs 1, 3 (RSA-2048 and the s = 1..8 tradeoff sweep) and 5 (diagonal, m = 2048,
     sigma sweep) at their full sizes (dimension 2048) through the reference's generators with both
-    drop-ins; sampled slices re-computed by the reference on the host cores (integration/full_1d.py)."""
+    drop-ins; sampled slices re-computed by the reference on the host cores (tests/tools/full_1d.py)."""
     from oracle import ref
     if not _have() or not ref.available():
         pytest.skip("integration/_build or oracle/_ref missing")
     import sys
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "full_1d.py"), config, "8"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "full_1d.py"), config, "8"],
                        capture_output=True, text=True, timeout=3000)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]

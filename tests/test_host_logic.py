@@ -40,15 +40,20 @@ def test_no_cpu_fallback_without_a_device():
 
 
 def test_product_never_touches_the_oracle():
-    """Nothing under qunundrum_b200/ may import, load or link oracle/ or tests/."""
-    pkg = os.path.join(ROOT, "qunundrum_b200")
-    for root, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
-                txt = open(os.path.join(root, f), errors="replace").read()
-                assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", txt, re.M), f
-                assert "libqref" not in txt and "libhostsim" not in txt, f
-                assert not re.search(r'#include\s+"[^"]*(oracle|hostsim)', txt), f
+    """Nothing under qunundrum_b200/, include/ or integration/ (the product, its C ABI and the
+    reference-side integration build) may import, load, link, include or build from oracle/ or
+    tests/ -- not even a header path in a compiler command line."""
+    for top in ("qunundrum_b200", "include", "integration"):
+        for root, dirs, files in os.walk(os.path.join(ROOT, top)):
+            dirs[:] = [d for d in dirs if d not in ("_build", "_obj", "__pycache__")]
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".c", ".sh")):
+                    txt = open(os.path.join(root, f), errors="replace").read()
+                    assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", txt, re.M), f
+                    assert "libqref" not in txt and "libhostsim" not in txt, f
+                    assert not re.search(r'#include\s+"[^"]*(oracle|hostsim)', txt), f
+                    # path components in build commands: os.path.join(..., "oracle", ...) etc.
+                    assert not re.search(r'["\'](oracle|tests|hostsim)["\']', txt), f
 
 
 @pytest.mark.parametrize("l", list(range(3, 70)) + [128, 683, 768, 1023, 2048, 3072, 8192])

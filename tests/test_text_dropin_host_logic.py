@@ -4,7 +4,7 @@ to where fscanf would have stopped, running sums, fwrite.
 
 The reference's own importing executables are linked with dropin_text.cpp and a TEST-ONLY CPU
 stand-in for the two text entry points (tests/hostsim/abi_shim.cpp: the CPU compile of
-textfmt.cuh / textparse.cuh) -- the "shim" flavour of integration/build.py -- and must produce
+textfmt.cuh / textparse.cuh) -- tests/hostsim/shim_flavour.py -- and must produce
 the same bytes as the same executables with the reference's own *_slice_import_export.cpp."""
 import os
 import shutil
@@ -15,15 +15,16 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B = os.path.join(ROOT, "integration", "_build")
+SHIM = os.path.join(ROOT, "tests", "hostsim", "_build", "shim")
 
 
 def _have():
-    return os.path.exists(os.path.join(B, "shim", "filter_distribution"))
+    return os.path.exists(os.path.join(SHIM, "filter_distribution"))
 
 
 def _tool(flavour, exe, args, cwd):
     os.makedirs(os.path.join(cwd, "distributions"), exist_ok=True)
-    p = subprocess.run([os.path.join(B, flavour, exe), *args], cwd=cwd, capture_output=True, text=True,
+    p = subprocess.run([os.path.join(SHIM if flavour == "shim" else os.path.join(B, flavour), exe), *args], cwd=cwd, capture_output=True, text=True,
                        timeout=3000)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     return p.stdout
@@ -32,7 +33,7 @@ def _tool(flavour, exe, args, cwd):
 @pytest.fixture(scope="module")
 def generated():
     if not _have():
-        pytest.skip("integration/_build/shim missing (needs /root/reference at build time)")
+        pytest.skip("tests/hostsim/_build/shim missing (needs /root/reference at build time)")
     t = tempfile.mkdtemp()
     os.makedirs(os.path.join(t, "distributions"))
     # the reference's integrators on the CPU: small enough for a few seconds

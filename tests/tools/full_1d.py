@@ -2,13 +2,13 @@
 executables + both drop-ins, checked against the reference itself (oracle/_ref) on a sample of
 slices on the host cores.
 
-    python integration/full_1d.py rsa       # config 3: generate_linear_distribution_rsa, n = 2048
+    python tests/tools/full_1d.py rsa       # config 3: generate_linear_distribution_rsa, n = 2048
                                             #   (m = 1023, l = 1003), synthetic p and q
-    python integration/full_1d.py sweep     # config 3: generate_linear_distribution -d -exp <d_rsa>
+    python tests/tools/full_1d.py sweep     # config 3: generate_linear_distribution -d -exp <d_rsa>
                                             #   1023 s for s = 1 .. 8 in ONE run
-    python integration/full_1d.py diagonal  # config 5: generate_diagonal_distribution, m = 2048,
+    python tests/tools/full_1d.py diagonal  # config 5: generate_diagonal_distribution, m = 2048,
                                             #   sigma in {0, 5, 12}, eta-bound 2, in ONE run
-    python integration/full_1d.py linear    # config 1 at full dimension: m = 128, s = 2, -d and -r
+    python tests/tools/full_1d.py linear    # config 1 at full dimension: m = 128, s = 2, -d and -r
 
 Appends a report to gpurun_out/full_1d_report.json.
 """
@@ -21,7 +21,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 

@@ -2,7 +2,7 @@
 executable + the drop-in (BASELINE.json configs[1]) and check a random sample of its slices
 against the reference itself (oracle/_ref) on the host cores.
 
-    python integration/full_distribution.py [--clients 1] [--dim 256] [--sample 32]
+    python tests/tools/full_distribution.py [--clients 1] [--dim 256] [--sample 32]
 
 Writes gpurun_out/full_distribution_report.json.
 """
@@ -16,7 +16,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
