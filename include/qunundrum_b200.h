@@ -13,6 +13,8 @@
  *                                            linear_distribution_slice_compute_richardson src/linear_distribution_slice_compute_richardson.cpp:17
  *   qb200_slice1d_compute (DIAGONAL)         diagonal_distribution_slice_compute            src/diagonal_distribution_slice_compute.cpp:30
  *                                            diagonal_distribution_slice_compute_richardson src/diagonal_distribution_slice_compute_richardson.cpp:17
+ *   qb200_text_format_* / qb200_text_parse_* the value loops of *_slice_export / *_slice_import   (see "text export" below)
+ *   qb200_sampler_tau_estimate               tau_estimate / tau_estimate_linear             src/tau_estimate.cpp:23,89
  *
  * Conventions
  *  - plain pointers and sizes only; all buffers are caller-owned;
@@ -226,6 +228,76 @@ int qb200_text_parse_device(qb200_context *ctx, const char *d_text, size_t len, 
 int qb200_text_pow10(int k, uint32_t w[6], int32_t *e2, uint32_t *exact);
 int qb200_text_set_force_exact(qb200_context *ctx, int on);
 uint64_t qb200_text_exact_count(qb200_context *ctx);
+
+/* ---- sampling from a stored distribution: tau estimation ----------------------
+ *
+ * SURVEY.md section 8(f) #3. estimate_runs_* draw 10^6 estimates of n samples per tried n
+ * (src/executables_estimate_runs_distribution.h:23-28) through
+ *   tau_estimate          src/tau_estimate.cpp:23-87    -> distribution_sample_approximate_alpha_d_r
+ *                                                          src/distribution.cpp:464-527
+ *   tau_estimate_linear   src/tau_estimate.cpp:89-133   -> linear_distribution_sample_approximate_alpha
+ *                                                          src/linear_distribution.cpp:618-666
+ * and every sample is two linear long double walks (slices: src/distribution.cpp:384-401, then
+ * the D^2 cells of the slice: src/distribution_slice.cpp:191-223). A qb200_sampler holds the
+ * distribution in device memory; the entry points below take the random stream as the 64-bit
+ * words the reference's random_generate_pivot_* (src/random.c:116-156) would have drawn, in
+ * its order (slice pivot, region pivot, one fraction per axis), and return what the reference
+ * returns for the same words: the same slices and regions (its x87 rounding included), the
+ * same alphas to ~1e-30 relative, tau to the last place or two of a long double. */
+#define QB200_SAMPLER_LINEAR 1 /* Linear_Distribution, src/linear_distribution.h */
+#define QB200_SAMPLER_2D 2     /* Distribution, src/distribution.h:55-85 */
+
+typedef struct qb200_sampler qb200_sampler;
+
+/* The slices in the distribution's current (walk) order: dimension[i], coordinates
+ * (c0 = min_log_alpha_d, c1 = min_log_alpha_r; linear: c0 = min_log_alpha, c1 may be NULL),
+ * cells[i] = norm_matrix / norm_vector (dimension^dims long doubles, read during the call
+ * only), slice_total[i] = total_probability of the slice, total_probability of the
+ * distribution, m of its parameters. Dimensions must be powers of two. */
+int qb200_sampler_create(qb200_context *ctx, int dims, uint32_t m, uint32_t n_slices,
+                         const uint32_t *dimension, const int32_t *c0, const int32_t *c1,
+                         const long double *const *cells, const long double *slice_total,
+                         long double total_probability, qb200_sampler **sampler);
+void qb200_sampler_destroy(qb200_sampler *sampler);
+
+/* 64-bit words one successful sample consumes: 4 (two-dimensional) or 3 (linear). A sample
+ * whose slice pivot runs past the last slice consumes one word and fails. */
+uint32_t qb200_sampler_words_per_sample(const qb200_sampler *sampler);
+uint64_t qb200_sampler_cells(const qb200_sampler *sampler);
+
+/* k independent samples, sample i from words[i * words_per_sample ...]: index of the slice
+ * and of the region (cell) the reference would select, alpha / 2^m per axis rounded to double
+ * (signed), status 0 ok / 1 out of bounds (the reference returns FALSE) / 2 no region (the
+ * reference calls critical()). Any output pointer may be NULL. */
+int qb200_sampler_sample(qb200_sampler *sampler, uint32_t k, const uint64_t *words, int32_t *slice,
+                         int32_t *cell, double *x0, double *x1, int32_t *status);
+
+/* Up to `count` consecutive calls of tau_estimate(distribution, random_state, n, ...) on the
+ * stream words[0, n_words): estimate t starts where estimate t - 1 stopped reading (an
+ * estimate stops at its first out-of-bounds sample: ok = 0, tau = DBL_MAX, as the reference).
+ * *done = estimates completed before the words ran out (count if n_words >= count * n *
+ * words_per_sample), *words_used = words they consumed. tau1 is written for two-dimensional
+ * distributions only (tau_d in tau0, tau_r in tau1) and may be NULL otherwise.
+ * Error -41: a region walk ran off its slice (the reference: critical("Failed to sample a
+ * region from the slice.")). */
+int qb200_sampler_tau_estimate(qb200_sampler *sampler, uint32_t n, uint32_t count,
+                               const uint64_t *words, size_t n_words, size_t *words_used,
+                               uint32_t *done, long double *tau0, long double *tau1, uint8_t *ok);
+
+/* Device-resident form: d_words holds count * n * words_per_sample words in the regular
+ * layout; two launches on `stream` (NULL = the context's own), no synchronisation. d_sums:
+ * count x 4 doubles (sum of (alpha_d / 2^m)^2 as hi, lo, then the same for alpha_r); d_status:
+ * count ints (0, or the status of the estimate's first failing sample). */
+int qb200_sampler_tau_device(qb200_sampler *sampler, uint32_t n, uint32_t count,
+                             const uint64_t *d_words, double *d_sums, int32_t *d_status,
+                             void *stream);
+
+/* Test hooks: send every walk through the bit-exact x87 replay (on = 1); the number of walks
+ * of the last call that needed it; the smallest slice-pivot word that runs out of bounds
+ * (return value 0: none does). */
+int qb200_sampler_set_force_exact(qb200_sampler *sampler, int on);
+uint64_t qb200_sampler_exact_count(const qb200_sampler *sampler);
+int qb200_sampler_first_failing_word(const qb200_sampler *sampler, uint64_t *word);
 
 /* ---- introspection (host logic; usable without a GPU) --------------------- */
 

@@ -79,6 +79,22 @@ def lib():
     L.qref_probability_approx_quick.argtypes = [vp, cp, cp, cp, sz]
     L.qref_linear_probability.argtypes = [vp, C.c_int, cp, cp, sz]
     L.qref_diagonal_probability_f_eta.argtypes = [vp, cp, i32, u32, cp, sz]
+    # sampling path (ref_capi_sample.cpp)
+    L.qref_dist_new.argtypes = [C.c_int, vp, u32, vp, vp, vp, ldp, ldp]
+    L.qref_dist_new.restype = vp
+    L.qref_dist_free.argtypes = [vp]
+    L.qref_dist_sort.argtypes = [vp]
+    L.qref_dist_describe.argtypes = [vp, vp, vp, vp, ldp, ldp]
+    L.qref_dist_set_total.argtypes = [vp, C.c_longdouble]
+    L.qref_random_new.argtypes = [cp]
+    L.qref_random_new.restype = vp
+    L.qref_random_free.argtypes = [vp]
+    L.qref_random_bytes.argtypes = [vp, vp, u32]
+    L.qref_dist_sample_region.argtypes = [vp, vp, u32, vp, vp]
+    L.qref_dist_sample_region.restype = u32
+    L.qref_dist_sample_alpha.argtypes = [vp, vp, u32, ldp, ldp, vp]
+    L.qref_dist_sample_alpha.restype = u32
+    L.qref_tau_estimate.argtypes = [vp, vp, u32, u32, ldp, ldp, vp]
     _lib = L
     return L
 
@@ -237,3 +253,87 @@ def heuristic_sigma(l: int) -> int:
     v = (f(l) + f(11) + f(4) - f(1.6515)) / f(2.0)
     # C round(): half away from zero.
     return int(np.floor(float(v) + 0.5))
+
+
+# --------------------------------------------------------------------------- #
+# Sampling from stored distributions              #
+# --------------------------------------------------------------------------- #
+
+class RefRandom:
+    """Random_State expanded from a 32-byte seed (src/keccak_random.c:52)."""
+
+    def __init__(self, seed: bytes):
+        assert len(seed) == 32
+        self.h = lib().qref_random_new(seed)
+
+    def bytes(self, n: int) -> bytes:
+        out = np.zeros(n, dtype=np.uint8)
+        lib().qref_random_bytes(self.h, out.ctypes.data, n)
+        return out.tobytes()
+
+    def words(self, n: int) -> np.ndarray:
+        """n consecutive 8-byte draws as the uint64 values random_generate_pivot_* see."""
+        return np.frombuffer(self.bytes(8 * n), dtype="<u8").copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qref_random_free(self.h)
+            self.h = None
+
+
+class RefDistribution:
+    """Distribution (dims = 2) or Linear_Distribution (dims = 1) owned by the reference."""
+
+    def __init__(self, dims: int, params: RefParameters, dimension, c0, c1, cells, totals=None):
+        self.dims, self.params = dims, params
+        self.n = len(dimension)
+        dim = np.ascontiguousarray(dimension, dtype=np.uint32)
+        a = np.ascontiguousarray(c0, dtype=np.int32)
+        b = np.ascontiguousarray(c1 if c1 is not None else np.zeros(self.n), dtype=np.int32)
+        cl = np.ascontiguousarray(cells, dtype=np.longdouble)
+        assert cl.size == int(sum(int(d) ** dims for d in dim))
+        t = None if totals is None else np.ascontiguousarray(totals, dtype=np.longdouble)
+        self.h = lib().qref_dist_new(dims, params.h, self.n, dim.ctypes.data, a.ctypes.data,
+                                     b.ctypes.data, cl.ctypes.data, None if t is None else t.ctypes.data)
+
+    def sort(self):
+        lib().qref_dist_sort(self.h)
+
+    def set_total(self, total):
+        lib().qref_dist_set_total(self.h, np.longdouble(total))
+
+    def describe(self):
+        dim = np.zeros(self.n, dtype=np.uint32)
+        a = np.zeros(self.n, dtype=np.int32)
+        b = np.zeros(self.n, dtype=np.int32)
+        t = np.zeros(self.n, dtype=np.longdouble)
+        tot = np.zeros(1, dtype=np.longdouble)
+        lib().qref_dist_describe(self.h, dim.ctypes.data, a.ctypes.data, b.ctypes.data, t.ctypes.data,
+                                 tot.ctypes.data)
+        return dim, a, b, t, tot[0]
+
+    def sample_region(self, rng: RefRandom, k: int):
+        out = np.zeros((k, 4))
+        ok = np.zeros(k, dtype=np.uint8)
+        lib().qref_dist_sample_region(self.h, rng.h, k, out.ctypes.data, ok.ctypes.data)
+        return out, ok.astype(bool)
+
+    def sample_alpha(self, rng: RefRandom, k: int):
+        """alpha / 2^m of k samples (long double), and the success flags."""
+        a0 = np.zeros(k, dtype=np.longdouble)
+        a1 = np.zeros(k, dtype=np.longdouble)
+        ok = np.zeros(k, dtype=np.uint8)
+        lib().qref_dist_sample_alpha(self.h, rng.h, k, a0.ctypes.data, a1.ctypes.data, ok.ctypes.data)
+        return a0, a1, ok.astype(bool)
+
+    def tau_estimate(self, rng: RefRandom, n: int, count: int):
+        t0 = np.zeros(count, dtype=np.longdouble)
+        t1 = np.zeros(count, dtype=np.longdouble)
+        ok = np.zeros(count, dtype=np.uint8)
+        lib().qref_tau_estimate(self.h, rng.h, n, count, t0.ctypes.data, t1.ctypes.data, ok.ctypes.data)
+        return t0, t1, ok.astype(bool)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qref_dist_free(self.h)
+            self.h = None

@@ -1,0 +1,235 @@
+/* oracle/ref_capi_sample.cpp -- plain-C handle API over the UNMODIFIED reference's sampling
+ * path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see ref_capi.cpp): linked into oracle/_ref/libqref.so, which only
+ * tests/, __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of bench.py load.
+ *
+ *   reference function                                   (file:line)
+ *   distribution_init / _insert_slice / _sort_slices     src/distribution.cpp:40,159,258
+ *   distribution_sample_slice / _region                  src/distribution.cpp:359,411
+ *   distribution_sample_approximate_alpha_d_r            src/distribution.cpp:464
+ *   distribution_slice_sample_region                     src/distribution_slice.cpp:167
+ *   linear_distribution_init / _insert_slice             src/linear_distribution.cpp:47,434
+ *   linear_distribution_sample_approximate_alpha         src/linear_distribution.cpp:618
+ *   sample_approximate_alpha_from_region                 src/sample.cpp:24
+ *   tau_estimate / tau_estimate_linear                   src/tau_estimate.cpp:23,89
+ *   random_generate / keccak_random_init_seed            src/random.c:88, src/keccak_random.c:52
+ *
+ * fpLLL is not in the image: lattice_alpha_init / _clear (called by distribution_init, never by
+ * the sampling functions above) come from integration/stubs/lattice_stub.cpp.
+ */
+#include "common.h"
+#include "distribution.h"
+#include "distribution_slice.h"
+#include "keccak_random.h"
+#include "linear_distribution.h"
+#include "linear_distribution_slice.h"
+#include "parameters.h"
+#include "random.h"
+#include "tau_estimate.h"
+
+#include <gmp.h>
+#include <mpfr.h>
+
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+struct Dist {
+  int dims;
+  Distribution d2;
+  Linear_Distribution d1;
+};
+
+void ensure_precision() { mpfr_set_default_prec(PRECISION); }
+
+}  // namespace
+
+extern "C" {
+
+/* dims = 2: Distribution of n slices (c0 = min_log_alpha_d, c1 = min_log_alpha_r, dimension[i]^2
+ * cells each, concatenated in `cells`); dims = 1: Linear_Distribution (c0 = min_log_alpha,
+ * dimension[i] cells each). totals: the slices' total_probability (NULL: the sum of the cells in
+ * index order, as the importers compute it). */
+void *qref_dist_new(int dims, void *params, uint32_t n, const uint32_t *dimension, const int32_t *c0,
+                    const int32_t *c1, const long double *cells, const long double *totals) {
+  ensure_precision();
+  Dist *h = (Dist *)calloc(1, sizeof(Dist));
+  h->dims = dims;
+  const Parameters *p = (const Parameters *)params;
+  size_t off = 0;
+  if (dims == 2) {
+    distribution_init(&h->d2, p, n ? n : 1);
+    for (uint32_t i = 0; i < n; i++) {
+      Distribution_Slice *s = distribution_slice_alloc();
+      distribution_slice_init(s, dimension[i]);
+      const size_t nc = (size_t)dimension[i] * dimension[i];
+      memcpy(s->norm_matrix, cells + off, nc * sizeof(long double));
+      off += nc;
+      s->min_log_alpha_d = c0[i];
+      s->min_log_alpha_r = c1[i];
+      long double t = 0;
+      for (size_t k = 0; k < nc; k++) t += s->norm_matrix[k];
+      s->total_probability = totals ? totals[i] : t;
+      s->total_error = 0;
+      distribution_insert_slice(&h->d2, s);
+    }
+  } else {
+    linear_distribution_init(&h->d1, p, 0, n ? n : 1);
+    for (uint32_t i = 0; i < n; i++) {
+      Linear_Distribution_Slice *s = linear_distribution_slice_alloc();
+      linear_distribution_slice_init(s, dimension[i]);
+      const size_t nc = dimension[i];
+      memcpy(s->norm_vector, cells + off, nc * sizeof(long double));
+      off += nc;
+      s->min_log_alpha = c0[i];
+      long double t = 0;
+      for (size_t k = 0; k < nc; k++) t += s->norm_vector[k];
+      s->total_probability = totals ? totals[i] : t;
+      s->total_error = 0;
+      linear_distribution_insert_slice(&h->d1, s);
+    }
+  }
+  return h;
+}
+
+void qref_dist_free(void *hh) {
+  Dist *h = (Dist *)hh;
+  if (!h) return;
+  if (h->dims == 2)
+    distribution_clear(&h->d2);
+  else
+    linear_distribution_clear(&h->d1);
+  free(h);
+}
+
+void qref_dist_sort(void *hh) {
+  Dist *h = (Dist *)hh;
+  if (h->dims == 2)
+    distribution_sort_slices(&h->d2);
+  else
+    linear_distribution_sort_slices(&h->d1);
+}
+
+/* The slices in their current order: coordinates, dimension and total_probability. */
+void qref_dist_describe(void *hh, uint32_t *dimension, int32_t *c0, int32_t *c1, long double *totals,
+                        long double *total) {
+  Dist *h = (Dist *)hh;
+  if (h->dims == 2) {
+    for (uint32_t i = 0; i < h->d2.count; i++) {
+      dimension[i] = h->d2.slices[i]->dimension;
+      c0[i] = h->d2.slices[i]->min_log_alpha_d;
+      c1[i] = h->d2.slices[i]->min_log_alpha_r;
+      totals[i] = h->d2.slices[i]->total_probability;
+    }
+    *total = h->d2.total_probability;
+  } else {
+    for (uint32_t i = 0; i < h->d1.count; i++) {
+      dimension[i] = h->d1.slices[i]->dimension;
+      c0[i] = h->d1.slices[i]->min_log_alpha;
+      c1[i] = 0;
+      totals[i] = h->d1.slices[i]->total_probability;
+    }
+    *total = h->d1.total_probability;
+  }
+}
+
+/* Overwrite the distribution's total_probability (to exercise the "> 1" branch of
+ * distribution_sample_slice, src/distribution.cpp:373-381). */
+void qref_dist_set_total(void *hh, long double total) {
+  Dist *h = (Dist *)hh;
+  if (h->dims == 2)
+    h->d2.total_probability = total;
+  else
+    h->d1.total_probability = total;
+}
+
+/* A Random_State expanded from a 32-byte seed (keccak_random_init_seed). */
+void *qref_random_new(const uint8_t *seed) {
+  Random_State *rs = (Random_State *)calloc(1, sizeof(Random_State));
+  random_init(rs);
+  keccak_random_init_seed(&rs->keccak_state, seed);
+  return rs;
+}
+
+void qref_random_free(void *rs) {
+  if (!rs) return;
+  random_close((Random_State *)rs);
+  free(rs);
+}
+
+void qref_random_bytes(void *rs, uint8_t *out, uint32_t n) { random_generate(out, n, (Random_State *)rs); }
+
+/* k calls of distribution_sample_region / linear_distribution_sample_region: out[4 * i ...] =
+ * min_log_alpha_d, max_log_alpha_d, min_log_alpha_r, max_log_alpha_r (linear: the first two).
+ * Returns the number of successful samples. */
+uint32_t qref_dist_sample_region(void *hh, void *rs, uint32_t k, double *out, uint8_t *ok) {
+  Dist *h = (Dist *)hh;
+  uint32_t good = 0;
+  for (uint32_t i = 0; i < k; i++) {
+    double *o = out + 4 * (size_t)i;
+    o[0] = o[1] = o[2] = o[3] = 0;
+    bool r;
+    if (h->dims == 2)
+      r = distribution_sample_region(&h->d2, (Random_State *)rs, &o[0], &o[1], &o[2], &o[3]);
+    else
+      r = linear_distribution_sample_region(&h->d1, (Random_State *)rs, &o[0], &o[1]);
+    ok[i] = r ? 1 : 0;
+    good += r ? 1 : 0;
+  }
+  return good;
+}
+
+/* k calls of distribution_sample_approximate_alpha_d_r / linear_..._alpha; alpha / 2^m as long
+ * double (mpfr_get_ld of the 192-bit value scaled by 2^-m; infinity on failure). */
+uint32_t qref_dist_sample_alpha(void *hh, void *rs, uint32_t k, long double *a0, long double *a1,
+                                uint8_t *ok) {
+  ensure_precision();
+  Dist *h = (Dist *)hh;
+  mpfr_t x, y;
+  mpfr_init2(x, PRECISION);
+  mpfr_init2(y, PRECISION);
+  const uint32_t m = h->dims == 2 ? h->d2.parameters.m : h->d1.parameters.m;
+  uint32_t good = 0;
+  for (uint32_t i = 0; i < k; i++) {
+    bool r;
+    if (h->dims == 2) {
+      r = distribution_sample_approximate_alpha_d_r(&h->d2, (Random_State *)rs, x, y);
+      mpfr_mul_2si(x, x, -(long)m, MPFR_RNDN);
+      mpfr_mul_2si(y, y, -(long)m, MPFR_RNDN);
+      a0[i] = mpfr_get_ld(x, MPFR_RNDN);
+      a1[i] = mpfr_get_ld(y, MPFR_RNDN);
+    } else {
+      r = linear_distribution_sample_approximate_alpha(&h->d1, (Random_State *)rs, x);
+      mpfr_mul_2si(x, x, -(long)m, MPFR_RNDN);
+      a0[i] = mpfr_get_ld(x, MPFR_RNDN);
+      a1[i] = 0;
+    }
+    ok[i] = r ? 1 : 0;
+    good += r ? 1 : 0;
+  }
+  mpfr_clear(x);
+  mpfr_clear(y);
+  return good;
+}
+
+/* count calls of tau_estimate / tau_estimate_linear with n samples each. */
+void qref_tau_estimate(void *hh, void *rs, uint32_t n, uint32_t count, long double *tau0,
+                       long double *tau1, uint8_t *ok) {
+  ensure_precision();
+  Dist *h = (Dist *)hh;
+  for (uint32_t i = 0; i < count; i++) {
+    bool r;
+    if (h->dims == 2) {
+      r = tau_estimate(&h->d2, (Random_State *)rs, n, tau0[i], tau1[i]);
+    } else {
+      r = tau_estimate_linear(&h->d1, (Random_State *)rs, n, tau0[i]);
+      tau1[i] = 0;
+    }
+    ok[i] = r ? 1 : 0;
+  }
+}
+
+} /* extern "C" */

@@ -47,6 +47,13 @@ from .host import (  # noqa: F401
     linear_distribution_slice_export,
     linear_distribution_slice_import,
     text_pow10,
+    # sampling from stored distributions: tau estimation
+    Distribution,
+    Linear_Distribution,
+    Sampler,
+    WordStream,
+    tau_estimate,
+    tau_estimate_linear,
 )
 from . import host  # noqa: F401,E402
 

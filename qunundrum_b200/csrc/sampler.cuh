@@ -1,0 +1,257 @@
+// sampler.cuh -- sampling (alpha_d, alpha_r) / alpha from a stored distribution, one sample
+// per thread.
+//
+// Replaces, for a batch of samples, what the reference does per sample in
+//   distribution_sample_approximate_alpha_d_r   src/distribution.cpp:464-527
+//     distribution_sample_slice                 src/distribution.cpp:359-409   (walk over <= 6404 slices)
+//     distribution_slice_sample_region          src/distribution_slice.cpp:167-228 (walk over D^2 cells)
+//     distribution_slice_region_coordinates     src/distribution_slice.cpp:130-165
+//     sample_approximate_alpha_from_region x 2  src/sample.cpp:24-77
+//   linear_distribution_sample_approximate_alpha src/linear_distribution.cpp:618-666 (same, one axis)
+// which is what tau_estimate / tau_estimate_linear (src/tau_estimate.cpp:23-133) spend their
+// time in: 10^6 estimates of n samples per tried n in estimate_runs_*
+// (src/executables_estimate_runs_distribution.h:23-28), every sample two linear long double
+// walks of up to 6404 + 65,536 steps.
+//
+// Here a walk is a binary search over prefix sums kept per block of 32 elements (exact
+// double-double images of the x87 numbers) followed by a scan of one block. The reference's
+// walk rounds to 64 bits at every step, so its stopping index can differ from the exact one
+// only when the pivot lies within the accumulated rounding error B of a prefix sum: the fast
+// path accepts an index only if the pivot clears every earlier prefix (their running maximum --
+// Richardson cells may be negative, so prefixes are not monotone) and the stopping prefix by
+// more than B; otherwise the walk is replayed bit for bit with x87soft.cuh. The results are
+// therefore the reference's for the same random words, not merely the same distribution.
+//
+// Everything is __host__ __device__: tests/hostsim runs the identical code on the CPU.
+#pragma once
+
+#include "integrands.cuh"
+#include "x87soft.cuh"
+
+namespace qb200 {
+
+#define QB_SEG_BLOCK 32
+
+struct RawX87 {  // the 16 bytes of an x86-64 long double
+  uint64_t mant;
+  uint64_t se;   // low 16 bits: sign and exponent; the rest is padding (ignored)
+};
+
+struct SegCoarse {  // state of the walk BEFORE a block
+  dd c;             // prefix sum
+  dd m;             // running maximum of the earlier prefix sums (-1e300 before the first)
+};
+
+struct SamplerSlice {
+  uint64_t cell_off;    // first cell in SamplerView::cells
+  uint64_t coarse_off;  // first entry in SamplerView::coarse (n_blocks + 1 entries)
+  uint32_t n_cells;
+  uint32_t D;
+  int32_t c0, c1;       // min_log_alpha_d, min_log_alpha_r (linear: min_log_alpha, 0)
+  uint32_t geo_off;     // 2^(j / D), j = 0 .. D, in SamplerView::geo
+  uint32_t pad;
+  double abs_sum;       // sum of |cell|: scale of the rounding-error band
+};
+
+struct SamplerView {
+  const RawX87* cells;
+  const SegCoarse* coarse;
+  const SamplerSlice* slices;
+  const RawX87* totals;            // the slices' total_probability, in walk order
+  const SegCoarse* totals_coarse;
+  const dd* geo;
+  double totals_abs_sum;
+  RawX87 dist_total;               // distribution->total_probability
+  uint32_t n_slices;
+  int scale_by_total;              // total_probability > 1 (src/distribution.cpp:373)
+  int m;
+  int dims;                        // 2: Distribution, 1: Linear_Distribution
+};
+
+struct SampleOut {  // 64 bytes
+  double sq0_hi, sq0_lo;  // (alpha_d / 2^m)^2   (linear: (alpha / 2^m)^2)
+  double sq1_hi, sq1_lo;  // (alpha_r / 2^m)^2
+  double x0, x1;          // alpha / 2^m rounded to double, signed
+  int32_t slice, cell;
+  int32_t status;         // 0 ok, 1 out of bounds (reference returns FALSE), 2 no region (reference: critical)
+  int32_t exact;          // number of walks that needed the bit-exact replay
+};
+
+enum { kSampleOk = 0, kSampleOutOfBounds = 1, kSampleNoRegion = 2 };
+
+QHD bool dd_ge(dd a, dd b) { return a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo); }
+QHD dd dd_max(dd a, dd b) { return dd_ge(a, b) ? a : b; }
+
+QHD X87 x87_load(const RawX87* p, bool* ok) {
+  X87 v;
+  const RawX87 r = *p;
+  if (!x87_decode(r.mant, (uint32_t)r.se & 0xffffu, &v)) *ok = false;
+  return v;
+}
+
+// Summary of block b of a segment: its sum, the maximum of its own prefix sums (from 0), the
+// sum of magnitudes, and whether every element decodes.
+QHD void seg_block_summary(const RawX87* v, uint32_t n, uint32_t b, dd* sum, dd* maxp, double* abs_sum,
+                           bool* ok) {
+  dd c = make_dd(0.0, 0.0), mx = make_dd(-1e300, 0.0);
+  double ab = 0.0;
+  const uint32_t lo = b * QB_SEG_BLOCK, hi = lo + QB_SEG_BLOCK < n ? lo + QB_SEG_BLOCK : n;
+  for (uint32_t k = lo; k < hi; k++) {
+    const dd x = x87_to_dd(x87_load(v + k, ok));
+    c = dd_add(c, x);
+    mx = dd_max(mx, c);
+    ab += fabs(x.hi);
+  }
+  *sum = c;
+  *maxp = mx;
+  *abs_sum = ab;
+}
+
+// In place: entries 1 .. n_blocks of `coarse` hold the block summaries {sum, maxp} of blocks
+// 0 .. n_blocks - 1; turn them into the walk states before each block (entry n_blocks: after
+// the last one).
+QHD void seg_scan(SegCoarse* coarse, uint32_t n_blocks) {
+  dd c = make_dd(0.0, 0.0), m = make_dd(-1e300, 0.0);
+  coarse[0].c = c;
+  coarse[0].m = m;
+  for (uint32_t b = 0; b < n_blocks; b++) {
+    const dd sum = coarse[b + 1].c, maxp = coarse[b + 1].m;
+    m = dd_max(m, dd_add(c, maxp));
+    c = dd_add(c, sum);
+    coarse[b + 1].c = c;
+    coarse[b + 1].m = m;
+  }
+}
+
+// The reference's walk, replayed bit for bit: first k with pivot - v[0] - ... - v[k] <= 0.
+QHD uint32_t seg_walk_exact(const RawX87* v, uint32_t n, X87 p) {
+  bool ok = true;
+  for (uint32_t k = 0; k < n; k++) {
+    p = x87_add(p, x87_neg(x87_load(v + k, &ok)));
+    if (x87_nonpositive(p)) return k;
+  }
+  return n;
+}
+
+// First k at which the reference's walk stops, or n. *exact is incremented when the replay ran.
+QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, uint32_t n, double abs_sum, X87 p,
+                      bool force_exact, int* exact) {
+  if (n == 0) return 0;
+  if (force_exact) {
+    *exact += 1;
+    return seg_walk_exact(v, n, p);
+  }
+  const dd pd = x87_to_dd(p);
+  const uint32_t nb = (n + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK;
+  const double unit = 1.0842021724855044e-19 * (fabs(pd.hi) + abs_sum);  // 2^-63 * scale
+  // smallest block whose running maximum at its end reaches the pivot
+  uint32_t lo = 0, hi = nb;  // answer in [lo, hi]; hi == nb: none
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (dd_ge(coarse[mid + 1].m, pd))
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  if (lo == nb) {
+    // no prefix reaches the pivot: certain only if the largest one misses it by more than B
+    const dd gap = dd_add(pd, dd_neg(coarse[nb].m));
+    if (gap.hi > (double)(n + 2) * unit) return n;
+    *exact += 1;
+    return seg_walk_exact(v, n, p);
+  }
+  dd c = coarse[lo].c, mprev = coarse[lo].m;
+  const uint32_t k0 = lo * QB_SEG_BLOCK, k1 = k0 + QB_SEG_BLOCK < n ? k0 + QB_SEG_BLOCK : n;
+  bool ok = true;
+  for (uint32_t k = k0; k < k1; k++) {
+    c = dd_add(c, x87_to_dd(x87_load(v + k, &ok)));
+    if (dd_ge(c, pd)) {
+      const double band = (double)(k + 2) * unit;
+      const dd over = dd_add(c, dd_neg(pd)), clear = dd_add(pd, dd_neg(mprev));
+      if (over.hi > band && clear.hi > band) return k;
+      *exact += 1;
+      return seg_walk_exact(v, n, p);
+    }
+    mprev = dd_max(mprev, c);
+  }
+  // the block summary promised a hit inside this block; rounding of the summary itself
+  *exact += 1;
+  return seg_walk_exact(v, n, p);
+}
+
+// |alpha| / 2^m for region j of an axis with coordinate k and dimension D, and fraction word w
+// (src/sample.cpp:42-61): alpha_min + (alpha_max - alpha_min) * (double)fraction, with
+// alpha_min/max = round(2^(|k| + j / D)) and fraction = (w mod 2^63) / 2^63 (src/random.c:137-156).
+QHD dd sample_axis(const SamplerView& s, const SamplerSlice& sl, int32_t k, uint32_t j, uint64_t w) {
+  const int k_abs = k < 0 ? -k : k;
+  const dd xmin = grid_x(s.geo[sl.geo_off + j], k_abs, 1, s.m);
+  const dd xmax = grid_x(s.geo[sl.geo_off + j + 1], k_abs, 1, s.m);
+  const double f = (double)(w & 0x7fffffffffffffffull) * 1.0842021724855044e-19;  // RN to 53 bits, / 2^63
+  const dd x = dd_add(xmin, dd_mul_d(dd_add(xmax, dd_neg(xmin)), f));
+  return x;
+}
+
+// One sample from the words w[0 .. dims + 1] (the reference's draws, in its order: slice
+// pivot, region pivot, one fraction per axis).
+QHD void sample_one(const SamplerView& s, const uint64_t* w, bool force_exact, SampleOut* out) {
+  out->sq0_hi = out->sq0_lo = out->sq1_hi = out->sq1_lo = 0.0;
+  out->x0 = out->x1 = 0.0;
+  out->slice = out->cell = -1;
+  out->exact = 0;
+  bool ok = true;
+  X87 p = x87_pivot_inclusive(w[0]);
+  if (s.scale_by_total) p = x87_mul(p, x87_load(&s.dist_total, &ok));
+  const uint32_t i = seg_find(s.totals, s.totals_coarse, s.n_slices, s.totals_abs_sum, p, force_exact,
+                              &out->exact);
+  if (i >= s.n_slices) {
+    out->status = kSampleOutOfBounds;
+    return;
+  }
+  out->slice = (int32_t)i;
+  const SamplerSlice sl = s.slices[i];
+  const X87 p2 = x87_mul(x87_pivot_inclusive(w[1]), x87_load(s.totals + i, &ok));
+  const uint32_t c = seg_find(s.cells + sl.cell_off, s.coarse + sl.coarse_off, sl.n_cells, sl.abs_sum,
+                              p2, force_exact, &out->exact);
+  if (c >= sl.n_cells) {
+    out->status = kSampleNoRegion;
+    return;
+  }
+  out->cell = (int32_t)c;
+  out->status = kSampleOk;
+  if (s.dims == 2) {
+    const dd xd = sample_axis(s, sl, sl.c0, c % sl.D, w[2]);
+    const dd xr = sample_axis(s, sl, sl.c1, c / sl.D, w[3]);
+    const dd qd = dd_mul(xd, xd), qr = dd_mul(xr, xr);
+    out->sq0_hi = qd.hi; out->sq0_lo = qd.lo;
+    out->sq1_hi = qr.hi; out->sq1_lo = qr.lo;
+    out->x0 = sl.c0 < 0 ? -xd.hi : xd.hi;
+    out->x1 = sl.c1 < 0 ? -xr.hi : xr.hi;
+  } else {
+    const dd x = sample_axis(s, sl, sl.c0, c, w[2]);
+    const dd q = dd_mul(x, x);
+    out->sq0_hi = q.hi; out->sq0_lo = q.lo;
+    out->x0 = sl.c0 < 0 ? -x.hi : x.hi;
+  }
+}
+
+// Sum of the squares of the n samples of one estimate, in sample order (fixed => reproducible).
+// Returns the index of the first failing sample, or n.
+QHD uint32_t tau_sums(const SampleOut* o, uint32_t n, dd* s0, dd* s1, int* status) {
+  dd a = make_dd(0.0, 0.0), b = make_dd(0.0, 0.0);
+  *status = kSampleOk;
+  for (uint32_t i = 0; i < n; i++) {
+    if (o[i].status != kSampleOk) {
+      *status = o[i].status;
+      *s0 = a;
+      *s1 = b;
+      return i;
+    }
+    a = dd_add(a, make_dd(o[i].sq0_hi, o[i].sq0_lo));
+    b = dd_add(b, make_dd(o[i].sq1_hi, o[i].sq1_lo));
+  }
+  *s0 = a;
+  *s1 = b;
+  return n;
+}
+
+}  // namespace qb200

@@ -117,6 +117,22 @@ def lib():
     L.qb200_text_set_force_exact.argtypes = [vp, C.c_int]
     L.qb200_text_exact_count.argtypes = [vp]
     L.qb200_text_exact_count.restype = C.c_uint64
+    u64p = C.c_void_p
+    L.qb200_sampler_create.argtypes = [vp, C.c_int, u32, u32, vp, vp, vp, vp, vp, C.c_longdouble,
+                                       C.POINTER(vp)]
+    L.qb200_sampler_destroy.argtypes = [vp]
+    L.qb200_sampler_words_per_sample.argtypes = [vp]
+    L.qb200_sampler_words_per_sample.restype = u32
+    L.qb200_sampler_cells.argtypes = [vp]
+    L.qb200_sampler_cells.restype = C.c_uint64
+    L.qb200_sampler_sample.argtypes = [vp, u32, u64p, vp, vp, vp, vp, vp]
+    L.qb200_sampler_tau_estimate.argtypes = [vp, u32, u32, u64p, C.c_size_t, C.POINTER(C.c_size_t),
+                                             C.POINTER(u32), vp, vp, vp]
+    L.qb200_sampler_tau_device.argtypes = [vp, u32, u32, vp, vp, vp, vp]
+    L.qb200_sampler_set_force_exact.argtypes = [vp, C.c_int]
+    L.qb200_sampler_exact_count.argtypes = [vp]
+    L.qb200_sampler_exact_count.restype = C.c_uint64
+    L.qb200_sampler_first_failing_word.argtypes = [vp, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -677,3 +693,161 @@ def diagonal_distribution_slice_import(file, ctx=None) -> Diagonal_Distribution_
 def _sequential_sum(v) -> np.longdouble:
     # the reference accumulates in index order in long double; np.cumsum does exactly that
     return np.cumsum(np.asarray(v, dtype=np.longdouble))[-1] if len(v) else np.longdouble(0)
+
+
+# --------------------------------------------------------------------------- #
+# Sampling from stored distributions: tau estimation      #
+# --------------------------------------------------------------------------- #
+
+@dataclass
+class Distribution:
+    """Distribution (src/distribution.h:55-85): the slices in walk order, the parameters' m and
+    the running totals distribution_insert_slice keeps (src/distribution.cpp:159-176)."""
+    m: int
+    slices: list = field(default_factory=list)
+    total_probability: np.longdouble = np.longdouble(0)
+    total_error: np.longdouble = np.longdouble(0)
+
+    def insert_slice(self, slice_):
+        self.slices.append(slice_)
+        self.total_probability = np.longdouble(self.total_probability + slice_.total_probability)
+        self.total_error = np.longdouble(self.total_error + slice_.total_error)
+
+    def sort_slices(self):
+        """distribution_sort_slices (src/distribution.cpp:258-270): descending total probability.
+        (qsort leaves the order of equal keys unspecified; this one is stable.)"""
+        self.slices.sort(key=lambda s: -s.total_probability)
+
+
+@dataclass
+class Linear_Distribution(Distribution):
+    """Linear_Distribution (src/linear_distribution.h)."""
+
+
+class Sampler:
+    """A distribution resident on the GPU (qb200_sampler)."""
+
+    def __init__(self, distribution, ctx: "Context" = None):
+        self.ctx = ctx or default_context()
+        sl = distribution.slices
+        linear = isinstance(distribution, Linear_Distribution) or (
+            len(sl) > 0 and isinstance(sl[0], Linear_Distribution_Slice))
+        self.dims = 1 if linear else 2
+        n = len(sl)
+        dim = np.array([x.dimension for x in sl], dtype=np.uint32)
+        if linear:
+            c0 = _i32([x.min_log_alpha for x in sl])
+            c1 = _i32(np.zeros(n))
+            cells = [np.ascontiguousarray(x.norm_vector, dtype=np.longdouble) for x in sl]
+        else:
+            c0 = _i32([x.min_log_alpha_d for x in sl])
+            c1 = _i32([x.min_log_alpha_r for x in sl])
+            cells = [np.ascontiguousarray(x.norm_matrix, dtype=np.longdouble) for x in sl]
+        ptrs = (C.c_void_p * max(1, n))(*[c.ctypes.data for c in cells])
+        totals = np.array([x.total_probability for x in sl], dtype=np.longdouble)
+        h = C.c_void_p()
+        _check(lib().qb200_sampler_create(self.ctx.h, self.dims, distribution.m, n, dim.ctypes.data,
+                                          c0.ctypes.data, c1.ctypes.data, ptrs, totals.ctypes.data,
+                                          C.c_longdouble(distribution.total_probability), C.byref(h)),
+               "qb200_sampler_create")
+        self.h = h
+        self.words_per_sample = int(lib().qb200_sampler_words_per_sample(h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().qb200_sampler_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_force_exact(self, on: bool):
+        lib().qb200_sampler_set_force_exact(self.h, 1 if on else 0)
+
+    @property
+    def exact_count(self) -> int:
+        return int(lib().qb200_sampler_exact_count(self.h))
+
+    def first_failing_word(self):
+        """Smallest slice-pivot word whose walk runs out of bounds, or None."""
+        w = C.c_uint64(0)
+        any_fail = lib().qb200_sampler_first_failing_word(self.h, C.byref(w))
+        return int(w.value) if any_fail else None
+
+    def sample(self, words):
+        """len(words) // words_per_sample independent samples: (slice, cell, x0, x1, status)."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        k = w.size // self.words_per_sample
+        sl = np.zeros(k, dtype=np.int32)
+        ce = np.zeros(k, dtype=np.int32)
+        x0 = np.zeros(k)
+        x1 = np.zeros(k)
+        st = np.zeros(k, dtype=np.int32)
+        _check(lib().qb200_sampler_sample(self.h, k, w.ctypes.data, sl.ctypes.data, ce.ctypes.data,
+                                          x0.ctypes.data, x1.ctypes.data, st.ctypes.data),
+               "qb200_sampler_sample")
+        return sl, ce, x0, x1, st
+
+    def tau_estimate(self, n: int, count: int, words):
+        """Up to `count` consecutive tau estimates of n samples on the word stream; returns
+        (tau0, tau1, ok, words_used) for the estimates completed."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        t0 = np.zeros(count, dtype=np.longdouble)
+        t1 = np.zeros(count, dtype=np.longdouble)
+        ok = np.zeros(count, dtype=np.uint8)
+        used = C.c_size_t(0)
+        done = C.c_uint32(0)
+        _check(lib().qb200_sampler_tau_estimate(self.h, n, count, w.ctypes.data, w.size, C.byref(used),
+                                                C.byref(done), t0.ctypes.data, t1.ctypes.data,
+                                                ok.ctypes.data), "qb200_sampler_tau_estimate")
+        d = int(done.value)
+        return t0[:d], t1[:d], ok[:d].astype(bool), int(used.value)
+
+    def tau_device(self, n: int, count: int, d_words_ptr: int, d_sums_ptr: int, d_status_ptr: int,
+                   stream: int = 0):
+        _check(lib().qb200_sampler_tau_device(self.h, n, count, d_words_ptr, d_sums_ptr, d_status_ptr,
+                                              stream), "qb200_sampler_tau_device")
+
+
+class WordStream:
+    """The random stream as the reference consumes it: consecutive 8-byte draws of a
+    Random_State (src/random.c:88-156), handed over as little-endian 64-bit words."""
+
+    def __init__(self, words):
+        self.words = np.ascontiguousarray(words, dtype=np.uint64)
+        self.pos = 0
+
+
+_samplers = {}
+
+
+def _sampler_for(distribution, ctx):
+    key = id(distribution)
+    s = _samplers.get(key)
+    if s is None or s[1] is not distribution or s[2] != len(distribution.slices):
+        s = (Sampler(distribution, ctx), distribution, len(distribution.slices))
+        _samplers[key] = s
+    return s[0]
+
+
+def tau_estimate(distribution, random_state: WordStream, n: int, ctx=None):
+    """tau_estimate (src/tau_estimate.cpp:23-87): returns (result, tau_d, tau_r)."""
+    s = _sampler_for(distribution, ctx)
+    t0, t1, ok, used = s.tau_estimate(n, 1, random_state.words[random_state.pos:])
+    if len(t0) == 0:
+        raise CriticalError("tau_estimate(): the random stream is exhausted")
+    random_state.pos += used
+    return bool(ok[0]), t0[0], t1[0]
+
+
+def tau_estimate_linear(distribution, random_state: WordStream, n: int, ctx=None):
+    """tau_estimate_linear (src/tau_estimate.cpp:89-133): returns (result, tau)."""
+    s = _sampler_for(distribution, ctx)
+    t0, _, ok, used = s.tau_estimate(n, 1, random_state.words[random_state.pos:])
+    if len(t0) == 0:
+        raise CriticalError("tau_estimate_linear(): the random stream is exhausted")
+    random_state.pos += used
+    return bool(ok[0]), t0[0]

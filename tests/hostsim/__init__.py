@@ -18,7 +18,8 @@ _SRCS = [os.path.join(_HERE, "hostsim.cpp"),
          os.path.join(_ROOT, "qunundrum_b200", "csrc", "text_tables.cpp")]
 _DEPS = _SRCS + [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
                  ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "sigma_opt.cuh", "plan.hpp",
-                  "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "textparse.cuh", "text_tables.hpp")]
+                  "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "textparse.cuh", "text_tables.hpp",
+                  "sampler.cuh", "x87soft.cuh")]
 _lib = None
 
 
@@ -149,3 +150,61 @@ def text_parse_ld(text: bytes, n: int, force_band=False):
     if rc:
         raise ValueError(rc)
     return v[:n], used.value, nx.value
+
+
+# ---- sampler twin (sampler.cuh / x87soft.cuh) -------------------------------------------------
+
+def x87_op(op: int, a, b):
+    """RN64 result of a (+, -, *) b through x87soft.cuh, as np.longdouble; None if unsupported."""
+    aa = np.array([a], dtype=np.longdouble)
+    bb = np.array([b], dtype=np.longdouble)
+    out = np.zeros(1, dtype=np.longdouble)
+    ok = lib().hostsim_x87_op(op, aa.ctypes.data_as(C.c_void_p), bb.ctypes.data_as(C.c_void_p),
+                              out.ctypes.data_as(C.c_void_p))
+    return out[0] if ok else None
+
+
+def x87_pivot(w: int):
+    out = np.zeros(1, dtype=np.longdouble)
+    hi, lo = C.c_double(0), C.c_double(0)
+    lib().hostsim_x87_pivot(C.c_uint64(w), out.ctypes.data_as(C.c_void_p), C.byref(hi), C.byref(lo))
+    return out[0], hi.value, lo.value
+
+
+class HostSampler:
+    """CPU twin of qb200_sampler: the same __host__ __device__ code, driven by plain loops."""
+
+    def __init__(self, dims, m, dimension, c0, c1, cells, totals, total):
+        self.dims = dims
+        n = len(dimension)
+        dim = np.ascontiguousarray(dimension, dtype=np.uint32)
+        a = np.ascontiguousarray(c0, dtype=np.int32)
+        b = np.ascontiguousarray(c1 if c1 is not None else np.zeros(n), dtype=np.int32)
+        cl = np.ascontiguousarray(cells, dtype=np.longdouble)
+        t = np.ascontiguousarray(totals, dtype=np.longdouble)
+        tt = np.array([total], dtype=np.longdouble)
+        L = lib()
+        L.hostsim_sampler_new.restype = C.c_void_p
+        self.h = C.c_void_p(L.hostsim_sampler_new(
+            dims, C.c_uint32(m), C.c_uint32(n), dim.ctypes.data_as(C.c_void_p),
+            a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), cl.ctypes.data_as(C.c_void_p),
+            t.ctypes.data_as(C.c_void_p), tt.ctypes.data_as(C.c_void_p)))
+
+    def bad(self) -> bool:
+        return bool(lib().hostsim_sampler_bad(self.h))
+
+    def sample(self, words, force_exact=False):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        k = w.size // (self.dims + 2)
+        out = np.zeros((k, 8))
+        st = np.zeros(k, dtype=np.int32)
+        ex = np.zeros(k, dtype=np.int32)
+        lib().hostsim_sampler_sample(self.h, C.c_uint32(k), w.ctypes.data_as(C.c_void_p),
+                                     1 if force_exact else 0, out.ctypes.data_as(C.c_void_p),
+                                     st.ctypes.data_as(C.c_void_p), ex.ctypes.data_as(C.c_void_p))
+        return out, st, ex
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().hostsim_sampler_free(self.h)
+            self.h = None

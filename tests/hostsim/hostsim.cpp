@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../qunundrum_b200/csrc/plan.hpp"
+#include "../../qunundrum_b200/csrc/sampler.cuh"
 
 using namespace qb200;
 
@@ -386,6 +387,148 @@ int hostsim_text_parse_ld(const char* textp, size_t len, size_t n, long double* 
   if (consumed) *consumed = pos;
   if (n_exact) *n_exact = slow;
   return 0;
+}
+
+// ---- sampler (sampler.cuh, x87soft.cuh) -----------------------------------------------------
+
+// op: 0 add, 1 sub, 2 mul; returns 0 if an operand is not representable (denormal / inf / nan).
+int hostsim_x87_op(int op, const long double* a, const long double* b, long double* out) {
+  RawX87 ra, rb;
+  memset(&ra, 0, 16);
+  memset(&rb, 0, 16);
+  memcpy(&ra, a, 10);
+  memcpy(&rb, b, 10);
+  bool ok = true;
+  X87 x = x87_load(&ra, &ok), y = x87_load(&rb, &ok);
+  if (!ok) return 0;
+  X87 r = op == 0 ? x87_add(x, y) : op == 1 ? x87_add(x, x87_neg(y)) : x87_mul(x, y);
+  memset(out, 0, 16);
+  if (r.mant) {
+    const int e = r.exp + 16383;
+    if (e <= 0 || e >= 0x7fff) return 0;
+    const uint16_t se = (uint16_t)(e | (r.neg << 15));
+    memcpy(out, &r.mant, 8);
+    memcpy((char*)out + 8, &se, 2);
+  }
+  return 1;
+}
+
+void hostsim_x87_pivot(uint64_t w, long double* out, double* dd_hi, double* dd_lo) {
+  const X87 r = x87_pivot_inclusive(w);
+  memset(out, 0, 16);
+  if (r.mant) {
+    const uint16_t se = (uint16_t)(r.exp + 16383);
+    memcpy(out, &r.mant, 8);
+    memcpy((char*)out + 8, &se, 2);
+  }
+  const dd v = x87_to_dd(r);
+  *dd_hi = v.hi;
+  *dd_lo = v.lo;
+}
+
+struct HostSampler {
+  std::vector<RawX87> cells, totals;
+  std::vector<SegCoarse> coarse;
+  std::vector<SamplerSlice> slices;
+  std::vector<dd> geo;
+  SamplerView view;
+  bool bad = false;
+};
+
+static void build_segment(const RawX87* v, uint32_t n, SegCoarse* coarse, double* abs_out, bool* bad) {
+  const uint32_t nb = (n + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK;
+  double ab = 0.0;
+  bool ok = true;
+  for (uint32_t b = 0; b < nb; b++) {
+    dd sum, maxp;
+    double a;
+    seg_block_summary(v, n, b, &sum, &maxp, &a, &ok);
+    coarse[b + 1].c = sum;
+    coarse[b + 1].m = maxp;
+    ab += a;
+  }
+  seg_scan(coarse, nb);
+  *abs_out = ab;
+  if (!ok) *bad = true;
+}
+
+void* hostsim_sampler_new(int dims, uint32_t m, uint32_t n_slices, const uint32_t* dimension,
+                          const int32_t* c0, const int32_t* c1, const long double* cells,
+                          const long double* slice_total, const long double* total) {
+  HostSampler* h = new HostSampler;
+  std::vector<std::pair<uint32_t, uint32_t>> geo_off;
+  uint64_t cell_off = 0, coarse_off = 0;
+  h->slices.resize(n_slices);
+  for (uint32_t i = 0; i < n_slices; i++) {
+    const uint32_t D = dimension[i];
+    uint32_t go = 0xffffffffu;
+    for (auto& g : geo_off)
+      if (g.first == D) go = g.second;
+    if (go == 0xffffffffu) {
+      go = (uint32_t)h->geo.size();
+      geo_off.emplace_back(D, go);
+      std::vector<DD> t((size_t)D + 1);
+      exp2_table_dd(D, t.data());
+      for (auto& e : t) h->geo.push_back(make_dd(e.hi, e.lo));
+    }
+    SamplerSlice& sl = h->slices[i];
+    sl.cell_off = cell_off;
+    sl.coarse_off = coarse_off;
+    sl.n_cells = dims == 2 ? D * D : D;
+    sl.D = D;
+    sl.c0 = c0[i];
+    sl.c1 = dims == 2 ? c1[i] : 0;
+    sl.geo_off = go;
+    sl.pad = 0;
+    sl.abs_sum = 0.0;
+    cell_off += sl.n_cells;
+    coarse_off += (sl.n_cells + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK + 1;
+  }
+  const uint64_t tco = coarse_off;
+  coarse_off += (n_slices + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK + 1;
+  h->cells.resize(cell_off);
+  memcpy(h->cells.data(), cells, cell_off * 16);
+  h->totals.resize(n_slices);
+  memcpy(h->totals.data(), slice_total, (size_t)n_slices * 16);
+  h->coarse.resize(coarse_off);
+  for (uint32_t i = 0; i < n_slices; i++)
+    build_segment(h->cells.data() + h->slices[i].cell_off, h->slices[i].n_cells,
+                  h->coarse.data() + h->slices[i].coarse_off, &h->slices[i].abs_sum, &h->bad);
+  SamplerView& v = h->view;
+  build_segment(h->totals.data(), n_slices, h->coarse.data() + tco, &v.totals_abs_sum, &h->bad);
+  v.cells = h->cells.data();
+  v.coarse = h->coarse.data();
+  v.slices = h->slices.data();
+  v.totals = h->totals.data();
+  v.totals_coarse = h->coarse.data() + tco;
+  v.geo = h->geo.data();
+  memset(&v.dist_total, 0, 16);
+  memcpy(&v.dist_total, total, 10);
+  v.n_slices = n_slices;
+  v.scale_by_total = *total > 1 ? 1 : 0;
+  v.m = (int)m;
+  v.dims = dims;
+  return h;
+}
+
+void hostsim_sampler_free(void* h) { delete (HostSampler*)h; }
+int hostsim_sampler_bad(void* h) { return ((HostSampler*)h)->bad ? 1 : 0; }
+
+// k samples, sample i from words[i * (dims + 2) ...]; out: k x 8 doubles
+// (sq0_hi, sq0_lo, sq1_hi, sq1_lo, x0, x1, slice, cell), status, exact.
+void hostsim_sampler_sample(void* hh, uint32_t k, const uint64_t* words, int force_exact, double* out,
+                            int32_t* status, int32_t* exact) {
+  HostSampler* h = (HostSampler*)hh;
+  const uint32_t wps = (uint32_t)h->view.dims + 2;
+  for (uint32_t i = 0; i < k; i++) {
+    SampleOut o;
+    sample_one(h->view, words + (size_t)i * wps, force_exact != 0, &o);
+    double* d = out + 8 * (size_t)i;
+    d[0] = o.sq0_hi; d[1] = o.sq0_lo; d[2] = o.sq1_hi; d[3] = o.sq1_lo;
+    d[4] = o.x0; d[5] = o.x1; d[6] = o.slice; d[7] = o.cell;
+    status[i] = o.status;
+    exact[i] = o.exact;
+  }
 }
 
 }  // extern "C"
