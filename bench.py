@@ -395,6 +395,136 @@ def text_section(ctx, qb, torch, stream, cells, hbm_peak):
     }
 
 
+def tau_section(ctx, qb, torch, stream, h_cells, tp, coords, hbm_peak, cpu_baseline=True):
+    """Sampling from the step's own distribution: the 3362 slices the
+    step computed plus their mirror images (what generate_distribution stores), sorted like
+    distribution_sort_slices; 2^16 tau estimates of n = 16 samples per timed call.
+    Rank 0, N = 1."""
+    import ctypes as C
+    n_slices = len(coords)
+    D = DIM
+    t0 = time.perf_counter()
+    dist = qb.Distribution(M)
+    LD = np.longdouble
+    for i, (a, b) in enumerate(coords):
+        cells = np.ascontiguousarray(h_cells[i], dtype=LD)   # widened as the drop-in does
+        total = LD(0)
+        for j in range(0, D * D, 4096):                       # (blocked: the order is immaterial here)
+            total += cells[j:j + 4096].sum(dtype=LD)
+        for sa, sb in ((a, b), (-a, -b)):                     # the server's mirrored copy
+            sl = qb.Distribution_Slice(D, int(sa), int(sb), norm_matrix=cells)
+            sl.total_probability = total
+            dist.insert_slice(sl)
+    dist.sort_slices()
+    t_host = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sampler = qb.Sampler(dist, ctx)
+    torch.cuda.synchronize()
+    t_create = time.perf_counter() - t0
+    wps = sampler.words_per_sample
+    n, count = 16, 1 << 16
+    total = n * count
+    g = torch.Generator(device="cuda")
+    g.manual_seed(20482048)
+    d_words = torch.randint(-2 ** 63, 2 ** 63 - 1, (total * wps,), dtype=torch.int64, device="cuda", generator=g)
+    d_sums = torch.zeros(count * 4, dtype=torch.float64, device="cuda")
+    d_status = torch.zeros(count, dtype=torch.int32, device="cuda")
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    reps = 10
+    l0 = ctx.launch_count
+
+    def run():
+        sampler.tau_device(n, count, d_words.data_ptr(), d_sums.data_ptr(), d_status.data_ptr(),
+                           stream.cuda_stream)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    launches = ctx.launch_count - l0
+    failed = int((d_status != 0).sum().item())
+    # end to end: host words in, long double taus out, through the C ABI
+    h_words = d_words.cpu().numpy().view(np.uint64)
+    sampler.tau_estimate(n, count, h_words)
+    t0 = time.perf_counter()
+    e2e_reps = 3
+    for _ in range(e2e_reps):
+        ta, tb, ok, used = sampler.tau_estimate(n, count, h_words)
+    wall = (time.perf_counter() - t0) / e2e_reps
+    done = len(ta)
+    # algorithmic bytes per sample: two searches (ceil(log2(blocks)) coarse entries of 32 B and
+    # on average half a block of 32 x 16 B each), the words in, 64 B out
+    import math
+    blocks_s = math.ceil(len(dist.slices) / 32)
+    blocks_c = D * D // 32
+    bytes_per_sample = (math.ceil(math.log2(blocks_s)) + math.ceil(math.log2(blocks_c))) * 32 + 2 * 256 \
+        + wps * 8 + 64
+    gbs = total * bytes_per_sample / (ms * 1e-3) / 1e9
+    out = {
+        "workload": (f"tau_estimate on the step's own distribution: {len(dist.slices)} slices "
+                     f"({n_slices} computed + mirrored) x {D * D} cells = {sampler_cells(sampler)} cells "
+                     f"resident ({sampler_cells(sampler) * 16 / 1e9:.2f} GB x87 + coarse index); "
+                     f"{count} estimates of n = {n} samples per call"),
+        "samples_per_call": total,
+        "value": total / (ms * 1e-3), "unit": "samples/s", "ms": ms,
+        "out_of_bounds_estimates": failed,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                     "traffic": None, "bytes_per_sample": bytes_per_sample, "kernel": "k_sample",
+                     "limiter": "dependent random reads (two binary searches per sample): latency, not bandwidth"},
+        "e2e": {"value": done * n / wall, "unit": "samples/s", "h2d_bytes_per_step": int(used * 8 + done * 8),
+                "d2h_bytes_per_step": int(done * 36), "ms": wall * 1e3,
+                "api": "qb200_sampler_tau_estimate (host words in, long double taus out)"},
+        "setup": {"host_containers_s": t_host, "sampler_create_s": t_create,
+                  "note": "once per distribution: upload of the cells as they lie in the slices + k_seg_build"},
+        "gpu_launches": int(launches),
+    }
+    if cpu_baseline:
+        try:
+            from oracle import ref             # checker + CPU baseline only
+            if ref.available():
+                d, r = synthetic_d_r(20482048)
+                RP = ref.RefParameters(M, S, d, r)
+                order = dist.slices
+                rd = ref.RefDistribution(2, RP, [s.dimension for s in order],
+                                         [s.min_log_alpha_d for s in order],
+                                         [s.min_log_alpha_r for s in order],
+                                         np.concatenate([s.norm_matrix for s in order]),
+                                         [s.total_probability for s in order])
+                seed = bytes(range(32))
+                k = 2000
+                t0 = time.perf_counter()
+                r0, r1, rok = rd.tau_estimate(ref.RefRandom(seed), n, k)
+                w = time.perf_counter() - t0
+                words = ref.RefRandom(seed).words(k * n * wps)
+                g0, g1, gok, _ = sampler.tau_estimate(n, k, words)
+                same = bool((gok == rok).all())
+                err = float(max(np.abs(g0[rok] - r0[rok]).max(), np.abs(g1[rok] - r1[rok]).max())) if rok.any() else 0.0
+                out["cpu_baseline"] = {"value": k * n / w, "unit": "samples/s", "cores": 1, "kind": "reference",
+                                       "sample": (f"{k} calls of the reference's tau_estimate (n = {n}) on the same "
+                                                  f"distribution, its own Keccak stream, {w:.1f} s")}
+                out["parity"] = (f"{k} estimates on the reference's stream: success flags identical: {same}; "
+                                 f"max |tau - tau_ref| = {err:.2e}")
+                if not same or err > 2.0 ** -63 * (2 * M + 16):
+                    raise SystemExit("bench.py: tau estimates differ from the reference's")
+        except SystemExit:
+            raise
+        except Exception as exc:  # pragma: no cover
+            out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference",
+                                   "sample": f"failed: {exc}"}
+    sampler.close()
+    return out
+
+
+def sampler_cells(sampler):
+    import qunundrum_b200 as qb
+    return int(qb.lib().qb200_sampler_cells(sampler.h))
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import qunundrum_b200 as qb
@@ -531,6 +661,15 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": None, "unit": "cells/s", "cores": 0, "kind": "reference",
                    "sample": f"failed: {exc}"}
 
+    tau = None
+    if world == 1 and not args.no_tau:
+        try:
+            hbm_peak_tau = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak_tau = 6650.0
+        tau = tau_section(ctx, qb, torch, stream, h_cells, tp2, coords, hbm_peak_tau,
+                          cpu_baseline=not args.no_cpu_baseline)
+
     L.qb200_host_free(C.c_void_p(hptr))
     if dist is not None:
         dist.barrier()
@@ -577,6 +716,7 @@ def run_ours(args, rank, world, local_rank):
             },
             "cpu_baseline": cpu,
             "text": text,
+            "tau": tau,
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "ms_per_step": wall / e2e_steps * 1e3,
@@ -603,6 +743,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text", action="store_true")
+    ap.add_argument("--no-tau", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -620,6 +761,8 @@ def main():
             cmd.append("--no-cpu-baseline")
         if args.no_text:
             cmd.append("--no-text")
+        if args.no_tau:
+            cmd.append("--no-tau")
         raise SystemExit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

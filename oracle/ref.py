@@ -84,6 +84,8 @@ def lib():
     L.qref_dist_new.restype = vp
     L.qref_dist_free.argtypes = [vp]
     L.qref_dist_sort.argtypes = [vp]
+    L.qref_dist_ptr.argtypes = [vp]
+    L.qref_dist_ptr.restype = vp
     L.qref_dist_describe.argtypes = [vp, vp, vp, vp, ldp, ldp]
     L.qref_dist_set_total.argtypes = [vp, C.c_longdouble]
     L.qref_random_new.argtypes = [cp]
@@ -298,6 +300,10 @@ class RefDistribution:
 
     def sort(self):
         lib().qref_dist_sort(self.h)
+
+    def ptr(self) -> int:
+        """Distribution * / Linear_Distribution * (the reference's own struct)."""
+        return lib().qref_dist_ptr(self.h)
 
     def set_total(self, total):
         lib().qref_dist_set_total(self.h, np.longdouble(total))

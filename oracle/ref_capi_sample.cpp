@@ -105,6 +105,13 @@ void qref_dist_free(void *hh) {
   free(h);
 }
 
+/* The reference's own container (Distribution * or Linear_Distribution *), to hand to code
+ * that takes the reference's types (the drop-in translation unit under test). */
+void *qref_dist_ptr(void *hh) {
+  Dist *h = (Dist *)hh;
+  return h->dims == 2 ? (void *)&h->d2 : (void *)&h->d1;
+}
+
 void qref_dist_sort(void *hh) {
   Dist *h = (Dist *)hh;
   if (h->dims == 2)

@@ -1,11 +1,13 @@
-"""Compile-test of the reference-side forwarding TU (dropin.cpp).
+"""Compile-test of the reference-side forwarding TUs (dropin.cpp: the six integrators;
+dropin_tau.cpp: tau_estimate / tau_estimate_linear).
 
 Needs the reference's headers (/root/reference/src, used in place, never copied)
 and -- only because this image lacks libgmp-dev -- the declaration shim
 integration/shims/gmp.h. Output: qunundrum_b200/dropin/libqunundrum_dropin.so, which
 exports the six C++ entry points of the reference with their mangled names and
 depends on ../libqunundrum_b200.so and libgmp. It also compiles the reference's
-src/errors.c (critical()) in place so that the test library is self-contained.
+src/errors.c (critical()) and generator (src/random.c, src/keccak*.c) in place so that the
+test library is self-contained.
 """
 from __future__ import annotations
 
@@ -22,21 +24,28 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> str |
     src = os.path.join(reference_root, "src")
     if not os.path.isdir(src):
         return LIB if os.path.exists(LIB) else None
-    deps = [os.path.join(HERE, "dropin.cpp"), os.path.join(ROOT, "include", "qunundrum_b200.h")]
+    deps = [os.path.join(HERE, "dropin.cpp"), os.path.join(HERE, "dropin_tau.cpp"),
+            os.path.join(ROOT, "include", "qunundrum_b200.h"), os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(
             os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     gmp = "/lib/x86_64-linux-gnu/libgmp.so.10"
-    obj = os.path.join(HERE, "_errors.o")
-    subprocess.check_call(["gcc", "-O2", "-fPIC", "-w", "-iquote", src, "-c",
-                           os.path.join(src, "errors.c"), "-o", obj])
+    # the reference's own errors.c (critical()) and generator (random_generate(), which
+    # dropin_tau.cpp draws the caller's stream with), compiled where they lie
+    objs = []
+    for f in ("errors", "random", "keccak", "keccak_random", "debug_common"):
+        o = os.path.join(HERE, f"_{f}.o")
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-w", "-I", os.path.join(ROOT, "integration", "shims"),
+                               "-iquote", src, "-c", os.path.join(src, f + ".c"), "-o", o])
+        objs.append(o)
     subprocess.check_call(
         ["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-w",
          "-I", os.path.join(ROOT, "integration", "shims"), "-I", os.path.join(ROOT, "integration", "minimpi"),
-         "-I", os.path.join(ROOT, "include"),
-         "-iquote", src, os.path.join(HERE, "dropin.cpp"), obj,
+         "-I", os.path.join(ROOT, "integration", "stubs"), "-I", os.path.join(ROOT, "include"),
+         "-iquote", src, os.path.join(HERE, "dropin.cpp"), os.path.join(HERE, "dropin_tau.cpp"), *objs,
          "-o", LIB, "-L", PKG, "-lqunundrum_b200", "-Wl,-rpath,$ORIGIN/..", gmp])
-    os.remove(obj)
+    for o in objs:
+        os.remove(o)
     return LIB
 
 

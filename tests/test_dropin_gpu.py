@@ -88,3 +88,75 @@ def test_dropin_called_like_the_reference():
     h(C.byref(ds), RDP.h, 126, -2)
     R = ref.diagonal_distribution_slice_compute(RDP, 64, 126, -2)
     assert cell_errors(vec, R.cells) <= CELL_RTOL and ds.eta == -2 and ds.min_log_alpha_r == 126
+
+
+SYM_TAU = "_Z12tau_estimatePK12DistributionP12Random_StatejReS4_"
+SYM_TAU_LINEAR = "_Z19tau_estimate_linearPK19Linear_DistributionP12Random_StatejRe"
+
+
+def test_dropin_exports_the_tau_symbols():
+    if not os.path.exists(DROPIN):
+        pytest.skip("drop-in not built (needs the reference headers at build time)")
+    out = subprocess.run(["nm", "-D", "--defined-only", DROPIN], capture_output=True, text=True).stdout
+    assert SYM_TAU in out and SYM_TAU_LINEAR in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["2d", "lin"])
+def test_tau_dropin_called_like_the_reference(name):
+    """dropin_tau.cpp on the reference's own Distribution / Random_State structs (built by the
+    reference's functions in oracle/_ref): for the same generator seed, the sequence of
+    tau_estimate() calls an estimate_runs client makes returns what the reference's
+    tau_estimate() returns -- across batch boundaries (QB200_TAU_BATCH = 64 here, 150 calls) and
+    across a change of n -- and leaves the generator where the reference leaves it."""
+    ref = ref_or_none()
+    if ref is None or not os.path.exists(DROPIN):
+        pytest.skip("needs oracle/_ref and the built drop-in")
+    from tests.test_sampler import GOLD, Gold, assert_tau
+    g = Gold(np.load(GOLD), name)
+    os.environ["QB200_DEVICE"] = "0"
+    os.environ["QB200_TAU_BATCH"] = "64"
+    L = C.CDLL(DROPIN, mode=os.RTLD_LOCAL)
+    d, r = ref.deterministic_d_r(g.m)
+    P = ref.RefParameters(g.m, 2, d, r)
+    dist = ref.RefDistribution(g.dims, P, g.dimension, g.c0, g.c1, g.cells, g.totals)
+    seed = bytes(range(50, 82))
+    if g.dims == 2:
+        f = getattr(L, SYM_TAU)
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    else:
+        f = getattr(L, SYM_TAU_LINEAR)
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    f.restype = C.c_bool
+    rs_gpu, rs_ref = ref.RefRandom(seed), ref.RefRandom(seed)
+    # 128 = two full batches of n = 3, then two full batches of n = 5: the generator must end
+    # where the reference's ends
+    for n, calls in ((3, 128), (5, 128)):
+        want0, want1, want_ok = dist.tau_estimate(rs_ref, n, calls)
+        for i in range(calls):
+            t0 = np.zeros(1, dtype=np.longdouble)
+            t1 = np.zeros(1, dtype=np.longdouble)
+            if g.dims == 2:
+                ok = f(dist.ptr(), rs_gpu.h, n, t0.ctypes.data, t1.ctypes.data)
+            else:
+                ok = f(dist.ptr(), rs_gpu.h, n, t0.ctypes.data)
+            assert bool(ok) == bool(want_ok[i]), (n, i)
+            if ok:
+                assert_tau(t0[0], want0[i], g.m)
+                if g.dims == 2:
+                    assert_tau(t1[0], want1[i], g.m)
+            else:
+                assert float(t0[0]) == np.finfo(np.float64).max
+    # words queued by the drop-in (estimates that failed early) are still in front of the
+    # generator: after one more batch-aligned round both streams are in step again only if the
+    # drop-in consumed exactly what the reference consumed. Check through the next estimates.
+    want0, _, want_ok = dist.tau_estimate(rs_ref, 2, 64)
+    for i in range(64):
+        t0 = np.zeros(1, dtype=np.longdouble)
+        t1 = np.zeros(1, dtype=np.longdouble)
+        ok = f(dist.ptr(), rs_gpu.h, 2, t0.ctypes.data, t1.ctypes.data) if g.dims == 2 else \
+            f(dist.ptr(), rs_gpu.h, 2, t0.ctypes.data)
+        assert bool(ok) == bool(want_ok[i])
+        if ok:
+            assert_tau(t0[0], want0[i], g.m)
+    os.environ.pop("QB200_TAU_BATCH", None)
