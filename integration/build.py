@@ -7,7 +7,10 @@
                                       + libqunundrum_b200.so
 
 plus, in both flavours, the importing executables filter_distribution, info_distribution and
-compare_[linear_|diagonal_]distributions (they load stored distributions: the importer path).
+compare_[linear_|diagonal_]distributions (they load stored distributions: the importer path), and
+estimate_runs_distribution / estimate_runs_linear_distribution (gpu flavour: tau_estimate and
+tau_estimate_linear from qunundrum_b200/dropin/dropin_tau.cpp; the reference's tau_estimate.cpp
+stays for tau_estimate_diagonal, compiled with two -D renames).
 
 INTEGRATION-TEST INFRASTRUCTURE. Sources are compiled where they lie under /root/reference/src
 (never copied); neither OpenMPI nor fpLLL nor the GMP/MPFR development headers exist in this
@@ -35,13 +38,19 @@ COMMON_CPP = """math rsa parameters diagonal_parameters parameters_selection sam
  linear_distribution linear_distribution_enumerator linear_distribution_info linear_distribution_mpi
  linear_distribution_slice linear_distribution_slice_mpi
  diagonal_distribution diagonal_distribution_enumerator diagonal_distribution_info
- diagonal_distribution_mpi diagonal_distribution_slice diagonal_distribution_slice_mpi""".split()
+ diagonal_distribution_mpi diagonal_distribution_slice diagonal_distribution_slice_mpi
+ distribution_loader linear_distribution_loader tau_ordered_list tau_volume_quotient log""".split()
 TEXT_IO = """distribution_slice_import_export linear_distribution_slice_import_export
  diagonal_distribution_slice_import_export""".split()
 COMMON_C = "errors random keccak keccak_random gmp_mpi mpfr_mpi string_utilities thread_pool debug_common".split()
 INTEGRATORS = """distribution_slice_compute distribution_slice_compute_richardson
  linear_distribution_slice_compute linear_distribution_slice_compute_richardson
  diagonal_distribution_slice_compute diagonal_distribution_slice_compute_richardson""".split()
+# tau_estimate.cpp: as it is in the "ref" flavour; in the "gpu" flavour compiled with two renames
+# (tau_estimate_diagonal stays the reference's) next to qunundrum_b200/dropin/dropin_tau.cpp
+TAU = ["tau_estimate"]
+TAU_RENAMES = ["-Dtau_estimate=tau_estimate_cpu_unused", "-Dtau_estimate_linear=tau_estimate_linear_cpu_unused"]
+ESTIMATORS = ["estimate_runs_distribution", "estimate_runs_linear_distribution"]
 MAINS = ["generate_distribution", "generate_linear_distribution", "generate_linear_distribution_rsa",
          "generate_diagonal_distribution", "filter_distribution", "info_distribution",
          "compare_distributions", "compare_linear_distributions", "compare_diagonal_distributions"]
@@ -54,6 +63,7 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
         return os.path.exists(done)
     deps = [os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin.cpp"),
             os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
+            os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau.cpp"),
             os.path.join(HERE, "minimpi", "minimpi.c"), os.path.join(HERE, "minimpi", "mpi.h"),
             os.path.join(HERE, "build.py"), os.path.join(ROOT, "include", "qunundrum_b200.h"),
             ]
@@ -67,7 +77,7 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
            "-I", os.path.join(HERE, "shims"), "-I", os.path.join(ROOT, "include"),
            "-iquote", src]
     jobs = []
-    for f in COMMON_CPP + INTEGRATORS + TEXT_IO + ["main_" + m for m in MAINS]:
+    for f in COMMON_CPP + INTEGRATORS + TEXT_IO + TAU + ["main_" + m for m in MAINS + ESTIMATORS]:
         jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *inc, "-c",
                      os.path.join(src, f + ".cpp"), "-o", os.path.join(obj, f + ".o")])
     for f in COMMON_C:
@@ -81,6 +91,11 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
                  os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
                  "-o", os.path.join(obj, "dropin_text.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *TAU_RENAMES, *inc, "-c",
+                 os.path.join(src, "tau_estimate.cpp"), "-o", os.path.join(obj, "tau_estimate_renamed.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
+                 os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau.cpp"),
+                 "-o", os.path.join(obj, "dropin_tau.o")])
     jobs.append(["gcc", "-O2", "-c", os.path.join(HERE, "minimpi", "minimpi.c"),
                  "-o", os.path.join(obj, "minimpi.o")])
     with ThreadPoolExecutor(8) as ex:
@@ -95,6 +110,19 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
                                *[os.path.join(obj, f + ".o") for f in INTEGRATORS + TEXT_IO],
                                *libs, "-o", os.path.join(OUT, "ref", m)])
         subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "dropin.o"),
+                               os.path.join(obj, "dropin_text.o"),
+                               "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
+                               "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
+                               "-o", os.path.join(OUT, "gpu", m)])
+    # estimate_runs_*: the reference's tau estimators (ref) against dropin_tau.cpp (gpu); the
+    # integrators and the text format are the same drop-ins as above in the gpu flavour
+    for m in ESTIMATORS:
+        main_o = os.path.join(obj, "main_" + m + ".o")
+        subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "tau_estimate.o"),
+                               *[os.path.join(obj, f + ".o") for f in INTEGRATORS + TEXT_IO],
+                               *libs, "-o", os.path.join(OUT, "ref", m)])
+        subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "tau_estimate_renamed.o"),
+                               os.path.join(obj, "dropin_tau.o"), os.path.join(obj, "dropin.o"),
                                os.path.join(obj, "dropin_text.o"),
                                "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
                                "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,

@@ -92,6 +92,7 @@ void mpfr_set_inf(mpfr_ptr, int);
 void mpfr_set_nan(mpfr_ptr);
 void mpfr_set_zero(mpfr_ptr, int);
 int mpfr_printf(const char *, ...);
+#define mpfr_fprintf __gmpfr_fprintf /* as <mpfr.h> does: the library exports the prefixed name */
 int mpfr_fprintf(FILE *, const char *, ...);
 int mpfr_sprintf(char *, const char *, ...);
 int mpfr_snprintf(char *, size_t, const char *, ...);
@@ -100,6 +101,8 @@ int mpfr_sin(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);
 int mpfr_cos(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);
 int mpfr_exp2(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);
 int mpfr_log2(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);
+int mpfr_gamma(mpfr_ptr, mpfr_srcptr, mpfr_rnd_t);
+int mpfr_pow(mpfr_ptr, mpfr_srcptr, mpfr_srcptr, mpfr_rnd_t);
 int mpfr_const_pi(mpfr_ptr, mpfr_rnd_t);
 int mpfr_const_catalan(mpfr_ptr, mpfr_rnd_t);
 

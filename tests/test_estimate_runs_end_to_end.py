@@ -1,0 +1,90 @@
+"""The reference's own estimate_runs_distribution / estimate_runs_linear_distribution executables
+(argv parsing, distribution loader, MPI farm, ordered tau lists, volume quotients, logs) with
+tau_estimate / tau_estimate_linear coming from qunundrum_b200/dropin/dropin_tau.cpp, against
+the same executables with the reference's tau_estimate.cpp.
+
+Every client seeds its generator from /dev/urandom (src/keccak_random.h:42), so two runs of the
+REFERENCE do not print the same digits either; what is pinned bit for bit for a given seed is in
+tests/test_sampler.py and tests/test_dropin_gpu.py. Here the statistics must agree: the same
+sequence of tried n and the same final n, and the 99 % quantiles tau_d / tau_r (10^6 estimates
+each) within 0.02 -- twice the spread between two reference runs."""
+import os
+import re
+import subprocess
+import tempfile
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+B = os.path.join(ROOT, "integration", "_build")
+# two-dimensional: "m: 64 s: 2 n: 4 -- tau_d 10.66 v_d: 0.10 <0> -- tau_r: 6.69 v_r: 1.1E-07 <0>"
+# linear:          "m: 128 s: 2 n: 3 -- tau: 4.52 v: 0.01 <0>"
+LINE = re.compile(r"m: (\d+) [sl]: (\d+) n: (\d+) -- tau(?:_d)?:? ([-\d.]+) v(?:_d)?: (\S+) <(\d+)>"
+                  r"(?: -- tau_r: ([-\d.]+) v_r: (\S+) <(\d+)>)?")
+
+
+def _have():
+    return os.path.exists(os.path.join(B, "gpu", "estimate_runs_distribution"))
+
+
+def _mpirun(flavour, exe, args, np_, cwd, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    t0 = time.perf_counter()
+    p = subprocess.run([os.path.join(B, "minimpirun"), "-np", str(np_), os.path.join(B, flavour, exe), *args],
+                       cwd=cwd, env=e, capture_output=True, text=True, timeout=3000)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout, time.perf_counter() - t0
+
+
+def _log_lines(cwd):
+    out = []
+    logs = os.path.join(cwd, "logs")     # estimate-runs.txt / estimate-runs-linear.txt
+    for f in sorted(os.listdir(logs)):
+        for line in open(os.path.join(logs, f)):
+            m = LINE.search(line)
+            if m:
+                out.append(m.groups())
+    return out
+
+
+CASES = [
+    ("generate_distribution", ["-det", "-dim", "32", "64", "2"], "estimate_runs_distribution",
+     "distribution-det-dim-32-sigma-heuristic-m-64-s-2.txt"),
+    ("generate_linear_distribution", ["-d", "-det", "-dim", "256", "128", "2"], "estimate_runs_linear_distribution",
+     "linear-distribution-det-dim-256-d-m-128-s-2.txt"),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gen,gen_args,exe,name", CASES, ids=["2d", "linear"])
+def test_estimate_runs_with_the_tau_dropin_matches_the_reference(gen, gen_args, exe, name):
+    if not _have():
+        pytest.skip("integration/_build missing (needs /root/reference at build time)")
+    cores = max(2, min(16, os.cpu_count() or 2))
+    with tempfile.TemporaryDirectory() as t:
+        os.makedirs(os.path.join(t, "distributions"))
+        _mpirun("gpu", gen, gen_args, 3, t, {"QB200_DEVICE": "0"})
+        path = os.path.join("distributions", name)
+        assert os.path.exists(os.path.join(t, path))
+        runs = {}
+        for flavour, np_ in (("ref", cores + 1), ("gpu", 3)):
+            cwd = os.path.join(t, flavour)
+            os.makedirs(cwd)
+            os.symlink(os.path.join(t, "distributions"), os.path.join(cwd, "distributions"))
+            _, wall = _mpirun(flavour, exe, [path], np_, cwd, {"QB200_DEVICE": "0", "QB200_TEXT_DEVICE": "0"})
+            runs[flavour] = (_log_lines(cwd), wall)
+        ref, gpu = runs["ref"][0], runs["gpu"][0]
+        print(f"\n{exe}: reference {runs['ref'][1]:.1f} s on {cores} client cores, "
+              f"drop-in {runs['gpu'][1]:.1f} s with 2 client ranks on one GPU")
+        for a, b in zip(ref, gpu):
+            print("  ref", a, "\n  gpu", b)
+        assert len(ref) == len(gpu) and len(ref) >= 2
+        for a, b in zip(ref, gpu):
+            assert a[:3] == b[:3]                                   # m, s, n: the same search path
+            assert abs(float(a[3]) - float(b[3])) <= 0.02           # tau_d (tau) quantile
+            ea, eb = int(a[5]), int(b[5])                           # estimates with a sampling error
+            assert abs(ea - eb) <= 5 * max(ea, eb) ** 0.5 + 5
+            if a[6] is not None:
+                assert abs(float(a[6]) - float(b[6])) <= 0.02       # tau_r quantile
