@@ -28,6 +28,14 @@
 //     unused estimates are dropped: the results remain correct samples, but the stream position
 //     then differs from the reference's (never the case in the reference's executables with the
 //     default batch).
+//   * the generator itself. The reference's Keccak sponge (src/keccak_random.c:96-125: one
+//     keccak_f per 168 bytes, bytes taken one at a time, most significant first) delivers
+//     48 MB/s, which would cap a client rank at 1.5e6 samples/s. draw_words() below produces the
+//     SAME bytes from the SAME Keccak_Random_State (its lanes and offset are advanced exactly
+//     as the reference would advance them) with an unrolled permutation and whole-lane
+//     extraction; tests compare megabytes of both streams. QB200_TAU_REFERENCE_RNG=1 switches
+//     back to random_generate(); a device-backed Random_State (random_init_device) and a state
+//     left in mid-lane by other draws always go through random_generate().
 //   * errors are fatal: critical() (src/errors.c).
 #include "common.h"
 #include "distribution.h"
@@ -35,6 +43,8 @@
 #include "errors.h"
 #include "linear_distribution.h"
 #include "linear_distribution_slice.h"
+#include "keccak.h"
+#include "keccak_random.h"
 #include "random.h"
 #include "tau_estimate.h"
 
@@ -147,6 +157,75 @@ uint64_t fingerprint(const SliceList& l) {
   return h;
 }
 
+// ---- the reference's random stream, faster ----------------------------------------------------
+
+inline uint64_t rotl64(uint64_t x, unsigned n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+
+// Keccak-f[1600] (FIPS 202 section 3), lanes[x + 5 y]; the same permutation as the reference's
+// keccak_f (src/keccak.c:47-108), written with the rho offsets and pi destinations as tables
+// so that the compiler unrolls each step.
+void keccak_f1600(uint64_t* a) {
+  static const uint64_t rc[24] = {
+      0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+      0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+      0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+      0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+      0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+  static const unsigned rho[25] = {0,  1,  62, 28, 27, 36, 44, 6,  55, 20, 3,  10, 43,
+                                   25, 39, 41, 45, 15, 21, 8,  18, 2,  61, 56, 14};
+  uint64_t b[25], c[5], d[5];
+  for (int round = 0; round < 24; round++) {
+#pragma GCC unroll 5
+    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma GCC unroll 5
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma GCC unroll 25
+    for (int i = 0; i < 25; i++) {
+      const int x = i % 5, y = i / 5;
+      b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(a[i] ^ d[x], rho[i]);
+    }
+#pragma GCC unroll 25
+    for (int i = 0; i < 25; i++) {
+      const int x = i % 5, j = i - x;
+      a[i] = b[i] ^ (~b[j + (x + 1) % 5] & b[j + (x + 2) % 5]);
+    }
+    a[0] ^= rc[round];
+  }
+}
+
+// n consecutive 8-byte draws of random_generate() (src/random.c:88-114), as the little-endian
+// words random_generate_pivot_*() would read them.
+void draw_words(Random_State* rs, uint64_t* dst, size_t n, bool use_reference) {
+  random_generate(dst, 0, rs);  // the reference's initialisation check (canary), no bytes
+  Keccak_Random_State* const k = &rs->keccak_state;
+  if (use_reference || NULL != rs->random_device || 0 != (k->offset % 8) ||
+      k->offset > 8 * KECCAK_LANE_COUNT) {
+    while (n) {  // random_generate() takes a 32-bit byte count
+      const size_t t = n < (size_t)(1u << 27) ? n : (size_t)(1u << 27);
+      random_generate(dst, (uint32_t)(8 * t), rs);
+      dst += t;
+      n -= t;
+    }
+    return;
+  }
+  uint32_t offset = k->offset;
+  while (n) {
+    if (offset >= 8 * KECCAK_LANE_COUNT) {  // src/keccak_random.c:108-111
+      keccak_f1600(k->lanes);
+      offset = KECCAK_RANDOM_SEED_LENGTH;
+    }
+    size_t take = (8 * KECCAK_LANE_COUNT - offset) / 8;
+    if (take > n) take = n;
+    const uint64_t* lane = k->lanes + offset / 8;
+    for (size_t i = 0; i < take; i++) dst[i] = __builtin_bswap64(lane[i]);  // most significant byte first
+    dst += take;
+    n -= take;
+    offset += (uint32_t)(8 * take);
+  }
+  k->offset = offset;
+}
+
 struct State {
   const void* distribution = NULL;
   const void* slices = NULL;
@@ -212,12 +291,7 @@ bool estimate(const Dist* distribution, Random_State* rs, uint32_t n, long doubl
   if (g.fifo.size() < need) {
     const size_t have = g.fifo.size();
     g.fifo.resize(need);
-    size_t at = have;
-    while (at < need) {  // random_generate() takes a 32-bit byte count
-      const size_t k = (need - at) < (size_t)(1u << 27) ? (need - at) : (size_t)(1u << 27);
-      random_generate(&g.fifo[at], (uint32_t)(8 * k), rs);
-      at += k;
-    }
+    draw_words(rs, &g.fifo[have], need - have, env_int("QB200_TAU_REFERENCE_RNG", 0) != 0);
   }
   g.tau0.assign(batch, 0);
   g.tau1.assign(batch, 0);
@@ -242,6 +316,12 @@ bool estimate(const Dist* distribution, Random_State* rs, uint32_t n, long doubl
 }
 
 }  // namespace
+
+// Test hook: n draws through either path (tests compare the two streams and the states they leave).
+extern "C" void qb200_dropin_tau_draw(Random_State* random_state, uint64_t* dst, size_t n,
+                                      int use_reference) {
+  draw_words(random_state, dst, n, use_reference != 0);
+}
 
 bool tau_estimate(const Distribution* const distribution, Random_State* const random_state,
                   const uint32_t n, long double& tau_d, long double& tau_r) {

@@ -160,3 +160,40 @@ def test_tau_dropin_called_like_the_reference(name):
         if ok:
             assert_tau(t0[0], want0[i], g.m)
     os.environ.pop("QB200_TAU_BATCH", None)
+
+
+def test_tau_dropin_draws_the_reference_stream():
+    """draw_words() of dropin_tau.cpp (unrolled Keccak-f[1600], whole-lane extraction) against the
+    reference's random_generate() (src/random.c:88, src/keccak_random.c:96) on the reference's own
+    Random_State: the same bytes, and the same state afterwards (the next draws of the
+    reference's generator agree), for lengths around the 21-lane block boundary, for a state
+    left in mid-lane by a 3-byte draw (falls back to the reference), and for 2^18 words.
+    Host code only: runs without a GPU."""
+    ref = ref_or_none()
+    if ref is None or not os.path.exists(DROPIN):
+        pytest.skip("needs oracle/_ref and the built drop-in")
+    L = C.CDLL(DROPIN, mode=os.RTLD_LOCAL)
+    f = L.qb200_dropin_tau_draw
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    f.restype = None
+    seed = bytes((11 * i + 1) & 0xff for i in range(32))
+    for pre_bytes in (0, 8, 3):
+        for n in (1, 20, 21, 22, 41, 42, 43, 1000, 1 << 18):
+            a, b = ref.RefRandom(seed), ref.RefRandom(seed)
+            if pre_bytes:
+                a.bytes(pre_bytes)
+                b.bytes(pre_bytes)
+            x = np.zeros(n, dtype=np.uint64)
+            y = np.zeros(n, dtype=np.uint64)
+            f(a.h, x.ctypes.data, n, 0)
+            f(b.h, y.ctypes.data, n, 1)
+            assert (x == y).all(), (pre_bytes, n)
+            assert a.bytes(300) == b.bytes(300), (pre_bytes, n)     # the states are in step
+    # several consecutive fast draws == one reference draw
+    a, b = ref.RefRandom(seed), ref.RefRandom(seed)
+    parts = []
+    for n in (5, 16, 1, 100, 21, 64):
+        x = np.zeros(n, dtype=np.uint64)
+        f(a.h, x.ctypes.data, n, 0)
+        parts.append(x)
+    assert (np.concatenate(parts) == b.words(207)).all()
