@@ -6,8 +6,10 @@ the same executables with the reference's tau_estimate.cpp.
 Every client seeds its generator from /dev/urandom (src/keccak_random.h:42), so two runs of the
 REFERENCE do not print the same digits either; what is pinned bit for bit for a given seed is in
 tests/test_sampler.py and tests/test_dropin_gpu.py. Here the statistics must agree: the same
-sequence of tried n and the same final n, and the 99 % quantiles tau_d / tau_r (10^6 estimates
-each) within 0.02 -- twice the spread between two reference runs."""
+sequence of tried n and the same final n, and the quantiles tau_d / tau_r (10^6 estimates each)
+within 0.05. Measured spread between runs of the REFERENCE itself on these inputs: 0.006 for the
+two-dimensional case (10.9606 ... 10.9611), 0.028 for the linear one (n = 2: 4.7815, 4.8026,
+4.8078, 4.8095; the drop-in gave 4.8045), and 162 ... 209 failing estimates per 10^6."""
 import os
 import re
 import subprocess
@@ -83,8 +85,8 @@ def test_estimate_runs_with_the_tau_dropin_matches_the_reference(gen, gen_args, 
         assert len(ref) == len(gpu) and len(ref) >= 2
         for a, b in zip(ref, gpu):
             assert a[:3] == b[:3]                                   # m, s, n: the same search path
-            assert abs(float(a[3]) - float(b[3])) <= 0.02           # tau_d (tau) quantile
+            assert abs(float(a[3]) - float(b[3])) <= 0.05           # tau_d (tau) quantile
             ea, eb = int(a[5]), int(b[5])                           # estimates with a sampling error
             assert abs(ea - eb) <= 5 * max(ea, eb) ** 0.5 + 5
             if a[6] is not None:
-                assert abs(float(a[6]) - float(b[6])) <= 0.02       # tau_r quantile
+                assert abs(float(a[6]) - float(b[6])) <= 0.05       # tau_r quantile
