@@ -30,7 +30,9 @@
 
 namespace qb200 {
 
+#ifndef QB_SEG_BLOCK
 #define QB_SEG_BLOCK 32
+#endif
 
 struct RawX87 {  // the 16 bytes of an x86-64 long double
   uint64_t mant;

@@ -20,6 +20,8 @@
 // long double arithmetic.
 #pragma once
 
+#include <string.h>
+
 #include "qmath.cuh"
 
 namespace qb200 {
@@ -214,25 +216,28 @@ QHD X87 x87_add(X87 a, X87 b) {
   return r;
 }
 
-// Exact double-double image (64 <= 106 bits); magnitudes below 2^-1000 flush to zero, which
+// Exact double-double image (64 <= 106 bits); magnitudes below 2^-959 flush to zero, which
 // the sampler's error band covers.
+QHD double qb_bits_to_double(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+#endif
+}
+
 QHD dd x87_to_dd(X87 a) {
   if (a.mant == 0) return make_dd(0.0, 0.0);
-  const int e = a.exp - 63;
-  if (e < -1060 || e > 900) return make_dd(0.0, 0.0);
-  const double hi = (double)(a.mant >> 11) * 2048.0;
-  const double lo = (double)(a.mant & 0x7ffull);
-  dd v = quick_two_sum(hi, lo);
-  // scale by 2^e in two exact steps (e can be below the normal range of one factor)
-  const int e1 = e / 2, e2 = e - e1;
-  const double s1 = pow2i(e1), s2 = pow2i(e2);
-  v.hi = v.hi * s1 * s2;
-  v.lo = v.lo * s1 * s2;
-  if (a.neg) {
-    v.hi = -v.hi;
-    v.lo = -v.lo;
-  }
-  return v;
+  // the top 53 bits are a double as they stand (no rounding); the low 11 bits follow 2^-52 below
+  const int eh = a.exp + 1023, el = a.exp - 63 + 1023;
+  if (el < 1 || eh > 2046) return make_dd(0.0, 0.0);  // below 2^-959 (or absurdly large): flushed
+  const uint64_t sign = a.neg ? 0x8000000000000000ull : 0ull;
+  const double hi = qb_bits_to_double(sign | ((uint64_t)eh << 52) | ((a.mant >> 11) & 0xfffffffffffffull));
+  double lo = (double)(uint32_t)(a.mant & 0x7ffull) * qb_bits_to_double((uint64_t)el << 52);
+  if (a.neg) lo = -lo;
+  return quick_two_sum(hi, lo);
 }
 
 }  // namespace qb200

@@ -8,7 +8,7 @@ flavours of integration/build.py:
 
     python tests/tools/estimate_runs_timing.py [--ref-clients 16] [--gpu-clients 8] [--skip-ref]
 
-Writes gpurun_out/estimate_runs_report.json (wall clocks, the log lines of both runs).
+Writes gpurun_out/estimate_runs_report_s<s>.json (wall clocks, the log lines of both runs).
 """
 import argparse
 import json
@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--skip-ref", action="store_true")
     ap.add_argument("--m", type=int, default=2048)
     ap.add_argument("--dim", type=int, default=256)
+    ap.add_argument("--s", type=int, default=1, help="tradeoff factor: l = ceil(m / s); large s = many runs n")
     args = ap.parse_args()
     m = args.m
     rnd = random.Random(20482048)
@@ -63,12 +64,12 @@ def main():
     os.makedirs(os.path.join(t, "distributions"))
     env = {"QB200_DEVICE": "0", "QB200_TEXT_DEVICE": "0", "QB200_DROPIN_STATS": "1"}
     _, _, gen_wall, _ = run("gpu", "generate_distribution",
-                            ["-exp", str(d), str(r), "-dim", str(args.dim), str(m), "1"], 3, t, env)
+                            ["-exp", str(d), str(r), "-dim", str(args.dim), str(m), str(args.s)], 3, t, env)
     name = [f for f in os.listdir(os.path.join(t, "distributions"))
             if f.startswith("distribution-") and f.endswith(".txt")][0]
     path = os.path.join("distributions", name)
     size = os.path.getsize(os.path.join(t, path))
-    rep = {"distribution": name, "file_bytes": size, "generate_wall_s": gen_wall, "m": m, "runs": {}}
+    rep = {"distribution": name, "file_bytes": size, "generate_wall_s": gen_wall, "m": m, "s": args.s, "runs": {}}
     for flavour, clients in (("gpu", args.gpu_clients), ("ref", args.ref_clients)):
         if flavour == "ref" and args.skip_ref:
             continue
@@ -83,7 +84,7 @@ def main():
         for l in lines:
             print("   ", l)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "estimate_runs_report.json"), "w"), indent=1)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", f"estimate_runs_report_s{args.s}.json"), "w"), indent=1)
     shutil.rmtree(t, ignore_errors=True)
 
 
