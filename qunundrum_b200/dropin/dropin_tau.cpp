@@ -49,6 +49,8 @@
 #include "tau_estimate.h"
 
 #include <float.h>
+#include <stdio.h>
+#include <time.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -60,6 +62,27 @@
 namespace {
 
 qb200_context* g_ctx = NULL;
+
+// QB200_DROPIN_STATS=1: at exit, where the time of this rank's estimates went.
+struct Stats {
+  bool on = false;
+  unsigned long calls = 0, batches = 0, creates = 0;
+  double s_draw = 0, s_abi = 0, s_create = 0;
+} g_stats;
+
+double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+void print_stats() {
+  if (g_stats.on && g_stats.calls)
+    fprintf(stderr,
+            "qunundrum_b200 tau drop-in: %lu estimates in %lu batches; %.3f s drawing the random words, "
+            "%.3f s inside qb200_sampler_tau_estimate, %lu sampler set-ups in %.3f s\n",
+            g_stats.calls, g_stats.batches, g_stats.s_draw, g_stats.s_abi, g_stats.creates, g_stats.s_create);
+}
 
 int env_int(const char* name, int fallback) {
   const char* v = getenv(name);
@@ -79,6 +102,11 @@ qb200_context* context() {
     device = ((local - 1) % n + n) % n;
   }
   if (0 != qb200_create(device, &g_ctx)) critical("qunundrum_b200: %s", qb200_last_error());
+  const char* st = getenv("QB200_DROPIN_STATS");
+  if (st && *st && *st != '0') {
+    g_stats.on = true;
+    atexit(print_stats);
+  }
   return g_ctx;
 }
 
@@ -252,6 +280,7 @@ bool estimate(const Dist* distribution, Random_State* rs, uint32_t n, long doubl
     if (tau1) *tau1 = DBL_MAX;
     return false;
   }
+  g_stats.calls++;
   if (g.next < g.ok.size() && g.distribution == (const void*)distribution && g.rs == rs && g.n == n &&
       g.count == distribution->count && g.slices == (const void*)distribution->slices &&
       0 == memcmp(&g.total, &distribution->total_probability, 10)) {
@@ -274,12 +303,15 @@ bool estimate(const Dist* distribution, Random_State* rs, uint32_t n, long doubl
   if (NULL == g.sampler || g.distribution != (const void*)distribution || g.print != fp) {
     if (g.sampler) qb200_sampler_destroy(g.sampler);
     g.sampler = NULL;
+    const double t_create = now_s();
     if (0 != qb200_sampler_create(context(), l.dims, l.m, l.count, l.dimension.data(), l.c0.data(),
                                   l.c1.data(), l.cells.data(), l.totals.data(), l.total, &g.sampler)) {
       critical("%s(): %s", who, qb200_last_error());
     }
     g.distribution = (const void*)distribution;
     g.print = fp;
+    g_stats.creates++;
+    g_stats.s_create += now_s() - t_create;
   }
   if (g.fifo_rs != rs) {
     g.fifo.clear();
@@ -291,17 +323,22 @@ bool estimate(const Dist* distribution, Random_State* rs, uint32_t n, long doubl
   if (g.fifo.size() < need) {
     const size_t have = g.fifo.size();
     g.fifo.resize(need);
+    const double t_draw = now_s();
     draw_words(rs, &g.fifo[have], need - have, env_int("QB200_TAU_REFERENCE_RNG", 0) != 0);
+    g_stats.s_draw += now_s() - t_draw;
   }
   g.tau0.assign(batch, 0);
   g.tau1.assign(batch, 0);
   g.ok.assign(batch, 0);
   size_t used = 0;
   uint32_t done = 0;
+  const double t_abi = now_s();
   if (0 != qb200_sampler_tau_estimate(g.sampler, n, batch, g.fifo.data(), g.fifo.size(), &used, &done,
                                       g.tau0.data(), g.tau1.data(), g.ok.data())) {
     critical("%s(): %s", who, qb200_last_error());
   }
+  g_stats.s_abi += now_s() - t_abi;
+  g_stats.batches++;
   if (done != batch) critical("%s(): internal error: the word queue ran dry.", who);
   g.fifo.erase(g.fifo.begin(), g.fifo.begin() + (long)used);
   g.rs = rs;
