@@ -458,17 +458,18 @@ def tau_section(ctx, qb, torch, stream, h_cells, tp, coords, hbm_peak, cpu_basel
     wall = (time.perf_counter() - t0) / e2e_reps
     done = len(ta)
     # algorithmic bytes per sample: two searches (ceil(log2(blocks)) coarse entries of 32 B and
-    # on average half a block of 32 x 16 B each), the words in, 64 B out
+    # on average half a block of 8 x 16 B each), the words in, 64 B out
     import math
-    blocks_s = math.ceil(len(dist.slices) / 32)
-    blocks_c = D * D // 32
-    bytes_per_sample = (math.ceil(math.log2(blocks_s)) + math.ceil(math.log2(blocks_c))) * 32 + 2 * 256 \
-        + wps * 8 + 64
+    seg_block = 8                                             # QB_SEG_BLOCK, sampler.cuh
+    blocks_s = math.ceil(len(dist.slices) / seg_block)
+    blocks_c = D * D // seg_block
+    bytes_per_sample = (math.ceil(math.log2(blocks_s)) + math.ceil(math.log2(blocks_c))) * 32 \
+        + 2 * (seg_block // 2) * 16 + wps * 8 + 64
     gbs = total * bytes_per_sample / (ms * 1e-3) / 1e9
     out = {
         "workload": (f"tau_estimate on the step's own distribution: {len(dist.slices)} slices "
                      f"({n_slices} computed + mirrored) x {D * D} cells = {sampler_cells(sampler)} cells "
-                     f"resident ({sampler_cells(sampler) * 16 / 1e9:.2f} GB x87 + coarse index); "
+                     f"resident ({sampler_cells(sampler) * 16 / 1e9:.2f} GB x87 + 25 % coarse index); "
                      f"{count} estimates of n = {n} samples per call"),
         "samples_per_call": total,
         "value": total / (ms * 1e-3), "unit": "samples/s", "ms": ms,

@@ -2,12 +2,12 @@
 // code and the reference citations).
 //
 //   k_seg_build   one CTA per segment (a slice's cells, or the list of slice totals): block
-//                 summaries of 32 elements each in parallel, then the walk states before every
+//                 summaries of QB_SEG_BLOCK (8) elements each in parallel, then the walk states before every
 //                 block (prefix sum and running maximum, double-double). Runs once per
 //                 distribution. HBM-bound: 16 B read per cell.
-//   k_sample      one thread per sample: two searches (slices, then the cells of the slice: 11
-//                 dependent 32-byte reads of the coarse index + one 512-byte block of cells) and
-//                 the two axis draws. Latency / random-access bound.
+//   k_sample      one thread per sample: two searches (slices, then the cells of the slice: 10 + 11
+//                 dependent 32-byte reads of the coarse index + one 128-byte block of cells each)
+//                 and the two axis draws. Instruction-issue / latency bound.
 //   k_tau_reduce  one thread per estimate: the n squares summed in sample order.
 #pragma once
 

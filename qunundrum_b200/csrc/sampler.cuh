@@ -13,7 +13,7 @@
 // (src/executables_estimate_runs_distribution.h:23-28), every sample two linear long double
 // walks of up to 6404 + 65,536 steps.
 //
-// Here a walk is a binary search over prefix sums kept per block of 32 elements (exact
+// Here a walk is a binary search over prefix sums kept per block of 8 elements (exact
 // double-double images of the x87 numbers) followed by a scan of one block. The reference's
 // walk rounds to 64 bits at every step, so its stopping index can differ from the exact one
 // only when the pivot lies within the accumulated rounding error B of a prefix sum: the fast
@@ -30,8 +30,11 @@
 
 namespace qb200 {
 
+// Elements per block of the coarse index. Measured on the bench distribution (B200, 2^20 samples
+// per call): 32 -> 2.03e9 samples/s, 16 -> 2.97e9, 8 -> 3.78e9, 4 -> 4.29e9; the index costs
+// 32 / QB_SEG_BLOCK bytes per 16-byte cell. 8: +25 % memory for 1.9 x.
 #ifndef QB_SEG_BLOCK
-#define QB_SEG_BLOCK 32
+#define QB_SEG_BLOCK 8
 #endif
 
 struct RawX87 {  // the 16 bytes of an x86-64 long double
