@@ -292,8 +292,9 @@ int qb200_sampler_tau_device(qb200_sampler *sampler, uint32_t n, uint32_t count,
                              const uint64_t *d_words, double *d_sums, int32_t *d_status,
                              void *stream);
 
-/* Test hooks: send every walk through the bit-exact x87 replay (on = 1); the number of walks
- * of the last call that needed it; the smallest slice-pivot word that runs out of bounds
+/* Test hooks: send every walk through the bit-exact x87 replay (on = 1) or every search through
+ * the double-double path, skipping the quick pass in doubles (on = 2); the number of walks of the
+ * last call that needed the replay; the smallest slice-pivot word that runs out of bounds
  * (return value 0: none does). */
 int qb200_sampler_set_force_exact(qb200_sampler *sampler, int on);
 uint64_t qb200_sampler_exact_count(const qb200_sampler *sampler);

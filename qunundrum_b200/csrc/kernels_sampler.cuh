@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) k_sample(SamplerView view, const uint64_t
   uint64_t w[4];
   for (uint32_t q = 0; q < wps; q++) w[q] = words[base + q];
   SampleOut o;
-  sample_one(view, w, force_exact != 0, &o);
+  sample_one(view, w, force_exact, &o);
   out[g] = o;
 }
 

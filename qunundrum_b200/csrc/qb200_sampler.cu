@@ -267,7 +267,7 @@ uint32_t qb200_sampler_words_per_sample(const qb200_sampler* s) { return (uint32
 uint64_t qb200_sampler_cells(const qb200_sampler* s) { return s->n_cells; }
 
 int qb200_sampler_set_force_exact(qb200_sampler* s, int on) {
-  s->force_exact = on ? 1 : 0;
+  s->force_exact = (on == 1 || on == 2) ? on : 0;
   return 0;
 }
 uint64_t qb200_sampler_exact_count(const qb200_sampler* s) { return s->exact_last; }

@@ -87,6 +87,16 @@ enum { kSampleOk = 0, kSampleOutOfBounds = 1, kSampleNoRegion = 2 };
 QHD bool dd_ge(dd a, dd b) { return a.hi > b.hi || (a.hi == b.hi && a.lo >= b.lo); }
 QHD dd dd_max(dd a, dd b) { return dd_ge(a, b) ? a : b; }
 
+// The top 53 bits of an element as a double (truncated; zero for zeros and for magnitudes
+// outside the double range -- the callers' error bands cover both).
+QHD double x87_raw_to_double(const RawX87 r) {
+  const uint32_t se = (uint32_t)r.se;
+  const int e = (int)(se & 0x7fffu) - 16383 + 1023;
+  if ((se & 0x7fffu) == 0 || e < 1 || e > 2046) return 0.0;
+  return qb_bits_to_double(((uint64_t)(se & 0x8000u) << 48) | ((uint64_t)e << 52) |
+                           ((r.mant >> 11) & 0xfffffffffffffull));
+}
+
 QHD X87 x87_load(const RawX87* p, bool* ok) {
   X87 v;
   const RawX87 r = *p;
@@ -139,10 +149,12 @@ QHD uint32_t seg_walk_exact(const RawX87* v, uint32_t n, X87 p) {
 }
 
 // First k at which the reference's walk stops, or n. *exact is incremented when the replay ran.
+// mode (test switch): 0 normal; 1 every walk through the bit-exact replay; 2 skip the quick pass in
+// doubles (every search through the double-double path).
 QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, uint32_t n, double abs_sum, X87 p,
-                      bool force_exact, int* exact) {
+                      int mode, int* exact) {
   if (n == 0) return 0;
-  if (force_exact) {
+  if (mode == 1) {
     *exact += 1;
     return seg_walk_exact(v, n, p);
   }
@@ -165,8 +177,30 @@ QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, uint32_t n, doub
     *exact += 1;
     return seg_walk_exact(v, n, p);
   }
-  dd c = coarse[lo].c, mprev = coarse[lo].m;
   const uint32_t k0 = lo * QB_SEG_BLOCK, k1 = k0 + QB_SEG_BLOCK < n ? k0 + QB_SEG_BLOCK : n;
+  // Quick pass over the block in plain doubles (top 53 bits of every element): its prefix sums
+  // are within 2^-49 * scale of the exact ones, so a hit that clears the pivot -- and a pivot
+  // that clears every earlier prefix -- by 2^-47 * scale is the exact walk's and, a fortiori
+  // (2^-47 >> n 2^-63), the reference's. All but ~1e-10 of the searches end here.
+  if (mode != 2) {
+    double x[QB_SEG_BLOCK];
+#pragma unroll
+    for (int q = 0; q < QB_SEG_BLOCK; q++)  // independent loads first
+      x[q] = k0 + q < k1 ? x87_raw_to_double(v[k0 + q]) : 0.0;
+    const double wide = 7.105427357601002e-15 * (fabs(pd.hi) + abs_sum);  // 2^-47 * scale
+    double c = coarse[lo].c.hi, mprev = coarse[lo].m.hi;
+#pragma unroll
+    for (int q = 0; q < QB_SEG_BLOCK; q++) {
+      if (k0 + q >= k1) break;
+      c += x[q];
+      if (c >= pd.hi) {
+        if (c - pd.hi > wide && pd.hi - mprev > wide) return k0 + (uint32_t)q;
+        break;  // too close to call in doubles
+      }
+      mprev = fmax(mprev, c);
+    }
+  }
+  dd c = coarse[lo].c, mprev = coarse[lo].m;
   bool ok = true;
   for (uint32_t k = k0; k < k1; k++) {
     c = dd_add(c, x87_to_dd(x87_load(v + k, &ok)));
@@ -198,7 +232,7 @@ QHD dd sample_axis(const SamplerView& s, const SamplerSlice& sl, int32_t k, uint
 
 // One sample from the words w[0 .. dims + 1] (the reference's draws, in its order: slice
 // pivot, region pivot, one fraction per axis).
-QHD void sample_one(const SamplerView& s, const uint64_t* w, bool force_exact, SampleOut* out) {
+QHD void sample_one(const SamplerView& s, const uint64_t* w, int mode, SampleOut* out) {
   out->sq0_hi = out->sq0_lo = out->sq1_hi = out->sq1_lo = 0.0;
   out->x0 = out->x1 = 0.0;
   out->slice = out->cell = -1;
@@ -206,7 +240,7 @@ QHD void sample_one(const SamplerView& s, const uint64_t* w, bool force_exact, S
   bool ok = true;
   X87 p = x87_pivot_inclusive(w[0]);
   if (s.scale_by_total) p = x87_mul(p, x87_load(&s.dist_total, &ok));
-  const uint32_t i = seg_find(s.totals, s.totals_coarse, s.n_slices, s.totals_abs_sum, p, force_exact,
+  const uint32_t i = seg_find(s.totals, s.totals_coarse, s.n_slices, s.totals_abs_sum, p, mode,
                               &out->exact);
   if (i >= s.n_slices) {
     out->status = kSampleOutOfBounds;
@@ -216,7 +250,7 @@ QHD void sample_one(const SamplerView& s, const uint64_t* w, bool force_exact, S
   const SamplerSlice sl = s.slices[i];
   const X87 p2 = x87_mul(x87_pivot_inclusive(w[1]), x87_load(s.totals + i, &ok));
   const uint32_t c = seg_find(s.cells + sl.cell_off, s.coarse + sl.coarse_off, sl.n_cells, sl.abs_sum,
-                              p2, force_exact, &out->exact);
+                              p2, mode, &out->exact);
   if (c >= sl.n_cells) {
     out->status = kSampleNoRegion;
     return;

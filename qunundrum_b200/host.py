@@ -764,8 +764,9 @@ class Sampler:
         except Exception:
             pass
 
-    def set_force_exact(self, on: bool):
-        lib().qb200_sampler_set_force_exact(self.h, 1 if on else 0)
+    def set_force_exact(self, on):
+        """Test switch: 1 / True = bit-exact replay of every walk; 2 = no quick pass in doubles."""
+        lib().qb200_sampler_set_force_exact(self.h, int(on))
 
     @property
     def exact_count(self) -> int:

@@ -200,7 +200,7 @@ class HostSampler:
         st = np.zeros(k, dtype=np.int32)
         ex = np.zeros(k, dtype=np.int32)
         lib().hostsim_sampler_sample(self.h, C.c_uint32(k), w.ctypes.data_as(C.c_void_p),
-                                     1 if force_exact else 0, out.ctypes.data_as(C.c_void_p),
+                                     int(force_exact), out.ctypes.data_as(C.c_void_p),
                                      st.ctypes.data_as(C.c_void_p), ex.ctypes.data_as(C.c_void_p))
         return out, st, ex
 

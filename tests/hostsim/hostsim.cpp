@@ -522,7 +522,7 @@ void hostsim_sampler_sample(void* hh, uint32_t k, const uint64_t* words, int for
   const uint32_t wps = (uint32_t)h->view.dims + 2;
   for (uint32_t i = 0; i < k; i++) {
     SampleOut o;
-    sample_one(h->view, words + (size_t)i * wps, force_exact != 0, &o);
+    sample_one(h->view, words + (size_t)i * wps, force_exact, &o);
     double* d = out + 8 * (size_t)i;
     d[0] = o.sq0_hi; d[1] = o.sq0_lo; d[2] = o.sq1_hi; d[3] = o.sq1_lo;
     d[4] = o.x0; d[5] = o.x1; d[6] = o.slice; d[7] = o.cell;
