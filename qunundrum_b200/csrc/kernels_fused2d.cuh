@@ -745,8 +745,16 @@ inline bool fused2d_prepare(const Plan& h, unsigned n_chunks, FusedPlan2D* f, st
   unsigned base = 0;
   for (unsigned ch = 0; ch < n_chunks; ch++) {
     FusedChunk fc;
-    fc.slot_begin = (unsigned)((uint64_t)n * ch / n_chunks);
-    fc.slot_end = (unsigned)((uint64_t)n * (ch + 1) / n_chunks);
+    // equal chunks, except that the first one is a quarter of a share (and the second makes up
+    // for it): the first device-to-host copy of the synchronous API starts that much earlier
+    const auto edge = [&](unsigned c) -> unsigned {
+      if (c == 0) return 0u;
+      if (c >= n_chunks) return n;
+      const uint64_t quarters = c == 1 && n_chunks > 2 ? 1 : 4 * (uint64_t)c;
+      return (unsigned)((uint64_t)n * quarters / (4 * (uint64_t)n_chunks));
+    };
+    fc.slot_begin = edge(ch);
+    fc.slot_end = edge(ch + 1);
     std::vector<FusedSlice> by_cls[3];
     for (unsigned i = fc.slot_begin; i < fc.slot_end; i++) {
       const double umax = 2.0 * (h.slices[i].scale_a + akappa * h.slices[i].scale_b);

@@ -163,19 +163,26 @@ inline int coord_ok(int32_t k, uint32_t m, std::string* err) {
   return 1;
 }
 
-inline int intern_table(std::map<std::pair<int, int>, int>& index, std::vector<TabDesc>& tabs,
-                        int32_t k) {
+// Distinct signed coordinates -> table index. Coordinates are within m - 400 .. m + 59
+// (coord_ok), so the index is a flat array: planning a 3362-slice batch is on the critical path
+// of the synchronous API (the GPU idles until the plan is uploaded).
+struct TableIndex {
+  int m;
+  std::vector<int> slot;  // [(|k| - m + 400) * 2 + (k >= 0)] -> table, -1 = none yet
+  explicit TableIndex(uint32_t m_) : m((int)m_), slot(2 * 460, -1) {}
+};
+
+inline int intern_table(TableIndex& index, std::vector<TabDesc>& tabs, int32_t k) {
   const int sign = k < 0 ? -1 : 1;  // sgn_d(): zero counts as positive (src/math.cpp)
   const int ka = (int)std::labs((long)k);
-  const auto key = std::make_pair(ka, sign);
-  auto it = index.find(key);
-  if (it != index.end()) return it->second;
+  int& at = index.slot[(size_t)(ka - index.m + 400) * 2 + (sign > 0 ? 1 : 0)];
+  if (at >= 0) return at;
   TabDesc t;
   t.k_abs = ka;
   t.sign = sign;
   tabs.push_back(t);
-  index[key] = (int)tabs.size() - 1;
-  return (int)tabs.size() - 1;
+  at = (int)tabs.size() - 1;
+  return at;
 }
 
 inline int plan_2d(const ParamsView& p, int method, int richardson, uint32_t D, uint32_t n,
@@ -196,7 +203,7 @@ inline int plan_2d(const ParamsView& p, int method, int richardson, uint32_t D, 
   plan->kind = -1;
   plan->method = method;
   plan->with_error = (method != kMethodQuick);
-  std::map<std::pair<int, int>, int> ia, ib;
+  TableIndex ia(p.m), ib(p.m);
   plan->slices.resize(n);
   plan->k_a.assign(a_d, a_d + n);
   plan->k_b.assign(a_r, a_r + n);
@@ -235,7 +242,7 @@ inline int plan_1d(const ParamsView& p, int kind, int richardson, uint32_t D, ui
   plan->richardson = richardson ? 1 : 0;
   plan->kind = kind;
   plan->with_error = false;
-  std::map<std::pair<int, int>, int> ia;
+  TableIndex ia(p.m);
   plan->slices.resize(n);
   plan->k_a.assign(a, a + n);
   plan->k_b.assign(n, 0);
