@@ -99,8 +99,8 @@ struct FusedPlan2D {
 //   R = 5 D    the last main column h = 4 D
 // Fields: yh, yl, sr, cr, wF, wF2, wC, wC2, b, t2p.
 //   wF  : fine Simpson weight of the column within cell J   (x T2 / pi^2)
-//   wF2 : fine weight of the column as LAST column of cell J - 1 (k = 0 only)
-//   wC / wC2 : the same for the coarse pass
+//   wF2 : fine weight of the column as LAST column of cell J - 1 (k = 0); wF * b for k = 1, 2, 3
+//   wC / wC2 : the same for the coarse pass (k = 4: wC2 = wC * b)
 __global__ void k_fused_cols(int D, int m, const TabDesc* __restrict__ desc_b,
                              const AxisR* __restrict__ tab_b, const double* __restrict__ gw,
                              double* __restrict__ cols) {
@@ -151,6 +151,11 @@ __global__ void k_fused_cols(int D, int m, const TabDesc* __restrict__ desc_b,
   o[5] = wF2 * f;
   o[6] = wC * f;
   o[7] = wC2 * f;
+  // Interior fine columns (k = 1, 2, 3) have no "last column" weight and the coarse mid column
+  // (k = 4) has no wC2: those slots carry the error-moment weights wF * b / wC * b, the very
+  // products the march would otherwise form per column in every lane (bit-identical).
+  if (k >= 1 && k <= 3) o[5] = o[4] * a.b;
+  if (k == 4) o[7] = o[6] * a.b;
   o[8] = a.b;
   o[9] = t2p;
 }
@@ -390,7 +395,7 @@ __device__ __forceinline__ void fused_march(const FusedConst& k, const RowReg& r
       sF0 = fma(c.wF, T0, sF0); sF1 = fma(c.wF, T1, sF1);
       sF2 = fma(c.wF, T2, sF2); sF3 = fma(c.wF, T3, sF3);
       if (HAS_ERR) {
-        const double wb = c.wF * c.b;
+        const double wb = c.wF2;  // = wF * b, prepared by k_fused_cols
         bF0 = fma(wb, T0, bF0); bF1 = fma(wb, T1, bF1);
         bF2 = fma(wb, T2, bF2); bF3 = fma(wb, T3, bF3);
         if (HAS_M2) {
@@ -406,7 +411,7 @@ __device__ __forceinline__ void fused_march(const FusedConst& k, const RowReg& r
       QB_EVAL2(r0, rc, c, T0, Tm)
       sC0 = fma(c.wC, T0, sC0); sCm = fma(c.wC, Tm, sCm);
       if (HAS_ERR) {
-        const double wcb = c.wC * c.b;
+        const double wcb = c.wC2;  // = wC * b, prepared by k_fused_cols
         bC0 = fma(wcb, T0, bC0); bCm = fma(wcb, Tm, bCm);
         if (HAS_M2) {
           const double wcbb = wcb * c.b;
