@@ -23,6 +23,7 @@
 #include "ctx_access.hpp"
 #include "hostconst.hpp"
 #include "kernels_sampler.cuh"
+#include "sampler_host.hpp"
 
 using namespace qb200;
 
@@ -79,55 +80,14 @@ struct qb200_sampler {
   int force_exact = 0;
   uint64_t exact_last = 0;
   uint64_t n_cells = 0;
-  // the serial part of the reference's semantics, decided once on the host in the host's own
-  // long double arithmetic: the smallest pivot word whose walk over the slices runs out of bounds
-  bool any_fail = false;
-  uint64_t first_failing_word = 0;
-  std::vector<long double> h_totals;
-  long double h_total = 0;
+  // the serial part of the reference's semantics (sampler_host.hpp): the smallest pivot word
+  // whose walk over the slices runs out of bounds, decided once in the host's own long double
+  FailureThreshold fail;
+  TauLayout layout;
   qb200_sampler() {
     h_sums.host = h_status.host = h_words.host = h_off.host = h_out.host = true;
   }
 };
-
-namespace {
-
-// distribution_sample_slice (src/distribution.cpp:359-409) for one pivot word, verbatim
-// semantics in the host's x87 arithmetic: true if no slice is selected.
-bool host_walk_fails(const qb200_sampler* s, uint64_t w) {
-  long double pivot = (long double)w;
-  pivot /= (long double)0xffffffffffffffffULL;
-  if (s->h_total > 1) pivot *= s->h_total;
-  for (size_t i = 0; i < s->h_totals.size(); i++) {
-    pivot -= s->h_totals[i];
-    if (pivot <= 0) return false;
-  }
-  return true;
-}
-
-void find_failure_threshold(qb200_sampler* s) {
-  // the walk's result is monotone in the pivot (rounding is monotone): binary search
-  if (!host_walk_fails(s, 0xffffffffffffffffULL)) {
-    s->any_fail = false;
-    return;
-  }
-  s->any_fail = true;
-  uint64_t lo = 0, hi = 0xffffffffffffffffULL;  // fails(hi), smallest failing word in [lo, hi]
-  while (lo < hi) {
-    const uint64_t mid = lo + (hi - lo) / 2;
-    if (host_walk_fails(s, mid))
-      hi = mid;
-    else
-      lo = mid + 1;
-  }
-  s->first_failing_word = lo;
-}
-
-inline bool word_fails(const qb200_sampler* s, uint64_t w) {
-  return s->any_fail && w >= s->first_failing_word;
-}
-
-}  // namespace
 
 extern "C" {
 
@@ -249,9 +209,7 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
     if (!x87_decode(v.dist_total.mant, (uint32_t)v.dist_total.se & 0xffffu, &t))
       return set_error(-14, "the distribution's total probability is denormal, infinite or NaN");
   }
-  s->h_totals.assign(slice_total, slice_total + n_slices);
-  s->h_total = total_probability;
-  find_failure_threshold(s.get());
+  s->fail = find_failure_threshold(slice_total, n_slices, total_probability);
   *out = s.release();
   return 0;
 }
@@ -273,8 +231,8 @@ int qb200_sampler_set_force_exact(qb200_sampler* s, int on) {
 uint64_t qb200_sampler_exact_count(const qb200_sampler* s) { return s->exact_last; }
 
 int qb200_sampler_first_failing_word(const qb200_sampler* s, uint64_t* word) {
-  if (word) *word = s->first_failing_word;
-  return s->any_fail ? 1 : 0;
+  if (word) *word = s->fail.first;
+  return s->fail.any ? 1 : 0;
 }
 
 int qb200_sampler_sample(qb200_sampler* s, uint32_t k, const uint64_t* words, int32_t* slice,
@@ -333,34 +291,10 @@ int qb200_sampler_tau_estimate(qb200_sampler* s, uint32_t n, uint32_t count, con
   QS_CUDA(cudaSetDevice(s->device));
   const uint32_t wps = qb200_sampler_words_per_sample(s);
   // ---- the serial part: where each estimate starts in the stream -------------------------
-  if (int rc = s->h_off.reserve((size_t)count * 8 + 8)) return rc;
-  uint64_t* off = s->h_off.as<uint64_t>();
-  size_t cur = 0;
-  uint32_t t = 0;
-  for (; t < count; t++) {
-    size_t used = 0;
-    bool fails = false, short_of_words = false;
-    for (uint32_t i = 0; i < n; i++) {
-      if (cur + used >= n_words) {
-        short_of_words = true;
-        break;
-      }
-      if (word_fails(s, words[cur + used])) {  // distribution_sample_slice() returns NULL: one draw
-        used += 1;
-        fails = true;
-        break;
-      }
-      if (cur + used + wps > n_words) {
-        short_of_words = true;
-        break;
-      }
-      used += wps;
-    }
-    if (short_of_words) break;
-    off[t] = fails ? QB_TAU_SKIP : (uint64_t)cur;
-    cur += used;
-  }
-  const uint32_t nt = t;
+  tau_layout(s->fail, wps, n, count, words, n_words, &s->layout);
+  const uint32_t nt = s->layout.done;
+  const size_t cur = s->layout.words_used;
+  const uint64_t* off = s->layout.off.data();
   if (done) *done = nt;
   if (words_used) *words_used = cur;
   s->exact_last = 0;
@@ -393,31 +327,10 @@ int qb200_sampler_tau_estimate(qb200_sampler* s, uint32_t n, uint32_t count, con
   QS_CUDA(cudaStreamSynchronize(s->stream));
   s->exact_last = *h_exact;
   // ---- host: tau = log2(mean alpha^2) / 2 - m (src/tau_estimate.cpp:63-71) ------------------
-  const double* sums = s->h_sums.as<double>();
-  const int* status = s->h_status.as<int>();
-  const long double two_m = (long double)(2.0 * (double)s->view.m);
-  for (uint32_t i = 0; i < nt; i++) {
-    if (off[i] == QB_TAU_SKIP) {
-      ok[i] = 0;
-      tau0[i] = DBL_MAX;
-      if (tau1) tau1[i] = DBL_MAX;
-      continue;
-    }
-    if (status[i] == kSampleNoRegion)
-      return set_error(-41, "Failed to sample a region from the slice.");
-    if (status[i] != kSampleOk)
-      return set_error(-40, "internal error: the device and the host disagree on an out-of-bounds sample");
-    ok[i] = 1;
-    const long double a = ((long double)sums[4 * i] + (long double)sums[4 * i + 1]) / (long double)n;
-    tau0[i] = (two_m + log2l(a)) / 2 - (long double)s->view.m;
-    if (s->view.dims == 2) {
-      const long double b = ((long double)sums[4 * i + 2] + (long double)sums[4 * i + 3]) / (long double)n;
-      tau1[i] = (two_m + log2l(b)) / 2 - (long double)s->view.m;
-    } else if (tau1) {
-      tau1[i] = 0;
-    }
-  }
-  return 0;
+  std::string err;
+  const int rc = tau_finish(s->view.dims, s->view.m, n, s->layout, s->h_sums.as<double>(),
+                            s->h_status.as<int>(), tau0, tau1, ok, &err);
+  return rc ? set_error(rc, err) : 0;
 }
 
 }  // extern "C"

@@ -24,7 +24,9 @@
 //     call of a run computes QB200_TAU_BATCH (default 1000) estimates in one batch and the
 //     following calls with the same (distribution, random state, n) return them in order; words
 //     drawn but not consumed (estimates that failed early) stay queued in front of the
-//     generator. If the caller changes n, the distribution or the generator in mid-batch, the
+//     generator, so the logical stream -- queue first, then the Random_State -- is consumed
+//     exactly as the reference consumes its generator (the Random_State itself runs ahead by the
+//     length of the queue). If the caller changes n, the distribution or the generator in mid-batch, the
 //     unused estimates are dropped: the results remain correct samples, but the stream position
 //     then differs from the reference's (never the case in the reference's executables with the
 //     default batch).

@@ -61,3 +61,104 @@ int qb200_text_parse_ld(qb200_context*, const char* text, size_t len, size_t n, 
 }
 
 }  // extern "C"
+
+// ---- sampler entry points (TEST-ONLY, same purpose): the host logic of
+// qunundrum_b200/dropin/dropin_tau.cpp -- batching, the queue of pre-drawn words, the fast
+// Keccak stream, re-use across calls -- and the serial part of qb200_sampler_tau_estimate
+// (csrc/sampler_host.hpp: stream layout, failure threshold, log2 in long double) run in the
+// GPU-less suite on the reference's own Distribution / Random_State structs. The samples
+// themselves come from the CPU compile of sampler.cuh (hostsim_sampler_*).
+#include "../../qunundrum_b200/csrc/sampler_host.hpp"
+
+extern "C" {
+void* hostsim_sampler_new(int dims, uint32_t m, uint32_t n_slices, const uint32_t* dimension,
+                          const int32_t* c0, const int32_t* c1, const long double* cells,
+                          const long double* slice_total, const long double* total);
+void hostsim_sampler_free(void* h);
+int hostsim_sampler_bad(void* h);
+void hostsim_sampler_sample(void* hh, uint32_t k, const uint64_t* words, int force_exact, double* out,
+                            int32_t* status, int32_t* exact);
+}
+
+struct qb200_sampler {
+  void* h = nullptr;
+  int dims = 2;
+  int m = 0;
+  qb200::FailureThreshold fail;
+  qb200::TauLayout layout;
+};
+
+extern "C" {
+
+int qb200_sampler_create(qb200_context*, int dims, uint32_t m, uint32_t n_slices, const uint32_t* dimension,
+                         const int32_t* c0, const int32_t* c1, const long double* const* cells,
+                         const long double* slice_total, long double total_probability,
+                         qb200_sampler** out) {
+  std::vector<long double> flat;
+  for (uint32_t i = 0; i < n_slices; i++) {
+    const size_t nc = dims == 2 ? (size_t)dimension[i] * dimension[i] : dimension[i];
+    flat.insert(flat.end(), cells[i], cells[i] + nc);
+  }
+  qb200_sampler* s = new qb200_sampler;
+  s->dims = dims;
+  s->m = (int)m;
+  s->h = hostsim_sampler_new(dims, m, n_slices, dimension, c0, c1, flat.data(), slice_total,
+                             &total_probability);
+  if (hostsim_sampler_bad(s->h)) {
+    hostsim_sampler_free(s->h);
+    delete s;
+    g_err = "unsupported probability value";
+    return -14;
+  }
+  s->fail = qb200::find_failure_threshold(slice_total, n_slices, total_probability);
+  *out = s;
+  return 0;
+}
+
+void qb200_sampler_destroy(qb200_sampler* s) {
+  if (!s) return;
+  hostsim_sampler_free(s->h);
+  delete s;
+}
+
+uint32_t qb200_sampler_words_per_sample(const qb200_sampler* s) { return (uint32_t)s->dims + 2u; }
+
+int qb200_sampler_tau_estimate(qb200_sampler* s, uint32_t n, uint32_t count, const uint64_t* words,
+                               size_t n_words, size_t* words_used, uint32_t* done, long double* tau0,
+                               long double* tau1, uint8_t* ok) {
+  if (n == 0) {
+    g_err = "n must be positive";
+    return -15;
+  }
+  const uint32_t wps = (uint32_t)s->dims + 2u;
+  qb200::tau_layout(s->fail, wps, n, count, words, n_words, &s->layout);
+  if (done) *done = s->layout.done;
+  if (words_used) *words_used = s->layout.words_used;
+  std::vector<double> sums(4 * (size_t)s->layout.done, 0.0);
+  std::vector<int> status(s->layout.done, 0);
+  std::vector<double> out(8 * (size_t)n);
+  std::vector<int32_t> st(n), ex(n);
+  for (uint32_t t = 0; t < s->layout.done; t++) {
+    if (s->layout.off[t] == QB_TAU_SKIP) continue;
+    hostsim_sampler_sample(s->h, n, words + s->layout.off[t], 0, out.data(), st.data(), ex.data());
+    long double a = 0, b = 0;   // (the device sums in double-double; long double is as good here)
+    for (uint32_t i = 0; i < n; i++) {
+      if (st[i] != 0) {
+        status[t] = st[i];
+        break;
+      }
+      a += (long double)out[8 * i] + (long double)out[8 * i + 1];
+      b += (long double)out[8 * i + 2] + (long double)out[8 * i + 3];
+    }
+    sums[4 * (size_t)t] = (double)a;
+    sums[4 * (size_t)t + 1] = (double)(a - (long double)(double)a);
+    sums[4 * (size_t)t + 2] = (double)b;
+    sums[4 * (size_t)t + 3] = (double)(b - (long double)(double)b);
+  }
+  std::string err;
+  const int rc = qb200::tau_finish(s->dims, s->m, n, s->layout, sums.data(), status.data(), tau0, tau1, ok, &err);
+  if (rc) g_err = err;
+  return rc;
+}
+
+}  // extern "C"

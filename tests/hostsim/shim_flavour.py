@@ -20,6 +20,46 @@ TOOLS = ("filter_distribution", "compare_distributions", "compare_linear_distrib
          "compare_diagonal_distributions", "info_distribution")
 
 
+DROPIN_TAU_SHIM = os.path.join(OUT, "libdropin_tau_shim.so")
+
+
+def build_tau(reference_root: str = "/root/reference", force: bool = False):
+    """TEST-ONLY: qunundrum_b200/dropin/dropin_tau.cpp linked against the CPU stand-in of the sampler
+    entry points (abi_shim.cpp) and the reference's own generator / errors sources compiled in
+    place, so that the drop-in's host logic and csrc/sampler_host.hpp run without a GPU
+    (tests/test_dropin_gpu.py::test_tau_dropin_host_logic_on_the_cpu_shim)."""
+    src = os.path.join(reference_root, "src")
+    if not os.path.isdir(src):
+        return DROPIN_TAU_SHIM if os.path.exists(DROPIN_TAU_SHIM) else None
+    deps = [os.path.join(_HERE, "abi_shim.cpp"), os.path.join(_HERE, "hostsim.cpp"), os.path.abspath(__file__),
+            os.path.join(_ROOT, "qunundrum_b200", "dropin", "dropin_tau.cpp")]
+    deps += [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
+             ("sampler.cuh", "x87soft.cuh", "sampler_host.hpp")]
+    if not force and os.path.exists(DROPIN_TAU_SHIM) and all(
+            os.path.getmtime(d) <= os.path.getmtime(DROPIN_TAU_SHIM) for d in deps):
+        return DROPIN_TAU_SHIM
+    os.makedirs(OUT, exist_ok=True)
+    inc = ["-I", os.path.join(_ROOT, "integration", "shims"), "-I", os.path.join(_ROOT, "integration", "minimpi"),
+           "-I", os.path.join(_ROOT, "integration", "stubs"), "-I", os.path.join(_ROOT, "include"), "-iquote", src]
+    objs = []
+    for f in ("errors", "random", "keccak", "keccak_random", "debug_common"):
+        o = os.path.join(OUT, f"_{f}.o")
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-w", *inc, "-c", os.path.join(src, f + ".c"), "-o", o])
+        objs.append(o)
+    o = os.path.join(OUT, "_dropin_tau.o")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-fPIC", "-w", *inc, "-c",
+                           os.path.join(_ROOT, "qunundrum_b200", "dropin", "dropin_tau.cpp"), "-o", o])
+    objs.append(o)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-x", "c++",
+                           os.path.join(_HERE, "abi_shim.cpp"), os.path.join(_HERE, "hostsim.cpp"),
+                           os.path.join(_ROOT, "qunundrum_b200", "csrc", "hostconst.cpp"),
+                           os.path.join(_ROOT, "qunundrum_b200", "csrc", "text_tables.cpp"),
+                           "-x", "none", *objs, "/lib/x86_64-linux-gnu/libgmp.so.10", "-o", DROPIN_TAU_SHIM])
+    for o in objs:
+        os.remove(o)
+    return DROPIN_TAU_SHIM
+
+
 def build(force: bool = False) -> bool:
     from integration import build as ib
     obj = os.path.join(ib.OUT, "obj")

@@ -101,65 +101,82 @@ def test_dropin_exports_the_tau_symbols():
     assert SYM_TAU in out and SYM_TAU_LINEAR in out
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", ["2d", "lin"])
-def test_tau_dropin_called_like_the_reference(name):
+def _tau_dropin_called_like_the_reference(libpath, name):
     """dropin_tau.cpp on the reference's own Distribution / Random_State structs (built by the
     reference's functions in oracle/_ref): for the same generator seed, the sequence of
     tau_estimate() calls an estimate_runs client makes returns what the reference's
-    tau_estimate() returns -- across batch boundaries (QB200_TAU_BATCH = 64 here, 150 calls) and
-    across a change of n -- and leaves the generator where the reference leaves it."""
+    tau_estimate() returns -- across batch boundaries (QB200_TAU_BATCH = 64 here, 128 calls per
+    n) and across a change of n, with the words of early-failing estimates carried over."""
     ref = ref_or_none()
-    if ref is None or not os.path.exists(DROPIN):
+    if ref is None or not os.path.exists(libpath):
         pytest.skip("needs oracle/_ref and the built drop-in")
     from tests.test_sampler import GOLD, Gold, assert_tau
     g = Gold(np.load(GOLD), name)
     os.environ["QB200_DEVICE"] = "0"
     os.environ["QB200_TAU_BATCH"] = "64"
-    L = C.CDLL(DROPIN, mode=os.RTLD_LOCAL)
-    d, r = ref.deterministic_d_r(g.m)
-    P = ref.RefParameters(g.m, 2, d, r)
-    dist = ref.RefDistribution(g.dims, P, g.dimension, g.c0, g.c1, g.cells, g.totals)
-    seed = bytes(range(50, 82))
-    if g.dims == 2:
-        f = getattr(L, SYM_TAU)
-        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
-    else:
-        f = getattr(L, SYM_TAU_LINEAR)
-        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
-    f.restype = C.c_bool
-    rs_gpu, rs_ref = ref.RefRandom(seed), ref.RefRandom(seed)
-    # 128 = two full batches of n = 3, then two full batches of n = 5: the generator must end
-    # where the reference's ends
-    for n, calls in ((3, 128), (5, 128)):
-        want0, want1, want_ok = dist.tau_estimate(rs_ref, n, calls)
-        for i in range(calls):
+    try:
+        L = C.CDLL(libpath, mode=os.RTLD_LOCAL)
+        d, r = ref.deterministic_d_r(g.m)
+        P = ref.RefParameters(g.m, 2, d, r)
+        dist = ref.RefDistribution(g.dims, P, g.dimension, g.c0, g.c1, g.cells, g.totals)
+        seed = bytes(range(50, 82))
+        if g.dims == 2:
+            f = getattr(L, SYM_TAU)
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        else:
+            f = getattr(L, SYM_TAU_LINEAR)
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        f.restype = C.c_bool
+        rs_gpu, rs_ref = ref.RefRandom(seed), ref.RefRandom(seed)
+
+        def call(n):
             t0 = np.zeros(1, dtype=np.longdouble)
             t1 = np.zeros(1, dtype=np.longdouble)
             if g.dims == 2:
                 ok = f(dist.ptr(), rs_gpu.h, n, t0.ctypes.data, t1.ctypes.data)
             else:
                 ok = f(dist.ptr(), rs_gpu.h, n, t0.ctypes.data)
-            assert bool(ok) == bool(want_ok[i]), (n, i)
-            if ok:
-                assert_tau(t0[0], want0[i], g.m)
-                if g.dims == 2:
-                    assert_tau(t1[0], want1[i], g.m)
-            else:
-                assert float(t0[0]) == np.finfo(np.float64).max
-    # words queued by the drop-in (estimates that failed early) are still in front of the
-    # generator: after one more batch-aligned round both streams are in step again only if the
-    # drop-in consumed exactly what the reference consumed. Check through the next estimates.
-    want0, _, want_ok = dist.tau_estimate(rs_ref, 2, 64)
-    for i in range(64):
-        t0 = np.zeros(1, dtype=np.longdouble)
-        t1 = np.zeros(1, dtype=np.longdouble)
-        ok = f(dist.ptr(), rs_gpu.h, 2, t0.ctypes.data, t1.ctypes.data) if g.dims == 2 else \
-            f(dist.ptr(), rs_gpu.h, 2, t0.ctypes.data)
-        assert bool(ok) == bool(want_ok[i])
-        if ok:
-            assert_tau(t0[0], want0[i], g.m)
-    os.environ.pop("QB200_TAU_BATCH", None)
+            return bool(ok), t0[0], t1[0]
+        # two full batches of n = 3, two of n = 5, one of n = 2: words queued by the drop-in
+        # (estimates that failed early) must be consumed exactly as the reference consumes them,
+        # or the later estimates drift apart
+        for n, calls in ((3, 128), (5, 128), (2, 64)):
+            want0, want1, want_ok = dist.tau_estimate(rs_ref, n, calls)
+            for i in range(calls):
+                ok, t0, t1 = call(n)
+                assert ok == bool(want_ok[i]), (n, i)
+                if ok:
+                    assert_tau(t0, want0[i], g.m)
+                    if g.dims == 2:
+                        assert_tau(t1, want1[i], g.m)
+                else:
+                    assert float(t0) == np.finfo(np.float64).max
+        # n = 0: the reference's loop does not run -> FALSE, DBL_MAX, nothing drawn
+        ok, t0, _ = call(0)
+        assert not ok and float(t0) == np.finfo(np.float64).max
+        # (the Random_State itself may be AHEAD of the reference's by the words still queued in
+        # the drop-in -- the logical stream, queue first, is what stays in step, as the rounds
+        # above show)
+    finally:
+        os.environ.pop("QB200_TAU_BATCH", None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["2d", "lin"])
+def test_tau_dropin_called_like_the_reference(name):
+    _tau_dropin_called_like_the_reference(DROPIN, name)
+
+
+@pytest.mark.parametrize("name", ["2d", "lin"])
+def test_tau_dropin_host_logic_on_the_cpu_shim(name):
+    """The same scenario in the GPU-less suite: dropin_tau.cpp and csrc/sampler_host.hpp (stream
+    layout, failure threshold, batching, the queue of pre-drawn words, the fast Keccak stream)
+    over the TEST-ONLY CPU stand-in of the sampler entry points (tests/hostsim/abi_shim.cpp)."""
+    from tests.hostsim import shim_flavour
+    lib = shim_flavour.build_tau()
+    if lib is None:
+        pytest.skip("tests/hostsim/_build/shim/libdropin_tau_shim.so missing (needs /root/reference at build time)")
+    _tau_dropin_called_like_the_reference(lib, name)
 
 
 def test_tau_dropin_draws_the_reference_stream():
