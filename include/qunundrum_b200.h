@@ -15,6 +15,9 @@
  *                                            diagonal_distribution_slice_compute_richardson src/diagonal_distribution_slice_compute_richardson.cpp:17
  *   qb200_text_format_* / qb200_text_parse_* the value loops of *_slice_export / *_slice_import   (see "text export" below)
  *   qb200_sampler_tau_estimate               tau_estimate / tau_estimate_linear             src/tau_estimate.cpp:23,89
+ *   qb200_diagk_sample                       sample_k_from_diagonal_j_eta_pivot             src/sample.cpp:412
+ *   qb200_diagk_h                            diagonal_probability_approx_h                  src/diagonal_probability.cpp:99
+ *   qb200_diagk_tau_estimate                 the sum and log of tau_estimate_diagonal       src/tau_estimate.cpp:135
  *
  * Conventions
  *  - plain pointers and sizes only; all buffers are caller-owned;
@@ -299,6 +302,71 @@ int qb200_sampler_tau_device(qb200_sampler *sampler, uint32_t n, uint32_t count,
 int qb200_sampler_set_force_exact(qb200_sampler *sampler, int on);
 uint64_t qb200_sampler_exact_count(const qb200_sampler *sampler);
 int qb200_sampler_first_failing_word(const qb200_sampler *sampler, uint64_t *word);
+
+/* ---- diagonal distribution: k given (j, eta) ------------------------------------------
+ *
+ * SURVEY.md section 8(f) #3, second half. diagonal_distribution_sample_pair_j_k
+ * (src/diagonal_distribution.cpp:474-552) first draws (j, eta) from the stored distribution and
+ * then calls
+ *   sample_k_from_diagonal_j_eta_pivot   src/sample.cpp:412-646
+ * which evaluates diagonal_probability_approx_h (src/diagonal_probability.cpp:99-162: two
+ * mpfr_sin at 2 (m + sigma) bits) for k = k0, k0 + 1, k0 - 1, ... at 3 (m + sigma) bits until the
+ * pivot is used up. Here the same k comes out of integer arithmetic on m-bit numbers (one
+ * product r j, one product with d, Barrett divisions by r) and a double-double walk; see
+ * qunundrum_b200/csrc/diagk.cuh. A qb200_diagk holds d, r and the reciprocal of r on the device.
+ *
+ * Integers travel as little-endian 32-bit words (mpz_export(buf, &count, -1, 4, 0, 0, z)), one
+ * row per sample, zero padded: j in qb200_diagk_j_limbs() = ceil((m + sigma) / 32) words
+ * (0 <= j < 2^(m + sigma)), k in qb200_diagk_k_limbs() = ceil(l / 32) words.
+ * params: m, l, sigma, d, r of the Diagonal_Parameters (0 < d < r < 2^m, l <= m + sigma,
+ * m + sigma <= 16384). */
+typedef struct qb200_diagk qb200_diagk;
+
+int qb200_diagk_create(qb200_context *ctx, const qb200_params *params, qb200_diagk **sampler);
+void qb200_diagk_destroy(qb200_diagk *sampler);
+uint32_t qb200_diagk_j_limbs(const qb200_diagk *sampler);
+uint32_t qb200_diagk_k_limbs(const qb200_diagk *sampler);
+
+#define QB200_DIAGK_OK 0
+#define QB200_DIAGK_OUT_OF_BOUNDS 1 /* the reference returns FALSE (k = 0, alpha_phi = 0) */
+#define QB200_DIAGK_OK_NEGATIVE_PHI 2 /* success with alpha_phi = 2^(m + sigma - l) (x - 2^l): the
+                                       * reference's mpfr_fmod keeps the sign of a negative dividend
+                                       * (src/sample.cpp:566-574), which happens for
+                                       * j < |eta| 2^(m + sigma) / r only */
+#define QB200_DIAGK_GAVE_UP 4       /* pivot not used up after 2^22 steps although delta_bound
+                                     * allows more (a pivot within ~1e-7 of 1) */
+
+/* n independent calls of sample_k_from_diagonal_j_eta_pivot(parameters, pivot[i], j[i], eta[i],
+ * delta_bound, k, alpha_phi). Outputs (each may be NULL): k[i] (rows of k_limbs words);
+ * alpha_phi[i] / 2^(m + sigma - l) as an unevaluated sum x_hi + x_lo of two doubles (the
+ * binding scales it back: mpfr_set_d / mpfr_add_d / mpfr_mul_2si); delta[i] with
+ * k = (k0 + delta) mod 2^l; status[i]. Error -42: a pivot outside [0, 1] (the reference:
+ * critical("The pivot is out of bounds.")). */
+int qb200_diagk_sample(qb200_diagk *sampler, uint32_t n, const uint32_t *j, const int32_t *eta,
+                       const long double *pivot, uint32_t delta_bound, uint32_t *k, double *x_hi,
+                       double *x_lo, int64_t *delta, int32_t *status);
+
+/* Device-resident form: the rows of n samples in device memory (d_pivot: 16-byte long doubles),
+ * launches on `stream` (NULL = the context's own), no synchronisation. d_out: n records of 32
+ * bytes {double x_hi, x_lo; int64 delta; int32 status; int32 pad}; d_k (rows of k_limbs words)
+ * may be NULL. Scratch of ~20 k bytes per sample (k = bytes of r) is held by the sampler. */
+int qb200_diagk_sample_device(qb200_diagk *sampler, uint32_t n, const uint32_t *d_j,
+                              const int32_t *d_eta, const long double *d_pivot,
+                              uint32_t delta_bound, uint32_t *d_k, void *d_out, void *stream);
+
+/* `count` estimates of n samples each from count * n rows (j, eta, pivot) in sample order:
+ * tau[t] = log2(sum alpha_phi^2 / n) / 2 - (m + sigma - l) and ok[t] = 1, or DBL_MAX and 0 if
+ * a sample of the estimate runs out of bounds or has |eta| > eta_bound
+ * (src/tau_estimate.cpp:163-201). Error -43: a sample gave up, or has status 2 with l > 1000
+ * (alpha_phi^2 ~ 2^(2 l) leaves the doubles). */
+int qb200_diagk_tau_estimate(qb200_diagk *sampler, uint32_t n, uint32_t count, const uint32_t *j,
+                             const int32_t *eta, const long double *pivot, uint32_t delta_bound,
+                             uint32_t eta_bound, long double *tau, uint8_t *ok);
+
+/* diagonal_probability_approx_h at phi[i] = 2 pi (x_hi[i] + x_lo[i]) / 2^l, |x| <= 2^(l - 1),
+ * rounded to long double as mpfr_get_ld does. */
+int qb200_diagk_h(qb200_diagk *sampler, uint32_t n, const double *x_hi, const double *x_lo,
+                  long double *h);
 
 /* ---- introspection (host logic; usable without a GPU) --------------------- */
 

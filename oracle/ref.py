@@ -97,6 +97,11 @@ def lib():
     L.qref_dist_sample_alpha.argtypes = [vp, vp, u32, ldp, ldp, vp]
     L.qref_dist_sample_alpha.restype = u32
     L.qref_tau_estimate.argtypes = [vp, vp, u32, u32, ldp, ldp, vp]
+    L.qref_sample_k_from_diagonal.argtypes = [
+        vp, C.c_longdouble, cp, i32, u32, u32, cp, sz, ldp, cp, sz]
+    L.qref_sample_k_from_diagonal.restype = C.c_int
+    L.qref_diagonal_probability_h.argtypes = [vp, cp, u32]
+    L.qref_diagonal_probability_h.restype = C.c_longdouble
     _lib = L
     return L
 
@@ -343,3 +348,23 @@ class RefDistribution:
         if getattr(self, "h", None):
             lib().qref_dist_free(self.h)
             self.h = None
+
+
+def sample_k_from_diagonal_j_eta_pivot(params: RefDiagonalParameters, pivot, j: int, eta: int,
+                                       delta_bound: int = 0xffffffff, precision: int = 0):
+    """sample_k_from_diagonal_j_eta_pivot (src/sample.cpp:412): (ok, k, alpha_phi scaled by
+    2^-(m + sigma - l) as a long double, alpha_phi with 60 digits as a string)."""
+    kb = C.create_string_buffer(4096)
+    ab = C.create_string_buffer(256)
+    a = np.zeros(1, dtype=np.longdouble)
+    rc = lib().qref_sample_k_from_diagonal(
+        params.h, C.c_longdouble(pivot), str(j).encode(), eta, delta_bound, precision, kb, 4096,
+        a.ctypes.data_as(C.c_void_p), ab, 256)
+    if rc < 0:
+        raise RuntimeError("buffer too small")
+    return bool(rc), int(kb.value), a[0], ab.value.decode()
+
+
+def diagonal_probability_h(params: RefDiagonalParameters, phi: str, precision: int = 0):
+    """diagonal_probability_approx_h (src/diagonal_probability.cpp:99) as a long double."""
+    return np.longdouble(lib().qref_diagonal_probability_h(params.h, phi.encode(), precision))

@@ -13,12 +13,16 @@
  *   linear_distribution_sample_approximate_alpha         src/linear_distribution.cpp:618
  *   sample_approximate_alpha_from_region                 src/sample.cpp:24
  *   tau_estimate / tau_estimate_linear                   src/tau_estimate.cpp:23,89
+ *   sample_k_from_diagonal_j_eta_pivot                   src/sample.cpp:412-646
+ *   diagonal_probability_approx_h                        src/diagonal_probability.cpp:99-162
  *   random_generate / keccak_random_init_seed            src/random.c:88, src/keccak_random.c:52
  *
  * fpLLL is not in the image: lattice_alpha_init / _clear (called by distribution_init, never by
  * the sampling functions above) come from integration/stubs/lattice_stub.cpp.
  */
 #include "common.h"
+#include "diagonal_parameters.h"
+#include "diagonal_probability.h"
 #include "distribution.h"
 #include "distribution_slice.h"
 #include "keccak_random.h"
@@ -26,6 +30,7 @@
 #include "linear_distribution_slice.h"
 #include "parameters.h"
 #include "random.h"
+#include "sample.h"
 #include "tau_estimate.h"
 
 #include <gmp.h>
@@ -237,6 +242,58 @@ void qref_tau_estimate(void *hh, void *rs, uint32_t n, uint32_t count, long doub
     }
     ok[i] = r ? 1 : 0;
   }
+}
+
+/* sample_k_from_diagonal_j_eta_pivot (src/sample.cpp:412) for one (j, eta, pivot): k in decimal,
+ * alpha_phi as a long double after scaling by 2^-(m + sigma - l) at `precision` bits, and with
+ * 60 significant digits (unscaled) in alpha_out. Returns 1 on success, 0 when the reference
+ * returns FALSE, -1 if a buffer is too small. precision = 0: 2 l as in the reference's KAT test
+ * (src/test/test_sample.cpp:717). */
+int qref_sample_k_from_diagonal(void *params, long double pivot, const char *j_dec, int32_t eta,
+                                uint32_t delta_bound, uint32_t precision, char *k_out, size_t k_cap,
+                                long double *alpha_scaled, char *alpha_out, size_t alpha_cap) {
+  ensure_precision();
+  const Diagonal_Parameters *p = (const Diagonal_Parameters *)params;
+  if (0 == precision) precision = 2 * p->l;
+  if (precision < 64) precision = 64;
+  mpz_t j, k;
+  mpz_init(j);
+  mpz_init(k);
+  mpz_set_str(j, j_dec, 10);
+  mpfr_t alpha;
+  mpfr_init2(alpha, precision);
+  const bool ok = sample_k_from_diagonal_j_eta_pivot(p, pivot, j, eta, delta_bound, k, alpha);
+  int rc = ok ? 1 : 0;
+  if (mpz_sizeinbase(k, 10) + 2 > k_cap) {
+    rc = -1;
+  } else {
+    mpz_get_str(k_out, 10, k);
+  }
+  if (alpha_out) mpfr_snprintf(alpha_out, alpha_cap, "%.60Re", alpha);
+  mpfr_mul_2si(alpha, alpha, -((long)p->m + (long)p->sigma - (long)p->l), MPFR_RNDN);
+  *alpha_scaled = mpfr_get_ld(alpha, MPFR_RNDN);
+  mpfr_clear(alpha);
+  mpz_clear(j);
+  mpz_clear(k);
+  return rc;
+}
+
+/* diagonal_probability_approx_h (src/diagonal_probability.cpp:99) at phi given in decimal, read
+ * at `precision` bits (the KAT test uses 3 l, src/test/test_diagonal_probability.cpp:212). */
+long double qref_diagonal_probability_h(void *params, const char *phi_dec, uint32_t precision) {
+  ensure_precision();
+  const Diagonal_Parameters *p = (const Diagonal_Parameters *)params;
+  if (0 == precision) precision = 3 * p->l;
+  if (precision < 64) precision = 64;
+  mpfr_t phi, norm;
+  mpfr_init2(phi, precision);
+  mpfr_init2(norm, precision);
+  mpfr_set_str(phi, phi_dec, 10, MPFR_RNDN);
+  diagonal_probability_approx_h(norm, phi, p);
+  const long double out = mpfr_get_ld(norm, MPFR_RNDN);
+  mpfr_clear(phi);
+  mpfr_clear(norm);
+  return out;
 }
 
 } /* extern "C" */

@@ -395,6 +395,81 @@ def diagonal_probability_approx_f_eta(theta_r, eta: int, p: DiagonalParameters):
         return +norm
 
 
+def diagonal_probability_approx_h(phi, p: DiagonalParameters):
+    """src/diagonal_probability.cpp:99-162: (1 - cos(2^l phi)) / (2^2l (1 - cos phi))."""
+    if phi == 0:
+        return mp.mpf(1)
+    precision = 2 * max(p.m + p.sigma, PRECISION)
+    with mp.workprec(precision):
+        tmp2 = phi / 2
+        tmp = _pow2(p.l)
+        tmp = phi * tmp
+        tmp = tmp / 2
+        tmp = mp.sin(tmp)
+        tmp = tmp * tmp
+        tmp = tmp * 2
+        tmp2 = mp.sin(tmp2)
+        tmp2 = tmp2 * tmp2
+        tmp2 = tmp2 * 2
+        tmp = tmp / tmp2
+        tmp2 = _pow2(2 * p.l)
+        return tmp / tmp2
+
+
+def _mod_reduce(x: int, n: int) -> int:
+    """mod_reduce (src/math.cpp): x mod n on [-n/2, n/2)."""
+    x %= n
+    return x - n if x >= (n >> 1) else x
+
+
+def sample_k_from_diagonal_j_eta_pivot(p: DiagonalParameters, pivot, j: int, eta: int,
+                                       delta_bound: int):
+    """src/sample.cpp:412-646. pivot: np.longdouble. Returns (ok, k, alpha_phi) with alpha_phi
+    an mpf at 3 max(m + sigma, PRECISION) bits."""
+    pivot = np.longdouble(pivot)
+    assert 0 <= pivot <= 1
+    precision = 3 * max(p.m + p.sigma, PRECISION)
+    pow2_m_sigma = 1 << (p.m + p.sigma)
+    pow2_m_sigma_l = 1 << (p.m + p.sigma - p.l)
+    pow2_l = 1 << p.l
+    alpha_r = _mod_reduce(p.r * j, pow2_m_sigma)                      # :477-478
+    with mp.workprec(precision):
+        tmp_z = alpha_r - pow2_m_sigma * eta                           # :481-482
+        tmp = mp.mpf(tmp_z)
+        tmp = tmp * p.d
+        tmp = tmp / p.r
+        tmp = tmp - p.d * j                                            # :490-492
+        tmp = tmp / pow2_m_sigma_l
+        k0 = int(_round_int(tmp)) % pow2_l                             # :498-500
+        scale = +mp.pi
+        scale = scale * 2
+        scale = scale / pow2_m_sigma                                   # :514-517
+        term = mp.mpf(tmp_z)
+        term = term * p.d
+        term = term / p.r
+        term = term - p.d * j
+        term = -term                                                   # :525-537
+        half = mp.mpf(pow2_m_sigma) / 2
+        delta_abs = 0
+        while delta_abs <= delta_bound:
+            for sgn in (1, -1):
+                if delta_abs == 0 and sgn == -1:
+                    continue
+                k = (k0 + sgn * delta_abs) % pow2_l                    # :552-559
+                phi = term + pow2_m_sigma_l * k
+                phi = mp.fmod(phi, mp.mpf(pow2_m_sigma))               # :566-568
+                if phi >= half:
+                    phi = phi - pow2_m_sigma
+                alpha_phi = phi
+                phi = phi * scale
+                h = diagonal_probability_approx_h(phi, p)
+                pivot = pivot - _get_ld(h)                             # :594
+                if pivot <= 0:
+                    return True, k, alpha_phi
+            delta_abs += 1
+    return False, 0, mp.mpf(0)
+
+
 # --------------------------------------------------------------------------- #
 # Slices                                                                      #
 # --------------------------------------------------------------------------- #

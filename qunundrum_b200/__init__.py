@@ -54,6 +54,11 @@ from .host import (  # noqa: F401
     WordStream,
     tau_estimate,
     tau_estimate_linear,
+    # the diagonal distribution's k given (j, eta) (second half)
+    DiagonalKSampler,
+    int_to_limbs,
+    limbs_to_int,
+    sample_k_from_diagonal_j_eta_pivot,
 )
 from . import host  # noqa: F401,E402
 

@@ -1,0 +1,510 @@
+// diagk.cuh -- k given (j, eta) for the diagonal distribution, without multi-thousand-bit floats.
+//
+// Replaces sample_k_from_diagonal_j_eta_pivot (src/sample.cpp:412-646) and its integrand
+// diagonal_probability_approx_h (src/diagonal_probability.cpp:99-162). The reference forms, at
+// 3 (m + sigma) bits of MPFR precision,
+//     term = d j - (d / r) ({r j}_{2^(m+sigma)} - 2^(m+sigma) eta)                  :525-537
+//     k0   = round(-term / 2^(m+sigma-l)) mod 2^l                                    :480-500
+//     phi  = (2 pi / 2^(m+sigma)) {term + 2^(m+sigma-l) k}_{2^(m+sigma)}             :561-583
+// for k = k0, k0 + 1, k0 - 1, ... and subtracts h(phi) = (1 - cos(2^l phi)) / (2^2l (1 - cos phi))
+// from the pivot until it is used up. With r j = alpha_r + q 2^(m+sigma) (q an integer) the term
+// is (d / r) 2^(m+sigma) (q + eta) EXACTLY, so everything the walk needs is the fraction
+//     2^l d (q + eta) / r mod 2^l = Qv + w2 / r,       w = d (q + eta) mod r, (Qv, w2) = divmod(2^l w, r)
+// i.e. integer arithmetic on m-bit numbers: k0 = -(Qv + c) mod 2^l with c = [2 w2 >= r],
+// t = w2 / r - c in [-1/2, 1/2), alpha_phi = 2^(m+sigma-l) (t + delta) and
+//     h = sin^2(pi t) / (2^l sin(pi (t + delta) / 2^l))^2
+// where t is needed to double-double accuracy only. The integers are exact (k matches the
+// reference bit for bit unless a pivot is used up within ~2^-100 of a step, which the reference's
+// own 64-bit rounding of h decides), the walk subtracts h rounded to the x87 format as the
+// reference's `pivot -= mpfr_get_ld(...)` does (:594).
+//
+// The multi-limb part: one product r j, one product d s, Barrett reductions modulo r with a
+// host-prepared reciprocal; 32-bit limbs, product scanning with a 96-bit column accumulator.
+// Operands that are the same for every sample (r, d, mu) are read through `c`; per-sample
+// operands live in caller-provided arrays with a stride (1 on the host, the batch size on the
+// device so that the threads of a warp read consecutive words).
+//
+// __host__ __device__ so that tests/hostsim can run exactly this code on the CPU.
+#pragma once
+
+#include "x87soft.cuh"
+
+namespace qb200 {
+
+struct DiagKConst {
+  uint32_t m, sigma, l;
+  uint32_t n;        // m + sigma
+  uint32_t k;        // limbs of r (top limb non-zero)
+  uint32_t wj;       // limbs of j: ceil(n / 32)
+  uint32_t wl;       // limbs of k: ceil(l / 32)
+  const uint32_t* r;   // k limbs
+  const uint32_t* d;   // k limbs (d < r)
+  const uint32_t* mu;  // k + 2 limbs: floor(2^(64 k) / r)
+  dd r_top;            // the top four limbs of r as a number (limb k - 4 has weight 1)
+};
+
+// Scratch words one sample needs (times the stride).
+QHD uint32_t diagk_scratch_limbs(uint32_t k) { return (2 * k + 2) + (k + 3) + (k + 2) + (k + 2); }
+
+#define QB_DIAGK_OK 0
+#define QB_DIAGK_OK_NEGATIVE_PHI 2  // success, and alpha_phi = 2^(m+sigma-l) (x - 2^l): see diagk_sample
+#define QB_DIAGK_OUT_OF_BOUNDS 1  // the reference returns FALSE: pivot not used up within delta_bound
+#define QB_DIAGK_GAVE_UP 4        // more than QB_DIAGK_MAX_STEPS steps (the caller's delta_bound allows more)
+#define QB_DIAGK_MAX_STEPS (1ull << 22)
+
+// ---- double-double pieces -----------------------------------------------------------
+
+QHD dd dd_div(dd a, dd b) {
+  const double q1 = a.hi / b.hi;
+  dd r = dd_add(a, dd_neg(dd_mul_d(b, q1)));
+  const double q2 = r.hi / b.hi;
+  r = dd_add(r, dd_neg(dd_mul_d(b, q2)));
+  const double q3 = r.hi / b.hi;
+  return dd_add_d(quick_two_sum(q1, q2), q3);
+}
+
+// sin(pi t) for a double-double |t| <= 1/2 to double-double accuracy (~2^-100 relative): Taylor
+// series of sin on |pi t| <= pi/4, of cos on the rest (sin(pi t) = sgn(t) cos(pi (1/2 - |t|))).
+QHD dd sinpi_acc(dd t) {
+  const double SC[16][2] = {
+      {1.0, 0.0},
+      {-0.16666666666666666, -9.25185853854297e-18},
+      {0.008333333333333333, 1.1564823173178714e-19},
+      {-0.0001984126984126984, -1.7209558293420705e-22},
+      {2.7557319223985893e-06, -1.858393274046472e-22},
+      {-2.505210838544172e-08, 1.448814070935912e-24},
+      {1.6059043836821613e-10, 1.2585294588752098e-26},
+      {-7.647163731819816e-13, -7.03872877733453e-30},
+      {2.8114572543455206e-15, 1.6508842730861433e-31},
+      {-8.22063524662433e-18, -2.2141894119604265e-34},
+      {1.9572941063391263e-20, -1.3643503830087908e-36},
+      {-3.868170170630684e-23, 8.843177655482344e-40},
+      {6.446950284384474e-26, -1.9330404233703465e-42},
+      {-9.183689863795546e-29, -1.4303150396787322e-45},
+      {1.1309962886447716e-31, 1.0498015412959506e-47},
+      {-1.216125041553518e-34, -5.586290567888806e-51}};
+  const double CC[16][2] = {
+      {1.0, 0.0},
+      {-0.5, 0.0},
+      {0.041666666666666664, 2.3129646346357427e-18},
+      {-0.001388888888888889, 5.300543954373577e-20},
+      {2.48015873015873e-05, 2.1511947866775882e-23},
+      {-2.755731922398589e-07, -2.3767714622250297e-23},
+      {2.08767569878681e-09, -1.20734505911326e-25},
+      {-1.1470745597729725e-11, -2.0655512752830745e-28},
+      {4.779477332387385e-14, 4.399205485834081e-31},
+      {-1.5619206968586225e-16, -1.1910679660273754e-32},
+      {4.110317623312165e-19, 1.4412973378659527e-36},
+      {-8.896791392450574e-22, 7.911402614872376e-38},
+      {1.6117375710961184e-24, -3.6846573564509766e-41},
+      {-2.4795962632247976e-27, 1.2953730964765229e-43},
+      {3.279889237069838e-30, 1.5117542744029879e-46},
+      {-3.7699876288159054e-33, -2.5870347832750324e-49}};
+  const dd pi = make_dd(QB_PI_HI, QB_PI_LO);
+  const bool neg = t.hi < 0;
+  const dd a = neg ? dd_neg(t) : t;
+  if (a.hi <= 0.25) {
+    const dd y = dd_mul(pi, a);
+    const dd z = dd_mul(y, y);
+    dd p = make_dd(SC[15][0], SC[15][1]);
+    for (int i = 14; i >= 0; i--) p = dd_add(dd_mul(p, z), make_dd(SC[i][0], SC[i][1]));
+    p = dd_mul(p, y);
+    return neg ? dd_neg(p) : p;
+  }
+  const dd y = dd_mul(pi, dd_add_d(dd_neg(a), 0.5));
+  const dd z = dd_mul(y, y);
+  dd p = make_dd(CC[15][0], CC[15][1]);
+  for (int i = 14; i >= 0; i--) p = dd_add(dd_mul(p, z), make_dd(CC[i][0], CC[i][1]));
+  return neg ? dd_neg(p) : p;
+}
+
+QHD uint64_t qb_double_bits(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(d);
+#else
+  uint64_t b;
+  memcpy(&b, &d, 8);
+  return b;
+#endif
+}
+
+// RN64 of a positive double-double (mpfr_get_ld of the reference's h); zero for anything
+// non-positive or below the normal doubles.
+QHD X87 x87_from_dd(dd a) {
+  X87 r = x87_zero();
+  if (!(a.hi > 0)) return r;
+  const uint64_t bh = qb_double_bits(a.hi);
+  const int ebh = (int)((bh >> 52) & 0x7ff);
+  if (ebh == 0 || ebh == 0x7ff) return r;
+  int eh = ebh - 1023;
+  uint64_t Mh = ((bh & 0xfffffffffffffull) | (1ull << 52)) << 11, Ml = 0;  // a.hi = M 2^(eh - 127)
+  bool sticky = false;
+  const uint64_t bl = qb_double_bits(a.lo);
+  const int ebl = (int)((bl >> 52) & 0x7ff);
+  if (ebl != 0 && a.lo != 0.0) {
+    const uint64_t ml = (bl & 0xfffffffffffffull) | (1ull << 52);
+    const int sh = (ebl - 1023) - eh + 75;  // a.lo = ml 2^(sh) in units of 2^(eh - 127)
+    uint64_t Lh = 0, Ll = 0;
+    if (sh >= 0) {
+      // |lo| <= ulp(hi) / 2 keeps sh <= 22
+      Ll = ml << sh;
+      Lh = sh ? (ml >> (64 - sh)) : 0;
+    } else if (sh > -64) {
+      Ll = ml >> (-sh);
+      sticky = (ml << (64 + sh)) != 0;
+    } else {
+      sticky = true;
+    }
+    if (!(bl >> 63)) {
+      const uint64_t s0 = Ml + Ll;
+      const uint64_t c0 = s0 < Ml;
+      const uint64_t s1 = Mh + Lh + c0;
+      const bool carry = (s1 < Mh) || (c0 && s1 == Mh && Lh == ~0ull);
+      Ml = s0;
+      Mh = s1;
+      if (carry) {  // hi had an all-ones mantissa and lo half a last place
+        sticky = sticky || (Ml & 1ull);
+        Ml = (Ml >> 1) | (Mh << 63);
+        Mh = (Mh >> 1) | (1ull << 63);
+        eh += 1;
+      }
+    } else {
+      // M - L - (a fraction if sticky)
+      uint64_t b0 = Ml < Ll;
+      uint64_t s0 = Ml - Ll;
+      uint64_t s1 = Mh - Lh - b0;
+      if (sticky) {
+        b0 = s0 == 0;
+        s0 -= 1;
+        s1 -= b0;
+      }
+      Ml = s0;
+      Mh = s1;
+      if (!(Mh >> 63)) {  // hi was a power of two
+        Mh = (Mh << 1) | (Ml >> 63);
+        Ml <<= 1;  // the shifted-in bit is below the sticky fraction: leave it zero, sticky covers it
+        eh -= 1;
+      }
+    }
+  }
+  r.mant = Mh;
+  r.exp = eh;
+  r.neg = 0;
+  x87_round(&r, Ml, sticky);
+  return r;
+}
+
+// ---- multi-limb pieces ---------------------------------------------------------------
+
+#define QB_L(p, s, i) (p)[(size_t)(i) * (s)]
+
+struct Acc96 {
+  uint64_t lo;
+  uint32_t hi;
+};
+QHD void acc_mad(Acc96& a, uint32_t x, uint32_t y) {
+  const uint64_t p = (uint64_t)x * (uint64_t)y;
+  a.lo += p;
+  a.hi += (a.lo < p) ? 1u : 0u;
+}
+QHD uint32_t acc_pop(Acc96& a) {
+  const uint32_t out = (uint32_t)a.lo;
+  a.lo = (a.lo >> 32) | ((uint64_t)a.hi << 32);
+  a.hi = 0;
+  return out;
+}
+
+// W (k + 1 limbs, strided) >= r (k limbs)?
+QHD bool limbs_ge_r(const uint32_t* W, size_t s, const uint32_t* r, uint32_t k) {
+  if (QB_L(W, s, k)) return true;
+  for (uint32_t i = k; i-- > 0;) {
+    const uint32_t a = QB_L(W, s, i), b = r[i];
+    if (a != b) return a > b;
+  }
+  return true;
+}
+QHD void limbs_sub_r(uint32_t* W, size_t s, const uint32_t* r, uint32_t k) {
+  uint32_t borrow = 0;
+  for (uint32_t i = 0; i < k; i++) {
+    const uint64_t v = (uint64_t)QB_L(W, s, i) - r[i] - borrow;
+    QB_L(W, s, i) = (uint32_t)v;
+    borrow = (uint32_t)(v >> 63);
+  }
+  QB_L(W, s, k) -= borrow;
+}
+
+// Barrett division of x = A[0, 2k) < 2^(64 k) by r (Handbook of Applied Cryptography 14.42):
+// Q (k + 2 limbs) = floor(x / r), W (k + 1 limbs, the top one zero on return) = x mod r. The
+// columns of q1 mu below k - 1 are dropped (the estimate loses at most one more unit, which the
+// final loop restores).
+QHD void diagk_barrett(const DiagKConst& c, const uint32_t* A, uint32_t* Q, uint32_t* W, size_t s) {
+  const uint32_t k = c.k;
+  Acc96 acc;
+  acc.lo = 0;
+  acc.hi = 0;
+  for (uint32_t col = k - 1; col <= 2 * k + 1; col++) {
+    const uint32_t i0 = col > k + 1 ? col - (k + 1) : 0;
+    const uint32_t i1 = col < k ? col : k;
+    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, QB_L(A, s, k - 1 + i), c.mu[col - i]);
+    const uint32_t limb = acc_pop(acc);
+    if (col >= k + 1) QB_L(Q, s, col - (k + 1)) = limb;
+  }
+  QB_L(Q, s, k + 1) = (uint32_t)acc.lo;
+  // W = (x - Q r) mod 2^(32 (k + 1))
+  acc.lo = 0;
+  acc.hi = 0;
+  uint32_t borrow = 0;
+  for (uint32_t col = 0; col <= k; col++) {
+    const uint32_t i1 = col < k - 1 ? col : k - 1;
+    for (uint32_t i = 0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(Q, s, col - i));
+    const uint32_t limb = acc_pop(acc);
+    const uint64_t v = (uint64_t)QB_L(A, s, col) - limb - borrow;
+    QB_L(W, s, col) = (uint32_t)v;
+    borrow = (uint32_t)(v >> 63);
+  }
+  while (limbs_ge_r(W, s, c.r, k)) {
+    limbs_sub_r(W, s, c.r, k);
+    for (uint32_t i = 0; i <= k + 1; i++) {
+      if (++QB_L(Q, s, i)) break;
+    }
+  }
+}
+
+// Four limbs from index `top` downwards as a double-double (limb top - 3 has weight 1).
+QHD dd limbs_top_dd(const uint32_t* p, size_t s, uint32_t top) {
+  dd v = make_dd(0.0, 0.0);
+  double w = 79228162514264337593543950336.0;  // 2^96
+  for (int i = 0; i < 4; i++) {
+    const uint32_t limb = (top >= (uint32_t)i) ? QB_L(p, s, top - i) : 0u;
+    v = dd_add_d(v, (double)limb * w);
+    w *= 2.3283064365386962890625e-10;  // 2^-32
+  }
+  return v;
+}
+
+// h = S / (2^l sin(pi x / 2^l))^2 with S = sin^2(pi x) (diagonal_probability_approx_h at
+// phi = 2 pi x / 2^l, src/diagonal_probability.cpp:99-162), x on [-2^(l-1), 2^(l-1)).
+//   l >= 110: (2^l sin(pi x / 2^l))^2 = (pi x)^2 to double-double accuracy for |x| < 2^33.
+QHD dd diagk_h(uint32_t l, dd S, dd x) {
+  if (x.hi == 0.0) return make_dd(1.0, 0.0);  // :104-108
+  dd D;
+  if (l >= 110) {
+    D = dd_mul(make_dd(QB_PI_HI, QB_PI_LO), x);
+  } else {
+    D = sinpi_acc(dd_mul_pow2(x, ldexp(1.0, -(int)l)));
+    D = dd_mul_pow2(D, ldexp(1.0, (int)l));
+  }
+  return dd_div(S, dd_mul(D, D));
+}
+
+// The walk of src/sample.cpp:539-604 on x = t + delta.
+QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int64_t* delta_out, dd* x_out) {
+  const dd st = sinpi_acc(t);
+  const dd S = dd_mul(st, st);
+  const bool wraps = l < 62;  // k = (k0 + delta) mod 2^l and phi on [-2^(m+sigma-1), 2^(m+sigma-1)) (:566-574)
+  const int64_t M = wraps ? ((int64_t)1 << l) : 0;
+  const double two_l = wraps ? (double)M : 0.0;
+  uint64_t steps = 0;
+  for (uint64_t da = 0; da <= delta_bound; da++) {
+    for (int sg = 1; sg >= -1; sg -= 2) {
+      if (da == 0 && sg < 0) continue;
+      if (++steps > QB_DIAGK_MAX_STEPS) return QB_DIAGK_GAVE_UP;
+      const int64_t delta = sg > 0 ? (int64_t)da : -(int64_t)da;
+      dd x;
+      if (wraps) {
+        int64_t dm = ((delta % M) + M) % M;
+        if (dm >= M / 2) dm -= M;  // |dm| <= 2^32 or < 2^53: exact as a double
+        x = dd_add_d(t, (double)dm);
+        if (x.hi >= 0.5 * two_l) x = dd_add_d(x, -two_l);
+        if (x.hi < -0.5 * two_l) x = dd_add_d(x, two_l);
+      } else {
+        x = dd_add_d(t, (double)delta);
+      }
+      pivot = x87_add(pivot, x87_neg(x87_from_dd(diagk_h(l, S, x))));
+      if (x87_nonpositive(pivot)) {
+        *delta_out = delta;
+        *x_out = x;
+        return QB_DIAGK_OK;
+      }
+    }
+  }
+  *delta_out = 0;
+  *x_out = make_dd(0.0, 0.0);
+  return QB_DIAGK_OUT_OF_BOUNDS;
+}
+
+// One sample. j: c.wj limbs (j < 2^n), stride sj. scratch: diagk_scratch_limbs(k) words, stride
+// ss. k_out: c.wl limbs, stride sk (may be null). x_out = alpha_phi / 2^(m + sigma - l).
+QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, size_t sj, int32_t eta, X87 pivot,
+                     uint64_t delta_bound, uint32_t* scratch, size_t ss, uint32_t* k_out, size_t sk,
+                     dd* x_out, int64_t* delta_out) {
+  const uint32_t k = c.k;
+  uint32_t* A = scratch;                         // 2k + 2
+  uint32_t* Q = A + (size_t)(2 * k + 2) * ss;    // k + 3
+  uint32_t* W = Q + (size_t)(k + 3) * ss;        // k + 2
+  uint32_t* S = W + (size_t)(k + 2) * ss;        // k + 2
+
+  // ---- q = round-to-centred quotient of r j by 2^n (alpha_r = {r j}_{2^n}, :477-478) ----
+  const uint32_t cs = c.n >> 5, sh = c.n & 31;
+  Acc96 acc;
+  acc.lo = 0;
+  acc.hi = 0;
+  uint32_t below = 0;  // column cs - 1
+  const uint32_t ncol = k + c.wj;
+  for (uint32_t col = 0; col < ncol; col++) {
+    const uint32_t i0 = col >= c.wj ? col - c.wj + 1 : 0;
+    const uint32_t i1 = col < k - 1 ? col : k - 1;
+    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(j, sj, col - i));
+    const uint32_t limb = acc_pop(acc);
+    if (col + 1 == cs) below = limb;
+    if (col >= cs) QB_L(S, ss, col - cs) = limb;
+  }
+  const uint32_t ns = ncol - cs;  // <= k + 1 limbs hold Z >> (32 cs)
+  for (uint32_t i = ns; i < k + 2; i++) QB_L(S, ss, i) = 0;
+  uint32_t half_bit;
+  if (sh == 0) {
+    half_bit = below >> 31;
+  } else {
+    half_bit = (QB_L(S, ss, 0) >> (sh - 1)) & 1u;
+    for (uint32_t i = 0; i < k + 1; i++)
+      QB_L(S, ss, i) = (QB_L(S, ss, i) >> sh) | (QB_L(S, ss, i + 1) << (32 - sh));
+    QB_L(S, ss, k + 1) >>= sh;
+  }
+  // ---- s = q + eta, brought to [0, r): adding r to s adds the integer d to d s / r ----
+  int64_t carry = (int64_t)half_bit + (int64_t)eta;
+  for (uint32_t i = 0; i < k + 2; i++) {
+    const int64_t v = (int64_t)QB_L(S, ss, i) + carry;
+    QB_L(S, ss, i) = (uint32_t)v;
+    carry = v >> 32;
+    if (carry == 0) break;
+  }
+  const bool s_negative = carry < 0;
+  bool whole = false;  // q + eta < 0 and d |q + eta| >= r: the unreduced phi is negative
+  if (s_negative) {
+    const uint32_t abs_s = 0u - QB_L(S, ss, 0);  // |q + eta| <= |eta|
+    uint64_t cw = 0;
+    for (uint32_t i = 0; i < k; i++) {
+      const uint64_t v = (uint64_t)c.d[i] * abs_s + cw;
+      QB_L(A, ss, i) = (uint32_t)v;
+      cw = v >> 32;
+    }
+    QB_L(A, ss, k) = (uint32_t)cw;
+    whole = limbs_ge_r(A, ss, c.r, k);
+    uint64_t cy = 0;
+    for (uint32_t i = 0; i < k + 2; i++) {
+      const uint64_t v = (uint64_t)QB_L(S, ss, i) + (i < k ? c.r[i] : 0u) + cy;
+      QB_L(S, ss, i) = (uint32_t)v;
+      cy = v >> 32;
+    }
+  }
+  for (int guard = 0; guard < 64; guard++) {
+    if (QB_L(S, ss, k + 1) == 0 && !limbs_ge_r(S, ss, c.r, k)) break;
+    // s >= r: s <= r + |eta| + 1 for j < 2^n, so one round is the rule
+    uint32_t borrow = 0;
+    for (uint32_t i = 0; i < k + 2; i++) {
+      const uint64_t v = (uint64_t)QB_L(S, ss, i) - (i < k ? c.r[i] : 0u) - borrow;
+      QB_L(S, ss, i) = (uint32_t)v;
+      borrow = (uint32_t)(v >> 63);
+    }
+  }
+  // ---- w = d s mod r ----
+  acc.lo = 0;
+  acc.hi = 0;
+  for (uint32_t col = 0; col < 2 * k; col++) {
+    const uint32_t i0 = col >= k ? col - k + 1 : 0;
+    const uint32_t i1 = col < k - 1 ? col : k - 1;
+    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.d[i], QB_L(S, ss, col - i));
+    QB_L(A, ss, col) = acc_pop(acc);
+  }
+  diagk_barrett(c, A, Q, W, ss);
+  // ---- (Qv, w2) = divmod(2^l w, r), at most 32 k bits of the shift at a time ----
+  const uint32_t chunk = 32 * k;
+  const uint32_t nch = (c.l + chunk - 1) / chunk;
+  if (k_out)
+    for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, sk, i) = 0;
+  for (uint32_t ci = 0; ci < nch; ci++) {
+    const uint32_t bits = ci == 0 ? c.l - chunk * (nch - 1) : chunk;
+    const uint32_t ls = bits >> 5, bs = bits & 31;
+    for (uint32_t i = 0; i < 2 * k; i++) {
+      uint32_t v = 0;
+      if (i >= ls && i - ls < k) v = QB_L(W, ss, i - ls) << bs;
+      if (bs && i >= ls + 1 && i - ls - 1 < k) v |= QB_L(W, ss, i - ls - 1) >> (32 - bs);
+      QB_L(A, ss, i) = v;
+    }
+    diagk_barrett(c, A, Q, W, ss);
+    if (k_out) {
+      const uint32_t off = k * (nch - 1 - ci), nq = (bits + 31) >> 5;
+      for (uint32_t i = 0; i < nq && off + i < c.wl; i++) QB_L(k_out, sk, off + i) = QB_L(Q, ss, i);
+    }
+  }
+  // ---- t = w2 / r - c ----
+  // 2 w2 >= r  <=>  w2 >= r - w2: form r - w2 in A and compare
+  uint32_t borrow = 0;
+  for (uint32_t i = 0; i < k; i++) {
+    const uint64_t v = (uint64_t)c.r[i] - QB_L(W, ss, i) - borrow;
+    QB_L(A, ss, i) = (uint32_t)v;
+    borrow = (uint32_t)(v >> 63);
+  }
+  bool cflag = true;  // w2 >= r - w2
+  for (uint32_t i = k; i-- > 0;) {
+    const uint32_t a = QB_L(W, ss, i), b = QB_L(A, ss, i);
+    if (a != b) {
+      cflag = a > b;
+      break;
+    }
+  }
+  const uint32_t* N = cflag ? A : W;
+  int top = -1;
+  for (uint32_t i = k; i-- > 0;) {
+    if (QB_L(N, ss, i)) {
+      top = (int)i;
+      break;
+    }
+  }
+  dd t = make_dd(0.0, 0.0);
+  if (top >= 0) {
+    const int e = 32 * (top - (int)k + 1);
+    if (e >= -960) {
+      t = dd_div(limbs_top_dd(N, ss, (uint32_t)top), c.r_top);
+      t = dd_mul_pow2(t, pow2i(e));
+      if (cflag) t = dd_neg(t);
+    }
+  }
+  // ---- the walk ----
+  int64_t delta = 0;
+  dd x = make_dd(0.0, 0.0);
+  const int status = diagk_walk(c.l, t, pivot, delta_bound, &delta, &x);
+  if (status != QB_DIAGK_OK) {
+    if (k_out)
+      for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, sk, i) = 0;
+    *x_out = make_dd(0.0, 0.0);
+    *delta_out = 0;
+    return status;
+  }
+  // mpfr_fmod keeps the sign of a negative dividend (:566-574): with q + eta < 0 and
+  // d |q + eta| >= r the unreduced phi is negative and a positive residue is not folded back
+  // (j < |eta| 2^(m+sigma) / r: never drawn in practice). 2^l may not be a double: reported as
+  // a status, the subtraction is the caller's.
+  const int ok_status = (whole && x.hi > 0.0) ? QB_DIAGK_OK_NEGATIVE_PHI : QB_DIAGK_OK;
+  if (k_out) {
+    // k = (-(Qv + c) + delta) mod 2^l = -(Qv + c - delta) mod 2^l
+    int64_t cy = (int64_t)(cflag ? 1 : 0) - delta;
+    for (uint32_t i = 0; i < c.wl; i++) {
+      const int64_t v = (int64_t)QB_L(k_out, sk, i) + cy;
+      QB_L(k_out, sk, i) = (uint32_t)v;
+      cy = v >> 32;
+    }
+    uint32_t one = 1;
+    for (uint32_t i = 0; i < c.wl; i++) {
+      const uint64_t v = (uint64_t)(~QB_L(k_out, sk, i)) + one;
+      QB_L(k_out, sk, i) = (uint32_t)v;
+      one = (uint32_t)(v >> 32);
+    }
+    if (c.l & 31) QB_L(k_out, sk, c.wl - 1) &= (1u << (c.l & 31)) - 1u;
+  }
+  *x_out = x;
+  *delta_out = delta;
+  return ok_status;
+}
+
+}  // namespace qb200

@@ -1,0 +1,69 @@
+// diagk_host.hpp -- per-distribution constants of the diagonal k sampler (no CUDA in this file).
+//
+// Once per (m, sigma, l, d, r): the limbs of r and d, the Barrett reciprocal
+// mu = floor(2^(64 k) / r) and the top of r as a double-double (diagk.cuh). Shared by the CUDA
+// library (qb200_diagk.cu) and the test-only CPU twin of tests/hostsim.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "bigint.hpp"
+#include "diagk.cuh"
+
+namespace qb200 {
+
+struct DiagKHost {
+  std::vector<uint32_t> r, d, mu;
+  DiagKConst c;
+};
+
+inline std::vector<uint32_t> limbs32(const BigUInt& x, size_t n) {
+  std::vector<uint32_t> out(n, 0);
+  for (size_t i = 0; i < n; i++) {
+    const size_t w = i / 2;
+    if (w < x.w.size()) out[i] = (uint32_t)(x.w[w] >> (32 * (i % 2)));
+  }
+  return out;
+}
+
+// 0, or a negative code with *err set. The pointers of h->c refer to the vectors of *h (host
+// side); the CUDA library replaces them by device copies.
+inline int diagk_prepare(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* d_be, size_t d_len,
+                         const uint8_t* r_be, size_t r_len, DiagKHost* h, std::string* err) {
+  if (!d_be || !r_be) {
+    *err = "null argument";
+    return -1;
+  }
+  const BigUInt d = BigUInt::from_bytes_be(d_be, d_len), r = BigUInt::from_bytes_be(r_be, r_len);
+  if (r.is_zero() || d.is_zero() || BigUInt::cmp(d, r) >= 0) {
+    *err = "diagonal k sampler: need 0 < d < r";
+    return -2;
+  }
+  if (m < 32 || l == 0 || l > m + sigma || r.bit_length() > m || m + sigma > (1u << 20)) {
+    *err = "diagonal k sampler: need m >= 32, 0 < l <= m + sigma, r < 2^m";
+    return -3;
+  }
+  const uint32_t k = (uint32_t)((r.bit_length() + 31) / 32);
+  h->r = limbs32(r, k);
+  h->d = limbs32(d, k);
+  BigUInt q, rem;
+  BigUInt::divmod(BigUInt::pow2(64ull * k), r, q, rem);
+  h->mu = limbs32(q, k + 2);
+  DiagKConst& c = h->c;
+  c.m = m;
+  c.sigma = sigma;
+  c.l = l;
+  c.n = m + sigma;
+  c.k = k;
+  c.wj = (c.n + 31) / 32;
+  c.wl = (l + 31) / 32;
+  c.r = h->r.data();
+  c.d = h->d.data();
+  c.mu = h->mu.data();
+  c.r_top = limbs_top_dd(h->r.data(), 1, k - 1);
+  return 0;
+}
+
+}  // namespace qb200

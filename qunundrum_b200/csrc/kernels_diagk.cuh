@@ -1,0 +1,136 @@
+// kernels_diagk.cuh -- kernels of the diagonal k sampler (diagk.cuh has the per-sample code and
+// the reference citations).
+//
+//   k_diagk_gather   j of a chunk from the caller's row-per-sample layout to limb-major
+//                    (word i of sample g at [i * B + g]) so that the threads of a warp, which
+//                    all work on the same limb index at the same time, read consecutive words.
+//   k_diagk          one thread per sample: r j, d (q + eta) mod r, divmod(2^l w, r) in 32-bit
+//                    limbs (about 5 k^2 multiply-adds, k = limbs of r), then the walk over delta
+//                    in double-double. r, d and the Barrett reciprocal are staged in shared
+//                    memory (every thread reads the same limb: broadcast). Integer-pipe bound.
+//   k_diagk_scatter  k of a chunk back to row-per-sample.
+//   k_diagk_tau      one thread per estimate: sum of (alpha_phi / 2^(m+sigma-l))^2 in sample
+//                    order (tau_estimate_diagonal, src/tau_estimate.cpp:135-210).
+//   k_diagk_h        h at given x (diagonal_probability_approx_h), for the known-answer tests.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "diagk.cuh"
+#include "sampler.cuh"
+
+namespace qb200 {
+
+__global__ void k_diagk_gather(const uint32_t* __restrict__ rows, uint32_t w, uint32_t B,
+                               uint32_t* __restrict__ cols) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)w * B) return;
+  const uint32_t i = (uint32_t)(t / B), g = (uint32_t)(t - (uint64_t)i * B);
+  cols[t] = rows[(size_t)g * w + i];
+}
+
+__global__ void k_diagk_scatter(const uint32_t* __restrict__ cols, uint32_t w, uint32_t B,
+                                uint32_t* __restrict__ rows) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)w * B) return;
+  const uint32_t g = (uint32_t)(t / w), i = (uint32_t)(t - (uint64_t)g * w);
+  rows[t] = cols[(size_t)i * B + g];
+}
+
+struct DiagKOut {
+  double x_hi, x_lo;   // alpha_phi / 2^(m + sigma - l)
+  long long delta;
+  int status;
+  int pad;
+};
+
+__global__ void __launch_bounds__(128) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
+                                                const int32_t* __restrict__ eta,
+                                                const RawX87* __restrict__ pivot,
+                                                unsigned long long delta_bound, uint32_t B,
+                                                uint32_t* __restrict__ scratch, uint32_t* __restrict__ kT,
+                                                DiagKOut* __restrict__ out) {
+  extern __shared__ uint32_t sh[];
+  const uint32_t k = c.k;
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+    sh[i] = c.r[i];
+    sh[k + i] = c.d[i];
+  }
+  for (uint32_t i = threadIdx.x; i < k + 2; i += blockDim.x) sh[2 * k + i] = c.mu[i];
+  __syncthreads();
+  c.r = sh;
+  c.d = sh + k;
+  c.mu = sh + 2 * k;
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B) return;
+  bool ok = true;
+  const X87 p = x87_load(pivot + g, &ok);
+  DiagKOut o;
+  o.pad = 0;
+  if (!ok || p.neg || p.exp > 0 || (p.exp == 0 && p.mant != 0x8000000000000000ull)) {
+    // the reference: critical("The pivot is out of bounds.") (src/sample.cpp:421-425)
+    o.x_hi = o.x_lo = 0.0;
+    o.delta = 0;
+    o.status = -1;
+    if (kT)
+      for (uint32_t i = 0; i < c.wl; i++) kT[(size_t)i * B + g] = 0;
+    out[g] = o;
+    return;
+  }
+  dd x;
+  int64_t delta;
+  o.status = diagk_sample(c, jT + g, B, eta[g], p, delta_bound, scratch + g, B, kT ? kT + g : nullptr, B,
+                          &x, &delta);
+  o.x_hi = x.hi;
+  o.x_lo = x.lo;
+  o.delta = (long long)delta;
+  out[g] = o;
+}
+
+// status[t] = 0, 1 (a sample ran out of bounds, or |eta| > eta_bound: the reference breaks and
+// returns FALSE), or the first other status of the estimate's samples (2: a sample with a negative
+// unreduced phi and l > 1000, whose alpha_phi^2 ~ 2^(2 l) leaves the doubles).
+__global__ void k_diagk_tau(const DiagKOut* __restrict__ out, const int32_t* __restrict__ eta, uint32_t l,
+                            uint32_t n, uint32_t count, uint32_t eta_bound, double* __restrict__ sums,
+                            int* __restrict__ status) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  dd s = make_dd(0.0, 0.0);
+  int st = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const DiagKOut o = out[(size_t)t * n + i];
+    if (o.status != 0 && !(o.status == QB_DIAGK_OK_NEGATIVE_PHI && l <= 1000)) {
+      st = o.status;
+      break;
+    }
+    const int32_t e = eta[(size_t)t * n + i];
+    if ((uint32_t)(e < 0 ? -e : e) > eta_bound) {
+      st = QB_DIAGK_OUT_OF_BOUNDS;
+      break;
+    }
+    dd x = make_dd(o.x_hi, o.x_lo);
+    if (o.status == QB_DIAGK_OK_NEGATIVE_PHI) x = dd_add_d(x, -ldexp(1.0, (int)l));
+    s = dd_add(s, dd_mul(x, x));
+  }
+  sums[2 * (size_t)t] = s.hi;
+  sums[2 * (size_t)t + 1] = s.lo;
+  status[t] = st;
+}
+
+__global__ void k_diagk_h(uint32_t l, uint32_t n, const double* __restrict__ x_hi,
+                          const double* __restrict__ x_lo, RawX87* __restrict__ out) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const dd x = quick_two_sum(x_hi[g], x_lo[g]);
+  dd t = dd_add_d(x, -rint(x.hi));
+  if (t.hi > 0.5) t = dd_add_d(t, -1.0);
+  if (t.hi < -0.5) t = dd_add_d(t, 1.0);
+  const dd st = sinpi_acc(t);
+  const X87 h = x87_from_dd(diagk_h(l, dd_mul(st, st), x));
+  RawX87 r;
+  r.mant = h.mant;
+  r.se = h.mant ? (uint64_t)(h.exp + 16383) : 0;
+  out[g] = r;
+}
+
+}  // namespace qb200

@@ -1,0 +1,258 @@
+// qb200_diagk.cu -- C ABI of the diagonal k sampler (include/qunundrum_b200.h, "diagonal (j, k)").
+//
+// Replaces sample_k_from_diagonal_j_eta_pivot (src/sample.cpp:412-646), the second half of
+// diagonal_distribution_sample_pair_j_k (src/diagonal_distribution.cpp:474-552), and the sum of
+// tau_estimate_diagonal (src/tau_estimate.cpp:135-210), by batched kernels. There is no CPU
+// path: the entry points fail without a CUDA device like the rest of the library.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/qunundrum_b200.h"
+#include "ctx_access.hpp"
+#include "diagk_host.hpp"
+#include "kernels_diagk.cuh"
+
+using namespace qb200;
+
+#define QD_CUDA(call)                                                                   \
+  do {                                                                                  \
+    const cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess)                                                              \
+      return set_error(-100, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+namespace {
+
+struct DBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DBuf() {
+    if (p) cudaFree(p);
+  }
+  int reserve(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    QD_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return 0;
+  }
+  template <class T>
+  T* as() const {
+    return (T*)p;
+  }
+};
+
+}  // namespace
+
+struct qb200_diagk {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t* launches = nullptr;
+  DiagKHost host;
+  DiagKConst dev;  // pointers into `consts`
+  DBuf consts, rows_j, cols_j, eta, pivot, scratch, cols_k, rows_k, out, sums, status, xh, xl, hout;
+  uint32_t chunk = 0;
+};
+
+// Samples per launch: enough threads for every SM, scratch of at most ~1 GB.
+static uint32_t pick_chunk(const qb200_diagk* s, int sm_count) {
+  const size_t per = ((size_t)diagk_scratch_limbs(s->host.c.k) + s->host.c.wj + s->host.c.wl) * 4;
+  size_t b = (size_t)sm_count * 2048;
+  while (b > 4096 && b * per > ((size_t)1 << 30)) b /= 2;
+  return (uint32_t)b;
+}
+
+extern "C" {
+
+int qb200_diagk_create(qb200_context* ctx, const qb200_params* params, qb200_diagk** out) {
+  if (out) *out = nullptr;
+  if (!ctx || !params || !out) return set_error(-1, "null argument");
+  std::unique_ptr<qb200_diagk> s(new qb200_diagk);
+  std::string err;
+  const int rc = diagk_prepare(params->m, params->sigma, params->l, params->d_be, params->d_len,
+                               params->r_be, params->r_len, &s->host, &err);
+  if (rc) return set_error(rc, err);
+  if (params->m + params->sigma > 16384)
+    return set_error(-4, "diagonal k sampler: m + sigma above 16384 bits is not supported");
+  const CtxView cv = ctx_view(ctx);
+  QD_CUDA(cudaSetDevice(cv.device));
+  s->device = cv.device;
+  s->stream = cv.stream;
+  s->launches = cv.launches;
+  const uint32_t k = s->host.c.k;
+  if (s->consts.reserve((size_t)(3 * k + 2) * 4)) return -100;
+  uint32_t* c = s->consts.as<uint32_t>();
+  QD_CUDA(cudaMemcpy(c, s->host.r.data(), (size_t)k * 4, cudaMemcpyHostToDevice));
+  QD_CUDA(cudaMemcpy(c + k, s->host.d.data(), (size_t)k * 4, cudaMemcpyHostToDevice));
+  QD_CUDA(cudaMemcpy(c + 2 * k, s->host.mu.data(), (size_t)(k + 2) * 4, cudaMemcpyHostToDevice));
+  s->dev = s->host.c;
+  s->dev.r = c;
+  s->dev.d = c + k;
+  s->dev.mu = c + 2 * k;
+  s->chunk = pick_chunk(s.get(), cv.sm_count);
+  *out = s.release();
+  return 0;
+}
+
+void qb200_diagk_destroy(qb200_diagk* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  delete s;
+}
+
+uint32_t qb200_diagk_j_limbs(const qb200_diagk* s) { return s ? s->host.c.wj : 0; }
+uint32_t qb200_diagk_k_limbs(const qb200_diagk* s) { return s ? s->host.c.wl : 0; }
+
+// The launches of one chunk of B samples whose rows already lie in device memory.
+static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const int32_t* d_eta,
+                        const RawX87* d_pivot, uint32_t delta_bound, uint32_t* d_k_rows, DiagKOut* d_out,
+                        cudaStream_t stream) {
+  const DiagKConst& c = s->host.c;
+  const size_t scr = diagk_scratch_limbs(c.k);
+  if (s->cols_j.reserve((size_t)B * c.wj * 4) || s->scratch.reserve((size_t)B * scr * 4)) return -100;
+  if (d_k_rows && s->cols_k.reserve((size_t)B * c.wl * 4)) return -100;
+  const uint64_t nj = (uint64_t)B * c.wj;
+  k_diagk_gather<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(d_j, c.wj, B, s->cols_j.as<uint32_t>());
+  const size_t shmem = (size_t)(3 * c.k + 2) * 4;
+  k_diagk<<<(B + 127) / 128, 128, shmem, stream>>>(s->dev, s->cols_j.as<uint32_t>(), d_eta, d_pivot,
+                                                  (unsigned long long)delta_bound, B,
+                                                  s->scratch.as<uint32_t>(),
+                                                  d_k_rows ? s->cols_k.as<uint32_t>() : nullptr, d_out);
+  *s->launches += 2;
+  if (d_k_rows) {
+    const uint64_t nk = (uint64_t)B * c.wl;
+    k_diagk_scatter<<<(unsigned)((nk + 255) / 256), 256, 0, stream>>>(s->cols_k.as<uint32_t>(), c.wl, B,
+                                                                     d_k_rows);
+    *s->launches += 1;
+  }
+  QD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// One chunk of B samples from host rows; results stay on the device in s->out / s->rows_k.
+static int run_chunk(qb200_diagk* s, uint32_t B, const uint32_t* j, const int32_t* eta,
+                     const long double* pivot, uint32_t delta_bound, bool want_k) {
+  const DiagKConst& c = s->host.c;
+  if (s->rows_j.reserve((size_t)B * c.wj * 4) || s->eta.reserve((size_t)B * 4) ||
+      s->pivot.reserve((size_t)B * 16) || s->out.reserve((size_t)B * sizeof(DiagKOut)))
+    return -100;
+  if (want_k && s->rows_k.reserve((size_t)B * c.wl * 4)) return -100;
+  QD_CUDA(cudaMemcpyAsync(s->rows_j.p, j, (size_t)B * c.wj * 4, cudaMemcpyHostToDevice, s->stream));
+  QD_CUDA(cudaMemcpyAsync(s->eta.p, eta, (size_t)B * 4, cudaMemcpyHostToDevice, s->stream));
+  QD_CUDA(cudaMemcpyAsync(s->pivot.p, pivot, (size_t)B * 16, cudaMemcpyHostToDevice, s->stream));
+  return launch_chunk(s, B, s->rows_j.as<uint32_t>(), s->eta.as<int32_t>(), s->pivot.as<RawX87>(), delta_bound,
+                      want_k ? s->rows_k.as<uint32_t>() : nullptr, s->out.as<DiagKOut>(), s->stream);
+}
+
+int qb200_diagk_sample_device(qb200_diagk* s, uint32_t n, const uint32_t* d_j, const int32_t* d_eta,
+                              const long double* d_pivot, uint32_t delta_bound, uint32_t* d_k,
+                              void* d_out, void* stream) {
+  if (!s || !d_j || !d_eta || !d_pivot || !d_out) return set_error(-1, "null argument");
+  QD_CUDA(cudaSetDevice(s->device));
+  return launch_chunk(s, n, d_j, d_eta, (const RawX87*)d_pivot, delta_bound, d_k, (DiagKOut*)d_out,
+                      stream ? (cudaStream_t)stream : s->stream);
+}
+
+int qb200_diagk_sample(qb200_diagk* s, uint32_t n, const uint32_t* j, const int32_t* eta,
+                       const long double* pivot, uint32_t delta_bound, uint32_t* k, double* x_hi,
+                       double* x_lo, int64_t* delta, int32_t* status) {
+  if (!s || !j || !eta || !pivot) return set_error(-1, "null argument");
+  QD_CUDA(cudaSetDevice(s->device));
+  const DiagKConst& c = s->host.c;
+  std::vector<DiagKOut> ho;
+  for (uint32_t done = 0; done < n;) {
+    const uint32_t B = n - done < s->chunk ? n - done : s->chunk;
+    const int rc = run_chunk(s, B, j + (size_t)done * c.wj, eta + done, pivot + done, delta_bound, k != nullptr);
+    if (rc) return rc;
+    ho.resize(B);
+    QD_CUDA(cudaMemcpyAsync(ho.data(), s->out.p, (size_t)B * sizeof(DiagKOut), cudaMemcpyDeviceToHost, s->stream));
+    if (k)
+      QD_CUDA(cudaMemcpyAsync(k + (size_t)done * c.wl, s->rows_k.p, (size_t)B * c.wl * 4, cudaMemcpyDeviceToHost,
+                              s->stream));
+    QD_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t i = 0; i < B; i++) {
+      if (ho[i].status < 0) return set_error(-42, "The pivot is out of bounds.");
+      if (x_hi) x_hi[done + i] = ho[i].x_hi;
+      if (x_lo) x_lo[done + i] = ho[i].x_lo;
+      if (delta) delta[done + i] = ho[i].delta;
+      if (status) status[done + i] = ho[i].status;
+    }
+    done += B;
+  }
+  return 0;
+}
+
+int qb200_diagk_tau_estimate(qb200_diagk* s, uint32_t n, uint32_t count, const uint32_t* j,
+                             const int32_t* eta, const long double* pivot, uint32_t delta_bound,
+                             uint32_t eta_bound, long double* tau, uint8_t* ok) {
+  if (!s || !j || !eta || !pivot || !tau || !ok) return set_error(-1, "null argument");
+  if (n == 0) return set_error(-2, "n must be positive");
+  QD_CUDA(cudaSetDevice(s->device));
+  const DiagKConst& c = s->host.c;
+  uint32_t per = s->chunk / n;  // whole estimates per launch
+  if (per == 0) per = 1;
+  std::vector<double> hs;
+  std::vector<int> hst;
+  for (uint32_t done = 0; done < count;) {
+    const uint32_t E = count - done < per ? count - done : per;
+    const uint32_t B = E * n;
+    const size_t first = (size_t)done * n;
+    const int rc = run_chunk(s, B, j + first * c.wj, eta + first, pivot + first, delta_bound, false);
+    if (rc) return rc;
+    if (s->sums.reserve((size_t)E * 16) || s->status.reserve((size_t)E * 4)) return -100;
+    k_diagk_tau<<<(E + 127) / 128, 128, 0, s->stream>>>(s->out.as<DiagKOut>(), s->eta.as<int32_t>(), c.l, n, E,
+                                                        eta_bound, s->sums.as<double>(), s->status.as<int>());
+    *s->launches += 1;
+    QD_CUDA(cudaGetLastError());
+    hs.resize((size_t)E * 2);
+    hst.resize(E);
+    QD_CUDA(cudaMemcpyAsync(hs.data(), s->sums.p, (size_t)E * 16, cudaMemcpyDeviceToHost, s->stream));
+    QD_CUDA(cudaMemcpyAsync(hst.data(), s->status.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
+    QD_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t t = 0; t < E; t++) {
+      if (hst[t] < 0) return set_error(-42, "The pivot is out of bounds.");
+      if (hst[t] == QB_DIAGK_OK_NEGATIVE_PHI || hst[t] == QB_DIAGK_GAVE_UP)
+        return set_error(-43, hst[t] == QB_DIAGK_GAVE_UP
+                                  ? "diagonal k sampler: gave up after 2^22 steps"
+                                  : "diagonal k sampler: j below |eta| 2^(m + sigma) / r with l > 1000");
+      if (hst[t] != 0) {
+        // src/tau_estimate.cpp:190-193
+        ok[done + t] = 0;
+        tau[done + t] = DBL_MAX;
+        continue;
+      }
+      // log2(sum alpha_phi^2 / n) / 2 - (m + sigma - l) with alpha_phi = 2^(m+sigma-l) x (:194-201)
+      const long double a = ((long double)hs[2 * t] + (long double)hs[2 * t + 1]) / (long double)n;
+      ok[done + t] = 1;
+      tau[done + t] = log2l(a) / 2;
+    }
+    done += E;
+  }
+  return 0;
+}
+
+int qb200_diagk_h(qb200_diagk* s, uint32_t n, const double* x_hi, const double* x_lo, long double* h) {
+  if (!s || !x_hi || !x_lo || !h) return set_error(-1, "null argument");
+  QD_CUDA(cudaSetDevice(s->device));
+  if (n == 0) return 0;
+  if (s->xh.reserve((size_t)n * 8) || s->xl.reserve((size_t)n * 8) || s->hout.reserve((size_t)n * 16)) return -100;
+  QD_CUDA(cudaMemcpyAsync(s->xh.p, x_hi, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+  QD_CUDA(cudaMemcpyAsync(s->xl.p, x_lo, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+  k_diagk_h<<<(n + 127) / 128, 128, 0, s->stream>>>(s->host.c.l, n, s->xh.as<double>(), s->xl.as<double>(),
+                                                     s->hout.as<RawX87>());
+  *s->launches += 1;
+  QD_CUDA(cudaGetLastError());
+  QD_CUDA(cudaMemcpyAsync(h, s->hout.p, (size_t)n * 16, cudaMemcpyDeviceToHost, s->stream));
+  QD_CUDA(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -133,6 +133,16 @@ def lib():
     L.qb200_sampler_exact_count.argtypes = [vp]
     L.qb200_sampler_exact_count.restype = C.c_uint64
     L.qb200_sampler_first_failing_word.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.qb200_diagk_create.argtypes = [vp, PP, C.POINTER(vp)]
+    L.qb200_diagk_destroy.argtypes = [vp]
+    L.qb200_diagk_j_limbs.argtypes = [vp]
+    L.qb200_diagk_j_limbs.restype = u32
+    L.qb200_diagk_k_limbs.argtypes = [vp]
+    L.qb200_diagk_k_limbs.restype = u32
+    L.qb200_diagk_sample.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.qb200_diagk_sample_device.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, vp]
+    L.qb200_diagk_tau_estimate.argtypes = [vp, u32, u32, vp, vp, vp, u32, u32, vp, vp]
+    L.qb200_diagk_h.argtypes = [vp, u32, vp, vp, vp]
     _lib = L
     return L
 
@@ -852,3 +862,113 @@ def tau_estimate_linear(distribution, random_state: WordStream, n: int, ctx=None
         raise CriticalError("tau_estimate_linear(): the random stream is exhausted")
     random_state.pos += used
     return bool(ok[0]), t0[0]
+
+
+# --------------------------------------------------------------------------- #
+# Diagonal distribution: k given (j, eta)                                     #
+# --------------------------------------------------------------------------- #
+
+def int_to_limbs(x: int, n: int) -> np.ndarray:
+    """Little-endian 32-bit words (mpz_export(buf, &count, -1, 4, 0, 0, z)), zero padded to n."""
+    return np.frombuffer(int(x).to_bytes(4 * n, "little"), dtype=np.uint32).copy()
+
+
+def limbs_to_int(a) -> int:
+    return int.from_bytes(np.ascontiguousarray(a, dtype=np.uint32).tobytes(), "little")
+
+
+class DiagonalKSampler:
+    """d, r and the reciprocal of r on the GPU (qb200_diagk)."""
+
+    def __init__(self, parameters: Diagonal_Parameters, ctx: "Context" = None):
+        self.ctx = ctx or default_context()
+        self.parameters = parameters
+        h = C.c_void_p()
+        p = parameters._c()
+        _check(lib().qb200_diagk_create(self.ctx.h, C.byref(p), C.byref(h)), "qb200_diagk_create")
+        self.h = h
+        self.j_limbs = int(lib().qb200_diagk_j_limbs(h))
+        self.k_limbs = int(lib().qb200_diagk_k_limbs(h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().qb200_diagk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pack_j(self, js) -> np.ndarray:
+        J = np.zeros((len(js), self.j_limbs), dtype=np.uint32)
+        for i, j in enumerate(js):
+            J[i] = int_to_limbs(j, self.j_limbs)
+        return J
+
+    def sample(self, js, etas, pivots, delta_bound: int = 0xffffffff, want_k: bool = True):
+        """n calls of sample_k_from_diagonal_j_eta_pivot: (k as Python ints or None, x = alpha_phi /
+        2^(m + sigma - l) as rows (hi, lo), delta, status). js: Python ints or packed rows."""
+        J = js if isinstance(js, np.ndarray) else self.pack_j(js)
+        J = np.ascontiguousarray(J, dtype=np.uint32)
+        n = J.shape[0]
+        eta = np.ascontiguousarray(etas, dtype=np.int32)
+        piv = np.ascontiguousarray(pivots, dtype=np.longdouble)
+        K = np.zeros((n, self.k_limbs), dtype=np.uint32) if want_k else None
+        xh, xl = np.zeros(n), np.zeros(n)
+        delta = np.zeros(n, dtype=np.int64)
+        status = np.zeros(n, dtype=np.int32)
+        _check(lib().qb200_diagk_sample(self.h, n, J.ctypes.data, eta.ctypes.data, piv.ctypes.data,
+                                        delta_bound, K.ctypes.data if want_k else None, xh.ctypes.data,
+                                        xl.ctypes.data, delta.ctypes.data, status.ctypes.data),
+               "qb200_diagk_sample")
+        ks = [limbs_to_int(K[i]) for i in range(n)] if want_k else None
+        return ks, np.stack([xh, xl], axis=1), delta, status
+
+    def sample_device(self, n: int, d_j_ptr: int, d_eta_ptr: int, d_pivot_ptr: int, delta_bound: int,
+                      d_k_ptr: int, d_out_ptr: int, stream: int = 0):
+        _check(lib().qb200_diagk_sample_device(self.h, n, d_j_ptr, d_eta_ptr, d_pivot_ptr, delta_bound,
+                                               d_k_ptr or None, d_out_ptr, stream or None),
+               "qb200_diagk_sample_device")
+
+    def tau_estimate(self, n: int, count: int, js, etas, pivots, delta_bound: int, eta_bound: int):
+        J = js if isinstance(js, np.ndarray) else self.pack_j(js)
+        J = np.ascontiguousarray(J, dtype=np.uint32)
+        assert J.shape[0] == n * count
+        eta = np.ascontiguousarray(etas, dtype=np.int32)
+        piv = np.ascontiguousarray(pivots, dtype=np.longdouble)
+        tau = np.zeros(count, dtype=np.longdouble)
+        ok = np.zeros(count, dtype=np.uint8)
+        _check(lib().qb200_diagk_tau_estimate(self.h, n, count, J.ctypes.data, eta.ctypes.data,
+                                              piv.ctypes.data, delta_bound, eta_bound, tau.ctypes.data,
+                                              ok.ctypes.data), "qb200_diagk_tau_estimate")
+        return tau, ok.astype(bool)
+
+    def h(self, x):
+        """diagonal_probability_approx_h at phi = 2 pi x / 2^l; x: rows (hi, lo)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
+        xh, xl = np.ascontiguousarray(x[:, 0]), np.ascontiguousarray(x[:, 1])
+        out = np.zeros(len(xh), dtype=np.longdouble)
+        _check(lib().qb200_diagk_h(self.h, len(xh), xh.ctypes.data, xl.ctypes.data, out.ctypes.data),
+               "qb200_diagk_h")
+        return out
+
+
+def sample_k_from_diagonal_j_eta_pivot(parameters: Diagonal_Parameters, pivot, j: int, eta: int,
+                                       delta_bound: int, ctx=None):
+    """sample_k_from_diagonal_j_eta_pivot (src/sample.cpp:412-646): returns (result, k,
+    alpha_phi / 2^(m + sigma - l) as (hi, lo))."""
+    key = (id(parameters), parameters.m, parameters.sigma, parameters.l, parameters.d, parameters.r)
+    s = _diagk.get(key)
+    if s is None:
+        s = _diagk[key] = DiagonalKSampler(parameters, ctx)
+    ks, x, _, st = s.sample([j], [eta], [pivot], delta_bound)
+    if st[0] == 4:
+        raise CriticalError("sample_k_from_diagonal_j_eta_pivot(): gave up after 2^22 steps")
+    if st[0] == 2:  # QB200_DIAGK_OK_NEGATIVE_PHI
+        return True, ks[0], (x[0, 0] - 2.0 ** parameters.l, x[0, 1])
+    return st[0] == 0, ks[0], (x[0, 0], x[0, 1])
+
+
+_diagk = {}

@@ -19,7 +19,7 @@ _SRCS = [os.path.join(_HERE, "hostsim.cpp"),
 _DEPS = _SRCS + [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
                  ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "sigma_opt.cuh", "plan.hpp",
                   "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "textparse.cuh", "text_tables.hpp",
-                  "sampler.cuh", "x87soft.cuh")]
+                  "sampler.cuh", "x87soft.cuh", "diagk.cuh", "diagk_host.hpp")]
 _lib = None
 
 
@@ -208,3 +208,76 @@ class HostSampler:
         if getattr(self, "h", None):
             lib().hostsim_sampler_free(self.h)
             self.h = None
+
+
+# ---- diagonal k sampler (diagk.cuh) -----------------------------------------------------
+
+def int_to_limbs(x: int, n: int) -> np.ndarray:
+    return np.frombuffer(x.to_bytes(4 * n, "little"), dtype=np.uint32).copy()
+
+
+def limbs_to_int(a) -> int:
+    return int.from_bytes(np.ascontiguousarray(a, dtype=np.uint32).tobytes(), "little")
+
+
+class DiagK:
+    """CPU twin of the diagonal k sampler: diagk_sample() of csrc/diagk.cuh in a plain loop."""
+
+    def __init__(self, m, sigma, l, d, r):
+        L = lib()
+        L.hostsim_diagk_new.restype = C.c_void_p
+        db, rb = be(d), be(r)
+        self.h = L.hostsim_diagk_new(C.c_uint32(m), C.c_uint32(sigma), C.c_uint32(l), db,
+                                     C.c_size_t(len(db)), rb, C.c_size_t(len(rb)))
+        if not self.h:
+            raise ValueError(L.hostsim_last_error().decode())
+        dims = (C.c_uint32 * 3)()
+        L.hostsim_diagk_dims(C.c_void_p(self.h), dims)
+        self.k, self.wj, self.wl = [int(v) for v in dims]
+        self.m, self.sigma, self.l = m, sigma, l
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().hostsim_diagk_free(C.c_void_p(self.h))
+            self.h = None
+
+    def sample(self, js, etas, pivots, delta_bound=0xffffffff):
+        """-> (k as Python ints, x = alpha_phi / 2^(m+sigma-l) as (hi, lo) rows, delta, status)"""
+        n = len(js)
+        J = np.zeros((n, self.wj), dtype=np.uint32)
+        for i, j in enumerate(js):
+            J[i] = int_to_limbs(j, self.wj)
+        eta = np.ascontiguousarray(etas, dtype=np.int32)
+        piv = np.ascontiguousarray(pivots, dtype=np.longdouble)
+        K = np.zeros((n, self.wl), dtype=np.uint32)
+        x = np.zeros((n, 2))
+        delta = np.zeros(n, dtype=np.int64)
+        status = np.zeros(n, dtype=np.int32)
+        rc = lib().hostsim_diagk_sample(
+            C.c_void_p(self.h), C.c_uint32(n), J.ctypes.data_as(C.c_void_p),
+            eta.ctypes.data_as(C.c_void_p), piv.ctypes.data_as(C.c_void_p),
+            C.c_uint64(delta_bound), K.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
+            delta.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p))
+        if rc:
+            raise ValueError("bad pivot")
+        return [limbs_to_int(K[i]) for i in range(n)], x, delta, status
+
+
+def sinpi_acc(hi, lo=0.0):
+    out = np.zeros(2)
+    lib().hostsim_sinpi_acc(C.c_double(hi), C.c_double(lo), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def x87_from_dd(hi, lo):
+    out = np.zeros(1, dtype=np.longdouble)
+    lib().hostsim_x87_from_dd(C.c_double(hi), C.c_double(lo), out.ctypes.data_as(C.c_void_p))
+    return out[0]
+
+
+def diagk_h(l, x):
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
+    out = np.zeros(len(x), dtype=np.longdouble)
+    lib().hostsim_diagk_h(C.c_uint32(l), C.c_uint32(len(x)), x.ctypes.data_as(C.c_void_p),
+                          out.ctypes.data_as(C.c_void_p))
+    return out

@@ -532,3 +532,80 @@ void hostsim_sampler_sample(void* hh, uint32_t k, const uint64_t* words, int for
 }
 
 }  // extern "C"
+
+// ---- diagonal k sampler (diagk.cuh): the device function in a plain loop ----------------------
+#include "../../qunundrum_b200/csrc/diagk_host.hpp"
+
+extern "C" {
+
+void* hostsim_diagk_new(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* d, size_t dn,
+                        const uint8_t* r, size_t rn) {
+  DiagKHost* h = new DiagKHost;
+  if (diagk_prepare(m, sigma, l, d, dn, r, rn, h, &g_err)) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+void hostsim_diagk_free(void* h) { delete (DiagKHost*)h; }
+void hostsim_diagk_dims(void* hh, uint32_t* out3) {
+  const DiagKHost* h = (const DiagKHost*)hh;
+  out3[0] = h->c.k;
+  out3[1] = h->c.wj;
+  out3[2] = h->c.wl;
+}
+
+// n samples; j: n x wj limbs, k_out: n x wl limbs (row per sample), x: n x (hi, lo).
+int hostsim_diagk_sample(void* hh, uint32_t n, const uint32_t* j, const int32_t* eta,
+                         const long double* pivot, uint64_t delta_bound, uint32_t* k_out, double* x,
+                         int64_t* delta, int32_t* status) {
+  const DiagKHost* h = (const DiagKHost*)hh;
+  std::vector<uint32_t> scratch(diagk_scratch_limbs(h->c.k));
+  for (uint32_t i = 0; i < n; i++) {
+    RawX87 raw;
+    memset(&raw, 0, 16);
+    memcpy(&raw, &pivot[i], 10);
+    bool ok = true;
+    const X87 p = x87_load(&raw, &ok);
+    if (!ok || p.neg) return -1;
+    dd xo;
+    status[i] = diagk_sample(h->c, j + (size_t)i * h->c.wj, 1, eta[i], p, delta_bound, scratch.data(),
+                             1, k_out + (size_t)i * h->c.wl, 1, &xo, &delta[i]);
+    x[2 * i] = xo.hi;
+    x[2 * i + 1] = xo.lo;
+  }
+  return 0;
+}
+
+void hostsim_sinpi_acc(double hi, double lo, double* out2) {
+  const dd r = sinpi_acc(make_dd(hi, lo));
+  out2[0] = r.hi;
+  out2[1] = r.lo;
+}
+
+static void store_x87(X87 r, long double* out) {
+  memset(out, 0, 16);
+  if (r.mant) {
+    const uint16_t se = (uint16_t)((r.exp + 16383) | (r.neg << 15));
+    memcpy(out, &r.mant, 8);
+    memcpy((char*)out + 8, &se, 2);
+  }
+}
+
+void hostsim_x87_from_dd(double hi, double lo, long double* out) { store_x87(x87_from_dd(make_dd(hi, lo)), out); }
+
+// h at x = (hi, lo) pairs, rounded to the x87 format.
+void hostsim_diagk_h(uint32_t l, uint32_t n, const double* x, long double* out) {
+  for (uint32_t i = 0; i < n; i++) {
+    const dd xi = make_dd(x[2 * i], x[2 * i + 1]);
+    // sin^2(pi x) from the fractional part of x
+    const double nearest = rint(xi.hi);
+    dd t = dd_add_d(xi, -nearest);
+    if (t.hi > 0.5) t = dd_add_d(t, -1.0);
+    if (t.hi < -0.5) t = dd_add_d(t, 1.0);
+    const dd st = sinpi_acc(t);
+    store_x87(x87_from_dd(diagk_h(l, dd_mul(st, st), xi)), &out[i]);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+"""The diagonal k sampler (second half):
+sample_k_from_diagonal_j_eta_pivot (src/sample.cpp:412-646) over
+diagonal_probability_approx_h (src/diagonal_probability.cpp:99-162), and the sum of
+tau_estimate_diagonal (src/tau_estimate.cpp:135-210).
+
+Oracle, in this order of authority:
+  * the reference's known-answer vectors res/test-vectors/sample-k-from-diagonal-j-eta-pivot-*
+    and diagonal-probabilities-h-det-* (src/test/test_sample.cpp:675-838,
+    src/test/test_diagonal_probability.cpp:174-300): a sample of 9 + 9 files is committed under
+    tests/golden/kat; where /root/reference is present ALL 522 sample-k files are run;
+  * the compiled reference (oracle/_ref) on seeded random inputs and the edge cases of the
+    domain, committed as tests/golden/diagk.npz (tests/golden/make_diagk_golden.py);
+  * oracle/restate.py, the mpmath restatement, pinned on the same vectors.
+
+The bar: k identical to the reference's (every bit), the same success flag, alpha_phi to
+1e-25 relative (the product carries it as a double-double; the vectors themselves carry it at
+2 l bits, so small l limits what they can show).
+
+CPU tests run the very same __host__ __device__ code through tests/hostsim; GPU tests call the
+C ABI.
+"""
+import glob
+import math
+import os
+import re
+import sys
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+from oracle import restate as rs
+from tests import hostsim as hs
+from tests.conftest import GOLDEN, ref_or_none
+
+sys.set_int_max_str_digits(0)
+
+LD = np.longdouble
+KAT = os.path.join(GOLDEN, "kat")
+TV = "/root/reference/res/test-vectors"
+REF = ref_or_none()
+needs_ref = pytest.mark.skipif(REF is None, reason="oracle/_ref not built (no /root/reference)")
+
+K_FILES = sorted(glob.glob(os.path.join(KAT, "sample-k-from-diagonal-j-eta-pivot-m-*.txt")))
+H_FILES = sorted(glob.glob(os.path.join(KAT, "diagonal-probabilities-h-det-m-*.txt")))
+
+
+def _msl(path):
+    m, sigma, s = map(int, re.search(r"m-(\d+)-sigma-(\d+)-s-(\d+)", path).groups())
+    return m, sigma, int(math.ceil(m / s))  # src/test/test_sample.cpp:713
+
+
+def k_records(path):
+    """(j, eta, pivot, k, alpha_phi) x 25, src/test/test_sample.cpp:764-790."""
+    L = open(path).read().split()
+    return [(int(L[i]), int(L[i + 1]), LD(L[i + 2]), int(L[i + 3]), L[i + 4])
+            for i in range(0, len(L) - 4, 5)]
+
+
+def _alpha_errors(path, recs, x):
+    """Relative error of x = alpha_phi / 2^(m+sigma-l) against the vectors."""
+    m, sigma, l = _msl(path)
+    errs = []
+    with mp.workprec(400):
+        for q, xi in zip(recs, x):
+            want = mp.mpf(q[4]) / mp.mpf(2) ** (m + sigma - l)
+            got = mp.mpf(float(xi[0])) + mp.mpf(float(xi[1]))
+            errs.append(float(abs(got - want) / abs(want)) if want != 0 else float(abs(got)))
+    return errs
+
+
+def _alpha_tolerance(l):
+    # the vectors carry alpha_phi at 2 l bits (src/test/test_sample.cpp:717)
+    return max(1e-25, 2.0 ** (3 - 2 * l))
+
+
+def check_k_file(path, sampler_factory):
+    m, sigma, l = _msl(path)
+    d, r = rs.deterministic_d_r(m)
+    recs = k_records(path)
+    assert len(recs) == 25
+    S = sampler_factory(m, sigma, l, d, r)
+    ks, x, delta, st = S.sample([q[0] for q in recs], [q[1] for q in recs], [q[2] for q in recs])
+    assert list(st) == [0] * 25
+    assert ks == [q[3] for q in recs], os.path.basename(path)
+    assert max(_alpha_errors(path, recs, x)) < _alpha_tolerance(l)
+
+
+# ---- pieces -------------------------------------------------------------------------
+
+def test_sinpi_acc_is_double_double_accurate():
+    rng = np.random.default_rng(5)
+    ts = list(rng.uniform(-0.5, 0.5, 300)) + [0.25, -0.25, 0.5, -0.5, 1e-200, 2.0 ** -60, 0.2500000001]
+    worst = 0.0
+    with mp.workprec(300):
+        for t in ts:
+            lo = float(rng.uniform(-1, 1)) * abs(t) * 2.0 ** -54 if 1e-200 < abs(t) < 0.49 else 0.0
+            got = hs.sinpi_acc(float(t), lo)
+            want = mp.sin(mp.pi * (mp.mpf(float(t)) + mp.mpf(lo)))
+            worst = max(worst, float(abs((mp.mpf(got[0]) + mp.mpf(got[1])) / want - 1)))
+    assert worst < 1e-31, worst
+
+
+def test_x87_from_dd_rounds_like_the_fpu():
+    rng = np.random.default_rng(6)
+    cases = []
+    for _ in range(4000):
+        hi = float(rng.uniform(0.5, 1.0)) * 2.0 ** int(rng.integers(-200, 10))
+        lo = float(rng.uniform(-0.5, 0.5)) * np.spacing(hi) * 2.0 ** -int(rng.integers(0, 30))
+        cases.append((hi, lo))
+    one = 1.0
+    for hi in (one, 2.0 ** -40, np.nextafter(2.0, 0.0), np.nextafter(one, 2.0)):
+        u = np.spacing(hi)
+        for lo in (0.0, u / 2, -u / 4, -u / 2 ** 11, u / 2 ** 12, -u / 2 ** 12, u / 2 ** 12 * (1 + 2.0 ** -30),
+                   u / 2 ** 12 * (1 - 2.0 ** -30), -u / 2 ** 80, u / 2 ** 80, 3 * u / 2 ** 12, -u / 2):
+            if hi + lo == hi:
+                cases.append((hi, lo))
+    for hi, lo in cases:
+        want = LD(hi) + LD(lo)  # one rounding to the 64-bit significand
+        got = hs.x87_from_dd(hi, lo)
+        assert got == want, (hi, lo, got, want)
+    assert hs.x87_from_dd(0.0, 0.0) == 0 and hs.x87_from_dd(-1.0, 0.0) == 0
+
+
+# ---- the oracle on the reference's vectors -----------------------------------------------
+
+@pytest.mark.parametrize("path", [p for p in K_FILES if _msl(p)[0] <= 512], ids=os.path.basename)
+def test_restatement_reproduces_the_k_vectors(path):
+    m, sigma, l = _msl(path)
+    d, r = rs.deterministic_d_r(m)
+    P = rs.DiagonalParameters(m, sigma, 0, d, r, eta_bound=25, t=30, l=l)
+    for j, eta, pivot, k, alpha in k_records(path)[:10]:
+        ok, got_k, got_alpha = rs.sample_k_from_diagonal_j_eta_pivot(P, pivot, j, eta, 0xffffffff)
+        assert ok and got_k == k
+        with mp.workprec(400):
+            assert abs(got_alpha - mp.mpf(alpha)) <= abs(mp.mpf(alpha)) * mp.mpf(2) ** (3 - 2 * l)
+
+
+@needs_ref
+@pytest.mark.parametrize("path", K_FILES[:5], ids=os.path.basename)
+def test_compiled_reference_reproduces_the_k_vectors(path):
+    m, sigma, l = _msl(path)
+    d, r = rs.deterministic_d_r(m)
+    P = REF.RefDiagonalParameters(m, sigma, 0, d, r, eta_bound=25, t=30, l=l)
+    for j, eta, pivot, k, _ in k_records(path)[:8]:
+        ok, got_k, _, _ = REF.sample_k_from_diagonal_j_eta_pivot(P, pivot, j, eta)
+        assert ok and got_k == k
+
+
+# ---- the device code on the CPU (tests/hostsim) -------------------------------------------
+
+@pytest.mark.parametrize("path", K_FILES, ids=os.path.basename)
+def test_twin_k_vectors(path):
+    check_k_file(path, hs.DiagK)
+
+
+@pytest.mark.skipif(not os.path.isdir(TV), reason="needs /root/reference")
+def test_twin_all_522_k_vector_files():
+    files = sorted(glob.glob(os.path.join(TV, "sample-k-from-diagonal-j-eta-pivot-m-*.txt")))
+    assert len(files) == 522
+    for path in files:
+        check_k_file(path, hs.DiagK)
+
+
+def h_records(path):
+    L = open(path).read().split()
+    return [(L[i], L[i + 1]) for i in range(0, len(L) - 1, 2)]
+
+
+def h_inputs(path):
+    """x = phi 2^l / (2 pi) as (hi, lo) rows, and the expected h as long doubles."""
+    m, sigma, l = _msl(path)
+    xs, want = [], []
+    with mp.workprec(3 * l + 400):
+        for phi, h in h_records(path):
+            x = mp.mpf(phi) * mp.mpf(2) ** l / (2 * mp.pi)
+            hi = float(x)
+            xs.append((hi, float(x - mp.mpf(hi))))
+            want.append(rs._get_ld(mp.mpf(h)))
+    return l, np.array(xs), np.array(want, dtype=LD)
+
+
+def check_h(l, got, want):
+    # the reference's own tolerance is 1e-6 (test_cmp_ld, src/test/test_common.cpp:75-93)
+    assert np.all(got > 0)
+    rel = np.abs(got - want) / np.minimum(got, want)
+    assert float(rel.max()) < 1e-15, float(rel.max())
+
+
+@pytest.mark.parametrize("path", H_FILES, ids=os.path.basename)
+def test_twin_h_vectors(path):
+    l, xs, want = h_inputs(path)
+    assert len(xs) == 25
+    check_h(l, hs.diagk_h(l, xs), want)
+
+
+class DiagGold:
+    def __init__(self, z, name):
+        g = lambda k: z[f"{name}_{k}"]  # noqa: E731
+        self.name = name
+        self.m, self.sigma, self.l = [int(v) for v in g("params")]
+        self.d = int.from_bytes(g("d").tobytes(), "big")
+        self.r = int.from_bytes(g("r").tobytes(), "big")
+        self.J, self.eta, self.pivot, self.bound = g("j"), g("eta"), g("pivot"), g("bound")
+        self.K, self.ok, self.alpha = g("k"), g("ok"), g("alpha")
+
+
+def diag_gold():
+    z = np.load(os.path.join(GOLDEN, "diagk.npz"))
+    return [DiagGold(z, str(n)) for n in z["names"]]
+
+
+GOLD = diag_gold()
+
+
+def check_gold(g, S):
+    """S.sample(js, etas, pivots, delta_bound) against the reference's outputs."""
+    js = [hs.limbs_to_int(row) for row in g.J]
+    for bound in sorted(set(int(b) for b in g.bound)):
+        idx = [i for i in range(len(js)) if int(g.bound[i]) == bound]
+        ks, x, delta, st = S.sample([js[i] for i in idx], g.eta[idx], g.pivot[idx], bound)
+        for n, i in enumerate(idx):
+            assert (st[n] in (0, 2)) == bool(g.ok[i]), (g.name, i)
+            assert st[n] in (0, 1, 2)
+            assert ks[n] == hs.limbs_to_int(g.K[i]), (g.name, i, js[i], int(g.eta[i]))
+            got = LD(x[n, 0]) + LD(x[n, 1])
+            if st[n] == 2:  # negative unreduced phi: j < |eta| 2^(m+sigma) / r (src/sample.cpp:566-574)
+                assert js[i] < 26 * (1 << (g.m + g.sigma)) // g.r + 2
+                got -= LD(2) ** g.l
+            want = g.alpha[i]
+            assert abs(got - want) <= abs(want) * LD(2) ** -62, (g.name, i, got, want)
+            assert abs(delta[n]) <= bound
+
+
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: g.name)
+def test_twin_matches_the_reference_on_random_and_edge_inputs(g):
+    check_gold(g, hs.DiagK(g.m, g.sigma, g.l, g.d, g.r))
+
+
+@needs_ref
+def test_twin_matches_the_live_reference_on_fresh_seeds():
+    rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
+    import random
+    prng = random.Random(int(rng.integers(1 << 30)))
+    for m, sigma, l in ((128, 3, 64), (160, 0, 20), (512, 7, 300), (2048, 5, 1027)):
+        r = (1 << (m - 1)) + 1 + prng.randrange((1 << (m - 1)) - 1)
+        d = r // 2 + prng.randrange(r // 2)
+        P = REF.RefDiagonalParameters(m, sigma, 0, d, r, eta_bound=25, t=30, l=l)
+        S = hs.DiagK(m, sigma, l, d, r)
+        js = [prng.randrange(1 << (m + sigma)) for _ in range(12)]
+        etas = [prng.randrange(-25, 26) for _ in js]
+        piv = np.array([LD(prng.random()) * LD(0.98) for _ in js], dtype=LD)
+        ks, x, _, st = S.sample(js, etas, piv, 4000)
+        for i, j in enumerate(js):
+            ok, k, a, _ = REF.sample_k_from_diagonal_j_eta_pivot(P, piv[i], j, etas[i], 4000, precision=256)
+            assert ok == (st[i] == 0) and k == ks[i], (m, sigma, l, d, r, j, etas[i], piv[i])
+            assert abs((LD(x[i, 0]) + LD(x[i, 1])) - a) <= abs(a) * LD(2) ** -62
+
+
+def test_twin_refuses_bad_parameters():
+    with pytest.raises(ValueError):
+        hs.DiagK(128, 0, 64, 5, 3)          # d >= r
+    with pytest.raises(ValueError):
+        hs.DiagK(128, 0, 200, 3, 5)         # l > m + sigma
+    with pytest.raises(ValueError):
+        hs.DiagK(64, 0, 32, 3, (1 << 70) + 1)  # r >= 2^m
+
+
+# ---- the C ABI on the GPU ------------------------------------------------------------------
+
+def _gpu_factory(gpu_ctx):
+    import qunundrum_b200 as qb
+
+    def make(m, sigma, l, d, r):
+        return qb.DiagonalKSampler(qb.Diagonal_Parameters(m, sigma, 0, d, r, eta_bound=25, t=30, l=l), gpu_ctx)
+    return make
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", K_FILES, ids=os.path.basename)
+def test_gpu_k_vectors(path, gpu_ctx):
+    check_k_file(path, _gpu_factory(gpu_ctx))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", H_FILES, ids=os.path.basename)
+def test_gpu_h_vectors(path, gpu_ctx):
+    l, xs, want = h_inputs(path)
+    m, sigma, _ = _msl(path)
+    d, r = rs.deterministic_d_r(m)
+    S = _gpu_factory(gpu_ctx)(m, sigma, l, d, r)
+    got = S.h(xs)
+    check_h(l, got, want)
+    assert np.array_equal(got, hs.diagk_h(l, xs))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: g.name)
+def test_gpu_matches_the_reference_on_random_and_edge_inputs(g, gpu_ctx):
+    check_gold(g, _gpu_factory(gpu_ctx)(g.m, g.sigma, g.l, g.d, g.r))
+
+
+def _random_batch(m, sigma, n, seed):
+    import random
+    prng = random.Random(seed)
+    r = (1 << (m - 1)) + 1 + prng.randrange((1 << (m - 1)) - 1)
+    d = r // 2 + prng.randrange(r // 2)
+    wj = (m + sigma + 31) // 32
+    rng = np.random.default_rng(seed)
+    J = rng.integers(0, 1 << 32, size=(n, wj), dtype=np.uint64).astype(np.uint32)
+    if (m + sigma) % 32:
+        J[:, -1] &= np.uint32((1 << ((m + sigma) % 32)) - 1)
+    eta = rng.integers(-25, 26, size=n).astype(np.int32)
+    piv = rng.random(n).astype(LD) * LD(0.995)
+    return d, r, J, eta, piv
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,sigma,l,n", [(2048, 5, 2048, 3000), (128, 2, 40, 400000), (1023, 0, 1003, 2000)])
+def test_gpu_equals_the_twin_on_a_batch(m, sigma, l, n, gpu_ctx):
+    """Same code on both sides: k, delta and status identical, x to the last bits (the host
+    compiler may contract a multiply-add the device build keeps apart). 400000 samples span
+    more than one launch."""
+    d, r, J, eta, piv = _random_batch(m, sigma, n, 77 + m)
+    S = _gpu_factory(gpu_ctx)(m, sigma, l, d, r)
+    ks, x, delta, st = S.sample(J, eta, piv, 3000)
+    sub = np.arange(n) if n <= 3000 else np.random.default_rng(1).choice(n, 3000, replace=False)
+    T = hs.DiagK(m, sigma, l, d, r)
+    ks2, x2, delta2, st2 = T.sample([hs.limbs_to_int(J[i]) for i in sub], eta[sub], piv[sub], 3000)
+    assert [ks[i] for i in sub] == ks2
+    assert np.array_equal(delta[sub], delta2) and np.array_equal(st[sub], st2)
+    xa = x[sub, 0].astype(LD) + x[sub, 1].astype(LD)
+    xb = x2[:, 0].astype(LD) + x2[:, 1].astype(LD)
+    assert np.all(np.abs(xa - xb) <= np.abs(xb) * LD(2) ** -60)
+    assert (st == 0).mean() > 0.9
+
+
+@pytest.mark.gpu
+def test_gpu_tau_estimate(gpu_ctx):
+    """tau = log2(mean alpha_phi^2) / 2 - (m + sigma - l) per estimate; an estimate with an
+    out-of-bounds sample or |eta| > eta_bound gives DBL_MAX and FALSE (src/tau_estimate.cpp:163-201)."""
+    m, sigma, l, n, count = 2048, 3, 2048, 16, 64
+    d, r, J, eta, piv = _random_batch(m, sigma, n * count, 5)
+    piv[7 * n + 3] = LD(1)          # runs out of bounds with delta_bound = 50
+    eta[9 * n + 1] = 26             # above eta_bound
+    S = _gpu_factory(gpu_ctx)(m, sigma, l, d, r)
+    tau, ok = S.tau_estimate(n, count, J, eta, piv, 50, 25)
+    _, x, _, st = S.sample(J, eta, piv, 50, want_k=False)
+    for t in range(count):
+        sl = slice(t * n, (t + 1) * n)
+        good = np.all(st[sl] == 0) and np.all(np.abs(eta[sl]) <= 25)
+        assert ok[t] == good
+        if not good:
+            assert tau[t] == LD(np.finfo(np.float64).max)
+            continue
+        with mp.workprec(192):
+            acc = mp.mpf(0)
+            for hi, lo in x[sl]:
+                a = mp.mpf(float(hi)) + mp.mpf(float(lo))
+                acc += a * a
+            want = mp.log(acc / n, 2) / 2
+        assert abs(float(tau[t]) - float(want)) < 1e-15 and abs(tau[t] - rs._get_ld(want)) <= LD(2) ** -60
+    assert not ok[7] and not ok[9] and ok.sum() >= count - 8
+
+
+@pytest.mark.gpu
+def test_gpu_pivot_out_of_bounds_is_fatal(gpu_ctx):
+    import qunundrum_b200 as qb
+    d, r, J, eta, piv = _random_batch(128, 0, 4, 9)
+    S = _gpu_factory(gpu_ctx)(128, 0, 128, d, r)
+    piv[2] = LD(1.5)
+    with pytest.raises(qb.CriticalError, match="pivot is out of bounds"):
+        S.sample(J, eta, piv, 10)
+    with pytest.raises(qb.CriticalError):
+        qb.DiagonalKSampler(qb.Diagonal_Parameters(128, 0, 0, 5, 3, l=64), gpu_ctx)
