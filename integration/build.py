@@ -10,7 +10,8 @@ plus, in both flavours, the importing executables filter_distribution, info_dist
 compare_[linear_|diagonal_]distributions (they load stored distributions: the importer path), and
 estimate_runs_distribution / estimate_runs_linear_distribution (gpu flavour: tau_estimate and
 tau_estimate_linear from qunundrum_b200/dropin/dropin_tau.cpp; the reference's tau_estimate.cpp
-stays for tau_estimate_diagonal, compiled with two -D renames).
+stays in the build compiled with three -D renames; tau_estimate_diagonal from
+qunundrum_b200/dropin/dropin_tau_diagonal.cpp).
 
 INTEGRATION-TEST INFRASTRUCTURE. Sources are compiled where they lie under /root/reference/src
 (never copied); neither OpenMPI nor fpLLL nor the GMP/MPFR development headers exist in this
@@ -39,18 +40,21 @@ COMMON_CPP = """math rsa parameters diagonal_parameters parameters_selection sam
  linear_distribution_slice linear_distribution_slice_mpi
  diagonal_distribution diagonal_distribution_enumerator diagonal_distribution_info
  diagonal_distribution_mpi diagonal_distribution_slice diagonal_distribution_slice_mpi
- distribution_loader linear_distribution_loader tau_ordered_list tau_volume_quotient log""".split()
+ distribution_loader linear_distribution_loader diagonal_distribution_loader tau_ordered_list
+ tau_volume_quotient log""".split()
 TEXT_IO = """distribution_slice_import_export linear_distribution_slice_import_export
  diagonal_distribution_slice_import_export""".split()
 COMMON_C = "errors random keccak keccak_random gmp_mpi mpfr_mpi string_utilities thread_pool debug_common".split()
 INTEGRATORS = """distribution_slice_compute distribution_slice_compute_richardson
  linear_distribution_slice_compute linear_distribution_slice_compute_richardson
  diagonal_distribution_slice_compute diagonal_distribution_slice_compute_richardson""".split()
-# tau_estimate.cpp: as it is in the "ref" flavour; in the "gpu" flavour compiled with two renames
-# (tau_estimate_diagonal stays the reference's) next to qunundrum_b200/dropin/dropin_tau.cpp
+# tau_estimate.cpp: as it is in the "ref" flavour; in the "gpu" flavour compiled with three renames
+# next to qunundrum_b200/dropin/dropin_tau.cpp and dropin_tau_diagonal.cpp
 TAU = ["tau_estimate"]
-TAU_RENAMES = ["-Dtau_estimate=tau_estimate_cpu_unused", "-Dtau_estimate_linear=tau_estimate_linear_cpu_unused"]
-ESTIMATORS = ["estimate_runs_distribution", "estimate_runs_linear_distribution"]
+TAU_RENAMES = ["-Dtau_estimate=tau_estimate_cpu_unused", "-Dtau_estimate_linear=tau_estimate_linear_cpu_unused",
+               "-Dtau_estimate_diagonal=tau_estimate_diagonal_cpu_unused"]
+ESTIMATORS = ["estimate_runs_distribution", "estimate_runs_linear_distribution",
+              "estimate_runs_diagonal_distribution"]
 MAINS = ["generate_distribution", "generate_linear_distribution", "generate_linear_distribution_rsa",
          "generate_diagonal_distribution", "filter_distribution", "info_distribution",
          "compare_distributions", "compare_linear_distributions", "compare_diagonal_distributions"]
@@ -64,6 +68,8 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     deps = [os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin.cpp"),
             os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
             os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau.cpp"),
+            os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau_diagonal.cpp"),
+            os.path.join(HERE, "tools", "tau_diagonal_check.cpp"),
             os.path.join(HERE, "minimpi", "minimpi.c"), os.path.join(HERE, "minimpi", "mpi.h"),
             os.path.join(HERE, "build.py"), os.path.join(ROOT, "include", "qunundrum_b200.h"),
             ]
@@ -96,6 +102,12 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
                  os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau.cpp"),
                  "-o", os.path.join(obj, "dropin_tau.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *inc, "-c",
+                 os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau_diagonal.cpp"),
+                 "-o", os.path.join(obj, "dropin_tau_diagonal.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *inc, "-c",
+                 os.path.join(HERE, "tools", "tau_diagonal_check.cpp"),
+                 "-o", os.path.join(obj, "tau_diagonal_check.o")])
     jobs.append(["gcc", "-O2", "-c", os.path.join(HERE, "minimpi", "minimpi.c"),
                  "-o", os.path.join(obj, "minimpi.o")])
     with ThreadPoolExecutor(8) as ex:
@@ -122,11 +134,19 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
                                *[os.path.join(obj, f + ".o") for f in INTEGRATORS + TEXT_IO],
                                *libs, "-o", os.path.join(OUT, "ref", m)])
         subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "tau_estimate_renamed.o"),
-                               os.path.join(obj, "dropin_tau.o"), os.path.join(obj, "dropin.o"),
-                               os.path.join(obj, "dropin_text.o"),
+                               os.path.join(obj, "dropin_tau.o"), os.path.join(obj, "dropin_tau_diagonal.o"),
+                               os.path.join(obj, "dropin.o"), os.path.join(obj, "dropin_text.o"),
                                "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
                                "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
                                "-o", os.path.join(OUT, "gpu", m)])
+    # test driver: the drop-in tau_estimate_diagonal against the reference's (renamed) in one process
+    subprocess.check_call(["g++", os.path.join(obj, "tau_diagonal_check.o"), *common,
+                           os.path.join(obj, "tau_estimate_renamed.o"), os.path.join(obj, "dropin_tau.o"),
+                           os.path.join(obj, "dropin_tau_diagonal.o"), os.path.join(obj, "dropin.o"),
+                           os.path.join(obj, "dropin_text.o"),
+                           "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
+                           "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
+                           "-o", os.path.join(OUT, "gpu", "tau_diagonal_check")])
     open(done, "w").write("ok\n")
     return True
 

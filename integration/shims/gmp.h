@@ -35,6 +35,12 @@ typedef const __mpz_struct *mpz_srcptr;
 
 #define mpz_init __gmpz_init
 void __gmpz_init(mpz_ptr);
+#define mpz_init_set __gmpz_init_set
+void __gmpz_init_set(mpz_ptr, mpz_srcptr);
+#define mpz_fdiv_q_2exp __gmpz_fdiv_q_2exp
+void __gmpz_fdiv_q_2exp(mpz_ptr, mpz_srcptr, mp_bitcnt_t);
+#define mpz_fdiv_r_2exp __gmpz_fdiv_r_2exp
+void __gmpz_fdiv_r_2exp(mpz_ptr, mpz_srcptr, mp_bitcnt_t);
 #define mpz_init_set_ui __gmpz_init_set_ui
 void __gmpz_init_set_ui(mpz_ptr, unsigned long);
 #define mpz_clear __gmpz_clear

@@ -162,3 +162,70 @@ int qb200_sampler_tau_estimate(qb200_sampler* s, uint32_t n, uint32_t count, con
 }
 
 }  // extern "C"
+
+// ---- diagonal k sampler entry points (TEST-ONLY, same purpose): the host logic of
+// qunundrum_b200/dropin/dropin_tau_diagonal.cpp -- the (j, eta) draws with the kept region bounds
+// and inverse, the replay after a failing sample, the MPFR sum -- runs in the GPU-less suite
+// inside integration/tools/tau_diagonal_check.cpp, next to the reference's own
+// tau_estimate_diagonal. k and alpha_phi come from the CPU compile of diagk.cuh.
+extern "C" {
+void* hostsim_diagk_new(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* d, size_t dn,
+                        const uint8_t* r, size_t rn);
+void hostsim_diagk_free(void* h);
+void hostsim_diagk_dims(void* hh, uint32_t* out3);
+int hostsim_diagk_sample(void* hh, uint32_t n, const uint32_t* j, const int32_t* eta,
+                         const long double* pivot, uint64_t delta_bound, uint32_t* k_out, double* x,
+                         int64_t* delta, int32_t* status);
+const char* hostsim_last_error();
+}
+
+struct qb200_diagk {
+  void* h = nullptr;
+  uint32_t dims[3] = {0, 0, 0};
+};
+
+extern "C" {
+
+int qb200_diagk_create(qb200_context*, const qb200_params* p, qb200_diagk** out) {
+  *out = nullptr;
+  void* h = hostsim_diagk_new(p->m, p->sigma, p->l, p->d_be, p->d_len, p->r_be, p->r_len);
+  if (!h) {
+    g_err = hostsim_last_error();
+    return -2;
+  }
+  qb200_diagk* s = new qb200_diagk;
+  s->h = h;
+  hostsim_diagk_dims(h, s->dims);
+  *out = s;
+  return 0;
+}
+void qb200_diagk_destroy(qb200_diagk* s) {
+  if (!s) return;
+  hostsim_diagk_free(s->h);
+  delete s;
+}
+uint32_t qb200_diagk_j_limbs(const qb200_diagk* s) { return s->dims[1]; }
+uint32_t qb200_diagk_k_limbs(const qb200_diagk* s) { return s->dims[2]; }
+
+int qb200_diagk_sample(qb200_diagk* s, uint32_t n, const uint32_t* j, const int32_t* eta,
+                       const long double* pivot, uint32_t delta_bound, uint32_t* k, double* x_hi,
+                       double* x_lo, int64_t* delta, int32_t* status) {
+  std::vector<uint32_t> kk((size_t)n * s->dims[2]);
+  std::vector<double> x(2 * (size_t)n);
+  std::vector<int64_t> dl(n);
+  std::vector<int32_t> st(n);
+  if (hostsim_diagk_sample(s->h, n, j, eta, pivot, delta_bound, kk.data(), x.data(), dl.data(), st.data())) {
+    g_err = "The pivot is out of bounds.";
+    return -42;
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    if (x_hi) x_hi[i] = x[2 * i];
+    if (x_lo) x_lo[i] = x[2 * i + 1];
+    if (delta) delta[i] = dl[i];
+    if (status) status[i] = st[i];
+  }
+  if (k) memcpy(k, kk.data(), kk.size() * 4);
+  return 0;
+}
+
+}  // extern "C"

@@ -60,6 +60,42 @@ def build_tau(reference_root: str = "/root/reference", force: bool = False):
     return DROPIN_TAU_SHIM
 
 
+TAU_DIAGONAL_CHECK = os.path.join(OUT, "tau_diagonal_check")
+
+
+def build_tau_diagonal(force: bool = False):
+    """TEST-ONLY: integration/tools/tau_diagonal_check.cpp -- the drop-in tau_estimate_diagonal of
+    qunundrum_b200/dropin/dropin_tau_diagonal.cpp next to the reference's own in one process --
+    linked against the CPU stand-in of the qb200_diagk_* entry points (abi_shim.cpp over the CPU
+    compile of csrc/diagk.cuh) and the reference's own text importers, from the object files
+    integration/build.py left behind. Returns the executable's path, or None."""
+    from integration import build as ib
+    obj = os.path.join(ib.OUT, "obj")
+    need = [os.path.join(obj, f) for f in ("tau_diagonal_check.o", "dropin_tau_diagonal.o",
+                                           "tau_estimate_renamed.o")]
+    if not all(os.path.exists(f) for f in need):
+        return TAU_DIAGONAL_CHECK if os.path.exists(TAU_DIAGONAL_CHECK) else None
+    srcs = [os.path.join(_HERE, "abi_shim.cpp"), os.path.join(_HERE, "hostsim.cpp"),
+            os.path.join(_ROOT, "qunundrum_b200", "csrc", "hostconst.cpp"),
+            os.path.join(_ROOT, "qunundrum_b200", "csrc", "text_tables.cpp")]
+    deps = srcs + need + [os.path.abspath(__file__)]
+    deps += [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in ("diagk.cuh", "diagk_host.hpp")]
+    if not force and os.path.exists(TAU_DIAGONAL_CHECK) and all(
+            os.path.getmtime(d) <= os.path.getmtime(TAU_DIAGONAL_CHECK) for d in deps):
+        return TAU_DIAGONAL_CHECK
+    os.makedirs(OUT, exist_ok=True)
+    shim = os.path.join(OUT, "libqb200_diagkshim.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-x", "c++", *srcs,
+                           "-o", shim])
+    common = [os.path.join(obj, f + ".o") for f in ib.COMMON_CPP + ib.COMMON_C + ["lattice_stub", "minimpi"]]
+    libs = [os.path.join(ib.LIBDIR, "libmpfr.so.6"), os.path.join(ib.LIBDIR, "libgmp.so.10"),
+            "-lpthread", "-lm"]
+    subprocess.check_call(["g++", *need, *common,
+                           *[os.path.join(obj, f + ".o") for f in ib.INTEGRATORS + ib.TEXT_IO],
+                           shim, "-Wl,-rpath,$ORIGIN", *libs, "-o", TAU_DIAGONAL_CHECK])
+    return TAU_DIAGONAL_CHECK
+
+
 def build(force: bool = False) -> bool:
     from integration import build as ib
     obj = os.path.join(ib.OUT, "obj")

@@ -373,3 +373,80 @@ def test_gpu_pivot_out_of_bounds_is_fatal(gpu_ctx):
         S.sample(J, eta, piv, 10)
     with pytest.raises(qb.CriticalError):
         qb.DiagonalKSampler(qb.Diagonal_Parameters(128, 0, 0, 5, 3, l=64), gpu_ctx)
+
+
+# ---- tau_estimate_diagonal: the drop-in next to the reference's own, in one process -----------
+
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import tempfile  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+IB = os.path.join(ROOT, "integration", "_build")
+
+
+def _generate_diagonal(flavour, cwd, args, np_=5):
+    os.makedirs(os.path.join(cwd, "distributions"), exist_ok=True)
+    env = dict(os.environ, QB200_DEVICE="0", QB200_TEXT_DEVICE="0")
+    p = subprocess.run([os.path.join(IB, "minimpirun"), "-np", str(np_),
+                        os.path.join(IB, flavour, "generate_diagonal_distribution"), *args],
+                       cwd=cwd, env=env, capture_output=True, text=True, timeout=1800)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-1500:]
+    files = os.listdir(os.path.join(cwd, "distributions"))
+    assert len(files) == 1
+    return os.path.join(cwd, "distributions", files[0])
+
+
+def _check(exe, dist, n, estimates, delta_bound, eta_bound, seed):
+    p = subprocess.run([exe, dist, str(n), str(estimates), str(delta_bound), str(eta_bound), str(seed)],
+                       capture_output=True, text=True, timeout=1800,
+                       env=dict(os.environ, QB200_DEVICE="0"))
+    assert p.stdout.strip(), p.stderr[-2000:]
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    assert p.returncode == 0 and out["ok"], out
+    assert out["mismatched_flags"] == 0 and out["mismatched_taus"] == 0 and out["mismatched_states"] == 0
+    return out
+
+
+# (n, estimates, delta_bound, eta_bound): plain; a delta bound that pivots outrun and an eta bound
+# below the distribution's (failing samples in mid-estimate: the stream is put back and replayed);
+# delta_bound 0
+TAU_RUNS = [(4, 300, 1000, 2), (3, 200, 1, 1), (16, 150, 0, 2)]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(IB, "obj", "tau_diagonal_check.o")),
+                    reason="integration/_build missing (needs /root/reference at build time)")
+def test_tau_diagonal_dropin_host_logic_on_the_cpu_shim():
+    """qunundrum_b200/dropin/dropin_tau_diagonal.cpp over the CPU stand-in of qb200_diagk_*
+    (tests/hostsim/abi_shim.cpp): the same success flags, tau and -- after every call -- the same
+    Random_State as the reference's tau_estimate_diagonal on identically seeded generators."""
+    from tests.hostsim import shim_flavour as sf
+    exe = sf.build_tau_diagonal()
+    assert exe
+    with tempfile.TemporaryDirectory() as t:
+        dist = _generate_diagonal("ref", t, ["-dim", "128", "-eta-bound", "2", "-det", "128", "3", "1"], np_=9)
+        failed = 0
+        for seed, (n, est, db, eb) in enumerate(TAU_RUNS):
+            out = _check(exe, dist, n, est, db, eb, seed + 1)
+            assert out["worst_tau_difference"] <= 2.0 ** -58
+            failed += out["failed_estimates"]
+        assert failed > 20          # the replay path was taken
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,runs", [
+    (["-dim", "128", "-eta-bound", "2", "-det", "128", "3", "1"], TAU_RUNS),
+    (["-dim", "256", "-eta-bound", "2", "-det", "2048", "5", "1"], [(8, 40, 1000, 2), (3, 60, 1, 1)]),
+    (["-dim", "256", "-eta-bound", "1", "-det", "1024", "2", "4"], [(5, 60, 1000, 1)]),
+], ids=["m128", "m2048", "m1024_s4"])
+def test_gpu_tau_diagonal_dropin_equals_the_reference_in_process(args, runs):
+    exe = os.path.join(IB, "gpu", "tau_diagonal_check")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build missing (needs /root/reference at build time)")
+    with tempfile.TemporaryDirectory() as t:
+        dist = _generate_diagonal("gpu", t, args)
+        for seed, (n, est, db, eb) in enumerate(runs):
+            out = _check(exe, dist, n, est, db, eb, seed + 1)
+            assert out["worst_tau_difference"] <= 2.0 ** -58
+            print(f"\n{os.path.basename(dist)} n={n}: reference {out['reference_s']:.3f} s, "
+                  f"drop-in {out['dropin_s']:.3f} s for {est} estimates")

@@ -22,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B = os.path.join(ROOT, "integration", "_build")
 # two-dimensional: "m: 64 s: 2 n: 4 -- tau_d 10.66 v_d: 0.10 <0> -- tau_r: 6.69 v_r: 1.1E-07 <0>"
 # linear:          "m: 128 s: 2 n: 3 -- tau: 4.52 v: 0.01 <0>"
-LINE = re.compile(r"m: (\d+) [sl]: (\d+) n: (\d+) -- tau(?:_d)?:? ([-\d.]+) v(?:_d)?: (\S+) <(\d+)>"
+# diagonal:        "m: 128 sigma: 3 s: 1 n: 2 -- tau: -0.82 v: 0.01 <0>"
+LINE = re.compile(r"m: (\d+) (?:sigma: \d+ )?[sl]: (\d+) n: (\d+) -- tau(?:_d)?:? ([-\d.]+) v(?:_d)?: (\S+) <(\d+)>"
                   r"(?: -- tau_r: ([-\d.]+) v_r: (\S+) <(\d+)>)?")
 
 
@@ -56,11 +57,14 @@ CASES = [
      "distribution-det-dim-32-sigma-heuristic-m-64-s-2.txt"),
     ("generate_linear_distribution", ["-d", "-det", "-dim", "256", "128", "2"], "estimate_runs_linear_distribution",
      "linear-distribution-det-dim-256-d-m-128-s-2.txt"),
+    # tau_estimate_diagonal from qunundrum_b200/dropin/dropin_tau_diagonal.cpp
+    ("generate_diagonal_distribution", ["-det", "-dim", "128", "-eta-bound", "8", "64", "6", "2"],
+     "estimate_runs_diagonal_distribution", "diagonal-distribution-det-dim-128-m-64-sigma-6-s-2.txt"),
 ]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gen,gen_args,exe,name", CASES, ids=["2d", "linear"])
+@pytest.mark.parametrize("gen,gen_args,exe,name", CASES, ids=["2d", "linear", "diagonal"])
 def test_estimate_runs_with_the_tau_dropin_matches_the_reference(gen, gen_args, exe, name):
     if not _have():
         pytest.skip("integration/_build missing (needs /root/reference at build time)")
