@@ -29,12 +29,23 @@
 //     PRECISION bits from the double-double alpha_phi the library returns.
 //
 // Semantics kept:
-//   * the random stream: the reference stops reading at the first sample that fails (no slice, k
-//     out of bounds, |eta| > eta_bound; src/tau_estimate.cpp:163-188). All n samples are drawn
-//     before the GPU is asked, so when sample i < n - 1 fails the Random_State is put back to where
-//     it was on entry and the draws of samples 0 .. i are repeated; afterwards the state is
-//     what the reference leaves behind. (A Random_State reading /dev/urandom cannot be put back and
-//     does not need to be.)
+//   * batching. The caller asks for one estimate per call, 1000 calls per job with the same
+//     arguments (TAU_CHUNK_SIZE, src/executables_estimate_runs_distribution.h:23;
+//     src/main_estimate_runs_diagonal_distribution.cpp:410-422). The first call computes
+//     QB200_TAU_BATCH (default 1000) consecutive estimates with one GPU call and the following
+//     calls with the same (distribution, random state, n, bounds) return them in order; the
+//     Random_State runs ahead to the end of the batch. With QB200_TAU_BATCH=1 the state after
+//     every call is the reference's (what the tests compare); with a batch the states agree at
+//     every batch boundary. If the caller changes its arguments in mid-batch the unused estimates
+//     are dropped: the results remain correct samples, the stream position then differs from the
+//     reference's (never the case in the reference's executable with the default batch).
+//   * the random stream: the reference stops reading at the first sample that fails (no slice,
+//     |eta| > eta_bound, k out of bounds; src/tau_estimate.cpp:163-188). The first two are seen
+//     while drawing. k out of bounds is only known after the GPU call: if it happens before an
+//     estimate's last sample, the Random_State is put back to where it was when that estimate
+//     began, the draws up to the failing sample are repeated, and the later estimates of the batch
+//     are drawn and computed anew. (A Random_State reading /dev/urandom cannot be put back and does
+//     not need to be.)
 //   * errors are fatal: critical() (src/errors.c).
 #include "common.h"
 #include "diagonal_distribution.h"
@@ -58,6 +69,7 @@
 #include <time.h>
 
 #include <map>
+#include <vector>
 #include <utility>
 #include <vector>
 
@@ -268,39 +280,169 @@ bool draw_j_eta(const Diagonal_Distribution* distribution, Random_State* rs, mpz
   return true;
 }
 
-struct Drawn {
-  uint32_t count = 0;      // samples with (j, eta, pivot) drawn
-  bool failed = false;     // the draw of sample `count` found no slice
-};
-
-void draw_all(const Diagonal_Distribution* distribution, Random_State* rs, uint32_t n, std::vector<uint32_t>& J,
-              std::vector<int32_t>& eta, std::vector<long double>& pivot, Drawn* out) {
-  mpz_t j, alpha_r, t_r, tmp;
-  mpz_init(j);
-  mpz_init(alpha_r);
-  mpz_init(t_r);
-  mpz_init(tmp);
-  out->count = 0;
-  out->failed = false;
-  for (uint32_t i = 0; i < n; i++) {
+// One estimate's draws (src/tau_estimate.cpp:158-188 without the k sampling): one row of
+// J / eta / pivot per sample whose k is wanted. Returns the number of rows appended; *failed is
+// set if the estimate fails on the host's side already -- no slice
+// (diagonal_distribution_sample_j_eta returns FALSE) or |eta| > eta_bound -- with the stream where
+// the reference leaves it in that case (the rows before the failing sample still go to the GPU:
+// an earlier k out of bounds would have stopped the reference earlier). `limit` < n: replay of the
+// first `limit` samples only.
+uint32_t draw_estimate(const Diagonal_Distribution* distribution, Random_State* rs, uint32_t limit,
+                       uint32_t eta_bound, std::vector<uint32_t>& J, std::vector<int32_t>& eta,
+                       std::vector<long double>& pivot, mpz_t* z, bool* failed) {
+  *failed = false;
+  for (uint32_t i = 0; i < limit; i++) {
     int32_t e = 0;
-    if (!draw_j_eta(distribution, rs, j, &e, alpha_r, t_r, tmp)) {
-      out->failed = true;
-      break;
+    if (!draw_j_eta(distribution, rs, z[0], &e, z[1], z[2], z[3])) {
+      *failed = true;
+      return i;
     }
-    // sample_k_from_diagonal_j_eta (src/sample.cpp:648-675) draws the pivot next
-    pivot[i] = random_generate_pivot_inclusive(rs);
-    eta[i] = e;
+    // sample_k_from_diagonal_j_eta (src/sample.cpp:648-675) draws the pivot next; the check of
+    // eta follows the k sampling (src/tau_estimate.cpp:175-181) and fails the estimate either way
+    const long double p = random_generate_pivot_inclusive(rs);
+    if (abs_i(e) > eta_bound) {
+      *failed = true;
+      return i;
+    }
+    eta.push_back(e);
+    pivot.push_back(p);
+    J.resize(eta.size() * g.j_limbs, 0u);
     size_t cnt = 0;
-    uint32_t* row = &J[(size_t)i * g.j_limbs];
-    memset(row, 0, (size_t)g.j_limbs * 4);
-    mpz_export(row, &cnt, -1, 4, 0, 0, j);
-    out->count = i + 1;
+    mpz_export(&J[(eta.size() - 1) * g.j_limbs], &cnt, -1, 4, 0, 0, z[0]);
   }
-  mpz_clear(j);
-  mpz_clear(alpha_r);
-  mpz_clear(t_r);
-  mpz_clear(tmp);
+  return limit;
+}
+
+// tau from the n samples starting at row `first` (src/tau_estimate.cpp:185-201).
+long double tau_of(uint32_t n, const double* x_hi, const double* x_lo, const int32_t* status,
+                   const Diagonal_Parameters* p) {
+  mpfr_t alpha, sum;
+  mpfr_init2(alpha, PRECISION);
+  mpfr_init2(sum, PRECISION);
+  mpfr_set_ui(sum, 0, MPFR_RNDN);
+  const long shift = (long)g.m + (long)g.sigma - (long)g.l;
+  for (uint32_t i = 0; i < n; i++) {
+    mpfr_set_d(alpha, x_hi[i], MPFR_RNDN);
+    mpfr_add_d(alpha, alpha, x_lo[i], MPFR_RNDN);
+    if (status[i] == QB200_DIAGK_OK_NEGATIVE_PHI) {  // alpha_phi = 2^(m+sigma-l) (x - 2^l)
+      mpfr_t q;
+      mpfr_init2(q, PRECISION);
+      mpfr_set_ui_2exp(q, 1, (mpfr_exp_t)g.l, MPFR_RNDN);
+      mpfr_sub(alpha, alpha, q, MPFR_RNDN);
+      mpfr_clear(q);
+    }
+    mpfr_mul_2si(alpha, alpha, shift, MPFR_RNDN);
+    mpfr_sqr(alpha, alpha, MPFR_RNDN);
+    mpfr_add(sum, sum, alpha, MPFR_RNDN);
+  }
+  mpfr_div_ui(sum, sum, n, MPFR_RNDN);
+  mpfr_log2(sum, sum, MPFR_RNDN);
+  const long double tau = mpfr_get_ld(sum, MPFR_RNDN) / 2.0f - (p->m + p->sigma - p->l);
+  mpfr_clear(alpha);
+  mpfr_clear(sum);
+  return tau;
+}
+
+// The results of a batch of consecutive estimates with the same arguments.
+struct Batch {
+  const Diagonal_Distribution* distribution = NULL;
+  Random_State* rs = NULL;
+  uint32_t n = 0, delta_bound = 0, eta_bound = 0;
+  std::vector<long double> tau;
+  std::vector<uint8_t> ok;
+  size_t next = 0;
+} g_batch;
+
+void compute_batch(const Diagonal_Distribution* distribution, Random_State* rs, uint32_t n,
+                   uint32_t delta_bound, uint32_t eta_bound, uint32_t B) {
+  g_batch.tau.assign(B, DBL_MAX);
+  g_batch.ok.assign(B, 0);
+  const bool can_rewind = (NULL == rs->random_device);
+  mpz_t z[4];
+  for (int i = 0; i < 4; i++) mpz_init(z[i]);
+  std::vector<uint32_t> J;
+  std::vector<int32_t> eta, status;
+  std::vector<long double> pivot;
+  std::vector<double> x_hi, x_lo;
+  std::vector<Random_State> entry;
+  struct Est {
+    size_t row;       // first row
+    uint32_t count;   // rows
+    bool failed;      // failed while drawing
+  };
+  std::vector<Est> est;
+  uint32_t t0 = 0;
+  while (t0 < B) {
+    J.clear();
+    eta.clear();
+    pivot.clear();
+    entry.clear();
+    est.clear();
+    double t = now_s();
+    for (uint32_t e = t0; e < B; e++) {
+      if (can_rewind) entry.push_back(*rs);
+      Est s;
+      s.row = eta.size();
+      s.count = draw_estimate(distribution, rs, n, eta_bound, J, eta, pivot, z, &s.failed);
+      est.push_back(s);
+    }
+    g_stats.s_draw += now_s() - t;
+    const uint32_t rows = (uint32_t)eta.size();
+    g_stats.samples += rows;
+    x_hi.resize(rows);
+    x_lo.resize(rows);
+    status.resize(rows);
+    if (rows) {
+      t = now_s();
+      if (0 != qb200_diagk_sample(g.sampler, rows, J.data(), eta.data(), pivot.data(), delta_bound, NULL,
+                                  x_hi.data(), x_lo.data(), NULL, status.data())) {
+        critical("tau_estimate_diagonal(): %s", qb200_last_error());
+      }
+      g_stats.s_abi += now_s() - t;
+    }
+    t = now_s();
+    uint32_t restart = B;
+    for (uint32_t e = t0; e < B; e++) {
+      const Est& s = est[e - t0];
+      uint32_t bad = s.count;
+      for (uint32_t i = 0; i < s.count; i++) {
+        if (status[s.row + i] == QB200_DIAGK_GAVE_UP) {
+          critical("tau_estimate_diagonal(): sample_k_from_diagonal_j_eta_pivot(): gave up after 2^22 steps "
+                   "(delta_bound = %u).", delta_bound);
+        }
+        if (status[s.row + i] == QB200_DIAGK_OUT_OF_BOUNDS) {
+          bad = i;
+          break;
+        }
+      }
+      if (bad == s.count) {
+        if (!s.failed) {
+          g_batch.tau[e] = tau_of(n, &x_hi[s.row], &x_lo[s.row], &status[s.row], &distribution->parameters);
+          g_batch.ok[e] = 1;
+        }
+        continue;  // (failed while drawing: DBL_MAX, FALSE, the stream is where the reference leaves it)
+      }
+      // k ran out of bounds at sample `bad`: the reference stops reading there
+      // (src/tau_estimate.cpp:163-173). If the estimate's draws went on after that sample, what was
+      // drawn is not what the reference draws: back to the estimate's entry state, its first
+      // bad + 1 samples again, the later estimates of the batch anew.
+      const bool drew_on = s.failed || bad + 1 < n;
+      if (drew_on && can_rewind) {
+        *rs = entry[e - t0];
+        std::vector<uint32_t> J2;
+        std::vector<int32_t> eta2;
+        std::vector<long double> pivot2;
+        bool f2;
+        draw_estimate(distribution, rs, bad + 1, eta_bound, J2, eta2, pivot2, z, &f2);
+        g_stats.replays++;
+        restart = e + 1;
+        break;
+      }
+    }
+    g_stats.s_sum += now_s() - t;
+    t0 = restart;
+  }
+  for (int i = 0; i < 4; i++) mpz_clear(z[i]);
 }
 
 }  // namespace
@@ -312,82 +454,20 @@ bool tau_estimate_diagonal(const Diagonal_Distribution* const distribution, Rand
     tau = DBL_MAX;
     return false;
   }
-  setup_for(&distribution->parameters);
   g_stats.calls++;
-  const bool can_rewind = (NULL == random_state->random_device);
-  Random_State entry;
-  if (can_rewind) memcpy(&entry, random_state, sizeof entry);
-  std::vector<uint32_t> J((size_t)n * g.j_limbs);
-  std::vector<int32_t> eta(n);
-  std::vector<long double> pivot(n);
-  std::vector<double> x_hi(n), x_lo(n);
-  std::vector<int32_t> status(n);
-  Drawn drawn;
-  double t0 = now_s();
-  draw_all(distribution, random_state, n, J, eta, pivot, &drawn);
-  g_stats.s_draw += now_s() - t0;
-  g_stats.samples += drawn.count;
-  if (drawn.count) {
-    t0 = now_s();
-    if (0 != qb200_diagk_sample(g.sampler, drawn.count, J.data(), eta.data(), pivot.data(), delta_bound, NULL,
-                                x_hi.data(), x_lo.data(), NULL, status.data())) {
-      critical("tau_estimate_diagonal(): %s", qb200_last_error());
-    }
-    g_stats.s_abi += now_s() - t0;
+  Batch& b = g_batch;
+  if (!(b.next < b.ok.size() && b.distribution == distribution && b.rs == random_state && b.n == n &&
+        b.delta_bound == delta_bound && b.eta_bound == eta_bound)) {
+    setup_for(&distribution->parameters);
+    const int want = env_int("QB200_TAU_BATCH", 1000);
+    compute_batch(distribution, random_state, n, delta_bound, eta_bound, (uint32_t)(want > 0 ? want : 1));
+    b.distribution = distribution;
+    b.rs = random_state;
+    b.n = n;
+    b.delta_bound = delta_bound;
+    b.eta_bound = eta_bound;
+    b.next = 0;
   }
-  // the first sample at which the reference breaks (src/tau_estimate.cpp:163-188)
-  uint32_t stop = drawn.count;
-  for (uint32_t i = 0; i < drawn.count; i++) {
-    if (status[i] == QB200_DIAGK_GAVE_UP) {
-      critical("tau_estimate_diagonal(): sample_k_from_diagonal_j_eta_pivot(): gave up after 2^22 steps "
-               "(delta_bound = %u).", delta_bound);
-    }
-    if (status[i] == QB200_DIAGK_OUT_OF_BOUNDS || abs_i(eta[i]) > eta_bound) {
-      stop = i;
-      break;
-    }
-  }
-  if (stop < drawn.count) {
-    if (can_rewind && (stop + 1 < drawn.count || drawn.failed)) {
-      // the reference never drew samples stop + 1 ...: back to the entry state, samples 0 .. stop again
-      memcpy(random_state, &entry, sizeof entry);
-      Drawn again;
-      draw_all(distribution, random_state, stop + 1, J, eta, pivot, &again);
-      g_stats.replays++;
-    }
-    tau = DBL_MAX;
-    return false;
-  }
-  if (drawn.failed) {
-    tau = DBL_MAX;
-    return false;
-  }
-  t0 = now_s();
-  mpfr_t alpha, sum;
-  mpfr_init2(alpha, PRECISION);
-  mpfr_init2(sum, PRECISION);
-  mpfr_set_ui(sum, 0, MPFR_RNDN);
-  const long shift = (long)g.m + (long)g.sigma - (long)g.l;
-  for (uint32_t i = 0; i < n; i++) {
-    mpfr_set_d(alpha, x_hi[i], MPFR_RNDN);
-    mpfr_add_d(alpha, alpha, x_lo[i], MPFR_RNDN);
-    if (status[i] == QB200_DIAGK_OK_NEGATIVE_PHI) {  // alpha_phi = 2^(m+sigma-l) (x - 2^l)
-      mpfr_t p;
-      mpfr_init2(p, PRECISION);
-      mpfr_set_ui_2exp(p, 1, (mpfr_exp_t)g.l, MPFR_RNDN);
-      mpfr_sub(alpha, alpha, p, MPFR_RNDN);
-      mpfr_clear(p);
-    }
-    mpfr_mul_2si(alpha, alpha, shift, MPFR_RNDN);
-    mpfr_sqr(alpha, alpha, MPFR_RNDN);               // src/tau_estimate.cpp:185-186
-    mpfr_add(sum, sum, alpha, MPFR_RNDN);
-  }
-  mpfr_div_ui(sum, sum, n, MPFR_RNDN);               // :194-201
-  mpfr_log2(sum, sum, MPFR_RNDN);
-  tau = mpfr_get_ld(sum, MPFR_RNDN) / 2.0f - (distribution->parameters.m + distribution->parameters.sigma -
-                                              distribution->parameters.l);
-  mpfr_clear(alpha);
-  mpfr_clear(sum);
-  g_stats.s_sum += now_s() - t0;
-  return true;
+  tau = b.tau[b.next];
+  return b.ok[b.next++] != 0;
 }

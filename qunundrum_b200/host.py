@@ -945,7 +945,7 @@ class DiagonalKSampler:
                                               ok.ctypes.data), "qb200_diagk_tau_estimate")
         return tau, ok.astype(bool)
 
-    def h(self, x):
+    def approx_h(self, x):
         """diagonal_probability_approx_h at phi = 2 pi x / 2^l; x: rows (hi, lo)."""
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
         xh, xl = np.ascontiguousarray(x[:, 0]), np.ascontiguousarray(x[:, 1])

@@ -289,7 +289,7 @@ def test_gpu_h_vectors(path, gpu_ctx):
     m, sigma, _ = _msl(path)
     d, r = rs.deterministic_d_r(m)
     S = _gpu_factory(gpu_ctx)(m, sigma, l, d, r)
-    got = S.h(xs)
+    got = S.approx_h(xs)
     check_h(l, got, want)
     assert np.array_equal(got, hs.diagk_h(l, xs))
 
@@ -397,10 +397,13 @@ def _generate_diagonal(flavour, cwd, args, np_=5):
     return os.path.join(cwd, "distributions", files[0])
 
 
-def _check(exe, dist, n, estimates, delta_bound, eta_bound, seed):
-    p = subprocess.run([exe, dist, str(n), str(estimates), str(delta_bound), str(eta_bound), str(seed)],
+def _check(exe, dist, n, estimates, delta_bound, eta_bound, seed, batch=1):
+    """batch = 1: the Random_States are compared after every call; batch > 1: the drop-in computes
+    `batch` estimates per GPU call and the states are compared at every batch boundary."""
+    p = subprocess.run([exe, dist, str(n), str(estimates), str(delta_bound), str(eta_bound), str(seed),
+                        str(batch)],
                        capture_output=True, text=True, timeout=1800,
-                       env=dict(os.environ, QB200_DEVICE="0"))
+                       env=dict(os.environ, QB200_DEVICE="0", QB200_TAU_BATCH=str(batch)))
     assert p.stdout.strip(), p.stderr[-2000:]
     out = json.loads(p.stdout.strip().splitlines()[-1])
     assert p.returncode == 0 and out["ok"], out
@@ -411,7 +414,7 @@ def _check(exe, dist, n, estimates, delta_bound, eta_bound, seed):
 # (n, estimates, delta_bound, eta_bound): plain; a delta bound that pivots outrun and an eta bound
 # below the distribution's (failing samples in mid-estimate: the stream is put back and replayed);
 # delta_bound 0
-TAU_RUNS = [(4, 300, 1000, 2), (3, 200, 1, 1), (16, 150, 0, 2)]
+TAU_RUNS = [(4, 300, 1000, 2), (3, 200, 1, 1), (16, 150, 0, 2)]   # estimates: multiples of the batches used
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(IB, "obj", "tau_diagonal_check.o")),
@@ -427,10 +430,11 @@ def test_tau_diagonal_dropin_host_logic_on_the_cpu_shim():
         dist = _generate_diagonal("ref", t, ["-dim", "128", "-eta-bound", "2", "-det", "128", "3", "1"], np_=9)
         failed = 0
         for seed, (n, est, db, eb) in enumerate(TAU_RUNS):
-            out = _check(exe, dist, n, est, db, eb, seed + 1)
-            assert out["worst_tau_difference"] <= 2.0 ** -58
-            failed += out["failed_estimates"]
-        assert failed > 20          # the replay path was taken
+            for batch in (1, 50):
+                out = _check(exe, dist, n, est, db, eb, seed + 1, batch)
+                assert out["worst_tau_difference"] <= 2.0 ** -58
+                failed += out["failed_estimates"]
+        assert failed > 40          # the replay path was taken
 
 
 @pytest.mark.gpu
@@ -446,7 +450,8 @@ def test_gpu_tau_diagonal_dropin_equals_the_reference_in_process(args, runs):
     with tempfile.TemporaryDirectory() as t:
         dist = _generate_diagonal("gpu", t, args)
         for seed, (n, est, db, eb) in enumerate(runs):
-            out = _check(exe, dist, n, est, db, eb, seed + 1)
+            _check(exe, dist, n, 20, db, eb, seed + 7, 1)
+            out = _check(exe, dist, n, est, db, eb, seed + 1, 20)
             assert out["worst_tau_difference"] <= 2.0 ** -58
             print(f"\n{os.path.basename(dist)} n={n}: reference {out['reference_s']:.3f} s, "
                   f"drop-in {out['dropin_s']:.3f} s for {est} estimates")
