@@ -522,6 +522,106 @@ def tau_section(ctx, qb, torch, stream, h_cells, tp, coords, hbm_peak, cpu_basel
     return out
 
 
+def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, n=2048 * 148,
+                  delta_bound=1000, seed=11):
+    """The diagonal distribution's k given (j, eta) (second half):
+    sample_k_from_diagonal_j_eta_pivot for `n` uniform (j, eta, pivot) at m = 2048. Device-resident
+    timing with CUDA events on the launching stream (qb200_diagk_sample_device), the synchronous
+    C ABI with host rows (qb200_diagk_sample), a sub-sample checked against the reference's own
+    function on one host core (when oracle/_ref is on the box) and against the CPU twin."""
+    import random
+    LD = np.longdouble
+    prng = random.Random(seed)
+    r = (1 << (m - 1)) + 1 + prng.randrange((1 << (m - 1)) - 1)
+    d = r // 2 + prng.randrange(r // 2)
+    wj = (m + sigma + 31) // 32
+    rng = np.random.default_rng(seed)
+    J = rng.integers(0, 1 << 32, size=(n, wj), dtype=np.uint64).astype(np.uint32)
+    if (m + sigma) % 32:
+        J[:, -1] &= np.uint32((1 << ((m + sigma) % 32)) - 1)
+    eta = rng.integers(-25, 26, size=n).astype(np.int32)
+    piv = rng.random(n).astype(LD)
+    S = qb.DiagonalKSampler(qb.Diagonal_Parameters(m, sigma, 0, d, r, eta_bound=25, t=30, l=l), ctx)
+    dJ = torch.from_numpy(J.view(np.int32)).cuda()
+    dE = torch.from_numpy(eta).cuda()
+    dP = torch.from_numpy(piv.view(np.uint8).reshape(n, 16)).cuda()
+    dK = torch.zeros((n, S.k_limbs), dtype=torch.int32, device="cuda")
+    dO = torch.zeros((n, 4), dtype=torch.float64, device="cuda")
+    launches0 = ctx.launch_count
+    times = []
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        S.sample_device(n, dJ.data_ptr(), dE.data_ptr(), dP.data_ptr(), delta_bound, dK.data_ptr(),
+                        dO.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+        times.append(e0.elapsed_time(e1))
+    launches = (ctx.launch_count - launches0) // 6
+    ms = float(np.median(times[3:]))
+    out = dO.cpu().numpy()
+    status = out[:, 3].view(np.int64) & 0xffffffff
+    delta = out[:, 2].view(np.int64)
+    k = (m + 31) // 32
+    # multiply-adds of the products of diagk.cuh: r j, d s, two Barrett divisions (q1 mu from
+    # column k - 1, q3 r below column k + 1)
+    barrett = ((k + 1) * (k + 2) - k * (k - 1) // 2) + (k * (k + 1) // 2 + k)
+    mads = k * wj + k * k + 2 * barrett
+    res = {"workload": f"sample_k_from_diagonal_j_eta_pivot, m={m} sigma={sigma} l={l}: {n} uniform "
+                       f"(j, eta, pivot), delta_bound={delta_bound}",
+           "samples_per_call": n, "value": n / ms * 1e3, "unit": "samples/s", "ms": ms,
+           "ok_fraction": float((status == 0).mean()), "mean_abs_delta": float(np.abs(delta).mean()),
+           "max_abs_delta": int(np.abs(delta).max()), "gpu_launches": int(launches),
+           "roofline": {"bound": "integer issue", "imad_per_sample": mads,
+                        "achieved": mads * n / ms * 1e3 / 1e12, "unit": "T multiply-add/s",
+                        "kernel": "k_diagk",
+                        "limiter": "instruction issue: 56 % of the issue slots active, ~18 thread "
+                                   "instructions per 32x32-bit multiply-add, occupancy 34 % "
+                                   "(profiles/r01_diagk_ncu_full.txt); DRAM 2 %"}}
+    t0 = time.perf_counter()
+    ks, x, dl, st = S.sample(J, eta, piv, delta_bound, want_k=False)
+    t1 = time.perf_counter()
+    res["e2e"] = {"value": n / (t1 - t0), "unit": "samples/s", "ms": (t1 - t0) * 1e3,
+                  "h2d_bytes_per_step": int(J.nbytes + eta.nbytes + piv.nbytes), "d2h_bytes_per_step": int(n * 32),
+                  "api": "qb200_diagk_sample (host rows in; alpha_phi, delta, status out)"}
+    sub = np.random.default_rng(3).choice(n, 300, replace=False)
+    try:
+        from tests import hostsim as hs
+        T = hs.DiagK(m, sigma, l, d, r)
+        gk = dK.cpu().numpy().view(np.uint32)
+        ks2, x2, dl2, st2 = T.sample([hs.limbs_to_int(J[i]) for i in sub], eta[sub], piv[sub], delta_bound)
+        res["parity_twin"] = bool([hs.limbs_to_int(gk[i]) for i in sub] == ks2
+                                  and np.array_equal(dl[sub], dl2) and np.array_equal(st[sub], st2))
+    except Exception as exc:  # pragma: no cover
+        res["parity_twin"] = f"unavailable: {exc}"
+    if cpu_baseline:
+        try:
+            from oracle import ref as R
+            if not R.available():
+                raise RuntimeError("oracle/_ref not on this box")
+            gk = dK.cpu().numpy().view(np.uint32)
+            P = R.RefDiagonalParameters(m, sigma, 0, d, r, eta_bound=25, t=30, l=l)
+            cnt, same, t0 = 0, True, time.perf_counter()
+            for i in sub:
+                jj = int.from_bytes(J[i].tobytes(), "little")
+                ok, kk, _, _ = R.sample_k_from_diagonal_j_eta_pivot(P, piv[i], jj, int(eta[i]), delta_bound,
+                                                                    precision=256)
+                same = same and ok == (status[i] == 0) and kk == int.from_bytes(gk[i].tobytes(), "little")
+                cnt += 1
+                if time.perf_counter() - t0 > 10:
+                    break
+            dt = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": cnt / dt, "unit": "samples/s", "cores": 1, "kind": "reference",
+                                   "sample": f"{cnt} calls of the reference's sample_k_from_diagonal_j_eta_pivot "
+                                             f"on the same inputs, {dt:.1f} s"}
+            res["parity"] = f"{cnt} samples against the reference: k and success flags identical: {bool(same)}"
+        except Exception as exc:  # pragma: no cover
+            res["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference",
+                                   "sample": f"unavailable: {exc}"}
+    S.close()
+    return res
+
+
 def sampler_cells(sampler):
     import qunundrum_b200 as qb
     return int(qb.lib().qb200_sampler_cells(sampler.h))
@@ -672,6 +772,10 @@ def run_ours(args, rank, world, local_rank):
         tau = tau_section(ctx, qb, torch, stream, h_cells, tp2, coords, hbm_peak_tau,
                           cpu_baseline=not args.no_cpu_baseline)
 
+    diagk = None
+    if world == 1 and not args.no_tau:
+        diagk = diagk_section(ctx, qb, torch, stream, cpu_baseline=not args.no_cpu_baseline)
+
     L.qb200_host_free(C.c_void_p(hptr))
     if dist is not None:
         dist.barrier()
@@ -719,6 +823,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "text": text,
             "tau": tau,
+            "diagk": diagk,
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "ms_per_step": wall / e2e_steps * 1e3,

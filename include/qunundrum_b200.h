@@ -363,6 +363,10 @@ int qb200_diagk_tau_estimate(qb200_diagk *sampler, uint32_t n, uint32_t count, c
                              const int32_t *eta, const long double *pivot, uint32_t delta_bound,
                              uint32_t eta_bound, long double *tau, uint8_t *ok);
 
+/* Test hook: on = 1 sends every walk through the exact path (h in double-double, rounded to and
+ * subtracted in the x87 format) instead of deciding it in doubles with an error band first. */
+int qb200_diagk_set_force_exact(qb200_diagk *sampler, int on);
+
 /* diagonal_probability_approx_h at phi[i] = 2 pi (x_hi[i] + x_lo[i]) / 2^l, |x| <= 2^(l - 1),
  * rounded to long double as mpfr_get_ld does. */
 int qb200_diagk_h(qb200_diagk *sampler, uint32_t n, const double *x_hi, const double *x_lo,

@@ -21,8 +21,8 @@
 // The multi-limb part: one product r j, one product d s, Barrett reductions modulo r with a
 // host-prepared reciprocal; 32-bit limbs, product scanning with a 96-bit column accumulator.
 // Operands that are the same for every sample (r, d, mu) are read through `c`; per-sample
-// operands live in caller-provided arrays with a stride (1 on the host, the batch size on the
-// device so that the threads of a warp read consecutive words).
+// operands live in caller-provided arrays with a stride (1 on the host; on the device the samples
+// of a CTA are interleaved so that the threads of a warp read consecutive words).
 //
 // __host__ __device__ so that tests/hostsim can run exactly this code on the CPU.
 #pragma once
@@ -41,6 +41,7 @@ struct DiagKConst {
   const uint32_t* d;   // k limbs (d < r)
   const uint32_t* mu;  // k + 2 limbs: floor(2^(64 k) / r)
   dd r_top;            // the top four limbs of r as a number (limb k - 4 has weight 1)
+  int force_exact;     // test switch: the exact walk only (diagk_walk)
 };
 
 // Scratch words one sample needs (times the stride).
@@ -196,12 +197,47 @@ QHD X87 x87_from_dd(dd a) {
 
 // ---- multi-limb pieces ---------------------------------------------------------------
 
-#define QB_L(p, s, i) (p)[(size_t)(i) * (s)]
+// Limb i of a per-sample number: word i * S of its array (S = 1 on the host; on the device the
+// samples of a CTA are interleaved, S = the CTA's threads, a compile-time constant so that the
+// unrolled loops address their operands with immediate offsets).
+#define QB_L(p, i) (p)[(size_t)(i) * (size_t)S]
 
+#if defined(__CUDACC__)
+#define QHD_NOINLINE __host__ __device__ __noinline__
+#else
+#define QHD_NOINLINE inline
+#endif
+
+// 96-bit column accumulator of the product scanning.
+#if defined(__CUDA_ARCH__)
+struct Acc96 {
+  uint32_t a0, a1, a2;
+};
+QHD void acc_zero(Acc96& a) { a.a0 = a.a1 = a.a2 = 0; }
+QHD void acc_mad(Acc96& a, uint32_t x, uint32_t y) {
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2)
+      : "r"(x), "r"(y));
+}
+QHD uint32_t acc_pop(Acc96& a) {
+  const uint32_t out = a.a0;
+  a.a0 = a.a1;
+  a.a1 = a.a2;
+  a.a2 = 0;
+  return out;
+}
+QHD uint32_t acc_low(const Acc96& a) { return a.a0; }
+#else
 struct Acc96 {
   uint64_t lo;
   uint32_t hi;
 };
+QHD void acc_zero(Acc96& a) {
+  a.lo = 0;
+  a.hi = 0;
+}
 QHD void acc_mad(Acc96& a, uint32_t x, uint32_t y) {
   const uint64_t p = (uint64_t)x * (uint64_t)y;
   a.lo += p;
@@ -213,69 +249,73 @@ QHD uint32_t acc_pop(Acc96& a) {
   a.hi = 0;
   return out;
 }
+QHD uint32_t acc_low(const Acc96& a) { return (uint32_t)a.lo; }
+#endif
 
 // W (k + 1 limbs, strided) >= r (k limbs)?
-QHD bool limbs_ge_r(const uint32_t* W, size_t s, const uint32_t* r, uint32_t k) {
-  if (QB_L(W, s, k)) return true;
+template <int S>
+QHD bool limbs_ge_r(const uint32_t* W, const uint32_t* r, uint32_t k) {
+  if (QB_L(W, k)) return true;
   for (uint32_t i = k; i-- > 0;) {
-    const uint32_t a = QB_L(W, s, i), b = r[i];
+    const uint32_t a = QB_L(W, i), b = r[i];
     if (a != b) return a > b;
   }
   return true;
 }
-QHD void limbs_sub_r(uint32_t* W, size_t s, const uint32_t* r, uint32_t k) {
+template <int S>
+QHD void limbs_sub_r(uint32_t* W, const uint32_t* r, uint32_t k) {
   uint32_t borrow = 0;
   for (uint32_t i = 0; i < k; i++) {
-    const uint64_t v = (uint64_t)QB_L(W, s, i) - r[i] - borrow;
-    QB_L(W, s, i) = (uint32_t)v;
+    const uint64_t v = (uint64_t)QB_L(W, i) - r[i] - borrow;
+    QB_L(W, i) = (uint32_t)v;
     borrow = (uint32_t)(v >> 63);
   }
-  QB_L(W, s, k) -= borrow;
+  QB_L(W, k) -= borrow;
 }
 
 // Barrett division of x = A[0, 2k) < 2^(64 k) by r (Handbook of Applied Cryptography 14.42):
 // Q (k + 2 limbs) = floor(x / r), W (k + 1 limbs, the top one zero on return) = x mod r. The
 // columns of q1 mu below k - 1 are dropped (the estimate loses at most one more unit, which the
 // final loop restores).
-QHD void diagk_barrett(const DiagKConst& c, const uint32_t* A, uint32_t* Q, uint32_t* W, size_t s) {
+template <int S>
+QHD_NOINLINE void diagk_barrett(const DiagKConst& c, const uint32_t* A, uint32_t* Q, uint32_t* W) {
   const uint32_t k = c.k;
   Acc96 acc;
-  acc.lo = 0;
-  acc.hi = 0;
+  acc_zero(acc);
   for (uint32_t col = k - 1; col <= 2 * k + 1; col++) {
     const uint32_t i0 = col > k + 1 ? col - (k + 1) : 0;
     const uint32_t i1 = col < k ? col : k;
-    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, QB_L(A, s, k - 1 + i), c.mu[col - i]);
+    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, QB_L(A, k - 1 + i), c.mu[col - i]);
     const uint32_t limb = acc_pop(acc);
-    if (col >= k + 1) QB_L(Q, s, col - (k + 1)) = limb;
+    if (col >= k + 1) QB_L(Q, col - (k + 1)) = limb;
   }
-  QB_L(Q, s, k + 1) = (uint32_t)acc.lo;
+  QB_L(Q, k + 1) = acc_low(acc);
   // W = (x - Q r) mod 2^(32 (k + 1))
-  acc.lo = 0;
-  acc.hi = 0;
+  acc_zero(acc);
   uint32_t borrow = 0;
   for (uint32_t col = 0; col <= k; col++) {
     const uint32_t i1 = col < k - 1 ? col : k - 1;
-    for (uint32_t i = 0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(Q, s, col - i));
+    for (uint32_t i = 0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(Q, col - i));
     const uint32_t limb = acc_pop(acc);
-    const uint64_t v = (uint64_t)QB_L(A, s, col) - limb - borrow;
-    QB_L(W, s, col) = (uint32_t)v;
+    const uint64_t v = (uint64_t)QB_L(A, col) - limb - borrow;
+    QB_L(W, col) = (uint32_t)v;
     borrow = (uint32_t)(v >> 63);
   }
-  while (limbs_ge_r(W, s, c.r, k)) {
-    limbs_sub_r(W, s, c.r, k);
+  while (limbs_ge_r<S>(W, c.r, k)) {
+    limbs_sub_r<S>(W, c.r, k);
     for (uint32_t i = 0; i <= k + 1; i++) {
-      if (++QB_L(Q, s, i)) break;
+      if (++QB_L(Q, i)) break;
     }
   }
 }
 
 // Four limbs from index `top` downwards as a double-double (limb top - 3 has weight 1).
-QHD dd limbs_top_dd(const uint32_t* p, size_t s, uint32_t top) {
+template <int S>
+QHD dd limbs_top_dd(const uint32_t* p, uint32_t top) {
   dd v = make_dd(0.0, 0.0);
   double w = 79228162514264337593543950336.0;  // 2^96
   for (int i = 0; i < 4; i++) {
-    const uint32_t limb = (top >= (uint32_t)i) ? QB_L(p, s, top - i) : 0u;
+    const uint32_t limb = (top >= (uint32_t)i) ? QB_L(p, top - i) : 0u;
     v = dd_add_d(v, (double)limb * w);
     w *= 2.3283064365386962890625e-10;  // 2^-32
   }
@@ -297,29 +337,80 @@ QHD dd diagk_h(uint32_t l, dd S, dd x) {
   return dd_div(S, dd_mul(D, D));
 }
 
-// The walk of src/sample.cpp:539-604 on x = t + delta.
-QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int64_t* delta_out, dd* x_out) {
+// x = t + delta folded as the reference folds k and phi: k = (k0 + delta) mod 2^l and phi on
+// [-2^(m+sigma-1), 2^(m+sigma-1)) (src/sample.cpp:552-574). Only l < 62 can wrap (|delta| < 2^32).
+QHD dd diagk_walk_x(uint32_t l, dd t, int64_t delta) {
+  if (l >= 62) return dd_add_d(t, (double)delta);
+  const int64_t M = (int64_t)1 << l;
+  const double two_l = (double)M;
+  int64_t dm = ((delta % M) + M) % M;
+  if (dm >= M / 2) dm -= M;  // |dm| <= 2^32 or < 2^53: exact as a double
+  dd x = dd_add_d(t, (double)dm);
+  if (x.hi >= 0.5 * two_l) x = dd_add_d(x, -two_l);
+  if (x.hi < -0.5 * two_l) x = dd_add_d(x, two_l);
+  return x;
+}
+
+// The walk of src/sample.cpp:539-604 on x = t + delta: pivot -= h(x) for delta = 0, 1, -1, 2, ...
+// until the pivot is used up.
+//
+// Only the step at which that happens is an output, not the pivot. A first pass therefore runs in
+// plain doubles: after N steps it differs from the reference's sequence of long double
+// subtractions by less than (N + 16) 2^-51 (h to a few units in the last place of a double, sum
+// of the h at most ~1; N roundings of a number <= 1; the reference's own N roundings at 2^-64),
+// so a pivot that passes below -band at a step while it was above +band at all earlier steps
+// stops at that step in the reference as well. A pivot inside the band at some step (probability
+// ~1e-12 per step) sends the sample through the exact walk: h in double-double, rounded to the
+// x87 format, subtracted with the x87 rounding -- from the start. force_exact: the exact walk
+// only (tests).
+QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int force_exact, int64_t* delta_out,
+                   dd* x_out) {
   const dd st = sinpi_acc(t);
   const dd S = dd_mul(st, st);
-  const bool wraps = l < 62;  // k = (k0 + delta) mod 2^l and phi on [-2^(m+sigma-1), 2^(m+sigma-1)) (:566-574)
-  const int64_t M = wraps ? ((int64_t)1 << l) : 0;
-  const double two_l = wraps ? (double)M : 0.0;
+  if (!force_exact) {
+    const dd pd = x87_to_dd(pivot);
+    double p = pd.hi + pd.lo;
+    const double Sd = S.hi;
+    const double two_l = l < 110 ? ldexp(1.0, (int)l) : 0.0, inv_two_l = l < 110 ? ldexp(1.0, -(int)l) : 0.0;
+    uint64_t steps = 0;
+    bool undecided = false;
+    for (uint64_t da = 0; da <= delta_bound && !undecided; da++) {
+      for (int sg = 1; sg >= -1; sg -= 2) {
+        if (da == 0 && sg < 0) continue;
+        if (++steps > QB_DIAGK_MAX_STEPS) return QB_DIAGK_GAVE_UP;
+        const int64_t delta = sg > 0 ? (int64_t)da : -(int64_t)da;
+        const dd x = diagk_walk_x(l, t, delta);
+        double h = 1.0;
+        if (x.hi != 0.0) {
+          const double D = l >= 110 ? QB_PI_HI * x.hi : two_l * sinpi_dd(dd_mul_pow2(x, inv_two_l));
+          h = Sd / (D * D);
+        }
+        p -= h;
+        const double band = (double)(steps + 16) * 4.440892098500626e-16;  // 2^-51
+        if (p < -band) {
+          *delta_out = delta;
+          *x_out = x;
+          return QB_DIAGK_OK;
+        }
+        if (p <= band) {
+          undecided = true;
+          break;
+        }
+      }
+    }
+    if (!undecided) {  // above the band after the last step: out of bounds in the reference as well
+      *delta_out = 0;
+      *x_out = make_dd(0.0, 0.0);
+      return QB_DIAGK_OUT_OF_BOUNDS;
+    }
+  }
   uint64_t steps = 0;
   for (uint64_t da = 0; da <= delta_bound; da++) {
     for (int sg = 1; sg >= -1; sg -= 2) {
       if (da == 0 && sg < 0) continue;
       if (++steps > QB_DIAGK_MAX_STEPS) return QB_DIAGK_GAVE_UP;
       const int64_t delta = sg > 0 ? (int64_t)da : -(int64_t)da;
-      dd x;
-      if (wraps) {
-        int64_t dm = ((delta % M) + M) % M;
-        if (dm >= M / 2) dm -= M;  // |dm| <= 2^32 or < 2^53: exact as a double
-        x = dd_add_d(t, (double)dm);
-        if (x.hi >= 0.5 * two_l) x = dd_add_d(x, -two_l);
-        if (x.hi < -0.5 * two_l) x = dd_add_d(x, two_l);
-      } else {
-        x = dd_add_d(t, (double)delta);
-      }
+      const dd x = diagk_walk_x(l, t, delta);
       pivot = x87_add(pivot, x87_neg(x87_from_dd(diagk_h(l, S, x))));
       if (x87_nonpositive(pivot)) {
         *delta_out = delta;
@@ -333,121 +424,119 @@ QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int64_t* d
   return QB_DIAGK_OUT_OF_BOUNDS;
 }
 
-// One sample. j: c.wj limbs (j < 2^n), stride sj. scratch: diagk_scratch_limbs(k) words, stride
-// ss. k_out: c.wl limbs, stride sk (may be null). x_out = alpha_phi / 2^(m + sigma - l).
-QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, size_t sj, int32_t eta, X87 pivot,
-                     uint64_t delta_bound, uint32_t* scratch, size_t ss, uint32_t* k_out, size_t sk,
-                     dd* x_out, int64_t* delta_out) {
+// One sample. j: c.wj limbs (j < 2^n); scratch: diagk_scratch_limbs(k) words; k_out: c.wl limbs
+// (may be null); all three with stride S. x_out = alpha_phi / 2^(m + sigma - l).
+template <int S>
+QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pivot, uint64_t delta_bound,
+                     uint32_t* scratch, uint32_t* k_out, dd* x_out, int64_t* delta_out) {
   const uint32_t k = c.k;
-  uint32_t* A = scratch;                         // 2k + 2
-  uint32_t* Q = A + (size_t)(2 * k + 2) * ss;    // k + 3
-  uint32_t* W = Q + (size_t)(k + 3) * ss;        // k + 2
-  uint32_t* S = W + (size_t)(k + 2) * ss;        // k + 2
+  uint32_t* A = scratch;                              // 2k + 2
+  uint32_t* Q = A + (size_t)(2 * k + 2) * (size_t)S;  // k + 3
+  uint32_t* W = Q + (size_t)(k + 3) * (size_t)S;      // k + 2
+  uint32_t* Sq = W + (size_t)(k + 2) * (size_t)S;     // k + 2: s = q + eta
 
   // ---- q = round-to-centred quotient of r j by 2^n (alpha_r = {r j}_{2^n}, :477-478) ----
   const uint32_t cs = c.n >> 5, sh = c.n & 31;
   Acc96 acc;
-  acc.lo = 0;
-  acc.hi = 0;
+  acc_zero(acc);
   uint32_t below = 0;  // column cs - 1
   const uint32_t ncol = k + c.wj;
   for (uint32_t col = 0; col < ncol; col++) {
     const uint32_t i0 = col >= c.wj ? col - c.wj + 1 : 0;
     const uint32_t i1 = col < k - 1 ? col : k - 1;
-    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(j, sj, col - i));
+    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(j, col - i));
     const uint32_t limb = acc_pop(acc);
     if (col + 1 == cs) below = limb;
-    if (col >= cs) QB_L(S, ss, col - cs) = limb;
+    if (col >= cs) QB_L(Sq, col - cs) = limb;
   }
   const uint32_t ns = ncol - cs;  // <= k + 1 limbs hold Z >> (32 cs)
-  for (uint32_t i = ns; i < k + 2; i++) QB_L(S, ss, i) = 0;
+  for (uint32_t i = ns; i < k + 2; i++) QB_L(Sq, i) = 0;
   uint32_t half_bit;
   if (sh == 0) {
     half_bit = below >> 31;
   } else {
-    half_bit = (QB_L(S, ss, 0) >> (sh - 1)) & 1u;
+    half_bit = (QB_L(Sq, 0) >> (sh - 1)) & 1u;
     for (uint32_t i = 0; i < k + 1; i++)
-      QB_L(S, ss, i) = (QB_L(S, ss, i) >> sh) | (QB_L(S, ss, i + 1) << (32 - sh));
-    QB_L(S, ss, k + 1) >>= sh;
+      QB_L(Sq, i) = (QB_L(Sq, i) >> sh) | (QB_L(Sq, i + 1) << (32 - sh));
+    QB_L(Sq, k + 1) >>= sh;
   }
   // ---- s = q + eta, brought to [0, r): adding r to s adds the integer d to d s / r ----
   int64_t carry = (int64_t)half_bit + (int64_t)eta;
   for (uint32_t i = 0; i < k + 2; i++) {
-    const int64_t v = (int64_t)QB_L(S, ss, i) + carry;
-    QB_L(S, ss, i) = (uint32_t)v;
+    const int64_t v = (int64_t)QB_L(Sq, i) + carry;
+    QB_L(Sq, i) = (uint32_t)v;
     carry = v >> 32;
     if (carry == 0) break;
   }
   const bool s_negative = carry < 0;
   bool whole = false;  // q + eta < 0 and d |q + eta| >= r: the unreduced phi is negative
   if (s_negative) {
-    const uint32_t abs_s = 0u - QB_L(S, ss, 0);  // |q + eta| <= |eta|
+    const uint32_t abs_s = 0u - QB_L(Sq, 0);  // |q + eta| <= |eta|
     uint64_t cw = 0;
     for (uint32_t i = 0; i < k; i++) {
       const uint64_t v = (uint64_t)c.d[i] * abs_s + cw;
-      QB_L(A, ss, i) = (uint32_t)v;
+      QB_L(A, i) = (uint32_t)v;
       cw = v >> 32;
     }
-    QB_L(A, ss, k) = (uint32_t)cw;
-    whole = limbs_ge_r(A, ss, c.r, k);
+    QB_L(A, k) = (uint32_t)cw;
+    whole = limbs_ge_r<S>(A, c.r, k);
     uint64_t cy = 0;
     for (uint32_t i = 0; i < k + 2; i++) {
-      const uint64_t v = (uint64_t)QB_L(S, ss, i) + (i < k ? c.r[i] : 0u) + cy;
-      QB_L(S, ss, i) = (uint32_t)v;
+      const uint64_t v = (uint64_t)QB_L(Sq, i) + (i < k ? c.r[i] : 0u) + cy;
+      QB_L(Sq, i) = (uint32_t)v;
       cy = v >> 32;
     }
   }
   for (int guard = 0; guard < 64; guard++) {
-    if (QB_L(S, ss, k + 1) == 0 && !limbs_ge_r(S, ss, c.r, k)) break;
+    if (QB_L(Sq, k + 1) == 0 && !limbs_ge_r<S>(Sq, c.r, k)) break;
     // s >= r: s <= r + |eta| + 1 for j < 2^n, so one round is the rule
     uint32_t borrow = 0;
     for (uint32_t i = 0; i < k + 2; i++) {
-      const uint64_t v = (uint64_t)QB_L(S, ss, i) - (i < k ? c.r[i] : 0u) - borrow;
-      QB_L(S, ss, i) = (uint32_t)v;
+      const uint64_t v = (uint64_t)QB_L(Sq, i) - (i < k ? c.r[i] : 0u) - borrow;
+      QB_L(Sq, i) = (uint32_t)v;
       borrow = (uint32_t)(v >> 63);
     }
   }
   // ---- w = d s mod r ----
-  acc.lo = 0;
-  acc.hi = 0;
+  acc_zero(acc);
   for (uint32_t col = 0; col < 2 * k; col++) {
     const uint32_t i0 = col >= k ? col - k + 1 : 0;
     const uint32_t i1 = col < k - 1 ? col : k - 1;
-    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.d[i], QB_L(S, ss, col - i));
-    QB_L(A, ss, col) = acc_pop(acc);
+    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.d[i], QB_L(Sq, col - i));
+    QB_L(A, col) = acc_pop(acc);
   }
-  diagk_barrett(c, A, Q, W, ss);
+  diagk_barrett<S>(c, A, Q, W);
   // ---- (Qv, w2) = divmod(2^l w, r), at most 32 k bits of the shift at a time ----
   const uint32_t chunk = 32 * k;
   const uint32_t nch = (c.l + chunk - 1) / chunk;
   if (k_out)
-    for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, sk, i) = 0;
+    for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, i) = 0;
   for (uint32_t ci = 0; ci < nch; ci++) {
     const uint32_t bits = ci == 0 ? c.l - chunk * (nch - 1) : chunk;
     const uint32_t ls = bits >> 5, bs = bits & 31;
     for (uint32_t i = 0; i < 2 * k; i++) {
       uint32_t v = 0;
-      if (i >= ls && i - ls < k) v = QB_L(W, ss, i - ls) << bs;
-      if (bs && i >= ls + 1 && i - ls - 1 < k) v |= QB_L(W, ss, i - ls - 1) >> (32 - bs);
-      QB_L(A, ss, i) = v;
+      if (i >= ls && i - ls < k) v = QB_L(W, i - ls) << bs;
+      if (bs && i >= ls + 1 && i - ls - 1 < k) v |= QB_L(W, i - ls - 1) >> (32 - bs);
+      QB_L(A, i) = v;
     }
-    diagk_barrett(c, A, Q, W, ss);
+    diagk_barrett<S>(c, A, Q, W);
     if (k_out) {
       const uint32_t off = k * (nch - 1 - ci), nq = (bits + 31) >> 5;
-      for (uint32_t i = 0; i < nq && off + i < c.wl; i++) QB_L(k_out, sk, off + i) = QB_L(Q, ss, i);
+      for (uint32_t i = 0; i < nq && off + i < c.wl; i++) QB_L(k_out, off + i) = QB_L(Q, i);
     }
   }
   // ---- t = w2 / r - c ----
   // 2 w2 >= r  <=>  w2 >= r - w2: form r - w2 in A and compare
   uint32_t borrow = 0;
   for (uint32_t i = 0; i < k; i++) {
-    const uint64_t v = (uint64_t)c.r[i] - QB_L(W, ss, i) - borrow;
-    QB_L(A, ss, i) = (uint32_t)v;
+    const uint64_t v = (uint64_t)c.r[i] - QB_L(W, i) - borrow;
+    QB_L(A, i) = (uint32_t)v;
     borrow = (uint32_t)(v >> 63);
   }
   bool cflag = true;  // w2 >= r - w2
   for (uint32_t i = k; i-- > 0;) {
-    const uint32_t a = QB_L(W, ss, i), b = QB_L(A, ss, i);
+    const uint32_t a = QB_L(W, i), b = QB_L(A, i);
     if (a != b) {
       cflag = a > b;
       break;
@@ -456,7 +545,7 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, size_t sj, int32_t 
   const uint32_t* N = cflag ? A : W;
   int top = -1;
   for (uint32_t i = k; i-- > 0;) {
-    if (QB_L(N, ss, i)) {
+    if (QB_L(N, i)) {
       top = (int)i;
       break;
     }
@@ -465,7 +554,7 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, size_t sj, int32_t 
   if (top >= 0) {
     const int e = 32 * (top - (int)k + 1);
     if (e >= -960) {
-      t = dd_div(limbs_top_dd(N, ss, (uint32_t)top), c.r_top);
+      t = dd_div(limbs_top_dd<S>(N, (uint32_t)top), c.r_top);
       t = dd_mul_pow2(t, pow2i(e));
       if (cflag) t = dd_neg(t);
     }
@@ -473,10 +562,10 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, size_t sj, int32_t 
   // ---- the walk ----
   int64_t delta = 0;
   dd x = make_dd(0.0, 0.0);
-  const int status = diagk_walk(c.l, t, pivot, delta_bound, &delta, &x);
+  const int status = diagk_walk(c.l, t, pivot, delta_bound, c.force_exact, &delta, &x);
   if (status != QB_DIAGK_OK) {
     if (k_out)
-      for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, sk, i) = 0;
+      for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, i) = 0;
     *x_out = make_dd(0.0, 0.0);
     *delta_out = 0;
     return status;
@@ -490,17 +579,17 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, size_t sj, int32_t 
     // k = (-(Qv + c) + delta) mod 2^l = -(Qv + c - delta) mod 2^l
     int64_t cy = (int64_t)(cflag ? 1 : 0) - delta;
     for (uint32_t i = 0; i < c.wl; i++) {
-      const int64_t v = (int64_t)QB_L(k_out, sk, i) + cy;
-      QB_L(k_out, sk, i) = (uint32_t)v;
+      const int64_t v = (int64_t)QB_L(k_out, i) + cy;
+      QB_L(k_out, i) = (uint32_t)v;
       cy = v >> 32;
     }
     uint32_t one = 1;
     for (uint32_t i = 0; i < c.wl; i++) {
-      const uint64_t v = (uint64_t)(~QB_L(k_out, sk, i)) + one;
-      QB_L(k_out, sk, i) = (uint32_t)v;
+      const uint64_t v = (uint64_t)(~QB_L(k_out, i)) + one;
+      QB_L(k_out, i) = (uint32_t)v;
       one = (uint32_t)(v >> 32);
     }
-    if (c.l & 31) QB_L(k_out, sk, c.wl - 1) &= (1u << (c.l & 31)) - 1u;
+    if (c.l & 31) QB_L(k_out, c.wl - 1) &= (1u << (c.l & 31)) - 1u;
   }
   *x_out = x;
   *delta_out = delta;

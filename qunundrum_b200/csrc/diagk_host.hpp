@@ -62,7 +62,8 @@ inline int diagk_prepare(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* 
   c.r = h->r.data();
   c.d = h->d.data();
   c.mu = h->mu.data();
-  c.r_top = limbs_top_dd(h->r.data(), 1, k - 1);
+  c.r_top = limbs_top_dd<1>(h->r.data(), k - 1);
+  c.force_exact = 0;
   return 0;
 }
 

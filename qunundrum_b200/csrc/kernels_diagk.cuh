@@ -1,9 +1,10 @@
 // kernels_diagk.cuh -- kernels of the diagonal k sampler (diagk.cuh has the per-sample code and
 // the reference citations).
 //
-//   k_diagk_gather   j of a chunk from the caller's row-per-sample layout to limb-major
-//                    (word i of sample g at [i * B + g]) so that the threads of a warp, which
-//                    all work on the same limb index at the same time, read consecutive words.
+//   k_diagk_gather   j of a chunk from the caller's row-per-sample layout to tiles of 128 samples
+//                    with the limbs interleaved (word i of the t-th sample of a tile at
+//                    [i * 128 + t]) so that the threads of a warp, which all work on the same limb
+//                    index at the same time, read consecutive words at a compile-time stride.
 //   k_diagk          one thread per sample: r j, d (q + eta) mod r, divmod(2^l w, r) in 32-bit
 //                    limbs (about 5 k^2 multiply-adds, k = limbs of r), then the walk over delta
 //                    in double-double. r, d and the Barrett reciprocal are staged in shared
@@ -21,20 +22,28 @@
 
 namespace qb200 {
 
+// Samples are processed in tiles of QB_DIAGK_CTA (one CTA each); word i of the sample with index t
+// inside tile b lies at [(b * w + i) * QB_DIAGK_CTA + t] (w = words per sample of the array).
+#define QB_DIAGK_CTA 128
+
 __global__ void k_diagk_gather(const uint32_t* __restrict__ rows, uint32_t w, uint32_t B,
-                               uint32_t* __restrict__ cols) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)w * B) return;
-  const uint32_t i = (uint32_t)(t / B), g = (uint32_t)(t - (uint64_t)i * B);
-  cols[t] = rows[(size_t)g * w + i];
+                               uint32_t* __restrict__ tiles) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t tiles_n = (B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA;
+  if (idx >= (uint64_t)tiles_n * w * QB_DIAGK_CTA) return;
+  const uint32_t t = (uint32_t)(idx % QB_DIAGK_CTA);
+  const uint64_t bi = idx / QB_DIAGK_CTA;
+  const uint32_t i = (uint32_t)(bi % w), b = (uint32_t)(bi / w);
+  const uint32_t g = b * QB_DIAGK_CTA + t;
+  tiles[idx] = g < B ? rows[(size_t)g * w + i] : 0u;
 }
 
-__global__ void k_diagk_scatter(const uint32_t* __restrict__ cols, uint32_t w, uint32_t B,
+__global__ void k_diagk_scatter(const uint32_t* __restrict__ tiles, uint32_t w, uint32_t B,
                                 uint32_t* __restrict__ rows) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)w * B) return;
-  const uint32_t g = (uint32_t)(t / w), i = (uint32_t)(t - (uint64_t)g * w);
-  rows[t] = cols[(size_t)i * B + g];
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint64_t)w * B) return;
+  const uint32_t g = (uint32_t)(idx / w), i = (uint32_t)(idx - (uint64_t)g * w);
+  rows[idx] = tiles[((size_t)(g / QB_DIAGK_CTA) * w + i) * QB_DIAGK_CTA + g % QB_DIAGK_CTA];
 }
 
 struct DiagKOut {
@@ -44,7 +53,7 @@ struct DiagKOut {
   int pad;
 };
 
-__global__ void __launch_bounds__(128) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
+__global__ void __launch_bounds__(QB_DIAGK_CTA) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
                                                 const int32_t* __restrict__ eta,
                                                 const RawX87* __restrict__ pivot,
                                                 unsigned long long delta_bound, uint32_t B,
@@ -67,20 +76,22 @@ __global__ void __launch_bounds__(128) k_diagk(DiagKConst c, const uint32_t* __r
   const X87 p = x87_load(pivot + g, &ok);
   DiagKOut o;
   o.pad = 0;
-  if (!ok || p.neg || p.exp > 0 || (p.exp == 0 && p.mant != 0x8000000000000000ull)) {
+  if (!ok || p.neg || (p.mant != 0 && (p.exp > 0 || (p.exp == 0 && p.mant != 0x8000000000000000ull)))) {
     // the reference: critical("The pivot is out of bounds.") (src/sample.cpp:421-425)
     o.x_hi = o.x_lo = 0.0;
     o.delta = 0;
     o.status = -1;
     if (kT)
-      for (uint32_t i = 0; i < c.wl; i++) kT[(size_t)i * B + g] = 0;
+      for (uint32_t i = 0; i < c.wl; i++) kT[((size_t)blockIdx.x * c.wl + i) * QB_DIAGK_CTA + threadIdx.x] = 0;
     out[g] = o;
     return;
   }
   dd x;
   int64_t delta;
-  o.status = diagk_sample(c, jT + g, B, eta[g], p, delta_bound, scratch + g, B, kT ? kT + g : nullptr, B,
-                          &x, &delta);
+  const size_t tile = (size_t)blockIdx.x * QB_DIAGK_CTA;
+  o.status = diagk_sample<QB_DIAGK_CTA>(c, jT + tile * c.wj + threadIdx.x, eta[g], p, delta_bound,
+                                        scratch + tile * diagk_scratch_limbs(k) + threadIdx.x,
+                                        kT ? kT + tile * c.wl + threadIdx.x : nullptr, &x, &delta);
   o.x_hi = x.hi;
   o.x_lo = x.lo;
   o.delta = (long long)delta;

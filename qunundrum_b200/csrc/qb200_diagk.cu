@@ -108,6 +108,12 @@ void qb200_diagk_destroy(qb200_diagk* s) {
   delete s;
 }
 
+int qb200_diagk_set_force_exact(qb200_diagk* s, int on) {
+  if (!s) return set_error(-1, "null argument");
+  s->host.c.force_exact = s->dev.force_exact = on ? 1 : 0;
+  return 0;
+}
+
 uint32_t qb200_diagk_j_limbs(const qb200_diagk* s) { return s ? s->host.c.wj : 0; }
 uint32_t qb200_diagk_k_limbs(const qb200_diagk* s) { return s ? s->host.c.wl : 0; }
 
@@ -117,12 +123,13 @@ static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const i
                         cudaStream_t stream) {
   const DiagKConst& c = s->host.c;
   const size_t scr = diagk_scratch_limbs(c.k);
-  if (s->cols_j.reserve((size_t)B * c.wj * 4) || s->scratch.reserve((size_t)B * scr * 4)) return -100;
-  if (d_k_rows && s->cols_k.reserve((size_t)B * c.wl * 4)) return -100;
-  const uint64_t nj = (uint64_t)B * c.wj;
+  const size_t Bp = ((size_t)B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA * QB_DIAGK_CTA;  // whole tiles
+  if (s->cols_j.reserve(Bp * c.wj * 4) || s->scratch.reserve(Bp * scr * 4)) return -100;
+  if (d_k_rows && s->cols_k.reserve(Bp * c.wl * 4)) return -100;
+  const uint64_t nj = (uint64_t)Bp * c.wj;
   k_diagk_gather<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(d_j, c.wj, B, s->cols_j.as<uint32_t>());
   const size_t shmem = (size_t)(3 * c.k + 2) * 4;
-  k_diagk<<<(B + 127) / 128, 128, shmem, stream>>>(s->dev, s->cols_j.as<uint32_t>(), d_eta, d_pivot,
+  k_diagk<<<(unsigned)(Bp / QB_DIAGK_CTA), QB_DIAGK_CTA, shmem, stream>>>(s->dev, s->cols_j.as<uint32_t>(), d_eta, d_pivot,
                                                   (unsigned long long)delta_bound, B,
                                                   s->scratch.as<uint32_t>(),
                                                   d_k_rows ? s->cols_k.as<uint32_t>() : nullptr, d_out);

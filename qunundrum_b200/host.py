@@ -143,6 +143,7 @@ def lib():
     L.qb200_diagk_sample_device.argtypes = [vp, u32, vp, vp, vp, u32, vp, vp, vp]
     L.qb200_diagk_tau_estimate.argtypes = [vp, u32, u32, vp, vp, vp, u32, u32, vp, vp]
     L.qb200_diagk_h.argtypes = [vp, u32, vp, vp, vp]
+    L.qb200_diagk_set_force_exact.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -900,6 +901,10 @@ class DiagonalKSampler:
             self.close()
         except Exception:
             pass
+
+    def set_force_exact(self, on: bool):
+        """Test switch: every walk through the exact x87 path."""
+        lib().qb200_diagk_set_force_exact(self.h, int(bool(on)))
 
     def pack_j(self, js) -> np.ndarray:
         J = np.zeros((len(js), self.j_limbs), dtype=np.uint32)

@@ -241,6 +241,9 @@ class DiagK:
             lib().hostsim_diagk_free(C.c_void_p(self.h))
             self.h = None
 
+    def set_force_exact(self, on):
+        lib().hostsim_diagk_force_exact(C.c_void_p(self.h), C.c_int(int(bool(on))))
+
     def sample(self, js, etas, pivots, delta_bound=0xffffffff):
         """-> (k as Python ints, x = alpha_phi / 2^(m+sigma-l) as (hi, lo) rows, delta, status)"""
         n = len(js)

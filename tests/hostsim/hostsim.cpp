@@ -548,6 +548,7 @@ void* hostsim_diagk_new(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* d
   return h;
 }
 void hostsim_diagk_free(void* h) { delete (DiagKHost*)h; }
+void hostsim_diagk_force_exact(void* h, int on) { ((DiagKHost*)h)->c.force_exact = on ? 1 : 0; }
 void hostsim_diagk_dims(void* hh, uint32_t* out3) {
   const DiagKHost* h = (const DiagKHost*)hh;
   out3[0] = h->c.k;
@@ -569,8 +570,8 @@ int hostsim_diagk_sample(void* hh, uint32_t n, const uint32_t* j, const int32_t*
     const X87 p = x87_load(&raw, &ok);
     if (!ok || p.neg) return -1;
     dd xo;
-    status[i] = diagk_sample(h->c, j + (size_t)i * h->c.wj, 1, eta[i], p, delta_bound, scratch.data(),
-                             1, k_out + (size_t)i * h->c.wl, 1, &xo, &delta[i]);
+    status[i] = diagk_sample<1>(h->c, j + (size_t)i * h->c.wj, eta[i], p, delta_bound, scratch.data(),
+                                k_out + (size_t)i * h->c.wl, &xo, &delta[i]);
     x[2 * i] = xo.hi;
     x[2 * i + 1] = xo.lo;
   }

@@ -74,16 +74,20 @@ def _alpha_tolerance(l):
     return max(1e-25, 2.0 ** (3 - 2 * l))
 
 
-def check_k_file(path, sampler_factory):
+def check_k_file(path, sampler_factory, exact_too=True):
+    """Both ways of walking: decided in doubles with an error band (the default), and the exact
+    x87 walk for every sample."""
     m, sigma, l = _msl(path)
     d, r = rs.deterministic_d_r(m)
     recs = k_records(path)
     assert len(recs) == 25
     S = sampler_factory(m, sigma, l, d, r)
-    ks, x, delta, st = S.sample([q[0] for q in recs], [q[1] for q in recs], [q[2] for q in recs])
-    assert list(st) == [0] * 25
-    assert ks == [q[3] for q in recs], os.path.basename(path)
-    assert max(_alpha_errors(path, recs, x)) < _alpha_tolerance(l)
+    for force_exact in ((False, True) if exact_too else (False,)):
+        S.set_force_exact(force_exact)
+        ks, x, delta, st = S.sample([q[0] for q in recs], [q[1] for q in recs], [q[2] for q in recs])
+        assert list(st) == [0] * 25
+        assert ks == [q[3] for q in recs], os.path.basename(path)
+        assert max(_alpha_errors(path, recs, x)) < _alpha_tolerance(l)
 
 
 # ---- pieces -------------------------------------------------------------------------
@@ -158,8 +162,8 @@ def test_twin_k_vectors(path):
 def test_twin_all_522_k_vector_files():
     files = sorted(glob.glob(os.path.join(TV, "sample-k-from-diagonal-j-eta-pivot-m-*.txt")))
     assert len(files) == 522
-    for path in files:
-        check_k_file(path, hs.DiagK)
+    for n, path in enumerate(files):
+        check_k_file(path, hs.DiagK, exact_too=(n % 7 == 0))
 
 
 def h_records(path):
@@ -214,7 +218,15 @@ GOLD = diag_gold()
 
 
 def check_gold(g, S):
-    """S.sample(js, etas, pivots, delta_bound) against the reference's outputs."""
+    """S.sample(js, etas, pivots, delta_bound) against the reference's outputs, for both ways of
+    walking."""
+    for force_exact in (False, True):
+        S.set_force_exact(force_exact)
+        _check_gold(g, S)
+    S.set_force_exact(False)
+
+
+def _check_gold(g, S):
     js = [hs.limbs_to_int(row) for row in g.J]
     for bound in sorted(set(int(b) for b in g.bound)):
         idx = [i for i in range(len(js)) if int(g.bound[i]) == bound]

@@ -75,7 +75,11 @@ def test_estimate_runs_with_the_tau_dropin_matches_the_reference(gen, gen_args, 
         path = os.path.join("distributions", name)
         assert os.path.exists(os.path.join(t, path))
         runs = {}
-        for flavour, np_ in (("ref", cores + 1), ("gpu", 3)):
+        # (the diagonal executable's quantile depends on how many clients merge their ordered lists --
+        # the reference itself gives tau = 3.86 ... 3.88 with 8 or 16 clients and 3.93 with 2 on the
+        # case below -- so both flavours run with the same number of ranks there)
+        gpu_np = cores + 1 if "diagonal" in exe else 3
+        for flavour, np_ in (("ref", cores + 1), ("gpu", gpu_np)):
             cwd = os.path.join(t, flavour)
             os.makedirs(cwd)
             os.symlink(os.path.join(t, "distributions"), os.path.join(cwd, "distributions"))
@@ -83,7 +87,7 @@ def test_estimate_runs_with_the_tau_dropin_matches_the_reference(gen, gen_args, 
             runs[flavour] = (_log_lines(cwd), wall)
         ref, gpu = runs["ref"][0], runs["gpu"][0]
         print(f"\n{exe}: reference {runs['ref'][1]:.1f} s on {cores} client cores, "
-              f"drop-in {runs['gpu'][1]:.1f} s with 2 client ranks on one GPU")
+              f"drop-in {runs['gpu'][1]:.1f} s with {gpu_np - 1} client ranks on one GPU")
         for a, b in zip(ref, gpu):
             print("  ref", a, "\n  gpu", b)
         assert len(ref) == len(gpu) and len(ref) >= 2
