@@ -575,9 +575,10 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
            "roofline": {"bound": "integer issue", "imad_per_sample": mads,
                         "achieved": mads * n / ms * 1e3 / 1e12, "unit": "T multiply-add/s",
                         "kernel": "k_diagk",
-                        "limiter": "instruction issue: 56 % of the issue slots active, ~18 thread "
-                                   "instructions per 32x32-bit multiply-add, occupancy 34 % "
-                                   "(profiles/r01_diagk_ncu_full.txt); DRAM 2 %"}}
+                        "limiter": "load/store pipe: two loads (one limb from L1, one from shared "
+                                   "memory) per 32x32-bit multiply-add, LSU 64 % busy, issue slots 59 % "
+                                   "active, ~4 thread instructions per multiply-add in the products "
+                                   "(profiles/r01_diagk_ncu_full.txt); DRAM 7 %"}}
     t0 = time.perf_counter()
     ks, x, dl, st = S.sample(J, eta, piv, delta_bound, want_k=False)
     t1 = time.perf_counter()

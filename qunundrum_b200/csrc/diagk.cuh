@@ -252,6 +252,19 @@ QHD uint32_t acc_pop(Acc96& a) {
 QHD uint32_t acc_low(const Acc96& a) { return (uint32_t)a.lo; }
 #endif
 
+// One column of a product: sum of cst[n * CS] * smp[n * SS * S] over n < count (CS, SS = +-1: the
+// directions in which the constant and the per-sample operand are walked). Pointers advanced by
+// compile-time steps, so that the unrolled loop addresses its operands with immediate offsets.
+template <int S, int CS, int SS>
+QHD void acc_column(Acc96& acc, const uint32_t* cst, const uint32_t* smp, uint32_t count) {
+#pragma unroll 8
+  for (uint32_t n = 0; n < count; n++) {
+    acc_mad(acc, *cst, *smp);
+    cst += CS;
+    smp += SS * S;
+  }
+}
+
 // W (k + 1 limbs, strided) >= r (k limbs)?
 template <int S>
 QHD bool limbs_ge_r(const uint32_t* W, const uint32_t* r, uint32_t k) {
@@ -285,7 +298,7 @@ QHD_NOINLINE void diagk_barrett(const DiagKConst& c, const uint32_t* A, uint32_t
   for (uint32_t col = k - 1; col <= 2 * k + 1; col++) {
     const uint32_t i0 = col > k + 1 ? col - (k + 1) : 0;
     const uint32_t i1 = col < k ? col : k;
-    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, QB_L(A, k - 1 + i), c.mu[col - i]);
+    if (i0 <= i1) acc_column<S, -1, 1>(acc, c.mu + (col - i0), &QB_L(A, k - 1 + i0), i1 - i0 + 1);
     const uint32_t limb = acc_pop(acc);
     if (col >= k + 1) QB_L(Q, col - (k + 1)) = limb;
   }
@@ -295,7 +308,7 @@ QHD_NOINLINE void diagk_barrett(const DiagKConst& c, const uint32_t* A, uint32_t
   uint32_t borrow = 0;
   for (uint32_t col = 0; col <= k; col++) {
     const uint32_t i1 = col < k - 1 ? col : k - 1;
-    for (uint32_t i = 0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(Q, col - i));
+    acc_column<S, 1, -1>(acc, c.r, &QB_L(Q, col), i1 + 1);
     const uint32_t limb = acc_pop(acc);
     const uint64_t v = (uint64_t)QB_L(A, col) - limb - borrow;
     QB_L(W, col) = (uint32_t)v;
@@ -444,7 +457,7 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pi
   for (uint32_t col = 0; col < ncol; col++) {
     const uint32_t i0 = col >= c.wj ? col - c.wj + 1 : 0;
     const uint32_t i1 = col < k - 1 ? col : k - 1;
-    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.r[i], QB_L(j, col - i));
+    if (i0 <= i1) acc_column<S, 1, -1>(acc, c.r + i0, &QB_L(j, col - i0), i1 - i0 + 1);
     const uint32_t limb = acc_pop(acc);
     if (col + 1 == cs) below = limb;
     if (col >= cs) QB_L(Sq, col - cs) = limb;
@@ -502,7 +515,7 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pi
   for (uint32_t col = 0; col < 2 * k; col++) {
     const uint32_t i0 = col >= k ? col - k + 1 : 0;
     const uint32_t i1 = col < k - 1 ? col : k - 1;
-    for (uint32_t i = i0; i <= i1; i++) acc_mad(acc, c.d[i], QB_L(Sq, col - i));
+    if (i0 <= i1) acc_column<S, 1, -1>(acc, c.d + i0, &QB_L(Sq, col - i0), i1 - i0 + 1);
     QB_L(A, col) = acc_pop(acc);
   }
   diagk_barrett<S>(c, A, Q, W);
