@@ -575,10 +575,10 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
            "roofline": {"bound": "integer issue", "imad_per_sample": mads,
                         "achieved": mads * n / ms * 1e3 / 1e12, "unit": "T multiply-add/s",
                         "kernel": "k_diagk",
-                        "limiter": "load/store pipe: two loads (one limb from L1, one from shared "
-                                   "memory) per 32x32-bit multiply-add, LSU 64 % busy, issue slots 59 % "
-                                   "active, ~4 thread instructions per multiply-add in the products "
-                                   "(profiles/r01_diagk_ncu_full.txt); DRAM 7 %"}}
+                        "limiter": "instruction issue and fetch: ~3.2 thread instructions per multiply-add "
+                                   "in the four-column products, issue slots 47 % active, stall_no_instruction "
+                                   "2.9 (120 KB of code), 28 warps/SM; LSU 24 %, DRAM 7 % "
+                                   "(profiles/r01_diagk_ncu_full.txt)"}}
     t0 = time.perf_counter()
     ks, x, dl, st = S.sample(J, eta, piv, delta_bound, want_k=False)
     t1 = time.perf_counter()

@@ -19,8 +19,7 @@ ctx = qb.Context(0)
 for g in GOLD:
     S = qb.DiagonalKSampler(qb.Diagonal_Parameters(g.m, g.sigma, 0, g.d, g.r, eta_bound=25, l=g.l), ctx)
     check_gold(g, S)
-    n = 6
-    rows = (len(g.eta) // n) * n
+    n, rows = 6, 48   # the random rows (the edge rows behind them include j < |eta| 2^(m+sigma) / r)
     S.tau_estimate(n, rows // n, g.J[:rows], g.eta[:rows], np.minimum(g.pivot[:rows], np.longdouble(0.9)), 50, 25)
     S.approx_h(np.array([[0.25, 0.0], [3.5, 1e-17], [-7.25, 0.0]]))
     S.close()
