@@ -27,7 +27,7 @@ total = sum(tot.values())
 print("ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 2 --warmup 1 --no-cpu-baseline")
 print("(per-launch times under ncu are serialised and cold-cache: compare SHARES, not absolutes; k_dfma_peak is the FP64")
 print("peak microbenchmark, the k_text_* launches are the `text` section and k_seg_build / k_sample / k_tau_reduce the")
-print("`tau` section: all outside the timed step)\n")
+print("`tau` section, k_diagk* the `diagk` section: all outside the timed step)\n")
 print(f"{'kernel':60s} {'launches':>8s} {'total_us':>10s} {'share':>7s}")
 for n in sorted(tot, key=lambda k: -tot[k]):
     print(f"{n[:60]:60s} {cnt[n]:8d} {tot[n]:10.1f} {100 * tot[n] / total:6.2f}%")
