@@ -20,8 +20,9 @@
 //     sample_j_from_diagonal_alpha_r (src/sample.cpp:352-410) with GMP, step by step the same
 //     calls on the same Random_State -- except that what these two functions recompute for
 //     every sample is kept: the integer bounds round(2^|log alpha|) of a region (two mpfr_exp2
-//     at 3 m bits per sample in the reference) and (r / 2^kappa_r)^-1 mod 2^(m + sigma) (one
-//     mpz_invert per sample). Same integers, same draws, same j.
+//     at 3 m bits per sample in the reference; here one mpfr_exp2 per distinct fractional part
+//     of log alpha, see bound_of()) and (r / 2^kappa_r)^-1 mod 2^(m + sigma) (one mpz_invert per
+//     sample). Same integers, same draws, same j.
 //   * k and alpha_phi given (j, eta, pivot) -- sample_k_from_diagonal_j_eta_pivot
 //     (src/sample.cpp:412-646), the part that evaluates diagonal_probability_approx_h at
 //     2 (m + sigma) bits -- come from the GPU for all n samples in one call.
@@ -95,7 +96,7 @@ void print_stats() {
   if (g_stats.on && g_stats.calls)
     fprintf(stderr,
             "qunundrum_b200 diagonal tau drop-in: %lu estimates, %lu samples; %.3f s drawing (j, eta) on the host "
-            "(%lu bounds 2^|log alpha| computed), %.3f s inside qb200_diagk_sample, %.3f s summing; %lu replays\n",
+            "(%lu mpfr_exp2 calls), %.3f s inside qb200_diagk_sample, %.3f s summing; %lu replays\n",
             g_stats.calls, g_stats.samples, g_stats.s_draw, g_stats.bounds, g_stats.s_abi, g_stats.s_sum,
             g_stats.replays);
 }
@@ -141,6 +142,10 @@ struct Setup {
     mpz_t z;
   };
   std::map<std::pair<double, uint32_t>, Z*> bounds;
+  struct F {
+    mpfr_t v;
+  };
+  std::map<double, F*> exp2_frac;  // 2^f, f in [0, 1), at 3 (m + sigma + 2) + 128 bits
 } g;
 
 void setup_clear() {
@@ -160,6 +165,11 @@ void setup_clear() {
     delete e.second;
   }
   g.bounds.clear();
+  for (auto& e : g.exp2_frac) {
+    mpfr_clear(e.second->v);
+    delete e.second;
+  }
+  g.exp2_frac.clear();
   if (g.sampler) qb200_diagk_destroy(g.sampler);
   g.sampler = NULL;
   g.valid = false;
@@ -206,23 +216,59 @@ void setup_for(const Diagonal_Parameters* p) {
 }
 
 // round(2^|log alpha|) as sample_alpha_from_region computes it (src/sample.cpp:97-124:
-// mpfr_set_d, mpfr_exp2, mpfr_round at `precision` bits, mpfr_get_z), kept per (value, precision):
-// the upper bound of one region is the lower bound of the next.
+// mpfr_set_d, mpfr_exp2, mpfr_round at `precision` = 3 ceil(|max log alpha|) bits, mpfr_get_z),
+// kept per (value, precision): the upper bound of one region is the lower bound of the next.
+//
+// The reference pays one mpfr_exp2 at ~3 m bits per bound (0.17 ms at m = 2048). Here
+// |log alpha| = e + f with an integer e and f = i / dimension: 2^f is computed once per f at a
+// precision above every precision the reference uses, and the bound is round(2^e 2^f). The two
+// agree whenever 2^(e+f) is farther from a half-integer than the reference's own rounding error
+// 2^(e + 1 - precision) <= 2^(-2 e - 2) -- which is checked: a value within 2^-64 of a
+// half-integer (never seen) is computed the reference's way.
 const mpz_t* bound_of(double abs_log_alpha, uint32_t precision) {
   const std::pair<double, uint32_t> key(abs_log_alpha, precision);
   auto it = g.bounds.find(key);
   if (it != g.bounds.end()) return &it->second->z;
   Setup::Z* b = new Setup::Z;
   mpz_init(b->z);
-  mpfr_t x;
-  mpfr_init2(x, precision);
-  mpfr_set_d(x, abs_log_alpha, MPFR_RNDN);
-  mpfr_exp2(x, x, MPFR_RNDN);
-  mpfr_round(x, x);
-  mpfr_get_z(b->z, x, MPFR_RNDN);
-  mpfr_clear(x);
+  const double e = floor(abs_log_alpha), f = abs_log_alpha - e;  // exact: dimension is a power of two
+  const uint32_t wide = 3 * (g.m + g.sigma + 2) + 128;
+  bool done = false;
+  if (precision + 64 <= wide && e >= 64 && e + 1 <= (double)(precision / 3 + 1)) {
+    Setup::F*& pf = g.exp2_frac[f];
+    if (!pf) {
+      pf = new Setup::F;
+      mpfr_init2(pf->v, wide);
+      mpfr_set_d(pf->v, f, MPFR_RNDN);
+      mpfr_exp2(pf->v, pf->v, MPFR_RNDN);
+      g_stats.bounds++;
+    }
+    mpfr_t y, t;
+    mpfr_init2(y, wide);
+    mpfr_init2(t, wide);
+    mpfr_mul_2si(y, pf->v, (long)e, MPFR_RNDN);  // exact
+    mpfr_floor(t, y);
+    mpfr_sub(t, y, t, MPFR_RNDN);                // fractional part, exact
+    mpfr_sub_d(t, t, 0.5, MPFR_RNDN);
+    if (mpfr_cmp_d(t, 5.421010862427522e-20) > 0 || mpfr_cmp_d(t, -5.421010862427522e-20) < 0) {  // 2^-64
+      mpfr_round(y, y);
+      mpfr_get_z(b->z, y, MPFR_RNDN);
+      done = true;
+    }
+    mpfr_clear(y);
+    mpfr_clear(t);
+  }
+  if (!done) {
+    mpfr_t x;
+    mpfr_init2(x, precision);
+    mpfr_set_d(x, abs_log_alpha, MPFR_RNDN);
+    mpfr_exp2(x, x, MPFR_RNDN);
+    mpfr_round(x, x);
+    mpfr_get_z(b->z, x, MPFR_RNDN);
+    mpfr_clear(x);
+    g_stats.bounds++;
+  }
   g.bounds[key] = b;
-  g_stats.bounds++;
   return &b->z;
 }
 
