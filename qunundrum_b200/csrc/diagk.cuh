@@ -279,11 +279,15 @@ QHD void acc_terms(Acc96& acc, const uint32_t* U, const uint32_t* V, uint32_t c,
 // and the next a needs the same window of V moved down by one -- so one pass over the common
 // range of a loads U[a] and ONE new limb of V per step and feeds four accumulators (two loads per
 // four multiply-adds; the ragged ends of the four ranges, at most three terms each, are added
-// term by term). Inlined at its four call sites: as a separate function (the accumulator passed
-// through memory) the kernel measured 3.35 ms against 2.46 ms.
+// term by term). The accumulator travels by value (registers), also when the routine is compiled
+// as a separate function (QB_MULCOL_ATTR).
+#ifndef QB_MULCOL_ATTR
+#define QB_MULCOL_ATTR QHD
+#endif
 template <int SU, int SV, int SO>
-QHD void mul_columns(const uint32_t* U, uint32_t nu, const uint32_t* V, uint32_t nv, uint32_t first,
-                     uint32_t last, uint32_t store_from, uint32_t* out, Acc96& acc) {
+QB_MULCOL_ATTR Acc96 mul_columns(const uint32_t* __restrict__ U, uint32_t nu, const uint32_t* __restrict__ V,
+                                 uint32_t nv, uint32_t first, uint32_t last, uint32_t store_from,
+                                 uint32_t* __restrict__ out, Acc96 acc) {
 #define QB_LO(c) ((c) >= nv ? (c) - nv + 1 : 0u)
 #define QB_HI(c) ((c) < nu ? (c) : nu - 1)
 #define QB_EMIT(c, limb)                                                        \
@@ -350,6 +354,7 @@ QHD void mul_columns(const uint32_t* U, uint32_t nu, const uint32_t* V, uint32_t
 #undef QB_LO
 #undef QB_HI
 #undef QB_EMIT
+  return acc;
 }
 
 // W (k + 1 limbs, strided) >= r (k limbs)?
@@ -383,11 +388,11 @@ QHD_NOINLINE void diagk_barrett(const DiagKConst& c, const uint32_t* A, uint32_t
   Acc96 acc;
   acc_zero(acc);
   // q2 = q1 mu with q1 = A[k - 1, 2k): k + 1 limbs, mu: k + 2 limbs; columns k + 1 .. 2k + 2 are Q
-  mul_columns<S, 1, S>(&QB_L(A, k - 1), k + 1, c.mu, k + 2, k - 1, 2 * k + 1, k + 1, Q, acc);
+  acc = mul_columns<S, 1, S>(&QB_L(A, k - 1), k + 1, c.mu, k + 2, k - 1, 2 * k + 1, k + 1, Q, acc);
   QB_L(Q, k + 1) = acc_low(acc);
   // W = (x - Q r) mod 2^(32 (k + 1))
   acc_zero(acc);
-  mul_columns<1, S, S>(c.r, k, Q, k + 2, 0, k, 0, W, acc);
+  acc = mul_columns<1, S, S>(c.r, k, Q, k + 2, 0, k, 0, W, acc);
   uint32_t borrow = 0;
   for (uint32_t col = 0; col <= k; col++) {
     const uint64_t v = (uint64_t)QB_L(A, col) - QB_L(W, col) - borrow;
@@ -534,7 +539,7 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pi
   acc_zero(acc);
   // Z = r j: the columns from cs - 1 on go to A (free here), then to Sq
   const uint32_t ncol = k + c.wj;
-  mul_columns<1, S, S>(c.r, k, j, c.wj, 0, ncol - 1, cs - 1, A, acc);
+  acc = mul_columns<1, S, S>(c.r, k, j, c.wj, 0, ncol - 1, cs - 1, A, acc);
   const uint32_t below = QB_L(A, 0);  // column cs - 1
   for (uint32_t i = 0; i + cs < ncol; i++) QB_L(Sq, i) = QB_L(A, i + 1);
   const uint32_t ns = ncol - cs;  // <= k + 1 limbs hold Z >> (32 cs)
@@ -587,7 +592,7 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pi
   }
   // ---- w = d s mod r ----
   acc_zero(acc);
-  mul_columns<1, S, S>(c.d, k, Sq, k, 0, 2 * k - 1, 0, A, acc);
+  acc = mul_columns<1, S, S>(c.d, k, Sq, k, 0, 2 * k - 1, 0, A, acc);
   diagk_barrett<S>(c, A, Q, W);
   // ---- (Qv, w2) = divmod(2^l w, r), at most 32 k bits of the shift at a time ----
   const uint32_t chunk = 32 * k;
