@@ -559,6 +559,21 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
         times.append(e0.elapsed_time(e1))
     launches = (ctx.launch_count - launches0) // 6
     ms = float(np.median(times[3:]))
+    # the same with the reference's default bound (BOUND_DELTA = 10^6, src/diagonal_distribution.h:56):
+    # pivots near 1 then walk up to 2 10^6 + 1 steps
+    times_default = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        S.sample_device(n, dJ.data_ptr(), dE.data_ptr(), dP.data_ptr(), 1000000, dK.data_ptr(),
+                        dO.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+        times_default.append(e0.elapsed_time(e1))
+    out_default = dO.cpu().numpy()
+    S.sample_device(n, dJ.data_ptr(), dE.data_ptr(), dP.data_ptr(), delta_bound, dK.data_ptr(),
+                    dO.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
     out = dO.cpu().numpy()
     status = out[:, 3].view(np.int64) & 0xffffffff
     delta = out[:, 2].view(np.int64)
@@ -572,6 +587,10 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
            "samples_per_call": n, "value": n / ms * 1e3, "unit": "samples/s", "ms": ms,
            "ok_fraction": float((status == 0).mean()), "mean_abs_delta": float(np.abs(delta).mean()),
            "max_abs_delta": int(np.abs(delta).max()), "gpu_launches": int(launches),
+           "default_delta_bound": {"delta_bound": 1000000, "ms": float(np.median(times_default)),
+                                   "value": n / float(np.median(times_default)) * 1e3,
+                                   "max_abs_delta": int(np.abs(out_default[:, 2].view(np.int64)).max()),
+                                   "ok_fraction": float(((out_default[:, 3].view(np.int64) & 0xffffffff) == 0).mean())},
            "roofline": {"bound": "integer issue", "imad_per_sample": mads,
                         "achieved": mads * n / ms * 1e3 / 1e12, "unit": "T multiply-add/s",
                         "kernel": "k_diagk",

@@ -441,80 +441,97 @@ QHD dd diagk_walk_x(uint32_t l, dd t, int64_t delta) {
   if (l >= 62) return dd_add_d(t, (double)delta);
   const int64_t M = (int64_t)1 << l;
   const double two_l = (double)M;
-  int64_t dm = ((delta % M) + M) % M;
-  if (dm >= M / 2) dm -= M;  // |dm| <= 2^32 or < 2^53: exact as a double
+  int64_t dm = delta;
+  if (delta >= M / 2 || delta < -(M / 2)) {
+    dm = ((delta % M) + M) % M;
+    if (dm >= M / 2) dm -= M;  // |dm| <= 2^32 or < 2^53: exact as a double
+  }
   dd x = dd_add_d(t, (double)dm);
   if (x.hi >= 0.5 * two_l) x = dd_add_d(x, -two_l);
   if (x.hi < -0.5 * two_l) x = dd_add_d(x, two_l);
   return x;
 }
 
-// The walk of src/sample.cpp:539-604 on x = t + delta: pivot -= h(x) for delta = 0, 1, -1, 2, ...
-// until the pivot is used up.
-//
-// Only the step at which that happens is an output, not the pivot. A first pass therefore runs in
-// plain doubles: after N steps it differs from the reference's sequence of long double
-// subtractions by less than (N + 16) 2^-51 (h to a few units in the last place of a double, sum
-// of the h at most ~1; N roundings of a number <= 1; the reference's own N roundings at 2^-64),
-// so a pivot that passes below -band at a step while it was above +band at all earlier steps
-// stops at that step in the reference as well. A pivot inside the band at some step (probability
-// ~1e-12 per step) sends the sample through the exact walk: h in double-double, rounded to the
-// x87 format, subtracted with the x87 rounding -- from the start. force_exact: the exact walk
-// only (tests).
-QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int force_exact, int64_t* delta_out,
-                   dd* x_out) {
-  const dd st = sinpi_acc(t);
-  const dd S = dd_mul(st, st);
-  if (!force_exact) {
-    const dd pd = x87_to_dd(pivot);
-    double p = pd.hi + pd.lo;
-    const double Sd = S.hi;
-    const double two_l = l < 110 ? ldexp(1.0, (int)l) : 0.0, inv_two_l = l < 110 ? ldexp(1.0, -(int)l) : 0.0;
-    uint64_t steps = 0;
-    bool undecided = false;
-    for (uint64_t da = 0; da <= delta_bound && !undecided; da++) {
-      for (int sg = 1; sg >= -1; sg -= 2) {
-        if (da == 0 && sg < 0) continue;
-        if (++steps > QB_DIAGK_MAX_STEPS) return QB_DIAGK_GAVE_UP;
-        const int64_t delta = sg > 0 ? (int64_t)da : -(int64_t)da;
-        const dd x = diagk_walk_x(l, t, delta);
-        double h = 1.0;
-        if (x.hi != 0.0) {
-          const double D = l >= 110 ? QB_PI_HI * x.hi : two_l * sinpi_dd(dd_mul_pow2(x, inv_two_l));
-          h = Sd / (D * D);
-        }
-        p -= h;
-        const double band = (double)(steps + 16) * 4.440892098500626e-16;  // 2^-51
-        if (p < -band) {
-          *delta_out = delta;
-          *x_out = x;
-          return QB_DIAGK_OK;
-        }
-        if (p <= band) {
-          undecided = true;
-          break;
-        }
-      }
+// Step idx of the walk: delta = 0, +1, -1, +2, -2, ... (src/sample.cpp:539-559); the last one is
+// idx = 2 delta_bound.
+QHD int64_t diagk_step_delta(uint64_t idx) {
+  const int64_t da = (int64_t)((idx + 1) >> 1);
+  return (idx & 1) ? da : -da;
+}
+
+// h in plain doubles (a few units in the last place): Sd = sin^2(pi t), two_l = 2^l and
+// inv_two_l = 2^-l for l < 110.
+QHD double diagk_quick_h(uint32_t l, double two_l, double inv_two_l, double Sd, dd x) {
+  if (x.hi == 0.0) return 1.0;
+  double D;
+  if (l >= 110) {
+    D = QB_PI_HI * x.hi;
+  } else {
+    const double y = x.hi * inv_two_l;
+    if (fabs(y) < 1.220703125e-4) {  // 2^-13: sin(e) / e = 1 - e^2/6 (1 - e^2/20) to 1e-24
+      const double e = QB_PI_HI * y, z = e * e;
+      D = QB_PI_HI * x.hi * (1.0 - z * (1.0 / 6.0) * (1.0 - z * 0.05));
+    } else {
+      D = two_l * sinpi_dd(dd_mul_pow2(x, inv_two_l));
     }
-    if (!undecided) {  // above the band after the last step: out of bounds in the reference as well
+  }
+  return Sd / (D * D);
+}
+
+// State of the pass in doubles: the pivot after the steps before idx (accumulated as an unevaluated
+// sum of two doubles, so that the additions themselves do not contribute to the error).
+struct DiagKQuick {
+  dd p;
+  uint64_t idx;
+};
+// The error band after N steps: 2^-47 for the h (each to ~8 units in the last place of a double,
+// their sum at most 2 because the walk stops once it reaches the pivot <= 1) and the partial sums
+// inside a warp step, plus N 2^-63 for the reference's own N roundings to 64 bits of a number <= 1.
+QHD double diagk_band(uint64_t steps) { return 7.105427357601002e-15 + (double)steps * 1.0842021724855044e-19; }
+#define QB_DIAGK_CONTINUE 100   // internal: not decided before idx_end
+#define QB_DIAGK_UNDECIDED 101  // internal: the pivot ended inside the error band: exact walk
+
+// Steps q->idx .. idx_end - 1 of the pass in doubles (see diagk_walk). QB_DIAGK_OK (with delta and
+// x), QB_DIAGK_OUT_OF_BOUNDS, QB_DIAGK_GAVE_UP, QB_DIAGK_UNDECIDED or QB_DIAGK_CONTINUE.
+QHD int diagk_quick_steps(uint32_t l, dd t, double Sd, uint64_t delta_bound, uint64_t idx_end, DiagKQuick* q,
+                          int64_t* delta_out, dd* x_out) {
+  const double two_l = l < 110 ? ldexp(1.0, (int)l) : 0.0, inv_two_l = l < 110 ? ldexp(1.0, -(int)l) : 0.0;
+  const uint64_t last = 2 * delta_bound;
+  while (q->idx < idx_end) {
+    if (q->idx > last) {  // above the band after the last step: out of bounds in the reference as well
       *delta_out = 0;
       *x_out = make_dd(0.0, 0.0);
       return QB_DIAGK_OUT_OF_BOUNDS;
     }
+    if (q->idx + 1 > QB_DIAGK_MAX_STEPS) return QB_DIAGK_GAVE_UP;
+    const int64_t delta = diagk_step_delta(q->idx);
+    const dd x = diagk_walk_x(l, t, delta);
+    q->p = dd_add_d(q->p, -diagk_quick_h(l, two_l, inv_two_l, Sd, x));
+    const double pv = q->p.hi + q->p.lo, band = diagk_band(q->idx + 1);
+    if (pv < -band) {
+      *delta_out = delta;
+      *x_out = x;
+      return QB_DIAGK_OK;
+    }
+    if (pv <= band) return QB_DIAGK_UNDECIDED;
+    q->idx++;
   }
-  uint64_t steps = 0;
-  for (uint64_t da = 0; da <= delta_bound; da++) {
-    for (int sg = 1; sg >= -1; sg -= 2) {
-      if (da == 0 && sg < 0) continue;
-      if (++steps > QB_DIAGK_MAX_STEPS) return QB_DIAGK_GAVE_UP;
-      const int64_t delta = sg > 0 ? (int64_t)da : -(int64_t)da;
-      const dd x = diagk_walk_x(l, t, delta);
-      pivot = x87_add(pivot, x87_neg(x87_from_dd(diagk_h(l, S, x))));
-      if (x87_nonpositive(pivot)) {
-        *delta_out = delta;
-        *x_out = x;
-        return QB_DIAGK_OK;
-      }
+  return QB_DIAGK_CONTINUE;
+}
+
+// The exact walk: h in double-double, rounded to the x87 format, subtracted with the x87 rounding
+// (pivot -= mpfr_get_ld(h), src/sample.cpp:594).
+QHD int diagk_walk_exact(uint32_t l, dd t, dd S, X87 pivot, uint64_t delta_bound, int64_t* delta_out, dd* x_out) {
+  const uint64_t last = 2 * delta_bound;
+  for (uint64_t idx = 0; idx <= last; idx++) {
+    if (idx + 1 > QB_DIAGK_MAX_STEPS) return QB_DIAGK_GAVE_UP;
+    const int64_t delta = diagk_step_delta(idx);
+    const dd x = diagk_walk_x(l, t, delta);
+    pivot = x87_add(pivot, x87_neg(x87_from_dd(diagk_h(l, S, x))));
+    if (x87_nonpositive(pivot)) {
+      *delta_out = delta;
+      *x_out = x;
+      return QB_DIAGK_OK;
     }
   }
   *delta_out = 0;
@@ -522,11 +539,43 @@ QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int force_
   return QB_DIAGK_OUT_OF_BOUNDS;
 }
 
-// One sample. j: c.wj limbs (j < 2^n); scratch: diagk_scratch_limbs(k) words; k_out: c.wl limbs
-// (may be null); all three with stride S. x_out = alpha_phi / 2^(m + sigma - l).
+// The walk of src/sample.cpp:539-604 on x = t + delta: pivot -= h(x) for delta = 0, 1, -1, 2, ...
+// until the pivot is used up.
+//
+// Only the step at which that happens is an output, not the pivot. A first pass therefore runs in
+// doubles (h in plain doubles, the pivot as a compensated sum): after N steps it differs from the
+// reference's sequence of long double subtractions by less than diagk_band(N), so a pivot that
+// passes below -band at a step while it was above +band at all earlier steps stops at that step
+// in the reference as well. A pivot inside the band at some step (probability ~1e-4 for a walk of
+// 10^5 steps, far less for short ones) sends the sample through the exact walk: h in double-double, rounded to the
+// x87 format, subtracted with the x87 rounding -- from the start. force_exact: the exact walk
+// only (tests). (The kernel runs the first steps of the pass in doubles per thread and the rest
+// thirty-two steps at a time across the warp, kernels_diagk.cuh: any order of summation stays
+// inside the same band.)
+QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int force_exact, int64_t* delta_out,
+                   dd* x_out) {
+  const dd st = sinpi_acc(t);
+  const dd S = dd_mul(st, st);
+  if (!force_exact) {
+    DiagKQuick q;
+    q.p = x87_to_dd(pivot);  // exact
+    q.idx = 0;
+    const int status = diagk_quick_steps(l, t, S.hi, delta_bound, ~(uint64_t)0, &q, delta_out, x_out);
+    if (status != QB_DIAGK_UNDECIDED) return status;
+  }
+  return diagk_walk_exact(l, t, S, pivot, delta_bound, delta_out, x_out);
+}
+
+struct DiagKFraction {
+  dd t;        // w2 / r - c
+  bool cflag;  // c = [2 w2 >= r]
+  bool whole;  // q + eta < 0 and d |q + eta| >= r: the unreduced phi is negative
+};
+
+// The integer part of one sample: k_out = Qv (if wanted), f = (t, c, whole).
 template <int S>
-QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pivot, uint64_t delta_bound,
-                     uint32_t* scratch, uint32_t* k_out, dd* x_out, int64_t* delta_out) {
+QHD void diagk_fraction(const DiagKConst& c, const uint32_t* j, int32_t eta, uint32_t* scratch, uint32_t* k_out,
+                        DiagKFraction* f) {
   const uint32_t k = c.k;
   uint32_t* A = scratch;                              // 2k + 2
   uint32_t* Q = A + (size_t)(2 * k + 2) * (size_t)S;  // k + 3
@@ -647,10 +696,15 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pi
       if (cflag) t = dd_neg(t);
     }
   }
-  // ---- the walk ----
-  int64_t delta = 0;
-  dd x = make_dd(0.0, 0.0);
-  const int status = diagk_walk(c.l, t, pivot, delta_bound, c.force_exact, &delta, &x);
+  f->t = t;
+  f->cflag = cflag;
+  f->whole = whole;
+}
+
+// After the walk: k = (k0 + delta) mod 2^l from Qv in k_out, the status, x.
+template <int S>
+QHD int diagk_finish(const DiagKConst& c, const DiagKFraction& f, int status, int64_t delta, dd x, uint32_t* k_out,
+                     dd* x_out, int64_t* delta_out) {
   if (status != QB_DIAGK_OK) {
     if (k_out)
       for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, i) = 0;
@@ -662,10 +716,10 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pi
   // d |q + eta| >= r the unreduced phi is negative and a positive residue is not folded back
   // (j < |eta| 2^(m+sigma) / r: never drawn in practice). 2^l may not be a double: reported as
   // a status, the subtraction is the caller's.
-  const int ok_status = (whole && x.hi > 0.0) ? QB_DIAGK_OK_NEGATIVE_PHI : QB_DIAGK_OK;
+  const int ok_status = (f.whole && x.hi > 0.0) ? QB_DIAGK_OK_NEGATIVE_PHI : QB_DIAGK_OK;
   if (k_out) {
     // k = (-(Qv + c) + delta) mod 2^l = -(Qv + c - delta) mod 2^l
-    int64_t cy = (int64_t)(cflag ? 1 : 0) - delta;
+    int64_t cy = (int64_t)(f.cflag ? 1 : 0) - delta;
     for (uint32_t i = 0; i < c.wl; i++) {
       const int64_t v = (int64_t)QB_L(k_out, i) + cy;
       QB_L(k_out, i) = (uint32_t)v;
@@ -682,6 +736,19 @@ QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pi
   *x_out = x;
   *delta_out = delta;
   return ok_status;
+}
+
+// One sample. j: c.wj limbs (j < 2^n); scratch: diagk_scratch_limbs(k) words; k_out: c.wl limbs
+// (may be null); all three with stride S. x_out = alpha_phi / 2^(m + sigma - l).
+template <int S>
+QHD int diagk_sample(const DiagKConst& c, const uint32_t* j, int32_t eta, X87 pivot, uint64_t delta_bound,
+                     uint32_t* scratch, uint32_t* k_out, dd* x_out, int64_t* delta_out) {
+  DiagKFraction f;
+  diagk_fraction<S>(c, j, eta, scratch, k_out, &f);
+  int64_t delta = 0;
+  dd x = make_dd(0.0, 0.0);
+  const int status = diagk_walk(c.l, f.t, pivot, delta_bound, c.force_exact, &delta, &x);
+  return diagk_finish<S>(c, f, status, delta, x, k_out, x_out, delta_out);
 }
 
 }  // namespace qb200

@@ -6,8 +6,11 @@
 //                    [i * 128 + t]) so that the threads of a warp, which all work on the same limb
 //                    index at the same time, read consecutive words at a compile-time stride.
 //   k_diagk          one thread per sample: r j, d (q + eta) mod r, divmod(2^l w, r) in 32-bit
-//                    limbs (about 5 k^2 multiply-adds, k = limbs of r), then the walk over delta
-//                    in double-double. r, d and the Barrett reciprocal are staged in shared
+//                    limbs (about 5 k^2 multiply-adds, k = limbs of r), then the walk over delta:
+//                    the first steps per thread, the rest of a long walk (a pivot near 1 takes
+//                    thousands of steps, up to 2 delta_bound + 1) thirty-two steps at a time
+//                    across the warp, so that one such sample does not hold its CTA for
+//                    milliseconds. r, d and the Barrett reciprocal are staged in shared
 //                    memory (every thread reads the same limb: broadcast). Integer-pipe bound.
 //   k_diagk_scatter  k of a chunk back to row-per-sample.
 //   k_diagk_tau      one thread per estimate: sum of (alpha_phi / 2^(m+sigma-l))^2 in sample
@@ -53,6 +56,53 @@ struct DiagKOut {
   int pad;
 };
 
+// Steps of the pass in doubles that every thread takes on its own before the warp walks together.
+#define QB_DIAGK_LOCAL_STEPS 7
+
+// The rest of one lane's pass in doubles, thirty-two steps at a time across the warp: lane i
+// evaluates h at step idx0 + i, an inclusive scan gives the pivot after every step, the first lane
+// at or below the band decides. Called by all 32 lanes with the walking lane's state broadcast.
+// Returns the outcome (QB_DIAGK_OK / _OUT_OF_BOUNDS / _GAVE_UP / _UNDECIDED) with delta and x.
+__device__ __forceinline__ int diagk_warp_walk(uint32_t l, dd t, double Sd, dd p, uint64_t idx0,
+                                               uint64_t delta_bound, int64_t* delta_out, dd* x_out) {
+  const unsigned full = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const double two_l = l < 110 ? ldexp(1.0, (int)l) : 0.0, inv_two_l = l < 110 ? ldexp(1.0, -(int)l) : 0.0;
+  const uint64_t last = 2 * delta_bound;
+  for (;;) {
+    const uint64_t idx = idx0 + lane;
+    const bool valid = idx <= last && idx + 1 <= QB_DIAGK_MAX_STEPS;
+    const int64_t delta = diagk_step_delta(idx);
+    const dd x = diagk_walk_x(l, t, delta);
+    double s = valid ? diagk_quick_h(l, two_l, inv_two_l, Sd, x) : 0.0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const double v = __shfl_up_sync(full, s, off);
+      if (lane >= (unsigned)off) s += v;
+    }
+    const dd pld = dd_add_d(p, -s);
+    const double pl = pld.hi + pld.lo;
+    const double band = diagk_band(idx + 1);
+    const unsigned hits = __ballot_sync(full, valid && pl <= band);
+    const unsigned invalid = __ballot_sync(full, !valid);
+    if (hits) {
+      const int f = __ffs(hits) - 1;
+      const double pf = __shfl_sync(full, pl, f), bf = __shfl_sync(full, band, f);
+      *delta_out = (int64_t)__shfl_sync(full, (long long)delta, f);
+      *x_out = make_dd(__shfl_sync(full, x.hi, f), __shfl_sync(full, x.lo, f));
+      return pf < -bf ? QB_DIAGK_OK : QB_DIAGK_UNDECIDED;
+    }
+    if (invalid) {
+      const uint64_t first_invalid = idx0 + (uint64_t)(__ffs(invalid) - 1);
+      *delta_out = 0;
+      *x_out = make_dd(0.0, 0.0);
+      return first_invalid > last ? QB_DIAGK_OUT_OF_BOUNDS : QB_DIAGK_GAVE_UP;
+    }
+    p = make_dd(__shfl_sync(full, pld.hi, 31), __shfl_sync(full, pld.lo, 31));
+    idx0 += 32;
+  }
+}
+
 __global__ void __launch_bounds__(QB_DIAGK_CTA) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
                                                 const int32_t* __restrict__ eta,
                                                 const RawX87* __restrict__ pivot,
@@ -71,30 +121,77 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA) k_diagk(DiagKConst c, const uint
   c.d = sh + k;
   c.mu = sh + 2 * k;
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= B) return;
-  bool ok = true;
-  const X87 p = x87_load(pivot + g, &ok);
+  const size_t tile = (size_t)blockIdx.x * QB_DIAGK_CTA;
+  uint32_t* k_out = kT ? kT + tile * c.wl + threadIdx.x : nullptr;
+  // every lane stays until the warp has walked together: `live` marks the ones with a sample
+  bool live = g < B;
+  X87 p = x87_zero();
+  if (live) {
+    bool ok = true;
+    p = x87_load(pivot + g, &ok);
+    if (!ok || p.neg || (p.mant != 0 && (p.exp > 0 || (p.exp == 0 && p.mant != 0x8000000000000000ull)))) {
+      // the reference: critical("The pivot is out of bounds.") (src/sample.cpp:421-425)
+      DiagKOut o;
+      o.x_hi = o.x_lo = 0.0;
+      o.delta = 0;
+      o.status = -1;
+      o.pad = 0;
+      if (k_out)
+        for (uint32_t i = 0; i < c.wl; i++) k_out[(size_t)i * QB_DIAGK_CTA] = 0;
+      out[g] = o;
+      live = false;
+    }
+  }
+  DiagKFraction f;
+  f.t = make_dd(0.0, 0.0);
+  f.cflag = f.whole = false;
+  dd S = make_dd(0.0, 0.0);
+  int status = QB_DIAGK_OUT_OF_BOUNDS;
+  int64_t delta = 0;
+  dd x = make_dd(0.0, 0.0);
+  DiagKQuick q;
+  q.p = make_dd(0.0, 0.0);
+  q.idx = 0;
+  if (live) {
+    diagk_fraction<QB_DIAGK_CTA>(c, jT + tile * c.wj + threadIdx.x, eta[g],
+                                 scratch + tile * diagk_scratch_limbs(k) + threadIdx.x, k_out, &f);
+    const dd st = sinpi_acc(f.t);
+    S = dd_mul(st, st);
+    if (c.force_exact) {
+      status = QB_DIAGK_UNDECIDED;
+    } else {
+      q.p = x87_to_dd(p);  // exact
+      status = diagk_quick_steps(c.l, f.t, S.hi, delta_bound, QB_DIAGK_LOCAL_STEPS, &q, &delta, &x);
+    }
+  }
+  // the lanes still walking, one after the other, with the whole warp
+  unsigned walking = __ballot_sync(0xffffffffu, live && status == QB_DIAGK_CONTINUE);
+  while (walking) {
+    const int L = __ffs(walking) - 1;
+    const dd tL = make_dd(__shfl_sync(0xffffffffu, f.t.hi, L), __shfl_sync(0xffffffffu, f.t.lo, L));
+    const double SL = __shfl_sync(0xffffffffu, S.hi, L);
+    const dd pL = make_dd(__shfl_sync(0xffffffffu, q.p.hi, L), __shfl_sync(0xffffffffu, q.p.lo, L));
+    const uint64_t iL = (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)q.idx, L);
+    int64_t dW;
+    dd xW;
+    const int sW = diagk_warp_walk(c.l, tL, SL, pL, iL, delta_bound, &dW, &xW);
+    if ((int)(threadIdx.x & 31u) == L) {
+      status = sW;
+      delta = dW;
+      x = xW;
+    }
+    walking &= walking - 1;
+  }
+  if (!live) return;
+  if (status == QB_DIAGK_UNDECIDED) status = diagk_walk_exact(c.l, f.t, S, p, delta_bound, &delta, &x);
   DiagKOut o;
   o.pad = 0;
-  if (!ok || p.neg || (p.mant != 0 && (p.exp > 0 || (p.exp == 0 && p.mant != 0x8000000000000000ull)))) {
-    // the reference: critical("The pivot is out of bounds.") (src/sample.cpp:421-425)
-    o.x_hi = o.x_lo = 0.0;
-    o.delta = 0;
-    o.status = -1;
-    if (kT)
-      for (uint32_t i = 0; i < c.wl; i++) kT[((size_t)blockIdx.x * c.wl + i) * QB_DIAGK_CTA + threadIdx.x] = 0;
-    out[g] = o;
-    return;
-  }
-  dd x;
-  int64_t delta;
-  const size_t tile = (size_t)blockIdx.x * QB_DIAGK_CTA;
-  o.status = diagk_sample<QB_DIAGK_CTA>(c, jT + tile * c.wj + threadIdx.x, eta[g], p, delta_bound,
-                                        scratch + tile * diagk_scratch_limbs(k) + threadIdx.x,
-                                        kT ? kT + tile * c.wl + threadIdx.x : nullptr, &x, &delta);
-  o.x_hi = x.hi;
-  o.x_lo = x.lo;
-  o.delta = (long long)delta;
+  dd xo;
+  int64_t dout;
+  o.status = diagk_finish<QB_DIAGK_CTA>(c, f, status, delta, x, k_out, &xo, &dout);
+  o.x_hi = xo.hi;
+  o.x_lo = xo.lo;
+  o.delta = (long long)dout;
   out[g] = o;
 }
 
