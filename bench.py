@@ -594,9 +594,9 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
            "roofline": {"bound": "integer issue", "imad_per_sample": mads,
                         "achieved": mads * n / ms * 1e3 / 1e12, "unit": "T multiply-add/s",
                         "kernel": "k_diagk",
-                        "limiter": "instruction issue and fetch: ~3.2 thread instructions per multiply-add "
-                                   "in the four-column products, issue slots 47 % active, stall_no_instruction "
-                                   "2.9 (120 KB of code), 28 warps/SM; LSU 24 %, DRAM 7 % "
+                        "limiter": "instruction issue: ~3.2 thread instructions per multiply-add in the "
+                                   "four-column products, issue slots 51 % active (dependent carry chains, L1 "
+                                   "latency, 24 warps/SM), LSU 28 %, DRAM 9 % "
                                    "(profiles/r01_diagk_ncu_full.txt)"}}
     t0 = time.perf_counter()
     ks, x, dl, st = S.sample(J, eta, piv, delta_bound, want_k=False)

@@ -269,6 +269,29 @@ def test_twin_matches_the_live_reference_on_fresh_seeds():
             assert abs((LD(x[i, 0]) + LD(x[i, 1])) - a) <= abs(a) * LD(2) ** -62
 
 
+@pytest.mark.parametrize("m,sigma,l", [(256, 4, 256), (128, 5, 20)])
+def test_twin_long_walks_decided_in_doubles_equal_the_exact_walk(m, sigma, l):
+    """Pivots next to 1 walk thousands of steps (for l = 20 around the whole ring of 2^20 values of
+    k): the pass in doubles with its error band must stop where the exact x87 walk stops."""
+    import random
+    prng = random.Random(m + l)
+    r = (1 << (m - 1)) + 1 + prng.randrange((1 << (m - 1)) - 1)
+    d = r // 2 + prng.randrange(r // 2)
+    n = 40
+    js = [prng.randrange(1 << (m + sigma)) for _ in range(n)]
+    etas = [prng.randrange(-25, 26) for _ in range(n)]
+    piv = np.array([LD(1) - LD(prng.random()) * LD(10.0 ** -prng.uniform(2.5, 4.5)) for _ in range(n)], dtype=LD)
+    S = hs.DiagK(m, sigma, l, d, r)
+    out = []
+    for exact in (False, True):
+        S.set_force_exact(exact)
+        out.append(S.sample(js, etas, piv, 30000))
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.abs(out[0][2]).max() > 2000 and (out[0][3] == 0).sum() >= n // 2
+
+
 def test_twin_refuses_bad_parameters():
     with pytest.raises(ValueError):
         hs.DiagK(128, 0, 64, 5, 3)          # d >= r
@@ -345,6 +368,29 @@ def test_gpu_equals_the_twin_on_a_batch(m, sigma, l, n, gpu_ctx):
     xb = x2[:, 0].astype(LD) + x2[:, 1].astype(LD)
     assert np.all(np.abs(xa - xb) <= np.abs(xb) * LD(2) ** -60)
     assert (st == 0).mean() > 0.9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,sigma,l", [(2048, 5, 2048), (128, 5, 20), (256, 0, 100)])
+def test_gpu_long_walks_equal_the_twin(m, sigma, l, gpu_ctx):
+    """Pivots next to 1: the walks that the kernel takes thirty-two steps at a time across the warp
+    (several lanes of a warp at once, and lanes that run out of bounds) against the sequential twin,
+    and against its own exact walk."""
+    n = 600
+    d, r, J, eta, piv = _random_batch(m, sigma, n, 1234 + l)
+    rng = np.random.default_rng(l)
+    far = rng.random(n) < 0.3
+    piv = np.where(far, LD(1) - (rng.random(n) * 10.0 ** -rng.uniform(2.0, 5.0, n)).astype(LD), piv)
+    S = _gpu_factory(gpu_ctx)(m, sigma, l, d, r)
+    ks, x, delta, st = S.sample(J, eta, piv, 20000)
+    T = hs.DiagK(m, sigma, l, d, r)
+    ks2, x2, delta2, st2 = T.sample([hs.limbs_to_int(J[i]) for i in range(n)], eta, piv, 20000)
+    assert ks == ks2 and np.array_equal(delta, delta2) and np.array_equal(st, st2)
+    S.set_force_exact(True)
+    sub = np.where(far)[0][:40]
+    ks3, x3, delta3, st3 = S.sample(J[sub], eta[sub], piv[sub], 20000)
+    assert ks3 == [ks[i] for i in sub] and np.array_equal(delta3, delta[sub]) and np.array_equal(st3, st[sub])
+    assert np.abs(delta).max() > 1000 and (st == 1).any() and (st == 0).sum() > n // 2
 
 
 @pytest.mark.gpu
