@@ -292,6 +292,83 @@ def test_twin_long_walks_decided_in_doubles_equal_the_exact_walk(m, sigma, l):
     assert np.abs(out[0][2]).max() > 2000 and (out[0][3] == 0).sum() >= n // 2
 
 
+def _exact_sample(m, sigma, l, d, r, j, eta, pivot, delta_bound):
+    """The scale-free form in exact integers and 200-bit floats (the derivation in
+    qunundrum_b200/csrc/diagk.cuh; itself checked against the reference's vectors in
+    test_exact_form_reproduces_the_k_vectors): (ok, k, x)."""
+    n = m + sigma
+    Z = r * j
+    q = (Z >> n) + (1 if (Z & ((1 << n) - 1)) >= (1 << (n - 1)) else 0)
+    s = (q + eta) % r
+    w = (d * s) % r
+    Qv, w2 = divmod(w << l, r)
+    c = 1 if 2 * w2 >= r else 0
+    k0 = (-(Qv + c)) % (1 << l)
+    with mp.workprec(200):
+        t = mp.mpf(w2 - c * r) / r
+        S = mp.sin(mp.pi * t) ** 2
+        p = rs._get_ld(mp.mpf(0)) + pivot
+        for idx in range(2 * delta_bound + 1):
+            delta = (idx + 1) // 2 if idx % 2 else -(idx // 2)
+            x = t + delta
+            if l < 62:
+                dm = delta % (1 << l)
+                if dm >= (1 << (l - 1)):
+                    dm -= 1 << l
+                x = t + dm
+                if x >= (1 << (l - 1)):
+                    x -= 1 << l
+                if x < -(1 << (l - 1)):
+                    x += 1 << l
+            h = mp.mpf(1) if x == 0 else S / (mp.mpf(2) ** l * mp.sin(mp.pi * x / mp.mpf(2) ** l)) ** 2
+            p = p - rs._get_ld(h)
+            if p <= 0:
+                return True, (k0 + delta) % (1 << l), x
+    return False, 0, mp.mpf(0)
+
+
+def test_exact_form_reproduces_the_k_vectors():
+    path = [p for p in K_FILES if "m-512-" in p][0]
+    m, sigma, l = _msl(path)
+    d, r = rs.deterministic_d_r(m)
+    for j, eta, pivot, k, _ in k_records(path)[:12]:
+        ok, got, _ = _exact_sample(m, sigma, l, d, r, j, eta, pivot, 5000)
+        assert ok and got == k
+
+
+def test_twin_integer_part_on_odd_shapes():
+    """Sizes the vectors do not have: r of 1 .. 9 limbs with any number of top bits, r much shorter
+    than 2^m and than 2^l (the shift by l then takes several Barrett rounds), m + sigma and l not
+    multiples of 32, l from 1 to m + sigma, d tiny and d = r - 1, j at both ends of its range."""
+    import random
+    prng = random.Random(99)
+    checked = 0
+    for trial in range(160):
+        rbits = prng.choice([33, 40, 63, 64, 65, 95, 96, 97, 128, 130, 191, 200, 257, 288])
+        m = rbits + prng.choice([0, 0, 1, 7, 40, 150])
+        sigma = prng.choice([0, 1, 5, 11, 31, 32])
+        l = prng.choice([1, 2, 13, 31, 32, 33, 61, 62, 63, 64, 96, 109, 110, 111, m, m + sigma])
+        l = max(1, min(l, m + sigma))
+        r = (1 << (rbits - 1)) + prng.randrange(1 << (rbits - 1))
+        d = prng.choice([1, 2, r - 1, r // 2, 1 + prng.randrange(r - 1)])
+        S = hs.DiagK(m, sigma, l, d, r)
+        n = m + sigma
+        js = [0, 1, (1 << n) - 1, (1 << n) - 2, 1 << (n - 1)] + [prng.randrange(1 << n) for _ in range(5)]
+        etas = [prng.randrange(-25, 26) for _ in js]
+        piv = np.array([LD(prng.random()) * LD(0.6) for _ in js], dtype=LD)
+        ks, x, delta, st = S.sample(js, etas, piv, 40)
+        for i, j in enumerate(js):
+            ok, k, xe = _exact_sample(m, sigma, l, d, r, j, etas[i], piv[i], 40)
+            assert ok == (st[i] in (0, 2)), (m, sigma, l, d, r, j, etas[i])
+            assert ks[i] == k, (m, sigma, l, d, r, j, etas[i], piv[i])
+            if ok:
+                with mp.workprec(200):
+                    got = mp.mpf(float(x[i, 0])) + mp.mpf(float(x[i, 1]))
+                    assert abs(got - xe) <= abs(xe) * mp.mpf(2) ** -95 + mp.mpf(2) ** -1000, (m, sigma, l, d, r, j)
+            checked += 1
+    assert checked == 1600
+
+
 def test_twin_refuses_bad_parameters():
     with pytest.raises(ValueError):
         hs.DiagK(128, 0, 64, 5, 3)          # d >= r
