@@ -7,10 +7,10 @@ QB200_DEVICE=0 QB200_TEXT_DEVICE=0 $B/minimpirun -np 3 $B/gpu/generate_diagonal_
 ls distributions
 for np in 17 5; do
   mkdir run$np; cd run$np; ln -s ../distributions distributions
-  t0=$(date +%s.%N)
+  t0=$(date +%s%N)
   QB200_DEVICE=0 QB200_TEXT_DEVICE=0 QB200_DROPIN_STATS=1 $B/minimpirun -np $np $B/gpu/estimate_runs_diagonal_distribution distributions/diagonal-distribution-det-dim-128-m-64-sigma-6-s-2.txt > out.log 2> err.log
-  t1=$(date +%s.%N)
-  echo "np=$np wall $(echo "$t1 - $t0" | bc) s"
+  t1=$(date +%s%N)
+  echo "np=$np wall $(( (t1 - t0) / 1000000 )) ms"
   grep "^m:" out.log; grep "drop-in" err.log | head -3
   cd ..
 done
