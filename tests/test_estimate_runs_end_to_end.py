@@ -93,7 +93,11 @@ def test_estimate_runs_with_the_tau_dropin_matches_the_reference(gen, gen_args, 
         assert len(ref) == len(gpu) and len(ref) >= 2
         for a, b in zip(ref, gpu):
             assert a[:3] == b[:3]                                   # m, s, n: the same search path
-            assert abs(float(a[3]) - float(b[3])) <= 0.05           # tau_d (tau) quantile
+            # tau_d (tau) quantile. The diagonal tau has a 1 / x tail (k walks |delta| > x with
+            # probability ~0.1 / x), so its quantile is noisier: seven runs of the REFERENCE gave
+            # 3.862 ... 3.915 for n = 2 (standard deviation 0.022) and 4.186 ... 4.228 for n = 3
+            tol = 0.15 if "diagonal" in exe else 0.05
+            assert abs(float(a[3]) - float(b[3])) <= tol
             ea, eb = int(a[5]), int(b[5])                           # estimates with a sampling error
             assert abs(ea - eb) <= 5 * max(ea, eb) ** 0.5 + 5
             if a[6] is not None:
