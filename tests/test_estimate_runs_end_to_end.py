@@ -1,6 +1,7 @@
-"""The reference's own estimate_runs_distribution / estimate_runs_linear_distribution executables
-(argv parsing, distribution loader, MPI farm, ordered tau lists, volume quotients, logs) with
-tau_estimate / tau_estimate_linear coming from qunundrum_b200/dropin/dropin_tau.cpp, against
+"""The reference's own estimate_runs_distribution / estimate_runs_linear_distribution /
+estimate_runs_diagonal_distribution executables (argv parsing, distribution loader, MPI farm, ordered
+tau lists, volume quotients, logs) with tau_estimate / tau_estimate_linear coming from
+qunundrum_b200/dropin/dropin_tau.cpp and tau_estimate_diagonal from dropin_tau_diagonal.cpp, against
 the same executables with the reference's tau_estimate.cpp.
 
 Every client seeds its generator from /dev/urandom (src/keccak_random.h:42), so two runs of the
