@@ -13,13 +13,16 @@
 // i.e. integer arithmetic on m-bit numbers: k0 = -(Qv + c) mod 2^l with c = [2 w2 >= r],
 // t = w2 / r - c in [-1/2, 1/2), alpha_phi = 2^(m+sigma-l) (t + delta) and
 //     h = sin^2(pi t) / (2^l sin(pi (t + delta) / 2^l))^2
-// where t is needed to double-double accuracy only. The integers are exact (k matches the
-// reference bit for bit unless a pivot is used up within ~2^-100 of a step, which the reference's
-// own 64-bit rounding of h decides), the walk subtracts h rounded to the x87 format as the
-// reference's `pivot -= mpfr_get_ld(...)` does (:594).
+// where t is needed to double-double accuracy only. The integers are exact. The walk is decided
+// in doubles where the pivot clears a rigorous error band (diagk_walk) and otherwise by the exact
+// walk, which subtracts h rounded to the x87 format as the reference's
+// `pivot -= mpfr_get_ld(...)` does (:594), h agreeing with the reference's to ~2^-100 -- so k
+// matches the reference bit for bit (a pivot used up within 2^-100 of a step, which only the
+// reference's own rounding of h to 64 bits could decide, does not occur).
 //
 // The multi-limb part: one product r j, one product d s, Barrett reductions modulo r with a
-// host-prepared reciprocal; 32-bit limbs, product scanning with a 96-bit column accumulator.
+// host-prepared reciprocal; 32-bit limbs, product scanning with 96-bit column accumulators, four
+// columns at a time (mul_columns).
 // Operands that are the same for every sample (r, d, mu) are read through `c`; per-sample
 // operands live in caller-provided arrays with a stride (1 on the host; on the device the samples
 // of a CTA are interleaved so that the threads of a warp read consecutive words).
