@@ -517,3 +517,63 @@ bool tau_estimate_diagonal(const Diagonal_Distribution* const distribution, Rand
   tau = b.tau[b.next];
   return b.ok[b.next++] != 0;
 }
+
+#ifdef QB200_DROPIN_SAMPLE_K
+// Optional second symbol: the reference's one-sample entry point itself (src/sample.h:184-191), for a
+// build that compiles the reference's sample.cpp with
+//   -Dsample_k_from_diagonal_j_eta_pivot=sample_k_from_diagonal_j_eta_pivot_cpu_unused
+// (solve_diagonal_*; the reference's own known-answer test
+// test_sample_k_from_diagonal_j_eta_pivot_kat(), src/test/test_sample.cpp:679-836, which
+// integration/tools/sample_k_kat_check.cpp runs against this function). One GPU call per sample:
+// a latency of tens of microseconds against the reference's 0.1 ... 10 ms.
+bool sample_k_from_diagonal_j_eta_pivot(const Diagonal_Parameters* const parameters, long double pivot,
+                                        const mpz_t j, const int32_t eta, const uint32_t delta_bound, mpz_t k,
+                                        mpfr_t alpha_phi) {
+  if ((pivot < 0) || (pivot > 1)) {
+    critical("sample_k_from_diagonal_j_eta_pivot(): The pivot is out of bounds.");
+  }
+  setup_for(parameters);
+  // j + a 2^(m+sigma) gives the same k and alpha_phi as j (r j changes by a multiple of 2^(m+sigma) r):
+  // the ABI takes j on [0, 2^(m+sigma))
+  mpz_t jr;
+  mpz_init(jr);
+  mpz_fdiv_r_2exp(jr, j, g.m + g.sigma);
+  std::vector<uint32_t> row(g.j_limbs, 0u), krow(qb200_diagk_k_limbs(g.sampler), 0u);
+  size_t cnt = 0;
+  mpz_export(row.data(), &cnt, -1, 4, 0, 0, jr);
+  mpz_clear(jr);
+  double x_hi = 0, x_lo = 0;
+  int32_t status = 0;
+  if (0 != qb200_diagk_sample(g.sampler, 1, row.data(), &eta, &pivot, delta_bound, krow.data(), &x_hi, &x_lo, NULL,
+                              &status)) {
+    critical("sample_k_from_diagonal_j_eta_pivot(): %s", qb200_last_error());
+  }
+  if (status == QB200_DIAGK_GAVE_UP) {
+    critical("sample_k_from_diagonal_j_eta_pivot(): gave up after 2^22 steps (delta_bound = %u).", delta_bound);
+  }
+  if (status == QB200_DIAGK_OUT_OF_BOUNDS) {  // src/sample.cpp:622-636
+    mpz_set_ui(k, 0);
+    if (NULL != alpha_phi) mpfr_set_ui(alpha_phi, 0, MPFR_RNDN);
+    return false;
+  }
+  mpz_import(k, krow.size(), -1, 4, 0, 0, krow.data());
+  if (NULL != alpha_phi) {
+    const bool negative_phi = (status == QB200_DIAGK_OK_NEGATIVE_PHI);  // alpha_phi = 2^(m+sigma-l) (x - 2^l)
+    mpfr_t a;
+    mpfr_init2(a, 128 + (negative_phi ? g.l : 0));
+    mpfr_set_d(a, x_hi, MPFR_RNDN);
+    mpfr_add_d(a, a, x_lo, MPFR_RNDN);  // exact
+    if (negative_phi) {
+      mpfr_t p;
+      mpfr_init2(p, 64);
+      mpfr_set_ui_2exp(p, 1, (mpfr_exp_t)g.l, MPFR_RNDN);
+      mpfr_sub(a, a, p, MPFR_RNDN);       // exact
+      mpfr_clear(p);
+    }
+    mpfr_mul_2si(a, a, (long)g.m + (long)g.sigma - (long)g.l, MPFR_RNDN);
+    mpfr_set(alpha_phi, a, MPFR_RNDN);  // src/sample.cpp:577-579
+    mpfr_clear(a);
+  }
+  return true;
+}
+#endif

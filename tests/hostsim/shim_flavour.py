@@ -96,6 +96,101 @@ def build_tau_diagonal(force: bool = False):
     return TAU_DIAGONAL_CHECK
 
 
+SAMPLE_K_KAT_CHECK = os.path.join(OUT, "sample_k_kat_check")
+
+
+def build_sample_k_kat(reference_root: str = "/root/reference", force: bool = False, flavour: str = "dropin"):
+    """TEST-ONLY: integration/tools/sample_k_kat_check.cpp -- the reference's own known-answer test
+    function of the diagonal k sampler (src/test/test_sample.cpp, compiled in place) linked against
+    the drop-in's sample_k_from_diagonal_j_eta_pivot (dropin_tau_diagonal.cpp with
+    -DQB200_DROPIN_SAMPLE_K), the reference's sample.cpp with that one function renamed, and the CPU
+    stand-in of qb200_diagk_*. flavour = "reference": the same driver over the unmodified sample.cpp
+    (to show that the vectors and the driver's comparison are sound). Returns the executable's path,
+    or None."""
+    if flavour == "reference":
+        return _build_sample_k_kat_reference(reference_root, force)
+    from integration import build as ib
+    src = os.path.join(reference_root, "src")
+    obj = os.path.join(ib.OUT, "obj")
+    if not os.path.isdir(src) or not os.path.exists(os.path.join(obj, "math.o")):
+        return SAMPLE_K_KAT_CHECK if os.path.exists(SAMPLE_K_KAT_CHECK) else None
+    dropin = os.path.join(_ROOT, "qunundrum_b200", "dropin", "dropin_tau_diagonal.cpp")
+    driver = os.path.join(_ROOT, "integration", "tools", "sample_k_kat_check.cpp")
+    srcs = [os.path.join(_HERE, "abi_shim.cpp"), os.path.join(_HERE, "hostsim.cpp"),
+            os.path.join(_ROOT, "qunundrum_b200", "csrc", "hostconst.cpp"),
+            os.path.join(_ROOT, "qunundrum_b200", "csrc", "text_tables.cpp")]
+    deps = srcs + [dropin, driver, os.path.abspath(__file__)]
+    deps += [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in ("diagk.cuh", "diagk_host.hpp")]
+    if not force and os.path.exists(SAMPLE_K_KAT_CHECK) and all(
+            os.path.getmtime(d) <= os.path.getmtime(SAMPLE_K_KAT_CHECK) for d in deps):
+        return SAMPLE_K_KAT_CHECK
+    os.makedirs(OUT, exist_ok=True)
+    inc = ["-I", os.path.join(_ROOT, "integration", "minimpi"), "-I", os.path.join(_ROOT, "integration", "stubs"),
+           "-I", os.path.join(_ROOT, "integration", "shims"), "-I", os.path.join(_ROOT, "include"), "-iquote", src]
+    cxx = ["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *inc, "-c"]
+    tmp = []
+
+    def cc(source, name, *flags):
+        o = os.path.join(OUT, name)
+        subprocess.check_call([*cxx, *flags, source, "-o", o])
+        tmp.append(o)
+        return o
+
+    objs = [cc(driver, "_kat_driver.o"),
+            cc(os.path.join(src, "test", "test_sample.cpp"), "_kat_test_sample.o"),
+            cc(os.path.join(src, "test", "test_common.cpp"), "_kat_test_common.o",
+               "-Dtest_cmp_ld=test_cmp_ld_of_the_reference"),
+            cc(os.path.join(src, "sample.cpp"), "_kat_sample_renamed.o",
+               "-Dsample_k_from_diagonal_j_eta_pivot=sample_k_from_diagonal_j_eta_pivot_cpu_unused"),
+            cc(dropin, "_kat_dropin.o", "-DQB200_DROPIN_SAMPLE_K")]
+    shim = os.path.join(OUT, "libqb200_diagkshim.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-x", "c++", *srcs,
+                           "-o", shim])
+    common = [os.path.join(obj, f + ".o") for f in ib.COMMON_CPP + ib.COMMON_C + ["lattice_stub", "minimpi"]
+              if f != "sample"]
+    libs = [os.path.join(ib.LIBDIR, "libmpfr.so.6"), os.path.join(ib.LIBDIR, "libgmp.so.10"),
+            "-lpthread", "-lm"]
+    subprocess.check_call(["g++", *objs, *common,
+                           *[os.path.join(obj, f + ".o") for f in ib.INTEGRATORS + ib.TEXT_IO],
+                           shim, "-Wl,-rpath,$ORIGIN", *libs, "-o", SAMPLE_K_KAT_CHECK])
+    for o in tmp:
+        os.remove(o)
+    return SAMPLE_K_KAT_CHECK
+
+
+def _build_sample_k_kat_reference(reference_root, force):
+    from integration import build as ib
+    src = os.path.join(reference_root, "src")
+    obj = os.path.join(ib.OUT, "obj")
+    exe = SAMPLE_K_KAT_CHECK + "_reference"
+    if not os.path.isdir(src) or not os.path.exists(os.path.join(obj, "sample.o")):
+        return exe if os.path.exists(exe) else None
+    driver = os.path.join(_ROOT, "integration", "tools", "sample_k_kat_check.cpp")
+    if not force and os.path.exists(exe) and os.path.getmtime(driver) <= os.path.getmtime(exe):
+        return exe
+    os.makedirs(OUT, exist_ok=True)
+    inc = ["-I", os.path.join(_ROOT, "integration", "minimpi"), "-I", os.path.join(_ROOT, "integration", "stubs"),
+           "-I", os.path.join(_ROOT, "integration", "shims"), "-I", os.path.join(_ROOT, "include"), "-iquote", src]
+    cxx = ["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *inc, "-c"]
+    objs = []
+    for source, name, flags in ((driver, "_katr_driver.o", []),
+                                (os.path.join(src, "test", "test_sample.cpp"), "_katr_test_sample.o", []),
+                                (os.path.join(src, "test", "test_common.cpp"), "_katr_test_common.o",
+                                 ["-Dtest_cmp_ld=test_cmp_ld_of_the_reference"])):
+        o = os.path.join(OUT, name)
+        subprocess.check_call([*cxx, *flags, source, "-o", o])
+        objs.append(o)
+    common = [os.path.join(obj, f + ".o") for f in ib.COMMON_CPP + ib.COMMON_C + ["lattice_stub", "minimpi"]]
+    libs = [os.path.join(ib.LIBDIR, "libmpfr.so.6"), os.path.join(ib.LIBDIR, "libgmp.so.10"),
+            "-lpthread", "-lm"]
+    subprocess.check_call(["g++", *objs, *common,
+                           *[os.path.join(obj, f + ".o") for f in ib.INTEGRATORS + ib.TEXT_IO],
+                           *libs, "-o", exe])
+    for o in objs:
+        os.remove(o)
+    return exe
+
+
 def build(force: bool = False) -> bool:
     from integration import build as ib
     obj = os.path.join(ib.OUT, "obj")
