@@ -1,4 +1,6 @@
-// sample_k_kat_check.cpp -- TEST DRIVER: the reference's OWN known-answer test of the diagonal k sampler,
+// sample_k_kat_check.cpp -- TEST DRIVER: the reference's OWN known-answer tests of the diagonal k sampler
+// and of its integrand h (test_diagonal_probability_h_approx_kat(), src/test/test_diagonal_probability.cpp:174-298,
+// against the drop-in's diagonal_probability_approx_h):
 // test_sample_k_from_diagonal_j_eta_pivot_kat() (src/test/test_sample.cpp:679-836: all 522 files of
 // res/test-vectors, 25 records each, k compared with mpz_cmp and alpha_phi with test_cmp_ld), run
 // against the drop-in's sample_k_from_diagonal_j_eta_pivot (qunundrum_b200/dropin/dropin_tau_diagonal.cpp
@@ -21,6 +23,7 @@
 #include <math.h>
 
 void test_sample_k_from_diagonal_j_eta_pivot_kat();  // src/test/test_sample.cpp:679 (not in test_sample.h)
+void test_diagonal_probability_h_approx_kat();       // src/test/test_diagonal_probability.cpp:174
 
 bool test_cmp_ld(const long double a, const long double b, const long double tolerance) {
   if (a == b) return TRUE;
@@ -36,6 +39,9 @@ bool test_cmp_ld(const long double a, const long double b, const long double tol
 int main() {
   mpfr_set_default_prec(PRECISION);
   test_sample_k_from_diagonal_j_eta_pivot_kat();
+  // ... and the one of its integrand: diagonal_probability_approx_h on the 522 files
+  // diagonal-probabilities-h-det-*, test_cmp_ld on the long double values
+  test_diagonal_probability_h_approx_kat();
   printf("ok\n");
   return 0;
 }

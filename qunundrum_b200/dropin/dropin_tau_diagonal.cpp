@@ -576,4 +576,34 @@ bool sample_k_from_diagonal_j_eta_pivot(const Diagonal_Parameters* const paramet
   }
   return true;
 }
+
+// ... and its integrand (src/diagonal_probability.h), for a build that compiles diagonal_probability.cpp
+// with -Ddiagonal_probability_approx_h=diagonal_probability_approx_h_cpu_unused: h at the angle
+// phi = 2 pi x / 2^l, i.e. x = phi 2^l / (2 pi) handed to qb200_diagk_h as an unevaluated sum of two
+// doubles. (The walk above does not come through here: the kernel forms x itself, exactly.)
+void diagonal_probability_approx_h(mpfr_t norm, const mpfr_t phi, const Diagonal_Parameters* const parameters) {
+  if (0 == mpfr_cmp_ui(phi, 0)) {  // src/diagonal_probability.cpp:104-108
+    mpfr_set_ui(norm, 1, MPFR_RNDN);
+    return;
+  }
+  setup_for(parameters);
+  const mpfr_prec_t prec = (mpfr_get_prec(phi) > 192 ? mpfr_get_prec(phi) : 192) + 64;
+  mpfr_t x, two_pi;
+  mpfr_init2(x, prec);
+  mpfr_init2(two_pi, prec);
+  mpfr_const_pi(two_pi, MPFR_RNDN);
+  mpfr_mul_2si(two_pi, two_pi, 1, MPFR_RNDN);
+  mpfr_div(x, phi, two_pi, MPFR_RNDN);
+  mpfr_mul_2si(x, x, (long)g.l, MPFR_RNDN);
+  const double x_hi = mpfr_get_d(x, MPFR_RNDN);
+  mpfr_sub_d(x, x, x_hi, MPFR_RNDN);
+  const double x_lo = mpfr_get_d(x, MPFR_RNDN);
+  mpfr_clear(x);
+  mpfr_clear(two_pi);
+  long double h = 0;
+  if (0 != qb200_diagk_h(g.sampler, 1, &x_hi, &x_lo, &h)) {
+    critical("diagonal_probability_approx_h(): %s", qb200_last_error());
+  }
+  mpfr_set_ld(norm, h, MPFR_RNDN);
+}
 #endif

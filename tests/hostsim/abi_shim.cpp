@@ -177,11 +177,13 @@ int hostsim_diagk_sample(void* hh, uint32_t n, const uint32_t* j, const int32_t*
                          const long double* pivot, uint64_t delta_bound, uint32_t* k_out, double* x,
                          int64_t* delta, int32_t* status);
 const char* hostsim_last_error();
+void hostsim_diagk_h(uint32_t l, uint32_t n, const double* x, long double* out);
 }
 
 struct qb200_diagk {
   void* h = nullptr;
   uint32_t dims[3] = {0, 0, 0};
+  uint32_t l = 0;
 };
 
 extern "C" {
@@ -195,6 +197,7 @@ int qb200_diagk_create(qb200_context*, const qb200_params* p, qb200_diagk** out)
   }
   qb200_diagk* s = new qb200_diagk;
   s->h = h;
+  s->l = p->l;
   hostsim_diagk_dims(h, s->dims);
   *out = s;
   return 0;
@@ -225,6 +228,16 @@ int qb200_diagk_sample(qb200_diagk* s, uint32_t n, const uint32_t* j, const int3
     if (status) status[i] = st[i];
   }
   if (k) memcpy(k, kk.data(), kk.size() * 4);
+  return 0;
+}
+
+int qb200_diagk_h(qb200_diagk* s, uint32_t n, const double* x_hi, const double* x_lo, long double* h) {
+  std::vector<double> x(2 * (size_t)n);
+  for (uint32_t i = 0; i < n; i++) {
+    x[2 * i] = x_hi[i];
+    x[2 * i + 1] = x_lo[i];
+  }
+  hostsim_diagk_h(s->l, n, x.data(), h);
   return 0;
 }
 

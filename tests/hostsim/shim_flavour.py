@@ -140,14 +140,17 @@ def build_sample_k_kat(reference_root: str = "/root/reference", force: bool = Fa
             cc(os.path.join(src, "test", "test_sample.cpp"), "_kat_test_sample.o"),
             cc(os.path.join(src, "test", "test_common.cpp"), "_kat_test_common.o",
                "-Dtest_cmp_ld=test_cmp_ld_of_the_reference"),
+            cc(os.path.join(src, "test", "test_diagonal_probability.cpp"), "_kat_test_diagonal_probability.o"),
             cc(os.path.join(src, "sample.cpp"), "_kat_sample_renamed.o",
                "-Dsample_k_from_diagonal_j_eta_pivot=sample_k_from_diagonal_j_eta_pivot_cpu_unused"),
+            cc(os.path.join(src, "diagonal_probability.cpp"), "_kat_diagonal_probability_renamed.o",
+               "-Ddiagonal_probability_approx_h=diagonal_probability_approx_h_cpu_unused"),
             cc(dropin, "_kat_dropin.o", "-DQB200_DROPIN_SAMPLE_K")]
     shim = os.path.join(OUT, "libqb200_diagkshim.so")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-x", "c++", *srcs,
                            "-o", shim])
     common = [os.path.join(obj, f + ".o") for f in ib.COMMON_CPP + ib.COMMON_C + ["lattice_stub", "minimpi"]
-              if f != "sample"]
+              if f not in ("sample", "diagonal_probability")]
     libs = [os.path.join(ib.LIBDIR, "libmpfr.so.6"), os.path.join(ib.LIBDIR, "libgmp.so.10"),
             "-lpthread", "-lm"]
     subprocess.check_call(["g++", *objs, *common,
@@ -175,6 +178,8 @@ def _build_sample_k_kat_reference(reference_root, force):
     objs = []
     for source, name, flags in ((driver, "_katr_driver.o", []),
                                 (os.path.join(src, "test", "test_sample.cpp"), "_katr_test_sample.o", []),
+                                (os.path.join(src, "test", "test_diagonal_probability.cpp"),
+                                 "_katr_test_diagonal_probability.o", []),
                                 (os.path.join(src, "test", "test_common.cpp"), "_katr_test_common.o",
                                  ["-Dtest_cmp_ld=test_cmp_ld_of_the_reference"])):
         o = os.path.join(OUT, name)

@@ -598,9 +598,11 @@ def test_gpu_tau_diagonal_dropin_equals_the_reference_in_process(args, runs):
                     reason="needs /root/reference and integration/_build")
 def test_the_references_own_kat_test_passes_with_the_dropin_sampler():
     """test_sample_k_from_diagonal_j_eta_pivot_kat() of src/test/test_sample.cpp:679-836 (all 522 files,
-    mpz_cmp on k, test_cmp_ld on alpha_phi), compiled in place and linked against
-    sample_k_from_diagonal_j_eta_pivot of qunundrum_b200/dropin/dropin_tau_diagonal.cpp
-    (-DQB200_DROPIN_SAMPLE_K) over the CPU stand-in of the library -- and, with the same driver, against
+    mpz_cmp on k, test_cmp_ld on alpha_phi) and test_diagonal_probability_h_approx_kat() of
+    src/test/test_diagonal_probability.cpp:174-298 (522 files), compiled in place and linked against
+    sample_k_from_diagonal_j_eta_pivot and diagonal_probability_approx_h of
+    qunundrum_b200/dropin/dropin_tau_diagonal.cpp (-DQB200_DROPIN_SAMPLE_K) over the CPU stand-in of
+    the library -- and, with the same driver, against
     the reference's own sample.cpp (the reference's test_cmp_ld refuses the negative alpha_phi of half
     of the records, so the unmodified test fails with the reference's own sampler as well; the driver,
     integration/tools/sample_k_kat_check.cpp, says what it supplies instead)."""
@@ -610,4 +612,4 @@ def test_the_references_own_kat_test_passes_with_the_dropin_sampler():
         assert exe
         p = subprocess.run([exe], cwd="/root/reference", capture_output=True, text=True, timeout=1500)
         assert p.returncode == 0 and p.stdout.strip().endswith("ok"), (flavour, p.stdout[-500:], p.stderr[-500:])
-        assert p.stdout.count("Processing:") == 522
+        assert p.stdout.count("Processing:") == 1044    # 522 files of k vectors + 522 of h vectors
