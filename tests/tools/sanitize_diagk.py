@@ -16,7 +16,10 @@ import qunundrum_b200 as qb  # noqa: E402
 from tests.test_diagk import GOLD, check_gold  # noqa: E402
 
 ctx = qb.Context(0)
+only = sys.argv[1:]
 for g in GOLD:
+    if only and g.name not in only:
+        continue
     S = qb.DiagonalKSampler(qb.Diagonal_Parameters(g.m, g.sigma, 0, g.d, g.r, eta_bound=25, l=g.l), ctx)
     check_gold(g, S)
     n, rows = 6, 48   # the random rows (the edge rows behind them include j < |eta| 2^(m+sigma) / r)
