@@ -13,6 +13,9 @@
  *                                            linear_distribution_slice_compute_richardson src/linear_distribution_slice_compute_richardson.cpp:17
  *   qb200_slice1d_compute (DIAGONAL)         diagonal_distribution_slice_compute            src/diagonal_distribution_slice_compute.cpp:30
  *                                            diagonal_distribution_slice_compute_richardson src/diagonal_distribution_slice_compute_richardson.cpp:17
+ *   qb200_slice2d_compute_scaled             ... followed by distribution_slice_copy_scale    src/distribution_slice.cpp:230
+ *   qb200_resident_collapse2d                linear_distribution_init_collapse_d / _r       src/linear_distribution.cpp:152,239
+ *   qb200_resident_format                    the value loops of distribution_export         src/distribution.cpp:305-357
  *   qb200_text_format_* / qb200_text_parse_* the value loops of *_slice_export / *_slice_import   (see "text export" below)
  *   qb200_sampler_tau_estimate               tau_estimate / tau_estimate_linear             src/tau_estimate.cpp:23,89
  *   qb200_diagk_sample                       sample_k_from_diagonal_j_eta_pivot             src/sample.cpp:412
@@ -47,7 +50,7 @@
 extern "C" {
 #endif
 
-#define QB200_VERSION 1
+#define QB200_VERSION 2
 
 /* Distribution_Slice_Compute_Method, src/distribution_slice.h:31-78. */
 #define QB200_METHOD_HEURISTIC_SIGMA 0
@@ -121,6 +124,24 @@ int qb200_slice1d_compute(qb200_context *ctx, const qb200_params *params, int ki
                           const int32_t *min_log_alpha, const int32_t *eta, double *cells,
                           long double *total_probability, uint32_t *flags);
 
+/* The generator client's tail: a slice computed at 512 or 1024 is
+ * scaled to MAX_SLICE_DIMENSION = 256 with distribution_slice_copy_scale before it is sent
+ * (src/main_generate_distribution.cpp:1308-1343, src/distribution_slice.cpp:230-264). Here the
+ * scaling happens on the device and only store_dimension^2 cells per slice cross the bus:
+ *   cells  n * store_dimension^2 LONG DOUBLES (a scaled cell is the long double sum of
+ *          (dimension / store_dimension)^2 cells in the reference's order, each partial sum
+ *          rounded to 64 bits: bit-identical to copy_scale applied to the unscaled doubles;
+ *          it does not fit a double)
+ *   total_probability / total_error / flags as qb200_slice2d_compute (of the UNscaled slice, which
+ *          is what copy_scale hands on; the binding ORs SLICE_FLAGS_SCALED).
+ * dimension must be a multiple of store_dimension. */
+int qb200_slice2d_compute_scaled(qb200_context *ctx, const qb200_params *params, int method,
+                                 int richardson, uint32_t dimension, uint32_t store_dimension,
+                                 uint32_t n, const int32_t *min_log_alpha_d,
+                                 const int32_t *min_log_alpha_r, long double *cells,
+                                 long double *total_probability, long double *total_error,
+                                 uint32_t *flags);
+
 /* ---- planned, device-resident execution ----------------------------------- */
 
 /* A plan holds the batch's constants, coordinates and axis-table descriptors
@@ -189,6 +210,44 @@ int qb200_text_format_f64(qb200_context *ctx, const double *values, size_t n,
  * the text length. kind = QB200_TEXT_X87 / QB200_TEXT_F64. */
 int qb200_text_format_device(qb200_context *ctx, int kind, const void *d_values, size_t n,
                              char *d_text, size_t cap, uint64_t *d_len, void *stream);
+
+/* ---- a stored distribution on the device ---------------------------------------
+ *
+ * what the generator's server does to a finished two-dimensional
+ * distribution -- collapse it to its two marginals
+ *   linear_distribution_init_collapse_d   src/linear_distribution.cpp:152-237
+ *   linear_distribution_init_collapse_r   src/linear_distribution.cpp:239-324
+ * (called from src/main_generate_distribution.cpp:709-760; ~2 x 10^8 long double divisions and
+ * additions) and export every slice (distribution_export, src/distribution.cpp:305-357).
+ * A qb200_resident holds the cells of all slices in device memory (uploaded ONCE from the
+ * slices' own norm_matrix arrays by a pinned, double-buffered gather), each slice followed by one
+ * spare value, its `tail` (total_error), so that a slice's export is one contiguous range. */
+typedef struct qb200_resident qb200_resident;
+
+/* cells[i]: n_cells[i] long doubles (read during the call only); tails may be NULL (zeros). */
+int qb200_resident_create(qb200_context *ctx, uint32_t n_slices, const uint64_t *n_cells,
+                          const long double *const *cells, const long double *tails,
+                          qb200_resident **resident);
+void qb200_resident_destroy(qb200_resident *resident);
+uint64_t qb200_resident_cells(const qb200_resident *resident);
+
+/* Collapse to a marginal: axis 0 = alpha_d (element x of a destination vector collects
+ * norm_matrix[x + y * dimension] over y), axis 1 = alpha_r. dimension[i]: the dimension of
+ * resident slice i (n_cells[i] = dimension[i]^2, a divisor of max_dimension). Destination k
+ * sums the slices src_index[src_begin[k] .. src_begin[k + 1]) in that order -- the binding lists
+ * them in the distribution's order, as the reference's loop meets them. out: n_dst *
+ * max_dimension long doubles, bit-identical to the reference's: every element is the
+ * reference's own sequence of `+= probability / (long double)divisor` in 64-bit arithmetic. */
+int qb200_resident_collapse2d(qb200_resident *resident, int axis, const uint32_t *dimension,
+                              uint32_t n_dst, const uint32_t *src_begin, const uint32_t *src_index,
+                              uint32_t max_dimension, long double *out);
+
+/* "%.24Lg\n" lines of the slices [first, first + count): slice first + i occupies
+ * text[offsets[i], offsets[i + 1]) -- its cells, then its tail. One exporter launch per slice,
+ * enqueued back to back, no upload, one synchronisation; *text points into pinned memory owned
+ * by the resident, valid until its next call. offsets: count + 1 entries. */
+int qb200_resident_format(qb200_resident *resident, uint32_t first, uint32_t count,
+                          const char **text, size_t *offsets);
 
 /* ---- text import: "%Lg" numbers ------------------------------------------------
  *

@@ -3,8 +3,9 @@
   integration/_build/ref/generate_*   the reference's slice integrators (MPFR, CPU)
   integration/_build/gpu/generate_*   the six integrator TUs replaced by
                                       qunundrum_b200/dropin/dropin.cpp, the three
-                                      *_slice_import_export TUs by dropin_text.cpp,
-                                      + libqunundrum_b200.so
+                                      *_slice_import_export TUs by dropin_text.cpp, the two
+                                      collapse functions of linear_distribution.cpp by
+                                      dropin_collapse.cpp, + libqunundrum_b200.so
 
 plus, in both flavours, the importing executables filter_distribution, info_distribution and
 compare_[linear_|diagonal_]distributions (they load stored distributions: the importer path), and
@@ -51,6 +52,10 @@ INTEGRATORS = """distribution_slice_compute distribution_slice_compute_richardso
 # tau_estimate.cpp: as it is in the "ref" flavour; in the "gpu" flavour compiled with three renames
 # next to qunundrum_b200/dropin/dropin_tau.cpp and dropin_tau_diagonal.cpp
 TAU = ["tau_estimate"]
+# linear_distribution.cpp: the two collapse functions renamed away in the "gpu" flavour, where
+# qunundrum_b200/dropin/dropin_collapse.cpp defines them
+COLLAPSE_RENAMES = ["-Dlinear_distribution_init_collapse_d=linear_distribution_init_collapse_d_cpu_unused",
+                    "-Dlinear_distribution_init_collapse_r=linear_distribution_init_collapse_r_cpu_unused"]
 TAU_RENAMES = ["-Dtau_estimate=tau_estimate_cpu_unused", "-Dtau_estimate_linear=tau_estimate_linear_cpu_unused",
                "-Dtau_estimate_diagonal=tau_estimate_diagonal_cpu_unused"]
 ESTIMATORS = ["estimate_runs_distribution", "estimate_runs_linear_distribution",
@@ -69,6 +74,7 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
             os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
             os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau.cpp"),
             os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_tau_diagonal.cpp"),
+            os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_collapse.cpp"),
             os.path.join(HERE, "tools", "tau_diagonal_check.cpp"),
             os.path.join(HERE, "minimpi", "minimpi.c"), os.path.join(HERE, "minimpi", "mpi.h"),
             os.path.join(HERE, "build.py"), os.path.join(ROOT, "include", "qunundrum_b200.h"),
@@ -97,6 +103,12 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
                  os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_text.cpp"),
                  "-o", os.path.join(obj, "dropin_text.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
+                 os.path.join(ROOT, "qunundrum_b200", "dropin", "dropin_collapse.cpp"),
+                 "-o", os.path.join(obj, "dropin_collapse.o")])
+    jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *COLLAPSE_RENAMES, *inc, "-c",
+                 os.path.join(src, "linear_distribution.cpp"),
+                 "-o", os.path.join(obj, "linear_distribution_renamed.o")])
     jobs.append(["g++", "-std=c++11", "-O2", "-w", "-include", "cmath", *TAU_RENAMES, *inc, "-c",
                  os.path.join(src, "tau_estimate.cpp"), "-o", os.path.join(obj, "tau_estimate_renamed.o")])
     jobs.append(["g++", "-std=c++11", "-O2", "-w", *inc, "-c",
@@ -115,13 +127,15 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
     subprocess.check_call(["gcc", "-O2", os.path.join(HERE, "minimpi", "minimpirun.c"),
                            "-o", os.path.join(OUT, "minimpirun")])
     common = [os.path.join(obj, f + ".o") for f in COMMON_CPP + COMMON_C + ["lattice_stub", "minimpi"]]
+    common_gpu = [o for o in common if not o.endswith(os.sep + "linear_distribution.o")] + [
+        os.path.join(obj, "linear_distribution_renamed.o"), os.path.join(obj, "dropin_collapse.o")]
     libs = [os.path.join(LIBDIR, "libmpfr.so.6"), os.path.join(LIBDIR, "libgmp.so.10"), "-lpthread", "-lm"]
     for m in MAINS:
         main_o = os.path.join(obj, "main_" + m + ".o")
         subprocess.check_call(["g++", main_o, *common,
                                *[os.path.join(obj, f + ".o") for f in INTEGRATORS + TEXT_IO],
                                *libs, "-o", os.path.join(OUT, "ref", m)])
-        subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "dropin.o"),
+        subprocess.check_call(["g++", main_o, *common_gpu, os.path.join(obj, "dropin.o"),
                                os.path.join(obj, "dropin_text.o"),
                                "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
                                "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
@@ -133,14 +147,14 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> bool:
         subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "tau_estimate.o"),
                                *[os.path.join(obj, f + ".o") for f in INTEGRATORS + TEXT_IO],
                                *libs, "-o", os.path.join(OUT, "ref", m)])
-        subprocess.check_call(["g++", main_o, *common, os.path.join(obj, "tau_estimate_renamed.o"),
+        subprocess.check_call(["g++", main_o, *common_gpu, os.path.join(obj, "tau_estimate_renamed.o"),
                                os.path.join(obj, "dropin_tau.o"), os.path.join(obj, "dropin_tau_diagonal.o"),
                                os.path.join(obj, "dropin.o"), os.path.join(obj, "dropin_text.o"),
                                "-L", os.path.join(ROOT, "qunundrum_b200"), "-lqunundrum_b200",
                                "-Wl,-rpath,$ORIGIN/../../../qunundrum_b200", *libs,
                                "-o", os.path.join(OUT, "gpu", m)])
     # test driver: the drop-in tau_estimate_diagonal against the reference's (renamed) in one process
-    subprocess.check_call(["g++", os.path.join(obj, "tau_diagonal_check.o"), *common,
+    subprocess.check_call(["g++", os.path.join(obj, "tau_diagonal_check.o"), *common_gpu,
                            os.path.join(obj, "tau_estimate_renamed.o"), os.path.join(obj, "dropin_tau.o"),
                            os.path.join(obj, "dropin_tau_diagonal.o"), os.path.join(obj, "dropin.o"),
                            os.path.join(obj, "dropin_text.o"),

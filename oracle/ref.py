@@ -323,6 +323,21 @@ class RefDistribution:
                                  tot.ctypes.data)
         return dim, a, b, t, tot[0]
 
+    def collapse(self, axis: int):
+        """linear_distribution_init_collapse_d (axis 0) / _r (axis 1): (coords, vectors, totals)."""
+        L = lib()
+        L.qref_dist_collapse.restype = C.c_uint32
+        L.qref_dist_collapse.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_uint32)]
+        md = C.c_uint32(0)
+        n = L.qref_dist_collapse(self.h, axis, 0, None, None, None, C.byref(md))
+        coords = np.zeros(n, dtype=np.int32)
+        vec = np.zeros((n, md.value), dtype=np.longdouble)
+        tot = np.zeros(n, dtype=np.longdouble)
+        L.qref_dist_collapse(self.h, axis, n, coords.ctypes.data, vec.ctypes.data, tot.ctypes.data,
+                             C.byref(md))
+        return coords, vec, tot
+
     def sample_region(self, rng: RefRandom, k: int):
         out = np.zeros((k, 4))
         ok = np.zeros(k, dtype=np.uint8)

@@ -148,6 +148,30 @@ void qref_dist_describe(void *hh, uint32_t *dimension, int32_t *c0, int32_t *c1,
   }
 }
 
+/* linear_distribution_init_collapse_d (axis 0) / _r (axis 1) of a dims = 2 handle
+ * (src/linear_distribution.cpp:152-324): the destination slices in the order the reference
+ * creates them. Returns their number; coords / totals: up to cap entries; vectors: cap *
+ * *max_dimension long doubles (the first call may pass cap = 0 to learn the sizes). */
+uint32_t qref_dist_collapse(void *hh, int axis, uint32_t cap, int32_t *coords, long double *vectors,
+                            long double *totals, uint32_t *max_dimension) {
+  Dist *h = (Dist *)hh;
+  Linear_Distribution dst;
+  if (axis == 0)
+    linear_distribution_init_collapse_d(&dst, &h->d2);
+  else
+    linear_distribution_init_collapse_r(&dst, &h->d2);
+  const uint32_t n = dst.count;
+  const uint32_t md = n ? dst.slices[0]->dimension : 0;
+  *max_dimension = md;
+  for (uint32_t i = 0; i < n && i < cap; i++) {
+    coords[i] = dst.slices[i]->min_log_alpha;
+    totals[i] = dst.slices[i]->total_probability;
+    memcpy(vectors + (size_t)i * md, dst.slices[i]->norm_vector, (size_t)md * sizeof(long double));
+  }
+  linear_distribution_clear(&dst);
+  return n;
+}
+
 /* Overwrite the distribution's total_probability (to exercise the "> 1" branch of
  * distribution_sample_slice, src/distribution.cpp:373-381). */
 void qref_dist_set_total(void *hh, long double total) {

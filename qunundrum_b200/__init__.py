@@ -54,6 +54,10 @@ from .host import (  # noqa: F401
     WordStream,
     tau_estimate,
     tau_estimate_linear,
+    # the server's work on a finished distribution
+    Resident,
+    linear_distribution_init_collapse_d,
+    linear_distribution_init_collapse_r,
     # the diagonal distribution's k given (j, eta) (second half)
     DiagonalKSampler,
     int_to_limbs,

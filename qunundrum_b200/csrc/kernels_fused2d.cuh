@@ -800,11 +800,10 @@ inline cudaError_t fused2d_launch_variant(const FusedPlan2D& f, const FusedArgs&
 #define QB_LAUNCH(E, M2, B)                                                                   \
   {                                                                                           \
     auto kern = k_fused2d<MODE, CLS, E, M2, B>;                                               \
-    static bool once = false;                                                                 \
-    if (!once) {                                                                              \
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);       \
-      once = true;                                                                            \
-    }                                                                                         \
+    /* per device, not per process: set before every launch (a host-side table write) */      \
+    const cudaError_t ea = cudaFuncSetAttribute(                                              \
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                          \
+    if (ea != cudaSuccess) return ea;                                                         \
     kern<<<g, b, sm, st>>>(args);                                                             \
   }
   switch (v) {

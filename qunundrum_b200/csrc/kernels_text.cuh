@@ -334,7 +334,10 @@ __global__ void __launch_bounds__(TB)
   uint64_t mant = 0;
   uint32_t se = 0;
   int q = 0;
-  if (i < n) {
+  // starts[] is written for the tokens the tokenizer found only (same stream, earlier):
+  // a truncated file leaves the tail of starts[] undefined, so those threads stay out
+  const unsigned long long found = info[INFO_TOKENS];
+  if (i < n && i < found && starts[i] < len) {
     const unsigned long long b = starts[i];
     int tlen = 0;
     uint32_t st = parse_number(text + b, (long)(len - b), &dec, &tlen);

@@ -13,6 +13,8 @@
 
 #include "../../include/qunundrum_b200.h"
 #include "ctx_access.hpp"
+#include "kernels_client.cuh"
+#include "kernels_fused1d.cuh"
 #include "kernels_fused2d.cuh"
 #include "kernels_plain.cuh"
 #include "kernels_sigma_opt.cuh"
@@ -105,7 +107,7 @@ struct qb200_context {
   uint64_t launches = 0;
   std::map<int, std::unique_ptr<DevGeometry>> geo;
   // staging for the synchronous host API
-  DevBuf out_cells, out_summary;
+  DevBuf out_cells, out_summary, out_scaled, out_status;
   void* h_summary = nullptr;
   size_t h_summary_bytes = 0;
   qb200::TextState* text = nullptr;  // text exporter / importer state (qb200_text.cu)
@@ -129,13 +131,16 @@ struct qb200_plan {
   // fused path
   FusedPlan2D fused;
   DevBuf fused_part, fused_cols, fused_slices;
+  // fused one-dimensional path: per-block partials and per-slice tickets
+  DevBuf f1d_part, f1d_tickets;
+  bool f1d_ready = false;
   // sigma-optimal scratch
   DevBuf so_sigma, so_guess, so_norm, so_erra, so_sigma0, so_status, so_changed;
   void bind_pool(Pool* pool) {
     DevBuf* all[] = {&desc_a, &desc_b, &slices, &tab_a, &tab_b, &cells_c, &cells_f, &part_c,
                      &part_f, &part_tp, &values, &fused_part, &fused_cols, &fused_slices,
                      &so_sigma, &so_guess, &so_norm, &so_erra, &so_sigma0, &so_status,
-                     &so_changed};
+                     &so_changed, &f1d_part, &f1d_tickets};
     for (DevBuf* b : all) b->pool = pool;
   }
 };
@@ -407,6 +412,34 @@ int run_plain_1d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_sum
   return 0;
 }
 
+// All slices of the batch in one launch (kernels_fused1d.cuh); grid.y carries the slices, so
+// batches beyond 65535 slices take one launch per 65535.
+int run_fused_1d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_summary) {
+  const Plan& h = pl->host;
+  qb200_context* ctx = pl->ctx;
+  if (pl->n == 0) return 0;
+  const int D = h.D;
+  const unsigned nb = (unsigned)((D + QB_F1D_BLOCK - 1) / QB_F1D_BLOCK);
+  if (!pl->f1d_ready) {
+    if (int rc = pl->f1d_part.reserve((size_t)pl->n * nb * 2 * sizeof(double))) return rc;
+    if (int rc = pl->f1d_tickets.reserve((size_t)pl->n * sizeof(unsigned int))) return rc;
+    // zeroed once: the kernel leaves every ticket at zero again
+    QB_CUDA(cudaMemsetAsync(pl->f1d_tickets.p, 0, (size_t)pl->n * sizeof(unsigned int), st));
+    pl->f1d_ready = true;
+  }
+  for (uint32_t s0 = 0; s0 < pl->n; s0 += 65535) {
+    const uint32_t ns = std::min<uint32_t>(65535, pl->n - s0);
+    k_fused1d<<<dim3(nb, ns), QB_F1D_BLOCK, 0, st>>>(
+        h.c, h.kind, D, h.richardson, pl->slices.as<DevSlice>() + s0, pl->desc_a.as<TabDesc>(),
+        pl->geo->gx.as<dd>(), pl->geo->gw.as<double>(), d_cells + (size_t)s0 * D,
+        pl->f1d_part.as<double>() + (size_t)s0 * nb * 2, pl->f1d_tickets.as<unsigned int>() + s0,
+        d_summary + (size_t)s0 * QB200_SUMMARY_STRIDE);
+    ctx->launches++;
+  }
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 uint32_t plain_chunk(const qb200_plan* pl) {
   const Plan& h = pl->host;
   const size_t D = (size_t)h.D;
@@ -491,7 +524,7 @@ int finish_common(qb200_plan* pl, unsigned n_chunks = 1, bool same_stream = fals
   // uploads above are asynchronous on the context stream from pageable vectors owned by
   // the plan (or already consumed): make them visible to any stream the caller runs on
   if (!same_stream) QB_CUDA(cudaStreamSynchronize(pl->ctx->stream));
-  pl->algo = pl->fused_ok ? 2 : 1;
+  pl->algo = (pl->fused_ok || pl->host.kind >= 0) ? 2 : 1;
   return 0;
 }
 
@@ -614,11 +647,17 @@ uint64_t qb200_plan_cells(const qb200_plan* plan) {
 }
 
 uint32_t qb200_plan_launches(const qb200_plan* plan) {
+  if (plan->host.kind >= 0 && plan->algo == 2) return (plan->n + 65534) / 65535;
   if (plan->algo == 2) return fused2d_launches(plan->fused);
   return plain_launches(plan);
 }
 
 int qb200_plan_set_algorithm(qb200_plan* plan, int algo) {
+  if (plan->host.kind >= 0) {  // one-dimensional: 2 = the single-launch kernel (default)
+    if (algo < 0 || algo > 2) return fail(-21, "unknown algorithm");
+    plan->algo = algo == 1 ? 1 : 2;
+    return 0;
+  }
   if (algo == 0) {
     plan->algo = plan->fused_ok ? 2 : 1;
     return 0;
@@ -641,7 +680,9 @@ int qb200_plan_run(qb200_plan* plan, void* stream, double* d_cells, double* d_su
   qb200_context* ctx = plan->ctx;
   QB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  if (plan->host.kind >= 0) return run_plain_1d(plan, st, d_cells, d_summary);
+  if (plan->host.kind >= 0)
+    return plan->algo == 2 ? run_fused_1d(plan, st, d_cells, d_summary)
+                           : run_plain_1d(plan, st, d_cells, d_summary);
   if (plan->algo == 2) {
     if (plan->n == 0) return 0;
     if (int rc = enqueue_fused_prologue(plan, st)) return rc;
@@ -679,6 +720,14 @@ int qb200_plan_finish(const qb200_plan* plan, const double* hs, long double* tp,
     }
   }
   return 0;
+}
+
+// Error paths: nothing of a failed call may still be in flight when its plan hands its
+// buffers back to the pool (the sticky error, if any, is already in g_err).
+static void drain(qb200_context* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaGetLastError();
 }
 
 static int run_sync(qb200_context* ctx, qb200_plan* pl, double* cells, long double* tp,
@@ -746,6 +795,69 @@ int qb200_slice2d_compute(qb200_context* ctx, const qb200_params* params, int me
                              /*same_stream=*/true))
     return rc;
   const int rc = run_sync(ctx, pl, cells, tp, te, flags);
+  if (rc) drain(ctx);  // enqueued work may still use the plan's pooled buffers
+  qb200_plan_destroy(pl);
+  return rc;
+}
+
+int qb200_slice2d_compute_scaled(qb200_context* ctx, const qb200_params* params, int method,
+                                 int richardson, uint32_t dimension, uint32_t store_dimension,
+                                 uint32_t n, const int32_t* a_d, const int32_t* a_r,
+                                 long double* cells, long double* tp, long double* te,
+                                 uint32_t* flags) {
+  if (!ctx || !params) return fail(-1, "null argument");
+  if (store_dimension == 0 || dimension % store_dimension != 0)
+    return fail(-12, "distribution_slice_copy_scale(): Incompatible dimensions.");
+  QB_CUDA(cudaSetDevice(ctx->device));
+  qb200_plan* pl = nullptr;
+  if (int rc = create_plan2d(ctx, params, method, richardson, dimension, n, a_d, a_r, 1, &pl,
+                             /*same_stream=*/true))
+    return rc;
+  int rc = 0;
+  do {
+    const uint64_t ncells = qb200_plan_cells(pl);
+    const size_t per = (size_t)store_dimension * store_dimension;
+    const size_t sum_bytes = (size_t)n * QB200_SUMMARY_STRIDE * sizeof(double);
+    if ((rc = ctx->out_cells.reserve(std::max<size_t>(8, ncells * sizeof(double))))) break;
+    if ((rc = ctx->out_summary.reserve(std::max<size_t>(8, sum_bytes)))) break;
+    if ((rc = ctx->out_scaled.reserve(std::max<size_t>(16, (size_t)n * per * 16)))) break;
+    if ((rc = ctx->out_status.reserve(sizeof(int)))) break;
+    std::vector<double> hs((size_t)n * QB200_SUMMARY_STRIDE);
+    int status = 0;
+    rc = -100;
+    g_err = "qb200_slice2d_compute_scaled: CUDA error";
+    if (cudaMemsetAsync(ctx->out_status.p, 0, sizeof(int), ctx->stream) != cudaSuccess) break;
+    if (int r2 = qb200_plan_run(pl, ctx->stream, ctx->out_cells.as<double>(), ctx->out_summary.as<double>())) {
+      rc = r2;
+      break;
+    }
+    // distribution_slice_copy_scale on the device: the scaled cells leave as x87 long doubles
+    for (uint32_t s0 = 0; s0 < n; s0 += 65535) {
+      const uint32_t ns = std::min<uint32_t>(65535, n - s0);
+      k_scale_x87<<<dim3((unsigned)((per + 255) / 256), ns), 256, 0, ctx->stream>>>(
+          (int)dimension, (int)store_dimension,
+          ctx->out_cells.as<double>() + (size_t)s0 * dimension * dimension,
+          ctx->out_scaled.as<ulonglong2>() + (size_t)s0 * per, ctx->out_status.as<int>());
+      ctx->launches++;
+    }
+    if (cudaGetLastError() != cudaSuccess) break;
+    if (n && cudaMemcpyAsync(cells, ctx->out_scaled.p, (size_t)n * per * 16, cudaMemcpyDeviceToHost,
+                             ctx->stream) != cudaSuccess)
+      break;
+    if (n && cudaMemcpyAsync(hs.data(), ctx->out_summary.p, sum_bytes, cudaMemcpyDeviceToHost,
+                             ctx->stream) != cudaSuccess)
+      break;
+    if (cudaMemcpyAsync(&status, ctx->out_status.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) !=
+        cudaSuccess)
+      break;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) break;
+    if (status) {
+      rc = fail(-4, "copy_scale: a scaled cell is below the normal long double range");
+      break;
+    }
+    rc = qb200_plan_finish(pl, hs.data(), tp, te, flags);
+  } while (0);
+  if (rc) drain(ctx);
   qb200_plan_destroy(pl);
   return rc;
 }
@@ -757,6 +869,7 @@ int qb200_slice1d_compute(qb200_context* ctx, const qb200_params* params, int ki
   if (int rc = qb200_plan1d_create(ctx, params, kind, richardson, dimension, n, a, eta, &pl))
     return rc;
   const int rc = run_sync(ctx, pl, cells, tp, nullptr, flags);
+  if (rc) drain(ctx);
   qb200_plan_destroy(pl);
   return rc;
 }

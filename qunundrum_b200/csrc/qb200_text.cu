@@ -141,6 +141,8 @@ int enqueue_format(const CtxView& view, TextState* st, int kind, const void* d_v
   QT_CUDA(cudaMemsetAsync(st->d_status.p, 0, st_bytes, stream));
   unsigned long long* status = (unsigned long long*)st->d_status.p;
   unsigned int* ticket = (unsigned int*)(status + n_tiles);
+  // the exact-path counter is per call (qb200_text_exact_count: "of the last call")
+  QT_CUDA(cudaMemsetAsync(st->d_scalars + 1, 0, sizeof(unsigned long long), stream));
   if (kind == QB200_TEXT_X87)
     k_text_format<SRC_X87><<<(unsigned)n_tiles, TEXT_THREADS, 0, stream>>>(
         d_values, n, st->d_tab, (unsigned char*)d_text, cap, status, ticket, d_len,

@@ -216,6 +216,51 @@ QHD X87 x87_add(X87 a, X87 b) {
   return r;
 }
 
+// (long double)v for a finite double, exact (53 <= 64 bits; denormal doubles are normalised).
+QHD X87 x87_from_double(double v) {
+  X87 r = x87_zero();
+  uint64_t b;
+#if defined(__CUDA_ARCH__)
+  b = (uint64_t)__double_as_longlong(v);
+#else
+  memcpy(&b, &v, 8);
+#endif
+  const int e = (int)((b >> 52) & 0x7ff);
+  uint64_t f = b & 0xfffffffffffffull;
+  if (e == 0) {
+    if (f == 0) return r;
+    const int lz = qb_clz64(f);       // denormal: value = f 2^-1074
+    r.mant = f << lz;
+    r.exp = -1074 + 63 - lz;
+  } else {
+    r.mant = (f | (1ull << 52)) << 11;
+    r.exp = e - 1023;
+  }
+  r.neg = (int32_t)(b >> 63);
+  return r;
+}
+
+// The 16 bytes of the x86-64 long double (mantissa word, then sign and biased exponent).
+// Results below the normal range (|x| < 2^-16382) are not represented by X87: *ok = false.
+QHD void x87_encode(X87 a, uint64_t* mant, uint64_t* sign_exp, bool* ok) {
+  if (a.mant == 0) {
+    *mant = 0;
+    *sign_exp = 0;
+    return;
+  }
+  const int e = a.exp + 16383;
+  if (e < 1 || e > 0x7ffe) *ok = false;
+  *mant = a.mant;
+  *sign_exp = (uint64_t)((uint32_t)(e & 0x7fff) | (a.neg ? 0x8000u : 0u));
+}
+
+// a / 2^k, k >= 0 (the divisions by the power-of-two `divisor` of
+// src/linear_distribution.cpp:224-227: exact while the result stays normal).
+QHD X87 x87_div_pow2(X87 a, int k) {
+  if (a.mant) a.exp -= k;
+  return a;
+}
+
 // Exact double-double image (64 <= 106 bits); magnitudes below 2^-959 flush to zero, which
 // the sampler's error band covers.
 QHD double qb_bits_to_double(uint64_t b) {

@@ -6,8 +6,8 @@ and -- only because this image lacks libgmp-dev -- the declaration shim
 integration/shims/gmp.h. Output: qunundrum_b200/dropin/libqunundrum_dropin.so, which
 exports the six C++ entry points of the reference with their mangled names and
 depends on ../libqunundrum_b200.so and libgmp. It also compiles the reference's
-src/errors.c (critical()) and generator (src/random.c, src/keccak*.c) in place so that the
-test library is self-contained.
+src/errors.c (critical()), generator (src/random.c, src/keccak*.c) and slice enumerators
+(src/*_enumerator.cpp, src/math.cpp) in place so that the test library is self-contained.
 """
 from __future__ import annotations
 
@@ -37,6 +37,15 @@ def build(reference_root: str = "/root/reference", force: bool = False) -> str |
         o = os.path.join(HERE, f"_{f}.o")
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-w", "-I", os.path.join(ROOT, "integration", "shims"),
                                "-iquote", src, "-c", os.path.join(src, f + ".c"), "-o", o])
+        objs.append(o)
+    # ... and its enumerators (the drop-in asks them which slices a generator will request)
+    inc = ["-I", os.path.join(ROOT, "integration", "shims"), "-I", os.path.join(ROOT, "integration", "minimpi"),
+           "-I", os.path.join(ROOT, "integration", "stubs"), "-iquote", src]
+    for f in ("distribution_enumerator", "linear_distribution_enumerator", "diagonal_distribution_enumerator",
+              "math"):
+        o = os.path.join(HERE, f"_{f}.o")
+        subprocess.check_call(["g++", "-std=c++11", "-O2", "-fPIC", "-w", "-include", "cmath", *inc, "-c",
+                               os.path.join(src, f + ".cpp"), "-o", o])
         objs.append(o)
     subprocess.check_call(
         ["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-w",

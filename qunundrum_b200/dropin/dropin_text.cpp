@@ -41,6 +41,12 @@
 
 #include "qunundrum_b200.h"
 
+// dropin_collapse.cpp, when linked in: the text of a slice whose cells already lie in device
+// memory (uploaded once for the collapse to the marginals), formatted ahead a few dozen slices per
+// synchronisation. Weak: the text drop-in also works on its own.
+bool qb200_dropin_resident_text(const long double* cells, size_t n, long double tail, const char** text,
+                                size_t* len) __attribute__((weak));
+
 namespace {
 
 qb200_context* g_text_ctx = NULL;
@@ -92,7 +98,8 @@ void export_values(FILE* const file, const long double* const values, const size
   size_t len = 0;
   qb200_context* const ctx = text_context();
   const double t0 = g_tstats.on ? tnow() : 0.0;
-  if (0 != qb200_text_format_ld(ctx, values, n, &total_error, &text, &len)) {
+  if (!(qb200_dropin_resident_text && qb200_dropin_resident_text(values, n, total_error, &text, &len)) &&
+      0 != qb200_text_format_ld(ctx, values, n, &total_error, &text, &len)) {
     critical("%s(): %s", who, qb200_last_error());
   }
   const double t1 = g_tstats.on ? tnow() : 0.0;
@@ -188,6 +195,10 @@ void import_common_diagonal(Diagonal_Distribution_Slice* const slice, FILE* cons
 }
 
 }  // namespace
+
+// Shared with dropin_collapse.cpp: one context and one lock for everything the server does.
+qb200_context* qb200_dropin_text_context() { return text_context(); }
+std::mutex& qb200_dropin_text_mutex() { return g_text_mutex; }
 
 /* ---- two-dimensional slices (src/distribution_slice_import_export.cpp) ---------- */
 

@@ -144,6 +144,14 @@ def lib():
     L.qb200_diagk_tau_estimate.argtypes = [vp, u32, u32, vp, vp, vp, u32, u32, vp, vp]
     L.qb200_diagk_h.argtypes = [vp, u32, vp, vp, vp]
     L.qb200_diagk_set_force_exact.argtypes = [vp, C.c_int]
+    L.qb200_slice2d_compute_scaled.argtypes = [vp, PP, C.c_int, C.c_int, u32, u32, u32, i32p, i32p,
+                                               vp, vp, vp, vp]
+    L.qb200_resident_create.argtypes = [vp, u32, vp, vp, vp, C.POINTER(vp)]
+    L.qb200_resident_destroy.argtypes = [vp]
+    L.qb200_resident_cells.argtypes = [vp]
+    L.qb200_resident_cells.restype = C.c_uint64
+    L.qb200_resident_collapse2d.argtypes = [vp, C.c_int, vp, u32, vp, vp, u32, vp]
+    L.qb200_resident_format.argtypes = [vp, u32, u32, C.POINTER(vp), vp]
     _lib = L
     return L
 
@@ -381,6 +389,25 @@ class Context:
             self.h, C.byref(p), method, int(bool(richardson)), dimension, n,
             a_d.ctypes.data, a_r.ctypes.data, cells.ctypes.data, tp.ctypes.data,
             te.ctypes.data, fl.ctypes.data), "qb200_slice2d_compute")
+        return cells, tp, te, fl
+
+    def slice2d_batch_scaled(self, params: Parameters, method: int, richardson: bool, dimension: int,
+                             store_dimension: int, min_log_alpha_d, min_log_alpha_r):
+        """Slices computed at `dimension` and scaled to `store_dimension` on the device as
+        distribution_slice_copy_scale does (src/distribution_slice.cpp:230-264): long double cells."""
+        a_d, a_r = _i32(min_log_alpha_d), _i32(min_log_alpha_r)
+        n = len(a_d)
+        if len(a_r) != n:
+            raise CriticalError("coordinate arrays differ in length")
+        cells = np.zeros((n, store_dimension * store_dimension), dtype=np.longdouble)
+        tp = np.zeros(n, dtype=np.longdouble)
+        te = np.zeros(n, dtype=np.longdouble)
+        fl = np.zeros(n, dtype=np.uint32)
+        p = params._c()
+        _check(lib().qb200_slice2d_compute_scaled(
+            self.h, C.byref(p), method, int(bool(richardson)), dimension, store_dimension, n,
+            a_d.ctypes.data, a_r.ctypes.data, cells.ctypes.data, tp.ctypes.data, te.ctypes.data,
+            fl.ctypes.data), "qb200_slice2d_compute_scaled")
         return cells, tp, te, fl
 
     def slice1d_batch(self, params, kind: int, richardson: bool, dimension: int,
@@ -728,6 +755,94 @@ class Distribution:
         """distribution_sort_slices (src/distribution.cpp:258-270): descending total probability.
         (qsort leaves the order of equal keys unspecified; this one is stable.)"""
         self.slices.sort(key=lambda s: -s.total_probability)
+
+
+class Resident:
+    """The cells of a stored two-dimensional distribution in device memory (qb200_resident):
+    uploaded once, collapsed to both marginals and exported from there."""
+
+    def __init__(self, slices, ctx: "Context" = None):
+        self.ctx = ctx or default_context()
+        self.slices = list(slices)
+        self._keep = [np.ascontiguousarray(s.norm_matrix, dtype=np.longdouble) for s in self.slices]
+        n = len(self.slices)
+        n_cells = np.array([a.size for a in self._keep], dtype=np.uint64)
+        ptrs = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in self._keep])
+        tails = np.array([s.total_error for s in self.slices], dtype=np.longdouble)
+        self.h = C.c_void_p()
+        _check(lib().qb200_resident_create(self.ctx.h, n, n_cells.ctypes.data, ptrs, tails.ctypes.data,
+                                           C.byref(self.h)), "qb200_resident_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().qb200_resident_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def collapse(self, axis: int):
+        """(coordinates, vectors [n_dst, max_dimension], totals): the destination slices in the order
+        linear_distribution_init_collapse_d (axis 0) / _r (axis 1) creates them."""
+        dims = np.array([s.dimension for s in self.slices], dtype=np.uint32)
+        if len(dims) == 0:
+            return np.zeros(0, dtype=np.int32), np.zeros((0, 0), dtype=np.longdouble), np.zeros(0, dtype=np.longdouble)
+        md = int(dims.max())
+        order, members, totals = [], {}, {}
+        for i, s in enumerate(self.slices):
+            c = int(s.min_log_alpha_d if axis == 0 else s.min_log_alpha_r)
+            if c not in members:
+                members[c] = []
+                totals[c] = np.longdouble(0)
+                order.append(c)
+            members[c].append(i)
+            totals[c] = totals[c] + np.longdouble(s.total_probability)
+        begin = np.zeros(len(order) + 1, dtype=np.uint32)
+        lst = []
+        for j, c in enumerate(order):
+            lst += members[c]
+            begin[j + 1] = len(lst)
+        lst = np.array(lst, dtype=np.uint32)
+        out = np.zeros((len(order), md), dtype=np.longdouble)
+        _check(lib().qb200_resident_collapse2d(self.h, axis, dims.ctypes.data, len(order), begin.ctypes.data,
+                                               lst.ctypes.data, md, out.ctypes.data), "qb200_resident_collapse2d")
+        return np.array(order, dtype=np.int32), out, np.array([totals[c] for c in order], dtype=np.longdouble)
+
+    def format(self, first: int, count: int):
+        """The "%.24Lg\\n" text of the slices [first, first + count): a list of bytes objects."""
+        text = C.c_void_p()
+        offsets = np.zeros(count + 1, dtype=np.uint64)
+        _check(lib().qb200_resident_format(self.h, first, count, C.byref(text), offsets.ctypes.data),
+               "qb200_resident_format")
+        return [C.string_at(text.value + int(offsets[i]), int(offsets[i + 1] - offsets[i])) for i in range(count)]
+
+
+def linear_distribution_init_collapse_d(distribution, ctx=None):
+    """linear_distribution_init_collapse_d (src/linear_distribution.cpp:152-237) on the device."""
+    return _collapse(distribution, 0, ctx)
+
+
+def linear_distribution_init_collapse_r(distribution, ctx=None):
+    """linear_distribution_init_collapse_r (src/linear_distribution.cpp:239-324) on the device."""
+    return _collapse(distribution, 1, ctx)
+
+
+def _collapse(distribution, axis, ctx):
+    res = Resident(distribution.slices, ctx)
+    try:
+        coords, vec, tot = res.collapse(axis)
+    finally:
+        res.close()
+    out = Linear_Distribution(distribution.m)
+    for k in range(len(coords)):
+        sl = Linear_Distribution_Slice(vec.shape[1], int(coords[k]), norm_vector=vec[k].copy())
+        sl.total_probability = tot[k]
+        out.insert_slice(sl)
+    out.total_probability = distribution.total_probability
+    return out
 
 
 @dataclass

@@ -19,7 +19,7 @@ _SRCS = [os.path.join(_HERE, "hostsim.cpp"),
 _DEPS = _SRCS + [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
                  ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "sigma_opt.cuh", "plan.hpp",
                   "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "textparse.cuh", "text_tables.hpp",
-                  "sampler.cuh", "x87soft.cuh", "diagk.cuh", "diagk_host.hpp")]
+                  "sampler.cuh", "x87soft.cuh", "diagk.cuh", "diagk_host.hpp", "client_math.cuh")]
 _lib = None
 
 
@@ -283,4 +283,41 @@ def diagk_h(l, x):
     out = np.zeros(len(x), dtype=np.longdouble)
     lib().hostsim_diagk_h(C.c_uint32(l), C.c_uint32(len(x)), x.ctypes.data_as(C.c_void_p),
                           out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+# ---- generator client / server tail (client_math.cuh) -------------------------------------------
+
+def x87_div_u32(a, q: int):
+    a = np.array([a], dtype=np.longdouble)
+    out = np.zeros(1, dtype=np.longdouble)
+    ok = lib().hostsim_x87_div_u32(a.ctypes.data_as(C.c_void_p), C.c_uint32(q), out.ctypes.data_as(C.c_void_p))
+    return out[0] if ok else None
+
+
+def x87_from_double(v: float):
+    out = np.zeros(1, dtype=np.longdouble)
+    lib().hostsim_x87_from_double(C.c_double(v), out.ctypes.data_as(C.c_void_p))
+    return out[0]
+
+
+def copy_scale(cells, D: int, store: int):
+    """distribution_slice_copy_scale as kernels_client.cuh computes it (D x D doubles in)."""
+    src = np.ascontiguousarray(cells, dtype=np.float64)
+    assert src.size == D * D
+    out = np.zeros(store * store, dtype=np.longdouble)
+    ok = lib().hostsim_copy_scale(D, store, src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert ok
+    return out
+
+
+def collapse(axis: int, max_dim: int, slices):
+    """One destination vector: `slices` = the source slices' cells (long double, D x D) in order."""
+    arrs = [np.ascontiguousarray(s, dtype=np.longdouble) for s in slices]
+    dims = np.array([int(round(a.size ** 0.5)) for a in arrs], dtype=np.uint32)
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    out = np.zeros(max_dim, dtype=np.longdouble)
+    ok = lib().hostsim_collapse(axis, C.c_uint32(max_dim), C.c_uint32(len(arrs)), dims.ctypes.data_as(C.c_void_p),
+                                ptrs, out.ctypes.data_as(C.c_void_p))
+    assert ok
     return out

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../qunundrum_b200/csrc/plan.hpp"
+#include "../../qunundrum_b200/csrc/client_math.cuh"
 #include "../../qunundrum_b200/csrc/sampler.cuh"
 
 using namespace qb200;
@@ -607,6 +608,66 @@ void hostsim_diagk_h(uint32_t l, uint32_t n, const double* x, long double* out) 
     const dd st = sinpi_acc(t);
     store_x87(x87_from_dd(diagk_h(l, dd_mul(st, st), xi)), &out[i]);
   }
+}
+
+
+// ---- generator client / server tail (client_math.cuh) -------------------------------------------
+
+static void store_raw(X87 r, long double* out, bool* ok) {
+  uint64_t m = 0, se = 0;
+  x87_encode(r, &m, &se, ok);
+  memset(out, 0, 16);
+  memcpy(out, &m, 8);
+  const uint16_t s16 = (uint16_t)se;
+  memcpy((char*)out + 8, &s16, 2);
+}
+
+// (long double)a / (long double)q as the kernels compute it; returns 0 if not representable.
+int hostsim_x87_div_u32(const long double* a, uint32_t q, long double* out) {
+  uint64_t m = 0;
+  uint16_t se = 0;
+  memcpy(&m, a, 8);
+  memcpy(&se, (const char*)a + 8, 2);
+  bool ok = true;
+  const X87 r = x87_div_u32(x87_load(m, se, &ok), q);
+  store_raw(r, out, &ok);
+  return ok ? 1 : 0;
+}
+
+int hostsim_x87_from_double(double v, long double* out) {
+  bool ok = true;
+  store_raw(x87_from_double(v), out, &ok);
+  return ok ? 1 : 0;
+}
+
+// distribution_slice_copy_scale: src D x D doubles -> out store x store long doubles.
+int hostsim_copy_scale(int D, int store, const double* src, long double* out) {
+  bool ok = true;
+  for (int idx = 0; idx < store * store; idx++) store_raw(scale_cell_x87(src, D, store, idx), out + idx, &ok);
+  return ok ? 1 : 0;
+}
+
+// One destination vector of linear_distribution_init_collapse_d (axis 0) / _r (axis 1): the
+// source slices in order, dims[i] x dims[i] long doubles each.
+int hostsim_collapse(int axis, uint32_t max_dim, uint32_t n_src, const uint32_t* dims,
+                     const long double* const* cells, long double* out) {
+  bool ok = true;
+  for (uint32_t e = 0; e < max_dim; e++) {
+    X87 acc = x87_zero();
+    for (uint32_t s = 0; s < n_src; s++) {
+      const uint32_t D = dims[s], q = max_dim / D;
+      for (uint32_t k = 0; k < D; k++) {
+        const size_t at = axis == 0 ? (size_t)(e / q) + (size_t)k * D : (size_t)k + (size_t)(e / q) * D;
+        uint64_t m = 0;
+        uint16_t se = 0;
+        memcpy(&m, cells[s] + at, 8);
+        memcpy(&se, (const char*)(cells[s] + at) + 8, 2);
+        acc = collapse_step(acc, m, se, q, &ok);
+      }
+    }
+    store_raw(acc, out + e, &ok);
+  }
+  return ok ? 1 : 0;
 }
 
 }  // extern "C"

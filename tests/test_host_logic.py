@@ -25,7 +25,7 @@ def test_library_is_built_and_exports_the_declared_abi():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/qunundrum_b200.h but not exported"
-    assert L.qb200_version() == 1
+    assert L.qb200_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device():
