@@ -63,6 +63,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <map>
 #include <utility>
@@ -93,15 +94,17 @@ double now_s() {
 }
 
 void print_stats() {
-  if (g_stats.on && g_stats.calls)
-    fprintf(stderr,
-            "qunundrum_b200 drop-in: %lu slice calls, %.3f s inside the drop-in functions (%.1f us per "
-            "call); %lu C-ABI calls for %lu slices (%.1f slices per call, %.3f s), %lu calls served from "
-            "the prefetched batch\n",
-            g_stats.calls, g_stats.seconds, 1e6 * g_stats.seconds / (double)g_stats.calls,
-            g_stats.abi_calls, g_stats.abi_slices,
-            g_stats.abi_calls ? (double)g_stats.abi_slices / (double)g_stats.abi_calls : 0.0,
-            g_stats.abi_seconds, g_stats.hits);
+  if (!(g_stats.on && g_stats.calls)) return;
+  char line[768];   // one write(): the ranks of a farm share stderr
+  const int len = snprintf(
+      line, sizeof line,
+      "qunundrum_b200 drop-in: %lu slice calls, %.3f s inside the drop-in functions (%.1f us per "
+      "call); %lu C-ABI calls for %lu slices (%.1f slices per call, %.3f s), %lu calls served from "
+      "prefetched batches\n",
+      g_stats.calls, g_stats.seconds, 1e6 * g_stats.seconds / (double)g_stats.calls, g_stats.abi_calls,
+      g_stats.abi_slices, g_stats.abi_calls ? (double)g_stats.abi_slices / (double)g_stats.abi_calls : 0.0,
+      g_stats.abi_seconds, g_stats.hits);
+  if (len > 0) (void)!write(2, line, (size_t)(len < (int)sizeof line ? len : (int)sizeof line - 1));
 }
 
 struct Timed {
@@ -234,12 +237,14 @@ struct Cache {
   bool valid;
   Identity id;
   std::vector<Coord> list;            // everything the enumerator hands out, in its order
-  std::map<uint32_t, Batch*> batches;  // by dimension
+  std::map<uint32_t, std::vector<Batch*> > batches;  // by dimension
   Cache() : valid(false) {}
   void clear() {
-    for (std::map<uint32_t, Batch*>::iterator it = batches.begin(); it != batches.end(); ++it) {
-      qb200_host_free(it->second->cells);
-      delete it->second;
+    for (std::map<uint32_t, std::vector<Batch*> >::iterator it = batches.begin(); it != batches.end(); ++it) {
+      for (size_t k = 0; k < it->second.size(); k++) {
+        qb200_host_free(it->second[k]->cells);
+        delete it->second[k];
+      }
     }
     batches.clear();
     list.clear();
@@ -311,8 +316,19 @@ Batch* compute_batch_2d(const Exported& e, int method, int richardson, uint32_t 
   return b;
 }
 
-// Cells, total error and flag bits of one two-dimensional slice: from the prefetched batch of
-// its dimension, creating that batch (or, for a coordinate outside it, a batch of one) first.
+const Batch* find_batch(const std::vector<Batch*>& bs, const Coord& c, uint32_t* at) {
+  for (size_t k = 0; k < bs.size(); k++) {
+    std::map<Coord, uint32_t>::const_iterator f = bs[k]->index.find(c);
+    if (f != bs[k]->index.end()) {
+      *at = f->second;
+      return bs[k];
+    }
+  }
+  return NULL;
+}
+
+// Cells, total error and flag bits of one two-dimensional slice: from a prefetched batch of its
+// dimension, computing one first if no batch holds the coordinate.
 void lookup_2d(const Exported& e, const Parameters* const parameters, int method, int richardson,
                uint32_t dimension, const Coord& c, const char* who, const double** cells,
                long double* te, uint32_t* flags, std::vector<double>* scratch) {
@@ -329,44 +345,65 @@ void lookup_2d(const Exported& e, const Parameters* const parameters, int method
       distribution_enumerator_clear(&en);
       C.valid = true;
     }
-    std::map<uint32_t, Batch*>::iterator it = C.batches.find(dimension);
-    if (it == C.batches.end()) {
-      // the first call at this dimension: everything the client may still ask for at it
-      const uint32_t base = C.batches.empty() ? dimension : C.batches.begin()->first;
-      const Batch* lower = C.batches.empty() ? NULL : C.batches.begin()->second;
+    std::vector<Batch*>& here = C.batches[dimension];
+    uint32_t at = 0;
+    const Batch* hit = find_batch(here, c, &at);
+    if (NULL == hit) {
+      // Everything the client may still ask for at this dimension, in one call. `base` is the
+      // client's initial dimension: the smallest seen so far -- or, on the very first call, a
+      // guess from the coordinate (a tail coordinate starts at 512 / 1024 under the heuristic,
+      // src/main_generate_distribution.cpp:1226-1240); a wrong guess costs one more batch.
+      const int32_t m = (int32_t)parameters->m;
+      uint32_t base = dimension;
+      bool first_call = true;
+      for (std::map<uint32_t, std::vector<Batch*> >::const_iterator it = C.batches.begin();
+           it != C.batches.end(); ++it) {
+        if (!it->second.empty()) {
+          first_call = false;
+          if (it->first < base) base = it->first;
+        }
+      }
+      const bool again = !here.empty();  // this dimension was speculated on before and missed c
+      if (first_call) {
+        if (dimension % 4 == 0 && may_be_asked_at(dimension, dimension / 4, c, m, false, 0)) base = dimension / 4;
+        else if (dimension % 2 == 0 && may_be_asked_at(dimension, dimension / 2, c, m, false, 0)) base = dimension / 2;
+      }
+      const std::vector<Batch*>* lower = NULL;
+      if (base < dimension) {
+        std::map<uint32_t, std::vector<Batch*> >::const_iterator it = C.batches.find(base);
+        if (it != C.batches.end()) lower = &it->second;
+      }
       std::vector<Coord> want;
       bool listed = false;
       for (size_t i = 0; i < C.list.size(); i++) {
         const Coord& q = C.list[i];
+        uint32_t k = 0;
+        if (find_batch(here, q, &k)) continue;
         bool known = false;
         long double tp = 0;
-        if (lower) {
-          std::map<Coord, uint32_t>::const_iterator f = lower->index.find(q);
-          if (f != lower->index.end()) {
+        if (lower && !again) {
+          const Batch* lb = find_batch(*lower, q, &k);
+          if (lb) {
             known = true;
-            tp = lower->tp[f->second];
+            tp = lb->tp[k];
           }
         }
-        if (q == c || may_be_asked_at(dimension, base, q, (int32_t)parameters->m, known, tp)) {
+        if (q == c || may_be_asked_at(dimension, again ? dimension : base, q, m, known, tp)) {
           want.push_back(q);
           listed = listed || q == c;
         }
       }
       if (!listed) want.push_back(c);
-      C.batches[dimension] = compute_batch_2d(e, method, richardson, dimension, want, who);
-      it = C.batches.find(dimension);
+      here.push_back(compute_batch_2d(e, method, richardson, dimension, want, who));
+      hit = find_batch(here, c, &at);
     }
-    Batch* b = it->second;
-    std::map<Coord, uint32_t>::const_iterator f = b->index.find(c);
-    if (f != b->index.end()) {
-      *cells = b->cells + (size_t)f->second * b->per;
-      *te = b->te[f->second];
-      *flags = b->flags[f->second];
-      g_stats.hits++;
-      return;
-    }
+    g_stats.hits++;
+    *cells = hit->cells + (size_t)at * hit->per;
+    *te = hit->te[at];
+    *flags = hit->flags[at];
+    return;
   }
-  // one slice on its own (prefetch off, or a coordinate the speculation did not cover)
+  // one slice per call (QB200_PREFETCH=0)
   scratch->resize((size_t)dimension * dimension);
   long double tp = 0;
   TimedAbi timed(1);
@@ -430,11 +467,18 @@ void compute_1d(long double* const norm_vector, const uint32_t dimension, const 
       lister(lister_parameters, c, &C.list);
       C.valid = true;
     }
-    std::map<uint32_t, Batch*>::iterator it = C.batches.find(dimension);
-    if (it == C.batches.end()) {
-      std::vector<Coord> want(C.list);
+    std::vector<Batch*>& here = C.batches[dimension];
+    uint32_t at = 0;
+    const Batch* hit = find_batch(here, c, &at);
+    if (NULL == hit) {
+      std::vector<Coord> want;
       bool listed = false;
-      for (size_t i = 0; i < want.size(); i++) listed = listed || want[i] == c;
+      for (size_t i = 0; i < C.list.size(); i++) {
+        uint32_t k = 0;
+        if (find_batch(here, C.list[i], &k)) continue;
+        want.push_back(C.list[i]);
+        listed = listed || C.list[i] == c;
+      }
       if (!listed) want.push_back(c);
       Batch* b = new Batch;
       b->dimension = dimension;
@@ -457,16 +501,12 @@ void compute_1d(long double* const norm_vector, const uint32_t dimension, const 
           critical("%s(): %s", who, qb200_last_error());
         }
       }
-      C.batches[dimension] = b;
-      it = C.batches.find(dimension);
+      here.push_back(b);
+      hit = find_batch(here, c, &at);
     }
-    Batch* b = it->second;
-    std::map<Coord, uint32_t>::const_iterator f = b->index.find(c);
-    if (f != b->index.end()) {
-      cells = b->cells + (size_t)f->second * b->per;
-      *flags = b->flags[f->second];
-      g_stats.hits++;
-    }
+    g_stats.hits++;
+    cells = hit->cells + (size_t)at * hit->per;
+    *flags = hit->flags[at];
   }
   if (NULL == cells) {
     scratch.resize(dimension);

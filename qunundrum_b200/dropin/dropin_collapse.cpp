@@ -39,6 +39,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <map>
 #include <mutex>
@@ -82,11 +83,15 @@ struct Registry {
 
 void print_collapse_stats() {
   if (g_reg.stats)
-    fprintf(stderr,
+    {
+    char line[768];
+    const int len = snprintf(line, sizeof line,
             "qunundrum_b200 collapse drop-in: %lu uploads (%.3f s), %lu collapses (%.3f s), %lu export "
             "batches (%.3f s) serving %lu slice exports from the device copy\n",
             g_reg.uploads, g_reg.upload_s, g_reg.collapses, g_reg.collapse_s, g_reg.formats,
             g_reg.format_s, g_reg.text_hits);
+    if (len > 0) (void)!write(2, line, (size_t)(len < (int)sizeof line ? len : (int)sizeof line - 1));
+  }
 }
 
 bool mark_matches(const Mark& k, const long double* cells, uint64_t n, long double tail) {

@@ -30,11 +30,13 @@
 #include "errors.h"
 #include "linear_distribution_slice.h"
 
+#include <dirent.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <mutex>
 #include <vector>
@@ -67,10 +69,14 @@ double tnow() {
 
 void print_text_stats() {
   if (g_tstats.on && (g_tstats.exports || g_tstats.imports))
-    fprintf(stderr,
+    {
+    char line[768];
+    const int len = snprintf(line, sizeof line,
             "qunundrum_b200 text drop-in: %lu slice exports, %lu slice imports, %.3f s inside the C ABI, "
             "%.3f s in fwrite / fread\n",
             g_tstats.exports, g_tstats.imports, g_tstats.abi_s, g_tstats.io_s);
+    if (len > 0) (void)!write(2, line, (size_t)(len < (int)sizeof line ? len : (int)sizeof line - 1));
+  }
 }
 
 qb200_context* text_context() {
@@ -80,11 +86,29 @@ qb200_context* text_context() {
     g_tstats.on = true;
     atexit(print_text_stats);
   }
-  const int n = qb200_device_count();
-  if (n <= 0) critical("qunundrum_b200: no CUDA device (there is no CPU path).");
   const char* v = getenv("QB200_TEXT_DEVICE");
   if (!v || !*v) v = getenv("QB200_DEVICE");
   int device = (v && *v) ? atoi(v) : 0;
+  // As in dropin.cpp: a process that has not started CUDA yet makes only its own GPU visible
+  // (seconds of start-up per process on an 8-GPU node otherwise).
+  const char* vis = getenv("CUDA_VISIBLE_DEVICES");
+  const char* pin = getenv("QB200_PIN_VISIBLE");
+  if ((!vis || !*vis) && !(pin && *pin == '0')) {
+    int total = 0;
+    if (DIR* d = opendir("/proc/driver/nvidia/gpus")) {
+      while (struct dirent* e = readdir(d))
+        if (e->d_name[0] != '.') total++;
+      closedir(d);
+    }
+    if (total > 1) {
+      char buf[16];
+      snprintf(buf, sizeof buf, "%d", ((device % total) + total) % total);
+      setenv("CUDA_VISIBLE_DEVICES", buf, 1);
+      device = 0;
+    }
+  }
+  const int n = qb200_device_count();
+  if (n <= 0) critical("qunundrum_b200: no CUDA device (there is no CPU path).");
   device = ((device % n) + n) % n;
   if (0 != qb200_create(device, &g_text_ctx)) critical("qunundrum_b200: %s", qb200_last_error());
   return g_text_ctx;

@@ -10,7 +10,9 @@
 // It is NOT part of the product: nothing under qunundrum_b200/ references it, the
 // product library has no CPU path, and the "shim" flavour of the integration build is
 // used by tests/test_text_dropin_host_logic.py only.
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -238,6 +240,123 @@ int qb200_diagk_h(qb200_diagk* s, uint32_t n, const double* x_hi, const double* 
     x[2 * i + 1] = x_lo[i];
   }
   hostsim_diagk_h(s->l, n, x.data(), h);
+  return 0;
+}
+
+
+// ---- integrators and the resident distribution: HOST-LOGIC stand-ins -------------------------------
+// The slice integrators return SYNTHETIC cells here: a pure function of the coordinate, the
+// dimension and the cell index (no integration). That is all the host logic of dropin.cpp (batching
+// the enumerator list, serving one-slice calls from a batch, speculating on the dimension
+// heuristic's upgrades), dropin_collapse.cpp and the resident export of dropin_text.cpp needs to be
+// exercised inside the reference's own generator executables on a GPU-less machine
+// (tests/test_dropin_host_logic_cpu.py). The numbers mean nothing; the collapse and the text use
+// the real arithmetic (client_math.cuh / textfmt.cuh twins).
+
+int hostsim_collapse(int axis, uint32_t max_dim, uint32_t n_src, const uint32_t* dims,
+                     const long double* const* cells, long double* out);
+
+void* qb200_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void qb200_host_free(void* p) { free(p); }
+size_t qb200_text_bound(size_t n) { return 33 * n; }
+
+static uint64_t shim_mix(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+static double shim_cell(uint32_t m, int32_t a, int32_t b, uint32_t D, uint64_t idx, uint64_t cells) {
+  const int da = abs(abs(a) - (int)m), db = abs(abs(b) - (int)m);
+  const double base = ldexp(1e-3, -(da + db)) * (a < 0 ? 0.5 : 1.0);
+  const uint64_t h = shim_mix(((uint64_t)(uint32_t)a << 32) ^ (uint32_t)b ^ shim_mix(idx * 1315423911ull + D));
+  const double u = 0.5 + (double)(h >> 11) * (1.0 / 9007199254740992.0);
+  return (h & 63) == 0 ? -1e-3 * base * u / (double)cells : base * u / (double)cells;
+}
+
+int qb200_slice2d_compute(qb200_context*, const qb200_params* p, int, int richardson, uint32_t D, uint32_t n,
+                          const int32_t* a_d, const int32_t* a_r, double* cells, long double* tp,
+                          long double* te, uint32_t* flags) {
+  const uint64_t per = (uint64_t)D * D;
+  for (uint32_t i = 0; i < n; i++) {
+    long double t = 0;
+    for (uint64_t k = 0; k < per; k++) {
+      cells[i * per + k] = shim_cell(p->m, a_d[i], a_r[i], D, k, per);
+      t += cells[i * per + k];
+    }
+    if (tp) tp[i] = t;
+    if (te) te[i] = (long double)t * 1e-9L;
+    if (flags) flags[i] = QB200_FLAG_METHOD_SIMPSON | (richardson ? QB200_FLAG_METHOD_RICHARDSON : 0u);
+  }
+  return 0;
+}
+
+int qb200_slice1d_compute(qb200_context*, const qb200_params* p, int kind, int richardson, uint32_t D,
+                          uint32_t n, const int32_t* a, const int32_t* eta, double* cells, long double* tp,
+                          uint32_t* flags) {
+  for (uint32_t i = 0; i < n; i++) {
+    long double t = 0;
+    for (uint32_t k = 0; k < D; k++) {
+      cells[(size_t)i * D + k] = shim_cell(p->m, a[i], (int32_t)p->m + (eta ? eta[i] : 0) + kind, D, k, D);
+      t += cells[(size_t)i * D + k];
+    }
+    if (tp) tp[i] = t;
+    if (flags) flags[i] = QB200_FLAG_METHOD_SIMPSON | (richardson ? QB200_FLAG_METHOD_RICHARDSON : 0u);
+  }
+  return 0;
+}
+
+struct qb200_resident {
+  std::vector<std::vector<long double>> cells;
+  std::vector<long double> tails;
+  std::vector<char> text;
+};
+
+int qb200_resident_create(qb200_context*, uint32_t n, const uint64_t* n_cells, const long double* const* cells,
+                          const long double* tails, qb200_resident** out) {
+  qb200_resident* r = new qb200_resident;
+  for (uint32_t i = 0; i < n; i++) {
+    r->cells.emplace_back(cells[i], cells[i] + n_cells[i]);
+    r->tails.push_back(tails ? tails[i] : 0.0L);
+  }
+  *out = r;
+  return 0;
+}
+void qb200_resident_destroy(qb200_resident* r) { delete r; }
+
+int qb200_resident_collapse2d(qb200_resident* r, int axis, const uint32_t* dimension, uint32_t n_dst,
+                              const uint32_t* src_begin, const uint32_t* src_index, uint32_t max_dimension,
+                              long double* out) {
+  for (uint32_t k = 0; k < n_dst; k++) {
+    std::vector<uint32_t> dims;
+    std::vector<const long double*> ptrs;
+    for (uint32_t s = src_begin[k]; s < src_begin[k + 1]; s++) {
+      dims.push_back(dimension[src_index[s]]);
+      ptrs.push_back(r->cells[src_index[s]].data());
+    }
+    if (!hostsim_collapse(axis, max_dimension, (uint32_t)dims.size(), dims.data(), ptrs.data(),
+                          out + (size_t)k * max_dimension)) {
+      g_err = "collapse: value outside the normal long double range";
+      return -4;
+    }
+  }
+  return 0;
+}
+
+int qb200_resident_format(qb200_resident* r, uint32_t first, uint32_t count, const char** text, size_t* offsets) {
+  size_t cap = 64;
+  for (uint32_t i = 0; i < count; i++) cap += 34 * (r->cells[first + i].size() + 1);
+  r->text.resize(cap);
+  size_t pos = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    offsets[i] = pos;
+    const std::vector<long double>& c = r->cells[first + i];
+    pos += hostsim_text_format_ld(c.data(), c.size(), r->text.data() + pos, 0, nullptr);
+    pos += hostsim_text_format_ld(&r->tails[first + i], 1, r->text.data() + pos, 0, nullptr);
+  }
+  offsets[count] = pos;
+  *text = r->text.data();
   return 0;
 }
 

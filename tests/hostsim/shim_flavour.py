@@ -225,5 +225,49 @@ def build(force: bool = False) -> bool:
     return True
 
 
+GENERATORS = ("generate_distribution", "generate_linear_distribution", "generate_diagonal_distribution")
+
+
+def build_generators(force: bool = False):
+    """TEST-ONLY: the reference's own generator executables linked with dropin.cpp, dropin_text.cpp and
+    -- flavour "shim" -- dropin_collapse.cpp over the CPU stand-in of the C ABI (abi_shim.cpp: SYNTHETIC
+    cells, real collapse / text arithmetic), so that the host logic of the three drop-ins (prefetching
+    the enumerator list, speculating on the dimension upgrades, the resident collapse and export) runs
+    inside the real master-worker protocol in the GPU-less suite. Flavour "shim_refcollapse": the same
+    with the reference's own collapse functions, the checker for the collapsed files.
+    Returns the two directories, or None."""
+    from integration import build as ib
+    obj = os.path.join(ib.OUT, "obj")
+    need = [os.path.join(obj, f) for f in ("dropin.o", "dropin_text.o", "dropin_collapse.o",
+                                           "linear_distribution_renamed.o", "linear_distribution.o")]
+    outs = [os.path.join(OUT, "gen"), os.path.join(OUT, "gen_refcollapse")]
+    last = os.path.join(outs[1], GENERATORS[-1])
+    if not all(os.path.exists(f) for f in need):
+        return outs if os.path.exists(last) else None
+    srcs = [os.path.join(_HERE, "abi_shim.cpp"), os.path.join(_HERE, "hostsim.cpp"),
+            os.path.join(_ROOT, "qunundrum_b200", "csrc", "hostconst.cpp"),
+            os.path.join(_ROOT, "qunundrum_b200", "csrc", "text_tables.cpp")]
+    deps = srcs + need + [os.path.abspath(__file__),
+                          os.path.join(_ROOT, "qunundrum_b200", "csrc", "client_math.cuh")]
+    if not force and os.path.exists(last) and all(os.path.getmtime(d) <= os.path.getmtime(last) for d in deps):
+        return outs
+    for o in outs:
+        os.makedirs(o, exist_ok=True)
+    shim = os.path.join(OUT, "libqb200_genshim.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-x", "c++", *srcs,
+                           "-o", shim])
+    common = [os.path.join(obj, f + ".o") for f in ib.COMMON_CPP + ib.COMMON_C + ["lattice_stub", "minimpi"]]
+    common_gpu = [o for o in common if not o.endswith(os.sep + "linear_distribution.o")] + [
+        os.path.join(obj, "linear_distribution_renamed.o"), os.path.join(obj, "dropin_collapse.o")]
+    libs = [os.path.join(ib.LIBDIR, "libmpfr.so.6"), os.path.join(ib.LIBDIR, "libgmp.so.10"),
+            "-lpthread", "-lm"]
+    for m in GENERATORS:
+        for out, objs in ((outs[0], common_gpu), (outs[1], common)):
+            subprocess.check_call(["g++", os.path.join(obj, "main_" + m + ".o"), *objs,
+                                   os.path.join(obj, "dropin.o"), os.path.join(obj, "dropin_text.o"), shim,
+                                   "-Wl,-rpath,$ORIGIN/..", *libs, "-o", os.path.join(out, m)])
+    return outs
+
+
 if __name__ == "__main__":
     print(build(force=True))

@@ -95,6 +95,50 @@ def test_generator_with_dropin_matches_reference_generator(exe, args, kind, rank
         shutil.rmtree(tb, ignore_errors=True)
 
 
+PREFETCH = [
+    ("generate_distribution", ["-det", "128", "2"], 3),                       # dimension heuristic: upgrades
+    ("generate_distribution", ["-det", "-dim", "32", "-l", "64", "40", "96", "50"], 2),   # two parameter sets
+    ("generate_linear_distribution", ["-r", "-dim", "512", "-det", "128", "2"], 3),
+    ("generate_diagonal_distribution", ["-dim", "256", "-det", "-eta-bound", "2", "128", "5", "2"], 4),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe,args,ranks", PREFETCH, ids=[c[0] + str(i) for i, c in enumerate(PREFETCH)])
+def test_prefetching_dropin_is_invisible_to_the_generator(exe, args, ranks):
+    """the drop-in integrates the whole enumerator list in one C-ABI call
+    on the first request and serves the client's one-slice-at-a-time calls from that batch (the
+    dimension upgrades of the heuristic speculatively); collapse and export run from a device copy.
+    Every exported file must be byte-identical to a run with QB200_PREFETCH=0 (one slice per call),
+    and the statistics must show that the calls were served from batches."""
+    if not _have():
+        pytest.skip("integration/_build missing")
+    import filecmp
+    ta, tb = tempfile.mkdtemp(), tempfile.mkdtemp()
+    try:
+        e = {"QB200_DEVICE": "0", "QB200_DROPIN_STATS": "1"}
+        os.makedirs(os.path.join(ta, "distributions"), exist_ok=True)
+        p = subprocess.run([os.path.join(B, "minimpirun"), "-np", str(ranks), os.path.join(B, "gpu", exe), *args],
+                           cwd=ta, env=dict(os.environ, **e), capture_output=True, text=True, timeout=3000)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        stats = [l for l in p.stderr.splitlines() if "slices per call" in l]
+        assert stats, p.stderr[-2000:]
+        import re
+        served = sum(int(re.search(r"(\d+) calls served from", l).group(1)) for l in stats)
+        calls = sum(int(re.search(r"drop-in: (\d+) slice calls", l).group(1)) for l in stats)
+        abi = sum(int(re.search(r"; (\d+) C-ABI calls", l).group(1)) for l in stats)
+        assert served == calls and abi < calls / 4, stats
+        _run("gpu", exe, args, ranks, tb, env={"QB200_DEVICE": "0", "QB200_PREFETCH": "0"})
+        fa, fb = _files(ta), _files(tb)
+        assert fa == fb and len(fa) >= 1
+        for f in fa:
+            assert filecmp.cmp(os.path.join(ta, "distributions", f), os.path.join(tb, "distributions", f),
+                               shallow=False), f
+    finally:
+        shutil.rmtree(ta, ignore_errors=True)
+        shutil.rmtree(tb, ignore_errors=True)
+
+
 FULL = [
     # BASELINE config 4 shape: two-dimensional, m = 3072, s = 4 (l = 768, sigma = 391), Richardson
     ["--m", "3072", "--s", "4", "--dim", "64", "--sample", "16", "--clients", "2"],
