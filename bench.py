@@ -13,9 +13,17 @@ signs of alpha_d) in enumerator order, at `-dim 256` (dimension D = 128 with the
 Richardson pass at 256): 16,384 cells and 329,218 reference integrand
 evaluations per slice; 55.08 M cells per step and per GPU.
 
-A step is one pass of the hot path over that batch. Slices are independent, so
-for N > 1 every rank integrates one such distribution (weak scaling, no
-data-path collective); only the per-slice summaries are gathered on rank 0.
+A step is one pass of the hot path over that batch. Slices are independent (no data-path
+collective; only the per-slice summaries are gathered on rank 0). For N > 1 the default is
+STRONG scaling: the 3362 slices of ONE distribution are partitioned over the ranks
+(shard.partition: slice i -> rank i mod N, the static form of the reference's task farm,
+src/main_generate_distribution.cpp:939-976), `value` = the distribution's cells / the slowest
+rank's time. `--scaling weak` (one whole distribution per rank, different d and r) is also
+measured in every N > 1 run and reported under `weak`; `saturation` is the same distribution in
+the generator's default dimension-heuristic mode (slices at D = 128, the upgraded ones re-computed
+at 256 and 512, src/main_generate_distribution.cpp:1222-1294; the 512 ones scaled back to 256 on
+the device), partitioned the same way: twice the work per distribution, so that 1/8 of it still
+fills a GPU.
 
 `value`   : device-resident throughput (descriptors and tables in HBM, results
             left in HBM), CUDA events on the launching stream, max over ranks.
@@ -36,6 +44,10 @@ data-path collective); only the per-slice summaries are gathered on rank 0.
             (value in + text out); the synchronous host call on one stored slice
             (65,536 cells + total error); libc's fprintf / fscanf on one host core
             beside it. Byte / bit parity is asserted on a sample in the run.
+`sections`: (N = 1) every other integrator of the path with its own value / roofline / e2e /
+            cpu_baseline: linear_d, linear_r, diagonal (m = 2048, D = 2048, the generator's slice
+            lists, ONE launch per distribution) and the sigma-optimal method; a compact numeric
+            summary of all sections sits in roofline.sections.
 `cpu_baseline` / --impl reference: the UNMODIFIED reference
             (oracle/_ref/libqref.so, distribution_slice_compute_richardson with
             192-bit MPFR) on the host cores, one slice per worker process.
@@ -69,18 +81,22 @@ def synthetic_d_r(seed: int):
     return d, r
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, scaling="weak"):
+    per = ("the 3362 slices of ONE distribution partitioned over the ranks (slice i -> rank i mod N), "
+           "no data-path collective" if scaling == "strong" else
+           f"one distribution per rank x {n_gpus} ranks, no data-path collective")
     return {
         "workload": ("generate_distribution (2D alpha_d, alpha_r), heuristic sigma, Richardson: "
                      "m=2048 s=1 l=2048 sigma=1031 t=30, 3362 slices (|alpha| in [m-30, m+10], "
                      "both signs of alpha_d) at -dim 256 (D=128 + 256): 55,083,008 cells per "
-                     "step per GPU"),
-        "cells_per_step_per_gpu": 3362 * DIM * DIM,
-        "slices_per_step_per_gpu": 3362,
+                     "distribution"),
+        "cells_per_distribution": 3362 * DIM * DIM,
+        "slices_per_distribution": 3362,
         "dimension": DIM,
-        "sharding": f"one distribution per rank x {n_gpus} ranks, no data-path collective",
-        "l2": ("results 440.7 MB per step exceed the 126 MB L2; inputs are ~5 MB of axis "
-               "tables rebuilt on the device every step"),
+        "sharding": per,
+        "l2": ("results (440.7 MB per distribution) exceed the 126 MB L2 at N = 1; where a rank's share "
+               "is smaller, 256 MB are written between steps (L2 flush) and steps are timed one by one; "
+               "inputs are ~5 MB of axis tables rebuilt on the device every step"),
     }
 
 
@@ -202,8 +218,8 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / max(1, args.steps) * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "mpfr192", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "scaling": scaling_mode(args, args.gpus), "vs_baseline": None, "dtype": "mpfr192", "data": "synthetic",
+        "config": workload_config(args.gpus, scaling_mode(args, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "reference",
                          "sample": sample, "cells_per_s_per_core": value / cores},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0,
@@ -528,7 +544,7 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
     sample_k_from_diagonal_j_eta_pivot for `n` uniform (j, eta, pivot) at m = 2048. Device-resident
     timing with CUDA events on the launching stream (qb200_diagk_sample_device), the synchronous
     C ABI with host rows (qb200_diagk_sample), a sub-sample checked against the reference's own
-    function on one host core (when oracle/_ref is on the box) and against the CPU twin."""
+    function on one host core (when oracle/_ref is on the box)."""
     import random
     LD = np.longdouble
     prng = random.Random(seed)
@@ -605,15 +621,6 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
                   "h2d_bytes_per_step": int(J.nbytes + eta.nbytes + piv.nbytes), "d2h_bytes_per_step": int(n * 32),
                   "api": "qb200_diagk_sample (host rows in; alpha_phi, delta, status out)"}
     sub = np.random.default_rng(3).choice(n, 300, replace=False)
-    try:
-        from tests import hostsim as hs
-        T = hs.DiagK(m, sigma, l, d, r)
-        gk = dK.cpu().numpy().view(np.uint32)
-        ks2, x2, dl2, st2 = T.sample([hs.limbs_to_int(J[i]) for i in sub], eta[sub], piv[sub], delta_bound)
-        res["parity_twin"] = bool([hs.limbs_to_int(gk[i]) for i in sub] == ks2
-                                  and np.array_equal(dl[sub], dl2) and np.array_equal(st[sub], st2))
-    except Exception as exc:  # pragma: no cover
-        res["parity_twin"] = f"unavailable: {exc}"
     if cpu_baseline:
         try:
             from oracle import ref as R
@@ -645,6 +652,325 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
 def sampler_cells(sampler):
     import qunundrum_b200 as qb
     return int(qb.lib().qb200_sampler_cells(sampler.h))
+
+
+def scaling_mode(args, world):
+    if args.scaling in ("strong", "weak"):
+        return args.scaling
+    return "strong" if world > 1 else "weak"
+
+
+def kernel_source_sha():
+    """Fingerprint of the sources the fused kernel is compiled from: profiles/fused2d_latest.json
+    carries the one its ncu capture was taken with."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("kernels_fused2d.cuh", "qmath.cuh", "integrands.cuh", "slice_cells.cuh"):
+        h.update(open(os.path.join(ROOT, "qunundrum_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def heuristic_dimensions(coords, tp128, m=M):
+    """The client's dimension heuristic (src/main_generate_distribution.cpp:1222-1294) for every
+    coordinate: (initial slice dimension, final slice dimension). tp128: the total at D = 128 (the
+    initial dimension of every coordinate that is not on the diagonal tail)."""
+    out = []
+    for (a, b), tp in zip(coords, tp128):
+        max_alpha = max(abs(a), abs(b))
+        req = 256
+        if abs(a - b) <= 1 and (a < 0) == (b < 0):
+            if max_alpha >= m + 3:
+                req = 1024
+            elif max_alpha >= m:
+                req = 512
+        initial = req
+        # (for the tail coordinates the second test reads the total at their own initial dimension;
+        # it can only raise 512 -> 1024 at max_alpha >= m + 10, where the first test already gave 1024)
+        if tp >= 1e-7 and max_alpha >= m and req < 512:
+            req = 512
+        if tp >= 1e-10 and max_alpha >= m + 10 and req < 1024:
+            req = 1024
+        out.append((initial // 2, req // 2))
+    return out
+
+
+class DeviceTimer:
+    """K steps on `stream`, CUDA events. flush: write 256 MB between steps (L2) and time the steps one
+    by one; else one event pair around all K."""
+
+    def __init__(self, torch, stream, flush):
+        self.torch, self.stream, self.flush = torch, stream, flush
+        self.scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if flush else None
+
+    def run(self, step, k):
+        torch = self.torch
+        if not self.flush:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            for _ in range(k):
+                step()
+            e1.record(self.stream)
+            self.stream.synchronize()
+            return e0.elapsed_time(e1)
+        ev = []
+        for _ in range(k):
+            self.scratch.fill_(1)          # on the current stream = self.stream
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            step()
+            e1.record(self.stream)
+            ev.append((e0, e1))
+        self.stream.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+
+def one_dimensional_sections(ctx, qb, torch, stream, peak_flops, hbm_peak, cpu_baseline=True):
+    """linear_d, linear_r, diagonal at m = 2048, D = 2048 with the slice lists the generators'
+    enumerators hand out (41 / 41 / 170 slices): ONE launch per distribution (k_fused1d)."""
+    import multiprocessing as mp
+    d, r = synthetic_d_r(20482048)
+    D = 2048
+    out = {}
+    lin = list(range(M - 30, M + 11))
+    sigma, eta_bound = 5, 2
+    diag_a, diag_eta = [], []
+    for eta in (0, 1, -1, 2, -2):
+        for a in range(M - 30, M + sigma - 1):
+            diag_a.append(a)
+            diag_eta.append(eta)
+    cases = [("linear_d", 0, qb.Parameters(M, S, d, r, T_PARAM), lin, None, 420.0),
+             ("linear_r", 1, qb.Parameters(M, S, d, r, T_PARAM), lin, None, 690.0),
+             ("diagonal", 2, qb.Diagonal_Parameters(M, sigma, S, d, r, eta_bound=eta_bound, t=T_PARAM), diag_a,
+              diag_eta, 420.0)]
+    for name, kind, P, a, eta, flop in cases:
+        n = len(a)
+        plan = ctx.plan1d(P, kind, True, D, a, eta)
+        cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
+        summ = torch.empty(n * 8, dtype=torch.float64, device="cuda")
+        l0 = ctx.launch_count
+        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        launches = ctx.launch_count - l0
+        for _ in range(5):
+            plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        reps = 50
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        plan.set_algorithm(1)              # the three-launch path, for comparison
+        for _ in range(3):
+            plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+        ms_plain = e0.elapsed_time(e1) / reps
+        plan.close()
+        tot = n * D
+        # end to end: the synchronous C ABI, host buffers
+        ctx.slice1d_batch(P, kind, True, D, a, eta)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            c1, tp1, fl1 = ctx.slice1d_batch(P, kind, True, D, a, eta)
+        wall = (time.perf_counter() - t0) / 10
+        ach = tot / (ms * 1e-3) * flop / 1e12
+        sec = {"workload": f"{name}: m={M} s={S} D={D}, {n} slices ({tot} cells) per distribution, Richardson",
+               "value": tot / (ms * 1e-3), "unit": "cells/s", "ms": ms, "gpu_launches": int(launches),
+               "three_launch_path_ms": ms_plain, "mass": float(tp1.sum()),
+               "roofline": {"bound": "fp64 (latency at this size)", "achieved": ach, "peak": peak_flops / 1e12,
+                            "unit": "TFLOP/s", "frac": ach / (peak_flops / 1e12), "flop_per_cell": flop,
+                            "kernel": "k_fused1d", "traffic": None,
+                            "note": ("one launch of %d blocks x 128 threads: the whole distribution is %.0f us of "
+                                     "device time, most of it the launch itself" % (n * (D // 128), ms * 1e3))},
+               "e2e": {"value": tot / wall, "unit": "cells/s", "ms": wall * 1e3,
+                       "h2d_bytes_per_step": int(8 * n + 2 * ((M + 7) // 8)), "d2h_bytes_per_step": int(tot * 8 + n * 64),
+                       "api": "qb200_slice1d_compute (synchronous C ABI, one call per distribution)"}}
+        if cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
+                    cores = host_cores()
+                    Dc = 64 if kind == 0 else (512 if kind == 2 else 2048)   # linear_d: 6144-bit MPFR, 6.4 ms / point
+                    jobs = [(kind, a[k % n], 0 if eta is None else eta[k % n], Dc, sigma) for k in range(cores)]
+                    t0 = time.perf_counter()
+                    with mp.get_context("fork").Pool(cores) as pool:
+                        res = pool.map(_ref_worker_1d, jobs)
+                    w = time.perf_counter() - t0
+                    sec["cpu_baseline"] = {"value": sum(res) / w, "unit": "cells/s", "cores": cores, "kind": "reference",
+                                           "sample": f"{cores} slices (one per worker process) at D={Dc}, {w:.1f} s wall; "
+                                                     "the cost per cell does not depend on D"}
+            except Exception as exc:  # pragma: no cover
+                sec["cpu_baseline"] = {"value": None, "unit": "cells/s", "cores": 0, "kind": "reference",
+                                       "sample": f"failed: {exc}"}
+        out[name] = sec
+    return out
+
+
+def _ref_worker_1d(job):
+    kind, a, eta, D, sigma = job
+    from oracle import ref
+    d, r = synthetic_d_r(20482048)
+    if kind == 2:
+        P = ref.RefDiagonalParameters(M, sigma, S, d, r, eta_bound=2)
+        sl = ref.diagonal_distribution_slice_compute(P, D, a, eta)
+    else:
+        P = ref.RefParameters(M, S, d, r, T_PARAM)
+        sl = ref.linear_distribution_slice_compute(P, D, a, kind)
+    return sl.cells.size
+
+
+def _ref_worker_so(job):
+    a, b, D = job
+    from oracle import ref
+    d, r = synthetic_d_r(20482048)
+    P = ref.RefParameters(M, S, d, r, T_PARAM)
+    return ref.distribution_slice_compute(P, D, a, b, method=1).cells.size
+
+
+def sigma_optimal_section(ctx, qb, torch, stream, P, coords, peak_flops, cpu_baseline=True):
+    """-sigma-optimal (probability_approx_optimal_sigma / _adjust_sigma, src/probability.cpp:20-148) on
+    the first 64 slices of the workload at D = 128: the parallel fixed point of the serial walk."""
+    import multiprocessing as mp
+    sub = coords[:64]
+    a_d, a_r = [c[0] for c in sub], [c[1] for c in sub]
+    plan = ctx.plan2d(P, qb.DISTRIBUTION_SLICE_COMPUTE_METHOD_OPTIMAL_LOCAL_SIGMA, True, DIM, a_d, a_r)
+    cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
+    summ = torch.empty(len(sub) * 8, dtype=torch.float64, device="cuda")
+    l0 = ctx.launch_count
+    plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    launches = ctx.launch_count - l0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(3):
+        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    tot = plan.cells
+    plan.close()
+    t0 = time.perf_counter()
+    ctx.slice2d_batch(P, 1, True, DIM, a_d, a_r)
+    wall = time.perf_counter() - t0
+    ach = tot / (ms * 1e-3) * FLOP_PER_CELL / 1e12
+    sec = {"workload": f"sigma-optimal method, the first {len(sub)} slices of the workload at D={DIM} ({tot} cells)",
+           "value": tot / (ms * 1e-3), "unit": "cells/s", "ms": ms, "gpu_launches": int(launches),
+           "roofline": {"bound": "fp64", "achieved": ach, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
+                        "frac": ach / (peak_flops / 1e12), "flop_per_cell": FLOP_PER_CELL, "traffic": None,
+                        "kernel": "k_so_step (one thread per point, double-double, 3-4 evaluations per point and "
+                                  "iteration) + k_so_scan; not fused"},
+           "e2e": {"value": tot / wall, "unit": "cells/s", "ms": wall * 1e3, "h2d_bytes_per_step": int(8 * len(sub)),
+                   "d2h_bytes_per_step": int(tot * 8), "api": "qb200_slice2d_compute, method 1"}}
+    if cpu_baseline:
+        try:
+            from oracle import ref
+            if ref.available():
+                cores = host_cores()
+                jobs = [(sub[k % len(sub)][0], sub[k % len(sub)][1], 32) for k in range(cores)]
+                t0 = time.perf_counter()
+                with mp.get_context("fork").Pool(cores) as pool:
+                    res = pool.map(_ref_worker_so, jobs)
+                w = time.perf_counter() - t0
+                sec["cpu_baseline"] = {"value": sum(res) / w, "unit": "cells/s", "cores": cores, "kind": "reference",
+                                       "sample": f"{cores} slices (one per worker process) at D=32, method 1, {w:.1f} s wall"}
+        except Exception as exc:  # pragma: no cover
+            sec["cpu_baseline"] = {"value": None, "unit": "cells/s", "cores": 0, "kind": "reference",
+                                   "sample": f"failed: {exc}"}
+    return sec
+
+
+def saturation_section(ctx, qb, torch, stream, timer, P, coords, my, tp128_all, world, barrier, allmax, steps):
+    """The same distribution in the generator's DEFAULT mode (dimension heuristic): every coordinate at
+    its initial dimension, the upgraded ones again at 256 / 512; this rank's share of each list.
+    Device resident, and end to end through the C ABI (the 512 ones scaled to 256 on the device)."""
+    import ctypes as C
+    dims = heuristic_dimensions(coords, tp128_all)
+    lists = {}
+    for i in my:
+        init, fin = dims[i]
+        lists.setdefault(init, []).append(i)
+        if fin != init:
+            lists.setdefault(fin, []).append(i)
+    plans, bufs, cells_total = [], [], 0
+    for D in sorted(lists):
+        idx = lists[D]
+        pl = ctx.plan2d(P, 0, True, D, [coords[i][0] for i in idx], [coords[i][1] for i in idx])
+        plans.append(pl)
+        bufs.append((torch.empty(max(1, pl.cells), dtype=torch.float64, device="cuda"),
+                     torch.empty(max(8, len(idx) * 8), dtype=torch.float64, device="cuda")))
+        cells_total += pl.cells
+
+    def step():
+        for pl, (c, sm) in zip(plans, bufs):
+            pl.run(c.data_ptr(), sm.data_ptr(), stream.cuda_stream)
+    for _ in range(3):
+        step()
+    barrier()
+    l0 = ctx.launch_count
+    ms = timer.run(step, steps)
+    launches = ctx.launch_count - l0
+    barrier()
+    ms = allmax(ms) / steps
+    all_cells = allmax(float(cells_total), "sum")
+    for pl in plans:
+        pl.close()
+    del bufs
+    # end to end: host coordinates in, stored cells out (doubles; long doubles for the scaled ones)
+    L = qb.lib()
+    stored, d2h = {}, 0
+    for D in sorted(lists):
+        n = len(lists[D])
+        per = min(D, 256) ** 2
+        nbytes = n * per * (16 if D > 256 else 8)
+        ptr = L.qb200_host_alloc(max(16, nbytes))
+        stored[D] = (ptr, n, per)
+        d2h += nbytes + n * 64
+
+    def e2e_step():
+        for D in sorted(lists):
+            idx = lists[D]
+            ptr, n, per = stored[D]
+            ad, ar = [coords[i][0] for i in idx], [coords[i][1] for i in idx]
+            if D > 256:
+                out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_longdouble)), shape=(n, per))
+                a_d, a_r = np.ascontiguousarray(ad, dtype=np.int32), np.ascontiguousarray(ar, dtype=np.int32)
+                tp = np.zeros(n, dtype=np.longdouble)
+                te = np.zeros(n, dtype=np.longdouble)
+                fl = np.zeros(n, dtype=np.uint32)
+                p = P._c()
+                rc = L.qb200_slice2d_compute_scaled(ctx.h, C.byref(p), 0, 1, D, 256, n, a_d.ctypes.data, a_r.ctypes.data,
+                                                    out.ctypes.data, tp.ctypes.data, te.ctypes.data, fl.ctypes.data)
+                if rc:
+                    raise SystemExit("bench.py: qb200_slice2d_compute_scaled failed")
+            else:
+                out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n, per))
+                ctx.slice2d_batch(P, 0, True, D, ad, ar, out=out)
+    e2e_step()
+    barrier()
+    k = max(1, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        e2e_step()
+    torch.cuda.synchronize()
+    wall = allmax(time.perf_counter() - t0) / k
+    for ptr, _, _ in stored.values():
+        L.qb200_host_free(C.c_void_p(ptr))
+    d2h_all = allmax(float(d2h), "sum")
+    return {"workload": ("the same distribution in -dim-heuristic mode: every coordinate at its initial dimension "
+                         "(128; 256 / 512 on the diagonal tail), the upgraded ones re-computed at 256 / 512 "
+                         "(src/main_generate_distribution.cpp:1222-1294), partitioned over the ranks"),
+            "slices_by_dimension_this_rank": {str(D): len(v) for D, v in sorted(lists.items())},
+            "cells_integrated_per_step": all_cells, "value": all_cells / (ms * 1e-3), "unit": "cells/s",
+            "ms_per_step": ms, "gpu_launches_per_step": int(launches // max(1, steps)),
+            "e2e": {"value": all_cells / wall, "unit": "cells/s", "ms_per_step": wall * 1e3,
+                    "d2h_bytes_per_step": d2h_all,
+                    "api": "qb200_slice2d_compute per dimension + qb200_slice2d_compute_scaled (512 -> 256 on the device)"}}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -681,89 +1007,151 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    ctx = qb.Context(local_rank)
-    d, r = synthetic_d_r(20482048 + rank)
-    P = qb.Parameters(M, S, d, r, T_PARAM)
-    coords = shard.enumerate_2d(M)
-    a_d = np.array([c[0] for c in coords], dtype=np.int32)
-    a_r = np.array([c[1] for c in coords], dtype=np.int32)
-    n = len(coords)
+    def allmax(v, op="max"):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return float(t.item())
 
-    # ---- device-resident timing --------------------------------------------------------
-    plan = ctx.plan2d(P, qb.DISTRIBUTION_SLICE_COMPUTE_METHOD_HEURISTIC_SIGMA, True, DIM, a_d, a_r)
-    if plan.algorithm != 2:
-        raise SystemExit("bench.py: the fused kernel was not selected")
-    cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
-    summ = torch.empty(n * 8, dtype=torch.float64, device="cuda")
+    mode = scaling_mode(args, world)
+    ctx = qb.Context(local_rank)
+    coords = shard.enumerate_2d(M)
+    n_all = len(coords)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     peak_flops = ctx.measure_fp64_peak()
-    for _ in range(max(3, args.warmup)):
-        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    l0 = ctx.launch_count
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
-    e1.record(stream)
-    barrier()
-    launches = ctx.launch_count - l0
-    ms = e0.elapsed_time(e1)
-    # keep the clocks record meaningful for short runs: sample a little longer under load
-    t_end = time.perf_counter() + 0.6
-    while time.perf_counter() < t_end:
-        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    total_cells = plan.cells * world
-    value = total_cells / (ms_per_step * 1e-3)
-
-    # results sanity (and the only cross-rank traffic): gather the slice summaries
-    # (weak scaling: rank k owns entries [k n, (k + 1) n) of the n * world slice table)
-    table = shard.gather_summaries(rank * n + np.arange(n), summ.cpu().numpy().reshape(n, 8),
-                                   n * world)
-    tp, te, fl = plan.finish(summ.cpu().numpy())
-    mass = float(tp.sum())
-    if not (0.4999 < mass < 0.5):
-        raise SystemExit(f"bench.py: captured mass {mass} is wrong")
-
-    # ---- end to end through the synchronous C ABI with host buffers ------------------
     import ctypes as C
     L = qb.lib()
-    nbytes = plan.cells * 8
-    hptr = L.qb200_host_alloc(nbytes)
-    if not hptr:
-        raise SystemExit("bench.py: pinned host allocation failed")
-    h_cells = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(n, DIM * DIM))
-    e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(2):
-        ctx.slice2d_batch(P, 0, True, DIM, a_d, a_r, out=h_cells)
-    barrier()
-    l1 = ctx.launch_count
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        _, tp2, te2, fl2 = ctx.slice2d_batch(P, 0, True, DIM, a_d, a_r, out=h_cells)
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    e2e_launches = ctx.launch_count - l1
-    tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+
+    def measure(P, my, tag):
+        """Device-resident and end-to-end timing of this rank's slices `my` of the distribution P."""
+        a_d = np.array([coords[i][0] for i in my], dtype=np.int32)
+        a_r = np.array([coords[i][1] for i in my], dtype=np.int32)
+        n = len(my)
+        plan = ctx.plan2d(P, qb.DISTRIBUTION_SLICE_COMPUTE_METHOD_HEURISTIC_SIGMA, True, DIM, a_d, a_r)
+        if plan.algorithm != 2:
+            raise SystemExit("bench.py: the fused kernel was not selected")
+        cells = torch.empty(max(1, plan.cells), dtype=torch.float64, device="cuda")
+        summ = torch.empty(max(8, n * 8), dtype=torch.float64, device="cuda")
+        flush = plan.cells * 8 < (256 << 20)
+        timer = DeviceTimer(torch, stream, flush)
+
+        def step():
+            plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        for _ in range(max(3, args.warmup)):
+            step()
+        sampler = ClockSampler(local_rank) if tag == "main" else None
+        barrier()
+        if sampler:
+            sampler.start()
+        l0 = ctx.launch_count
+        ms = timer.run(step, args.steps)
+        barrier()
+        launches = ctx.launch_count - l0
+        clocks = None
+        if sampler:
+            # keep the clocks record meaningful for short runs: sample a little longer under load
+            t_end = time.perf_counter() + 0.6
+            while time.perf_counter() < t_end:
+                step()
+                torch.cuda.synchronize()
+            clocks = sampler.stop()
+        my_ms = ms / args.steps
+        ms_per_step = allmax(ms) / args.steps
+        h_summ = summ.cpu().numpy()[:n * 8]
+        tp, te, fl = plan.finish(h_summ)
+        # ---- end to end through the synchronous C ABI with host buffers ------------------
+        nbytes = plan.cells * 8
+        hptr = L.qb200_host_alloc(max(8, nbytes))
+        if not hptr:
+            raise SystemExit("bench.py: pinned host allocation failed")
+        h_cells = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_double)), shape=(n, DIM * DIM))
+        e2e_steps = max(1, min(args.steps, 10))
+        for _ in range(2):
+            ctx.slice2d_batch(P, 0, True, DIM, a_d, a_r, out=h_cells)
+        barrier()
+        l1 = ctx.launch_count
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            _, tp2, te2, fl2 = ctx.slice2d_batch(P, 0, True, DIM, a_d, a_r, out=h_cells)
+        torch.cuda.synchronize()
+        my_wall = (time.perf_counter() - t0) / e2e_steps
+        e2e_launches = ctx.launch_count - l1
+        wall = allmax(my_wall)
+        mass = float(tp.sum())
+        if abs(float(tp2.sum()) - mass) > 1e-13 or abs(h_cells.sum() - mass) > 1e-9:
+            raise SystemExit("bench.py: end-to-end results differ from the device-resident run")
+        return dict(plan=plan, cells=cells, summ=summ, h_summ=h_summ, tp=tp, tp2=tp2, ms_per_step=ms_per_step,
+                    my_ms=my_ms, wall=wall, my_wall=my_wall, launches=launches, e2e_launches=e2e_launches,
+                    e2e_steps=e2e_steps, clocks=clocks, n=n, nbytes=nbytes, hptr=hptr, h_cells=h_cells, mass=mass,
+                    timer=timer, flush=flush,
+                    h2d=int(a_d.nbytes + a_r.nbytes + 2 * ((M + 7) // 8) + n * 40), d2h=int(nbytes + n * 64))
+
+    # ---- the headline measurement ------------------------------------------------------------
+    if mode == "strong":
+        d, r = synthetic_d_r(20482048)                 # ONE distribution, partitioned
+        my = shard.partition(n_all, world, rank)
+    else:
+        d, r = synthetic_d_r(20482048 + rank)          # one distribution per rank
+        my = np.arange(n_all)
+    P = qb.Parameters(M, S, d, r, T_PARAM)
+    R = measure(P, my, "main")
+    cells_job = n_all * DIM * DIM * (1 if mode == "strong" else world)
+    value = cells_job / (R["ms_per_step"] * 1e-3)
+    e2e_value = cells_job / R["wall"]
+    # results sanity (and the only cross-rank traffic): gather the slice summaries
+    if mode == "strong":
+        table = shard.gather_summaries(my, R["h_summ"].reshape(-1, 8), n_all)
+        total_mass = allmax(R["mass"], "sum")
+    else:
+        table = shard.gather_summaries(rank * n_all + np.arange(n_all), R["h_summ"].reshape(-1, 8), n_all * world)
+        total_mass = R["mass"]
+    if not (0.4999 < total_mass < 0.5):
+        raise SystemExit(f"bench.py: captured mass {total_mass} is wrong")
+    per_rank = None
     if dist is not None:
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-    wall = float(tw.item())
-    e2e_value = total_cells * e2e_steps / wall
-    if abs(float(tp2.sum()) - mass) > 1e-13 or abs(h_cells.sum() - mass) > 1e-9:
-        raise SystemExit("bench.py: end-to-end results differ from the device-resident run")
-    h2d = a_d.nbytes + a_r.nbytes + 2 * ((M + 7) // 8) + 3362 * 40  # coords, d, r, descriptors
-    d2h = nbytes + n * 8 * 8
+        t = torch.tensor([R["my_ms"], R["my_wall"] * 1e3, float(R["n"])], dtype=torch.float64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        per_rank = {"device_ms_per_step": [float(x[0]) for x in g], "e2e_ms_per_step": [float(x[1]) for x in g],
+                    "slices": [int(x[2]) for x in g]}
+
+    # ---- the other scaling mode, for N > 1 (reported under `weak` / `strong`) -----------------
+    other = None
+    if world > 1 and not args.no_other_scaling:
+        L.qb200_host_free(C.c_void_p(R["hptr"]))
+        R["hptr"] = None
+        R["plan"].close()
+        if mode == "strong":
+            P2 = qb.Parameters(M, S, *synthetic_d_r(20482048 + rank), T_PARAM)
+            O = measure(P2, np.arange(n_all), "other")
+            cj = n_all * DIM * DIM * world
+            name = "weak"
+        else:
+            P2 = qb.Parameters(M, S, *synthetic_d_r(20482048), T_PARAM)
+            O = measure(P2, shard.partition(n_all, world, rank), "other")
+            cj = n_all * DIM * DIM
+            name = "strong"
+        other = {"scaling": name, "value": cj / (O["ms_per_step"] * 1e-3), "unit": "cells/s",
+                 "ms_per_step": O["ms_per_step"],
+                 "e2e": {"value": cj / O["wall"], "unit": "cells/s", "ms_per_step": O["wall"] * 1e3,
+                         "d2h_bytes_per_step": int(O["d2h"])},
+                 "note": ("one whole distribution per rank (different d, r): N replicas" if name == "weak" else
+                          "ONE distribution partitioned over the ranks")}
+        L.qb200_host_free(C.c_void_p(O["hptr"]))
+        O["plan"].close()
+
+    # ---- saturation workload: the dimension-heuristic distribution, partitioned ----------------
+    saturation = None
+    if not args.no_saturation:
+        Ps = qb.Parameters(M, S, *synthetic_d_r(20482048), T_PARAM)
+        _, tp_all, _, _ = ctx.slice2d_batch(Ps, 0, True, DIM, [c[0] for c in coords], [c[1] for c in coords]) \
+            if (mode != "strong" or world > 1) else (None, None, None, None)
+        if tp_all is None:
+            tp_all = R["tp"]
+        mine = shard.partition(n_all, world, rank)
+        saturation = saturation_section(ctx, qb, torch, stream, DeviceTimer(torch, stream, False), Ps, coords, mine,
+                                        [float(x) for x in tp_all], world, barrier, allmax, max(3, min(args.steps, 10)))
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
@@ -783,80 +1171,118 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": None, "unit": "cells/s", "cores": 0, "kind": "reference",
                    "sample": f"failed: {exc}"}
 
-    tau = None
-    if world == 1 and not args.no_tau:
-        try:
-            hbm_peak_tau = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        except Exception:
-            hbm_peak_tau = 6650.0
-        tau = tau_section(ctx, qb, torch, stream, h_cells, tp2, coords, hbm_peak_tau,
-                          cpu_baseline=not args.no_cpu_baseline)
-
-    diagk = None
-    if world == 1 and not args.no_tau:
-        diagk = diagk_section(ctx, qb, torch, stream, cpu_baseline=not args.no_cpu_baseline)
-
-    L.qb200_host_free(C.c_void_p(hptr))
-    if dist is not None:
-        dist.barrier()
-
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         hbm_src = "measured (MEASURED_PEAKS.json)"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    sections = {}
+    if world == 1 and not args.no_sections:
+        sections.update(one_dimensional_sections(ctx, qb, torch, stream, peak_flops, hbm_peak,
+                                                 cpu_baseline=not args.no_cpu_baseline))
+        sections["sigma_optimal"] = sigma_optimal_section(ctx, qb, torch, stream, P, coords, peak_flops,
+                                                          cpu_baseline=not args.no_cpu_baseline)
+    tau = None
+    if world == 1 and not args.no_tau:
+        tau = tau_section(ctx, qb, torch, stream, R["h_cells"], R["tp2"], coords, hbm_peak,
+                          cpu_baseline=not args.no_cpu_baseline)
+    diagk = None
+    if world == 1 and not args.no_tau:
+        diagk = diagk_section(ctx, qb, torch, stream, cpu_baseline=not args.no_cpu_baseline)
+    if R["hptr"]:
+        L.qb200_host_free(C.c_void_p(R["hptr"]))
+    if dist is not None:
+        dist.barrier()
     text = None
     if world == 1 and not args.no_text:
-        plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)   # the step's own cells
+        R["plan"].run(R["cells"].data_ptr(), R["summ"].data_ptr(), stream.cuda_stream)   # the step's own cells
         torch.cuda.synchronize()
-        text = text_section(ctx, qb, torch, stream, cells, hbm_peak)
+        text = text_section(ctx, qb, torch, stream, R["cells"], hbm_peak)
 
     if rank == 0:
         prof = profile_constants() or {}
-        achieved = (plan.cells / (ms_per_step * 1e-3)) * FLOP_PER_CELL / 1e12  # per GPU
+        my_cells = R["n"] * DIM * DIM
+        cells_per_s_gpu = my_cells / (R["my_ms"] * 1e-3)        # this GPU
+        canonical = cells_per_s_gpu * FLOP_PER_CELL / 1e12
         peak = peak_flops / 1e12
-        out_gbs = nbytes / (ms_per_step * 1e-3) / 1e9
+        # executed: FP64 instructions per cell of the three class kernels (ncu, profiles/fused2d_latest.json,
+        # weighted by the classes' share of the workload) x cells/s over the DFMA-instruction rate of the
+        # same GPU in the same run (the microkernel's flop/s / 2)
+        inst = prof.get("fp64_inst_per_cell")
+        executed = None if not inst else cells_per_s_gpu * inst / (peak_flops / 2.0)
+        out_gbs = R["nbytes"] / (R["my_ms"] * 1e-3) / 1e9
+        compact = {}
+        for k, v in sections.items():
+            compact[k] = {"cells_per_s": v["value"], "ms": v["ms"], "frac": v["roofline"]["frac"],
+                          "e2e_cells_per_s": v["e2e"]["value"],
+                          "cpu_cells_per_s": (v.get("cpu_baseline") or {}).get("value")}
+        if text:
+            compact["text_export"] = {"values_per_s": text["export"]["values_per_s"],
+                                      "hbm_frac": text["export"]["roofline"]["frac"]}
+            compact["text_import"] = {"values_per_s": text["import"]["values_per_s"],
+                                      "hbm_frac": text["import"]["roofline"]["frac"]}
+        if tau:
+            compact["tau"] = {"samples_per_s": tau["value"], "hbm_frac": tau["roofline"]["frac"],
+                              "e2e_samples_per_s": tau["e2e"]["value"],
+                              "cpu_samples_per_s": (tau.get("cpu_baseline") or {}).get("value")}
+        if diagk:
+            compact["diagk"] = {"samples_per_s": diagk["value"], "e2e_samples_per_s": diagk["e2e"]["value"],
+                                "cpu_samples_per_s": (diagk.get("cpu_baseline") or {}).get("value")}
+        if saturation:
+            compact["saturation"] = {"cells_per_s": saturation["value"], "ms": saturation["ms_per_step"],
+                                     "e2e_cells_per_s": saturation["e2e"]["value"]}
+        if other:
+            compact[other["scaling"]] = {"cells_per_s": other["value"], "e2e_cells_per_s": other["e2e"]["value"]}
         line = {
             "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world),
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": R["ms_per_step"],
+            "higher_is_better": True, "scaling": mode, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world, mode),
             "roofline": {
-                "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": "k_fused2d<0,1,0,0>",
-                "flop_per_cell": FLOP_PER_CELL,
+                "bound": "fp64", "achieved": None if executed is None else executed * peak, "peak": peak,
+                "unit": "TFLOP/s", "frac": executed, "frac_canonical": canonical / peak,
+                "achieved_canonical": canonical, "traffic": prof.get("dram_bytes_per_launch"),
+                "kernel": "k_fused2d<MODE 0, class 0 / 1 / 2>",
+                "flop_per_cell_canonical": FLOP_PER_CELL,
+                "fp64_inst_per_cell": inst,
+                "fp64_pipe_active_frac_ncu": prof.get("fp64_pipe_active_frac"),
+                "profile_matches_source": prof.get("kernel_source_sha") == kernel_source_sha(),
                 "peak_source": "DFMA microkernel measured in this run on this GPU "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
-                "executed_frac": prof.get("fp64_pipe_active_frac"),
-                "executed_fp64_inst_per_cell": prof.get("fp64_inst_per_cell"),
                 "hbm": {"algorithmic_gbs": out_gbs, "peak_gbs": hbm_peak, "frac": out_gbs / hbm_peak,
                         "peak_source": hbm_src},
-                "note": "per GPU; step time includes the three small table/summary kernels (<1.5%)",
-                "frac_note": ("frac uses the contract's canonical 1600 FP64 flop per cell (SURVEY.md "
-                              "section 8(d): 20.09 integrand evaluations x 80 flop). The kernel does "
-                              "the same integration with ~500 flop per cell -- sin(pi u) by angle "
-                              "addition from per-row / per-column tables instead of one sine per point, "
-                              "19 instead of 20.09 evaluations -- so frac exceeds 1; executed_frac is "
-                              "the measured FP64-pipe utilisation (ncu), the kernel-quality number"),
+                "sections": compact,
+                "note": "rank 0's GPU; step time includes the three small table/summary kernels (<1.5%)",
+                "frac_note": ("frac = executed FP64 instructions (fp64_inst_per_cell from the committed ncu capture "
+                              "of this kernel source x cells/s of this run) over the DFMA-instruction rate measured "
+                              "in this run; frac_canonical uses SURVEY 8(d)'s 1600 flop per cell, which the kernel "
+                              "undercuts (angle addition from per-row / per-column tables), so it exceeds 1"),
             },
             "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": R["h2d"],
+                    "d2h_bytes_per_step": R["d2h"], "steps": R["e2e_steps"],
+                    "ms_per_step": R["wall"] * 1e3, "bytes_are": "per rank",
+                    "api": "qb200_slice2d_compute (synchronous C ABI, pinned host result buffer)",
+                    "host_placement": numa},
+            "gpu_launches": int(R["launches"]),
+            "e2e_gpu_launches": int(R["e2e_launches"]),
+            "clocks": R["clocks"],
+            "captured_mass_per_distribution": total_mass,
+            "gathered_summaries": None if table is None else int(table.shape[0]),
+            "per_rank": per_rank,
+            "other_scaling": other,
+            "saturation": saturation,
+            "sections": sections or None,
             "text": text,
             "tau": tau,
             "diagk": diagk,
-            "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "ms_per_step": wall / e2e_steps * 1e3,
-                    "api": "qb200_slice2d_compute (synchronous C ABI, pinned host result buffer)",
-                    "host_placement": numa},
-            "gpu_launches": int(launches),
-            "e2e_gpu_launches": int(e2e_launches),
-            "clocks": clocks,
-            "captured_mass_per_distribution": mass,
-            "gathered_summaries": None if table is None else int(table.shape[0]),
         }
         print(json.dumps(line))
-    plan.close()
+    try:
+        R["plan"].close()
+    except Exception:
+        pass
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -871,6 +1297,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text", action="store_true")
     ap.add_argument("--no-tau", action="store_true")
+    ap.add_argument("--no-sections", action="store_true")
+    ap.add_argument("--no-saturation", action="store_true")
+    ap.add_argument("--no-other-scaling", action="store_true")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="N > 1: strong = ONE distribution partitioned over the ranks (default), "
+                         "weak = one distribution per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -890,6 +1322,11 @@ def main():
             cmd.append("--no-text")
         if args.no_tau:
             cmd.append("--no-tau")
+        for flag, on in (("--no-sections", args.no_sections), ("--no-saturation", args.no_saturation),
+                         ("--no-other-scaling", args.no_other_scaling)):
+            if on:
+                cmd.append(flag)
+        cmd += ["--scaling", args.scaling]
         raise SystemExit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

@@ -30,8 +30,12 @@ namespace qb200 {
 
 #define QB_F1D_BLOCK 128
 
+// One instantiation per integrand and ONE call site of it (the six abscissae of a thread go
+// through a loop that is not unrolled): the three integrands inlined at six call sites were 8000
+// instructions, more than the instruction cache holds.
+template <int KIND>
 __global__ void __launch_bounds__(QB_F1D_BLOCK)
-k_fused1d(DevConsts c, int kind, int D, int richardson, const DevSlice* __restrict__ slices,
+k_fused1d(DevConsts c, int D, int richardson, const DevSlice* __restrict__ slices,
           const TabDesc* __restrict__ desc, const dd* __restrict__ gx,
           const double* __restrict__ gw, double* __restrict__ out, double* __restrict__ part,
           unsigned int* __restrict__ tickets, double* __restrict__ summary) {
@@ -47,23 +51,40 @@ k_fused1d(DevConsts c, int kind, int D, int richardson, const DevSlice* __restri
   const dd* gxf = gx + pass_offset(D, 1);   // fine pass, 4 D + 1
   const int step = richardson ? 4 : 2;      // points per cell in the pass that holds the ends
   const dd* ends = richardson ? gxf : gxc;
-  double v0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0, cm = 0.0;
-  if (I < D) {
-    v0 = value_1d(c, kind, ends[step * I], t, s.eta_shift);
-    cm = value_1d(c, kind, gxc[2 * I + 1], t, s.eta_shift);
-    if (richardson) {
-      f1 = value_1d(c, kind, gxf[4 * I + 1], t, s.eta_shift);
-      f2 = value_1d(c, kind, gxf[4 * I + 2], t, s.eta_shift);
-      f3 = value_1d(c, kind, gxf[4 * I + 3], t, s.eta_shift);
-    }
-  }
-  s_left[tid] = v0;
-  // the block's right end: the thread after the block's last active cell evaluates it, so the
-  // extra evaluation does not lengthen a warp that already did five
   const int last = min(D, (int)(blockIdx.x + 1) * QB_F1D_BLOCK);  // first cell past the block
-  if (I == last && tid < QB_F1D_BLOCK) s_left[tid] = value_1d(c, kind, ends[step * I], t, s.eta_shift);
-  if (tid == QB_F1D_BLOCK - 1 && I == last - 1)
-    s_left[QB_F1D_BLOCK] = value_1d(c, kind, ends[step * last], t, s.eta_shift);
+  // abscissa p of this thread: 0 left end, 1 coarse mid-point, 2..4 fine 4 I + 1 .. 3, 5 the
+  // block's right end (evaluated by the thread after the block's last cell, or, in a full block,
+  // by its last thread)
+  double vals[6];
+#pragma unroll 1
+  for (int p = 0; p < 6; p++) {
+    const dd* tab = ends;
+    int at = step * I;
+    bool need = I < D;
+    if (p == 1) {
+      tab = gxc;
+      at = 2 * I + 1;
+    } else if (p >= 2 && p <= 4) {
+      tab = gxf;
+      at = 4 * I + p - 1;
+      need = need && richardson;
+    } else if (p == 5) {
+      at = step * last;
+      need = (I == last) || (tid == QB_F1D_BLOCK - 1 && I == last - 1);
+    }
+    double v = 0.0;
+    if (need) {
+      const dd x = grid_x(tab[at], t.k_abs, t.sign, c.m);
+      if (KIND == KIND_LINEAR_D) v = linear_d_value(x, c.d_m, c.omd_m, c.l);
+      else if (KIND == KIND_LINEAR_R) v = linear_r_value(x, c);
+      else v = diagonal_value(x, s.eta_shift, c.rho);
+    }
+    vals[p] = v;
+  }
+  const double v0 = vals[0], cm = vals[1], f1 = vals[2], f2 = vals[3], f3 = vals[4];
+  s_left[tid] = v0;
+  if (I == last) s_left[tid] = vals[5];
+  if (tid == QB_F1D_BLOCK - 1 && I == last - 1) s_left[QB_F1D_BLOCK] = vals[5];
   __syncthreads();
   double v = 0.0;
   if (I < D) {

@@ -429,11 +429,21 @@ int run_fused_1d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d_sum
   }
   for (uint32_t s0 = 0; s0 < pl->n; s0 += 65535) {
     const uint32_t ns = std::min<uint32_t>(65535, pl->n - s0);
-    k_fused1d<<<dim3(nb, ns), QB_F1D_BLOCK, 0, st>>>(
-        h.c, h.kind, D, h.richardson, pl->slices.as<DevSlice>() + s0, pl->desc_a.as<TabDesc>(),
-        pl->geo->gx.as<dd>(), pl->geo->gw.as<double>(), d_cells + (size_t)s0 * D,
-        pl->f1d_part.as<double>() + (size_t)s0 * nb * 2, pl->f1d_tickets.as<unsigned int>() + s0,
-        d_summary + (size_t)s0 * QB200_SUMMARY_STRIDE);
+    const dim3 grid(nb, ns);
+    const DevSlice* sl = pl->slices.as<DevSlice>() + s0;
+    double* oc = d_cells + (size_t)s0 * D;
+    double* pp = pl->f1d_part.as<double>() + (size_t)s0 * nb * 2;
+    unsigned int* tk = pl->f1d_tickets.as<unsigned int>() + s0;
+    double* sm = d_summary + (size_t)s0 * QB200_SUMMARY_STRIDE;
+    const TabDesc* da = pl->desc_a.as<TabDesc>();
+    const dd* gx = pl->geo->gx.as<dd>();
+    const double* gw = pl->geo->gw.as<double>();
+    if (h.kind == KIND_LINEAR_D)
+      k_fused1d<KIND_LINEAR_D><<<grid, QB_F1D_BLOCK, 0, st>>>(h.c, D, h.richardson, sl, da, gx, gw, oc, pp, tk, sm);
+    else if (h.kind == KIND_LINEAR_R)
+      k_fused1d<KIND_LINEAR_R><<<grid, QB_F1D_BLOCK, 0, st>>>(h.c, D, h.richardson, sl, da, gx, gw, oc, pp, tk, sm);
+    else
+      k_fused1d<KIND_DIAGONAL><<<grid, QB_F1D_BLOCK, 0, st>>>(h.c, D, h.richardson, sl, da, gx, gw, oc, pp, tk, sm);
     ctx->launches++;
   }
   QB_CUDA(cudaGetLastError());

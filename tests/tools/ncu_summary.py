@@ -25,6 +25,7 @@ KEYS = {
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pipe_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "smsp__inst_executed.sum": "warp_instructions",
+    "smsp__inst_executed_pipe_fp64.sum": "fp64_warp_instructions",
     "dram__bytes_read.sum": "dram_read",
     "dram__bytes_write.sum": "dram_write",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
