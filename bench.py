@@ -938,7 +938,8 @@ def saturation_section(ctx, qb, torch, stream, timer, P, coords, my, tp128_all, 
             ptr, n, per = stored[D]
             ad, ar = [coords[i][0] for i in idx], [coords[i][1] for i in idx]
             if D > 256:
-                out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_longdouble)), shape=(n, per))
+                out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(n * per * 16,)) \
+                    .view(np.longdouble).reshape(n, per)
                 a_d, a_r = np.ascontiguousarray(ad, dtype=np.int32), np.ascontiguousarray(ar, dtype=np.int32)
                 tp = np.zeros(n, dtype=np.longdouble)
                 te = np.zeros(n, dtype=np.longdouble)

@@ -127,6 +127,13 @@ static int send_bytes(const void *buf, size_t bytes, int dest, int tag) {
     exit(-1);
   }
   int hdr[3] = {g_rank, tag, (int)bytes};
+  if (bytes && bytes <= 4096) { /* small messages: header and payload in one write */
+    char tmp[sizeof(hdr) + 4096];
+    memcpy(tmp, hdr, sizeof(hdr));
+    memcpy(tmp + sizeof(hdr), buf, bytes);
+    write_all(g_fd[dest], tmp, sizeof(hdr) + bytes);
+    return MPI_SUCCESS;
+  }
   write_all(g_fd[dest], hdr, sizeof(hdr));
   if (bytes) write_all(g_fd[dest], buf, bytes);
   return MPI_SUCCESS;
@@ -180,7 +187,48 @@ static int recv_bytes(void *buf, size_t cap, int source, int tag, MPI_Status *st
       free(m);
       return MPI_SUCCESS;
     }
-    /* nothing queued matches: block for the next message from a candidate peer */
+    /* nothing queued matches. Receiving from ONE peer: read its next header and, if it is the
+     * message wanted, the payload straight into the caller's buffer (the 256 KiB slice matrices
+     * of *_slice_init_recv): no intermediate allocation, one copy less. */
+    if (source != MPI_ANY_SOURCE && source >= 0 && source < g_size && g_fd[source] >= 0) {
+      int hdr[3];
+      if (read_all(g_fd[source], hdr, sizeof(hdr)) != 0) {
+        fprintf(stderr, "minimpi[%d]: rank %d exited while a message was expected\n", g_rank, source);
+        exit(-1);
+      }
+      if (tag == MPI_ANY_TAG || hdr[1] == tag) {
+        if ((size_t)hdr[2] > cap) {
+          fprintf(stderr, "minimpi[%d]: message of %d bytes truncated (buffer %zu)\n", g_rank, hdr[2], cap);
+          exit(-1);
+        }
+        if (hdr[2] > 0 && read_all(g_fd[source], buf, (size_t)hdr[2]) != 0) {
+          fprintf(stderr, "minimpi[%d]: peer %d closed mid-message\n", g_rank, source);
+          exit(-1);
+        }
+        if (status) {
+          status->MPI_SOURCE = hdr[0];
+          status->MPI_TAG = hdr[1];
+          status->MPI_ERROR = MPI_SUCCESS;
+          status->count_bytes = hdr[2];
+        }
+        return MPI_SUCCESS;
+      }
+      /* some other tag: queue it and look again */
+      Msg *m = (Msg *)malloc(sizeof(Msg));
+      m->source = hdr[0];
+      m->tag = hdr[1];
+      m->bytes = hdr[2];
+      m->data = (char *)malloc(m->bytes > 0 ? (size_t)m->bytes : 1);
+      m->next = NULL;
+      if (m->bytes > 0 && read_all(g_fd[source], m->data, (size_t)m->bytes) != 0) {
+        fprintf(stderr, "minimpi[%d]: peer %d closed mid-message\n", g_rank, source);
+        exit(-1);
+      }
+      if (g_tail) g_tail->next = m; else g_head = m;
+      g_tail = m;
+      continue;
+    }
+    /* any source: block for the next message from a candidate peer */
     struct pollfd pf[MAX_RANKS];
     int idx[MAX_RANKS], n = 0;
     for (int i = 0; i < g_size; i++) {

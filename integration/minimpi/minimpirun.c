@@ -28,6 +28,12 @@ int main(int argc, char **argv) {
         perror("socketpair");
         return 1;
       }
+      /* room for several slice messages in flight (default 208 KiB < one 256 KiB slice) */
+      for (int e = 0; e < 2; e++) {
+        int sz = 8 << 20;
+        setsockopt(sv[e], SOL_SOCKET, SO_SNDBUF, &sz, sizeof(sz));
+        setsockopt(sv[e], SOL_SOCKET, SO_RCVBUF, &sz, sizeof(sz));
+      }
       fd[i][j] = sv[0];
       fd[j][i] = sv[1];
     }

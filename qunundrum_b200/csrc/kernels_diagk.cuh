@@ -103,25 +103,15 @@ __device__ __forceinline__ int diagk_warp_walk(uint32_t l, dd t, double Sd, dd p
   }
 }
 
-__global__ void __launch_bounds__(QB_DIAGK_CTA) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
-                                                const int32_t* __restrict__ eta,
-                                                const RawX87* __restrict__ pivot,
-                                                unsigned long long delta_bound, uint32_t B,
-                                                uint32_t* __restrict__ scratch, uint32_t* __restrict__ kT,
-                                                DiagKOut* __restrict__ out) {
-  extern __shared__ uint32_t sh[];
+// One tile of 128 samples (tile index tb). `scratch`: this CTA's own 128 x (5 k + 9) words.
+__device__ __forceinline__ void diagk_tile(const DiagKConst& c, uint32_t tb, const uint32_t* __restrict__ jT,
+                                           const int32_t* __restrict__ eta, const RawX87* __restrict__ pivot,
+                                           unsigned long long delta_bound, uint32_t B,
+                                           uint32_t* __restrict__ scratch, uint32_t* __restrict__ kT,
+                                           DiagKOut* __restrict__ out) {
   const uint32_t k = c.k;
-  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
-    sh[i] = c.r[i];
-    sh[k + i] = c.d[i];
-  }
-  for (uint32_t i = threadIdx.x; i < k + 2; i += blockDim.x) sh[2 * k + i] = c.mu[i];
-  __syncthreads();
-  c.r = sh;
-  c.d = sh + k;
-  c.mu = sh + 2 * k;
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t tile = (size_t)blockIdx.x * QB_DIAGK_CTA;
+  const uint32_t g = tb * QB_DIAGK_CTA + threadIdx.x;
+  const size_t tile = (size_t)tb * QB_DIAGK_CTA;
   uint32_t* k_out = kT ? kT + tile * c.wl + threadIdx.x : nullptr;
   // every lane stays until the warp has walked together: `live` marks the ones with a sample
   bool live = g < B;
@@ -153,8 +143,7 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA) k_diagk(DiagKConst c, const uint
   q.p = make_dd(0.0, 0.0);
   q.idx = 0;
   if (live) {
-    diagk_fraction<QB_DIAGK_CTA>(c, jT + tile * c.wj + threadIdx.x, eta[g],
-                                 scratch + tile * diagk_scratch_limbs(k) + threadIdx.x, k_out, &f);
+    diagk_fraction<QB_DIAGK_CTA>(c, jT + tile * c.wj + threadIdx.x, eta[g], scratch + threadIdx.x, k_out, &f);
     const dd st = sinpi_acc(f.t);
     S = dd_mul(st, st);
     if (c.force_exact) {
@@ -193,6 +182,34 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA) k_diagk(DiagKConst c, const uint
   o.x_lo = xo.lo;
   o.delta = (long long)dout;
   out[g] = o;
+}
+
+// Persistent CTAs: the grid is one wave (SMs x resident CTAs), every CTA walks the tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... and owns ONE scratch area of 128 x (5 k + 9) words for
+// all of them. The scratch of a launch is then ~150 MB that is rewritten in place (it stays in L2)
+// instead of 1.3 KB per SAMPLE streamed through DRAM once (ncu, round 1: 0.95 GB written and
+// 0.27 GB read per launch of 303,104 samples against 0.17 GB of algorithmic traffic).
+__global__ void __launch_bounds__(QB_DIAGK_CTA, 6) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
+                                                const int32_t* __restrict__ eta,
+                                                const RawX87* __restrict__ pivot,
+                                                unsigned long long delta_bound, uint32_t B,
+                                                uint32_t* __restrict__ scratch, uint32_t* __restrict__ kT,
+                                                DiagKOut* __restrict__ out) {
+  extern __shared__ uint32_t sh[];
+  const uint32_t k = c.k;
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+    sh[i] = c.r[i];
+    sh[k + i] = c.d[i];
+  }
+  for (uint32_t i = threadIdx.x; i < k + 2; i += blockDim.x) sh[2 * k + i] = c.mu[i];
+  __syncthreads();
+  c.r = sh;
+  c.d = sh + k;
+  c.mu = sh + 2 * k;
+  const uint32_t n_tiles = (B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA;
+  uint32_t* mine = scratch + (size_t)blockIdx.x * QB_DIAGK_CTA * diagk_scratch_limbs(k);
+  for (uint32_t tb = blockIdx.x; tb < n_tiles; tb += gridDim.x)
+    diagk_tile(c, tb, jT, eta, pivot, delta_bound, B, mine, kT, out);
 }
 
 // status[t] = 0, 1 (a sample ran out of bounds, or |eta| > eta_bound: the reference breaks and

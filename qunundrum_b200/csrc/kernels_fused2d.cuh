@@ -699,6 +699,12 @@ inline bool fused2d_prepare(const Plan& h, unsigned n_chunks, FusedPlan2D* f, st
     rel_max = std::max(rel_max, (int)std::labs((long)h.k_b[i]) - c.m);
   }
   if (h.slices.empty()) rel_max = 0;
+  // MODE and the second error moment are decided per PLAN; a generator never asks for a coordinate
+  // above m + 10 (src/main_generate_distribution.cpp:1196-1212), so every plan inside that range
+  // takes the decision of the whole range: a slice then has the same bits whichever batch it is
+  // computed in -- alone (one call per slice) or with the whole enumerator list (the prefetching
+  // drop-in). Plans that reach further out decide for themselves.
+  rel_max = std::max(rel_max, 10);
   // |u| <= |x_d| + |kappa| |x_r| < 2^(rel_max + 1) * (1 + |kappa|)
   const int log_u = rel_max + 1 + (int)std::ceil(std::log2(1.0 + akappa));
   if (c.lam_exp - log_u >= 29) {

@@ -6,6 +6,8 @@
 // path: the entry points fail without a CUDA device like the rest of the library.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -60,6 +62,7 @@ struct qb200_diagk {
   DiagKConst dev;  // pointers into `consts`
   DBuf consts, rows_j, cols_j, eta, pivot, scratch, cols_k, rows_k, out, sums, status, xh, xl, hout;
   uint32_t chunk = 0;
+  uint32_t resident_ctas = 0;
 };
 
 // Samples per launch: enough threads for every SM, scratch of at most ~1 GB.
@@ -124,12 +127,20 @@ static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const i
   const DiagKConst& c = s->host.c;
   const size_t scr = diagk_scratch_limbs(c.k);
   const size_t Bp = ((size_t)B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA * QB_DIAGK_CTA;  // whole tiles
-  if (s->cols_j.reserve(Bp * c.wj * 4) || s->scratch.reserve(Bp * scr * 4)) return -100;
+  const size_t shmem = (size_t)(3 * c.k + 2) * 4;
+  if (s->resident_ctas == 0) {  // one wave of CTAs: each owns one scratch area for all its tiles
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diagk, QB_DIAGK_CTA, shmem) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess || per_sm < 1)
+      return -100;
+    s->resident_ctas = (uint32_t)(per_sm * sms);
+  }
+  const uint32_t grid = (uint32_t)std::min<size_t>(Bp / QB_DIAGK_CTA, s->resident_ctas);
+  if (s->cols_j.reserve(Bp * c.wj * 4) || s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * scr * 4)) return -100;
   if (d_k_rows && s->cols_k.reserve(Bp * c.wl * 4)) return -100;
   const uint64_t nj = (uint64_t)Bp * c.wj;
   k_diagk_gather<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(d_j, c.wj, B, s->cols_j.as<uint32_t>());
-  const size_t shmem = (size_t)(3 * c.k + 2) * 4;
-  k_diagk<<<(unsigned)(Bp / QB_DIAGK_CTA), QB_DIAGK_CTA, shmem, stream>>>(s->dev, s->cols_j.as<uint32_t>(), d_eta, d_pivot,
+  k_diagk<<<grid, QB_DIAGK_CTA, shmem, stream>>>(s->dev, s->cols_j.as<uint32_t>(), d_eta, d_pivot,
                                                   (unsigned long long)delta_bound, B,
                                                   s->scratch.as<uint32_t>(),
                                                   d_k_rows ? s->cols_k.as<uint32_t>() : nullptr, d_out);

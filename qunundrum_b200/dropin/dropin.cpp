@@ -226,7 +226,7 @@ typedef std::pair<int32_t, int32_t> Coord;
 struct Batch {
   uint32_t dimension;
   size_t per;            // cells per slice
-  double* cells;         // pinned, n * per
+  double* cells;         // n * per (pageable: pinning 440 MB costs a second on a virtual machine)
   std::vector<long double> tp, te;
   std::vector<uint32_t> flags;
   std::map<Coord, uint32_t> index;
@@ -242,7 +242,7 @@ struct Cache {
   void clear() {
     for (std::map<uint32_t, std::vector<Batch*> >::iterator it = batches.begin(); it != batches.end(); ++it) {
       for (size_t k = 0; k < it->second.size(); k++) {
-        qb200_host_free(it->second[k]->cells);
+        free(it->second[k]->cells);
         delete it->second[k];
       }
     }
@@ -297,7 +297,7 @@ Batch* compute_batch_2d(const Exported& e, int method, int richardson, uint32_t 
   b->dimension = dimension;
   b->per = (size_t)dimension * dimension;
   const size_t n = coords.size();
-  b->cells = (double*)qb200_host_alloc(n * b->per * sizeof(double) + 8);
+  b->cells = (double*)malloc(n * b->per * sizeof(double) + 8);
   if (NULL == b->cells) critical("%s(): Failed to allocate memory.", who);
   b->tp.assign(n, 0);
   b->te.assign(n, 0);
@@ -484,7 +484,7 @@ void compute_1d(long double* const norm_vector, const uint32_t dimension, const 
       b->dimension = dimension;
       b->per = dimension;
       const size_t n = want.size();
-      b->cells = (double*)qb200_host_alloc(n * b->per * sizeof(double) + 8);
+      b->cells = (double*)malloc(n * b->per * sizeof(double) + 8);
       if (NULL == b->cells) critical("%s(): Failed to allocate memory.", who);
       b->tp.assign(n, 0);
       b->flags.assign(n, 0);

@@ -39,6 +39,7 @@
 #include <unistd.h>
 
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "qunundrum_b200.h"
@@ -79,18 +80,48 @@ void print_text_stats() {
   }
 }
 
+qb200_context* text_context_create();
+int text_device();
+std::once_flag g_text_once;
+
 qb200_context* text_context() {
-  if (g_text_ctx) return g_text_ctx;
-  const char* st = getenv("QB200_DROPIN_STATS");
-  if (st && *st && *st != '0') {
-    g_tstats.on = true;
-    atexit(print_text_stats);
+  std::call_once(g_text_once, [] { g_text_ctx = text_context_create(); });
+  return g_text_ctx;
+}
+
+// The SERVER of a generator run (rank 0 of an MPI job) needs its CUDA context seconds after it
+// started -- when the clients are done and the distribution is collapsed and exported -- and
+// creating one takes 0.3 ... 2 s. Start it in the background when the process starts.
+// QB200_EAGER_INIT=0 turns this off.
+struct EagerServerContext {
+  EagerServerContext() {
+    const char* off = getenv("QB200_EAGER_INIT");
+    if (off && *off == '0') return;
+    const char* names[] = {"QB200_MINIMPI_RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK"};
+    const char* sizes[] = {"QB200_MINIMPI_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", NULL};
+    for (int i = 0; i < 4; i++) {
+      const char* r = getenv(names[i]);
+      if (!r || !*r) continue;
+      const char* n = sizes[i] ? getenv(sizes[i]) : NULL;
+      if (atoi(r) == 0 && (!n || atoi(n) > 1)) {
+        text_device();  // the environment is settled on this thread, before the other one starts
+        std::thread([] { text_context(); }).detach();
+      }
+      return;
+    }
   }
+} g_eager_server_context;
+
+// Which device, and -- before anything starts CUDA in this process -- only that one visible (as in
+// dropin.cpp: seconds of start-up per process on an 8-GPU node otherwise). Environment work:
+// called from the main thread (static initialisation or the first use), once.
+int text_device() {
+  static int device = -1;
+  if (device >= 0) return device;
   const char* v = getenv("QB200_TEXT_DEVICE");
   if (!v || !*v) v = getenv("QB200_DEVICE");
-  int device = (v && *v) ? atoi(v) : 0;
-  // As in dropin.cpp: a process that has not started CUDA yet makes only its own GPU visible
-  // (seconds of start-up per process on an 8-GPU node otherwise).
+  device = (v && *v) ? atoi(v) : 0;
+  if (device < 0) device = 0;
   const char* vis = getenv("CUDA_VISIBLE_DEVICES");
   const char* pin = getenv("QB200_PIN_VISIBLE");
   if ((!vis || !*vis) && !(pin && *pin == '0')) {
@@ -102,16 +133,27 @@ qb200_context* text_context() {
     }
     if (total > 1) {
       char buf[16];
-      snprintf(buf, sizeof buf, "%d", ((device % total) + total) % total);
+      snprintf(buf, sizeof buf, "%d", device % total);
       setenv("CUDA_VISIBLE_DEVICES", buf, 1);
       device = 0;
     }
   }
+  return device;
+}
+
+qb200_context* text_context_create() {
+  const char* st = getenv("QB200_DROPIN_STATS");
+  if (st && *st && *st != '0') {
+    g_tstats.on = true;
+    atexit(print_text_stats);
+  }
+  int device = text_device();
   const int n = qb200_device_count();
   if (n <= 0) critical("qunundrum_b200: no CUDA device (there is no CPU path).");
   device = ((device % n) + n) % n;
-  if (0 != qb200_create(device, &g_text_ctx)) critical("qunundrum_b200: %s", qb200_last_error());
-  return g_text_ctx;
+  qb200_context* ctx = NULL;
+  if (0 != qb200_create(device, &ctx)) critical("qunundrum_b200: %s", qb200_last_error());
+  return ctx;
 }
 
 // The exporter's value loop: n cells, then the total error.

@@ -44,4 +44,6 @@ out = {
             "duration-weighted over them",
 }
 json.dump(out, open(os.path.join(ROOT, "profiles", "fused2d_latest.json"), "w"), indent=1)
+if os.path.isdir(os.path.join(ROOT, "gpurun_out")):   # on a GPU box: bring it home too
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fused2d_latest.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
