@@ -242,12 +242,16 @@ int qb200_resident_collapse2d(qb200_resident *resident, int axis, const uint32_t
                               uint32_t n_dst, const uint32_t *src_begin, const uint32_t *src_index,
                               uint32_t max_dimension, long double *out);
 
-/* "%.24Lg\n" lines of the slices [first, first + count): slice first + i occupies
- * text[offsets[i], offsets[i + 1]) -- its cells, then its tail. One exporter launch per slice,
- * enqueued back to back, no upload, one synchronisation; *text points into pinned memory owned
- * by the resident, valid until its next call. offsets: count + 1 entries. */
+/* "%.24Lg\\n" lines of the slices [first, first + count): slice first + i occupies
+ * text[offsets[i], offsets[i] + lengths[i]) -- its cells, then its tail. One exporter launch per
+ * slice, enqueued back to back, no upload, one synchronisation; *text points into pinned memory
+ * owned by the resident, valid until the call after the next one (two buffer sets).
+ * qb200_resident_format_prefetch starts the same work for a batch and returns at once: a following
+ * qb200_resident_format of exactly that batch only waits for it -- the caller writes batch k to its
+ * file while batch k + 1 is formatted. offsets, lengths: count entries each. */
 int qb200_resident_format(qb200_resident *resident, uint32_t first, uint32_t count,
-                          const char **text, size_t *offsets);
+                          const char **text, size_t *offsets, size_t *lengths);
+int qb200_resident_format_prefetch(qb200_resident *resident, uint32_t first, uint32_t count);
 
 /* ---- text import: "%Lg" numbers ------------------------------------------------
  *

@@ -32,14 +32,22 @@ struct qb200_resident {
   uint64_t total = 0;             // 16-byte units
   ulonglong2* d_cells = nullptr;
   int* d_status = nullptr;
-  // export: per-call scratch
-  char* d_text = nullptr;
-  size_t d_text_bytes = 0;
-  unsigned long long* d_lens = nullptr;
-  size_t d_lens_count = 0;
-  char* h_text = nullptr;
-  size_t h_text_bytes = 0;
-  unsigned long long* h_lens = nullptr;
+  // export: two buffer sets, so that a batch can be formatted while the caller still writes the
+  // previous one (qb200_resident_format_prefetch)
+  struct TextSet {
+    char* d_text = nullptr;
+    size_t d_text_bytes = 0;
+    unsigned long long* d_lens = nullptr;
+    size_t lens_count = 0;
+    char* h_text = nullptr;
+    size_t h_text_bytes = 0;
+    unsigned long long* h_lens = nullptr;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+    uint32_t first = 0, count = 0;
+    std::vector<size_t> at;   // slice i of the batch starts at at[i] (stride: its capacity)
+  } text[2];
+  int text_cur = 0;           // the set the last qb200_resident_format returned
   void* h_stage[2] = {nullptr, nullptr};
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
 };
@@ -72,10 +80,15 @@ void resident_free(qb200_resident* r) {
   cudaSetDevice(r->view.device);
   if (r->d_cells) cudaFree(r->d_cells);
   if (r->d_status) cudaFree(r->d_status);
-  if (r->d_text) cudaFree(r->d_text);
-  if (r->d_lens) cudaFree(r->d_lens);
-  if (r->h_text) cudaFreeHost(r->h_text);
-  if (r->h_lens) cudaFreeHost(r->h_lens);
+  for (int k = 0; k < 2; k++) {
+    qb200_resident::TextSet& t = r->text[k];
+    if (t.in_flight) cudaEventSynchronize(t.done);
+    if (t.d_text) cudaFree(t.d_text);
+    if (t.d_lens) cudaFree(t.d_lens);
+    if (t.h_text) cudaFreeHost(t.h_text);
+    if (t.h_lens) cudaFreeHost(t.h_lens);
+    if (t.done) cudaEventDestroy(t.done);
+  }
   for (int k = 0; k < 2; k++) {
     if (r->h_stage[k]) cudaFreeHost(r->h_stage[k]);
     if (r->stage_done[k]) cudaEventDestroy(r->stage_done[k]);
@@ -217,67 +230,83 @@ int qb200_resident_collapse2d(qb200_resident* r, int axis, const uint32_t* dimen
   return 0;
 }
 
-int qb200_resident_format(qb200_resident* r, uint32_t first, uint32_t count, const char** text,
-                          size_t* offsets) {
-  if (!r || !text || !offsets) return set_error(-1, "null argument");
-  if ((uint64_t)first + count > r->n) return set_error(-2, "slice range outside the resident distribution");
-  *text = nullptr;
-  offsets[0] = 0;
-  if (count == 0) return 0;
-  QC_CUDA(cudaSetDevice(r->view.device));
+// Enqueue the export of the slices [first, first + count) into buffer set `k`: one exporter launch
+// per slice (its cells and its tail), the lengths and the text (at the slices' capacities) copied
+// to pinned memory behind them; no synchronisation.
+static int format_enqueue(qb200_resident* r, int k, uint32_t first, uint32_t count) {
+  qb200_resident::TextSet& t = r->text[k];
   cudaStream_t st = r->view.stream;
-  std::vector<size_t> cap(count), at(count + 1, 0);
-  for (uint32_t i = 0; i < count; i++) {
-    cap[i] = (qb200_text_bound(r->cells_of[first + i] + 1) + 63) & ~size_t(63);
-    at[i + 1] = at[i] + cap[i];
+  if (t.in_flight) {
+    QC_CUDA(cudaEventSynchronize(t.done));
+    t.in_flight = false;
   }
-  if (r->d_text_bytes < at[count] + 64) {
-    if (r->d_text) cudaFree(r->d_text);
-    r->d_text = nullptr;
-    r->d_text_bytes = 0;
-    QC_CUDA(cudaMalloc(&r->d_text, at[count] + 64));
-    r->d_text_bytes = at[count] + 64;
+  t.first = first;
+  t.count = count;
+  t.at.assign(count + 1, 0);
+  for (uint32_t i = 0; i < count; i++)
+    t.at[i + 1] = t.at[i] + ((qb200_text_bound(r->cells_of[first + i] + 1) + 63) & ~size_t(63));
+  const size_t total = t.at[count];
+  if (t.d_text_bytes < total + 64) {
+    if (t.d_text) cudaFree(t.d_text);
+    if (t.h_text) cudaFreeHost(t.h_text);
+    t.d_text = t.h_text = nullptr;
+    t.d_text_bytes = t.h_text_bytes = 0;
+    QC_CUDA(cudaMalloc(&t.d_text, total + 64));
+    QC_CUDA(cudaHostAlloc(&t.h_text, total + 64, cudaHostAllocDefault));
+    t.d_text_bytes = t.h_text_bytes = total + 64;
   }
-  if (r->d_lens_count < count) {
-    if (r->d_lens) cudaFree(r->d_lens);
-    if (r->h_lens) cudaFreeHost(r->h_lens);
-    r->d_lens = nullptr;
-    r->h_lens = nullptr;
-    r->d_lens_count = 0;
-    QC_CUDA(cudaMalloc(&r->d_lens, count * sizeof(unsigned long long)));
-    QC_CUDA(cudaHostAlloc(&r->h_lens, count * sizeof(unsigned long long), cudaHostAllocDefault));
-    r->d_lens_count = count;
+  if (t.lens_count < count) {
+    if (t.d_lens) cudaFree(t.d_lens);
+    if (t.h_lens) cudaFreeHost(t.h_lens);
+    t.d_lens = t.h_lens = nullptr;
+    t.lens_count = 0;
+    QC_CUDA(cudaMalloc(&t.d_lens, count * sizeof(unsigned long long)));
+    QC_CUDA(cudaHostAlloc(&t.h_lens, count * sizeof(unsigned long long), cudaHostAllocDefault));
+    t.lens_count = count;
   }
-  // one exporter launch per slice (cells + its tail), back to back, one synchronisation
+  if (!t.done) QC_CUDA(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
   for (uint32_t i = 0; i < count; i++) {
     const int rc = qb200_text_format_device(r->ctx, QB200_TEXT_X87, r->d_cells + r->offset[first + i],
-                                            r->cells_of[first + i] + 1, r->d_text + at[i], cap[i],
-                                            (uint64_t*)(r->d_lens + i), st);
+                                            r->cells_of[first + i] + 1, t.d_text + t.at[i], t.at[i + 1] - t.at[i],
+                                            (uint64_t*)(t.d_lens + i), st);
     if (rc) return rc;
   }
-  QC_CUDA(cudaMemcpyAsync(r->h_lens, r->d_lens, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  QC_CUDA(cudaStreamSynchronize(st));
-  size_t total = 0;
+  QC_CUDA(cudaMemcpyAsync(t.h_lens, t.d_lens, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (total) QC_CUDA(cudaMemcpyAsync(t.h_text, t.d_text, total, cudaMemcpyDeviceToHost, st));
+  QC_CUDA(cudaEventRecord(t.done, st));
+  t.in_flight = true;
+  return 0;
+}
+
+int qb200_resident_format_prefetch(qb200_resident* r, uint32_t first, uint32_t count) {
+  if (!r) return set_error(-1, "null argument");
+  if ((uint64_t)first + count > r->n) return set_error(-2, "slice range outside the resident distribution");
+  if (count == 0) return 0;
+  QC_CUDA(cudaSetDevice(r->view.device));
+  return format_enqueue(r, r->text_cur ^ 1, first, count);
+}
+
+int qb200_resident_format(qb200_resident* r, uint32_t first, uint32_t count, const char** text,
+                          size_t* offsets, size_t* lengths) {
+  if (!r || !text || !offsets || !lengths) return set_error(-1, "null argument");
+  if ((uint64_t)first + count > r->n) return set_error(-2, "slice range outside the resident distribution");
+  *text = nullptr;
+  if (count == 0) return 0;
+  QC_CUDA(cudaSetDevice(r->view.device));
+  int k = r->text_cur ^ 1;   // a prefetched batch, if it is this one
+  if (!(r->text[k].in_flight && r->text[k].first == first && r->text[k].count == count)) {
+    if (int rc = format_enqueue(r, k, first, count)) return rc;
+  }
+  qb200_resident::TextSet& t = r->text[k];
+  QC_CUDA(cudaEventSynchronize(t.done));
+  t.in_flight = false;
   for (uint32_t i = 0; i < count; i++) {
-    if (r->h_lens[i] > cap[i]) return set_error(-3, "text buffer overflow (internal)");
-    offsets[i] = total;
-    total += (size_t)r->h_lens[i];
+    if (t.h_lens[i] > t.at[i + 1] - t.at[i]) return set_error(-3, "text buffer overflow (internal)");
+    offsets[i] = t.at[i];
+    lengths[i] = (size_t)t.h_lens[i];
   }
-  offsets[count] = total;
-  if (r->h_text_bytes < total) {
-    if (r->h_text) cudaFreeHost(r->h_text);
-    r->h_text = nullptr;
-    r->h_text_bytes = 0;
-    const size_t want = std::max(total + total / 8, size_t(1) << 20);
-    QC_CUDA(cudaHostAlloc(&r->h_text, want, cudaHostAllocDefault));
-    r->h_text_bytes = want;
-  }
-  for (uint32_t i = 0; i < count; i++)
-    if (r->h_lens[i])
-      QC_CUDA(cudaMemcpyAsync(r->h_text + offsets[i], r->d_text + at[i], (size_t)r->h_lens[i],
-                              cudaMemcpyDeviceToHost, st));
-  QC_CUDA(cudaStreamSynchronize(st));
-  *text = r->h_text;
+  r->text_cur = k;
+  *text = t.h_text;
   return 0;
 }
 

@@ -232,22 +232,19 @@ QHD dd sample_axis(const SamplerView& s, const SamplerSlice& sl, int32_t k, uint
   return x;
 }
 
-// One sample from the words w[0 .. dims + 1] (the reference's draws, in its order: slice
-// pivot, region pivot, one fraction per axis).
-QHD void sample_one(const SamplerView& s, const uint64_t* w, int mode, SampleOut* out) {
-  out->sq0_hi = out->sq0_lo = out->sq1_hi = out->sq1_lo = 0.0;
-  out->x0 = out->x1 = 0.0;
-  out->slice = out->cell = -1;
-  out->exact = 0;
+// First half of a sample: the slice the reference's walk over the slice totals stops at
+// (src/distribution.cpp:359-409), or n_slices (out of bounds: the reference returns FALSE).
+QHD uint32_t sample_slice(const SamplerView& s, uint64_t w0, int mode, int* exact) {
   bool ok = true;
-  X87 p = x87_pivot_inclusive(w[0]);
+  X87 p = x87_pivot_inclusive(w0);
   if (s.scale_by_total) p = x87_mul(p, x87_load(&s.dist_total, &ok));
-  const uint32_t i = seg_find(s.totals, s.totals_coarse, s.n_slices, s.totals_abs_sum, p, mode,
-                              &out->exact);
-  if (i >= s.n_slices) {
-    out->status = kSampleOutOfBounds;
-    return;
-  }
+  return seg_find(s.totals, s.totals_coarse, s.n_slices, s.totals_abs_sum, p, mode, exact);
+}
+
+// Second half: the region inside slice i (src/distribution_slice.cpp:167-228) and the two axis
+// draws (src/sample.cpp:24-77). w: the sample's words (w[0] is not read again).
+QHD void sample_in_slice(const SamplerView& s, uint32_t i, const uint64_t* w, int mode, SampleOut* out) {
+  bool ok = true;
   out->slice = (int32_t)i;
   const SamplerSlice sl = s.slices[i];
   const X87 p2 = x87_mul(x87_pivot_inclusive(w[1]), x87_load(s.totals + i, &ok));
@@ -273,6 +270,23 @@ QHD void sample_one(const SamplerView& s, const uint64_t* w, int mode, SampleOut
     out->sq0_hi = q.hi; out->sq0_lo = q.lo;
     out->x0 = sl.c0 < 0 ? -x.hi : x.hi;
   }
+}
+
+QHD void sample_out_clear(SampleOut* out) {
+  out->sq0_hi = out->sq0_lo = out->sq1_hi = out->sq1_lo = 0.0;
+  out->x0 = out->x1 = 0.0;
+  out->slice = out->cell = -1;
+  out->exact = 0;
+  out->status = kSampleOutOfBounds;
+}
+
+// One sample from the words w[0 .. dims + 1] (the reference's draws, in its order: slice
+// pivot, region pivot, one fraction per axis).
+QHD void sample_one(const SamplerView& s, const uint64_t* w, int mode, SampleOut* out) {
+  sample_out_clear(out);
+  const uint32_t i = sample_slice(s, w[0], mode, &out->exact);
+  if (i >= s.n_slices) return;  // status: out of bounds
+  sample_in_slice(s, i, w, mode, out);
 }
 
 // Sum of the squares of the n samples of one estimate, in sample order (fixed => reproducible).

@@ -84,8 +84,9 @@ struct Stats {
   unsigned long abi_calls;
   unsigned long abi_slices;
   unsigned long hits;
+  double context_seconds;  // qb200_create: CUDA start-up of this process
   bool on;
-} g_stats = {0.0, 0.0, 0, 0, 0, 0, false};
+} g_stats = {0.0, 0.0, 0, 0, 0, 0, 0.0, false};
 
 double now_s() {
   struct timespec ts;
@@ -100,10 +101,10 @@ void print_stats() {
       line, sizeof line,
       "qunundrum_b200 drop-in: %lu slice calls, %.3f s inside the drop-in functions (%.1f us per "
       "call); %lu C-ABI calls for %lu slices (%.1f slices per call, %.3f s), %lu calls served from "
-      "prefetched batches\n",
+      "prefetched batches; CUDA context created in %.3f s\n",
       g_stats.calls, g_stats.seconds, 1e6 * g_stats.seconds / (double)g_stats.calls, g_stats.abi_calls,
       g_stats.abi_slices, g_stats.abi_calls ? (double)g_stats.abi_slices / (double)g_stats.abi_calls : 0.0,
-      g_stats.abi_seconds, g_stats.hits);
+      g_stats.abi_seconds, g_stats.hits, g_stats.context_seconds);
   if (len > 0) (void)!write(2, line, (size_t)(len < (int)sizeof line ? len : (int)sizeof line - 1));
 }
 
@@ -174,9 +175,11 @@ qb200_context* context() {
   if (n <= 0) critical("qunundrum_b200: no CUDA device (there is no CPU path).");
   if (device < 0) device = ((local - 1) % n + n) % n;
   if (device >= n) device %= n;
+  const double t0 = now_s();
   if (0 != qb200_create(device, &g_ctx)) {
     critical("qunundrum_b200: %s", qb200_last_error());
   }
+  g_stats.context_seconds = now_s() - t0;
   const char* st = getenv("QB200_DROPIN_STATS");
   if (st && *st && *st != '0') {
     g_stats.on = true;
@@ -363,7 +366,10 @@ void lookup_2d(const Exported& e, const Parameters* const parameters, int method
           if (it->first < base) base = it->first;
         }
       }
-      const bool again = !here.empty();  // this dimension was speculated on before and missed c
+      // this dimension was speculated on before and missed c although no smaller dimension has
+      // been seen: the first-call guess ("dimension heuristic") was wrong, the client runs at a
+      // fixed dimension -- take everything that is left
+      const bool again = !here.empty() && base == dimension;
       if (first_call) {
         if (dimension % 4 == 0 && may_be_asked_at(dimension, dimension / 4, c, m, false, 0)) base = dimension / 4;
         else if (dimension % 2 == 0 && may_be_asked_at(dimension, dimension / 2, c, m, false, 0)) base = dimension / 2;

@@ -72,7 +72,7 @@ struct Registry {
   std::vector<uint32_t> dimension;   // of resident slice i
   // the exporter's look-ahead: text of the resident slices [text_first, text_first + text_count)
   const char* text;
-  std::vector<size_t> offsets;
+  std::vector<size_t> offsets, lengths;
   uint32_t text_first, text_count;
   double upload_s, collapse_s, format_s;
   unsigned long uploads, collapses, formats, text_hits;
@@ -233,6 +233,18 @@ void collapse(Linear_Distribution* const dst, const Distribution* const src, con
   dst->total_error = src->total_error;
 }
 
+// The exporter's look-ahead from resident slice `first`: up to 64 slices or ~96 MB of text.
+uint32_t batch_from(uint32_t first) {
+  const uint32_t total = (uint32_t)g_reg.dimension.size();
+  uint32_t count = 0;
+  size_t bytes = 0;
+  while (first + count < total && count < 64 && bytes < (size_t(96) << 20)) {
+    bytes += 30 * ((size_t)g_reg.dimension[first + count] * g_reg.dimension[first + count] + 1);
+    count++;
+  }
+  return count;
+}
+
 }  // namespace
 
 // For dropin_text.cpp (caller holds qb200_dropin_text_mutex()): the "%.24Lg\n" lines of a slice
@@ -247,26 +259,26 @@ bool qb200_dropin_resident_text(const long double* cells, size_t n, long double 
   const uint32_t i = it->second.index;
   if (NULL == g_reg.text || i < g_reg.text_first || i >= g_reg.text_first + g_reg.text_count) {
     const double t0 = cnow();
-    // look ahead: up to 64 slices or ~96 MB of text
-    const uint32_t total = (uint32_t)g_reg.dimension.size();
-    uint32_t count = 0;
-    size_t bytes = 0;
-    while (i + count < total && count < 64 && bytes < (size_t(96) << 20)) {
-      bytes += 30 * ((size_t)g_reg.dimension[i + count] * g_reg.dimension[i + count] + 1);
-      count++;
-    }
-    g_reg.offsets.assign(count + 1, 0);
-    if (0 != qb200_resident_format(g_reg.resident, i, count, &g_reg.text, g_reg.offsets.data())) {
+    const uint32_t count = batch_from(i);
+    g_reg.offsets.assign(count, 0);
+    g_reg.lengths.assign(count, 0);
+    if (0 != qb200_resident_format(g_reg.resident, i, count, &g_reg.text, g_reg.offsets.data(),
+                                   g_reg.lengths.data())) {
       critical("distribution_slice_export(): %s", qb200_last_error());
     }
     g_reg.text_first = i;
     g_reg.text_count = count;
+    // ... and the batch after it is formatted while the caller writes this one
+    const uint32_t next = batch_from(i + count);
+    if (next && 0 != qb200_resident_format_prefetch(g_reg.resident, i + count, next)) {
+      critical("distribution_slice_export(): %s", qb200_last_error());
+    }
     g_reg.formats++;
     g_reg.format_s += cnow() - t0;
   }
   const uint32_t k = i - g_reg.text_first;
   *text = g_reg.text + g_reg.offsets[k];
-  *len = g_reg.offsets[k + 1] - g_reg.offsets[k];
+  *len = g_reg.lengths[k];
   g_reg.text_hits++;
   return true;
 }

@@ -105,7 +105,17 @@ struct EagerServerContext {
       const char* n = sizes[i] ? getenv(sizes[i]) : NULL;
       if (atoi(r) == 0 && (!n || atoi(n) > 1)) {
         text_device();  // the environment is settled on this thread, before the other one starts
-        std::thread([] { text_context(); }).detach();
+        // ... after the clients have created theirs (context creations of one node queue up in
+        // the driver, and the clients' are on the critical path): QB200_EAGER_DELAY_MS, default 1500
+        const char* dl = getenv("QB200_EAGER_DELAY_MS");
+        const int delay_ms = (dl && *dl) ? atoi(dl) : 1500;
+        std::thread([delay_ms] {
+          if (delay_ms > 0) {
+            struct timespec ts = {delay_ms / 1000, (long)(delay_ms % 1000) * 1000000L};
+            nanosleep(&ts, NULL);
+          }
+          text_context();
+        }).detach();
       }
       return;
     }

@@ -151,7 +151,8 @@ def lib():
     L.qb200_resident_cells.argtypes = [vp]
     L.qb200_resident_cells.restype = C.c_uint64
     L.qb200_resident_collapse2d.argtypes = [vp, C.c_int, vp, u32, vp, vp, u32, vp]
-    L.qb200_resident_format.argtypes = [vp, u32, u32, C.POINTER(vp), vp]
+    L.qb200_resident_format.argtypes = [vp, u32, u32, C.POINTER(vp), vp, vp]
+    L.qb200_resident_format_prefetch.argtypes = [vp, u32, u32]
     _lib = L
     return L
 
@@ -811,13 +812,19 @@ class Resident:
                                                lst.ctypes.data, md, out.ctypes.data), "qb200_resident_collapse2d")
         return np.array(order, dtype=np.int32), out, np.array([totals[c] for c in order], dtype=np.longdouble)
 
-    def format(self, first: int, count: int):
-        """The "%.24Lg\\n" text of the slices [first, first + count): a list of bytes objects."""
+    def format(self, first: int, count: int, prefetch_next: int = 0):
+        """The "%.24Lg\\n" text of the slices [first, first + count): a list of bytes objects.
+        prefetch_next: start formatting that many slices after them before returning."""
         text = C.c_void_p()
-        offsets = np.zeros(count + 1, dtype=np.uint64)
-        _check(lib().qb200_resident_format(self.h, first, count, C.byref(text), offsets.ctypes.data),
-               "qb200_resident_format")
-        return [C.string_at(text.value + int(offsets[i]), int(offsets[i + 1] - offsets[i])) for i in range(count)]
+        offsets = np.zeros(max(1, count), dtype=np.uint64)
+        lengths = np.zeros(max(1, count), dtype=np.uint64)
+        _check(lib().qb200_resident_format(self.h, first, count, C.byref(text), offsets.ctypes.data,
+                                           lengths.ctypes.data), "qb200_resident_format")
+        out = [C.string_at(text.value + int(offsets[i]), int(lengths[i])) for i in range(count)]
+        if prefetch_next:
+            _check(lib().qb200_resident_format_prefetch(self.h, first + count, prefetch_next),
+                   "qb200_resident_format_prefetch")
+        return out
 
 
 def linear_distribution_init_collapse_d(distribution, ctx=None):

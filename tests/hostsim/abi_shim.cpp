@@ -310,7 +310,8 @@ int qb200_slice1d_compute(qb200_context*, const qb200_params* p, int kind, int r
 struct qb200_resident {
   std::vector<std::vector<long double>> cells;
   std::vector<long double> tails;
-  std::vector<char> text;
+  std::vector<char> text[2];
+  int cur = 0;
 };
 
 int qb200_resident_create(qb200_context*, uint32_t n, const uint64_t* n_cells, const long double* const* cells,
@@ -344,20 +345,24 @@ int qb200_resident_collapse2d(qb200_resident* r, int axis, const uint32_t* dimen
   return 0;
 }
 
-int qb200_resident_format(qb200_resident* r, uint32_t first, uint32_t count, const char** text, size_t* offsets) {
+int qb200_resident_format(qb200_resident* r, uint32_t first, uint32_t count, const char** text, size_t* offsets,
+                          size_t* lengths) {
   size_t cap = 64;
   for (uint32_t i = 0; i < count; i++) cap += 34 * (r->cells[first + i].size() + 1);
-  r->text.resize(cap);
+  std::vector<char>& buf = r->text[r->cur ^= 1];   // two sets, as the library
+  buf.resize(cap);
   size_t pos = 0;
   for (uint32_t i = 0; i < count; i++) {
     offsets[i] = pos;
     const std::vector<long double>& c = r->cells[first + i];
-    pos += hostsim_text_format_ld(c.data(), c.size(), r->text.data() + pos, 0, nullptr);
-    pos += hostsim_text_format_ld(&r->tails[first + i], 1, r->text.data() + pos, 0, nullptr);
+    pos += hostsim_text_format_ld(c.data(), c.size(), buf.data() + pos, 0, nullptr);
+    pos += hostsim_text_format_ld(&r->tails[first + i], 1, buf.data() + pos, 0, nullptr);
+    lengths[i] = pos - offsets[i];
   }
-  offsets[count] = pos;
-  *text = r->text.data();
+  *text = buf.data();
   return 0;
 }
+
+int qb200_resident_format_prefetch(qb200_resident*, uint32_t, uint32_t) { return 0; }
 
 }  // extern "C"

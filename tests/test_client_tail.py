@@ -252,6 +252,11 @@ def test_collapse_and_export_of_a_resident_distribution(gpu_ctx):
             assert texts[i] == gpu_ctx.text_format(s.norm_matrix, s.total_error), i
         assert res.format(3, 2) == texts[3:5] and res.format(n - 1, 1) == texts[-1:]
         assert res.format(0, 0) == []
+        # look-ahead: the next batch is formatted while the caller still holds this one
+        first = res.format(0, 4, prefetch_next=3)
+        assert first == texts[0:4]
+        assert res.format(4, 3) == texts[4:7] and first == texts[0:4]
+        assert res.format(2, 5, prefetch_next=2) == texts[2:7] and res.format(0, 1) == texts[0:1]   # a prefetch left unused
     finally:
         res.close()
 
