@@ -184,11 +184,12 @@ __device__ __forceinline__ void diagk_tile(const DiagKConst& c, uint32_t tb, con
   out[g] = o;
 }
 
-// Persistent CTAs: the grid is one wave (SMs x resident CTAs), every CTA walks the tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... and owns ONE scratch area of 128 x (5 k + 9) words for
-// all of them. The scratch of a launch is then ~150 MB that is rewritten in place (it stays in L2)
-// instead of 1.3 KB per SAMPLE streamed through DRAM once (ncu, round 1: 0.95 GB written and
-// 0.27 GB read per launch of 303,104 samples against 0.17 GB of algorithmic traffic).
+// The grid is either one CTA per tile (default) or one wave of persistent CTAs that walk the tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... (QB200_DIAGK_CTAS_PER_SM); a CTA owns ONE scratch area of
+// 128 x (5 k + 9) words for all its tiles. Measured (B200, m = 2048, 303,104 samples): the persistent
+// form keeps the scratch at 888 x 168 KB = 150 MB instead of 400 MB, but that is still more than the
+// L2 holds next to the inputs -- DRAM traffic 1.23 GB per launch either way, 1.93 ms against 1.76 ms
+// (profiles/r02_diagk_ncu_full.txt) -- so one CTA per tile stays the default.
 __global__ void __launch_bounds__(QB_DIAGK_CTA, 6) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
                                                 const int32_t* __restrict__ eta,
                                                 const RawX87* __restrict__ pivot,

@@ -247,22 +247,26 @@ static int format_enqueue(qb200_resident* r, int k, uint32_t first, uint32_t cou
     t.at[i + 1] = t.at[i] + ((qb200_text_bound(r->cells_of[first + i] + 1) + 63) & ~size_t(63));
   const size_t total = t.at[count];
   if (t.d_text_bytes < total + 64) {
+    const size_t prev = t.d_text_bytes;
     if (t.d_text) cudaFree(t.d_text);
     if (t.h_text) cudaFreeHost(t.h_text);
     t.d_text = t.h_text = nullptr;
     t.d_text_bytes = t.h_text_bytes = 0;
-    QC_CUDA(cudaMalloc(&t.d_text, total + 64));
-    QC_CUDA(cudaHostAlloc(&t.h_text, total + 64, cudaHostAllocDefault));
-    t.d_text_bytes = t.h_text_bytes = total + 64;
+    // (pinning costs milliseconds per MB on a virtual machine: grow in steps of at least 50 %)
+    const size_t want = std::max(total + 64, prev + prev / 2);
+    QC_CUDA(cudaMalloc(&t.d_text, want));
+    QC_CUDA(cudaHostAlloc(&t.h_text, want, cudaHostAllocDefault));
+    t.d_text_bytes = t.h_text_bytes = want;
   }
   if (t.lens_count < count) {
     if (t.d_lens) cudaFree(t.d_lens);
     if (t.h_lens) cudaFreeHost(t.h_lens);
     t.d_lens = t.h_lens = nullptr;
     t.lens_count = 0;
-    QC_CUDA(cudaMalloc(&t.d_lens, count * sizeof(unsigned long long)));
-    QC_CUDA(cudaHostAlloc(&t.h_lens, count * sizeof(unsigned long long), cudaHostAllocDefault));
-    t.lens_count = count;
+    const size_t room = std::max<size_t>(count, 64);
+    QC_CUDA(cudaMalloc(&t.d_lens, room * sizeof(unsigned long long)));
+    QC_CUDA(cudaHostAlloc(&t.h_lens, room * sizeof(unsigned long long), cudaHostAllocDefault));
+    t.lens_count = room;
   }
   if (!t.done) QC_CUDA(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
   for (uint32_t i = 0; i < count; i++) {

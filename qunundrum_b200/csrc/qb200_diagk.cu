@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include <cfloat>
 #include <cmath>
@@ -133,7 +134,11 @@ static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const i
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diagk, QB_DIAGK_CTA, shmem) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess || per_sm < 1)
       return -100;
-    s->resident_ctas = (uint32_t)(per_sm * sms);
+    // QB200_DIAGK_CTAS_PER_SM: 0 = one CTA (and one scratch area) per tile; N = at most N per SM
+    const char* env = getenv("QB200_DIAGK_CTAS_PER_SM");
+    const int want = (env && *env) ? atoi(env) : 0;
+    if (want > 0 && want < per_sm) per_sm = want;
+    s->resident_ctas = want == 0 ? 0xffffffffu : (uint32_t)(per_sm * sms);
   }
   const uint32_t grid = (uint32_t)std::min<size_t>(Bp / QB_DIAGK_CTA, s->resident_ctas);
   if (s->cols_j.reserve(Bp * c.wj * 4) || s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * scr * 4)) return -100;

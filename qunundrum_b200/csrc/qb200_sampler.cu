@@ -77,8 +77,6 @@ struct qb200_sampler {
   Buf cells, coarse, slices, totals, geo, scratch;
   // per-call staging
   Buf d_words, d_off, d_out, d_sums, d_status;
-  Buf d_slice_of, d_rank_of, d_order, d_counts;   // the bucketed path (kernels_sampler.cuh)
-  int bucketed = 1;                               // QB200_SAMPLER_BUCKETS=0: one kernel, draw order
   Buf h_sums, h_status, h_words, h_off, h_out;
   unsigned long long* d_exact = nullptr;
   int force_exact = 0;
@@ -93,36 +91,12 @@ struct qb200_sampler {
   }
 };
 
-// All samples of a call: bucketed by slice between the two searches (large calls), or the single
-// kernel in draw order. `accumulate_exact`: phase one adds its replays to d_exact itself.
+// All samples of a call: one thread per sample, in draw order.
 static int enqueue_samples(qb200_sampler* s, const uint64_t* d_words, const uint64_t* d_off, uint32_t n,
                            uint64_t total, cudaStream_t st) {
-  SampleOut* out = s->d_out.as<SampleOut>();
-  if (!s->bucketed || total < 16384 || total > 0xfffffff0ull) {
-    k_sample<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(s->view, d_words, d_off, n, total,
-                                                             s->force_exact, out);
-    *s->launches += 1;
-    return 0;
-  }
-  const uint32_t buckets = s->view.n_slices + 1;
-  if (int rc = s->d_slice_of.reserve(total * 4)) return rc;
-  if (int rc = s->d_rank_of.reserve(total * 4)) return rc;
-  if (int rc = s->d_order.reserve(total * 4)) return rc;
-  if (int rc = s->d_counts.reserve((size_t)(2 * buckets + 2) * 4)) return rc;
-  unsigned int* counts = s->d_counts.as<unsigned int>();
-  unsigned int* starts = counts + buckets;
-  QS_CUDA(cudaMemsetAsync(counts, 0, (size_t)buckets * 4, st));
-  const unsigned blocks = (unsigned)((total + 127) / 128);
-  k_sample_slices<<<blocks, 128, 0, st>>>(s->view, d_words, d_off, n, total, s->force_exact,
-                                          s->d_slice_of.as<uint32_t>(), s->d_rank_of.as<uint32_t>(), counts,
-                                          s->d_exact);
-  k_sample_offsets<<<1, 1024, 0, st>>>(counts, buckets, starts);
-  k_sample_order<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s->d_slice_of.as<uint32_t>(),
-                                                                 s->d_rank_of.as<uint32_t>(), starts, total,
-                                                                 s->d_order.as<uint32_t>());
-  k_sample_cells<<<blocks, 128, 0, st>>>(s->view, d_words, d_off, n, total, s->force_exact,
-                                         s->d_order.as<uint32_t>(), s->d_slice_of.as<uint32_t>(), out);
-  *s->launches += 4;
+  k_sample<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(s->view, d_words, d_off, n, total,
+                                                           s->force_exact, s->d_out.as<SampleOut>());
+  *s->launches += 1;
   return 0;
 }
 
@@ -227,10 +201,6 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
   if (back.bad)
     return set_error(-14, "the distribution holds a denormal, infinite or NaN probability (not supported)");
   QS_CUDA(cudaMalloc(&s->d_exact, sizeof(unsigned long long)));
-  {
-    const char* b = getenv("QB200_SAMPLER_BUCKETS");
-    s->bucketed = !(b && *b == '0');
-  }
   SamplerView& v = s->view;
   v.cells = s->cells.as<RawX87>();
   v.coarse = s->coarse.as<SegCoarse>();

@@ -233,12 +233,13 @@ void collapse(Linear_Distribution* const dst, const Distribution* const src, con
   dst->total_error = src->total_error;
 }
 
-// The exporter's look-ahead from resident slice `first`: up to 64 slices or ~96 MB of text.
+// The exporter's look-ahead from resident slice `first`: up to 64 slices or ~32 MB of text (the
+// library keeps two pinned buffers of the largest batch; pinning is not free).
 uint32_t batch_from(uint32_t first) {
   const uint32_t total = (uint32_t)g_reg.dimension.size();
   uint32_t count = 0;
   size_t bytes = 0;
-  while (first + count < total && count < 64 && bytes < (size_t(96) << 20)) {
+  while (first + count < total && count < 64 && bytes < (size_t(32) << 20)) {
     bytes += 30 * ((size_t)g_reg.dimension[first + count] * g_reg.dimension[first + count] + 1);
     count++;
   }
