@@ -824,12 +824,14 @@ inline cudaError_t fused2d_launch_variant(const FusedPlan2D& f, const FusedArgs&
 }
 
 // Enqueue the fused kernel for one chunk (one launch per slice class present).
+// streams: where each class goes (nullptr: all three on st, one after the other).
 inline int fused2d_launch_chunk(const FusedPlan2D& f, FusedArgs args, size_t chunk,
-                                cudaStream_t st) {
+                                cudaStream_t st_all, const cudaStream_t* streams = nullptr) {
   const FusedChunk& c = f.chunks[chunk];
   for (int cl = 0; cl < 3; cl++) {
     const unsigned lo = c.class_tiles[cl], hi = c.class_tiles[cl + 1];
     if (lo >= hi) continue;
+    const cudaStream_t st = streams ? streams[cl] : st_all;
     args.k.tile_base = lo;
     args.k.tile_end = hi;
     const unsigned blocks = (hi - lo + QB_FUSED_WARPS - 1) / QB_FUSED_WARPS;

@@ -22,6 +22,7 @@ struct SegDesc {
   const RawX87* vals;
   SegCoarse* coarse;
   double* abs_out;
+  uint32_t* guide;   // seg_guide_size(blocks) + 1 entries
   uint32_t n;
   uint32_t pad;
 };
@@ -49,6 +50,9 @@ __global__ void __launch_bounds__(256) k_seg_build(const SegDesc* __restrict__ s
     seg_scan(s.coarse, nb);
     *s.abs_out = sh_abs;
   }
+  __syncthreads();
+  const uint32_t G = seg_guide_size(nb);
+  for (uint32_t u = threadIdx.x; u <= G; u += blockDim.x) s.guide[u] = seg_guide_entry(s.coarse, nb, G, u);
 }
 
 #define QB_TAU_SKIP 0xffffffffffffffffull

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -102,6 +103,12 @@ struct qb200_context {
   int device = 0;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // device-to-host copies of the synchronous API
+  // The three slice classes of the fused kernel are independent launches: the smaller two run on
+  // side streams next to class 0, so that the partial last waves of the three overlap instead of
+  // following each other (what is left of a GPU's share when one distribution is split over 8).
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
+  bool overlap_classes = true;         // QB200_OVERLAP_CLASSES=0: one stream (A/B)
   std::vector<cudaEvent_t> events;
   int sm_count = 0;
   uint64_t launches = 0;
@@ -511,9 +518,25 @@ FusedArgs fused_args_of(qb200_plan* plan, double* d_cells) {
                       plan->geo->gw.as<double>(), plan->fused_part.as<double>(), d_cells);
 }
 
-int enqueue_fused_chunk(qb200_plan* plan, const FusedArgs& args, size_t c, cudaStream_t st) {
-  if (fused2d_launch_chunk(plan->fused, args, c, st)) return fail(-100, "fused kernel launch failed");
+int enqueue_fused_chunk(qb200_plan* plan, const FusedArgs& args, size_t c, cudaStream_t st,
+                        bool overlap_classes = false) {
+  qb200_context* ctx = plan->ctx;
   const FusedChunk& fc = plan->fused.chunks[c];
+  int present = 0;
+  for (int cl = 0; cl < 3; cl++) present += fc.class_tiles[cl + 1] > fc.class_tiles[cl] ? 1 : 0;
+  if (overlap_classes && present > 1 && ctx->side[0]) {
+    // fork: classes 1 and 2 on the side streams, behind everything st holds so far; join after
+    QB_CUDA(cudaEventRecord(ctx->fork_ev, st));
+    const cudaStream_t streams[3] = {st, ctx->side[0], ctx->side[1]};
+    for (int k = 0; k < 2; k++) QB_CUDA(cudaStreamWaitEvent(ctx->side[k], ctx->fork_ev, 0));
+    if (fused2d_launch_chunk(plan->fused, args, c, st, streams)) return fail(-100, "fused kernel launch failed");
+    for (int k = 0; k < 2; k++) {
+      QB_CUDA(cudaEventRecord(ctx->join_ev[k], ctx->side[k]));
+      QB_CUDA(cudaStreamWaitEvent(st, ctx->join_ev[k], 0));
+    }
+  } else if (fused2d_launch_chunk(plan->fused, args, c, st)) {
+    return fail(-100, "fused kernel launch failed");
+  }
   for (int cl = 0; cl < 3; cl++)
     plan->ctx->launches += fc.class_tiles[cl + 1] > fc.class_tiles[cl] ? 1 : 0;
   return 0;
@@ -570,9 +593,18 @@ int qb200_create(int device, qb200_context** out) {
   ctx->sm_count = prop.multiProcessorCount;
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+    e = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete ctx;
     return fail(-100, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  {
+    const char* v = getenv("QB200_OVERLAP_CLASSES");
+    ctx->overlap_classes = !(v && *v == '0');
   }
   ctx->out_cells.pool = nullptr;
   *out = ctx;
@@ -584,6 +616,11 @@ void qb200_destroy(qb200_context* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int k = 0; k < 2; k++) {
+    if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+    if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]);
+  }
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
   if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
   if (ctx->text) qb200::text_state_destroy(ctx->text);
@@ -698,7 +735,7 @@ int qb200_plan_run(qb200_plan* plan, void* stream, double* d_cells, double* d_su
     if (int rc = enqueue_fused_prologue(plan, st)) return rc;
     const FusedArgs args = fused_args_of(plan, d_cells);
     for (size_t c = 0; c < plan->fused.chunks.size(); c++)
-      if (int rc = enqueue_fused_chunk(plan, args, c, st)) return rc;
+      if (int rc = enqueue_fused_chunk(plan, args, c, st, /*overlap_classes=*/ctx->overlap_classes)) return rc;
     return enqueue_fused_epilogue(plan, st, d_summary);
   }
   return run_plain_2d(plan, st, d_cells, d_summary);
@@ -767,7 +804,7 @@ static int run_sync(qb200_context* ctx, qb200_plan* pl, double* cells, long doub
     const FusedArgs args = fused_args_of(pl, d_cells);
     const size_t per = (size_t)pl->host.D * pl->host.D;
     for (size_t c = 0; c < nch; c++) {
-      if (int rc = enqueue_fused_chunk(pl, args, c, ctx->stream)) return rc;
+      if (int rc = enqueue_fused_chunk(pl, args, c, ctx->stream, ctx->overlap_classes)) return rc;
       QB_CUDA(cudaEventRecord(ctx->events[c], ctx->stream));
       QB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->events[c], 0));
       const FusedChunk& fc = pl->fused.chunks[c];

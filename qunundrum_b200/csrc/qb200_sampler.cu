@@ -74,7 +74,7 @@ struct qb200_sampler {
   cudaStream_t stream = nullptr;
   uint64_t* launches = nullptr;
   SamplerView view;
-  Buf cells, coarse, slices, totals, geo, scratch;
+  Buf cells, coarse, slices, totals, geo, scratch, guide;
   // per-call staging
   Buf d_words, d_off, d_out, d_sums, d_status;
   Buf h_sums, h_status, h_words, h_off, h_out;
@@ -123,7 +123,7 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
   std::vector<SamplerSlice> hs(n_slices);
   std::map<uint32_t, uint32_t> geo_off;
   std::vector<DD> geo;
-  uint64_t cell_off = 0, coarse_off = 0;
+  uint64_t cell_off = 0, coarse_off = 0, guide_off = 0;
   for (uint32_t i = 0; i < n_slices; i++) {
     const uint32_t D = dimension[i];
     if (D == 0 || (D & (D - 1)) != 0 || D > (1u << 20) || (dims == 2 && D > 4096))
@@ -147,19 +147,24 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
     sl.c0 = c0[i];
     sl.c1 = dims == 2 ? c1[i] : 0;
     sl.geo_off = geo_off[D];
-    sl.pad = 0;
+    sl.guide_off = (uint32_t)guide_off;
     sl.abs_sum = 0.0;
     cell_off += sl.n_cells;
-    coarse_off += (sl.n_cells + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK + 1;
+    const uint32_t nb = (sl.n_cells + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK;
+    coarse_off += nb + 1;
+    guide_off += seg_guide_size(nb) + 1;
   }
-  const uint64_t totals_coarse_off = coarse_off;
+  const uint64_t totals_coarse_off = coarse_off, totals_guide_off = guide_off;
   coarse_off += (n_slices + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK + 1;
+  guide_off += seg_guide_size((n_slices + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK) + 1;
+  if (guide_off > 0xffffffffull) return set_error(-12, "too many slices for the sampler's guide tables");
   s->n_cells = cell_off;
   if (int rc = s->cells.reserve(cell_off * sizeof(RawX87))) return rc;
   if (int rc = s->coarse.reserve(coarse_off * sizeof(SegCoarse))) return rc;
   if (int rc = s->slices.reserve((size_t)n_slices * sizeof(SamplerSlice))) return rc;
   if (int rc = s->totals.reserve((size_t)n_slices * sizeof(RawX87))) return rc;
   if (int rc = s->geo.reserve(geo.size() * sizeof(DD))) return rc;
+  if (int rc = s->guide.reserve(guide_off * sizeof(uint32_t))) return rc;
   // scratch: segment descriptors, the totals' abs sum, the "bad value" flag
   const size_t seg_bytes = ((size_t)n_slices + 1) * sizeof(SegDesc);
   if (int rc = s->scratch.reserve(seg_bytes + 64)) return rc;
@@ -179,12 +184,14 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
     segs[i].vals = s->cells.as<RawX87>() + hs[i].cell_off;
     segs[i].coarse = s->coarse.as<SegCoarse>() + hs[i].coarse_off;
     segs[i].abs_out = &(s->slices.as<SamplerSlice>()[i].abs_sum);
+    segs[i].guide = s->guide.as<uint32_t>() + hs[i].guide_off;
     segs[i].n = hs[i].n_cells;
     segs[i].pad = 0;
   }
   segs[n_slices].vals = s->totals.as<RawX87>();
   segs[n_slices].coarse = s->coarse.as<SegCoarse>() + totals_coarse_off;
   segs[n_slices].abs_out = d_tot_abs;
+  segs[n_slices].guide = s->guide.as<uint32_t>() + totals_guide_off;
   segs[n_slices].n = n_slices;
   segs[n_slices].pad = 0;
   QS_CUDA(cudaMemsetAsync(d_tot_abs, 0, 16, s->stream));
@@ -208,6 +215,12 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
   v.totals = s->totals.as<RawX87>();
   v.totals_coarse = s->coarse.as<SegCoarse>() + totals_coarse_off;
   v.geo = s->geo.as<dd>();
+  {
+    const char* g = getenv("QB200_SAMPLER_GUIDE");   // 0: plain binary searches (A/B, tests)
+    v.guide = (g && *g == '0') ? nullptr : s->guide.as<uint32_t>();
+  }
+  v.totals_guide_off = (uint32_t)totals_guide_off;
+  v.pad0 = 0;
   v.totals_abs_sum = back.abs;
   std::memset(&v.dist_total, 0, sizeof(v.dist_total));
   std::memcpy(&v.dist_total, &total_probability, 10);

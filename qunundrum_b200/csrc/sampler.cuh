@@ -54,7 +54,7 @@ struct SamplerSlice {
   uint32_t D;
   int32_t c0, c1;       // min_log_alpha_d, min_log_alpha_r (linear: min_log_alpha, 0)
   uint32_t geo_off;     // 2^(j / D), j = 0 .. D, in SamplerView::geo
-  uint32_t pad;
+  uint32_t guide_off;   // first entry of this slice's guide table in SamplerView::guide
   double abs_sum;       // sum of |cell|: scale of the rounding-error band
 };
 
@@ -65,6 +65,9 @@ struct SamplerView {
   const RawX87* totals;            // the slices' total_probability, in walk order
   const SegCoarse* totals_coarse;
   const dd* geo;
+  const uint32_t* guide;           // guide tables (seg_guide_*): the slices', then the totals'
+  uint32_t totals_guide_off;
+  uint32_t pad0;
   double totals_abs_sum;
   RawX87 dist_total;               // distribution->total_probability
   uint32_t n_slices;
@@ -138,6 +141,39 @@ QHD void seg_scan(SegCoarse* coarse, uint32_t n_blocks) {
   }
 }
 
+// ---- guide tables ------------------------------------------------------------------------------
+// The search for the stopping block is a binary search over the running maxima: 10 + 11 DEPENDENT
+// loads per sample for the bench distribution, each a trip to L1 / L2 -- the kernel's limit (ncu,
+// round 1: L1/TEX-bound, issue slots 34 % active). A guide table per segment cuts the chain:
+// guide[u] = first block whose running maximum reaches u / G of the segment's final maximum
+// (G = a quarter to half of the number of blocks). The pivot's bucket u = floor(p / top * G)
+// brackets the answer between guide[u - 1] and guide[u + 2] -- a bracket that is CHECKED against
+// the running maxima themselves (two independent loads), so rounding in the table or in u can only
+// cost a fall-back to the full search, never a different result -- and the binary search runs over
+// a handful of blocks: 1 + 1 + ~2 dependent loads instead of 11.
+QHD uint32_t seg_guide_size(uint32_t n_blocks) {
+  uint32_t G = 1;
+  while (G * 4 <= n_blocks) G <<= 1;
+  return G;
+}
+
+// Entry u (0 <= u <= G) of the guide table of a segment with n_blocks blocks.
+QHD uint32_t seg_guide_entry(const SegCoarse* coarse, uint32_t n_blocks, uint32_t G, uint32_t u) {
+  if (u >= G) return n_blocks;
+  const double top = coarse[n_blocks].m.hi;
+  if (!(top > 0.0)) return 0;
+  const double th = top * ((double)u / (double)G);
+  uint32_t lo = 0, hi = n_blocks;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (coarse[mid + 1].m.hi >= th)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
 // The reference's walk, replayed bit for bit: first k with pivot - v[0] - ... - v[k] <= 0.
 QHD uint32_t seg_walk_exact(const RawX87* v, uint32_t n, X87 p) {
   bool ok = true;
@@ -151,8 +187,8 @@ QHD uint32_t seg_walk_exact(const RawX87* v, uint32_t n, X87 p) {
 // First k at which the reference's walk stops, or n. *exact is incremented when the replay ran.
 // mode (test switch): 0 normal; 1 every walk through the bit-exact replay; 2 skip the quick pass in
 // doubles (every search through the double-double path).
-QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, uint32_t n, double abs_sum, X87 p,
-                      int mode, int* exact) {
+QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* guide, uint32_t n,
+                      double abs_sum, X87 p, int mode, int* exact) {
   if (n == 0) return 0;
   if (mode == 1) {
     *exact += 1;
@@ -165,6 +201,22 @@ QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, uint32_t n, doub
   // kernel is bound by L1 lookups of divergent addresses, 82 % of peak in ncu; 4-, 8- and
   // 16-ary searches with independent probes per level were 11 %, 25 % and 44 % slower.)
   uint32_t lo = 0, hi = nb;  // answer in [lo, hi]; hi == nb: none
+  if (guide) {
+    const double top = coarse[nb].m.hi;
+    if (top > 0.0 && pd.hi > 0.0) {
+      const uint32_t G = seg_guide_size(nb);
+      const double f = pd.hi / top * (double)G;
+      const uint32_t u = f >= (double)(G - 1) ? G - 1 : (uint32_t)f;
+      const uint32_t L = guide[u ? u - 1 : 0], R = guide[u + 2 < G ? u + 2 : G];
+      // the bracket holds iff block L - 1 does not reach the pivot and block R does (or R == nb)
+      const bool below = L == 0 || !dd_ge(coarse[L].m, pd);
+      const bool above = R >= nb || dd_ge(coarse[R + 1].m, pd);
+      if (below && above && L <= R) {
+        lo = L;
+        hi = R < nb ? R : nb;
+      }
+    }
+  }
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
     if (dd_ge(coarse[mid + 1].m, pd))
@@ -238,7 +290,8 @@ QHD uint32_t sample_slice(const SamplerView& s, uint64_t w0, int mode, int* exac
   bool ok = true;
   X87 p = x87_pivot_inclusive(w0);
   if (s.scale_by_total) p = x87_mul(p, x87_load(&s.dist_total, &ok));
-  return seg_find(s.totals, s.totals_coarse, s.n_slices, s.totals_abs_sum, p, mode, exact);
+  return seg_find(s.totals, s.totals_coarse, s.guide ? s.guide + s.totals_guide_off : nullptr, s.n_slices,
+                  s.totals_abs_sum, p, mode, exact);
 }
 
 // Second half: the region inside slice i (src/distribution_slice.cpp:167-228) and the two axis
@@ -248,8 +301,9 @@ QHD void sample_in_slice(const SamplerView& s, uint32_t i, const uint64_t* w, in
   out->slice = (int32_t)i;
   const SamplerSlice sl = s.slices[i];
   const X87 p2 = x87_mul(x87_pivot_inclusive(w[1]), x87_load(s.totals + i, &ok));
-  const uint32_t c = seg_find(s.cells + sl.cell_off, s.coarse + sl.coarse_off, sl.n_cells, sl.abs_sum,
-                              p2, mode, &out->exact);
+  const uint32_t c = seg_find(s.cells + sl.cell_off, s.coarse + sl.coarse_off,
+                              s.guide ? s.guide + sl.guide_off : nullptr, sl.n_cells, sl.abs_sum, p2, mode,
+                              &out->exact);
   if (c >= sl.n_cells) {
     out->status = kSampleNoRegion;
     return;

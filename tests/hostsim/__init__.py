@@ -204,6 +204,15 @@ class HostSampler:
                                      st.ctypes.data_as(C.c_void_p), ex.ctypes.data_as(C.c_void_p))
         return out, st, ex
 
+    def guide_stats(self, words):
+        """(searches, brackets that held, mean bracket width in blocks) for the slice search and for
+        the cell search, over the pivots in `words` (two per sample)."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        out = np.zeros(6)
+        lib().hostsim_sampler_guide_stats(self.h, C.c_uint32(w.size // 2), w.ctypes.data_as(C.c_void_p),
+                                          out.ctypes.data_as(C.c_void_p))
+        return [(int(out[i]), int(out[i + 1]), out[i + 2] / max(1.0, out[i + 1])) for i in (0, 3)]
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().hostsim_sampler_free(self.h)

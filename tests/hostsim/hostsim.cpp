@@ -430,6 +430,7 @@ void hostsim_x87_pivot(uint64_t w, long double* out, double* dd_hi, double* dd_l
 struct HostSampler {
   std::vector<RawX87> cells, totals;
   std::vector<SegCoarse> coarse;
+  std::vector<uint32_t> guide;
   std::vector<SamplerSlice> slices;
   std::vector<dd> geo;
   SamplerView view;
@@ -458,7 +459,7 @@ void* hostsim_sampler_new(int dims, uint32_t m, uint32_t n_slices, const uint32_
                           const long double* slice_total, const long double* total) {
   HostSampler* h = new HostSampler;
   std::vector<std::pair<uint32_t, uint32_t>> geo_off;
-  uint64_t cell_off = 0, coarse_off = 0;
+  uint64_t cell_off = 0, coarse_off = 0, guide_off = 0;
   h->slices.resize(n_slices);
   for (uint32_t i = 0; i < n_slices; i++) {
     const uint32_t D = dimension[i];
@@ -480,13 +481,16 @@ void* hostsim_sampler_new(int dims, uint32_t m, uint32_t n_slices, const uint32_
     sl.c0 = c0[i];
     sl.c1 = dims == 2 ? c1[i] : 0;
     sl.geo_off = go;
-    sl.pad = 0;
+    sl.guide_off = (uint32_t)guide_off;
     sl.abs_sum = 0.0;
     cell_off += sl.n_cells;
-    coarse_off += (sl.n_cells + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK + 1;
+    const uint32_t nb = (sl.n_cells + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK;
+    coarse_off += nb + 1;
+    guide_off += seg_guide_size(nb) + 1;
   }
-  const uint64_t tco = coarse_off;
+  const uint64_t tco = coarse_off, tgo = guide_off;
   coarse_off += (n_slices + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK + 1;
+  guide_off += seg_guide_size((n_slices + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK) + 1;
   h->cells.resize(cell_off);
   memcpy(h->cells.data(), cells, cell_off * 16);
   h->totals.resize(n_slices);
@@ -497,6 +501,17 @@ void* hostsim_sampler_new(int dims, uint32_t m, uint32_t n_slices, const uint32_
                   h->coarse.data() + h->slices[i].coarse_off, &h->slices[i].abs_sum, &h->bad);
   SamplerView& v = h->view;
   build_segment(h->totals.data(), n_slices, h->coarse.data() + tco, &v.totals_abs_sum, &h->bad);
+  h->guide.resize(guide_off);
+  for (uint32_t i = 0; i <= n_slices; i++) {   // the guide tables, as k_seg_build fills them
+    const uint32_t n = i < n_slices ? h->slices[i].n_cells : n_slices;
+    const SegCoarse* co = h->coarse.data() + (i < n_slices ? h->slices[i].coarse_off : tco);
+    uint32_t* g = h->guide.data() + (i < n_slices ? h->slices[i].guide_off : tgo);
+    const uint32_t nb = (n + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK, G = seg_guide_size(nb);
+    for (uint32_t u = 0; u <= G; u++) g[u] = seg_guide_entry(co, nb, G, u);
+  }
+  v.guide = getenv("QB200_SAMPLER_GUIDE") && getenv("QB200_SAMPLER_GUIDE")[0] == '0' ? nullptr : h->guide.data();
+  v.totals_guide_off = (uint32_t)tgo;
+  v.pad0 = 0;
   v.cells = h->cells.data();
   v.coarse = h->coarse.data();
   v.slices = h->slices.data();
@@ -513,6 +528,44 @@ void* hostsim_sampler_new(int dims, uint32_t m, uint32_t n_slices, const uint32_
 }
 
 void hostsim_sampler_free(void* h) { delete (HostSampler*)h; }
+
+// How well the guide tables bracket: for k uniform pivots per segment kind (the slice totals; the
+// cells of the slice each pivot selects), the number of searches whose bracket held and the sum of
+// the bracket widths in blocks. out[0..5] = searches, brackets held, width sum (totals), then cells.
+void hostsim_sampler_guide_stats(void* hh, uint32_t k, const uint64_t* words, double* out) {
+  HostSampler* h = (HostSampler*)hh;
+  const SamplerView& s = h->view;
+  for (int i = 0; i < 6; i++) out[i] = 0.0;
+  auto probe = [&](const SegCoarse* coarse, const uint32_t* guide, uint32_t n, X87 p, double* o) {
+    const dd pd = x87_to_dd(p);
+    const uint32_t nb = (n + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK;
+    const double top = coarse[nb].m.hi;
+    o[0] += 1.0;
+    if (!(top > 0.0 && pd.hi > 0.0)) return;
+    const uint32_t G = seg_guide_size(nb);
+    const double f = pd.hi / top * (double)G;
+    const uint32_t u = f >= (double)(G - 1) ? G - 1 : (uint32_t)f;
+    const uint32_t L = guide[u ? u - 1 : 0], R = guide[u + 2 < G ? u + 2 : G];
+    const bool below = L == 0 || !dd_ge(coarse[L].m, pd);
+    const bool above = R >= nb || dd_ge(coarse[R + 1].m, pd);
+    if (below && above && L <= R) {
+      o[1] += 1.0;
+      o[2] += (double)(R - L);
+    }
+  };
+  for (uint32_t i = 0; i < k; i++) {
+    bool ok = true;
+    X87 p = x87_pivot_inclusive(words[2 * i]);
+    if (s.scale_by_total) p = x87_mul(p, x87_load(&s.dist_total, &ok));
+    probe(s.totals_coarse, h->guide.data() + s.totals_guide_off, s.n_slices, p, out);
+    int exact = 0;
+    const uint32_t sl = sample_slice(s, words[2 * i], 0, &exact);
+    if (sl >= s.n_slices) continue;
+    const SamplerSlice& S = s.slices[sl];
+    const X87 p2 = x87_mul(x87_pivot_inclusive(words[2 * i + 1]), x87_load(s.totals + sl, &ok));
+    probe(s.coarse + S.coarse_off, h->guide.data() + S.guide_off, S.n_cells, p2, out + 3);
+  }
+}
 int hostsim_sampler_bad(void* h) { return ((HostSampler*)h)->bad ? 1 : 0; }
 
 // k samples, sample i from words[i * (dims + 2) ...]; out: k x 8 doubles
