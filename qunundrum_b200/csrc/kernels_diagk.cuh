@@ -184,12 +184,13 @@ __device__ __forceinline__ void diagk_tile(const DiagKConst& c, uint32_t tb, con
   out[g] = o;
 }
 
-// The grid is either one CTA per tile (default) or one wave of persistent CTAs that walk the tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ... (QB200_DIAGK_CTAS_PER_SM); a CTA owns ONE scratch area of
-// 128 x (5 k + 9) words for all its tiles. Measured (B200, m = 2048, 303,104 samples): the persistent
-// form keeps the scratch at 888 x 168 KB = 150 MB instead of 400 MB, but that is still more than the
-// L2 holds next to the inputs -- DRAM traffic 1.23 GB per launch either way, 1.93 ms against 1.76 ms
-// (profiles/r02_diagk_ncu_full.txt) -- so one CTA per tile stays the default.
+// One CTA per tile, with its own scratch area of 128 x (5 k + 9) words (the loop below takes any
+// grid). Measured and dropped (B200, m = 2048, 303,104 samples, profiles/r02_diagk_persistent_ab.txt):
+// a persistent wave of 3 / 4 / 6 CTAs per SM that rewrites one scratch area per CTA -- 75 / 100 /
+// 150 MB instead of 400 MB streamed once -- is SLOWER (2.12 / 1.96 / 1.90 ms against 1.76 ms) and
+// does not lower the DRAM traffic either (1.23 GB per launch in ncu with 6 per SM: the in-flight
+// scratch of a full wave does not fit the L2 next to the inputs, and fewer CTAs cost more than
+// the traffic saves -- DRAM is at 8 % of its bandwidth here).
 __global__ void __launch_bounds__(QB_DIAGK_CTA, 6) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
                                                 const int32_t* __restrict__ eta,
                                                 const RawX87* __restrict__ pivot,

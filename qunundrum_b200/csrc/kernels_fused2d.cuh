@@ -51,10 +51,6 @@ namespace qb200 {
 #define QB_FUSED_PART_STRIDE 4  // doubles per tile partial
 #define QB_FUSED_WARPS 4
 
-struct FusedItem {  // kept for ABI stability of qb200_plan; tiles are indexed arithmetically
-  int unused;
-};
-
 struct FusedConst {
   double c1, c2, c3;   // 1/sinc^2(z) = 1 + c1 w + c2 w^2 + c3 w^3, w = u^2, z = pi u / Lambda
   double cs, e0s, r_m; // error bound pieces (src/probability.cpp:252-281)

@@ -63,7 +63,6 @@ struct qb200_diagk {
   DiagKConst dev;  // pointers into `consts`
   DBuf consts, rows_j, cols_j, eta, pivot, scratch, cols_k, rows_k, out, sums, status, xh, xl, hout;
   uint32_t chunk = 0;
-  uint32_t resident_ctas = 0;
 };
 
 // Samples per launch: enough threads for every SM, scratch of at most ~1 GB.
@@ -129,18 +128,9 @@ static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const i
   const size_t scr = diagk_scratch_limbs(c.k);
   const size_t Bp = ((size_t)B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA * QB_DIAGK_CTA;  // whole tiles
   const size_t shmem = (size_t)(3 * c.k + 2) * 4;
-  if (s->resident_ctas == 0) {  // one wave of CTAs: each owns one scratch area for all its tiles
-    int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diagk, QB_DIAGK_CTA, shmem) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device) != cudaSuccess || per_sm < 1)
-      return -100;
-    // QB200_DIAGK_CTAS_PER_SM: 0 = one CTA (and one scratch area) per tile; N = at most N per SM
-    const char* env = getenv("QB200_DIAGK_CTAS_PER_SM");
-    const int want = (env && *env) ? atoi(env) : 0;
-    if (want > 0 && want < per_sm) per_sm = want;
-    s->resident_ctas = want == 0 ? 0xffffffffu : (uint32_t)(per_sm * sms);
-  }
-  const uint32_t grid = (uint32_t)std::min<size_t>(Bp / QB_DIAGK_CTA, s->resident_ctas);
+  // one CTA (and one scratch area) per tile: a persistent wave with per-CTA scratch was measured
+  // and is slower (kernels_diagk.cuh)
+  const uint32_t grid = (uint32_t)(Bp / QB_DIAGK_CTA);
   if (s->cols_j.reserve(Bp * c.wj * 4) || s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * scr * 4)) return -100;
   if (d_k_rows && s->cols_k.reserve(Bp * c.wl * 4)) return -100;
   const uint64_t nj = (uint64_t)Bp * c.wj;
