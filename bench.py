@@ -835,44 +835,60 @@ def _ref_worker_so(job):
 
 def sigma_optimal_section(ctx, qb, torch, stream, P, coords, peak_flops, cpu_baseline=True):
     """-sigma-optimal (probability_approx_optimal_sigma / _adjust_sigma, src/probability.cpp:20-148) on
-    the first 64 slices of the workload at D = 128: the parallel fixed point of the serial walk."""
+    the whole workload at D = 128. l = 2048 is in the large-l regime: cells from the fused kernel, the
+    serial walk as a prefix minimum in closed form (k_so_fast). The general fixed-point iteration
+    (any l) is timed beside it on the first 64 slices."""
     import multiprocessing as mp
-    sub = coords[:64]
-    a_d, a_r = [c[0] for c in sub], [c[1] for c in sub]
-    plan = ctx.plan2d(P, qb.DISTRIBUTION_SLICE_COMPUTE_METHOD_OPTIMAL_LOCAL_SIGMA, True, DIM, a_d, a_r)
-    cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
-    summ = torch.empty(len(sub) * 8, dtype=torch.float64, device="cuda")
-    l0 = ctx.launch_count
-    plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
-    stream.synchronize()
-    launches = ctx.launch_count - l0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(3):
+    a_d, a_r = [c[0] for c in coords], [c[1] for c in coords]
+
+    def timed(ad, ar, reps):
+        plan = ctx.plan2d(P, qb.DISTRIBUTION_SLICE_COMPUTE_METHOD_OPTIMAL_LOCAL_SIGMA, True, DIM, ad, ar)
+        cells = torch.empty(plan.cells, dtype=torch.float64, device="cuda")
+        summ = torch.empty(len(ad) * 8, dtype=torch.float64, device="cuda")
+        l0 = ctx.launch_count
         plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
-    e1.record(stream)
-    stream.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    tot = plan.cells
-    plan.close()
+        stream.synchronize()
+        launches = ctx.launch_count - l0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            plan.run(cells.data_ptr(), summ.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tot = plan.cells
+        tp, te, fl = plan.finish(summ.cpu().numpy())
+        plan.close()
+        return ms, tot, launches, tp, te
+
+    ms, tot, launches, tp, te = timed(a_d, a_r, 5)
+    os.environ["QB200_SO_FAST"] = "0"
+    try:
+        ms_g, tot_g, launches_g, tp_g, te_g = timed(a_d[:64], a_r[:64], 2)
+    finally:
+        del os.environ["QB200_SO_FAST"]
+    agree = float(np.max(np.abs(((te[:64] - te_g) / te_g).astype(np.float64))))
     t0 = time.perf_counter()
     ctx.slice2d_batch(P, 1, True, DIM, a_d, a_r)
     wall = time.perf_counter() - t0
     ach = tot / (ms * 1e-3) * FLOP_PER_CELL / 1e12
-    sec = {"workload": f"sigma-optimal method, the first {len(sub)} slices of the workload at D={DIM} ({tot} cells)",
+    sec = {"workload": f"sigma-optimal method, all {len(coords)} slices of the workload at D={DIM} ({tot} cells)",
            "value": tot / (ms * 1e-3), "unit": "cells/s", "ms": ms, "gpu_launches": int(launches),
-           "roofline": {"bound": "fp64", "achieved": ach, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
+           "general_iteration": {"value": tot_g / (ms_g * 1e-3), "unit": "cells/s", "ms": ms_g, "slices": 64,
+                                 "gpu_launches": int(launches_g),
+                                 "total_error_agreement": agree},
+           "roofline": {"bound": "fp64 / integer issue", "achieved": ach, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
                         "frac": ach / (peak_flops / 1e12), "flop_per_cell": FLOP_PER_CELL, "traffic": None,
-                        "kernel": "k_so_step (one thread per point, double-double, 3-4 evaluations per point and "
-                                  "iteration) + k_so_scan; not fused"},
-           "e2e": {"value": tot / wall, "unit": "cells/s", "ms": wall * 1e3, "h2d_bytes_per_step": int(8 * len(sub)),
+                        "kernel": "k_fused2d (cells, quick-method constants) + k_so_fast (one thread per point: norm by "
+                                  "angle addition, sigma* in closed form, running minimum, error sums)"},
+           "e2e": {"value": tot / wall, "unit": "cells/s", "ms": wall * 1e3, "h2d_bytes_per_step": int(8 * len(coords)),
                    "d2h_bytes_per_step": int(tot * 8), "api": "qb200_slice2d_compute, method 1"}}
     if cpu_baseline:
         try:
             from oracle import ref
             if ref.available():
                 cores = host_cores()
-                jobs = [(sub[k % len(sub)][0], sub[k % len(sub)][1], 32) for k in range(cores)]
+                jobs = [(coords[k % len(coords)][0], coords[k % len(coords)][1], 32) for k in range(cores)]
                 t0 = time.perf_counter()
                 with mp.get_context("fork").Pool(cores) as pool:
                     res = pool.map(_ref_worker_so, jobs)
@@ -885,18 +901,22 @@ def sigma_optimal_section(ctx, qb, torch, stream, P, coords, peak_flops, cpu_bas
     return sec
 
 
-def saturation_section(ctx, qb, torch, stream, timer, P, coords, my, tp128_all, world, barrier, allmax, steps):
+def saturation_section(ctx, qb, torch, stream, timer, P, coords, rank, tp128_all, world, barrier, allmax, steps):
     """The same distribution in the generator's DEFAULT mode (dimension heuristic): every coordinate at
     its initial dimension, the upgraded ones again at 256 / 512; this rank's share of each list.
     Device resident, and end to end through the C ABI (the 512 ones scaled to 256 on the device)."""
     import ctypes as C
     dims = heuristic_dimensions(coords, tp128_all)
-    lists = {}
-    for i in my:
+    everything = {}
+    for i in range(len(coords)):
         init, fin = dims[i]
-        lists.setdefault(init, []).append(i)
+        everything.setdefault(init, []).append(i)
         if fin != init:
-            lists.setdefault(fin, []).append(i)
+            everything.setdefault(fin, []).append(i)
+    # every dimension's list is dealt out on its own (a 512 slice is 16 times a 128 slice: the
+    # farm hands them out one by one, a static partition has to balance them per dimension)
+    lists = {D: v[rank::max(1, world)] for D, v in everything.items()}
+    lists = {D: v for D, v in lists.items() if v}
     plans, bufs, cells_total = [], [], 0
     for D in sorted(lists):
         idx = lists[D]
@@ -1146,12 +1166,9 @@ def run_ours(args, rank, world, local_rank):
     saturation = None
     if not args.no_saturation:
         Ps = qb.Parameters(M, S, *synthetic_d_r(20482048), T_PARAM)
-        _, tp_all, _, _ = ctx.slice2d_batch(Ps, 0, True, DIM, [c[0] for c in coords], [c[1] for c in coords]) \
-            if (mode != "strong" or world > 1) else (None, None, None, None)
-        if tp_all is None:
-            tp_all = R["tp"]
-        mine = shard.partition(n_all, world, rank)
-        saturation = saturation_section(ctx, qb, torch, stream, DeviceTimer(torch, stream, False), Ps, coords, mine,
+        # the totals at D = 128 decide which coordinates the heuristic upgrades
+        _, tp_all, _, _ = ctx.slice2d_batch(Ps, 0, True, DIM, [c[0] for c in coords], [c[1] for c in coords])
+        saturation = saturation_section(ctx, qb, torch, stream, DeviceTimer(torch, stream, False), Ps, coords, rank,
                                         [float(x) for x in tp_all], world, barrier, allmax, max(3, min(args.steps, 10)))
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------

@@ -277,4 +277,116 @@ __global__ void k_so_final(int n, SoLayout L, int nb_c, int nb_f, int nb_o,
   o[7] = (double)(s0c + 65536 * s0f);
 }
 
+// ---- the large-l fast path: the walk as a prefix minimum (sigma_opt.cuh, "closed form") ------------
+// One block per slice, both passes one after the other; the points of a pass are taken 256 at a
+// time IN WALK ORDER (alpha_d outer, alpha_r inner), so the running minimum is a block scan with a
+// carry. Per point: the norm by angle addition from the axis tables of the companion plan (the
+// quick method's: kappa = -d/r; the fused kernel's separable sine), sigma*_p without a logarithm,
+// the point's share of the two error sums with its separable Simpson weight, the bound test.
+// Cells and mass come from the fused kernel of the companion plan; this kernel fills the rest of
+// the summary (slots 2 .. 7 as k_so_final) and raises *fallback when a point leaves the range in
+// which the closed form is proven (64 <= sigma_p <= l - 60).
+#define QB_SOF_BLOCK 256
+#define QB_SOF_NONE 0x3fffffff
+
+__global__ void __launch_bounds__(QB_SOF_BLOCK)
+k_so_fast(DevConsts c, SoLayout L, const DevSlice* __restrict__ slices, const AxisD* __restrict__ tab_a,
+          const AxisR* __restrict__ tab_b, const double* __restrict__ gw, double* __restrict__ summary,
+          int* __restrict__ fallback) {
+  __shared__ int warp_min[QB_SOF_BLOCK / 32];
+  __shared__ int carry_s, first_s;
+  __shared__ double sa[QB_SOF_BLOCK], sb[QB_SOF_BLOCK];
+  __shared__ int so[QB_SOF_BLOCK];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const DevSlice s = slices[blockIdx.x];
+  const int NP = table_points(L.D);
+  const double PI = 3.14159265358979323846;
+  double out_a[2] = {0.0, 0.0}, out_c[2] = {0.0, 0.0};
+  int sigma0[2] = {0, 0};
+  int bounded_c = 1, bad = 0;
+  for (int pass = 0; pass < L.passes; pass++) {
+    const int Dp = pass ? 2 * L.D : L.D, side = 2 * Dp + 1, npts = side * side;
+    const int off = pass_offset(L.D, pass);
+    const AxisD* ta = tab_a + (size_t)s.tab_a * NP + off;
+    const AxisR* tb = tab_b + (size_t)s.tab_b * NP + off;
+    const double* wd = gw + width_offset(L.D, pass);
+    if (tid == 0) carry_s = QB_SOF_NONE;
+    __syncthreads();
+    double A = 0.0, Cc = 0.0;
+    int ok = 1, s0 = 0;
+    int i = tid / side, j = tid - i * side;  // point p = start + tid of the walk: (i, j) = (alpha_d, alpha_r) index
+    for (int start = 0; start < npts; start += QB_SOF_BLOCK) {
+      const int p = start + tid;
+      const bool live = p < npts;
+      double n = 0.0, ph = 0.0, wgt = 0.0;
+      int v = QB_SOF_NONE;
+      if (live) {
+        const AxisD d = ta[i];
+        const AxisR r = tb[j];
+        const double u = (d.xh + r.yh) + (d.xl + r.yl);
+        // sin(pi u) / (pi u): the series next to the ridge, angle addition elsewhere
+        const double t1 = fabs(u) < 0.0625 ? sincpi_small(u) : fma(d.sd, r.cr, d.cd * r.sr) / (QB_PI_HI * u);
+        n = t1 * t1 * r.t2;
+        ph = PI * (fabs(d.xh) + r.b);
+        const double a = ph * n * c.r_m;
+        v = p == 0 ? so_fast_sigma_first(c.l, a) : so_fast_sigma_star(c.l, a);
+        wgt = so_axis_weight(wd, Dp, i) * so_axis_weight(wd, Dp, j);
+      }
+      // inclusive running minimum along the walk, carried from chunk to chunk
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = min(v, t);
+      }
+      if (lane == 31) warp_min[w] = v;
+      __syncthreads();
+      int pre = carry_s;
+      for (int k = 0; k < w; k++) pre = min(pre, warp_min[k]);
+      v = min(v, pre);
+      __syncthreads();
+      if (tid == QB_SOF_BLOCK - 1) carry_s = v;
+      if (start == 0 && tid == 0) first_s = v;
+      __syncthreads();
+      if (start == 0) s0 = first_s;  // sigma_0 of the pass
+      if (live) {
+        const int sg = v;
+        if (sg < 64 || sg > c.l - 60) {
+          bad = 1;
+        } else {
+          const int sl = sg - c.l;
+          const double sv = sl > -1000 ? ldexp(ph, sl) : 0.0;
+          const double era = ldexp(ph * (2.0 + sv) * n * c.r_m, max(sg - s0, -1000));
+          A = fma(wgt, era, A);
+          Cc = fma(wgt, ldexp(1.0, min(s0 - sg, 1000)), Cc);
+          if (pass == 0 && !so_bounded(c, n, so_error_given_norm(c, ph, n, sg))) ok = 0;
+        }
+      }
+      j += QB_SOF_BLOCK;
+      while (j >= side) {
+        j -= side;
+        i++;
+      }
+    }
+    const double f = s.scale_a * s.scale_b / 36.0;
+    A *= f;
+    Cc *= f;
+    block_sum2_and<QB_SOF_BLOCK>(A, Cc, ok, sa, sb, so);
+    out_a[pass] = A;
+    out_c[pass] = Cc;
+    sigma0[pass] = s0;
+    if (pass == 0) bounded_c = ok;
+    __syncthreads();
+  }
+  bad = __syncthreads_or(bad);
+  if (tid == 0) {
+    double* o = summary + (size_t)blockIdx.x * 8;
+    o[2] = out_a[0];
+    o[3] = out_c[0];
+    o[4] = bad ? -1.0 : (double)bounded_c;
+    o[5] = out_a[1];
+    o[6] = out_c[1];
+    o[7] = (double)(sigma0[0] + 65536 * sigma0[1]);
+    if (bad) atomicOr(fallback, 1);
+  }
+}
+
 }  // namespace qb200

@@ -141,6 +141,9 @@ struct qb200_plan {
   // fused one-dimensional path: per-block partials and per-slice tickets
   DevBuf f1d_part, f1d_tickets;
   bool f1d_ready = false;
+  // sigma-optimal, large l: the quick method's plan over the same slices (cells, mass and axis
+  // tables for k_so_fast; see sigma_opt.cuh "the walk in closed form")
+  qb200_plan* so_quick = nullptr;
   // sigma-optimal scratch
   DevBuf so_sigma, so_guess, so_norm, so_erra, so_sigma0, so_status, so_changed;
   void bind_pool(Pool* pool) {
@@ -270,6 +273,25 @@ int run_sigma_opt_2d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d
   L.n_c = (2 * D + 1) * (2 * D + 1);
   L.n_f = h.richardson ? (4 * D + 1) * (4 * D + 1) : 0;
   L.stride = L.n_c + L.n_f;
+  if (pl->so_quick) {
+    // Large l: cells and mass are the quick method's (fused kernel); the walk is a prefix minimum
+    // in closed form (k_so_fast). A slice that leaves the proven range sends the batch through the
+    // general iteration below.
+    qb200_plan* q = pl->so_quick;
+    if (int rc = pl->so_changed.reserve(sizeof(int))) return rc;
+    int* d_fallback = pl->so_changed.as<int>();
+    QB_CUDA(cudaMemsetAsync(d_fallback, 0, sizeof(int), st));
+    if (int rc = qb200_plan_run(q, st, d_cells, d_summary)) return rc;
+    k_so_fast<<<pl->n, QB_SOF_BLOCK, 0, st>>>(q->host.c, L, q->slices.as<DevSlice>(), q->tab_a.as<AxisD>(),
+                                             q->tab_b.as<AxisR>(), q->geo->gw.as<double>(), d_summary,
+                                             d_fallback);
+    ctx->launches++;
+    QB_CUDA(cudaGetLastError());
+    int fallback = 0;
+    QB_CUDA(cudaMemcpyAsync(&fallback, d_fallback, sizeof(int), cudaMemcpyDeviceToHost, st));
+    QB_CUDA(cudaStreamSynchronize(st));
+    if (!fallback) return 0;
+  }
   const size_t per_slice = (size_t)L.stride * 24 + (size_t)5 * D * D * 8;
   uint32_t chunk = (uint32_t)std::max<size_t>(1, (size_t(1) << 29) / per_slice);
   chunk = std::min<uint32_t>(std::min<uint32_t>(chunk, pl->n), 16384);
@@ -652,6 +674,18 @@ static int create_plan2d(qb200_context* ctx, const qb200_params* params, int met
   if (int rc = plan_2d(view_of(params), method, richardson, dimension, n, a_d, a_r, &pl->host, &err))
     return fail(rc, err);
   if (int rc = finish_common(pl.get(), n_chunks, same_stream)) return rc;
+  if (method == kMethodOptimalLocalSigma && richardson && dimension % 32 == 0 && params->l >= 256 && n > 0) {
+    const char* off = getenv("QB200_SO_FAST");
+    if (!(off && *off == '0')) {
+      qb200_plan* q = nullptr;
+      if (0 == create_plan2d(ctx, params, kMethodQuick, richardson, dimension, n, a_d, a_r, 1, &q, same_stream)) {
+        if (q->fused_ok && q->fused.mode == 0)
+          pl->so_quick = q;
+        else
+          qb200_plan_destroy(q);
+      }
+    }
+  }
   *out = pl.release();
   return 0;
 }
@@ -685,6 +719,7 @@ int qb200_plan1d_create(qb200_context* ctx, const qb200_params* params, int kind
 void qb200_plan_destroy(qb200_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->ctx->device);
+  if (plan->so_quick) qb200_plan_destroy(plan->so_quick);
   delete plan;
 }
 

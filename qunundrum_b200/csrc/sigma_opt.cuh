@@ -161,4 +161,55 @@ QHD int so_adjust(const DevConsts& c, const SigmaOptConsts& q, const SoPoint& p,
   return best;
 }
 
+// ---- the walk in closed form (large l) -----------------------------------------------------------
+// With a = pi h n r/2^m, the bound at a point is  e(sigma) = a 2^(sigma-l) (2 + pi h 2^(sigma-l))
+// + 2^(4-sigma) + 2^(3-l)  (so_eval). Two facts make the serial walk a prefix minimum when l is
+// large (l >= 256; the walk then stays near sigma = l / 2):
+//  (1) n does not depend on sigma there: kappa_sigma = -d/r + O(2^-sigma) moves u by less than
+//      2^(11-sigma) and Lambda sin(pi u / Lambda) = pi u to 2^-56, so for sigma >= 64 and
+//      l - sigma >= 60 the norm is the quick method's, to the last bits of a double;
+//  (2) e is then convex in 2^sigma, and the descent of probability_approx_adjust_sigma from any
+//      start s stops at the first sigma with e(sigma - 1) >= e(sigma), i.e.
+//          16 >= a 2^(2 sigma - l) (1 + 0.75 pi h 2^(sigma - l))           [the bracket is 1 to 2^-60]
+//      which holds exactly for sigma <= sigma* := max { sigma : a 2^(2 sigma - l) <= 16 }.
+//      Hence f_p(s) = min(s, sigma*_p) and sigma_p = min(sigma_0, sigma*_1, ..., sigma*_p).
+// sigma*_p needs no logarithm: a = f 2^e with f in [0.5, 1) gives 2 sigma - l + e <= 4 (5 if f = 0.5).
+// The range assumptions are CHECKED on the device for every point (64 <= sigma_p <= l - 60); a
+// slice that leaves them is computed by the general fixed-point iteration instead.
+QHD int so_fast_sigma_star(int l, double a) {
+  if (!(a > 0.0)) return 0x3fffffff;  // n = 0: e decreases with sigma for ever, the descent never moves
+  int e;
+  const double f = frexp(a, &e);
+  const int kmax = f == 0.5 ? 5 : 4;
+  const int t = kmax + l - e;  // 2 sigma <= t
+  return t >= 0 ? t / 2 : -((1 - t) / 2);  // floor(t / 2)
+}
+
+// The first point takes the arg-min over all sigma, the SMALLEST among equal values
+// (probability_approx_optimal_sigma, src/probability.cpp:102-148: strict improvement while scanning
+// upwards): sigma* itself unless e(sigma* - 1) == e(sigma*), i.e. a 2^(2 sigma* - l) == 16 exactly.
+QHD int so_fast_sigma_first(int l, double a) {
+  const int s = so_fast_sigma_star(l, a);
+  if (s >= 0x3fffffff) return s;
+  return ldexp(a, 2 * s - l) == 16.0 ? s - 1 : s;
+}
+
+// e(sigma) for a given norm (so_eval without the evaluation of the norm).
+QHD xd so_error_given_norm(const DevConsts& c, double ph, double n, int sigma) {
+  const int sl = sigma - c.l;
+  const double s = sl > -1000 ? ldexp(ph, sl) : 0.0;
+  xd e = xd_make(ph * (2.0 + s) * n * c.r_m, sl);
+  e = xd_add(e, xd_make(1.0, 4 - sigma));
+  e = xd_add(e, xd_make(1.0, 3 - c.l));
+  return e;
+}
+
+// Simpson weight of abscissa i (0 .. 2 Dp) of one axis over the cells it belongs to:
+// 4 w[I] for the mid-point of cell I, w[I - 1] + w[I] for a point shared by two cells.
+QHD double so_axis_weight(const double* w, int Dp, int i) {
+  if (i & 1) return 4.0 * w[i >> 1];
+  const int I = i >> 1;
+  return (I > 0 ? w[I - 1] : 0.0) + (I < Dp ? w[I] : 0.0);
+}
+
 }  // namespace qb200

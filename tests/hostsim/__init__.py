@@ -91,6 +91,25 @@ def slice2d(m, l, d, r, method, richardson, D, a_d, a_r):
     return cells, tp, te, fl
 
 
+def so_fast(m, l, d, r, richardson, D, a_d, a_r):
+    """total_error, flags and (sigma_0 coarse, fine) of the sigma-optimal method by the closed-form
+    walk (sigma_opt.cuh); fallback = True when a point left the range the closed form is proven in."""
+    a_d = np.ascontiguousarray(a_d, dtype=np.int32)
+    a_r = np.ascontiguousarray(a_r, dtype=np.int32)
+    n = len(a_d)
+    te = np.zeros(n, dtype=np.longdouble)
+    fl = np.zeros(n, dtype=np.uint32)
+    s0 = np.zeros((n, 2), dtype=np.int32)
+    db, rb = be(d), be(r)
+    rc = lib().hostsim_so_fast(
+        C.c_uint32(m), C.c_uint32(l), db, C.c_size_t(len(db)), rb, C.c_size_t(len(rb)), C.c_int(richardson),
+        C.c_uint32(D), C.c_uint32(n), a_d.ctypes.data_as(C.c_void_p), a_r.ctypes.data_as(C.c_void_p),
+        te.ctypes.data_as(C.c_void_p), fl.ctypes.data_as(C.c_void_p), s0.ctypes.data_as(C.c_void_p))
+    if rc < 0:
+        raise ValueError(lib().hostsim_last_error().decode())
+    return te, fl, s0, bool(rc)
+
+
 def slice1d(m, l, sigma, d, r, kind, richardson, D, a, eta=None):
     a = np.ascontiguousarray(a, dtype=np.int32)
     n = len(a)

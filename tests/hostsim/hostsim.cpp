@@ -228,6 +228,68 @@ int hostsim_slice2d(uint32_t m, uint32_t l, const uint8_t* d, size_t dn, const u
   return 0;
 }
 
+// The sigma-optimal method's error sums, bound flag and sigma_0 by the closed-form walk of
+// sigma_opt.cuh (what k_so_fast computes; the norm here by the accurate quick-method evaluation):
+// total_error and flags of n slices, to compare with the serial walk of hostsim_slice2d(method 1).
+// Returns 1 when a point left the range in which the closed form is proven.
+int hostsim_so_fast(uint32_t m, uint32_t l, const uint8_t* d, size_t dn, const uint8_t* r, size_t rn,
+                    int richardson, uint32_t D, uint32_t n, const int32_t* a_d, const int32_t* a_r,
+                    long double* total_error, uint32_t* flags, int32_t* sigma0_out) {
+  Plan quick, opt;
+  int rc = plan_2d(view(m, l, 0, d, dn, r, rn), kMethodQuick, richardson, D, n, a_d, a_r, &quick, &g_err);
+  if (rc) return rc;
+  rc = plan_2d(view(m, l, 0, d, dn, r, rn), kMethodOptimalLocalSigma, richardson, D, n, a_d, a_r, &opt, &g_err);
+  if (rc) return rc;
+  const Geometry geo = make_geometry((int)D);
+  const DevConsts& c = quick.c;
+  int fallback = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    const SliceDesc& sd = quick.slices[s];
+    double summ[8] = {0, 0, 0, 0, 1, 0, 0, 0};
+    int s0[2] = {0, 0};
+    bool bounded = true;
+    for (int pass = 0; pass <= richardson; pass++) {
+      const int Dp = pass ? 2 * (int)D : (int)D, side = 2 * Dp + 1, off = pass_offset((int)D, pass);
+      const double* wd = geo.gw.data() + width_offset((int)D, pass);
+      int run = 0x3fffffff;
+      double A = 0, Cc = 0;
+      for (int i = 0; i < side; i++)
+        for (int j = 0; j < side; j++) {
+          const dd xd_ = grid_x(make_dd(geo.gx[off + i].hi, geo.gx[off + i].lo), quick.tabs_a[sd.tab_a].k_abs,
+                                quick.tabs_a[sd.tab_a].sign, c.m);
+          const dd xr_ = grid_x(make_dd(geo.gx[off + j].hi, geo.gx[off + j].lo), quick.tabs_b[sd.tab_b].k_abs,
+                                quick.tabs_b[sd.tab_b].sign, c.m);
+          const double nn = t1_value(xd_, dd_mul(c.kappa, xr_), c.lam_exp) * t2_value(xr_, c.c_over_L, c.l);
+          const double ph = 3.14159265358979323846 * (fabs(xd_.hi) + fabs(xr_.hi));
+          const double a = ph * nn * c.r_m;
+          const int star = (i == 0 && j == 0) ? so_fast_sigma_first(c.l, a) : so_fast_sigma_star(c.l, a);
+          run = star < run ? star : run;
+          if (i == 0 && j == 0) s0[pass] = run;
+          if (run < 64 || run > c.l - 60) {
+            fallback = 1;
+            continue;
+          }
+          const int sl = run - c.l;
+          const double sv = sl > -1000 ? ldexp(ph, sl) : 0.0;
+          const double wgt = so_axis_weight(wd, Dp, i) * so_axis_weight(wd, Dp, j);
+          A += wgt * ldexp(ph * (2.0 + sv) * nn * c.r_m, run - s0[pass]);
+          Cc += wgt * ldexp(1.0, s0[pass] - run);
+          if (pass == 0 && !so_bounded(c, nn, so_error_given_norm(c, ph, nn, run))) bounded = false;
+        }
+      const double f = sd.scale_a * sd.scale_b / 36.0;
+      summ[pass ? 5 : 2] = A * f;
+      summ[pass ? 6 : 3] = Cc * f;
+    }
+    summ[7] = (double)(s0[0] + 65536 * s0[1]);
+    total_error[s] = total_error_sigma_opt(opt, s, summ);
+    flags[s] = kFlagMethodSimpson | (richardson ? kFlagMethodRichardson : 0u) |
+               (!bounded ? kFlagErrorBoundWarning : 0u);
+    sigma0_out[2 * s] = s0[0];
+    sigma0_out[2 * s + 1] = s0[1];
+  }
+  return fallback;
+}
+
 int hostsim_slice1d(uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d, size_t dn,
                     const uint8_t* r, size_t rn, int kind, int richardson, uint32_t D,
                     uint32_t n, const int32_t* a, const int32_t* eta, double* cells,

@@ -225,6 +225,51 @@ def test_sigma_optimal_matches_reference_on_this_box(gpu_ctx):
             assert int(fl[i]) == R.flags
 
 
+def test_sigma_optimal_closed_form_walk_equals_the_iteration(gpu_ctx):
+    """Large l (>= 256): the sigma-optimal walk is a prefix minimum in closed form (k_so_fast) over
+    the quick method's cells. Against the general fixed-point iteration (QB200_SO_FAST=0): cells to
+    1e-10 (the iteration evaluates every point in double-double), total_error to 1e-9, flags equal;
+    and against the reference itself where oracle/_ref is on the box."""
+    import os
+    ref = ref_or_none()
+    cases = [(_t2d_params(), 2048, 1, 32, [(2048, 2048), (-2049, 2048), (2058, 2057), (2018, 2058), (-2058, 2018), (2040, 2041)]),
+             (None, 512, 1, 32, [(512, 512), (-510, 515), (520, 521)]),
+             (None, 1024, 3, 64, [(1024, 1025), (-1030, 1020)])]
+    worst = [0.0, 0.0]
+    for P, m, s, D, coords in cases:
+        if P is None:
+            from oracle import restate as rs
+            d, r = rs.deterministic_d_r(m)
+            P = qb.Parameters(m, s, d, r)
+        ad, ar = [c[0] for c in coords], [c[1] for c in coords]
+        l0 = gpu_ctx.launch_count
+        cells, tp, te, fl = gpu_ctx.slice2d_batch(P, 1, True, D, ad, ar)
+        fast_launches = gpu_ctx.launch_count - l0
+        os.environ["QB200_SO_FAST"] = "0"
+        try:
+            l0 = gpu_ctx.launch_count
+            c0, tp0, te0, fl0 = gpu_ctx.slice2d_batch(P, 1, True, D, ad, ar)
+            slow_launches = gpu_ctx.launch_count - l0
+        finally:
+            del os.environ["QB200_SO_FAST"]
+        assert fast_launches <= 8 < slow_launches, (fast_launches, slow_launches)
+        assert cell_errors(cells, c0) <= 1e-10
+        assert np.max(np.abs((tp - tp0).astype(np.float64))) <= 1e-14
+        rel = float(np.max(np.abs(((te - te0) / te0).astype(np.float64))))
+        assert rel <= 1e-9 and np.array_equal(fl, fl0), (m, s, rel)
+        worst[0] = max(worst[0], rel)
+        if ref is not None and m <= 1024:
+            RP = ref.RefParameters(m, s, P.d, P.r)
+            for i in range(min(2, len(coords))):
+                R = ref.distribution_slice_compute(RP, D, ad[i], ar[i], method=1)
+                assert cell_errors(cells[i], R.cells) <= CELL_RTOL
+                assert abs(float(tp[i] - R.total_probability)) <= 1e-12
+                rr = abs(float((te[i] - R.total_error) / R.total_error))
+                assert rr <= 1e-9 and int(fl[i]) == R.flags
+                worst[1] = max(worst[1], rr)
+    print(f"sigma-optimal closed form: total_error vs iteration {worst[0]:.2e}, vs reference {worst[1]:.2e}")
+
+
 def test_empty_and_ragged_batches(gpu_ctx):
     P = _t2d_params()
     cells, tp, te, fl = gpu_ctx.slice2d_batch(P, 0, True, 32, [], [])

@@ -37,5 +37,33 @@ for name in ("2d", "lin"):
     s.set_force_exact(True)
     s.tau_estimate(2, 10, g.words)
     s.close()
+# round 2: single-launch one-dimensional kernel (ragged dimension, plain path beside it), copy_scale,
+# the resident distribution (collapse to both marginals, export with look-ahead)
+for kind, PP, eta in ((0, P, None), (1, P, None), (2, PD, [0, 1, -1])):
+    aa = [k["m"] - 1, k["m"], -k["m"] - 2]
+    plan = ctx.plan1d(PP, kind, True, 100, aa, eta)
+    import torch  # noqa: E402
+    cells = torch.zeros(plan.cells, dtype=torch.float64, device="cuda")
+    summ = torch.zeros(len(aa) * 8, dtype=torch.float64, device="cuda")
+    for algo in (2, 1):
+        plan.set_algorithm(algo)
+        plan.run(cells.data_ptr(), summ.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    plan.close()
+sc, tp, te, fl = ctx.slice2d_batch_scaled(P, 0, True, 64, 16, a, b)
+dist = qb.Distribution(k["m"])
+for D in (16, 32):
+    c2, tp2, te2, fl2 = ctx.slice2d_batch(P, 0, True, D, a, b)
+    for i in range(len(a)):
+        for sa, sb in ((a[i], b[i]), (-a[i], -b[i])):
+            sl = qb.Distribution_Slice(D, sa, sb, norm_matrix=c2[i].astype(np.longdouble))
+            sl.total_probability, sl.total_error = tp2[i], te2[i]
+            dist.insert_slice(sl)
+res = qb.Resident(dist.slices, ctx)
+for axis in (0, 1):
+    res.collapse(axis)
+res.format(0, 4, prefetch_next=3)
+res.format(4, 3)
+res.close()
 print("sanitize_slices: all kernels ran; launches:", ctx.launch_count)
 ctx.close()
