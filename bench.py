@@ -926,9 +926,22 @@ def saturation_section(ctx, qb, torch, stream, timer, P, coords, rank, tp128_all
                      torch.empty(max(8, len(idx) * 8), dtype=torch.float64, device="cuda")))
         cells_total += pl.cells
 
+    # the three batches (one per dimension) are independent: each runs on a stream of its own, forked
+    # from and joined to the timed stream, so that their tails and fixed costs overlap
+    side = [torch.cuda.Stream() for _ in plans[1:]]
+
     def step():
-        for pl, (c, sm) in zip(plans, bufs):
-            pl.run(c.data_ptr(), sm.data_ptr(), stream.cuda_stream)
+        fork = torch.cuda.Event()
+        fork.record(stream)
+        for k, (pl, (c, sm)) in enumerate(zip(plans, bufs)):
+            st = stream if k == 0 else side[k - 1]
+            if k:
+                st.wait_event(fork)
+            pl.run(c.data_ptr(), sm.data_ptr(), st.cuda_stream)
+        for st in side:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            stream.wait_event(ev)
     for _ in range(3):
         step()
     barrier()

@@ -156,6 +156,82 @@ __global__ void k_fused_cols(int D, int m, const TabDesc* __restrict__ desc_b,
   o[9] = t2p;
 }
 
+// Axis tables AND column records in one launch (grid.y: the alpha_d tables, the alpha_r tables,
+// then one row of blocks per alpha_r table for its column records). A column record needs one
+// abscissa of its table; it evaluates that abscissa itself (the same axis_r_point, the same bits)
+// instead of waiting for the table kernel: one dependent launch less per step, which is what
+// counts when a GPU holds an eighth of a distribution.
+__global__ void k_fused_prologue(DevConsts c, int D, int NP, int n_tab_a, int n_tab_b,
+                                 const TabDesc* __restrict__ desc_a, const TabDesc* __restrict__ desc_b,
+                                 const dd* __restrict__ gx, const double* __restrict__ gw,
+                                 AxisD* __restrict__ tab_a, AxisR* __restrict__ tab_b,
+                                 double* __restrict__ cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (y < n_tab_a + n_tab_b) {
+    if (i >= NP) return;
+    const dd g = gx[i];
+    if (y < n_tab_a) {
+      AxisD o;
+      axis_d_point(c, g, desc_a[y], &o);
+      tab_a[(size_t)y * NP + i] = o;
+    } else {
+      AxisR o;
+      axis_r_point(c, g, desc_b[y - n_tab_a], &o);
+      tab_b[(size_t)(y - n_tab_a) * NP + i] = o;
+    }
+    return;
+  }
+  const int R = i;
+  const int ncol = 5 * D + 1;
+  if (R >= ncol) return;
+  const int t = y - n_tab_a - n_tab_b;
+  const double* wc = gw;                          // coarse widths [D]
+  const double* wf = gw + width_offset(D, 1);     // fine widths [2 D]
+  const double sb = pow2i(desc_b[t].k_abs - c.m) / 6.0;
+  const double inv_pi2 = 0.101321183642337771443879463209;  // 1 / pi^2
+  const int J = R / 5, k = R % 5;
+  AxisR a;
+  double wF = 0.0, wF2 = 0.0, wC = 0.0, wC2 = 0.0;
+  if (k == 4) {
+    axis_r_point(c, gx[2 * J + 1], desc_b[t], &a);                       // coarse interleaved 2 J + 1
+    wC = 4.0 * wc[J];
+  } else {
+    axis_r_point(c, gx[pass_offset(D, 1) + 4 * J + k], desc_b[t], &a);   // fine interleaved 4 J + k
+    if (k == 0) {
+      if (J < D) {
+        wF = wf[2 * J];
+        wC = wc[J];
+      }
+      if (J >= 1) {
+        wF2 = wf[2 * J - 1];
+        wC2 = wc[J - 1];
+      }
+    } else if (k == 1) {
+      wF = 4.0 * wf[2 * J];
+    } else if (k == 2) {
+      wF = wf[2 * J] + wf[2 * J + 1];
+    } else {
+      wF = 4.0 * wf[2 * J + 1];
+    }
+  }
+  const double t2p = a.t2 * inv_pi2;
+  const double f = sb * t2p;
+  double* o = cols + ((size_t)t * ncol + R) * QB_FUSED_REC;
+  o[0] = a.yh;
+  o[1] = a.yl;
+  o[2] = a.sr;
+  o[3] = a.cr;
+  o[4] = wF * f;
+  o[5] = wF2 * f;
+  o[6] = wC * f;
+  o[7] = wC2 * f;
+  if (k >= 1 && k <= 3) o[5] = o[4] * a.b;   // error-moment weights, as k_fused_cols
+  if (k == 4) o[7] = o[6] * a.b;
+  o[8] = a.b;
+  o[9] = t2p;
+}
+
 // ---- device helpers ---------------------------------------------------------
 struct ColRec {
   double yh, yl, sr, cr, wF, wF2, wC, wC2, b, t2p;
@@ -312,7 +388,69 @@ struct FusedArgs {
   const double* gw;
   double* out;
   double* part;
+  // the slice's summary is written by the warp that finishes its last tile (ticket per slice,
+  // self-resetting); nullptr: k_fused_final does it in a launch of its own
+  unsigned int* tickets;
+  double* summary;
 };
+
+// The tile's partial, and -- when tickets are in use -- the slice's summary by the warp that
+// finishes its last tile: tile partials -> summary in tile order (the lanes fetch 32 partials at a
+// time, lane 0 adds them in order: the sums of k_fused_final, bit for bit). Not inlined: it runs
+// once per tile and must not take registers from the march.
+__device__ __noinline__ void fused_close_tile(double* part, unsigned int* tickets, double* summary,
+                                              unsigned slot, unsigned per_slice, unsigned rem, int lane,
+                                              double tp, double err1, double err2, int ok) {
+  unsigned last = 0;
+  if (lane == 0) {
+    double* p = part + ((size_t)slot * per_slice + rem) * QB_FUSED_PART_STRIDE;
+    p[0] = tp;
+    p[1] = err1;
+    p[2] = err2;
+    p[3] = (double)ok;
+    if (tickets) {
+      __threadfence();
+      last = atomicAdd(tickets + slot, 1u) == per_slice - 1 ? 1u : 0u;
+    }
+  }
+  if (tickets == nullptr) return;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  const double* pbase = part + (size_t)slot * per_slice * QB_FUSED_PART_STRIDE;
+  dd stp = make_dd(0.0, 0.0);
+  double m1 = 0.0, m2 = 0.0;
+  int sok = 1;
+  for (unsigned t0 = 0; t0 < per_slice; t0 += 32) {
+    const unsigned cnt = per_slice - t0 < 32u ? per_slice - t0 : 32u;
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 1.0;
+    if ((unsigned)lane < cnt) {
+      const double* p = pbase + (size_t)(t0 + lane) * QB_FUSED_PART_STRIDE;
+      q0 = __ldcg(p);
+      q1 = __ldcg(p + 1);
+      q2 = __ldcg(p + 2);
+      q3 = __ldcg(p + 3);
+    }
+    for (unsigned t = 0; t < cnt; t++) {
+      const double v0 = __shfl_sync(0xffffffffu, q0, (int)t), v1 = __shfl_sync(0xffffffffu, q1, (int)t);
+      const double v2 = __shfl_sync(0xffffffffu, q2, (int)t), v3 = __shfl_sync(0xffffffffu, q3, (int)t);
+      stp = dd_add_d(stp, v0);
+      m1 += v1;
+      m2 += v2;
+      sok &= (v3 != 0.0);
+    }
+  }
+  if (lane == 0) {
+    double* o = summary + (size_t)slot * 8;
+    o[0] = stp.hi;
+    o[1] = stp.lo;
+    o[2] = m1;
+    o[3] = m2;
+    o[4] = (double)sok;
+    o[5] = o[6] = o[7] = 0.0;
+    tickets[slot] = 0;  // ready for the next run
+  }
+}
 
 #ifndef QB_FUSED_MIN_CTAS
 #define QB_FUSED_MIN_CTAS 4
@@ -634,13 +772,7 @@ __global__ void __launch_bounds__(QB_FUSED_WARPS * 32, QB_FUSED_MIN_CTAS) k_fuse
     err2 += __shfl_down_sync(0xffffffffu, err2, off);
     ok &= __shfl_down_sync(0xffffffffu, ok, off);
   }
-  if (lane == 0) {
-    double* p = a.part + ((size_t)s.slot * per_slice + rem) * QB_FUSED_PART_STRIDE;
-    p[0] = tp;
-    p[1] = err1;
-    p[2] = err2;
-    p[3] = (double)ok;
-  }
+  fused_close_tile(a.part, a.tickets, a.summary, (unsigned)s.slot, per_slice, rem, lane, tp, err1, err2, ok);
 }
 
 // One WARP per slice: tile partials -> summary, in tile order. The lanes fetch 32 partials at a
@@ -806,8 +938,9 @@ inline bool fused2d_prepare(const Plan& h, unsigned n_chunks, FusedPlan2D* f, st
   return true;
 }
 
-inline uint32_t fused2d_launches(const FusedPlan2D& f) {
-  uint32_t n = 3;  // axis tables, column records, final summary
+inline uint32_t fused2d_launches(const FusedPlan2D& f, bool lean = true) {
+  uint32_t n = lean ? 1 : 3;  // lean: one prologue launch, summaries inside the class kernels;
+                              // else axis tables, column records and the final summary
   for (const FusedChunk& c : f.chunks)
     for (int cl = 0; cl < 3; cl++) n += c.class_tiles[cl + 1] > c.class_tiles[cl] ? 1 : 0;
   return n;
@@ -868,8 +1001,11 @@ inline int fused2d_launch_chunk(const FusedPlan2D& f, FusedArgs args, size_t chu
 
 inline FusedArgs fused2d_args(const FusedPlan2D& f, const FusedSlice* d_fslices,
                               const double* d_cols, const AxisD* tab_a, const double* gw,
-                              double* part, double* d_cells) {
+                              double* part, double* d_cells, unsigned int* tickets = nullptr,
+                              double* d_summary = nullptr) {
   FusedArgs args;
+  args.tickets = tickets;
+  args.summary = d_summary;
   args.k = f.k;
   args.slices = d_fslices;
   args.tab_a = tab_a;

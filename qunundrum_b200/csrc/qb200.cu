@@ -109,6 +109,10 @@ struct qb200_context {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
   bool overlap_classes = true;         // QB200_OVERLAP_CLASSES=0: one stream (A/B)
+  // one prologue launch (axis tables + column records) and the slice summaries written by the
+  // class kernels themselves (tickets): three dependent launches less per step than
+  // k_axis2d -> k_fused_cols -> k_fused2d x 3 -> k_fused_final. QB200_FUSED_LEAN=0: the latter (A/B)
+  bool fused_lean = true;
   std::vector<cudaEvent_t> events;
   int sm_count = 0;
   uint64_t launches = 0;
@@ -137,7 +141,7 @@ struct qb200_plan {
   DevBuf cells_c, cells_f, part_c, part_f, part_tp, values;
   // fused path
   FusedPlan2D fused;
-  DevBuf fused_part, fused_cols, fused_slices;
+  DevBuf fused_part, fused_cols, fused_slices, fused_tickets;
   // fused one-dimensional path: per-block partials and per-slice tickets
   DevBuf f1d_part, f1d_tickets;
   bool f1d_ready = false;
@@ -150,7 +154,7 @@ struct qb200_plan {
     DevBuf* all[] = {&desc_a, &desc_b, &slices, &tab_a, &tab_b, &cells_c, &cells_f, &part_c,
                      &part_f, &part_tp, &values, &fused_part, &fused_cols, &fused_slices,
                      &so_sigma, &so_guess, &so_norm, &so_erra, &so_sigma0, &so_status,
-                     &so_changed, &f1d_part, &f1d_tickets};
+                     &so_changed, &f1d_part, &f1d_tickets, &fused_tickets};
     for (DevBuf* b : all) b->pool = pool;
   }
 };
@@ -509,6 +513,11 @@ int setup_fused(qb200_plan* pl, unsigned n_chunks) {
                                       QB_FUSED_PART_STRIDE * sizeof(double)))
     return rc;
   if (int rc = pl->fused_cols.reserve(pl->fused.cols_bytes)) return rc;
+  if (int rc = pl->fused_tickets.reserve(std::max<size_t>(1, pl->host.slices.size()) * sizeof(unsigned int)))
+    return rc;
+  // zeroed once: the kernel leaves every ticket at zero again
+  QB_CUDA(cudaMemsetAsync(pl->fused_tickets.p, 0, std::max<size_t>(1, pl->host.slices.size()) * sizeof(unsigned int),
+                          pl->ctx->stream));
   const size_t fb = std::max<size_t>(1, pl->fused.fslices.size()) * sizeof(FusedSlice);
   if (int rc = pl->fused_slices.reserve(fb)) return rc;
   if (!pl->fused.fslices.empty())
@@ -523,6 +532,17 @@ int enqueue_fused_prologue(qb200_plan* plan, cudaStream_t st) {
   const Plan& h = plan->host;
   const int NP = table_points(h.D);
   const int n_a = (int)h.tabs_a.size(), n_b = (int)h.tabs_b.size();
+  if (plan->ctx->fused_lean) {
+    const int ncol = plan->fused.k.ncol;
+    dim3 g((std::max(NP, ncol) + 127) / 128, n_a + 2 * n_b);
+    k_fused_prologue<<<g, 128, 0, st>>>(h.c, h.D, NP, n_a, n_b, plan->desc_a.as<TabDesc>(),
+                                        plan->desc_b.as<TabDesc>(), plan->geo->gx.as<dd>(),
+                                        plan->geo->gw.as<double>(), plan->tab_a.as<AxisD>(),
+                                        plan->tab_b.as<AxisR>(), plan->fused_cols.as<double>());
+    plan->ctx->launches += 1;
+    QB_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((NP + 127) / 128, n_a + n_b);
   k_axis2d<<<grid, 128, 0, st>>>(h.c, NP, n_a, plan->desc_a.as<TabDesc>(),
                                  plan->desc_b.as<TabDesc>(), plan->geo->gx.as<dd>(),
@@ -534,10 +554,12 @@ int enqueue_fused_prologue(qb200_plan* plan, cudaStream_t st) {
   return 0;
 }
 
-FusedArgs fused_args_of(qb200_plan* plan, double* d_cells) {
+FusedArgs fused_args_of(qb200_plan* plan, double* d_cells, double* d_summary) {
+  const bool lean = plan->ctx->fused_lean;
   return fused2d_args(plan->fused, plan->fused_slices.as<FusedSlice>(),
                       plan->fused_cols.as<double>(), plan->tab_a.as<AxisD>(),
-                      plan->geo->gw.as<double>(), plan->fused_part.as<double>(), d_cells);
+                      plan->geo->gw.as<double>(), plan->fused_part.as<double>(), d_cells,
+                      lean ? plan->fused_tickets.as<unsigned int>() : nullptr, lean ? d_summary : nullptr);
 }
 
 int enqueue_fused_chunk(qb200_plan* plan, const FusedArgs& args, size_t c, cudaStream_t st,
@@ -565,6 +587,7 @@ int enqueue_fused_chunk(qb200_plan* plan, const FusedArgs& args, size_t c, cudaS
 }
 
 int enqueue_fused_epilogue(qb200_plan* plan, cudaStream_t st, double* d_summary) {
+  if (plan->ctx->fused_lean) return 0;  // the class kernels wrote the summaries
   fused2d_launch_final(plan->fused, plan->host, st, plan->fused_part.as<double>(), d_summary);
   plan->ctx->launches += 1;
   QB_CUDA(cudaGetLastError());
@@ -627,6 +650,8 @@ int qb200_create(int device, qb200_context** out) {
   {
     const char* v = getenv("QB200_OVERLAP_CLASSES");
     ctx->overlap_classes = !(v && *v == '0');
+    v = getenv("QB200_FUSED_LEAN");
+    ctx->fused_lean = !(v && *v == '0');
   }
   ctx->out_cells.pool = nullptr;
   *out = ctx;
@@ -730,7 +755,7 @@ uint64_t qb200_plan_cells(const qb200_plan* plan) {
 
 uint32_t qb200_plan_launches(const qb200_plan* plan) {
   if (plan->host.kind >= 0 && plan->algo == 2) return (plan->n + 65534) / 65535;
-  if (plan->algo == 2) return fused2d_launches(plan->fused);
+  if (plan->algo == 2) return fused2d_launches(plan->fused, plan->ctx->fused_lean);
   return plain_launches(plan);
 }
 
@@ -768,7 +793,7 @@ int qb200_plan_run(qb200_plan* plan, void* stream, double* d_cells, double* d_su
   if (plan->algo == 2) {
     if (plan->n == 0) return 0;
     if (int rc = enqueue_fused_prologue(plan, st)) return rc;
-    const FusedArgs args = fused_args_of(plan, d_cells);
+    const FusedArgs args = fused_args_of(plan, d_cells, d_summary);
     for (size_t c = 0; c < plan->fused.chunks.size(); c++)
       if (int rc = enqueue_fused_chunk(plan, args, c, st, /*overlap_classes=*/ctx->overlap_classes)) return rc;
     return enqueue_fused_epilogue(plan, st, d_summary);
@@ -836,7 +861,7 @@ static int run_sync(qb200_context* ctx, qb200_plan* pl, double* cells, long doub
       ctx->events.push_back(ev);
     }
     if (int rc = enqueue_fused_prologue(pl, ctx->stream)) return rc;
-    const FusedArgs args = fused_args_of(pl, d_cells);
+    const FusedArgs args = fused_args_of(pl, d_cells, d_summary);
     const size_t per = (size_t)pl->host.D * pl->host.D;
     for (size_t c = 0; c < nch; c++) {
       if (int rc = enqueue_fused_chunk(pl, args, c, ctx->stream, ctx->overlap_classes)) return rc;
