@@ -225,6 +225,38 @@ def test_sigma_optimal_matches_reference_on_this_box(gpu_ctx):
             assert int(fl[i]) == R.flags
 
 
+def test_replayed_plans_are_cuda_graphs_with_the_same_results(gpu_ctx):
+    """A plan run again into the same buffers replays its step as one CUDA graph (the class kernels on
+    side streams, summaries by ticket): the same cells and summaries bit for bit as the eager first
+    run, also after the buffers change, for the heuristic and the sigma-optimal (large l) methods."""
+    import torch
+    P = _t2d_params()
+    coords = shard.enumerate_2d(2048)[::40]
+    ad, ar = [c[0] for c in coords], [c[1] for c in coords]
+    for method in (0, 1):
+        plan = gpu_ctx.plan2d(P, method, True, 64, ad, ar)
+        st = torch.cuda.Stream()
+        bufs = [(torch.zeros(plan.cells, dtype=torch.float64, device="cuda"),
+                 torch.zeros(plan.n * 8, dtype=torch.float64, device="cuda")) for _ in range(2)]
+        outs, counts = [], []
+        for k in (0, 0, 0, 1, 1, 0, 0):                   # eager, capture + replay, replay, new buffers ...
+            c, sm = bufs[k]
+            c.zero_()
+            sm.zero_()
+            torch.cuda.synchronize()
+            l0 = gpu_ctx.launch_count
+            plan.run(c.data_ptr(), sm.data_ptr(), st.cuda_stream)
+            torch.cuda.synchronize()
+            counts.append(gpu_ctx.launch_count - l0)
+            outs.append((c.cpu().numpy().copy(), sm.cpu().numpy().copy()))
+        for c, sm in outs[1:]:
+            assert np.array_equal(c, outs[0][0]) and np.array_equal(sm, outs[0][1])
+        assert len(set(counts)) == 1 and counts[0] >= 3, counts     # the replays account for their kernels
+        tp, te, fl = plan.finish(outs[-1][1])
+        assert np.all(tp > 0) and np.all(te > 0)
+        plan.close()
+
+
 def test_sigma_optimal_closed_form_walk_equals_the_iteration(gpu_ctx):
     """Large l (>= 256): the sigma-optimal walk is a prefix minimum in closed form (k_so_fast) over
     the quick method's cells. Against the general fixed-point iteration (QB200_SO_FAST=0): cells to
