@@ -109,10 +109,13 @@ struct qb200_context {
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
   bool overlap_classes = true;         // QB200_OVERLAP_CLASSES=0: one stream (A/B)
-  // one prologue launch (axis tables + column records) and the slice summaries written by the
-  // class kernels themselves (tickets): three dependent launches less per step than
-  // k_axis2d -> k_fused_cols -> k_fused2d x 3 -> k_fused_final. QB200_FUSED_LEAN=0: the latter (A/B)
-  bool fused_lean = true;
+  // QB200_FUSED_LEAN=1: one prologue launch (axis tables + column records) and the slice summaries
+  // written by the class kernels themselves (tickets) -- two dependent launches less per step than
+  // k_axis2d -> k_fused_cols -> k_fused2d x 3 -> k_fused_final. Measured (B200, an eighth of the
+  // bench distribution per step): 2.6 % faster when every step is enqueued eagerly, no gain once the
+  // step is a CUDA graph (0.1538 vs 0.1537 ms), and 0.8 % slower on the whole distribution (the
+  // ticket atomics and the closing warp sit in the hot kernel): off by default.
+  bool fused_lean = false;
   bool use_graphs = true;
   std::vector<cudaEvent_t> events;
   int sm_count = 0;
@@ -662,7 +665,7 @@ int qb200_create(int device, qb200_context** out) {
     const char* v = getenv("QB200_OVERLAP_CLASSES");
     ctx->overlap_classes = !(v && *v == '0');
     v = getenv("QB200_FUSED_LEAN");
-    ctx->fused_lean = !(v && *v == '0');
+    ctx->fused_lean = v && *v == '1';
     v = getenv("QB200_GRAPHS");
     ctx->use_graphs = !(v && *v == '0');
   }
