@@ -16,7 +16,7 @@ evaluations per slice; 55.08 M cells per step and per GPU.
 A step is one pass of the hot path over that batch. Slices are independent (no data-path
 collective; only the per-slice summaries are gathered on rank 0). For N > 1 the default is
 STRONG scaling: the 3362 slices of ONE distribution are partitioned over the ranks
-(shard.partition: slice i -> rank i mod N, the static form of the reference's task farm,
+(shard.partition: a rotating interleave of the priority-sorted list, the static form of the reference's task farm,
 src/main_generate_distribution.cpp:939-976), `value` = the distribution's cells / the slowest
 rank's time. `--scaling weak` (one whole distribution per rank, different d and r) is also
 measured in every N > 1 run and reported under `weak`; `saturation` is the same distribution in
@@ -82,7 +82,7 @@ def synthetic_d_r(seed: int):
 
 
 def workload_config(n_gpus, scaling="weak"):
-    per = ("the 3362 slices of ONE distribution partitioned over the ranks (slice i -> rank i mod N), "
+    per = ("the 3362 slices of ONE distribution partitioned over the ranks (rotating interleave of the sorted list), "
            "no data-path collective" if scaling == "strong" else
            f"one distribution per rank x {n_gpus} ranks, no data-path collective")
     return {
@@ -915,7 +915,8 @@ def saturation_section(ctx, qb, torch, stream, timer, P, coords, rank, tp128_all
             everything.setdefault(fin, []).append(i)
     # every dimension's list is dealt out on its own (a 512 slice is 16 times a 128 slice: the
     # farm hands them out one by one, a static partition has to balance them per dimension)
-    lists = {D: v[rank::max(1, world)] for D, v in everything.items()}
+    from qunundrum_b200 import shard
+    lists = {D: [v[k] for k in shard.partition(len(v), max(1, world), rank)] for D, v in everything.items()}
     lists = {D: v for D, v in lists.items() if v}
     plans, bufs, cells_total = [], [], 0
     for D in sorted(lists):

@@ -55,7 +55,8 @@ def test_shard_and_gather_world2():
     assert table.shape == (n, 8)
     assert np.array_equal(table[:, 0], np.arange(n) * 0.5)
     assert np.all(table[:, 4] == 1.0)
-    assert np.array_equal(table[:, 7], np.arange(n) % world)     # slice i -> rank i mod world
+    i = np.arange(n)
+    assert np.array_equal(table[:, 7], (i + i // world) % world)  # slice i -> rank (i + i // world) mod world
 
 
 def test_gather_without_process_group_is_identity():
