@@ -173,6 +173,8 @@ uint32_t qb200_plan_launches(const qb200_plan *plan);
 int qb200_plan_set_algorithm(qb200_plan *plan, int algo);
 int qb200_plan_algorithm(const qb200_plan *plan);
 
+/* (A two-dimensional plan that is run again with the same d_cells / d_summary replays its step
+ * as one CUDA graph, captured during the second such run; any other buffers run eagerly.) */
 int qb200_plan_run(qb200_plan *plan, void *stream, double *d_cells, double *d_summary);
 int qb200_plan_finish(const qb200_plan *plan, const double *h_summary,
                       long double *total_probability, long double *total_error,
