@@ -40,6 +40,7 @@ struct DiagKConst {
   uint32_t k;        // limbs of r (top limb non-zero)
   uint32_t wj;       // limbs of j: ceil(n / 32)
   uint32_t wl;       // limbs of k: ceil(l / 32)
+  // each with QB_DIAGK_PAD zero limbs below index 0 and above its last limb (mul_columns):
   const uint32_t* r;   // k limbs
   const uint32_t* d;   // k limbs (d < r)
   const uint32_t* mu;  // k + 2 limbs: floor(2^(64 k) / r)
@@ -231,7 +232,6 @@ QHD uint32_t acc_pop(Acc96& a) {
   a.a2 = 0;
   return out;
 }
-QHD uint32_t acc_low(const Acc96& a) { return a.a0; }
 QHD void acc_add(Acc96& a, const Acc96& b) {
   asm("add.cc.u32 %0, %0, %3;\n\t"
       "addc.cc.u32 %1, %1, %4;\n\t"
@@ -259,59 +259,78 @@ QHD uint32_t acc_pop(Acc96& a) {
   a.hi = 0;
   return out;
 }
-QHD uint32_t acc_low(const Acc96& a) { return (uint32_t)a.lo; }
 QHD void acc_add(Acc96& a, const Acc96& b) {
   a.lo += b.lo;
   a.hi += b.hi + ((a.lo < b.lo) ? 1u : 0u);
 }
 #endif
 
-// The terms U[a] V[c - a], a in [from, to], of column c.
-template <int SU, int SV>
-QHD void acc_terms(Acc96& acc, const uint32_t* U, const uint32_t* V, uint32_t c, uint32_t from, uint32_t to) {
-  for (uint32_t a = from; a <= to && a != 0xffffffffu; a++)
-    acc_mad(acc, U[(size_t)a * SU], V[(size_t)(c - a) * SV]);
-}
+// Zero limbs the constant operands (r, d, mu) carry below index 0 and above their last limb.
+#define QB_DIAGK_PAD 3
 
 // Columns [first, last] of the product U V (U: nu limbs at stride SU, V: nv limbs at stride SV;
 // column c = sum of U[a] V[b] over a + b = c, plus the carry of the columns before): the limbs of
-// the columns >= store_from go to out[(c - store_from) * SO]; `acc` holds the carry on entry
-// (zero for a product that starts here) and on return.
+// the columns >= store_from go to out[(c - store_from) * SO]; `acc` holds the carry on entry (zero
+// for a product that starts here).
 //
 // Four columns at a time: for a given a, the columns c .. c + 3 need U[a] and V[c - a .. c + 3 - a],
-// and the next a needs the same window of V moved down by one -- so one pass over the common
-// range of a loads U[a] and ONE new limb of V per step and feeds four accumulators (two loads per
-// four multiply-adds; the ragged ends of the four ranges, at most three terms each, are added
-// term by term). The accumulator travels by value (registers), also when the routine is compiled
-// as a separate function (QB_MULCOL_ATTR).
+// and the next a needs the same window of V moved down by one -- so one pass over a loads U[a] and
+// ONE new limb of V per step and feeds four accumulators (two loads per four multiply-adds). The
+// pass runs over the UNION of the four columns' ranges of a: V MUST BE READABLE AND ZERO at the
+// QB_DIAGK_PAD indices below 0 and above nv - 1, so that the terms a column does not have are
+// products with zero. (Round 1 ran the pass over the intersection and added the ragged ends term
+// by term: a fifth of the kernel's instructions, ncu source view, for 4 % of its multiply-adds.)
+// Columns past `last` that the last group of four covers are computed and not stored; the carry
+// that is returned is the one after that group.
 #ifndef QB_MULCOL_ATTR
 #define QB_MULCOL_ATTR QHD
+#endif
+#ifndef QB_DIAGK_UNROLL
+#define QB_DIAGK_UNROLL 4
+#endif
+// Loads of V. QB_DIAGK_LDS (device code only): V is known to lie in shared memory (k_diagk stages
+// r, d and mu there) and is read with ld.shared instead of a generic load.
+#if defined(__CUDA_ARCH__) && defined(QB_DIAGK_LDS) && QB_DIAGK_LDS
+typedef unsigned QB_VPTR;
+__device__ __forceinline__ unsigned qb_vptr_of(const uint32_t* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t qb_vload(unsigned p, int i) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p + 4u * (unsigned)i));
+  return v;
+}
+#define QB_VPTR_OF(p) qb_vptr_of(p)
+#define QB_VLOAD(p, i) qb_vload(p, (int)(i))
+#define QB_VSTEP(sv) (4u * (unsigned)(sv))
+#else
+typedef const uint32_t* QB_VPTR;
+#define QB_VPTR_OF(p) (p)
+#define QB_VLOAD(p, i) (p)[(size_t)(i)]
+#define QB_VSTEP(sv) (sv)
 #endif
 template <int SU, int SV, int SO>
 QB_MULCOL_ATTR Acc96 mul_columns(const uint32_t* __restrict__ U, uint32_t nu, const uint32_t* __restrict__ V,
                                  uint32_t nv, uint32_t first, uint32_t last, uint32_t store_from,
                                  uint32_t* __restrict__ out, Acc96 acc) {
-#define QB_LO(c) ((c) >= nv ? (c) - nv + 1 : 0u)
-#define QB_HI(c) ((c) < nu ? (c) : nu - 1)
-#define QB_EMIT(c, limb)                                                        \
-  do {                                                                          \
-    if ((c) >= store_from) out[(size_t)((c) - store_from) * SO] = (limb);       \
+#define QB_EMIT(c, limb)                                                                  \
+  do {                                                                                    \
+    if ((c) >= store_from && (c) <= last) out[(size_t)((c) - store_from) * SO] = (limb);  \
   } while (0)
-  uint32_t c = first;
-  for (; c + 3 <= last; c += 4) {
+  for (uint32_t c = first; c <= last; c += 4) {
     Acc96 a1, a2, a3;
     acc_zero(a1);
     acc_zero(a2);
     acc_zero(a3);
-    const uint32_t alo = QB_LO(c + 3), ahi = QB_HI(c);
+    const uint32_t alo = c >= nv ? c - nv + 1 : 0u;    // first a of column c
+    const uint32_t ahi = c + 3 < nu ? c + 3 : nu - 1;  // last a of column c + 3
     if (alo <= ahi) {
       const uint32_t* pu = U + (size_t)alo * SU;
-      const uint32_t* pv = V + (size_t)(c - alo) * SV;
-      uint32_t w1 = pv[(size_t)1 * SV], w2 = pv[(size_t)2 * SV], w3 = pv[(size_t)3 * SV];
+      QB_VPTR pv = QB_VPTR_OF(V + (size_t)(c - alo) * SV);  // c - alo <= nv - 1
+      uint32_t w1 = QB_VLOAD(pv, 1 * SV), w2 = QB_VLOAD(pv, 2 * SV), w3 = QB_VLOAD(pv, 3 * SV);
       uint32_t n = ahi - alo + 1;
-#pragma unroll 4
+      constexpr int kUnroll = QB_DIAGK_UNROLL;
+#pragma unroll kUnroll
       for (; n; n--) {
-        const uint32_t u = *pu, v0 = *pv;
+        const uint32_t u = *pu, v0 = QB_VLOAD(pv, 0);
         acc_mad(acc, u, v0);
         acc_mad(a1, u, w1);
         acc_mad(a2, u, w2);
@@ -320,22 +339,8 @@ QB_MULCOL_ATTR Acc96 mul_columns(const uint32_t* __restrict__ U, uint32_t nu, co
         w2 = w1;
         w1 = v0;
         pu += SU;
-        pv -= SV;
+        pv -= QB_VSTEP(SV);  // down to V[c - ahi] >= V[-3]
       }
-      // the ragged ends: a below alo (columns c .. c + 2) and above ahi (columns c + 1 .. c + 3)
-      if (alo) {
-        acc_terms<SU, SV>(acc, U, V, c, QB_LO(c), alo - 1);
-        acc_terms<SU, SV>(a1, U, V, c + 1, QB_LO(c + 1), alo - 1);
-        acc_terms<SU, SV>(a2, U, V, c + 2, QB_LO(c + 2), alo - 1);
-      }
-      acc_terms<SU, SV>(a1, U, V, c + 1, ahi + 1, QB_HI(c + 1));
-      acc_terms<SU, SV>(a2, U, V, c + 2, ahi + 1, QB_HI(c + 2));
-      acc_terms<SU, SV>(a3, U, V, c + 3, ahi + 1, QB_HI(c + 3));
-    } else {
-      acc_terms<SU, SV>(acc, U, V, c, QB_LO(c), QB_HI(c));
-      acc_terms<SU, SV>(a1, U, V, c + 1, QB_LO(c + 1), QB_HI(c + 1));
-      acc_terms<SU, SV>(a2, U, V, c + 2, QB_LO(c + 2), QB_HI(c + 2));
-      acc_terms<SU, SV>(a3, U, V, c + 3, QB_LO(c + 3), QB_HI(c + 3));
     }
     uint32_t limb = acc_pop(acc);
     QB_EMIT(c, limb);
@@ -349,13 +354,6 @@ QB_MULCOL_ATTR Acc96 mul_columns(const uint32_t* __restrict__ U, uint32_t nu, co
     limb = acc_pop(acc);
     QB_EMIT(c + 3, limb);
   }
-  for (; c <= last; c++) {
-    acc_terms<SU, SV>(acc, U, V, c, QB_LO(c), QB_HI(c));
-    const uint32_t limb = acc_pop(acc);
-    QB_EMIT(c, limb);
-  }
-#undef QB_LO
-#undef QB_HI
 #undef QB_EMIT
   return acc;
 }
@@ -391,11 +389,11 @@ QHD_NOINLINE void diagk_barrett(const DiagKConst& c, const uint32_t* A, uint32_t
   Acc96 acc;
   acc_zero(acc);
   // q2 = q1 mu with q1 = A[k - 1, 2k): k + 1 limbs, mu: k + 2 limbs; columns k + 1 .. 2k + 2 are Q
-  acc = mul_columns<S, 1, S>(&QB_L(A, k - 1), k + 1, c.mu, k + 2, k - 1, 2 * k + 1, k + 1, Q, acc);
-  QB_L(Q, k + 1) = acc_low(acc);
+  // (column 2k + 2 is the carry out of the product's last column)
+  acc = mul_columns<S, 1, S>(&QB_L(A, k - 1), k + 1, c.mu, k + 2, k - 1, 2 * k + 2, k + 1, Q, acc);
   // W = (x - Q r) mod 2^(32 (k + 1))
   acc_zero(acc);
-  acc = mul_columns<1, S, S>(c.r, k, Q, k + 2, 0, k, 0, W, acc);
+  acc = mul_columns<S, 1, S>(Q, k + 2, c.r, k, 0, k, 0, W, acc);
   uint32_t borrow = 0;
   for (uint32_t col = 0; col <= k; col++) {
     const uint64_t v = (uint64_t)QB_L(A, col) - QB_L(W, col) - borrow;
@@ -591,7 +589,7 @@ QHD void diagk_fraction(const DiagKConst& c, const uint32_t* j, int32_t eta, uin
   acc_zero(acc);
   // Z = r j: the columns from cs - 1 on go to A (free here), then to Sq
   const uint32_t ncol = k + c.wj;
-  acc = mul_columns<1, S, S>(c.r, k, j, c.wj, 0, ncol - 1, cs - 1, A, acc);
+  acc = mul_columns<S, 1, S>(j, c.wj, c.r, k, 0, ncol - 1, cs - 1, A, acc);
   const uint32_t below = QB_L(A, 0);  // column cs - 1
   for (uint32_t i = 0; i + cs < ncol; i++) QB_L(Sq, i) = QB_L(A, i + 1);
   const uint32_t ns = ncol - cs;  // <= k + 1 limbs hold Z >> (32 cs)
@@ -644,7 +642,7 @@ QHD void diagk_fraction(const DiagKConst& c, const uint32_t* j, int32_t eta, uin
   }
   // ---- w = d s mod r ----
   acc_zero(acc);
-  acc = mul_columns<1, S, S>(c.d, k, Sq, k, 0, 2 * k - 1, 0, A, acc);
+  acc = mul_columns<S, 1, S>(Sq, k, c.d, k, 0, 2 * k - 1, 0, A, acc);
   diagk_barrett<S>(c, A, Q, W);
   // ---- (Qv, w2) = divmod(2^l w, r), at most 32 k bits of the shift at a time ----
   const uint32_t chunk = 32 * k;

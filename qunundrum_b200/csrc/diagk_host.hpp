@@ -15,15 +15,16 @@
 namespace qb200 {
 
 struct DiagKHost {
-  std::vector<uint32_t> r, d, mu;
+  std::vector<uint32_t> r, d, mu;  // QB_DIAGK_PAD zero limbs, the number, QB_DIAGK_PAD zero limbs
   DiagKConst c;
 };
 
-inline std::vector<uint32_t> limbs32(const BigUInt& x, size_t n) {
-  std::vector<uint32_t> out(n, 0);
+// x as n limbs with the zero limbs mul_columns reads around a constant operand.
+inline std::vector<uint32_t> limbs32_padded(const BigUInt& x, size_t n) {
+  std::vector<uint32_t> out(n + 2 * QB_DIAGK_PAD, 0);
   for (size_t i = 0; i < n; i++) {
     const size_t w = i / 2;
-    if (w < x.w.size()) out[i] = (uint32_t)(x.w[w] >> (32 * (i % 2)));
+    if (w < x.w.size()) out[QB_DIAGK_PAD + i] = (uint32_t)(x.w[w] >> (32 * (i % 2)));
   }
   return out;
 }
@@ -46,11 +47,11 @@ inline int diagk_prepare(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* 
     return -3;
   }
   const uint32_t k = (uint32_t)((r.bit_length() + 31) / 32);
-  h->r = limbs32(r, k);
-  h->d = limbs32(d, k);
+  h->r = limbs32_padded(r, k);
+  h->d = limbs32_padded(d, k);
   BigUInt q, rem;
   BigUInt::divmod(BigUInt::pow2(64ull * k), r, q, rem);
-  h->mu = limbs32(q, k + 2);
+  h->mu = limbs32_padded(q, k + 2);
   DiagKConst& c = h->c;
   c.m = m;
   c.sigma = sigma;
@@ -59,10 +60,10 @@ inline int diagk_prepare(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* 
   c.k = k;
   c.wj = (c.n + 31) / 32;
   c.wl = (l + 31) / 32;
-  c.r = h->r.data();
-  c.d = h->d.data();
-  c.mu = h->mu.data();
-  c.r_top = limbs_top_dd<1>(h->r.data(), k - 1);
+  c.r = h->r.data() + QB_DIAGK_PAD;
+  c.d = h->d.data() + QB_DIAGK_PAD;
+  c.mu = h->mu.data() + QB_DIAGK_PAD;
+  c.r_top = limbs_top_dd<1>(c.r, k - 1);
   c.force_exact = 0;
   return 0;
 }

@@ -109,7 +109,6 @@ __device__ __forceinline__ void diagk_tile(const DiagKConst& c, uint32_t tb, con
                                            unsigned long long delta_bound, uint32_t B,
                                            uint32_t* __restrict__ scratch, uint32_t* __restrict__ kT,
                                            DiagKOut* __restrict__ out) {
-  const uint32_t k = c.k;
   const uint32_t g = tb * QB_DIAGK_CTA + threadIdx.x;
   const size_t tile = (size_t)tb * QB_DIAGK_CTA;
   uint32_t* k_out = kT ? kT + tile * c.wl + threadIdx.x : nullptr;
@@ -191,7 +190,10 @@ __device__ __forceinline__ void diagk_tile(const DiagKConst& c, uint32_t tb, con
 // does not lower the DRAM traffic either (1.23 GB per launch in ncu with 6 per SM: the in-flight
 // scratch of a full wave does not fit the L2 next to the inputs, and fewer CTAs cost more than
 // the traffic saves -- DRAM is at 8 % of its bandwidth here).
-__global__ void __launch_bounds__(QB_DIAGK_CTA, 6) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
+#ifndef QB_DIAGK_MIN_CTAS
+#define QB_DIAGK_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(QB_DIAGK_CTA, QB_DIAGK_MIN_CTAS) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
                                                 const int32_t* __restrict__ eta,
                                                 const RawX87* __restrict__ pivot,
                                                 unsigned long long delta_bound, uint32_t B,
@@ -199,15 +201,14 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA, 6) k_diagk(DiagKConst c, const u
                                                 DiagKOut* __restrict__ out) {
   extern __shared__ uint32_t sh[];
   const uint32_t k = c.k;
-  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
-    sh[i] = c.r[i];
-    sh[k + i] = c.d[i];
-  }
-  for (uint32_t i = threadIdx.x; i < k + 2; i += blockDim.x) sh[2 * k + i] = c.mu[i];
+  // r, d, mu with their zero limbs: contiguous in global memory (qb200_diagk_create), c.r the first
+  const uint32_t words = 3 * k + 2 + 6 * QB_DIAGK_PAD;
+  const uint32_t* src = c.r - QB_DIAGK_PAD;
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sh[i] = src[i];
   __syncthreads();
-  c.r = sh;
-  c.d = sh + k;
-  c.mu = sh + 2 * k;
+  c.r = sh + QB_DIAGK_PAD;
+  c.d = sh + (k + 2 * QB_DIAGK_PAD) + QB_DIAGK_PAD;
+  c.mu = sh + 2 * (k + 2 * QB_DIAGK_PAD) + QB_DIAGK_PAD;
   const uint32_t n_tiles = (B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA;
   uint32_t* mine = scratch + (size_t)blockIdx.x * QB_DIAGK_CTA * diagk_scratch_limbs(k);
   for (uint32_t tb = blockIdx.x; tb < n_tiles; tb += gridDim.x)

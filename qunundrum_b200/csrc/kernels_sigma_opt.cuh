@@ -293,10 +293,12 @@ __global__ void __launch_bounds__(QB_SOF_BLOCK)
 k_so_fast(DevConsts c, SoLayout L, const DevSlice* __restrict__ slices, const AxisD* __restrict__ tab_a,
           const AxisR* __restrict__ tab_b, const double* __restrict__ gw, double* __restrict__ summary,
           int* __restrict__ fallback) {
-  __shared__ int warp_min[QB_SOF_BLOCK / 32];
-  __shared__ int carry_s, first_s;
+  constexpr int NW = QB_SOF_BLOCK / 32;
+  __shared__ int warp_min[2][NW];
+  __shared__ int first_s;
   __shared__ double sa[QB_SOF_BLOCK], sb[QB_SOF_BLOCK];
   __shared__ int so[QB_SOF_BLOCK];
+  extern __shared__ double s_wgt[];  // Simpson weight of every abscissa of an axis (4 D + 1 at most)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const DevSlice s = slices[blockIdx.x];
   const int NP = table_points(L.D);
@@ -310,14 +312,14 @@ k_so_fast(DevConsts c, SoLayout L, const DevSlice* __restrict__ slices, const Ax
     const AxisD* ta = tab_a + (size_t)s.tab_a * NP + off;
     const AxisR* tb = tab_b + (size_t)s.tab_b * NP + off;
     const double* wd = gw + width_offset(L.D, pass);
-    if (tid == 0) carry_s = QB_SOF_NONE;
+    for (int i = tid; i < side; i += QB_SOF_BLOCK) s_wgt[i] = so_axis_weight(wd, Dp, i);
     __syncthreads();
     double A = 0.0, Cc = 0.0;
-    int ok = 1, s0 = 0;
+    int ok = 1, s0 = 0, buf = 0;
+    int carry = QB_SOF_NONE;  // running minimum of the chunks before this one (the same in every thread)
     int i = tid / side, j = tid - i * side;  // point p = start + tid of the walk: (i, j) = (alpha_d, alpha_r) index
     for (int start = 0; start < npts; start += QB_SOF_BLOCK) {
-      const int p = start + tid;
-      const bool live = p < npts;
+      const bool live = start + tid < npts;
       double n = 0.0, ph = 0.0, wgt = 0.0;
       int v = QB_SOF_NONE;
       if (live) {
@@ -329,35 +331,41 @@ k_so_fast(DevConsts c, SoLayout L, const DevSlice* __restrict__ slices, const Ax
         n = t1 * t1 * r.t2;
         ph = PI * (fabs(d.xh) + r.b);
         const double a = ph * n * c.r_m;
-        v = p == 0 ? so_fast_sigma_first(c.l, a) : so_fast_sigma_star(c.l, a);
-        wgt = so_axis_weight(wd, Dp, i) * so_axis_weight(wd, Dp, j);
+        v = so_fast_sigma_star(c.l, a);
+        if (start + tid == 0) {
+          v = so_fast_sigma_first(c.l, a);
+          first_s = v;  // sigma_0 of the pass
+        }
+        wgt = s_wgt[i] * s_wgt[j];
       }
-      // inclusive running minimum along the walk, carried from chunk to chunk
+      // inclusive running minimum along the walk, carried from chunk to chunk: one barrier per chunk
+      // (the warps' minima go to alternating buffers, every thread folds all of them into its carry)
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o) v = min(v, t);
       }
-      if (lane == 31) warp_min[w] = v;
+      if (lane == 31) warp_min[buf][w] = v;
       __syncthreads();
-      int pre = carry_s;
-      for (int k = 0; k < w; k++) pre = min(pre, warp_min[k]);
+      int pre = carry;
+#pragma unroll
+      for (int k = 0; k < NW; k++) {
+        const int m = warp_min[buf][k];
+        if (k < w) pre = min(pre, m);
+        carry = min(carry, m);
+      }
+      buf ^= 1;
       v = min(v, pre);
-      __syncthreads();
-      if (tid == QB_SOF_BLOCK - 1) carry_s = v;
-      if (start == 0 && tid == 0) first_s = v;
-      __syncthreads();
-      if (start == 0) s0 = first_s;  // sigma_0 of the pass
+      if (start == 0) s0 = first_s;
       if (live) {
         const int sg = v;
         if (sg < 64 || sg > c.l - 60) {
           bad = 1;
         } else {
-          const int sl = sg - c.l;
-          const double sv = sl > -1000 ? ldexp(ph, sl) : 0.0;
-          const double era = ldexp(ph * (2.0 + sv) * n * c.r_m, max(sg - s0, -1000));
+          double era, ct;
+          so_fast_terms(c, ph, n, sg, s0, &era, &ct);
           A = fma(wgt, era, A);
-          Cc = fma(wgt, ldexp(1.0, min(s0 - sg, 1000)), Cc);
-          if (pass == 0 && !so_bounded(c, n, so_error_given_norm(c, ph, n, sg))) ok = 0;
+          Cc = fma(wgt, ct, Cc);
+          if (pass == 0 && !so_fast_bounded(c, ph, n, sg)) ok = 0;
         }
       }
       j += QB_SOF_BLOCK;

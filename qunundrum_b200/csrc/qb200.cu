@@ -300,7 +300,8 @@ int run_sigma_opt_2d(qb200_plan* pl, cudaStream_t st, double* d_cells, double* d
     int* d_fallback = pl->so_changed.as<int>();
     QB_CUDA(cudaMemsetAsync(d_fallback, 0, sizeof(int), st));
     if (int rc = qb200_plan_run(q, st, d_cells, d_summary)) return rc;
-    k_so_fast<<<pl->n, QB_SOF_BLOCK, 0, st>>>(q->host.c, L, q->slices.as<DevSlice>(), q->tab_a.as<AxisD>(),
+    const size_t wgt_bytes = (size_t)(4 * L.D + 1) * sizeof(double);  // the fine pass's abscissae
+    k_so_fast<<<pl->n, QB_SOF_BLOCK, wgt_bytes, st>>>(q->host.c, L, q->slices.as<DevSlice>(), q->tab_a.as<AxisD>(),
                                              q->tab_b.as<AxisR>(), q->geo->gw.as<double>(), d_summary,
                                              d_fallback);
     ctx->launches++;

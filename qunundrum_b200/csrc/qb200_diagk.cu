@@ -91,15 +91,18 @@ int qb200_diagk_create(qb200_context* ctx, const qb200_params* params, qb200_dia
   s->stream = cv.stream;
   s->launches = cv.launches;
   const uint32_t k = s->host.c.k;
-  if (s->consts.reserve((size_t)(3 * k + 2) * 4)) return -100;
+  // r, d, mu one after the other, each with its zero limbs (diagk_host.hpp); the kernel stages the
+  // same 3 k + 2 + 6 QB_DIAGK_PAD words in shared memory
+  const size_t nr = s->host.r.size(), nd = s->host.d.size(), nmu = s->host.mu.size();
+  if (s->consts.reserve((nr + nd + nmu) * 4)) return -100;
   uint32_t* c = s->consts.as<uint32_t>();
-  QD_CUDA(cudaMemcpy(c, s->host.r.data(), (size_t)k * 4, cudaMemcpyHostToDevice));
-  QD_CUDA(cudaMemcpy(c + k, s->host.d.data(), (size_t)k * 4, cudaMemcpyHostToDevice));
-  QD_CUDA(cudaMemcpy(c + 2 * k, s->host.mu.data(), (size_t)(k + 2) * 4, cudaMemcpyHostToDevice));
+  QD_CUDA(cudaMemcpy(c, s->host.r.data(), nr * 4, cudaMemcpyHostToDevice));
+  QD_CUDA(cudaMemcpy(c + nr, s->host.d.data(), nd * 4, cudaMemcpyHostToDevice));
+  QD_CUDA(cudaMemcpy(c + nr + nd, s->host.mu.data(), nmu * 4, cudaMemcpyHostToDevice));
   s->dev = s->host.c;
-  s->dev.r = c;
-  s->dev.d = c + k;
-  s->dev.mu = c + 2 * k;
+  s->dev.r = c + QB_DIAGK_PAD;
+  s->dev.d = c + nr + QB_DIAGK_PAD;
+  s->dev.mu = c + nr + nd + QB_DIAGK_PAD;
   s->chunk = pick_chunk(s.get(), cv.sm_count);
   *out = s.release();
   return 0;
@@ -127,7 +130,7 @@ static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const i
   const DiagKConst& c = s->host.c;
   const size_t scr = diagk_scratch_limbs(c.k);
   const size_t Bp = ((size_t)B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA * QB_DIAGK_CTA;  // whole tiles
-  const size_t shmem = (size_t)(3 * c.k + 2) * 4;
+  const size_t shmem = (size_t)(3 * c.k + 2 + 6 * QB_DIAGK_PAD) * 4;
   // one CTA (and one scratch area) per tile: a persistent wave with per-CTA scratch was measured
   // and is slower (kernels_diagk.cuh)
   const uint32_t grid = (uint32_t)(Bp / QB_DIAGK_CTA);

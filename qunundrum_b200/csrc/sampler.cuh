@@ -174,8 +174,15 @@ QHD uint32_t seg_guide_entry(const SegCoarse* coarse, uint32_t n_blocks, uint32_
   return lo;
 }
 
+// Rare paths are compiled out of line, so that the common path stays short.
+#if defined(__CUDACC__)
+#define QB_SEG_SLOW inline __host__ __device__ __noinline__
+#else
+#define QB_SEG_SLOW inline
+#endif
+
 // The reference's walk, replayed bit for bit: first k with pivot - v[0] - ... - v[k] <= 0.
-QHD uint32_t seg_walk_exact(const RawX87* v, uint32_t n, X87 p) {
+QB_SEG_SLOW uint32_t seg_walk_exact(const RawX87* v, uint32_t n, X87 p) {
   bool ok = true;
   for (uint32_t k = 0; k < n; k++) {
     p = x87_add(p, x87_neg(x87_load(v + k, &ok)));
@@ -183,6 +190,29 @@ QHD uint32_t seg_walk_exact(const RawX87* v, uint32_t n, X87 p) {
   }
   return n;
 }
+
+// The block [k0, k1) in double-double, for the searches the pass in doubles leaves open (~1e-10 of
+// them).
+QB_SEG_SLOW uint32_t seg_find_slow(const RawX87* v, const SegCoarse* coarse, uint32_t lo, uint32_t k0,
+                                   uint32_t k1, uint32_t n, double unit, X87 p, dd pd, int* exact) {
+  dd c = coarse[lo].c, mprev = coarse[lo].m;
+  bool ok = true;
+  for (uint32_t k = k0; k < k1; k++) {
+    c = dd_add(c, x87_to_dd(x87_load(v + k, &ok)));
+    if (dd_ge(c, pd)) {
+      const double band = (double)(k + 2) * unit;
+      const dd over = dd_add(c, dd_neg(pd)), clear = dd_add(pd, dd_neg(mprev));
+      if (over.hi > band && clear.hi > band) return k;
+      *exact += 1;
+      return seg_walk_exact(v, n, p);
+    }
+    mprev = dd_max(mprev, c);
+  }
+  // the block summary promised a hit inside this block; rounding of the summary itself
+  *exact += 1;
+  return seg_walk_exact(v, n, p);
+}
+
 
 // First k at which the reference's walk stops, or n. *exact is incremented when the replay ran.
 // mode (test switch): 0 normal; 1 every walk through the bit-exact replay; 2 skip the quick pass in
@@ -236,6 +266,9 @@ QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* 
   // are within 2^-49 * scale of the exact ones, so a hit that clears the pivot -- and a pivot
   // that clears every earlier prefix -- by 2^-47 * scale is the exact walk's and, a fortiori
   // (2^-47 >> n 2^-63), the reference's. All but ~1e-10 of the searches end here.
+  // The pass has ONE exit: with a `return` per element the threads of a warp reached the code
+  // after the search at up to eight different times and stayed apart to the end of the kernel
+  // (ncu, round 2: 16 threads per instruction after the first search, 9 after the second).
   if (mode != 2) {
     double x[QB_SEG_BLOCK];
 #pragma unroll
@@ -243,33 +276,20 @@ QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* 
       x[q] = k0 + q < k1 ? x87_raw_to_double(v[k0 + q]) : 0.0;
     const double wide = 7.105427357601002e-15 * (fabs(pd.hi) + abs_sum);  // 2^-47 * scale
     double c = coarse[lo].c.hi, mprev = coarse[lo].m.hi;
+    int hit = -1;
+    bool clear = false;
 #pragma unroll
     for (int q = 0; q < QB_SEG_BLOCK; q++) {
-      if (k0 + q >= k1) break;
       c += x[q];
-      if (c >= pd.hi) {
-        if (c - pd.hi > wide && pd.hi - mprev > wide) return k0 + (uint32_t)q;
-        break;  // too close to call in doubles
+      if (hit < 0 && k0 + q < k1 && c >= pd.hi) {
+        hit = q;
+        clear = c - pd.hi > wide && pd.hi - mprev > wide;  // else: too close to call in doubles
       }
-      mprev = fmax(mprev, c);
+      mprev = hit < 0 ? fmax(mprev, c) : mprev;
     }
+    if (clear) return k0 + (uint32_t)hit;
   }
-  dd c = coarse[lo].c, mprev = coarse[lo].m;
-  bool ok = true;
-  for (uint32_t k = k0; k < k1; k++) {
-    c = dd_add(c, x87_to_dd(x87_load(v + k, &ok)));
-    if (dd_ge(c, pd)) {
-      const double band = (double)(k + 2) * unit;
-      const dd over = dd_add(c, dd_neg(pd)), clear = dd_add(pd, dd_neg(mprev));
-      if (over.hi > band && clear.hi > band) return k;
-      *exact += 1;
-      return seg_walk_exact(v, n, p);
-    }
-    mprev = dd_max(mprev, c);
-  }
-  // the block summary promised a hit inside this block; rounding of the summary itself
-  *exact += 1;
-  return seg_walk_exact(v, n, p);
+  return seg_find_slow(v, coarse, lo, k0, k1, n, unit, p, pd, exact);
 }
 
 // |alpha| / 2^m for region j of an axis with coordinate k and dimension D, and fraction word w

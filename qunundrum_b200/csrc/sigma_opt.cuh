@@ -179,8 +179,19 @@ QHD int so_adjust(const DevConsts& c, const SigmaOptConsts& q, const SoPoint& p,
 QHD int so_fast_sigma_star(int l, double a) {
   if (!(a > 0.0)) return 0x3fffffff;  // n = 0: e decreases with sigma for ever, the descent never moves
   int e;
-  const double f = frexp(a, &e);
-  const int kmax = f == 0.5 ? 5 : 4;
+  bool half;
+#if defined(__CUDA_ARCH__)
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
+  const int field = (int)(bits >> 52);  // a > 0: no sign bit
+  if (field != 0 && field != 0x7ff) {   // a normal number: frexp without its special cases
+    e = field - 1022;
+    half = (bits & 0xfffffffffffffull) == 0;
+  } else
+#endif
+  {
+    half = frexp(a, &e) == 0.5;
+  }
+  const int kmax = half ? 5 : 4;
   const int t = kmax + l - e;  // 2 sigma <= t
   return t >= 0 ? t / 2 : -((1 - t) / 2);  // floor(t / 2)
 }
@@ -202,6 +213,31 @@ QHD xd so_error_given_norm(const DevConsts& c, double ph, double n, int sigma) {
   e = xd_add(e, xd_make(1.0, 4 - sigma));
   e = xd_add(e, xd_make(1.0, 3 - c.l));
   return e;
+}
+
+// A point's terms of the two error sums of a slice, both relative to sigma_0 of the pass (s0 >= sg):
+//   *era = pi h (2 + s) n r/2^m 2^(sg - s0),  s = pi h 2^(sg - l);    *cterm = 2^(s0 - sg)
+// i.e. 2^(l - s0) times the first and 2^(s0 - 4) times the second term of e(sg). Scaling by a power
+// of two is a multiplication here (exact, or rounded once where the product is subnormal, as ldexp).
+QHD void so_fast_terms(const DevConsts& c, double ph, double n, int sg, int s0, double* era, double* cterm) {
+  const int sl = sg - c.l;
+  const double sv = sl > -1000 ? ph * pow2i(sl) : 0.0;
+  const int down = sg - s0 > -1000 ? sg - s0 : -1000, up = s0 - sg < 1000 ? s0 - sg : 1000;
+  *era = ph * (2.0 + sv) * n * c.r_m * pow2i(down);
+  *cterm = pow2i(up);
+}
+
+// so_bounded(c, n, e(sg)) for a point of the closed-form walk, where 64 <= sg <= sigma* (the prefix
+// minimum). There a 2^(2 sg - l) <= 16 with a = pi h n r/2^m, so
+//     e(sg) 2^sg = a (2 + s) 2^(2 sg - l) + 16 + 2^(3 - l + sg) < 49,
+// and the bound holds whenever 0.01 n r/2^m 2^sg >= 49: decided without extended-range arithmetic
+// for every point whose norm is not vanishingly small; the others take the comparison itself.
+QHD bool so_fast_bounded(const DevConsts& c, double ph, double n, int sg) {
+  const double nr = n * c.r_m;
+  // 49 / 0.01f = 4900.0002; beyond sigma = 1000 the (stricter) threshold of sigma = 1000
+  const double need = 4900.001 * pow2i(sg <= 1000 ? -sg : -1000);
+  if (nr >= need) return true;
+  return so_bounded(c, n, so_error_given_norm(c, ph, n, sg));
 }
 
 // Simpson weight of abscissa i (0 .. 2 Dp) of one axis over the cells it belongs to:

@@ -269,12 +269,17 @@ int hostsim_so_fast(uint32_t m, uint32_t l, const uint8_t* d, size_t dn, const u
             fallback = 1;
             continue;
           }
-          const int sl = run - c.l;
-          const double sv = sl > -1000 ? ldexp(ph, sl) : 0.0;
           const double wgt = so_axis_weight(wd, Dp, i) * so_axis_weight(wd, Dp, j);
-          A += wgt * ldexp(ph * (2.0 + sv) * nn * c.r_m, run - s0[pass]);
-          Cc += wgt * ldexp(1.0, s0[pass] - run);
-          if (pass == 0 && !so_bounded(c, nn, so_error_given_norm(c, ph, nn, run))) bounded = false;
+          double era, ct;
+          so_fast_terms(c, ph, nn, run, s0[pass], &era, &ct);
+          A += wgt * era;
+          Cc += wgt * ct;
+          const bool in_bound = so_fast_bounded(c, ph, nn, run);
+          if (in_bound != so_bounded(c, nn, so_error_given_norm(c, ph, nn, run))) {
+            g_err = "so_fast_bounded disagrees with so_bounded";
+            return -77;
+          }
+          if (pass == 0 && !in_bound) bounded = false;
         }
       const double f = sd.scale_a * sd.scale_b / 36.0;
       summ[pass ? 5 : 2] = A * f;
