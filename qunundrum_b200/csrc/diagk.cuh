@@ -288,9 +288,12 @@ QHD void acc_add(Acc96& a, const Acc96& b) {
 #ifndef QB_DIAGK_UNROLL
 #define QB_DIAGK_UNROLL 4
 #endif
-// Loads of V. QB_DIAGK_LDS (device code only): V is known to lie in shared memory (k_diagk stages
-// r, d and mu there) and is read with ld.shared instead of a generic load.
-#if defined(__CUDA_ARCH__) && defined(QB_DIAGK_LDS) && QB_DIAGK_LDS
+// Loads of V. In device code V lies in shared memory (k_diagk stages r, d and mu there) and is read
+// with ld.shared instead of a generic load (+3 %; QB_DIAGK_LDS=0: generic loads, for the A/B).
+#ifndef QB_DIAGK_LDS
+#define QB_DIAGK_LDS 1
+#endif
+#if defined(__CUDA_ARCH__) && QB_DIAGK_LDS
 typedef unsigned QB_VPTR;
 __device__ __forceinline__ unsigned qb_vptr_of(const uint32_t* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t qb_vload(unsigned p, int i) {

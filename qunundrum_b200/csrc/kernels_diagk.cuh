@@ -191,7 +191,7 @@ __device__ __forceinline__ void diagk_tile(const DiagKConst& c, uint32_t tb, con
 // scratch of a full wave does not fit the L2 next to the inputs, and fewer CTAs cost more than
 // the traffic saves -- DRAM is at 8 % of its bandwidth here).
 #ifndef QB_DIAGK_MIN_CTAS
-#define QB_DIAGK_MIN_CTAS 6
+#define QB_DIAGK_MIN_CTAS 8
 #endif
 __global__ void __launch_bounds__(QB_DIAGK_CTA, QB_DIAGK_MIN_CTAS) k_diagk(DiagKConst c, const uint32_t* __restrict__ jT,
                                                 const int32_t* __restrict__ eta,

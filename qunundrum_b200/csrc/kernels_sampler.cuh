@@ -57,12 +57,22 @@ __global__ void __launch_bounds__(256) k_seg_build(const SegDesc* __restrict__ s
 
 #define QB_TAU_SKIP 0xffffffffffffffffull
 
+#ifndef QB_SAMPLE_MIN_CTAS
+#define QB_SAMPLE_MIN_CTAS 6
+#endif
+
 // Sample i of estimate t reads its words at off[t] + i * wps (off == QB_TAU_SKIP: the host
 // already knows that the estimate fails, nothing to do). off == nullptr: regular layout.
-__global__ void __launch_bounds__(128) k_sample(SamplerView view, const uint64_t* __restrict__ words,
-                                                 const uint64_t* __restrict__ off, uint32_t n,
-                                                 uint64_t total, int force_exact,
-                                                 SampleOut* __restrict__ out) {
+//
+// Bound by look-ups in L1: every load of a warp touches 32 different lines (ncu, round 2: 0.84 tag
+// look-ups per cycle and SM). What helped: 16-byte loads (ld16, sampler.cuh; 44 -> 33 million
+// look-ups per 2^20 samples, 4.4 -> 6.5e9 samples/s). What did not: fetching the 32 blocks of a
+// warp cooperatively (8 lanes x 16 bytes per block, values handed to their owners through shared
+// memory): a quarter fewer look-ups again, but every lane then waits for the slowest search of its
+// warp twice per sample -- 5.6e9 samples/s, removed (profiles/r02_sampler_cooperative_fetch.txt).
+__global__ void __launch_bounds__(128, QB_SAMPLE_MIN_CTAS)
+k_sample(SamplerView view, const uint64_t* __restrict__ words, const uint64_t* __restrict__ off, uint32_t n,
+         uint64_t total, int force_exact, SampleOut* __restrict__ out) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
   const uint32_t wps = (uint32_t)view.dims + 2u;
@@ -79,8 +89,9 @@ __global__ void __launch_bounds__(128) k_sample(SamplerView view, const uint64_t
   } else {
     base = g * wps;
   }
-  uint64_t w[4];
-  for (uint32_t q = 0; q < wps; q++) w[q] = words[base + q];
+  uint64_t w[4];  // (unrolled with a predicate: a loop to wps indexes w dynamically and puts it in local memory)
+#pragma unroll
+  for (uint32_t q = 0; q < 4; q++) w[q] = q < wps ? words[base + q] : 0ull;
   SampleOut o;
   sample_one(view, w, force_exact, &o);
   out[g] = o;

@@ -37,17 +37,44 @@ namespace qb200 {
 #define QB_SEG_BLOCK 8
 #endif
 
-struct RawX87 {  // the 16 bytes of an x86-64 long double
+// The structures below are read by threads whose addresses have nothing to do with each other:
+// every load instruction of a warp is 32 look-ups in L1, and the kernel is bound by exactly those
+// (ncu, round 2: 0.74 tag look-ups per cycle and SM, issue slots 25 % active). They are 16-byte
+// aligned and read 16 bytes at a time (ld16 below): half the look-ups of the 8-byte loads the
+// compiler emits for members it knows only to be 8-byte aligned.
+struct alignas(16) RawX87 {  // the 16 bytes of an x86-64 long double
   uint64_t mant;
   uint64_t se;   // low 16 bits: sign and exponent; the rest is padding (ignored)
 };
 
-struct SegCoarse {  // state of the walk BEFORE a block
+struct alignas(16) SegCoarse {  // state of the walk BEFORE a block
   dd c;             // prefix sum
   dd m;             // running maximum of the earlier prefix sums (-1e300 before the first)
 };
 
-struct SamplerSlice {
+// One 16-byte load from an array in GLOBAL memory (not for a member of a kernel parameter). As
+// inline PTX: written as a plain 16-byte access the compiler narrows it to the 8 + 4 bytes that
+// are used and is back to two look-ups.
+QHD RawX87 ld16(const RawX87* p) {
+#if defined(__CUDA_ARCH__)
+  RawX87 r;
+  asm("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.mant), "=l"(r.se) : "l"(__cvta_generic_to_global(p)));
+  return r;
+#else
+  return *p;
+#endif
+}
+QHD dd ld16(const dd* p) {
+#if defined(__CUDA_ARCH__)
+  dd r;
+  asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.hi), "=d"(r.lo) : "l"(__cvta_generic_to_global(p)));
+  return r;
+#else
+  return *p;
+#endif
+}
+
+struct alignas(16) SamplerSlice {
   uint64_t cell_off;    // first cell in SamplerView::cells
   uint64_t coarse_off;  // first entry in SamplerView::coarse (n_blocks + 1 entries)
   uint32_t n_cells;
@@ -76,7 +103,7 @@ struct SamplerView {
   int dims;                        // 2: Distribution, 1: Linear_Distribution
 };
 
-struct SampleOut {  // 64 bytes
+struct alignas(16) SampleOut {  // 64 bytes
   double sq0_hi, sq0_lo;  // (alpha_d / 2^m)^2   (linear: (alpha / 2^m)^2)
   double sq1_hi, sq1_lo;  // (alpha_r / 2^m)^2
   double x0, x1;          // alpha / 2^m rounded to double, signed
@@ -98,6 +125,13 @@ QHD double x87_raw_to_double(const RawX87 r) {
   if ((se & 0x7fffu) == 0 || e < 1 || e > 2046) return 0.0;
   return qb_bits_to_double(((uint64_t)(se & 0x8000u) << 48) | ((uint64_t)e << 52) |
                            ((r.mant >> 11) & 0xfffffffffffffull));
+}
+
+QHD X87 x87_load16(const RawX87* p, bool* ok) {  // p: an element of an array in global memory
+  X87 v;
+  const RawX87 r = ld16(p);
+  if (!x87_decode(r.mant, (uint32_t)r.se & 0xffffu, &v)) *ok = false;
+  return v;
 }
 
 QHD X87 x87_load(const RawX87* p, bool* ok) {
@@ -214,19 +248,28 @@ QB_SEG_SLOW uint32_t seg_find_slow(const RawX87* v, const SegCoarse* coarse, uin
 }
 
 
-// First k at which the reference's walk stops, or n. *exact is incremented when the replay ran.
+// ---- the search, in three steps -------------------------------------------------------------
+// seg_locate: the block the walk stops in (or the answer itself where no block is needed);
+// seg_block_doubles: the block's elements as doubles; seg_decide: the stopping element.
+// seg_find chains them. (The split exists because the middle step was tried with the whole warp --
+// kernels_sampler.cuh -- and is kept: the pieces are easier to read and to test.)
 // mode (test switch): 0 normal; 1 every walk through the bit-exact replay; 2 skip the quick pass in
-// doubles (every search through the double-double path).
-QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* guide, uint32_t n,
-                      double abs_sum, X87 p, int mode, int* exact) {
-  if (n == 0) return 0;
+// doubles (every search through the double-double path). *exact is incremented when the replay ran.
+
+// 1 with *res = the first k at which the reference's walk stops (or n); 0 with *lo = the block to
+// examine.
+QHD int seg_locate(const RawX87* v, const SegCoarse* coarse, const uint32_t* guide, uint32_t n,
+                   double abs_sum, X87 p, int mode, int* exact, uint32_t* lo_out, uint32_t* res) {
+  *lo_out = 0;
+  *res = 0;
+  if (n == 0) return 1;
   if (mode == 1) {
     *exact += 1;
-    return seg_walk_exact(v, n, p);
+    *res = seg_walk_exact(v, n, p);
+    return 1;
   }
   const dd pd = x87_to_dd(p);
   const uint32_t nb = (n + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK;
-  const double unit = 1.0842021724855044e-19 * (fabs(pd.hi) + abs_sum);  // 2^-63 * scale
   // smallest block whose running maximum at its end reaches the pivot. (Binary on purpose: the
   // kernel is bound by L1 lookups of divergent addresses, 82 % of peak in ncu; 4-, 8- and
   // 16-ary searches with independent probes per level were 11 %, 25 % and 44 % slower.)
@@ -239,8 +282,8 @@ QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* 
       const uint32_t u = f >= (double)(G - 1) ? G - 1 : (uint32_t)f;
       const uint32_t L = guide[u ? u - 1 : 0], R = guide[u + 2 < G ? u + 2 : G];
       // the bracket holds iff block L - 1 does not reach the pivot and block R does (or R == nb)
-      const bool below = L == 0 || !dd_ge(coarse[L].m, pd);
-      const bool above = R >= nb || dd_ge(coarse[R + 1].m, pd);
+      const bool below = L == 0 || !dd_ge(ld16(&coarse[L].m), pd);
+      const bool above = R >= nb || dd_ge(ld16(&coarse[R + 1].m), pd);
       if (below && above && L <= R) {
         lo = L;
         hi = R < nb ? R : nb;
@@ -249,31 +292,48 @@ QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* 
   }
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (dd_ge(coarse[mid + 1].m, pd))
+    if (dd_ge(ld16(&coarse[mid + 1].m), pd))
       hi = mid;
     else
       lo = mid + 1;
   }
   if (lo == nb) {
     // no prefix reaches the pivot: certain only if the largest one misses it by more than B
+    const double unit = 1.0842021724855044e-19 * (fabs(pd.hi) + abs_sum);  // 2^-63 * scale
     const dd gap = dd_add(pd, dd_neg(coarse[nb].m));
-    if (gap.hi > (double)(n + 2) * unit) return n;
+    if (gap.hi > (double)(n + 2) * unit) {
+      *res = n;
+      return 1;
+    }
     *exact += 1;
-    return seg_walk_exact(v, n, p);
+    *res = seg_walk_exact(v, n, p);
+    return 1;
   }
-  const uint32_t k0 = lo * QB_SEG_BLOCK, k1 = k0 + QB_SEG_BLOCK < n ? k0 + QB_SEG_BLOCK : n;
-  // Quick pass over the block in plain doubles (top 53 bits of every element): its prefix sums
-  // are within 2^-49 * scale of the exact ones, so a hit that clears the pivot -- and a pivot
-  // that clears every earlier prefix -- by 2^-47 * scale is the exact walk's and, a fortiori
-  // (2^-47 >> n 2^-63), the reference's. All but ~1e-10 of the searches end here.
-  // The pass has ONE exit: with a `return` per element the threads of a warp reached the code
-  // after the search at up to eight different times and stayed apart to the end of the kernel
-  // (ncu, round 2: 16 threads per instruction after the first search, 9 after the second).
-  if (mode != 2) {
-    double x[QB_SEG_BLOCK];
+  *lo_out = lo;
+  return 0;
+}
+
+// The top 53 bits of the elements of block lo, zero past the end of the segment.
+QHD void seg_block_doubles(const RawX87* v, uint32_t n, uint32_t lo, double* x) {
+  const uint32_t k0 = lo * QB_SEG_BLOCK;
 #pragma unroll
-    for (int q = 0; q < QB_SEG_BLOCK; q++)  // independent loads first
-      x[q] = k0 + q < k1 ? x87_raw_to_double(v[k0 + q]) : 0.0;
+  for (int q = 0; q < QB_SEG_BLOCK; q++)  // independent loads
+    x[q] = k0 + q < n ? x87_raw_to_double(ld16(v + k0 + q)) : 0.0;
+}
+
+// Quick pass over block lo in plain doubles (x: seg_block_doubles): its prefix sums are within
+// 2^-49 * scale of the exact ones, so a hit that clears the pivot -- and a pivot that clears every
+// earlier prefix -- by 2^-47 * scale is the exact walk's and, a fortiori (2^-47 >> n 2^-63), the
+// reference's. All but ~1e-10 of the searches end here.
+// The pass has ONE exit: with a `return` per element the threads of a warp reached the code
+// after the search at up to eight different times and stayed apart to the end of the kernel
+// (ncu, round 2: 16 threads per instruction after the first search, 9 after the second).
+QHD uint32_t seg_decide(const double* x, const RawX87* v, const SegCoarse* coarse, uint32_t lo, uint32_t n,
+                        double abs_sum, X87 p, int mode, int* exact) {
+  const dd pd = x87_to_dd(p);
+  const double unit = 1.0842021724855044e-19 * (fabs(pd.hi) + abs_sum);  // 2^-63 * scale
+  const uint32_t k0 = lo * QB_SEG_BLOCK, k1 = k0 + QB_SEG_BLOCK < n ? k0 + QB_SEG_BLOCK : n;
+  if (mode != 2) {
     const double wide = 7.105427357601002e-15 * (fabs(pd.hi) + abs_sum);  // 2^-47 * scale
     double c = coarse[lo].c.hi, mprev = coarse[lo].m.hi;
     int hit = -1;
@@ -292,13 +352,25 @@ QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* 
   return seg_find_slow(v, coarse, lo, k0, k1, n, unit, p, pd, exact);
 }
 
+// First k at which the reference's walk stops, or n.
+QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* guide, uint32_t n,
+                      double abs_sum, X87 p, int mode, int* exact) {
+  uint32_t lo, res;
+  if (seg_locate(v, coarse, guide, n, abs_sum, p, mode, exact, &lo, &res)) return res;
+  double x[QB_SEG_BLOCK];
+#pragma unroll
+  for (int q = 0; q < QB_SEG_BLOCK; q++) x[q] = 0.0;
+  if (mode != 2) seg_block_doubles(v, n, lo, x);
+  return seg_decide(x, v, coarse, lo, n, abs_sum, p, mode, exact);
+}
+
 // |alpha| / 2^m for region j of an axis with coordinate k and dimension D, and fraction word w
 // (src/sample.cpp:42-61): alpha_min + (alpha_max - alpha_min) * (double)fraction, with
 // alpha_min/max = round(2^(|k| + j / D)) and fraction = (w mod 2^63) / 2^63 (src/random.c:137-156).
 QHD dd sample_axis(const SamplerView& s, const SamplerSlice& sl, int32_t k, uint32_t j, uint64_t w) {
   const int k_abs = k < 0 ? -k : k;
-  const dd xmin = grid_x(s.geo[sl.geo_off + j], k_abs, 1, s.m);
-  const dd xmax = grid_x(s.geo[sl.geo_off + j + 1], k_abs, 1, s.m);
+  const dd xmin = grid_x(ld16(s.geo + sl.geo_off + j), k_abs, 1, s.m);
+  const dd xmax = grid_x(ld16(s.geo + sl.geo_off + j + 1), k_abs, 1, s.m);
   const double f = (double)(w & 0x7fffffffffffffffull) * 1.0842021724855044e-19;  // RN to 53 bits, / 2^63
   const dd x = dd_add(xmin, dd_mul_d(dd_add(xmax, dd_neg(xmin)), f));
   return x;
@@ -306,24 +378,33 @@ QHD dd sample_axis(const SamplerView& s, const SamplerSlice& sl, int32_t k, uint
 
 // First half of a sample: the slice the reference's walk over the slice totals stops at
 // (src/distribution.cpp:359-409), or n_slices (out of bounds: the reference returns FALSE).
-QHD uint32_t sample_slice(const SamplerView& s, uint64_t w0, int mode, int* exact) {
+QHD X87 sample_slice_pivot(const SamplerView& s, uint64_t w0) {
   bool ok = true;
   X87 p = x87_pivot_inclusive(w0);
   if (s.scale_by_total) p = x87_mul(p, x87_load(&s.dist_total, &ok));
-  return seg_find(s.totals, s.totals_coarse, s.guide ? s.guide + s.totals_guide_off : nullptr, s.n_slices,
-                  s.totals_abs_sum, p, mode, exact);
+  return p;
+}
+QHD const uint32_t* sample_totals_guide(const SamplerView& s) {
+  return s.guide ? s.guide + s.totals_guide_off : nullptr;
+}
+QHD uint32_t sample_slice(const SamplerView& s, uint64_t w0, int mode, int* exact) {
+  return seg_find(s.totals, s.totals_coarse, sample_totals_guide(s), s.n_slices, s.totals_abs_sum,
+                  sample_slice_pivot(s, w0), mode, exact);
 }
 
 // Second half: the region inside slice i (src/distribution_slice.cpp:167-228) and the two axis
 // draws (src/sample.cpp:24-77). w: the sample's words (w[0] is not read again).
-QHD void sample_in_slice(const SamplerView& s, uint32_t i, const uint64_t* w, int mode, SampleOut* out) {
+QHD X87 sample_region_pivot(const SamplerView& s, uint32_t i, uint64_t w1) {
   bool ok = true;
+  return x87_mul(x87_pivot_inclusive(w1), x87_load16(s.totals + i, &ok));
+}
+QHD const uint32_t* sample_slice_guide(const SamplerView& s, const SamplerSlice& sl) {
+  return s.guide ? s.guide + sl.guide_off : nullptr;
+}
+// The sample once its cell c of slice i (= sl) is known.
+QHD void sample_finish(const SamplerView& s, const SamplerSlice& sl, uint32_t i, uint32_t c, const uint64_t* w,
+                       SampleOut* out) {
   out->slice = (int32_t)i;
-  const SamplerSlice sl = s.slices[i];
-  const X87 p2 = x87_mul(x87_pivot_inclusive(w[1]), x87_load(s.totals + i, &ok));
-  const uint32_t c = seg_find(s.cells + sl.cell_off, s.coarse + sl.coarse_off,
-                              s.guide ? s.guide + sl.guide_off : nullptr, sl.n_cells, sl.abs_sum, p2, mode,
-                              &out->exact);
   if (c >= sl.n_cells) {
     out->status = kSampleNoRegion;
     return;
@@ -345,6 +426,12 @@ QHD void sample_in_slice(const SamplerView& s, uint32_t i, const uint64_t* w, in
     out->x0 = sl.c0 < 0 ? -x.hi : x.hi;
   }
 }
+QHD void sample_in_slice(const SamplerView& s, uint32_t i, const uint64_t* w, int mode, SampleOut* out, int* exact) {
+  const SamplerSlice sl = s.slices[i];
+  const uint32_t c = seg_find(s.cells + sl.cell_off, s.coarse + sl.coarse_off, sample_slice_guide(s, sl),
+                              sl.n_cells, sl.abs_sum, sample_region_pivot(s, i, w[1]), mode, exact);
+  sample_finish(s, sl, i, c, w, out);
+}
 
 QHD void sample_out_clear(SampleOut* out) {
   out->sq0_hi = out->sq0_lo = out->sq1_hi = out->sq1_lo = 0.0;
@@ -358,9 +445,12 @@ QHD void sample_out_clear(SampleOut* out) {
 // pivot, region pivot, one fraction per axis).
 QHD void sample_one(const SamplerView& s, const uint64_t* w, int mode, SampleOut* out) {
   sample_out_clear(out);
-  const uint32_t i = sample_slice(s, w[0], mode, &out->exact);
-  if (i >= s.n_slices) return;  // status: out of bounds
-  sample_in_slice(s, i, w, mode, out);
+  // (a counter of its own: the address goes to an out-of-line function, and with &out->exact the
+  // whole result lived in local memory)
+  int exact = 0;
+  const uint32_t i = sample_slice(s, w[0], mode, &exact);
+  if (i < s.n_slices) sample_in_slice(s, i, w, mode, out, &exact);  // else: status out of bounds
+  out->exact = exact;
 }
 
 // Sum of the squares of the n samples of one estimate, in sample order (fixed => reproducible).
