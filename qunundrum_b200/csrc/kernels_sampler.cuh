@@ -20,6 +20,7 @@ namespace qb200 {
 
 struct SegDesc {
   const RawX87* vals;
+  double* vals_d;    // the elements as doubles (seg_block_doubles), or null
   SegCoarse* coarse;
   double* abs_out;
   uint32_t* guide;   // seg_guide_size(blocks) + 1 entries
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(256) k_seg_build(const SegDesc* __restrict__ s
   for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
     dd sum, maxp;
     double a;
-    seg_block_summary(s.vals, s.n, b, &sum, &maxp, &a, &ok);
+    seg_block_summary(s.vals, s.vals_d, s.n, b, &sum, &maxp, &a, &ok);
     s.coarse[b + 1].c = sum;
     s.coarse[b + 1].m = maxp;
     ab += a;
@@ -66,10 +67,11 @@ __global__ void __launch_bounds__(256) k_seg_build(const SegDesc* __restrict__ s
 //
 // Bound by look-ups in L1: every load of a warp touches 32 different lines (ncu, round 2: 0.84 tag
 // look-ups per cycle and SM). What helped: 16-byte loads (ld16, sampler.cuh; 44 -> 33 million
-// look-ups per 2^20 samples, 4.4 -> 6.5e9 samples/s). What did not: fetching the 32 blocks of a
+// look-ups per 2^20 samples, 4.4 -> 6.5e9 samples/s) and the elements of a block kept as doubles
+// (seg_block_doubles: 4 loads per block instead of 8, 7.6e9). What did not: fetching the 32 blocks of a
 // warp cooperatively (8 lanes x 16 bytes per block, values handed to their owners through shared
 // memory): a quarter fewer look-ups again, but every lane then waits for the slowest search of its
-// warp twice per sample -- 5.6e9 samples/s, removed (profiles/r02_sampler_cooperative_fetch.txt).
+// warp twice per sample -- 5.6e9 samples/s, removed (profiles/r02_sampler_lookups_ab.txt).
 __global__ void __launch_bounds__(128, QB_SAMPLE_MIN_CTAS)
 k_sample(SamplerView view, const uint64_t* __restrict__ words, const uint64_t* __restrict__ off, uint32_t n,
          uint64_t total, int force_exact, SampleOut* __restrict__ out) {

@@ -74,7 +74,7 @@ struct qb200_sampler {
   cudaStream_t stream = nullptr;
   uint64_t* launches = nullptr;
   SamplerView view;
-  Buf cells, coarse, slices, totals, geo, scratch, guide;
+  Buf cells, coarse, slices, totals, geo, scratch, guide, cells_d, totals_d;
   // per-call staging
   Buf d_words, d_off, d_out, d_sums, d_status;
   Buf h_sums, h_status, h_words, h_off, h_out;
@@ -165,6 +165,18 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
   if (int rc = s->totals.reserve((size_t)n_slices * sizeof(RawX87))) return rc;
   if (int rc = s->geo.reserve(geo.size() * sizeof(DD))) return rc;
   if (int rc = s->guide.reserve(guide_off * sizeof(uint32_t))) return rc;
+  // the elements once more as doubles, for the quick pass (one block of slack: seg_block_doubles
+  // reads whole blocks); QB200_SAMPLER_DOUBLES=0: not kept (A/B, tests)
+  const char* dbl_env = getenv("QB200_SAMPLER_DOUBLES");
+  const bool keep_doubles = !(dbl_env && *dbl_env == '0');
+  if (keep_doubles) {
+    if (int rc = s->cells_d.reserve((cell_off + QB_SEG_BLOCK) * sizeof(double))) return rc;
+    if (int rc = s->totals_d.reserve(((size_t)n_slices + QB_SEG_BLOCK) * sizeof(double))) return rc;
+    QS_CUDA(cudaMemsetAsync((char*)s->cells_d.p + cell_off * sizeof(double), 0, QB_SEG_BLOCK * sizeof(double),
+                            s->stream));
+    QS_CUDA(cudaMemsetAsync((char*)s->totals_d.p + (size_t)n_slices * sizeof(double), 0,
+                            QB_SEG_BLOCK * sizeof(double), s->stream));
+  }
   // scratch: segment descriptors, the totals' abs sum, the "bad value" flag
   const size_t seg_bytes = ((size_t)n_slices + 1) * sizeof(SegDesc);
   if (int rc = s->scratch.reserve(seg_bytes + 64)) return rc;
@@ -182,6 +194,7 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
   int* d_bad = (int*)((char*)s->scratch.p + seg_bytes + 8);
   for (uint32_t i = 0; i < n_slices; i++) {
     segs[i].vals = s->cells.as<RawX87>() + hs[i].cell_off;
+    segs[i].vals_d = keep_doubles ? s->cells_d.as<double>() + hs[i].cell_off : nullptr;
     segs[i].coarse = s->coarse.as<SegCoarse>() + hs[i].coarse_off;
     segs[i].abs_out = &(s->slices.as<SamplerSlice>()[i].abs_sum);
     segs[i].guide = s->guide.as<uint32_t>() + hs[i].guide_off;
@@ -189,6 +202,7 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
     segs[i].pad = 0;
   }
   segs[n_slices].vals = s->totals.as<RawX87>();
+  segs[n_slices].vals_d = keep_doubles ? s->totals_d.as<double>() : nullptr;
   segs[n_slices].coarse = s->coarse.as<SegCoarse>() + totals_coarse_off;
   segs[n_slices].abs_out = d_tot_abs;
   segs[n_slices].guide = s->guide.as<uint32_t>() + totals_guide_off;
@@ -213,6 +227,8 @@ int qb200_sampler_create(qb200_context* ctx, int dims, uint32_t m, uint32_t n_sl
   v.coarse = s->coarse.as<SegCoarse>();
   v.slices = s->slices.as<SamplerSlice>();
   v.totals = s->totals.as<RawX87>();
+  v.cells_d = keep_doubles ? s->cells_d.as<double>() : nullptr;
+  v.totals_d = keep_doubles ? s->totals_d.as<double>() : nullptr;
   v.totals_coarse = s->coarse.as<SegCoarse>() + totals_coarse_off;
   v.geo = s->geo.as<dd>();
   {

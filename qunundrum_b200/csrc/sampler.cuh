@@ -90,6 +90,8 @@ struct SamplerView {
   const SegCoarse* coarse;
   const SamplerSlice* slices;
   const RawX87* totals;            // the slices' total_probability, in walk order
+  const double* cells_d;           // the top 53 bits of every cell / total as a double (what the
+  const double* totals_d;          // quick pass reads: 8 instead of 16 bytes per element); may be null
   const SegCoarse* totals_coarse;
   const dd* geo;
   const uint32_t* guide;           // guide tables (seg_guide_*): the slices', then the totals'
@@ -143,12 +145,13 @@ QHD X87 x87_load(const RawX87* p, bool* ok) {
 
 // Summary of block b of a segment: its sum, the maximum of its own prefix sums (from 0), the
 // sum of magnitudes, and whether every element decodes.
-QHD void seg_block_summary(const RawX87* v, uint32_t n, uint32_t b, dd* sum, dd* maxp, double* abs_sum,
-                           bool* ok) {
+QHD void seg_block_summary(const RawX87* v, double* vd, uint32_t n, uint32_t b, dd* sum, dd* maxp,
+                           double* abs_sum, bool* ok) {
   dd c = make_dd(0.0, 0.0), mx = make_dd(-1e300, 0.0);
   double ab = 0.0;
   const uint32_t lo = b * QB_SEG_BLOCK, hi = lo + QB_SEG_BLOCK < n ? lo + QB_SEG_BLOCK : n;
   for (uint32_t k = lo; k < hi; k++) {
+    if (vd) vd[k] = x87_raw_to_double(v[k]);  // the copy the quick pass reads (seg_block_doubles)
     const dd x = x87_to_dd(x87_load(v + k, ok));
     c = dd_add(c, x);
     mx = dd_max(mx, c);
@@ -313,9 +316,21 @@ QHD int seg_locate(const RawX87* v, const SegCoarse* coarse, const uint32_t* gui
   return 0;
 }
 
-// The top 53 bits of the elements of block lo, zero past the end of the segment.
-QHD void seg_block_doubles(const RawX87* v, uint32_t n, uint32_t lo, double* x) {
+// The top 53 bits of the elements of block lo, zero past the end of the segment. vd (may be null):
+// the same values kept as doubles by seg_block_summary -- four 16-byte loads instead of eight:
+// 6.3 -> 7.6e9 samples/s on the bench distribution for half as much memory again. (The array
+// behind vd is readable for a whole block past the last element of the distribution.)
+QHD void seg_block_doubles(const RawX87* v, const double* vd, uint32_t n, uint32_t lo, double* x) {
   const uint32_t k0 = lo * QB_SEG_BLOCK;
+  if (vd && (((size_t)(vd + k0)) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < QB_SEG_BLOCK; q += 2) {
+      const dd pair = ld16(reinterpret_cast<const dd*>(vd + k0 + q));
+      x[q] = k0 + q < n ? pair.hi : 0.0;
+      x[q + 1] = k0 + q + 1 < n ? pair.lo : 0.0;
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < QB_SEG_BLOCK; q++)  // independent loads
     x[q] = k0 + q < n ? x87_raw_to_double(ld16(v + k0 + q)) : 0.0;
@@ -353,14 +368,14 @@ QHD uint32_t seg_decide(const double* x, const RawX87* v, const SegCoarse* coars
 }
 
 // First k at which the reference's walk stops, or n.
-QHD uint32_t seg_find(const RawX87* v, const SegCoarse* coarse, const uint32_t* guide, uint32_t n,
-                      double abs_sum, X87 p, int mode, int* exact) {
+QHD uint32_t seg_find(const RawX87* v, const double* vd, const SegCoarse* coarse, const uint32_t* guide,
+                      uint32_t n, double abs_sum, X87 p, int mode, int* exact) {
   uint32_t lo, res;
   if (seg_locate(v, coarse, guide, n, abs_sum, p, mode, exact, &lo, &res)) return res;
   double x[QB_SEG_BLOCK];
 #pragma unroll
   for (int q = 0; q < QB_SEG_BLOCK; q++) x[q] = 0.0;
-  if (mode != 2) seg_block_doubles(v, n, lo, x);
+  if (mode != 2) seg_block_doubles(v, vd, n, lo, x);
   return seg_decide(x, v, coarse, lo, n, abs_sum, p, mode, exact);
 }
 
@@ -388,7 +403,7 @@ QHD const uint32_t* sample_totals_guide(const SamplerView& s) {
   return s.guide ? s.guide + s.totals_guide_off : nullptr;
 }
 QHD uint32_t sample_slice(const SamplerView& s, uint64_t w0, int mode, int* exact) {
-  return seg_find(s.totals, s.totals_coarse, sample_totals_guide(s), s.n_slices, s.totals_abs_sum,
+  return seg_find(s.totals, s.totals_d, s.totals_coarse, sample_totals_guide(s), s.n_slices, s.totals_abs_sum,
                   sample_slice_pivot(s, w0), mode, exact);
 }
 
@@ -428,8 +443,9 @@ QHD void sample_finish(const SamplerView& s, const SamplerSlice& sl, uint32_t i,
 }
 QHD void sample_in_slice(const SamplerView& s, uint32_t i, const uint64_t* w, int mode, SampleOut* out, int* exact) {
   const SamplerSlice sl = s.slices[i];
-  const uint32_t c = seg_find(s.cells + sl.cell_off, s.coarse + sl.coarse_off, sample_slice_guide(s, sl),
-                              sl.n_cells, sl.abs_sum, sample_region_pivot(s, i, w[1]), mode, exact);
+  const uint32_t c = seg_find(s.cells + sl.cell_off, s.cells_d ? s.cells_d + sl.cell_off : nullptr,
+                              s.coarse + sl.coarse_off, sample_slice_guide(s, sl), sl.n_cells, sl.abs_sum,
+                              sample_region_pivot(s, i, w[1]), mode, exact);
   sample_finish(s, sl, i, c, w, out);
 }
 

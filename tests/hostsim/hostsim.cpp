@@ -498,20 +498,21 @@ struct HostSampler {
   std::vector<RawX87> cells, totals;
   std::vector<SegCoarse> coarse;
   std::vector<uint32_t> guide;
+  std::vector<double> cells_d, totals_d;
   std::vector<SamplerSlice> slices;
   std::vector<dd> geo;
   SamplerView view;
   bool bad = false;
 };
 
-static void build_segment(const RawX87* v, uint32_t n, SegCoarse* coarse, double* abs_out, bool* bad) {
+static void build_segment(const RawX87* v, double* vd, uint32_t n, SegCoarse* coarse, double* abs_out, bool* bad) {
   const uint32_t nb = (n + QB_SEG_BLOCK - 1) / QB_SEG_BLOCK;
   double ab = 0.0;
   bool ok = true;
   for (uint32_t b = 0; b < nb; b++) {
     dd sum, maxp;
     double a;
-    seg_block_summary(v, n, b, &sum, &maxp, &a, &ok);
+    seg_block_summary(v, vd, n, b, &sum, &maxp, &a, &ok);
     coarse[b + 1].c = sum;
     coarse[b + 1].m = maxp;
     ab += a;
@@ -563,11 +564,18 @@ void* hostsim_sampler_new(int dims, uint32_t m, uint32_t n_slices, const uint32_
   h->totals.resize(n_slices);
   memcpy(h->totals.data(), slice_total, (size_t)n_slices * 16);
   h->coarse.resize(coarse_off);
+  h->cells_d.assign(cell_off + QB_SEG_BLOCK, 0.0);
+  h->totals_d.assign((size_t)n_slices + QB_SEG_BLOCK, 0.0);
   for (uint32_t i = 0; i < n_slices; i++)
-    build_segment(h->cells.data() + h->slices[i].cell_off, h->slices[i].n_cells,
-                  h->coarse.data() + h->slices[i].coarse_off, &h->slices[i].abs_sum, &h->bad);
+    build_segment(h->cells.data() + h->slices[i].cell_off, h->cells_d.data() + h->slices[i].cell_off,
+                  h->slices[i].n_cells, h->coarse.data() + h->slices[i].coarse_off, &h->slices[i].abs_sum,
+                  &h->bad);
   SamplerView& v = h->view;
-  build_segment(h->totals.data(), n_slices, h->coarse.data() + tco, &v.totals_abs_sum, &h->bad);
+  build_segment(h->totals.data(), h->totals_d.data(), n_slices, h->coarse.data() + tco, &v.totals_abs_sum,
+                &h->bad);
+  const bool shadow = !(getenv("QB200_SAMPLER_DOUBLES") && getenv("QB200_SAMPLER_DOUBLES")[0] == '0');
+  v.cells_d = shadow ? h->cells_d.data() : nullptr;
+  v.totals_d = shadow ? h->totals_d.data() : nullptr;
   h->guide.resize(guide_off);
   for (uint32_t i = 0; i <= n_slices; i++) {   // the guide tables, as k_seg_build fills them
     const uint32_t n = i < n_slices ? h->slices[i].n_cells : n_slices;
