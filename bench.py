@@ -473,27 +473,29 @@ def tau_section(ctx, qb, torch, stream, h_cells, tp, coords, hbm_peak, cpu_basel
         ta, tb, ok, used = sampler.tau_estimate(n, count, h_words)
     wall = (time.perf_counter() - t0) / e2e_reps
     done = len(ta)
-    # algorithmic bytes per sample: two searches (ceil(log2(blocks)) coarse entries of 32 B and
-    # on average half a block of 8 x 16 B each), the words in, 64 B out
-    import math
+    # algorithmic bytes per sample of the search as it is now (sampler.cuh): per search two guide
+    # entries (8 B), the two checks of the bracket and ~3 steps inside it (16 B each), the walk
+    # state before the block (16 B) and the block's 8 elements as doubles; the slice record (48 B),
+    # its total (16 B), four geometry entries (16 B each), the words in, 64 B out
     seg_block = 8                                             # QB_SEG_BLOCK, sampler.cuh
-    blocks_s = math.ceil(len(dist.slices) / seg_block)
-    blocks_c = D * D // seg_block
-    bytes_per_sample = (math.ceil(math.log2(blocks_s)) + math.ceil(math.log2(blocks_c))) * 32 \
-        + 2 * (seg_block // 2) * 16 + wps * 8 + 64
+    bytes_per_sample = 2 * (8 + 2 * 16 + 3 * 16 + 16 + seg_block * 8) + 48 + 16 + 4 * 16 + wps * 8 + 64
     gbs = total * bytes_per_sample / (ms * 1e-3) / 1e9
     out = {
         "workload": (f"tau_estimate on the step's own distribution: {len(dist.slices)} slices "
                      f"({n_slices} computed + mirrored) x {D * D} cells = {sampler_cells(sampler)} cells "
-                     f"resident ({sampler_cells(sampler) * 16 / 1e9:.2f} GB x87 + 25 % coarse index); "
+                     f"resident ({sampler_cells(sampler) * 16 / 1e9:.2f} GB x87 + 25 % coarse index + 50 % "
+                     f"the same elements as doubles for the quick pass); "
                      f"{count} estimates of n = {n} samples per call"),
         "samples_per_call": total,
         "value": total / (ms * 1e-3), "unit": "samples/s", "ms": ms,
         "out_of_bounds_estimates": failed,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                      "traffic": None, "bytes_per_sample": bytes_per_sample, "kernel": "k_sample",
-                     "limiter": ("L1/TEX lookups of divergent addresses (every thread searches its own slice): l1tex "
-                                 "throughput 82 % of peak, DRAM 9 % (profiles/r01_sampler_ncu_full.txt)")},
+                     "limiter": ("latency of ~10 dependent loads of divergent addresses per sample (every thread "
+                                 "searches its own slice): issue active 41 %, long-scoreboard 9 cycles per "
+                                 "instruction, DRAM 15 % (profiles/r02_sampler_ncu_full.txt; the L1 look-ups that "
+                                 "bounded the round-1 kernel were halved by 16-byte loads and a copy of the "
+                                 "elements as doubles, profiles/r02_sampler_lookups_ab.txt)")},
         "e2e": {"value": done * n / wall, "unit": "samples/s", "h2d_bytes_per_step": int(used * 8 + done * 8),
                 "d2h_bytes_per_step": int(done * 36), "ms": wall * 1e3,
                 "api": "qb200_sampler_tau_estimate (host words in, long double taus out)"},
@@ -610,10 +612,10 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
            "roofline": {"bound": "integer issue", "imad_per_sample": mads,
                         "achieved": mads * n / ms * 1e3 / 1e12, "unit": "T multiply-add/s",
                         "kernel": "k_diagk",
-                        "limiter": "instruction issue: ~3.2 thread instructions per multiply-add in the "
-                                   "four-column products, issue slots 51 % active (dependent carry chains, L1 "
-                                   "latency, 24 warps/SM), LSU 28 %, DRAM 9 % "
-                                   "(profiles/r01_diagk_ncu_full.txt)"}}
+                        "limiter": "instruction issue: ~2.8 thread instructions per multiply-add in the "
+                                   "four-column products, issue slots 49 % active (long scoreboard 5, wait 2.6, "
+                                   "math pipe 2.1 cycles per instruction; 32 warps/SM), LSU 34 %, DRAM 14 % "
+                                   "(profiles/r02_diagk_ncu_full.txt, r02_diagk_variants_ab.txt)"}}
     t0 = time.perf_counter()
     ks, x, dl, st = S.sample(J, eta, piv, delta_bound, want_k=False)
     t1 = time.perf_counter()
