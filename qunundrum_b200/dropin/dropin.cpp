@@ -37,13 +37,16 @@
 // secret: they are what the reference's own enumerators list for these parameters
 // (src/distribution_enumerator.cpp, linear_..., diagonal_...). On the first call for a set of
 // parameters the drop-in therefore integrates the WHOLE list in one C-ABI call (thousands of
-// slices per launch) into a pinned host cache and serves this and every later call from it; cells
+// slices per launch) into a host cache (pageable: pinning 440 MB costs more than the copy saves) and
+// serves this and every later call from it; cells
 // do not depend on the batch they are computed in (bit-identical, tested), so the caller cannot
 // tell. The two-dimensional client's dimension heuristic (:1222-1294) re-computes some slices at
 // 512 / 1024: the first call at a new dimension integrates, in one batch, every coordinate the
 // heuristic can send there (its geometric conditions; where the lower-dimension total is already
 // cached, its thresholds with a decade of slack). A coordinate outside the speculated set is
-// simply computed on its own. QB200_PREFETCH=0 restores one slice per call.
+// simply computed on its own. QB200_PREFETCH=0 restores one slice per call. (The six functions are
+// called from the client's main thread only -- the reference's thread pool runs the server's
+// exports, src/main_generate_distribution.cpp:1070 -- and are not re-entrant.)
 #include "common.h"
 #include "diagonal_distribution_enumerator.h"
 #include "diagonal_distribution_slice.h"
