@@ -596,10 +596,15 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
     status = out[:, 3].view(np.int64) & 0xffffffff
     delta = out[:, 2].view(np.int64)
     k = (m + 31) // 32
-    # multiply-adds of the products of diagk.cuh: r j, d s, two Barrett divisions (q1 mu from
-    # column k - 1, q3 r below column k + 1)
-    barrett = ((k + 1) * (k + 2) - k * (k - 1) // 2) + (k * (k + 1) // 2 + k)
-    mads = k * wj + k * k + 2 * barrett
+    # multiply-adds of the products of diagk.cuh on the common path: r j from three guard columns below
+    # 2^(m+sigma), and the columns fl - 8 .. fl + wl - 1 of s psi (fl = k + 4 fractional limbs of
+    # psi = 2^l d / r in fixed point, wl = limbs of k)
+    wl = (l + 31) // 32
+    cs = (m + sigma) >> 5
+    skipped = sum(min(c_ + 1, k, wj) for c_ in range(max(0, cs - 4)))   # columns of r j below the guards
+    fl, npsi = k + 4, k + 4 + wl
+    spsi = sum(min(c_, k - 1) - max(0, c_ - npsi + 1) + 1 for c_ in range(fl - 8, fl + wl))
+    mads = k * wj - skipped + spsi
     res = {"workload": f"sample_k_from_diagonal_j_eta_pivot, m={m} sigma={sigma} l={l}: {n} uniform "
                        f"(j, eta, pivot), delta_bound={delta_bound}",
            "samples_per_call": n, "value": n / ms * 1e3, "unit": "samples/s", "ms": ms,
@@ -613,9 +618,10 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
                         "achieved": mads * n / ms * 1e3 / 1e12, "unit": "T multiply-add/s",
                         "kernel": "k_diagk",
                         "limiter": "instruction issue: ~2.8 thread instructions per multiply-add in the "
-                                   "four-column products, issue slots 49 % active (long scoreboard 5, wait 2.6, "
-                                   "math pipe 2.1 cycles per instruction; 32 warps/SM), LSU 34 %, DRAM 14 % "
-                                   "(profiles/r02_diagk_ncu_full.txt, r02_diagk_variants_ab.txt)"}}
+                                   "four-column products, issue slots 49 % active (long scoreboard 3.9, wait "
+                                   "2.7, math pipe 2.4 cycles per instruction; 32 warps/SM), LSU 36 %, DRAM 10 % "
+                                   "(profiles/r02_diagk_ncu_full.txt, r02_diagk_variants_ab.txt; round 1 "
+                                   "needed 17,092 multiply-adds per sample at m = 2048)"}}
     t0 = time.perf_counter()
     ks, x, dl, st = S.sample(J, eta, piv, delta_bound, want_k=False)
     t1 = time.perf_counter()

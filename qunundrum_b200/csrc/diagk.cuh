@@ -9,7 +9,8 @@
 // for k = k0, k0 + 1, k0 - 1, ... and subtracts h(phi) = (1 - cos(2^l phi)) / (2^2l (1 - cos phi))
 // from the pivot until it is used up. With r j = alpha_r + q 2^(m+sigma) (q an integer) the term
 // is (d / r) 2^(m+sigma) (q + eta) EXACTLY, so everything the walk needs is the fraction
-//     2^l d (q + eta) / r mod 2^l = Qv + w2 / r,       w = d (q + eta) mod r, (Qv, w2) = divmod(2^l w, r)
+//     2^l d (q + eta) / r mod 2^l = Qv + w2 / r,       s = (q + eta) mod r,
+//     Qv = (s D' + floor(s rho / r)) mod 2^l, w2 = s rho mod r   with 2^l d = D' r + rho (host constants)
 // i.e. integer arithmetic on m-bit numbers: k0 = -(Qv + c) mod 2^l with c = [2 w2 >= r],
 // t = w2 / r - c in [-1/2, 1/2), alpha_phi = 2^(m+sigma-l) (t + delta) and
 //     h = sin^2(pi t) / (2^l sin(pi (t + delta) / 2^l))^2
@@ -20,9 +21,9 @@
 // matches the reference bit for bit (a pivot used up within 2^-100 of a step, which only the
 // reference's own rounding of h to 64 bits could decide, does not occur).
 //
-// The multi-limb part: one product r j, one product d s, Barrett reductions modulo r with a
-// host-prepared reciprocal; 32-bit limbs, product scanning with 96-bit column accumulators, four
-// columns at a time (mul_columns).
+// The multi-limb part: the products r j and s rho, one Barrett division by r with a host-prepared
+// reciprocal, the low l bits of s D' when k itself is wanted; 32-bit limbs, product scanning with
+// 96-bit column accumulators, four columns at a time (mul_columns).
 // Operands that are the same for every sample (r, d, mu) are read through `c`; per-sample
 // operands live in caller-provided arrays with a stride (1 on the host; on the device the samples
 // of a CTA are interleaved so that the threads of a warp read consecutive words).
@@ -34,6 +35,9 @@
 
 namespace qb200 {
 
+// Zero limbs the constant operands carry below index 0 and above their last limb (mul_columns).
+#define QB_DIAGK_PAD 3
+
 struct DiagKConst {
   uint32_t m, sigma, l;
   uint32_t n;        // m + sigma
@@ -44,9 +48,21 @@ struct DiagKConst {
   const uint32_t* r;   // k limbs
   const uint32_t* d;   // k limbs (d < r)
   const uint32_t* mu;  // k + 2 limbs: floor(2^(64 k) / r)
+  const uint32_t* rho; // k limbs: 2^l d mod r
+  const uint32_t* dq;  // wl limbs: floor(2^l d / r)
+  const uint32_t* psi; // k + 4 + wl limbs: floor(2^(32 (k + 4)) 2^l d / r)
   dd r_top;            // the top four limbs of r as a number (limb k - 4 has weight 1)
   int force_exact;     // test switch: the exact walk only (diagk_walk)
+  int full_product;    // test switch (QB200_DIAGK_FULL_PRODUCT=1): r j without the skipped columns
+  int exact_fraction;  // test switch (QB200_DIAGK_EXACT_FRACTION=1): diagk_fraction_exact for every sample
 };
+
+// Words of the constants r, d, mu, rho, dq, psi with their zero limbs, in this order (the kernel's
+// shared-memory copy).
+QHD uint32_t diagk_const_words(const DiagKConst& c) {
+  return 3 * (c.k + 2 * QB_DIAGK_PAD) + (c.k + 2 + 2 * QB_DIAGK_PAD) + (c.wl + 2 * QB_DIAGK_PAD) +
+         (c.k + 4 + c.wl + 2 * QB_DIAGK_PAD);
+}
 
 // Scratch words one sample needs (times the stride).
 QHD uint32_t diagk_scratch_limbs(uint32_t k) { return (2 * k + 2) + (k + 3) + (k + 2) + (k + 2); }
@@ -264,9 +280,6 @@ QHD void acc_add(Acc96& a, const Acc96& b) {
   a.hi += b.hi + ((a.lo < b.lo) ? 1u : 0u);
 }
 #endif
-
-// Zero limbs the constant operands (r, d, mu) carry below index 0 and above their last limb.
-#define QB_DIAGK_PAD 3
 
 // Columns [first, last] of the product U V (U: nu limbs at stride SU, V: nv limbs at stride SV;
 // column c = sum of U[a] V[b] over a + b = c, plus the carry of the columns before): the limbs of
@@ -570,6 +583,109 @@ QHD int diagk_walk(uint32_t l, dd t, X87 pivot, uint64_t delta_bound, int force_
   return diagk_walk_exact(l, t, S, pivot, delta_bound, delta_out, x_out);
 }
 
+// (Qv, t, c) with Qv + t + c = 2^l d s / r mod 2^l, exactly: Qv to k_out (if wanted), t = w2 / r - c,
+// c = [2 w2 >= r], for s in [0, r) in Sq. 2^l d = D' r + rho (host constants: D' = floor(2^l d / r)
+// < 2^l, rho < r), so 2^l d s = (s D' + floor(s rho / r)) r + (s rho mod r): one full product
+// s rho, one Barrett division, and -- only if k is wanted -- the low l bits of s D'. (Round 1
+// formed w = d s mod r and then divmod(2^l w, r), 32 k bits of the shift at a time: two Barrett
+// divisions and more for l > 32 k. The quotients differ by a multiple of 2^l.)
+// This is the path of the few samples diagk_fraction_fixed_point leaves open.
+template <int S>
+QHD_NOINLINE void diagk_fraction_exact(const DiagKConst& c, const uint32_t* Sq, uint32_t* A, uint32_t* Q,
+                                       uint32_t* W, uint32_t* k_out, dd* t_out, bool* cflag_out) {
+  const uint32_t k = c.k;
+  Acc96 acc;
+  acc_zero(acc);
+  acc = mul_columns<S, 1, S>(Sq, k, c.rho, k, 0, 2 * k - 1, 0, A, acc);
+  diagk_barrett<S>(c, A, Q, W);  // Q = floor(s rho / r) < r, W = w2
+  if (k_out) {
+    acc_zero(acc);
+    acc = mul_columns<S, 1, S>(Sq, k, c.dq, c.wl, 0, c.wl - 1, 0, k_out, acc);  // columns past l bits: dropped
+    uint32_t carry = 0;
+    for (uint32_t i = 0; i < c.wl; i++) {
+      const uint64_t v = (uint64_t)QB_L(k_out, i) + (i < k ? QB_L(Q, i) : 0u) + carry;
+      QB_L(k_out, i) = (uint32_t)v;
+      carry = (uint32_t)(v >> 32);
+    }  // (bits above l: masked in diagk_finish)
+  }
+  // ---- t = w2 / r - c ----
+  // 2 w2 >= r  <=>  w2 >= r - w2: form r - w2 in A and compare
+  uint32_t borrow = 0;
+  for (uint32_t i = 0; i < k; i++) {
+    const uint64_t v = (uint64_t)c.r[i] - QB_L(W, i) - borrow;
+    QB_L(A, i) = (uint32_t)v;
+    borrow = (uint32_t)(v >> 63);
+  }
+  bool cflag = true;  // w2 >= r - w2
+  for (uint32_t i = k; i-- > 0;) {
+    const uint32_t a = QB_L(W, i), b = QB_L(A, i);
+    if (a != b) {
+      cflag = a > b;
+      break;
+    }
+  }
+  const uint32_t* N = cflag ? A : W;
+  int top = -1;
+  for (uint32_t i = k; i-- > 0;) {
+    if (QB_L(N, i)) {
+      top = (int)i;
+      break;
+    }
+  }
+  dd t = make_dd(0.0, 0.0);
+  if (top >= 0) {
+    const int e = 32 * (top - (int)k + 1);
+    if (e >= -960) {
+      t = dd_div(limbs_top_dd<S>(N, (uint32_t)top), c.r_top);
+      t = dd_mul_pow2(t, pow2i(e));
+      if (cflag) t = dd_neg(t);
+    }
+  }
+  *t_out = t;
+  *cflag_out = cflag;
+}
+
+// The same from ONE truncated product, for all but ~2^-31 of the samples. psi = floor(2^(32 fl)
+// 2^l d / r) is 2^l d / r in fixed point with fl = k + 4 fractional limbs (error < 2^(-32 fl)), so
+// s psi / 2^(32 fl) misses 2^l d s / r by less than 2^-128: its integer part is Qv + c's carrier,
+// its four leading fractional limbs F' give the fraction F = w2 / r with F' <= F < F' + 2^-127.
+// Computed: the columns fl - 8 .. fl - 1 of s psi (four guard columns as for r j, four fractional
+// limbs) and, if k is wanted, the wl columns of the integer part. Returns false -- nothing decided,
+// k_out untouched -- when the guard, the integer part (F' within 2^-127 of 1), c (F' within 2^-127
+// of 1/2) or the relative accuracy of t (|t| < 2^-31: t must be good to 2^-96 of itself) is in doubt.
+template <int S>
+QHD bool diagk_fraction_fixed_point(const DiagKConst& c, const uint32_t* Sq, uint32_t* A, uint32_t* k_out,
+                                    dd* t_out, bool* cflag_out) {
+  const uint32_t k = c.k, fl = c.k + 4, np = fl + c.wl;
+  if (c.exact_fraction || fl < 8) return false;  // (r of fewer than four limbs: the exact path)
+  Acc96 acc;
+  acc_zero(acc);
+  acc = mul_columns<S, 1, S>(Sq, k, c.psi, np, fl - 8, fl - 1, fl - 8, A, acc);  // carry: into column fl
+  if (QB_L(A, 3) == 0xffffffffu) return false;  // the skipped columns' carry may pass the guards
+  const uint32_t f0 = QB_L(A, 4), f1 = QB_L(A, 5), f2 = QB_L(A, 6), f3 = QB_L(A, 7);  // f3: leading
+  const bool run = f2 == 0xffffffffu && f1 == 0xffffffffu && f0 >= 0xfffffffeu;
+  if (run && (f3 == 0xffffffffu || f3 == 0x7fffffffu)) return false;  // F' within 2^-127 of 1 or of 1/2
+  const bool cflag = (f3 >> 31) != 0;
+  // |t| 2^128 = F' or 2^128 - F' as an integer, then as a double-double
+  uint32_t n[4] = {f0, f1, f2, f3};
+  if (cflag) {
+    uint32_t one = 1;
+    for (int i = 0; i < 4; i++) {
+      const uint64_t v = (uint64_t)(~n[i]) + one;
+      n[i] = (uint32_t)v;
+      one = (uint32_t)(v >> 32);
+    }
+  }
+  dd t = limbs_top_dd<1>(n, 3);
+  t = dd_mul_pow2(t, 2.938735877055718769921841343055614194546e-39);  // 2^-128
+  if (!(t.hi >= 4.656612873077392578125e-10)) return false;  // |t| < 2^-31 (or zero)
+  if (cflag) t = dd_neg(t);
+  if (k_out) acc = mul_columns<S, 1, S>(Sq, k, c.psi, np, fl, fl + c.wl - 1, fl, k_out, acc);
+  *t_out = t;
+  *cflag_out = cflag;
+  return true;
+}
+
 struct DiagKFraction {
   dd t;        // w2 / r - c
   bool cflag;  // c = [2 w2 >= r]
@@ -590,11 +706,22 @@ QHD void diagk_fraction(const DiagKConst& c, const uint32_t* j, int32_t eta, uin
   const uint32_t cs = c.n >> 5, sh = c.n & 31;
   Acc96 acc;
   acc_zero(acc);
-  // Z = r j: the columns from cs - 1 on go to A (free here), then to Sq
+  // Z = r j: only the columns from cs - 1 on are needed (they go to A, free here, then to Sq). The
+  // product therefore starts three columns further down, with no carry from the columns it skips:
+  // that carry is below k 2^32, so it can reach past the three guard columns only if the third one
+  // comes out as 0xffffffff (one sample in 2^32) -- then the product is formed in full.
   const uint32_t ncol = k + c.wj;
-  acc = mul_columns<S, 1, S>(j, c.wj, c.r, k, 0, ncol - 1, cs - 1, A, acc);
-  const uint32_t below = QB_L(A, 0);  // column cs - 1
-  for (uint32_t i = 0; i + cs < ncol; i++) QB_L(Sq, i) = QB_L(A, i + 1);
+  const uint32_t zs = cs >= 2 ? cs - 2 : cs - 1;          // first column stored: the last guard (or cs - 1)
+  uint32_t first = (zs == cs - 2 && zs >= 2 && !c.full_product) ? zs - 2 : 0u;
+  for (;;) {
+    acc_zero(acc);
+    acc = mul_columns<S, 1, S>(j, c.wj, c.r, k, first, ncol - 1, zs, A, acc);
+    if (first == 0 || QB_L(A, 0) != 0xffffffffu) break;
+    first = 0;
+  }
+  const uint32_t* Az = &QB_L(A, cs - 1 - zs);  // Az[i]: column cs - 1 + i
+  const uint32_t below = QB_L(Az, 0);
+  for (uint32_t i = 0; i + cs < ncol; i++) QB_L(Sq, i) = QB_L(Az, i + 1);
   const uint32_t ns = ncol - cs;  // <= k + 1 limbs hold Z >> (32 cs)
   for (uint32_t i = ns; i < k + 2; i++) QB_L(Sq, i) = 0;
   uint32_t half_bit;
@@ -643,63 +770,10 @@ QHD void diagk_fraction(const DiagKConst& c, const uint32_t* j, int32_t eta, uin
       borrow = (uint32_t)(v >> 63);
     }
   }
-  // ---- w = d s mod r ----
-  acc_zero(acc);
-  acc = mul_columns<S, 1, S>(Sq, k, c.d, k, 0, 2 * k - 1, 0, A, acc);
-  diagk_barrett<S>(c, A, Q, W);
-  // ---- (Qv, w2) = divmod(2^l w, r), at most 32 k bits of the shift at a time ----
-  const uint32_t chunk = 32 * k;
-  const uint32_t nch = (c.l + chunk - 1) / chunk;
-  if (k_out)
-    for (uint32_t i = 0; i < c.wl; i++) QB_L(k_out, i) = 0;
-  for (uint32_t ci = 0; ci < nch; ci++) {
-    const uint32_t bits = ci == 0 ? c.l - chunk * (nch - 1) : chunk;
-    const uint32_t ls = bits >> 5, bs = bits & 31;
-    for (uint32_t i = 0; i < 2 * k; i++) {
-      uint32_t v = 0;
-      if (i >= ls && i - ls < k) v = QB_L(W, i - ls) << bs;
-      if (bs && i >= ls + 1 && i - ls - 1 < k) v |= QB_L(W, i - ls - 1) >> (32 - bs);
-      QB_L(A, i) = v;
-    }
-    diagk_barrett<S>(c, A, Q, W);
-    if (k_out) {
-      const uint32_t off = k * (nch - 1 - ci), nq = (bits + 31) >> 5;
-      for (uint32_t i = 0; i < nq && off + i < c.wl; i++) QB_L(k_out, off + i) = QB_L(Q, i);
-    }
-  }
-  // ---- t = w2 / r - c ----
-  // 2 w2 >= r  <=>  w2 >= r - w2: form r - w2 in A and compare
-  uint32_t borrow = 0;
-  for (uint32_t i = 0; i < k; i++) {
-    const uint64_t v = (uint64_t)c.r[i] - QB_L(W, i) - borrow;
-    QB_L(A, i) = (uint32_t)v;
-    borrow = (uint32_t)(v >> 63);
-  }
-  bool cflag = true;  // w2 >= r - w2
-  for (uint32_t i = k; i-- > 0;) {
-    const uint32_t a = QB_L(W, i), b = QB_L(A, i);
-    if (a != b) {
-      cflag = a > b;
-      break;
-    }
-  }
-  const uint32_t* N = cflag ? A : W;
-  int top = -1;
-  for (uint32_t i = k; i-- > 0;) {
-    if (QB_L(N, i)) {
-      top = (int)i;
-      break;
-    }
-  }
+  // ---- Qv + t + c = 2^l d s / r mod 2^l ----
   dd t = make_dd(0.0, 0.0);
-  if (top >= 0) {
-    const int e = 32 * (top - (int)k + 1);
-    if (e >= -960) {
-      t = dd_div(limbs_top_dd<S>(N, (uint32_t)top), c.r_top);
-      t = dd_mul_pow2(t, pow2i(e));
-      if (cflag) t = dd_neg(t);
-    }
-  }
+  bool cflag = false;
+  if (!diagk_fraction_fixed_point<S>(c, Sq, A, k_out, &t, &cflag)) diagk_fraction_exact<S>(c, Sq, A, Q, W, k_out, &t, &cflag);
   f->t = t;
   f->cflag = cflag;
   f->whole = whole;

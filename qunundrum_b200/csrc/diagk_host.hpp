@@ -1,11 +1,13 @@
 // diagk_host.hpp -- per-distribution constants of the diagonal k sampler (no CUDA in this file).
 //
 // Once per (m, sigma, l, d, r): the limbs of r and d, the Barrett reciprocal
-// mu = floor(2^(64 k) / r) and the top of r as a double-double (diagk.cuh). Shared by the CUDA
+// mu = floor(2^(64 k) / r), quotient and remainder of 2^l d by r, 2^l d / r in fixed point, and
+// the top of r as a double-double (diagk.cuh). Shared by the CUDA
 // library (qb200_diagk.cu) and the test-only CPU twin of tests/hostsim.
 #pragma once
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -15,7 +17,7 @@
 namespace qb200 {
 
 struct DiagKHost {
-  std::vector<uint32_t> r, d, mu;  // QB_DIAGK_PAD zero limbs, the number, QB_DIAGK_PAD zero limbs
+  std::vector<uint32_t> r, d, mu, rho, dq, psi;  // QB_DIAGK_PAD zero limbs, the number, QB_DIAGK_PAD zero limbs
   DiagKConst c;
 };
 
@@ -52,6 +54,14 @@ inline int diagk_prepare(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* 
   BigUInt q, rem;
   BigUInt::divmod(BigUInt::pow2(64ull * k), r, q, rem);
   h->mu = limbs32_padded(q, k + 2);
+  const uint32_t wl = (l + 31) / 32;
+  BigUInt dq, rho;
+  BigUInt::divmod(d.shl(l), r, dq, rho);  // 2^l d = dq r + rho
+  h->rho = limbs32_padded(rho, k);
+  h->dq = limbs32_padded(dq, wl);
+  BigUInt psi, psi_rem;
+  BigUInt::divmod(d.shl((size_t)l + 32 * (size_t)(k + 4)), r, psi, psi_rem);  // 2^l d / r, k + 4 fractional limbs
+  h->psi = limbs32_padded(psi, k + 4 + wl);
   DiagKConst& c = h->c;
   c.m = m;
   c.sigma = sigma;
@@ -63,8 +73,17 @@ inline int diagk_prepare(uint32_t m, uint32_t sigma, uint32_t l, const uint8_t* 
   c.r = h->r.data() + QB_DIAGK_PAD;
   c.d = h->d.data() + QB_DIAGK_PAD;
   c.mu = h->mu.data() + QB_DIAGK_PAD;
+  c.rho = h->rho.data() + QB_DIAGK_PAD;
+  c.dq = h->dq.data() + QB_DIAGK_PAD;
+  c.psi = h->psi.data() + QB_DIAGK_PAD;
   c.r_top = limbs_top_dd<1>(c.r, k - 1);
   c.force_exact = 0;
+  {
+    const char* fp = getenv("QB200_DIAGK_FULL_PRODUCT");
+    c.full_product = (fp && *fp == '1') ? 1 : 0;
+    const char* ef = getenv("QB200_DIAGK_EXACT_FRACTION");
+    c.exact_fraction = (ef && *ef == '1') ? 1 : 0;
+  }
   return 0;
 }
 

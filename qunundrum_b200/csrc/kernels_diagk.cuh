@@ -201,14 +201,25 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA, QB_DIAGK_MIN_CTAS) k_diagk(DiagK
                                                 DiagKOut* __restrict__ out) {
   extern __shared__ uint32_t sh[];
   const uint32_t k = c.k;
-  // r, d, mu with their zero limbs: contiguous in global memory (qb200_diagk_create), c.r the first
-  const uint32_t words = 3 * k + 2 + 6 * QB_DIAGK_PAD;
+  // r, d, mu, rho, dq, psi with their zero limbs: contiguous in global memory (qb200_diagk_create), c.r the first
+  const uint32_t words = diagk_const_words(c);
   const uint32_t* src = c.r - QB_DIAGK_PAD;
   for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sh[i] = src[i];
   __syncthreads();
-  c.r = sh + QB_DIAGK_PAD;
-  c.d = sh + (k + 2 * QB_DIAGK_PAD) + QB_DIAGK_PAD;
-  c.mu = sh + 2 * (k + 2 * QB_DIAGK_PAD) + QB_DIAGK_PAD;
+  {
+    uint32_t at = QB_DIAGK_PAD;
+    c.r = sh + at;
+    at += k + 2 * QB_DIAGK_PAD;
+    c.d = sh + at;
+    at += k + 2 * QB_DIAGK_PAD;
+    c.mu = sh + at;
+    at += k + 2 + 2 * QB_DIAGK_PAD;
+    c.rho = sh + at;
+    at += k + 2 * QB_DIAGK_PAD;
+    c.dq = sh + at;
+    at += c.wl + 2 * QB_DIAGK_PAD;
+    c.psi = sh + at;
+  }
   const uint32_t n_tiles = (B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA;
   uint32_t* mine = scratch + (size_t)blockIdx.x * QB_DIAGK_CTA * diagk_scratch_limbs(k);
   for (uint32_t tb = blockIdx.x; tb < n_tiles; tb += gridDim.x)

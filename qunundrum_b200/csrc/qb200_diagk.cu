@@ -91,18 +91,29 @@ int qb200_diagk_create(qb200_context* ctx, const qb200_params* params, qb200_dia
   s->stream = cv.stream;
   s->launches = cv.launches;
   const uint32_t k = s->host.c.k;
-  // r, d, mu one after the other, each with its zero limbs (diagk_host.hpp); the kernel stages the
-  // same 3 k + 2 + 6 QB_DIAGK_PAD words in shared memory
-  const size_t nr = s->host.r.size(), nd = s->host.d.size(), nmu = s->host.mu.size();
-  if (s->consts.reserve((nr + nd + nmu) * 4)) return -100;
+  // r, d, mu, rho, dq, psi one after the other, each with its zero limbs (diagk_host.hpp); the kernel
+  // stages the same words in shared memory (diagk_const_words)
+  const std::vector<uint32_t>* parts[6] = {&s->host.r,   &s->host.d,  &s->host.mu,
+                                           &s->host.rho, &s->host.dq, &s->host.psi};
+  size_t total_words = 0;
+  for (int i = 0; i < 6; i++) total_words += parts[i]->size();
+  if (total_words != diagk_const_words(s->host.c)) return set_error(-100, "diagonal k sampler: constant layout");
+  if (s->consts.reserve(total_words * 4)) return -100;
   uint32_t* c = s->consts.as<uint32_t>();
-  QD_CUDA(cudaMemcpy(c, s->host.r.data(), nr * 4, cudaMemcpyHostToDevice));
-  QD_CUDA(cudaMemcpy(c + nr, s->host.d.data(), nd * 4, cudaMemcpyHostToDevice));
-  QD_CUDA(cudaMemcpy(c + nr + nd, s->host.mu.data(), nmu * 4, cudaMemcpyHostToDevice));
+  size_t at = 0;
+  const uint32_t* dev_ptr[6];
+  for (int i = 0; i < 6; i++) {
+    QD_CUDA(cudaMemcpy(c + at, parts[i]->data(), parts[i]->size() * 4, cudaMemcpyHostToDevice));
+    dev_ptr[i] = c + at + QB_DIAGK_PAD;
+    at += parts[i]->size();
+  }
   s->dev = s->host.c;
-  s->dev.r = c + QB_DIAGK_PAD;
-  s->dev.d = c + nr + QB_DIAGK_PAD;
-  s->dev.mu = c + nr + nd + QB_DIAGK_PAD;
+  s->dev.r = dev_ptr[0];
+  s->dev.d = dev_ptr[1];
+  s->dev.mu = dev_ptr[2];
+  s->dev.rho = dev_ptr[3];
+  s->dev.dq = dev_ptr[4];
+  s->dev.psi = dev_ptr[5];
   s->chunk = pick_chunk(s.get(), cv.sm_count);
   *out = s.release();
   return 0;
@@ -130,7 +141,7 @@ static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const i
   const DiagKConst& c = s->host.c;
   const size_t scr = diagk_scratch_limbs(c.k);
   const size_t Bp = ((size_t)B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA * QB_DIAGK_CTA;  // whole tiles
-  const size_t shmem = (size_t)(3 * c.k + 2 + 6 * QB_DIAGK_PAD) * 4;
+  const size_t shmem = (size_t)diagk_const_words(c) * 4;
   // one CTA (and one scratch area) per tile: a persistent wave with per-CTA scratch was measured
   // and is slower (kernels_diagk.cuh)
   const uint32_t grid = (uint32_t)(Bp / QB_DIAGK_CTA);

@@ -369,6 +369,88 @@ def test_twin_integer_part_on_odd_shapes():
     assert checked == 1600
 
 
+def test_twin_skipped_columns_of_r_j():
+    """The product r j starts three guard columns below the first column that is needed and is
+    formed in full when the third guard comes out as 0xffffffff (diagk_fraction). Both paths against
+    the exact integers: random inputs with and without the switch that disables the short cut, and
+    inputs CONSTRUCTED so that the guard is all ones (one sample in 2^32 otherwise)."""
+    import os
+    import random
+    prng = random.Random(4242)
+    m, sigma, l = 256, 0, 256
+    n = m + sigma
+    first = (n >> 5) - 4                       # first column of the shortened product
+    cases = []
+    for trial in range(12):
+        r = (1 << (m - 1)) + prng.randrange(1 << (m - 1))
+        j0 = prng.randrange(1 << 32) | 1
+        if trial < 8:
+            # j = j0 (one limb): the partial product is j0 * (r >> 32 first); make its third limb all ones
+            target = (0xFFFFFFFF << 64) | prng.randrange(1 << 64)
+            X = (target * pow(j0, -1, 1 << 96)) % (1 << 96)
+            mask = ((1 << 96) - 1) << (32 * first)
+            r = (r & ~mask) | (X << (32 * first))
+            assert ((j0 * (r >> (32 * first))) >> 64) & 0xFFFFFFFF == 0xFFFFFFFF
+            j = j0
+        else:
+            j = prng.randrange(1 << n)
+        d = 1 + prng.randrange(r - 1)
+        cases.append((d, r, j, prng.randrange(-25, 26), LD(prng.random()) * LD(0.6)))
+    for full in ("0", "1"):
+        os.environ["QB200_DIAGK_FULL_PRODUCT"] = full
+        try:
+            for d, r, j, eta, piv in cases:
+                S = hs.DiagK(m, sigma, l, d, r)
+                ks, x, delta, st = S.sample([j], [eta], np.array([piv], dtype=LD), 40)
+                ok, k, xe = _exact_sample(m, sigma, l, d, r, j, eta, piv, 40)
+                assert ok == (st[0] in (0, 2)) and ks[0] == k, (full, d, r, j, eta)
+        finally:
+            del os.environ["QB200_DIAGK_FULL_PRODUCT"]
+
+
+def test_twin_fixed_point_fraction_equals_the_exact_one():
+    """diagk_fraction_fixed_point (one truncated product with 2^l d / r in fixed point) against
+    diagk_fraction_exact (s rho, Barrett division, low bits of s D'; QB200_DIAGK_EXACT_FRACTION=1
+    sends every sample there) and against the exact integers: k identical, x to 2^-95 of itself --
+    over odd shapes, and on inputs where the fixed-point path must decline (s = 0: t = 0)."""
+    import os
+    import random
+    prng = random.Random(777)
+    cases = []
+    for trial in range(60):
+        rbits = prng.choice([128, 130, 191, 200, 257, 288, 512])
+        m = rbits + prng.choice([0, 1, 7, 40])
+        sigma = prng.choice([0, 1, 5, 31, 32])
+        l = max(1, min(prng.choice([1, 13, 32, 33, 64, 109, 110, 111, m, m + sigma]), m + sigma))
+        r = (1 << (rbits - 1)) + prng.randrange(1 << (rbits - 1))
+        d = prng.choice([1, r - 1, r // 2, 1 + prng.randrange(r - 1)])
+        n = m + sigma
+        js = [0, 1, (1 << n) - 1, 1 << (n - 1)] + [prng.randrange(1 << n) for _ in range(4)]
+        etas = [0, 0, 1, -1] + [prng.randrange(-25, 26) for _ in range(4)]
+        piv = np.array([LD(prng.random()) * LD(0.6) for _ in js], dtype=LD)
+        cases.append((m, sigma, l, d, r, js, etas, piv))
+    got = {}
+    for exact in ("0", "1"):
+        os.environ["QB200_DIAGK_EXACT_FRACTION"] = exact
+        try:
+            for ci, (m, sigma, l, d, r, js, etas, piv) in enumerate(cases):
+                S = hs.DiagK(m, sigma, l, d, r)
+                ks, x, delta, st = S.sample(js, etas, piv, 40)
+                got[(exact, ci)] = (ks, x.copy(), delta.copy(), st.copy())
+                for i, j in enumerate(js):
+                    ok, k, xe = _exact_sample(m, sigma, l, d, r, j, etas[i], piv[i], 40)
+                    assert ok == (st[i] in (0, 2)) and ks[i] == k, (exact, m, sigma, l, d, r, j, etas[i])
+                    if ok:
+                        with mp.workprec(200):
+                            v = mp.mpf(float(x[i, 0])) + mp.mpf(float(x[i, 1]))
+                            assert abs(v - xe) <= abs(xe) * mp.mpf(2) ** -95 + mp.mpf(2) ** -1000, (exact, m, l, j)
+        finally:
+            del os.environ["QB200_DIAGK_EXACT_FRACTION"]
+    for ci in range(len(cases)):
+        a, b = got[("0", ci)], got[("1", ci)]
+        assert a[0] == b[0] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
 def test_twin_refuses_bad_parameters():
     with pytest.raises(ValueError):
         hs.DiagK(128, 0, 64, 5, 3)          # d >= r
