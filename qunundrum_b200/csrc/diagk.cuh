@@ -299,7 +299,7 @@ QHD void acc_add(Acc96& a, const Acc96& b) {
 #define QB_MULCOL_ATTR QHD
 #endif
 #ifndef QB_DIAGK_UNROLL
-#define QB_DIAGK_UNROLL 4
+#define QB_DIAGK_UNROLL 8
 #endif
 // Loads of V. In device code V lies in shared memory (k_diagk stages r, d and mu there) and is read
 // with ld.shared instead of a generic load (+3 %; QB_DIAGK_LDS=0: generic loads, for the A/B).
