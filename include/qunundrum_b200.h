@@ -21,6 +21,11 @@
  *   qb200_diagk_sample                       sample_k_from_diagonal_j_eta_pivot             src/sample.cpp:412
  *   qb200_diagk_h                            diagonal_probability_approx_h                  src/diagonal_probability.cpp:99
  *   qb200_diagk_tau_estimate                 the sum and log of tau_estimate_diagonal       src/tau_estimate.cpp:135
+ *   qb200_exact_alpha                        sample_alpha_from_region                       src/sample.cpp:78
+ *   qb200_exact_j_k                          sample_j_from_alpha_r, sample_j_k_from_alpha_d, src/sample.cpp:160,210,275,354
+ *                                            sample_j_k_from_alpha_d_r, sample_j_from_diagonal_alpha_r
+ *   qb200_diagk_sample_drawn                 diagonal_distribution_sample_pair_j_k after    src/diagonal_distribution.cpp:474
+ *                                            the region is chosen
  *
  * Conventions
  *  - plain pointers and sizes only; all buffers are caller-owned;
@@ -436,6 +441,98 @@ int qb200_diagk_set_force_exact(qb200_diagk *sampler, int on);
  * rounded to long double as mpfr_get_ld does. */
 int qb200_diagk_h(qb200_diagk *sampler, uint32_t n, const double *x_hi, const double *x_lo,
                   long double *h);
+
+/* ---- exact samplers ---------------------------------------------------------
+ * The reference draws an integer argument from a region of a slice and maps it to the pair (j, k)
+ * with MPFR at 3 m bits and GMP, one sample per call:
+ *   sample_alpha_from_region           src/sample.cpp:78-158   alpha = min + (v mod (max - min))
+ *   sample_j_from_alpha_r              src/sample.cpp:160-208
+ *   sample_j_k_from_alpha_d            src/sample.cpp:210-273
+ *   sample_j_k_from_alpha_d_r          src/sample.cpp:275-352
+ *   sample_j_from_diagonal_alpha_r     src/sample.cpp:354-410
+ * (the second halves of linear_distribution_sample_alpha, src/linear_distribution.cpp:668-724,
+ * diagonal_distribution_sample_alpha_r / _j_eta, src/diagonal_distribution.cpp:355-472, and
+ * distribution_sample_pair_j_k, src/distribution.cpp:615-680). Here a batch of samples is one
+ * call; the integers are the reference's bit for bit (qunundrum_b200/csrc/exact.cuh).
+ *
+ * A qb200_exact holds, for one set of parameters: (r / 2^kappa_r)^-1 and (d / 2^kappa_d)^-1 modulo
+ * 2^n, d, and the table 2^(i / dimension_max) from which the bounds round(2^|log alpha|) of a region
+ * are formed. kind QB200_EXACT_TWO_DIMENSIONAL: n = m + l, k has l bits (Parameters; also the
+ * linear distributions); QB200_EXACT_DIAGONAL: n = m + sigma, no k (Diagonal_Parameters; k comes
+ * from qb200_diagk). dimension_max: the largest slice dimension, a power of two <= 16384. emax:
+ * bounds up to 2^emax (0: m + 64; |alpha| < 2^emax travels in alpha_limbs = ceil((emax + 1) / 32)
+ * words). Limits: m >= 64, n <= 32768, kappa_d, kappa_r <= 64.
+ *
+ * Integers travel as little-endian 32-bit words, one row per sample, zero padded: |alpha| in
+ * alpha_limbs words with the sign apart (negative[i] = 1: alpha < 0), j in j_limbs = ceil(n / 32)
+ * words, k in k_limbs = ceil(l / 32) words, t in max(1, ceil(kappa / 32)) words. */
+typedef struct qb200_exact qb200_exact;
+
+#define QB200_EXACT_TWO_DIMENSIONAL 0
+#define QB200_EXACT_DIAGONAL 1
+
+int qb200_exact_create(qb200_context *ctx, const qb200_params *params, int kind,
+                       uint32_t dimension_max, uint32_t emax, qb200_exact **sampler);
+void qb200_exact_destroy(qb200_exact *sampler);
+/* out: alpha_limbs, j_limbs, k_limbs, kappa_d, kappa_r, emax. */
+void qb200_exact_dims(const qb200_exact *sampler, uint32_t out[6]);
+
+/* One region of a slice as distribution_slice_region_coordinates (src/distribution_slice.cpp:130-165)
+ * and its linear / diagonal twins give it: |log alpha| on [e + region / dimension,
+ * e + (region + 1) / dimension] with e = |min_log_alpha|, the slice's coordinate, whose sign is
+ * alpha's; the sample's random bytes are stream[offset, offset + length). */
+typedef struct qb200_exact_region {
+  int32_t min_log_alpha;
+  uint32_t region;
+  uint32_t dimension;
+  uint32_t length;
+  uint64_t offset;
+} qb200_exact_region;
+
+#define QB200_EXACT_OK 0
+#define QB200_EXACT_LENGTH 1      /* length is not what random_generate_mpz reads for this region */
+#define QB200_EXACT_AMBIGUOUS 2   /* a bound within 2^-64 of a half-integer (never observed) */
+#define QB200_EXACT_UNSUPPORTED 3 /* |min_log_alpha| < 64 or >= emax, dimension not a power of two
+                                   * up to dimension_max, region >= dimension */
+
+/* The bytes random_generate_mpz (src/random.c:158-181) reads for a sample of this region:
+ * (bits(max - min) + 72) / 8. Stream layout, computed on the host (the caller cannot cut a
+ * sample's bytes out of its random stream without it). Errors: -50 unsupported, -51 ambiguous. */
+int qb200_exact_region_bytes(const qb200_exact *sampler, int32_t min_log_alpha, uint32_t region,
+                             uint32_t dimension, uint32_t *bytes);
+
+/* n independent calls of sample_alpha_from_region(alpha, min_log_alpha, max_log_alpha, kappa,
+ * random_state) with the bytes the Random_State would deliver given in `stream`. status[i] != 0:
+ * alpha[i] is not valid. */
+int qb200_exact_alpha(qb200_exact *sampler, uint32_t n, const qb200_exact_region *regions,
+                      uint32_t kappa, const uint8_t *stream, uint64_t stream_len, uint32_t *alpha,
+                      int32_t *negative, int32_t *status);
+
+#define QB200_EXACT_J_FROM_ALPHA_R 0      /* sample_j_from_alpha_r / sample_j_from_diagonal_alpha_r */
+#define QB200_EXACT_J_K_FROM_ALPHA_D_R 1  /* sample_j_k_from_alpha_d_r */
+#define QB200_EXACT_J_FROM_ALPHA_D_K 2    /* sample_j_k_from_alpha_d (k drawn by the caller) */
+
+/* n independent calls of the (j, k) sampler `mode` selects. What the reference draws inside them
+ * is drawn by the caller (it is stream layout: fixed sizes per parameter set) and passed in:
+ * t = t_r (modes 0, 1; for mode 1 already multiplied by 2^kappa_t_r, src/sample.cpp:294-309) or
+ * t_d (mode 2), NULL when the kappa in question is 0; k (mode 2, input). Outputs: j; k (mode 1).
+ * Arguments a mode does not use may be NULL. */
+int qb200_exact_j_k(qb200_exact *sampler, int mode, uint32_t n, const uint32_t *alpha_d,
+                    const int32_t *negative_d, const uint32_t *alpha_r, const int32_t *negative_r,
+                    const uint32_t *t, uint32_t *j, uint32_t *k);
+
+/* The diagonal distribution's sample from its random bytes to k without leaving the device
+ * (diagonal_distribution_sample_pair_j_k, src/diagonal_distribution.cpp:474-552, after the region
+ * is chosen): alpha_r from regions[i] (kappa = kappa_r), j = sample_j_from_diagonal_alpha_r
+ * (t_r: rows, NULL for odd r), then qb200_diagk_sample's outputs for (j, eta[i], pivot[i]).
+ * `exact` must be a QB200_EXACT_DIAGONAL sampler of the same parameters. exact_status[i] != 0
+ * (QB200_EXACT_*): the sample's other outputs are not valid. */
+int qb200_diagk_sample_drawn(qb200_diagk *sampler, qb200_exact *exact, uint32_t n,
+                             const qb200_exact_region *regions, const uint32_t *t_r,
+                             const uint8_t *stream, uint64_t stream_len, const int32_t *eta,
+                             const long double *pivot, uint32_t delta_bound, uint32_t *k,
+                             double *x_hi, double *x_lo, int64_t *delta, int32_t *status,
+                             int32_t *exact_status);
 
 /* ---- introspection (host logic; usable without a GPU) --------------------- */
 

@@ -102,6 +102,10 @@ def lib():
     L.qref_sample_k_from_diagonal.restype = C.c_int
     L.qref_diagonal_probability_h.argtypes = [vp, cp, u32]
     L.qref_diagonal_probability_h.restype = C.c_longdouble
+    L.qref_sample_alpha_from_region.argtypes = [C.c_double, C.c_double, u32, vp, cp, sz]
+    L.qref_sample_alpha_from_region.restype = C.c_int
+    L.qref_sample_j_k.argtypes = [C.c_int, vp, cp, cp, vp, cp, cp, sz]
+    L.qref_sample_j_k.restype = C.c_int
     _lib = L
     return L
 
@@ -383,3 +387,31 @@ def sample_k_from_diagonal_j_eta_pivot(params: RefDiagonalParameters, pivot, j: 
 def diagonal_probability_h(params: RefDiagonalParameters, phi: str, precision: int = 0):
     """diagonal_probability_approx_h (src/diagonal_probability.cpp:99) as a long double."""
     return np.longdouble(lib().qref_diagonal_probability_h(params.h, phi.encode(), precision))
+
+
+# --------------------------------------------------------------------------- #
+# The exact samplers (src/sample.cpp:78-410)                                  #
+# --------------------------------------------------------------------------- #
+
+def sample_alpha_from_region(min_log_alpha: float, max_log_alpha: float, kappa: int,
+                             rng: RefRandom) -> int:
+    """sample_alpha_from_region (src/sample.cpp:78-158) on the given Random_State."""
+    buf = C.create_string_buffer(16384)
+    rc = lib().qref_sample_alpha_from_region(min_log_alpha, max_log_alpha, kappa, rng.h, buf, 16384)
+    if rc:
+        raise RuntimeError("buffer too small")
+    return int(buf.value, 16)
+
+
+def sample_j_k(mode: int, params, alpha_d, alpha_r, rng: RefRandom):
+    """mode 0: sample_j_from_alpha_r, 1: sample_j_k_from_alpha_d_r, 2: sample_j_k_from_alpha_d
+    (RefParameters); 3: sample_j_from_diagonal_alpha_r (RefDiagonalParameters). Returns (j, k)."""
+    jb = C.create_string_buffer(16384)
+    kb = C.create_string_buffer(16384)
+    rc = lib().qref_sample_j_k(mode, params.h,
+                               None if alpha_d is None else format(alpha_d, "x").encode(),
+                               None if alpha_r is None else format(alpha_r, "x").encode(),
+                               rng.h, jb, kb, 16384)
+    if rc:
+        raise RuntimeError("buffer too small")
+    return int(jb.value, 16), int(kb.value, 16)

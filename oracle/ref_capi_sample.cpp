@@ -14,6 +14,9 @@
  *   sample_approximate_alpha_from_region                 src/sample.cpp:24
  *   tau_estimate / tau_estimate_linear                   src/tau_estimate.cpp:23,89
  *   sample_k_from_diagonal_j_eta_pivot                   src/sample.cpp:412-646
+ *   sample_alpha_from_region                             src/sample.cpp:78-158
+ *   sample_j_from_alpha_r / sample_j_k_from_alpha_d[_r]  src/sample.cpp:160-352
+ *   sample_j_from_diagonal_alpha_r                       src/sample.cpp:354-410
  *   diagonal_probability_approx_h                        src/diagonal_probability.cpp:99-162
  *   random_generate / keccak_random_init_seed            src/random.c:88, src/keccak_random.c:52
  *
@@ -318,6 +321,69 @@ long double qref_diagonal_probability_h(void *params, const char *phi_dec, uint3
   mpfr_clear(phi);
   mpfr_clear(norm);
   return out;
+}
+
+/* sample_alpha_from_region (src/sample.cpp:78-158): alpha as a signed hexadecimal string.
+ * Returns 0, or -1 if the buffer is too small. */
+int qref_sample_alpha_from_region(double min_log_alpha, double max_log_alpha, uint32_t kappa, void *rs,
+                                  char *out, size_t cap) {
+  ensure_precision();
+  mpz_t alpha;
+  mpz_init(alpha);
+  sample_alpha_from_region(alpha, min_log_alpha, max_log_alpha, kappa, (Random_State *)rs);
+  int rc = 0;
+  if (mpz_sizeinbase(alpha, 16) + 3 > cap)
+    rc = -1;
+  else
+    mpz_get_str(out, 16, alpha);
+  mpz_clear(alpha);
+  return rc;
+}
+
+/* The (j, k) samplers on given arguments (signed hexadecimal strings), drawing from rs what the
+ * reference draws:
+ *   mode 0  sample_j_from_alpha_r           (Parameters; alpha_r)              -> j
+ *   mode 1  sample_j_k_from_alpha_d_r       (Parameters; alpha_d, alpha_r)     -> j, k
+ *   mode 2  sample_j_k_from_alpha_d         (Parameters; alpha_d)              -> j, k (k drawn)
+ *   mode 3  sample_j_from_diagonal_alpha_r  (Diagonal_Parameters; alpha_r)     -> j
+ * Returns 0, or -1 if a buffer is too small. */
+int qref_sample_j_k(int mode, void *params, const char *alpha_d_hex, const char *alpha_r_hex, void *rs,
+                    char *j_out, char *k_out, size_t cap) {
+  ensure_precision();
+  mpz_t ad, ar, j, k;
+  mpz_init(ad);
+  mpz_init(ar);
+  mpz_init(j);
+  mpz_init(k);
+  if (alpha_d_hex) mpz_set_str(ad, alpha_d_hex, 16);
+  if (alpha_r_hex) mpz_set_str(ar, alpha_r_hex, 16);
+  Random_State *r = (Random_State *)rs;
+  switch (mode) {
+    case 0:
+      sample_j_from_alpha_r(j, ar, (const Parameters *)params, r);
+      break;
+    case 1:
+      sample_j_k_from_alpha_d_r(j, k, ad, ar, (const Parameters *)params, r);
+      break;
+    case 2:
+      sample_j_k_from_alpha_d(j, k, ad, (const Parameters *)params, r);
+      break;
+    default:
+      sample_j_from_diagonal_alpha_r(j, ar, (const Diagonal_Parameters *)params, r);
+      break;
+  }
+  int rc = 0;
+  if (mpz_sizeinbase(j, 16) + 3 > cap || mpz_sizeinbase(k, 16) + 3 > cap) {
+    rc = -1;
+  } else {
+    mpz_get_str(j_out, 16, j);
+    mpz_get_str(k_out, 16, k);
+  }
+  mpz_clear(ad);
+  mpz_clear(ar);
+  mpz_clear(j);
+  mpz_clear(k);
+  return rc;
 }
 
 } /* extern "C" */

@@ -25,7 +25,7 @@ OBJ = os.path.join(HERE, "_obj")
 
 def sources():
     return [os.path.join(CSRC, f) for f in
-            ("qb200.cu", "qb200_text.cu", "qb200_sampler.cu", "qb200_diagk.cu", "qb200_client.cu", "hostconst.cpp",
+            ("qb200.cu", "qb200_text.cu", "qb200_sampler.cu", "qb200_diagk.cu", "qb200_exact.cu", "qb200_client.cu", "hostconst.cpp",
              "text_tables.cpp")]
 
 

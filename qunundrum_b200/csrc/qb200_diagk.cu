@@ -18,42 +18,12 @@
 
 #include "../../include/qunundrum_b200.h"
 #include "ctx_access.hpp"
+#include "devbuf.hpp"
 #include "diagk_host.hpp"
+#include "exact_api.hpp"
 #include "kernels_diagk.cuh"
 
 using namespace qb200;
-
-#define QD_CUDA(call)                                                                   \
-  do {                                                                                  \
-    const cudaError_t e_ = (call);                                                      \
-    if (e_ != cudaSuccess)                                                              \
-      return set_error(-100, std::string(#call) + ": " + cudaGetErrorString(e_));       \
-  } while (0)
-
-namespace {
-
-struct DBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  ~DBuf() {
-    if (p) cudaFree(p);
-  }
-  int reserve(size_t n) {
-    if (n <= bytes) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    QD_CUDA(cudaMalloc(&p, n));
-    bytes = n;
-    return 0;
-  }
-  template <class T>
-  T* as() const {
-    return (T*)p;
-  }
-};
-
-}  // namespace
 
 struct qb200_diagk {
   int device = 0;
@@ -135,9 +105,10 @@ uint32_t qb200_diagk_j_limbs(const qb200_diagk* s) { return s ? s->host.c.wj : 0
 uint32_t qb200_diagk_k_limbs(const qb200_diagk* s) { return s ? s->host.c.wl : 0; }
 
 // The launches of one chunk of B samples whose rows already lie in device memory.
+// d_j_tiles != NULL: j already lies in tiles (k_exact_jk wrote it) and d_j is not read.
 static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const int32_t* d_eta,
                         const RawX87* d_pivot, uint32_t delta_bound, uint32_t* d_k_rows, DiagKOut* d_out,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const uint32_t* d_j_tiles = nullptr) {
   const DiagKConst& c = s->host.c;
   const size_t scr = diagk_scratch_limbs(c.k);
   const size_t Bp = ((size_t)B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA * QB_DIAGK_CTA;  // whole tiles
@@ -145,15 +116,19 @@ static int launch_chunk(qb200_diagk* s, uint32_t B, const uint32_t* d_j, const i
   // one CTA (and one scratch area) per tile: a persistent wave with per-CTA scratch was measured
   // and is slower (kernels_diagk.cuh)
   const uint32_t grid = (uint32_t)(Bp / QB_DIAGK_CTA);
-  if (s->cols_j.reserve(Bp * c.wj * 4) || s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * scr * 4)) return -100;
+  if ((!d_j_tiles && s->cols_j.reserve(Bp * c.wj * 4)) || s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * scr * 4))
+    return -100;
   if (d_k_rows && s->cols_k.reserve(Bp * c.wl * 4)) return -100;
-  const uint64_t nj = (uint64_t)Bp * c.wj;
-  k_diagk_gather<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(d_j, c.wj, B, s->cols_j.as<uint32_t>());
-  k_diagk<<<grid, QB_DIAGK_CTA, shmem, stream>>>(s->dev, s->cols_j.as<uint32_t>(), d_eta, d_pivot,
-                                                  (unsigned long long)delta_bound, B,
+  if (!d_j_tiles) {
+    const uint64_t nj = (uint64_t)Bp * c.wj;
+    k_diagk_gather<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(d_j, c.wj, B, s->cols_j.as<uint32_t>());
+    *s->launches += 1;
+  }
+  k_diagk<<<grid, QB_DIAGK_CTA, shmem, stream>>>(s->dev, d_j_tiles ? d_j_tiles : s->cols_j.as<uint32_t>(), d_eta,
+                                                  d_pivot, (unsigned long long)delta_bound, B,
                                                   s->scratch.as<uint32_t>(),
                                                   d_k_rows ? s->cols_k.as<uint32_t>() : nullptr, d_out);
-  *s->launches += 2;
+  *s->launches += 1;
   if (d_k_rows) {
     const uint64_t nk = (uint64_t)B * c.wl;
     k_diagk_scatter<<<(unsigned)((nk + 255) / 256), 256, 0, stream>>>(s->cols_k.as<uint32_t>(), c.wl, B,
@@ -201,6 +176,59 @@ int qb200_diagk_sample(qb200_diagk* s, uint32_t n, const uint32_t* j, const int3
     if (rc) return rc;
     ho.resize(B);
     QD_CUDA(cudaMemcpyAsync(ho.data(), s->out.p, (size_t)B * sizeof(DiagKOut), cudaMemcpyDeviceToHost, s->stream));
+    if (k)
+      QD_CUDA(cudaMemcpyAsync(k + (size_t)done * c.wl, s->rows_k.p, (size_t)B * c.wl * 4, cudaMemcpyDeviceToHost,
+                              s->stream));
+    QD_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t i = 0; i < B; i++) {
+      if (ho[i].status < 0) return set_error(-42, "The pivot is out of bounds.");
+      if (x_hi) x_hi[done + i] = ho[i].x_hi;
+      if (x_lo) x_lo[done + i] = ho[i].x_lo;
+      if (delta) delta[done + i] = ho[i].delta;
+      if (status) status[done + i] = ho[i].status;
+    }
+    done += B;
+  }
+  return 0;
+}
+
+int qb200_diagk_sample_drawn(qb200_diagk* s, qb200_exact* ex, uint32_t n, const qb200_exact_region* regions,
+                             const uint32_t* t_r, const uint8_t* stream, uint64_t stream_len, const int32_t* eta,
+                             const long double* pivot, uint32_t delta_bound, uint32_t* k, double* x_hi,
+                             double* x_lo, int64_t* delta, int32_t* status, int32_t* exact_status) {
+  if (!s || !ex || !regions || !stream || !eta || !pivot || !exact_status) return set_error(-1, "null argument");
+  const DiagKConst& c = s->host.c;
+  if (exact_j_limbs(ex) != c.wj || exact_device(ex) != s->device)
+    return set_error(-2, "qb200_diagk_sample_drawn: the exact sampler is not a diagonal one of the same parameters "
+                         "on the same device");
+  QD_CUDA(cudaSetDevice(s->device));
+  uint32_t dims[6];
+  qb200_exact_dims(ex, dims);
+  const uint32_t tl = dims[4] ? (dims[4] + 31) / 32 : 1;
+  const uint8_t* d_stream = nullptr;
+  int rc = exact_upload_stream(ex, stream, stream_len, &d_stream, s->stream);
+  if (rc) return rc;
+  const uint32_t chunk = s->chunk < exact_chunk(ex) ? s->chunk : exact_chunk(ex);
+  std::vector<DiagKOut> ho;
+  for (uint32_t done = 0; done < n;) {
+    const uint32_t B = n - done < chunk ? n - done : chunk;
+    const uint32_t* d_jT = nullptr;
+    const int32_t* d_st = nullptr;
+    rc = exact_draw_j_tiles(ex, B, regions + done, t_r ? t_r + (size_t)done * tl : nullptr, d_stream, stream_len,
+                            &d_jT, &d_st, s->stream);
+    if (rc) return rc;
+    if (s->eta.reserve((size_t)B * 4) || s->pivot.reserve((size_t)B * 16) ||
+        s->out.reserve((size_t)B * sizeof(DiagKOut)))
+      return -100;
+    if (k && s->rows_k.reserve((size_t)B * c.wl * 4)) return -100;
+    QD_CUDA(cudaMemcpyAsync(s->eta.p, eta + done, (size_t)B * 4, cudaMemcpyHostToDevice, s->stream));
+    QD_CUDA(cudaMemcpyAsync(s->pivot.p, pivot + done, (size_t)B * 16, cudaMemcpyHostToDevice, s->stream));
+    rc = launch_chunk(s, B, nullptr, s->eta.as<int32_t>(), s->pivot.as<RawX87>(), delta_bound,
+                      k ? s->rows_k.as<uint32_t>() : nullptr, s->out.as<DiagKOut>(), s->stream, d_jT);
+    if (rc) return rc;
+    ho.resize(B);
+    QD_CUDA(cudaMemcpyAsync(ho.data(), s->out.p, (size_t)B * sizeof(DiagKOut), cudaMemcpyDeviceToHost, s->stream));
+    QD_CUDA(cudaMemcpyAsync(exact_status + done, d_st, (size_t)B * 4, cudaMemcpyDeviceToHost, s->stream));
     if (k)
       QD_CUDA(cudaMemcpyAsync(k + (size_t)done * c.wl, s->rows_k.p, (size_t)B * c.wl * 4, cudaMemcpyDeviceToHost,
                               s->stream));

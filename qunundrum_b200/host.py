@@ -144,6 +144,15 @@ def lib():
     L.qb200_diagk_tau_estimate.argtypes = [vp, u32, u32, vp, vp, vp, u32, u32, vp, vp]
     L.qb200_diagk_h.argtypes = [vp, u32, vp, vp, vp]
     L.qb200_diagk_set_force_exact.argtypes = [vp, C.c_int]
+    L.qb200_exact_create.argtypes = [vp, PP, C.c_int, u32, u32, C.POINTER(vp)]
+    L.qb200_exact_destroy.argtypes = [vp]
+    L.qb200_exact_dims.argtypes = [vp, vp]
+    L.qb200_exact_dims.restype = None
+    L.qb200_exact_region_bytes.argtypes = [vp, C.c_int32, u32, u32, C.POINTER(u32)]
+    L.qb200_exact_alpha.argtypes = [vp, u32, vp, u32, vp, C.c_uint64, vp, vp, vp]
+    L.qb200_exact_j_k.argtypes = [vp, C.c_int, u32, vp, vp, vp, vp, vp, vp, vp]
+    L.qb200_diagk_sample_drawn.argtypes = [vp, vp, u32, vp, vp, vp, C.c_uint64, vp, vp, u32, vp, vp, vp,
+                                           vp, vp, vp]
     L.qb200_slice2d_compute_scaled.argtypes = [vp, PP, C.c_int, C.c_int, u32, u32, u32, i32p, i32p,
                                                vp, vp, vp, vp]
     L.qb200_resident_create.argtypes = [vp, u32, vp, vp, vp, C.POINTER(vp)]
@@ -1099,3 +1108,133 @@ def sample_k_from_diagonal_j_eta_pivot(parameters: Diagonal_Parameters, pivot, j
 
 
 _diagk = {}
+
+
+# --------------------------------------------------------------------------- #
+# Exact samplers: alpha from a region, (j, k) from alpha                      #
+# --------------------------------------------------------------------------- #
+
+EXACT_TWO_DIMENSIONAL, EXACT_DIAGONAL = 0, 1
+EXACT_REGION_DTYPE = np.dtype([("min_log_alpha", "<i4"), ("region", "<u4"), ("dimension", "<u4"),
+                               ("length", "<u4"), ("offset", "<u8")])
+
+
+def _abs_rows(vals, w: int) -> np.ndarray:
+    out = np.zeros((len(vals), w), dtype=np.uint32)
+    for i, v in enumerate(vals):
+        out[i] = int_to_limbs(abs(int(v)), w)
+    return out
+
+
+def _signs(vals) -> np.ndarray:
+    return np.array([1 if v < 0 else 0 for v in vals], dtype=np.int32)
+
+
+def pack_regions(regions) -> np.ndarray:
+    """(min_log_alpha, region, dimension, offset, length) per sample -> qb200_exact_region records."""
+    g = np.zeros(len(regions), dtype=EXACT_REGION_DTYPE)
+    for i, (a, reg, dim, off, ln) in enumerate(regions):
+        g[i] = (a, reg, dim, ln, off)
+    return g
+
+
+class ExactSampler:
+    """sample_alpha_from_region and the (j, k) samplers of src/sample.cpp:78-410 for batches, on the
+    GPU (qb200_exact). parameters: Parameters (kind EXACT_TWO_DIMENSIONAL) or Diagonal_Parameters
+    (EXACT_DIAGONAL)."""
+
+    def __init__(self, parameters, dimension_max: int, emax: int = 0, ctx: "Context" = None):
+        self.ctx = ctx or default_context()
+        self.parameters = parameters
+        self.kind = EXACT_DIAGONAL if isinstance(parameters, Diagonal_Parameters) else EXACT_TWO_DIMENSIONAL
+        h = C.c_void_p()
+        p = parameters._c()
+        _check(lib().qb200_exact_create(self.ctx.h, C.byref(p), self.kind, dimension_max, emax, C.byref(h)),
+               "qb200_exact_create")
+        self.h = h
+        out = (C.c_uint32 * 6)()
+        lib().qb200_exact_dims(h, out)
+        self.wa, self.wn, self.wk, self.kappa_d, self.kappa_r, self.emax = [int(x) for x in out]
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().qb200_exact_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def region_bytes(self, min_log_alpha: int, region: int, dimension: int):
+        """(bytes random_generate_mpz reads, status) -- status 0, 2 (ambiguous) or 3 (unsupported)."""
+        n = C.c_uint32(0)
+        rc = lib().qb200_exact_region_bytes(self.h, min_log_alpha, region, dimension, C.byref(n))
+        return int(n.value), {0: 0, -51: 2, -50: 3}.get(rc, rc)
+
+    def alpha(self, regions, kappa: int, stream: bytes):
+        """n calls of sample_alpha_from_region: signed Python ints and the status codes."""
+        g = regions if isinstance(regions, np.ndarray) else pack_regions(regions)
+        buf = np.frombuffer(stream, dtype=np.uint8)
+        n = len(g)
+        rows = np.zeros((n, self.wa), dtype=np.uint32)
+        neg = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        _check(lib().qb200_exact_alpha(self.h, n, g.ctypes.data, kappa, buf.ctypes.data, len(buf),
+                                       rows.ctypes.data, neg.ctypes.data, st.ctypes.data), "qb200_exact_alpha")
+        vals = [(-limbs_to_int(r) if s else limbs_to_int(r)) for r, s in zip(rows, neg)]
+        return vals, st
+
+    def _jk(self, mode, alpha_d, alpha_r, t, k_in=None):
+        n = len(alpha_d if alpha_d is not None else alpha_r)
+        kap = self.kappa_d if mode == 2 else self.kappa_r
+        tl = max(1, (kap + 31) // 32)
+        ad = _abs_rows(alpha_d, self.wa) if alpha_d is not None else None
+        ar = _abs_rows(alpha_r, self.wa) if alpha_r is not None else None
+        nd = _signs(alpha_d) if alpha_d is not None else None
+        nr = _signs(alpha_r) if alpha_r is not None else None
+        tt = _abs_rows(t, tl) if (t is not None and kap) else None
+        j = np.zeros((n, self.wn), dtype=np.uint32)
+        k = _abs_rows(k_in, self.wk) if k_in is not None else np.zeros((n, max(1, self.wk)), dtype=np.uint32)
+        p = lambda a: a.ctypes.data if a is not None else None
+        _check(lib().qb200_exact_j_k(self.h, mode, n, p(ad), p(nd), p(ar), p(nr), p(tt), p(j), p(k)),
+               "qb200_exact_j_k")
+        return [limbs_to_int(r) for r in j], [limbs_to_int(r) for r in k]
+
+    def j_from_alpha_r(self, alpha_r, t=None):
+        """sample_j_from_alpha_r / sample_j_from_diagonal_alpha_r with t_r as drawn by the caller."""
+        return self._jk(0, None, alpha_r, t)[0]
+
+    def j_k_from_alpha_d_r(self, alpha_d, alpha_r, t=None):
+        """sample_j_k_from_alpha_d_r: (j list, k list)."""
+        return self._jk(1, alpha_d, alpha_r, t)
+
+    def j_from_alpha_d_k(self, alpha_d, k, t=None):
+        """sample_j_k_from_alpha_d with k and t_d as drawn by the caller."""
+        return self._jk(2, alpha_d, None, t, k_in=k)[0]
+
+
+def diagonal_sample_drawn(diagk: DiagonalKSampler, exact: ExactSampler, regions, t_r, stream: bytes, etas,
+                          pivots, delta_bound: int = 0xffffffff, want_k: bool = True):
+    """qb200_diagk_sample_drawn: a diagonal sample from its random bytes to k on the device. Returns
+    (k ints or None, x rows (hi, lo), delta, status, exact_status)."""
+    g = regions if isinstance(regions, np.ndarray) else pack_regions(regions)
+    n = len(g)
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    tl = max(1, (exact.kappa_r + 31) // 32)
+    tt = _abs_rows(t_r, tl) if (t_r is not None and exact.kappa_r) else None
+    eta = np.ascontiguousarray(etas, dtype=np.int32)
+    piv = np.ascontiguousarray(pivots, dtype=np.longdouble)
+    K = np.zeros((n, diagk.k_limbs), dtype=np.uint32) if want_k else None
+    xh, xl = np.zeros(n), np.zeros(n)
+    delta = np.zeros(n, dtype=np.int64)
+    status = np.zeros(n, dtype=np.int32)
+    est = np.zeros(n, dtype=np.int32)
+    _check(lib().qb200_diagk_sample_drawn(diagk.h, exact.h, n, g.ctypes.data, tt.ctypes.data if tt is not None else None,
+                                          buf.ctypes.data, len(buf), eta.ctypes.data, piv.ctypes.data, delta_bound,
+                                          K.ctypes.data if want_k else None, xh.ctypes.data, xl.ctypes.data,
+                                          delta.ctypes.data, status.ctypes.data, est.ctypes.data),
+           "qb200_diagk_sample_drawn")
+    ks = [limbs_to_int(K[i]) for i in range(n)] if want_k else None
+    return ks, np.stack([xh, xl], axis=1), delta, status, est

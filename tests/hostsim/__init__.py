@@ -19,7 +19,7 @@ _SRCS = [os.path.join(_HERE, "hostsim.cpp"),
 _DEPS = _SRCS + [os.path.join(_ROOT, "qunundrum_b200", "csrc", f) for f in
                  ("qmath.cuh", "integrands.cuh", "slice_cells.cuh", "sigma_opt.cuh", "plan.hpp",
                   "hostconst.hpp", "bigint.hpp", "textfmt.cuh", "textparse.cuh", "text_tables.hpp",
-                  "sampler.cuh", "x87soft.cuh", "diagk.cuh", "diagk_host.hpp", "client_math.cuh")]
+                  "sampler.cuh", "x87soft.cuh", "diagk.cuh", "diagk_host.hpp", "client_math.cuh", "exact.cuh", "exact_host.hpp")]
 _lib = None
 
 
@@ -349,3 +349,104 @@ def collapse(axis: int, max_dim: int, slices):
                                 ptrs, out.ctypes.data_as(C.c_void_p))
     assert ok
     return out
+
+
+# ---- exact samplers (exact.cuh) ---------------------------------------------------------------
+
+REGION_DTYPE = np.dtype([("min_log_alpha", "<i4"), ("region", "<u4"), ("dimension", "<u4"),
+                         ("length", "<u4"), ("offset", "<u8")])
+
+
+def _rows(vals, w):
+    out = np.zeros((len(vals), w), dtype=np.uint32)
+    for i, v in enumerate(vals):
+        out[i] = np.frombuffer(int(abs(v)).to_bytes(4 * w, "little"), dtype=np.uint32)
+    return out
+
+
+def _ints(rows):
+    return [int.from_bytes(np.ascontiguousarray(r).tobytes(), "little") for r in rows]
+
+
+class Exact:
+    """The exact samplers through the CPU twin; the interface of qunundrum_b200.host.ExactSampler."""
+
+    def __init__(self, kind, m, l, sigma, d, r, dimension_max, emax=0):
+        db, rb = be(d), be(r)
+        L = lib()
+        L.hostsim_exact_new.restype = C.c_void_p
+        L.hostsim_exact_table.restype = C.c_void_p
+        L.hostsim_exact_inverse.restype = C.c_void_p
+        L.hostsim_exact_region_bytes.restype = C.c_uint32
+        self.h = C.c_void_p(L.hostsim_exact_new(
+            C.c_int(kind), C.c_uint32(m), C.c_uint32(l), C.c_uint32(sigma), db, C.c_size_t(len(db)), rb,
+            C.c_size_t(len(rb)), C.c_uint32(dimension_max), C.c_uint32(emax)))
+        if not self.h:
+            raise ValueError(L.hostsim_last_error().decode())
+        out = (C.c_uint32 * 9)()
+        L.hostsim_exact_dims(self.h, out)
+        (self.wa, self.wn, self.wk, self.kappa_d, self.kappa_r, self.tw, self.P, self.table_dim,
+         self.emax) = [int(x) for x in out]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().hostsim_exact_free(self.h)
+            self.h = None
+
+    def table(self):
+        p = lib().hostsim_exact_table(self.h)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.table_dim, self.tw))
+        return _ints(a)
+
+    def inverse(self, which):
+        p = lib().hostsim_exact_inverse(self.h, C.c_int(which))
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(1, self.wn))
+        return _ints(a)[0]
+
+    def region_bytes(self, min_log_alpha, region, dimension):
+        st = C.c_int32(0)
+        n = lib().hostsim_exact_region_bytes(self.h, C.c_int32(min_log_alpha), C.c_uint32(region),
+                                             C.c_uint32(dimension), C.byref(st))
+        return int(n), int(st.value)
+
+    def alpha(self, regions, kappa, stream: bytes):
+        """regions: (min_log_alpha, region, dimension, offset, length) per sample. Returns the signed
+        integers and the status codes."""
+        g = np.zeros(len(regions), dtype=REGION_DTYPE)
+        for i, (a, reg, dim, off, ln) in enumerate(regions):
+            g[i] = (a, reg, dim, ln, off)
+        buf = np.frombuffer(stream, dtype=np.uint8)
+        n = len(g)
+        rows = np.zeros((n, self.wa), dtype=np.uint32)
+        neg = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        lib().hostsim_exact_alpha(self.h, C.c_uint32(n), g.ctypes.data_as(C.c_void_p), C.c_uint32(kappa),
+                                  buf.ctypes.data_as(C.c_void_p), C.c_uint64(len(buf)),
+                                  rows.ctypes.data_as(C.c_void_p), neg.ctypes.data_as(C.c_void_p),
+                                  st.ctypes.data_as(C.c_void_p))
+        vals = [(-v if s else v) for v, s in zip(_ints(rows), neg)]
+        return vals, st
+
+    def _jk(self, mode, alpha_d, alpha_r, t, k_in=None):
+        n = len(alpha_d if alpha_d is not None else alpha_r)
+        kap = self.kappa_d if mode == 2 else self.kappa_r
+        tl = max(1, (kap + 31) // 32)
+        ad = _rows(alpha_d, self.wa) if alpha_d is not None else None
+        ar = _rows(alpha_r, self.wa) if alpha_r is not None else None
+        nd = np.array([1 if v < 0 else 0 for v in alpha_d], dtype=np.int32) if alpha_d is not None else None
+        nr = np.array([1 if v < 0 else 0 for v in alpha_r], dtype=np.int32) if alpha_r is not None else None
+        tt = _rows(t, tl) if (t is not None and kap) else None
+        j = np.zeros((n, self.wn), dtype=np.uint32)
+        k = _rows(k_in, self.wk) if k_in is not None else np.zeros((n, max(1, self.wk)), dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        lib().hostsim_exact_jk(self.h, C.c_int(mode), C.c_uint32(n), p(ad), p(nd), p(ar), p(nr), p(tt), p(j), p(k))
+        return _ints(j), _ints(k)
+
+    def j_from_alpha_r(self, alpha_r, t=None):
+        return self._jk(0, None, alpha_r, t)[0]
+
+    def j_k_from_alpha_d_r(self, alpha_d, alpha_r, t=None):
+        return self._jk(1, alpha_d, alpha_r, t)
+
+    def j_from_alpha_d_k(self, alpha_d, k, t=None):
+        return self._jk(2, alpha_d, None, t, k_in=k)[0]

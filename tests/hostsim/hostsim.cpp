@@ -799,3 +799,87 @@ int hostsim_collapse(int axis, uint32_t max_dim, uint32_t n_src, const uint32_t*
 }
 
 }  // extern "C"
+
+// ---- exact samplers (exact.cuh): the device functions in plain loops ---------------------------
+#include "../../qunundrum_b200/csrc/exact_host.hpp"
+
+extern "C" {
+
+void* hostsim_exact_new(int kind, uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d, size_t dn,
+                        const uint8_t* r, size_t rn, uint32_t dimension_max, uint32_t emax) {
+  ExactHost* h = new ExactHost;
+  if (exact_prepare(kind, m, l, sigma, d, dn, r, rn, dimension_max, emax, h, &g_err)) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+void hostsim_exact_free(void* h) { delete (ExactHost*)h; }
+void hostsim_exact_dims(void* hh, uint32_t* out9) {
+  const ExactConst& c = ((ExactHost*)hh)->c;
+  const uint32_t v[9] = {c.wa, c.wn, c.wk, c.kappa_d, c.kappa_r, c.tw, c.P, c.table_dim, c.emax};
+  for (int i = 0; i < 9; i++) out9[i] = v[i];
+}
+const uint32_t* hostsim_exact_table(void* hh) { return ((ExactHost*)hh)->table.data(); }
+const uint32_t* hostsim_exact_inverse(void* hh, int which) {
+  ExactHost* h = (ExactHost*)hh;
+  return (which ? h->inv_d : h->inv_r).data() + QB_DIAGK_PAD;
+}
+
+// The bytes random_generate_mpz reads for a region (0: see *status).
+uint32_t hostsim_exact_region_bytes(void* hh, int32_t min_log_alpha, uint32_t region, uint32_t dimension,
+                                    int32_t* status) {
+  const ExactConst& c = ((ExactHost*)hh)->c;
+  std::vector<uint32_t> lo(c.wa), M(c.wa + 1);
+  ExactRegion g;
+  g.min_log_alpha = min_log_alpha;
+  g.region = region;
+  g.dimension = dimension;
+  g.length = 0;
+  g.offset = 0;
+  int st = 0;
+  const uint32_t bits = exact_region_modulus<1>(c, g, lo.data(), M.data(), &st);
+  *status = st;
+  return st == QB_EXACT_OK ? exact_bytes_for_bits(bits) : 0;
+}
+
+void hostsim_exact_alpha(void* hh, uint32_t n, const ExactRegion* regions, uint32_t kappa, const uint8_t* stream,
+                         uint64_t stream_len, uint32_t* alpha, int32_t* negative, int32_t* status) {
+  const ExactConst& c = ((ExactHost*)hh)->c;
+  std::vector<uint32_t> scratch(exact_alpha_scratch_limbs(c));
+  for (uint32_t i = 0; i < n; i++) {
+    int neg = 0;
+    status[i] = exact_alpha<1, 1>(c, regions[i], kappa, stream, stream_len, scratch.data(),
+                                  alpha + (size_t)i * c.wa, &neg);
+    negative[i] = neg;
+  }
+}
+
+// mode 0 / 3: j from alpha_r (t: rows of max(1, ceil(kappa_r / 32)) words, NULL when kappa_r = 0);
+// mode 1: (j, k) from (alpha_d, alpha_r); mode 2: j from (alpha_d, k) with k and t given.
+void hostsim_exact_jk(void* hh, int mode, uint32_t n, const uint32_t* alpha_d, const int32_t* neg_d,
+                      const uint32_t* alpha_r, const int32_t* neg_r, const uint32_t* t, uint32_t* j,
+                      uint32_t* k) {
+  const ExactConst& c = ((ExactHost*)hh)->c;
+  std::vector<uint32_t> scratch(exact_jk_scratch_limbs(c));
+  const uint32_t kap = mode == 2 ? c.kappa_d : c.kappa_r;
+  const uint32_t tl = kap ? (kap + 31) / 32 : 1;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t* ti = t ? t + (size_t)i * tl : nullptr;
+    uint32_t* ji = j + (size_t)i * c.wn;
+    if (mode == 2) {
+      exact_j_from_alpha_d_k<1, 1, 1, 1, 1>(c, alpha_d + (size_t)i * c.wa, neg_d[i], k + (size_t)i * c.wk, ti,
+                                            scratch.data(), ji);
+      continue;
+    }
+    exact_j_from_alpha_r<1, 1, 1, 1>(c, alpha_r + (size_t)i * c.wa, neg_r[i], ti, scratch.data(), ji);
+    if (mode == 1)
+      exact_k_from_alpha_d_j<1, 1, 1, 1>(c, alpha_d + (size_t)i * c.wa, neg_d[i], ji, scratch.data(),
+                                         k + (size_t)i * c.wk);
+  }
+}
+
+// exact_mod on given numbers: V (nv limbs, room for one more) mod M (wm limbs, room for one more).
+void hostsim_exact_mod(uint32_t* V, uint32_t nv, uint32_t* M, uint32_t wm) { exact_mod<1>(V, nv, M, wm); }
+
+}  // extern "C"
