@@ -14,18 +14,20 @@
 // links against the function below.
 //
 // Division of labour for one estimate of n samples (src/tau_estimate.cpp:135-210):
-//   * (j, eta) of every sample is drawn here, on the host, by the reference's own
-//     diagonal_distribution_sample_region (src/diagonal_distribution.cpp:306-352), followed by the
-//     arithmetic of sample_alpha_from_region (src/sample.cpp:77-157) and
-//     sample_j_from_diagonal_alpha_r (src/sample.cpp:352-410) with GMP, step by step the same
-//     calls on the same Random_State -- except that what these two functions recompute for
-//     every sample is kept: the integer bounds round(2^|log alpha|) of a region (two mpfr_exp2
-//     at 3 m bits per sample in the reference; here one mpfr_exp2 per distinct fractional part
-//     of log alpha, see bound_of()) and (r / 2^kappa_r)^-1 mod 2^(m + sigma) (one mpz_invert per
-//     sample). Same integers, same draws, same j.
-//   * k and alpha_phi given (j, eta, pivot) -- sample_k_from_diagonal_j_eta_pivot
-//     (src/sample.cpp:412-646), the part that evaluates diagonal_probability_approx_h at
-//     2 (m + sigma) bits -- come from the GPU for all n samples in one call.
+//   * which region a sample falls in is decided here, on the host, by the reference's own
+//     diagonal_distribution_sample_region (src/diagonal_distribution.cpp:306-352) on the caller's
+//     Random_State: the number of bytes the sample then reads -- (bits(max - min) + 72) / 8,
+//     src/random.c:163-164 -- depends on the region, so the position of sample i + 1 in the stream is
+//     known only once sample i is placed; per Random_State this walk is serial wherever it runs.
+//     What follows the region -- the bytes of alpha_r, those of t_r for an even r, the pivot of the
+//     k sampling -- is only READ here (random_generate into the batch's byte buffer, the reference's
+//     random_generate_pivot_inclusive), not computed with.
+//   * alpha_r = min + (bytes mod (max - min)) (sample_alpha_from_region, src/sample.cpp:78-158: two
+//     mpfr_exp2 at 3 m bits and an mpz_mod per sample in the reference), j =
+//     sample_j_from_diagonal_alpha_r (src/sample.cpp:354-410: an mpz_invert and a product per sample),
+//     k and alpha_phi given (j, eta, pivot) (sample_k_from_diagonal_j_eta_pivot, src/sample.cpp:412-646)
+//     come from the GPU for all samples of a batch in ONE call, qb200_diagk_sample_drawn; j never
+//     leaves the device. No GMP arithmetic is left in this file.
 //   * the sum of alpha_phi^2, its log2 and tau are formed as the reference forms them, in MPFR at
 //     PRECISION bits from the double-double alpha_phi the library returns.
 //
@@ -130,72 +132,41 @@ qb200_context* context() {
 // What is the same for every sample of a distribution.
 struct Setup {
   bool valid = false;
-  uint32_t m = 0, sigma = 0, l = 0, kappa_r = 0;
-  mpz_t d, r, inverse, pow2_n;  // inverse = (r / 2^kappa_r)^-1 mod 2^(m + sigma)
+  uint32_t m = 0, sigma = 0, l = 0, kappa_r = 0, dimension_max = 0, t_words = 1;
+  mpz_t d, r;
   qb200_diagk* sampler = NULL;
-  uint32_t j_limbs = 0;
-  struct Bounds {
-    mpz_t min_alpha, modulus;  // round(2^|min_log|), round(2^|max_log|) - round(2^|min_log|)
-  };
-  std::map<std::pair<double, double>, Bounds*> regions;
-  struct Z {
-    mpz_t z;
-  };
-  std::map<std::pair<double, uint32_t>, Z*> bounds;
-  struct F {
-    mpfr_t v;
-  };
-  std::map<double, F*> exp2_frac;  // 2^f, f in [0, 1), at 3 (m + sigma + 2) + 128 bits
+  qb200_exact* exact = NULL;
+  std::map<uint64_t, uint32_t> region_bytes;  // (sign, e, dimension, region) -> bytes of a sample
 } g;
 
 void setup_clear() {
   if (!g.valid) return;
   mpz_clear(g.d);
   mpz_clear(g.r);
-  mpz_clear(g.inverse);
-  mpz_clear(g.pow2_n);
-  for (auto& e : g.regions) {
-    mpz_clear(e.second->min_alpha);
-    mpz_clear(e.second->modulus);
-    delete e.second;
-  }
-  g.regions.clear();
-  for (auto& e : g.bounds) {
-    mpz_clear(e.second->z);
-    delete e.second;
-  }
-  g.bounds.clear();
-  for (auto& e : g.exp2_frac) {
-    mpfr_clear(e.second->v);
-    delete e.second;
-  }
-  g.exp2_frac.clear();
+  g.region_bytes.clear();
   if (g.sampler) qb200_diagk_destroy(g.sampler);
+  if (g.exact) qb200_exact_destroy(g.exact);
   g.sampler = NULL;
+  g.exact = NULL;
   g.valid = false;
 }
 
-void setup_for(const Diagonal_Parameters* p) {
-  if (g.valid && g.m == p->m && g.sigma == p->sigma && g.l == p->l && 0 == mpz_cmp(g.d, p->d) &&
-      0 == mpz_cmp(g.r, p->r))
+void setup_for(const Diagonal_Parameters* p, uint32_t dimension_max) {
+  if (g.valid && g.m == p->m && g.sigma == p->sigma && g.l == p->l && g.dimension_max >= dimension_max &&
+      0 == mpz_cmp(g.d, p->d) && 0 == mpz_cmp(g.r, p->r))
     return;
   setup_clear();
   g.m = p->m;
   g.sigma = p->sigma;
   g.l = p->l;
+  g.dimension_max = dimension_max;
   mpz_init_set(g.d, p->d);
   mpz_init_set(g.r, p->r);
-  mpz_init(g.inverse);
-  mpz_init(g.pow2_n);
   g.kappa_r = kappa(p->r);
-  mpz_setbit(g.pow2_n, p->m + p->sigma);
-  mpz_t t;
-  mpz_init(t);
-  mpz_fdiv_q_2exp(t, p->r, g.kappa_r);              // src/sample.cpp:377-379
-  if (0 == mpz_invert(g.inverse, t, g.pow2_n)) {     // :384
-    critical("tau_estimate_diagonal(): r / 2^kappa_r is not invertible modulo 2^(m + sigma).");
+  g.t_words = g.kappa_r ? (g.kappa_r + 31) / 32 : 1;
+  if (dimension_max > 0 && g.kappa_r > 64) {
+    critical("tau_estimate_diagonal(): r divisible by more than 2^64 is not supported.");
   }
-  mpz_clear(t);
   std::vector<uint8_t> db((mpz_sizeinbase(p->d, 2) + 7) / 8 + 1), rb((mpz_sizeinbase(p->r, 2) + 7) / 8 + 1);
   size_t dn = 0, rn = 0;
   mpz_export(db.data(), &dn, 1, 1, 1, 0, p->d);
@@ -211,135 +182,116 @@ void setup_for(const Diagonal_Parameters* p) {
   if (0 != qb200_diagk_create(context(), &q, &g.sampler)) {
     critical("tau_estimate_diagonal(): %s", qb200_last_error());
   }
-  g.j_limbs = qb200_diagk_j_limbs(g.sampler);
+  // dimension_max = 0: the one-sample entry points below, which take j from their caller
+  if (dimension_max > 0 &&
+      0 != qb200_exact_create(context(), &q, QB200_EXACT_DIAGONAL, dimension_max, 0, &g.exact)) {
+    critical("tau_estimate_diagonal(): %s", qb200_last_error());
+  }
   g.valid = true;
 }
 
-// round(2^|log alpha|) as sample_alpha_from_region computes it (src/sample.cpp:97-124:
-// mpfr_set_d, mpfr_exp2, mpfr_round at `precision` = 3 ceil(|max log alpha|) bits, mpfr_get_z),
-// kept per (value, precision): the upper bound of one region is the lower bound of the next.
-//
-// The reference pays one mpfr_exp2 at ~3 m bits per bound (0.17 ms at m = 2048). Here
-// |log alpha| = e + f with an integer e and f = i / dimension: 2^f is computed once per f at a
-// precision above every precision the reference uses, and the bound is round(2^e 2^f). The two
-// agree whenever 2^(e+f) is farther from a half-integer than the reference's own rounding error
-// 2^(e + 1 - precision) <= 2^(-2 e - 2) -- which is checked: a value within 2^-64 of a
-// half-integer (never seen) is computed the reference's way.
-const mpz_t* bound_of(double abs_log_alpha, uint32_t precision) {
-  const std::pair<double, uint32_t> key(abs_log_alpha, precision);
-  auto it = g.bounds.find(key);
-  if (it != g.bounds.end()) return &it->second->z;
-  Setup::Z* b = new Setup::Z;
-  mpz_init(b->z);
-  const double e = floor(abs_log_alpha), f = abs_log_alpha - e;  // exact: dimension is a power of two
-  const uint32_t wide = 3 * (g.m + g.sigma + 2) + 128;
-  bool done = false;
-  if (precision + 64 <= wide && e >= 64 && e + 1 <= (double)(precision / 3 + 1)) {
-    Setup::F*& pf = g.exp2_frac[f];
-    if (!pf) {
-      pf = new Setup::F;
-      mpfr_init2(pf->v, wide);
-      mpfr_set_d(pf->v, f, MPFR_RNDN);
-      mpfr_exp2(pf->v, pf->v, MPFR_RNDN);
-      g_stats.bounds++;
+void setup_for(const Diagonal_Distribution* distribution) {
+  uint32_t dimension_max = 1;
+  for (uint32_t i = 0; i < distribution->count; i++) {
+    const uint32_t dim = distribution->slices[i]->dimension;
+    if (dim == 0 || (dim & (dim - 1)) != 0 || dim > 16384) {
+      critical("tau_estimate_diagonal(): a slice dimension of %u (not a power of two up to 16384) is not "
+               "supported by the GPU sampler.", dim);
     }
-    mpfr_t y, t;
-    mpfr_init2(y, wide);
-    mpfr_init2(t, wide);
-    mpfr_mul_2si(y, pf->v, (long)e, MPFR_RNDN);  // exact
-    mpfr_floor(t, y);
-    mpfr_sub(t, y, t, MPFR_RNDN);                // fractional part, exact
-    mpfr_sub_d(t, t, 0.5, MPFR_RNDN);
-    if (mpfr_cmp_d(t, 5.421010862427522e-20) > 0 || mpfr_cmp_d(t, -5.421010862427522e-20) < 0) {  // 2^-64
-      mpfr_round(y, y);
-      mpfr_get_z(b->z, y, MPFR_RNDN);
-      done = true;
-    }
-    mpfr_clear(y);
-    mpfr_clear(t);
+    if (dim > dimension_max) dimension_max = dim;
   }
-  if (!done) {
-    mpfr_t x;
-    mpfr_init2(x, precision);
-    mpfr_set_d(x, abs_log_alpha, MPFR_RNDN);
-    mpfr_exp2(x, x, MPFR_RNDN);
-    mpfr_round(x, x);
-    mpfr_get_z(b->z, x, MPFR_RNDN);
-    mpfr_clear(x);
-    g_stats.bounds++;
-  }
-  g.bounds[key] = b;
-  return &b->z;
+  setup_for(&distribution->parameters, dimension_max);
 }
 
-// The integers sample_alpha_from_region (src/sample.cpp:77-128) derives from the region's
-// bounds, once per region.
-const Setup::Bounds* bounds_of(double min_log_alpha, double max_log_alpha) {
-  const std::pair<double, double> key(min_log_alpha, max_log_alpha);
-  auto it = g.regions.find(key);
-  if (it != g.regions.end()) return it->second;
-  if (sgn_d(min_log_alpha) != sgn_d(max_log_alpha)) {
-    critical("sample_alpha_from_region(): Incompatible signs for min_log_alpha and max_log_alpha.");
+// The rows of a batch: what the GPU call takes.
+struct Rows {
+  std::vector<qb200_exact_region> region;
+  std::vector<uint32_t> t;       // t_r, g.t_words per sample (zero for an odd r)
+  std::vector<int32_t> eta;
+  std::vector<long double> pivot;
+  std::vector<uint8_t> bytes;    // the samples' random bytes, one after the other
+  void clear() {
+    region.clear();
+    t.clear();
+    eta.clear();
+    pivot.clear();
+    bytes.clear();
   }
-  if (abs_d(min_log_alpha) >= abs_d(max_log_alpha)) {
-    critical("sample_alpha_from_region(): Incompatible absolute values for min_log_alpha and max_log_alpha.");
+};
+
+// The bytes sample_alpha_from_region reads for a region (random_generate_mpz, src/random.c:163-164):
+// stream layout, once per region.
+uint32_t bytes_of_region(int32_t min_log_alpha, uint32_t region, uint32_t dimension) {
+  const uint64_t key = ((uint64_t)(uint32_t)(min_log_alpha + 65536) << 40) | ((uint64_t)dimension << 20) | region;
+  auto it = g.region_bytes.find(key);
+  if (it != g.region_bytes.end()) return it->second;
+  uint32_t n = 0;
+  if (0 != qb200_exact_region_bytes(g.exact, min_log_alpha, region, dimension, &n)) {
+    critical("tau_estimate_diagonal(): %s", qb200_last_error());
   }
-  const uint32_t m = ceil(abs_d(max_log_alpha));   // :93
-  const uint32_t precision = 3 * m;                // :95
-  Setup::Bounds* b = new Setup::Bounds;
-  mpz_init_set(b->min_alpha, *bound_of(abs_d(min_log_alpha), precision));             // :97-103, :118-120
-  mpz_init(b->modulus);
-  mpz_sub(b->modulus, *bound_of(abs_d(max_log_alpha), precision), b->min_alpha);      // :105-111, :122-128
-  g.regions[key] = b;
-  return b;
+  g.region_bytes[key] = n;
+  return n;
 }
 
-// diagonal_distribution_sample_j_eta (src/diagonal_distribution.cpp:410-472): the same draws
-// from the same Random_State, the same j.
-bool draw_j_eta(const Diagonal_Distribution* distribution, Random_State* rs, mpz_t j, int32_t* eta,
-                mpz_t alpha_r, mpz_t t_r, mpz_t tmp) {
+// diagonal_distribution_sample_j_eta (src/diagonal_distribution.cpp:410-472) as far as the stream
+// is concerned: the same reads from the same Random_State in the same order; the arithmetic on what
+// is read happens on the device.
+bool draw_row(const Diagonal_Distribution* distribution, Random_State* rs, Rows& rows, int32_t* eta) {
   double min_log_alpha_r, max_log_alpha_r;
   if (FALSE == diagonal_distribution_sample_region(distribution, rs, &min_log_alpha_r, &max_log_alpha_r, eta)) {
     return false;  // :366-383, :428-443
   }
-  // sample_alpha_from_region(alpha_r, min, max, kappa_r, rs), src/sample.cpp:77-157
-  const Setup::Bounds* b = bounds_of(min_log_alpha_r, max_log_alpha_r);
-  random_generate_mpz(alpha_r, b->modulus, rs);     // :130
-  mpz_add(alpha_r, b->min_alpha, alpha_r);          // :131
-  if (g.kappa_r > 0) {                              // :133-144
-    mpz_fdiv_r_2exp(tmp, alpha_r, g.kappa_r);
-    mpz_sub(alpha_r, alpha_r, tmp);
+  // the region as (slice coordinate, index, dimension): diagonal_distribution_slice_region_coordinates
+  // (src/diagonal_distribution_slice.cpp:153-179) formed min = sgn (e + i / D), max = sgn (e + (i + 1) / D)
+  // in doubles, exactly (D is a power of two)
+  if (sgn_d(min_log_alpha_r) != sgn_d(max_log_alpha_r)) {
+    critical("sample_alpha_from_region(): Incompatible signs for min_log_alpha and max_log_alpha.");
   }
-  if (sgn_d(min_log_alpha_r) == -1) mpz_neg(alpha_r, alpha_r);  // :147-149
-  // sample_j_from_diagonal_alpha_r(j, alpha_r, parameters, rs), src/sample.cpp:352-410
-  mpz_set_ui(t_r, 0);
-  if (g.kappa_r > 0) {                              // :368-372
-    mpz_set_ui(tmp, 0);
-    mpz_setbit(tmp, g.kappa_r);
-    random_generate_mpz(t_r, tmp, rs);
+  const double lo = abs_d(min_log_alpha_r), hi = abs_d(max_log_alpha_r);
+  if (lo >= hi) {
+    critical("sample_alpha_from_region(): Incompatible absolute values for min_log_alpha and max_log_alpha.");
   }
-  mpz_mul(j, g.inverse, alpha_r);                   // :386-387
-  mpz_fdiv_q_2exp(j, j, g.kappa_r);                 // :389-393 (mpz_div floors)
-  mpz_mul_2exp(tmp, t_r, g.m + g.sigma - g.kappa_r);  // :395-399
-  mpz_add(j, j, tmp);                               // :400
-  mpz_fdiv_r_2exp(j, j, g.m + g.sigma);             // :402-406 (mpz_mod: non-negative)
+  const double e = floor(lo), dim = 1.0 / (hi - lo);
+  qb200_exact_region q;
+  q.min_log_alpha = (int32_t)(sgn_d(min_log_alpha_r) == -1 ? -e : e);
+  q.dimension = (uint32_t)dim;
+  q.region = (uint32_t)((lo - e) * dim);
+  q.length = bytes_of_region(q.min_log_alpha, q.region, q.dimension);
+  q.offset = rows.bytes.size();
+  // sample_alpha_from_region -> random_generate_mpz(alpha, max - min, rs), src/sample.cpp:130
+  rows.bytes.resize(rows.bytes.size() + q.length);
+  random_generate(&rows.bytes[q.offset], q.length, rs);
+  rows.region.push_back(q);
+  // sample_j_from_diagonal_alpha_r -> random_generate_mpz(t_r, 2^kappa_r, rs), src/sample.cpp:370-375:
+  // (kappa_r + 1 + 72) / 8 bytes, big-endian, reduced modulo 2^kappa_r -- its low kappa_r bits
+  const size_t at = rows.t.size();
+  rows.t.resize(at + g.t_words, 0u);
+  if (g.kappa_r > 0) {
+    uint8_t buf[32];
+    const uint32_t len = (g.kappa_r + 1 + 64 + 8) / 8;  // <= 17
+    random_generate(buf, len, rs);
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < 8; i++) v = (v << 8) | buf[len - 8 + i];
+    if (g.kappa_r < 64) v &= ((uint64_t)1 << g.kappa_r) - 1;
+    rows.t[at] = (uint32_t)v;
+    if (g.t_words > 1) rows.t[at + 1] = (uint32_t)(v >> 32);
+  }
   return true;
 }
 
-// One estimate's draws (src/tau_estimate.cpp:158-188 without the k sampling): one row of
-// J / eta / pivot per sample whose k is wanted. Returns the number of rows appended; *failed is
-// set if the estimate fails on the host's side already -- no slice
-// (diagonal_distribution_sample_j_eta returns FALSE) or |eta| > eta_bound -- with the stream where
-// the reference leaves it in that case (the rows before the failing sample still go to the GPU:
-// an earlier k out of bounds would have stopped the reference earlier). `limit` < n: replay of the
-// first `limit` samples only.
+// One estimate's draws (src/tau_estimate.cpp:158-188 without the arithmetic): one row per sample
+// whose k is wanted. Returns the number of rows appended; *failed is set if the estimate fails on
+// the host's side already -- no slice (diagonal_distribution_sample_j_eta returns FALSE) or
+// |eta| > eta_bound -- with the stream where the reference leaves it in that case (the rows before
+// the failing sample still go to the GPU: an earlier k out of bounds would have stopped the reference
+// earlier). `limit` < n: replay of the first `limit` samples only.
 uint32_t draw_estimate(const Diagonal_Distribution* distribution, Random_State* rs, uint32_t limit,
-                       uint32_t eta_bound, std::vector<uint32_t>& J, std::vector<int32_t>& eta,
-                       std::vector<long double>& pivot, mpz_t* z, bool* failed) {
+                       uint32_t eta_bound, Rows& rows, bool* failed) {
   *failed = false;
   for (uint32_t i = 0; i < limit; i++) {
     int32_t e = 0;
-    if (!draw_j_eta(distribution, rs, z[0], &e, z[1], z[2], z[3])) {
+    const size_t n_region = rows.region.size(), n_t = rows.t.size(), n_bytes = rows.bytes.size();
+    if (!draw_row(distribution, rs, rows, &e)) {
       *failed = true;
       return i;
     }
@@ -347,14 +299,14 @@ uint32_t draw_estimate(const Diagonal_Distribution* distribution, Random_State* 
     // eta follows the k sampling (src/tau_estimate.cpp:175-181) and fails the estimate either way
     const long double p = random_generate_pivot_inclusive(rs);
     if (abs_i(e) > eta_bound) {
+      rows.region.resize(n_region);  // the failing sample's k is not wanted
+      rows.t.resize(n_t);
+      rows.bytes.resize(n_bytes);
       *failed = true;
       return i;
     }
-    eta.push_back(e);
-    pivot.push_back(p);
-    J.resize(eta.size() * g.j_limbs, 0u);
-    size_t cnt = 0;
-    mpz_export(&J[(eta.size() - 1) * g.j_limbs], &cnt, -1, 4, 0, 0, z[0]);
+    rows.eta.push_back(e);
+    rows.pivot.push_back(p);
   }
   return limit;
 }
@@ -404,11 +356,8 @@ void compute_batch(const Diagonal_Distribution* distribution, Random_State* rs, 
   g_batch.tau.assign(B, DBL_MAX);
   g_batch.ok.assign(B, 0);
   const bool can_rewind = (NULL == rs->random_device);
-  mpz_t z[4];
-  for (int i = 0; i < 4; i++) mpz_init(z[i]);
-  std::vector<uint32_t> J;
-  std::vector<int32_t> eta, status;
-  std::vector<long double> pivot;
+  Rows rows, replay;
+  std::vector<int32_t> status, exact_status;
   std::vector<double> x_hi, x_lo;
   std::vector<Random_State> entry;
   struct Est {
@@ -419,32 +368,39 @@ void compute_batch(const Diagonal_Distribution* distribution, Random_State* rs, 
   std::vector<Est> est;
   uint32_t t0 = 0;
   while (t0 < B) {
-    J.clear();
-    eta.clear();
-    pivot.clear();
+    rows.clear();
     entry.clear();
     est.clear();
     double t = now_s();
     for (uint32_t e = t0; e < B; e++) {
       if (can_rewind) entry.push_back(*rs);
       Est s;
-      s.row = eta.size();
-      s.count = draw_estimate(distribution, rs, n, eta_bound, J, eta, pivot, z, &s.failed);
+      s.row = rows.eta.size();
+      s.count = draw_estimate(distribution, rs, n, eta_bound, rows, &s.failed);
       est.push_back(s);
     }
     g_stats.s_draw += now_s() - t;
-    const uint32_t rows = (uint32_t)eta.size();
-    g_stats.samples += rows;
-    x_hi.resize(rows);
-    x_lo.resize(rows);
-    status.resize(rows);
-    if (rows) {
+    const uint32_t count = (uint32_t)rows.eta.size();
+    g_stats.samples += count;
+    x_hi.resize(count);
+    x_lo.resize(count);
+    status.resize(count);
+    exact_status.resize(count);
+    if (count) {
       t = now_s();
-      if (0 != qb200_diagk_sample(g.sampler, rows, J.data(), eta.data(), pivot.data(), delta_bound, NULL,
-                                  x_hi.data(), x_lo.data(), NULL, status.data())) {
+      if (rows.bytes.empty()) rows.bytes.push_back(0);
+      if (0 != qb200_diagk_sample_drawn(g.sampler, g.exact, count, rows.region.data(),
+                                        g.kappa_r ? rows.t.data() : NULL, rows.bytes.data(), rows.bytes.size(),
+                                        rows.eta.data(), rows.pivot.data(), delta_bound, NULL, x_hi.data(),
+                                        x_lo.data(), NULL, status.data(), exact_status.data())) {
         critical("tau_estimate_diagonal(): %s", qb200_last_error());
       }
       g_stats.s_abi += now_s() - t;
+      for (uint32_t i = 0; i < count; i++) {
+        if (exact_status[i] != QB200_EXACT_OK) {
+          critical("tau_estimate_diagonal(): the GPU sampler declined a region (status %d).", exact_status[i]);
+        }
+      }
     }
     t = now_s();
     uint32_t restart = B;
@@ -475,11 +431,9 @@ void compute_batch(const Diagonal_Distribution* distribution, Random_State* rs, 
       const bool drew_on = s.failed || bad + 1 < n;
       if (drew_on && can_rewind) {
         *rs = entry[e - t0];
-        std::vector<uint32_t> J2;
-        std::vector<int32_t> eta2;
-        std::vector<long double> pivot2;
         bool f2;
-        draw_estimate(distribution, rs, bad + 1, eta_bound, J2, eta2, pivot2, z, &f2);
+        replay.clear();
+        draw_estimate(distribution, rs, bad + 1, eta_bound, replay, &f2);
         g_stats.replays++;
         restart = e + 1;
         break;
@@ -488,7 +442,6 @@ void compute_batch(const Diagonal_Distribution* distribution, Random_State* rs, 
     g_stats.s_sum += now_s() - t;
     t0 = restart;
   }
-  for (int i = 0; i < 4; i++) mpz_clear(z[i]);
 }
 
 }  // namespace
@@ -504,7 +457,7 @@ bool tau_estimate_diagonal(const Diagonal_Distribution* const distribution, Rand
   Batch& b = g_batch;
   if (!(b.next < b.ok.size() && b.distribution == distribution && b.rs == random_state && b.n == n &&
         b.delta_bound == delta_bound && b.eta_bound == eta_bound)) {
-    setup_for(&distribution->parameters);
+    setup_for(distribution);
     const int want = env_int("QB200_TAU_BATCH", 1000);
     compute_batch(distribution, random_state, n, delta_bound, eta_bound, (uint32_t)(want > 0 ? want : 1));
     b.distribution = distribution;
@@ -532,13 +485,13 @@ bool sample_k_from_diagonal_j_eta_pivot(const Diagonal_Parameters* const paramet
   if ((pivot < 0) || (pivot > 1)) {
     critical("sample_k_from_diagonal_j_eta_pivot(): The pivot is out of bounds.");
   }
-  setup_for(parameters);
+  setup_for(parameters, 0);
   // j + a 2^(m+sigma) gives the same k and alpha_phi as j (r j changes by a multiple of 2^(m+sigma) r):
   // the ABI takes j on [0, 2^(m+sigma))
   mpz_t jr;
   mpz_init(jr);
   mpz_fdiv_r_2exp(jr, j, g.m + g.sigma);
-  std::vector<uint32_t> row(g.j_limbs, 0u), krow(qb200_diagk_k_limbs(g.sampler), 0u);
+  std::vector<uint32_t> row(qb200_diagk_j_limbs(g.sampler), 0u), krow(qb200_diagk_k_limbs(g.sampler), 0u);
   size_t cnt = 0;
   mpz_export(row.data(), &cnt, -1, 4, 0, 0, jr);
   mpz_clear(jr);
@@ -586,7 +539,7 @@ void diagonal_probability_approx_h(mpfr_t norm, const mpfr_t phi, const Diagonal
     mpfr_set_ui(norm, 1, MPFR_RNDN);
     return;
   }
-  setup_for(parameters);
+  setup_for(parameters, 0);
   const mpfr_prec_t prec = (mpfr_get_prec(phi) > 192 ? mpfr_get_prec(phi) : 192) + 64;
   mpfr_t x, two_pi;
   mpfr_init2(x, prec);

@@ -431,6 +431,8 @@ class Exact:
         n = len(alpha_d if alpha_d is not None else alpha_r)
         kap = self.kappa_d if mode == 2 else self.kappa_r
         tl = max(1, (kap + 31) // 32)
+        if kap and t is None:
+            raise ValueError("t is needed when the divisor is even")
         ad = _rows(alpha_d, self.wa) if alpha_d is not None else None
         ar = _rows(alpha_r, self.wa) if alpha_r is not None else None
         nd = np.array([1 if v < 0 else 0 for v in alpha_d], dtype=np.int32) if alpha_d is not None else None

@@ -243,6 +243,86 @@ int qb200_diagk_h(qb200_diagk* s, uint32_t n, const double* x_hi, const double* 
   return 0;
 }
 
+}  // extern "C"
+
+// ---- exact sampler entry points (TEST-ONLY, same purpose): the stream layout of
+// dropin_tau_diagonal.cpp (regions, byte counts, t_r) runs in the GPU-less suite; alpha_r, j and k come
+// from the CPU compile of exact.cuh and diagk.cuh.
+extern "C" {
+void* hostsim_exact_new(int kind, uint32_t m, uint32_t l, uint32_t sigma, const uint8_t* d, size_t dn,
+                        const uint8_t* r, size_t rn, uint32_t dimension_max, uint32_t emax);
+void hostsim_exact_free(void* h);
+void hostsim_exact_dims(void* hh, uint32_t* out9);
+uint32_t hostsim_exact_region_bytes(void* hh, int32_t min_log_alpha, uint32_t region, uint32_t dimension,
+                                    int32_t* status);
+void hostsim_exact_alpha(void* hh, uint32_t n, const void* regions, uint32_t kappa, const uint8_t* stream,
+                         uint64_t stream_len, uint32_t* alpha, int32_t* negative, int32_t* status);
+void hostsim_exact_jk(void* hh, int mode, uint32_t n, const uint32_t* alpha_d, const int32_t* neg_d,
+                      const uint32_t* alpha_r, const int32_t* neg_r, const uint32_t* t, uint32_t* j,
+                      uint32_t* k);
+}
+
+struct qb200_exact {
+  void* h = nullptr;
+  uint32_t dims[9] = {0};
+};
+
+extern "C" {
+
+int qb200_exact_create(qb200_context*, const qb200_params* p, int kind, uint32_t dimension_max, uint32_t emax,
+                       qb200_exact** out) {
+  *out = nullptr;
+  void* h = hostsim_exact_new(kind, p->m, p->l, p->sigma, p->d_be, p->d_len, p->r_be, p->r_len, dimension_max, emax);
+  if (!h) {
+    g_err = hostsim_last_error();
+    return -2;
+  }
+  qb200_exact* s = new qb200_exact;
+  s->h = h;
+  hostsim_exact_dims(h, s->dims);
+  *out = s;
+  return 0;
+}
+void qb200_exact_destroy(qb200_exact* s) {
+  if (!s) return;
+  hostsim_exact_free(s->h);
+  delete s;
+}
+void qb200_exact_dims(const qb200_exact* s, uint32_t out[6]) {
+  out[0] = s->dims[0];
+  out[1] = s->dims[1];
+  out[2] = s->dims[2];
+  out[3] = s->dims[3];
+  out[4] = s->dims[4];
+  out[5] = s->dims[8];
+}
+int qb200_exact_region_bytes(const qb200_exact* s, int32_t min_log_alpha, uint32_t region, uint32_t dimension,
+                             uint32_t* bytes) {
+  int32_t st = 0;
+  *bytes = hostsim_exact_region_bytes(s->h, min_log_alpha, region, dimension, &st);
+  if (st == 3) {
+    g_err = "exact sampler: region outside the sampler's range";
+    return -50;
+  }
+  if (st) {
+    g_err = "exact sampler: a bound within 2^-64 of a half-integer";
+    return -51;
+  }
+  return 0;
+}
+
+int qb200_diagk_sample_drawn(qb200_diagk* s, qb200_exact* ex, uint32_t n, const qb200_exact_region* regions,
+                             const uint32_t* t_r, const uint8_t* stream, uint64_t stream_len, const int32_t* eta,
+                             const long double* pivot, uint32_t delta_bound, uint32_t* k, double* x_hi,
+                             double* x_lo, int64_t* delta, int32_t* status, int32_t* exact_status) {
+  const uint32_t wa = ex->dims[0], wn = ex->dims[1], kappa_r = ex->dims[4];
+  std::vector<uint32_t> alpha((size_t)n * wa), j((size_t)n * wn);
+  std::vector<int32_t> neg(n);
+  hostsim_exact_alpha(ex->h, n, regions, kappa_r, stream, stream_len, alpha.data(), neg.data(), exact_status);
+  hostsim_exact_jk(ex->h, 0, n, nullptr, nullptr, alpha.data(), neg.data(), kappa_r ? t_r : nullptr, j.data(),
+                   nullptr);
+  return qb200_diagk_sample(s, n, j.data(), eta, pivot, delta_bound, k, x_hi, x_lo, delta, status);
+}
 
 // ---- integrators and the resident distribution: HOST-LOGIC stand-ins -------------------------------
 // The slice integrators return SYNTHETIC cells here: a pure function of the coordinate, the
