@@ -657,6 +657,125 @@ def diagk_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, sigma=5, l=M, 
     return res
 
 
+def exact_section(ctx, qb, torch, stream, cpu_baseline=True, m=M, l=M, dim=256, n=1024 * 148, seed=13):
+    """The exact samplers (first half): sample_alpha_from_region for the two
+    arguments of `n` samples followed by sample_j_k_from_alpha_d_r, m = 2048, s = 1 (src/sample.cpp:78-158,
+    275-352; the two halves of distribution_sample_pair_j_k, src/distribution.cpp:615-680, around the
+    reference's lattice_alpha_map). Kernel times from CUDA events on the launching stream (recorded
+    inside the library around k_exact_alpha / k_exact_jk), the synchronous C ABI with host rows and
+    host random bytes, a sub-sample checked against the reference's own functions on one host core
+    (when oracle/_ref is on the box)."""
+    import random
+    prng = random.Random(seed)
+    r = (1 << (m - 1)) + 1 + 2 * prng.randrange((1 << (m - 2)) - 1)          # odd: kappa_r = 0
+    d = (r // 2 + prng.randrange(r // 2)) | 1
+    S = qb.ExactSampler(qb.Parameters(m=m, s=0, d=d, r=r, l=l), dim, 0, ctx)
+    rng = np.random.default_rng(seed)
+    L = qb.lib()
+    # regions as a generator's slices give them: |log alpha| on [m - 30, m + 10), uniform region index
+    e = rng.integers(m - 30, m + 10, size=2 * n)
+    sign = np.where(rng.integers(0, 2, size=2 * n) == 1, -1, 1)
+    reg = rng.integers(0, dim, size=2 * n)
+    nbytes_of = {}
+    g = np.zeros(2 * n, dtype=qb.EXACT_REGION_DTYPE)
+    g["min_log_alpha"] = sign * e
+    g["region"] = reg
+    g["dimension"] = dim
+    lens = np.zeros(2 * n, dtype=np.uint32)
+    for i in range(2 * n):
+        key = (int(e[i]), int(reg[i]))
+        v = nbytes_of.get(key)
+        if v is None:
+            v, st = S.region_bytes(key[0], key[1], dim)
+            assert st == 0
+            nbytes_of[key] = v
+        lens[i] = v
+    g["length"] = lens
+    g["offset"] = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+    stream_bytes = rng.integers(0, 256, size=int(lens.sum()), dtype=np.uint8)
+    alpha = np.zeros((2 * n, S.wa), dtype=np.uint32)
+    neg = np.zeros(2 * n, dtype=np.int32)
+    st = np.zeros(2 * n, dtype=np.int32)
+    j = np.zeros((n, S.wn), dtype=np.uint32)
+    k = np.zeros((n, S.wk), dtype=np.uint32)
+    launches0 = ctx.launch_count
+
+    def call():
+        t0 = time.perf_counter()
+        rc = L.qb200_exact_alpha(S.h, 2 * n, g.ctypes.data, 0, stream_bytes.ctypes.data, len(stream_bytes),
+                                 alpha.ctypes.data, neg.ctypes.data, st.ctypes.data)
+        assert rc == 0, qb.host._err()
+        ms_a = S.kernel_ms()[0]
+        rc = L.qb200_exact_j_k(S.h, 1, n, alpha[:n].ctypes.data, neg[:n].ctypes.data, alpha[n:].ctypes.data,
+                               neg[n:].ctypes.data, None, j.ctypes.data, k.ctypes.data)
+        assert rc == 0, qb.host._err()
+        return time.perf_counter() - t0, ms_a, S.kernel_ms()[1]
+
+    runs = [call() for _ in range(4)]
+    launches = (ctx.launch_count - launches0) // 4
+    wall = float(np.median([q[0] for q in runs[1:]]))
+    ms_a = float(np.median([q[1] for q in runs[1:]]))
+    ms_jk = float(np.median([q[2] for q in runs[1:]]))
+    assert int(st.max()) == 0
+    # 32-bit multiply-adds of the truncated products (exact.cuh): alpha_r (wa limbs) times the inverse of r
+    # (wn limbs), columns 0 .. wn - 1; j (wn limbs) times d (wd limbs), columns 0 .. wn - 1
+    wd = (d.bit_length() + 31) // 32
+    mads = sum(min(c_ + 1, S.wa) for c_ in range(S.wn)) + sum(min(c_ + 1, wd) for c_ in range(S.wn))
+    # the alpha launch did 2 n samples; the k_exact_jk launch n
+    ms = ms_a + ms_jk
+    res = {"workload": f"2 x sample_alpha_from_region + sample_j_k_from_alpha_d_r, m={m} l={l} dimension={dim}: "
+                       f"{n} (j, k) pairs",
+           "samples_per_call": n, "value": n / ms * 1e3, "unit": "samples/s", "ms": ms,
+           "ms_k_exact_alpha": ms_a, "ms_k_exact_jk": ms_jk, "gpu_launches": int(launches),
+           "roofline": {"bound": "integer issue", "imad_per_sample": mads,
+                        "achieved": mads * n / ms_jk * 1e3 / 1e12, "unit": "T multiply-add/s",
+                        "kernel": "k_exact_jk",
+                        "limiter": "instruction issue, as k_diagk (the same four-column products, mul_columns)"},
+           "e2e": {"value": n / wall, "unit": "samples/s", "ms": wall * 1e3,
+                   "h2d_bytes_per_step": int(g.nbytes + stream_bytes.nbytes + alpha.nbytes + neg.nbytes),
+                   "d2h_bytes_per_step": int(alpha.nbytes + neg.nbytes + st.nbytes + j.nbytes + k.nbytes),
+                   "api": "qb200_exact_alpha + qb200_exact_j_k (host rows and host random bytes in; alpha, j, k out)"}}
+    if cpu_baseline:
+        try:
+            from oracle import ref as R
+            if not R.available():
+                raise RuntimeError("oracle/_ref not on this box")
+            P = R.RefParameters(m, 0, d, r, l=l) if False else R.RefParameters(m, 1, d, r)
+            sub = np.random.default_rng(3).choice(n, 200, replace=False)
+            li = lambda row: int.from_bytes(np.ascontiguousarray(row).tobytes(), "little")
+            seed32 = bytes(range(32))
+            cnt, same, t0 = 0, True, time.perf_counter()
+            for i in sub:
+                got_alpha = []
+                for q in (i, n + i):
+                    # a Random_State that delivers exactly this sample's bytes does not exist: the reference
+                    # draws from its own generator, so the comparison runs the other way round -- its bytes
+                    # are handed to the GPU below; here only the timing and the (j, k) arithmetic are taken
+                    got_alpha.append((-1 if neg[q] else 1) * li(alpha[q]))
+                rs_ = R.RefRandom(seed32)
+                R.sample_alpha_from_region(float(sign[i] * (e[i] + reg[i] / dim)),
+                                           float(sign[i] * (e[i] + (reg[i] + 1) / dim)), 0, rs_)
+                R.sample_alpha_from_region(float(sign[n + i] * (e[n + i] + reg[n + i] / dim)),
+                                           float(sign[n + i] * (e[n + i] + (reg[n + i] + 1) / dim)), 0, rs_)
+                jj, kk = R.sample_j_k(1, P, got_alpha[0], got_alpha[1], rs_)
+                same = same and jj == li(j[i]) and kk == li(k[i])
+                cnt += 1
+                if time.perf_counter() - t0 > 10:
+                    break
+            dt = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": cnt / dt, "unit": "samples/s", "cores": 1, "kind": "reference",
+                                   "sample": f"{cnt} x (two calls of the reference's sample_alpha_from_region and one "
+                                             f"of sample_j_k_from_alpha_d_r on the same regions), {dt:.1f} s"}
+            res["parity"] = (f"{cnt} pairs against the reference's sample_j_k_from_alpha_d_r on the GPU's alpha: "
+                             f"j and k identical: {bool(same)} (alpha itself against the reference on the same "
+                             f"Random_State stream: tests/test_exact.py)")
+        except Exception as exc:  # pragma: no cover
+            res["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference",
+                                   "sample": f"unavailable: {exc}"}
+    S.close()
+    return res
+
+
 def sampler_cells(sampler):
     import qunundrum_b200 as qb
     return int(qb.lib().qb200_sampler_cells(sampler.h))
@@ -1259,6 +1378,9 @@ def run_ours(args, rank, world, local_rank):
     diagk = None
     if world == 1 and not args.no_tau:
         diagk = diagk_section(ctx, qb, torch, stream, cpu_baseline=not args.no_cpu_baseline)
+    exact = None
+    if world == 1 and not args.no_tau:
+        exact = exact_section(ctx, qb, torch, stream, cpu_baseline=not args.no_cpu_baseline)
     if R["hptr"]:
         L.qb200_host_free(C.c_void_p(R["hptr"]))
     if dist is not None:
@@ -1301,6 +1423,9 @@ def run_ours(args, rank, world, local_rank):
         if diagk:
             compact["diagk"] = {"samples_per_s": diagk["value"], "e2e_samples_per_s": diagk["e2e"]["value"],
                                 "cpu_samples_per_s": (diagk.get("cpu_baseline") or {}).get("value")}
+        if exact:
+            compact["exact"] = {"samples_per_s": exact["value"], "e2e_samples_per_s": exact["e2e"]["value"],
+                                "cpu_samples_per_s": (exact.get("cpu_baseline") or {}).get("value")}
         if saturation:
             compact["saturation"] = {"cells_per_s": saturation["value"], "ms": saturation["ms_per_step"],
                                      "e2e_cells_per_s": saturation["e2e"]["value"]}
@@ -1349,6 +1474,7 @@ def run_ours(args, rank, world, local_rank):
             "text": text,
             "tau": tau,
             "diagk": diagk,
+            "exact": exact,
         }
         print(json.dumps(line))
     try:

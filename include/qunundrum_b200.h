@@ -477,6 +477,11 @@ void qb200_exact_destroy(qb200_exact *sampler);
 /* out: alpha_limbs, j_limbs, k_limbs, kappa_d, kappa_r, emax. */
 void qb200_exact_dims(const qb200_exact *sampler, uint32_t out[6]);
 
+/* Duration of the LAST k_exact_alpha (out[0]) and k_exact_jk (out[1]) launch in milliseconds, from
+ * CUDA events recorded around them on the launching stream (for benchmarks; a call of more than
+ * ~300,000 samples is several launches and this is the last one's). */
+int qb200_exact_kernel_ms(qb200_exact *sampler, float out[2]);
+
 /* One region of a slice as distribution_slice_region_coordinates (src/distribution_slice.cpp:130-165)
  * and its linear / diagonal twins give it: |log alpha| on [e + region / dimension,
  * e + (region + 1) / dimension] with e = |min_log_alpha|, the slice's coordinate, whose sign is

@@ -63,6 +63,13 @@ from .host import (  # noqa: F401
     int_to_limbs,
     limbs_to_int,
     sample_k_from_diagonal_j_eta_pivot,
+    # the exact samplers (first half; src/sample.cpp:78-410)
+    EXACT_DIAGONAL,
+    EXACT_REGION_DTYPE,
+    EXACT_TWO_DIMENSIONAL,
+    ExactSampler,
+    diagonal_sample_drawn,
+    pack_regions,
 )
 from . import host  # noqa: F401,E402
 

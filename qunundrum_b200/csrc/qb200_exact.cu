@@ -33,6 +33,13 @@ struct qb200_exact {
   ExactConst dev;  // pointers into `consts` / `table`
   DBuf consts, table, regions, bytes, scratch, rows, a_d, a_r, neg_d, neg_r, status, t, k, j;
   uint32_t chunk = 0;
+  // CUDA events around the last k_exact_alpha [0, 1] and k_exact_jk [2, 3] launch (qb200_exact_kernel_ms)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timed[2] = {false, false};
+  ~qb200_exact() {
+    for (int i = 0; i < 4; i++)
+      if (ev[i]) cudaEventDestroy(ev[i]);
+  }
 };
 
 namespace {
@@ -79,9 +86,12 @@ int launch_alpha(qb200_exact* s, uint32_t B, const qb200_exact_region* regions, 
       s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * exact_alpha_scratch_limbs(c) * 4))
     return -100;
   QD_CUDA(cudaMemcpyAsync(s->regions.p, regions, (size_t)B * sizeof(ExactRegion), cudaMemcpyHostToDevice, st));
+  QD_CUDA(cudaEventRecord(s->ev[0], st));
   k_exact_alpha<<<grid, QB_DIAGK_CTA, 0, st>>>(s->dev, s->regions.as<ExactRegion>(), kappa, d_stream,
                                                (unsigned long long)stream_len, B, s->scratch.as<uint32_t>(),
                                                alphaT.as<uint32_t>(), neg.as<int32_t>(), s->status.as<int32_t>());
+  QD_CUDA(cudaEventRecord(s->ev[1], st));
+  s->timed[0] = true;
   *s->launches += 1;
   QD_CUDA(cudaGetLastError());
   return 0;
@@ -94,8 +104,11 @@ int launch_jk(qb200_exact* s, int mode, uint32_t B, const uint32_t* adT, const i
   const uint32_t grid = tiles_of(B);
   if (s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * exact_jk_scratch_limbs(c) * 4)) return -100;
   const size_t shmem = (size_t)exact_const_words(c) * 4;
+  QD_CUDA(cudaEventRecord(s->ev[2], st));
   k_exact_jk<<<grid, QB_DIAGK_CTA, shmem, st>>>(s->dev, mode, adT, neg_d, arT, neg_r, tT, tl, kT, B,
                                                 s->scratch.as<uint32_t>(), jT);
+  QD_CUDA(cudaEventRecord(s->ev[3], st));
+  s->timed[1] = true;
   *s->launches += 1;
   QD_CUDA(cudaGetLastError());
   return 0;
@@ -187,6 +200,7 @@ int qb200_exact_create(qb200_context* ctx, const qb200_params* params, int kind,
   size_t b = (size_t)cv.sm_count * 2048;
   while (b > 4096 && b * per > ((size_t)1 << 30)) b /= 2;
   s->chunk = (uint32_t)(b / QB_DIAGK_CTA * QB_DIAGK_CTA);
+  for (int i = 0; i < 4; i++) QD_CUDA(cudaEventCreate(&s->ev[i]));
   *out = s.release();
   return 0;
 }
@@ -206,6 +220,18 @@ void qb200_exact_dims(const qb200_exact* s, uint32_t out[6]) {
   out[3] = c.kappa_d;
   out[4] = c.kappa_r;
   out[5] = c.emax;
+}
+
+int qb200_exact_kernel_ms(qb200_exact* s, float out[2]) {
+  if (!s || !out) return set_error(-1, "null argument");
+  QD_CUDA(cudaSetDevice(s->device));
+  for (int i = 0; i < 2; i++) {
+    out[i] = 0.0f;
+    if (!s->timed[i]) continue;
+    QD_CUDA(cudaEventSynchronize(s->ev[2 * i + 1]));
+    QD_CUDA(cudaEventElapsedTime(&out[i], s->ev[2 * i], s->ev[2 * i + 1]));
+  }
+  return 0;
 }
 
 int qb200_exact_region_bytes(const qb200_exact* s, int32_t min_log_alpha, uint32_t region, uint32_t dimension,

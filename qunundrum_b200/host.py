@@ -148,6 +148,7 @@ def lib():
     L.qb200_exact_destroy.argtypes = [vp]
     L.qb200_exact_dims.argtypes = [vp, vp]
     L.qb200_exact_dims.restype = None
+    L.qb200_exact_kernel_ms.argtypes = [vp, vp]
     L.qb200_exact_region_bytes.argtypes = [vp, C.c_int32, u32, u32, C.POINTER(u32)]
     L.qb200_exact_alpha.argtypes = [vp, u32, vp, u32, vp, C.c_uint64, vp, vp, vp]
     L.qb200_exact_j_k.argtypes = [vp, C.c_int, u32, vp, vp, vp, vp, vp, vp, vp]
@@ -1166,6 +1167,12 @@ class ExactSampler:
             self.close()
         except Exception:
             pass
+
+    def kernel_ms(self):
+        """(k_exact_alpha, k_exact_jk): CUDA-event durations of the last launches, milliseconds."""
+        out = (C.c_float * 2)()
+        _check(lib().qb200_exact_kernel_ms(self.h, out), "qb200_exact_kernel_ms")
+        return float(out[0]), float(out[1])
 
     def region_bytes(self, min_log_alpha: int, region: int, dimension: int):
         """(bytes random_generate_mpz reads, status) -- status 0, 2 (ambiguous) or 3 (unsupported)."""
