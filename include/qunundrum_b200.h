@@ -461,7 +461,7 @@ int qb200_diagk_h(qb200_diagk *sampler, uint32_t n, const double *x_hi, const do
  * linear distributions); QB200_EXACT_DIAGONAL: n = m + sigma, no k (Diagonal_Parameters; k comes
  * from qb200_diagk). dimension_max: the largest slice dimension, a power of two <= 16384. emax:
  * bounds up to 2^emax (0: m + 64; |alpha| < 2^emax travels in alpha_limbs = ceil((emax + 1) / 32)
- * words). Limits: m >= 64, n <= 32768, kappa_d, kappa_r <= 64.
+ * words). Limits: m >= 8, n <= 32768, kappa_d, kappa_r <= 64, regions with |min_log_alpha| >= 8.
  *
  * Integers travel as little-endian 32-bit words, one row per sample, zero padded: |alpha| in
  * alpha_limbs words with the sign apart (negative[i] = 1: alpha < 0), j in j_limbs = ceil(n / 32)
@@ -497,7 +497,7 @@ typedef struct qb200_exact_region {
 #define QB200_EXACT_OK 0
 #define QB200_EXACT_LENGTH 1      /* length is not what random_generate_mpz reads for this region */
 #define QB200_EXACT_AMBIGUOUS 2   /* a bound within 2^-64 of a half-integer (never observed) */
-#define QB200_EXACT_UNSUPPORTED 3 /* |min_log_alpha| < 64 or >= emax, dimension not a power of two
+#define QB200_EXACT_UNSUPPORTED 3 /* |min_log_alpha| < 8 or >= emax, dimension not a power of two
                                    * up to dimension_max, region >= dimension */
 
 /* The bytes random_generate_mpz (src/random.c:158-181) reads for a sample of this region:

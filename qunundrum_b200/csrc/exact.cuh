@@ -21,8 +21,8 @@
 //     than the largest e needs (exact_host.hpp). The reference's own rounding of 2^(e + i/D) to
 //     3 ceil(e + 1) bits moves the value by less than 2^(-2 e); a bound is therefore the
 //     reference's unless 2^(e + i/D) lies within 2^-64 of a half-integer, which is detected
-//     (QB_EXACT_AMBIGUOUS; never observed) -- and e >= 64 is required for that argument
-//     (QB_EXACT_UNSUPPORTED below; a generator's slices have e >= m - 400).
+//     (QB_EXACT_AMBIGUOUS; never observed). For e < 31 (toy parameters: m < 61) that argument does not
+//     hold and both of the reference's roundings are carried out as it does them (exact_bound).
 //   * v mod (max - min) with v the (bits(max - min) + 72) / 8 bytes random_generate_mpz
 //     (src/random.c:158-181) reads, big-endian: v exceeds the modulus by at most 73 bits, so the
 //     division is Knuth's algorithm D with at most four 32-bit quotient digits (exact_mod).
@@ -46,7 +46,7 @@ namespace qb200 {
 #define QB_EXACT_OK 0
 #define QB_EXACT_LENGTH 1       // the bytes given are not what random_generate_mpz reads for this modulus
 #define QB_EXACT_AMBIGUOUS 2    // a bound within 2^-64 of a half-integer: only the reference's own rounding decides
-#define QB_EXACT_UNSUPPORTED 3  // e < 64, e + 1 above the table, dimension not a power of two the table holds
+#define QB_EXACT_UNSUPPORTED 3  // e < 8, e + 1 above the table, dimension not a power of two the table holds, max = min
 
 // Guard bits of the table below the rounding position of the largest bound.
 #define QB_EXACT_GUARD 128
@@ -102,30 +102,72 @@ QHD uint32_t exact_table_bits(const uint32_t* T, uint32_t tw, uint32_t bit) {
   return (lo >> off) | (hi << (32u - off));
 }
 
-// out (wa limbs, strided) = round(2^(e + idx / D_max)), idx on [0, D_max]. Returns QB_EXACT_OK or
-// QB_EXACT_AMBIGUOUS. Requires 64 <= e and e + 1 <= emax (idx = D_max: the bound 2^(e + 1)).
+// 64 bits of the entry T from bit position `bit` upwards.
+QHD uint64_t exact_table_bits64(const uint32_t* T, uint32_t tw, uint32_t bit) {
+  return (uint64_t)exact_table_bits(T, tw, bit) | ((uint64_t)exact_table_bits(T, tw, bit + 32) << 32);
+}
+
+// Is the value within 2^-64 of the rounding boundary below bit position `pos` of T (rounding bit at
+// pos - 1)? -- all zero above a set rounding bit or all one below a clear one in the 64 bits that
+// follow (an entry is good to 2 units of 2^-P, far below).
+QHD bool exact_near_boundary(const uint32_t* T, uint32_t tw, uint32_t pos) {
+  const uint32_t round_bit = exact_table_bits(T, tw, pos - 1) & 1u;
+  const uint64_t guard = exact_table_bits64(T, tw, pos - 65);
+  return round_bit ? guard == 0ull : guard == ~0ull;
+}
+
+// Below this e the reference's own rounding of 2^(e + i/D) to 3 (e + 1) bits (src/sample.cpp:97-115:
+// precision = 3 ceil(|max_log_alpha|), mpfr_exp2 to nearest) is wider than 2^-64 and is reproduced
+// step by step instead of being argued away.
+#define QB_EXACT_SMALL_E 31
+// ... and below this one mpfr_set_d rounds the argument e + i / D itself (3 (e + 1) bits < 4 + 14 for
+// the largest dimension): not supported. |alpha| < 256 there.
+#define QB_EXACT_MIN_E 8
+
+// out (wa limbs, strided) = round(2^(e + idx / D_max)) as the reference computes it, idx on
+// [0, D_max]. Returns QB_EXACT_OK or QB_EXACT_AMBIGUOUS. Requires e + 1 <= emax (idx = D_max: the
+// bound 2^(e + 1), at the precision of the region below it: `e_region` is the region's own e).
 template <int S>
-QHD int exact_bound(const ExactConst& c, uint32_t e, uint32_t idx, uint32_t* out) {
+QHD int exact_bound(const ExactConst& c, uint32_t e_region, uint32_t e, uint32_t idx, uint32_t* out) {
   if (idx == c.table_dim) {
     e += 1;
     idx = 0;
   }
   const uint32_t* T = c.table + (size_t)idx * c.tw;
   const uint32_t sh = c.P - e;  // >= QB_EXACT_GUARD: the integer part of T 2^(e - P) starts at bit sh
-  const uint32_t round_bit = (exact_table_bits(T, c.tw, sh - 1) & 1u);
-  // the 64 bits below the rounding bit: all zero above a set rounding bit or all one below a clear
-  // one put the value within 2^-64 of a half-integer (an entry is good to 2 units of 2^-P <= 2^-128)
-  const uint32_t g1 = exact_table_bits(T, c.tw, sh - 33), g0 = exact_table_bits(T, c.tw, sh - 65);
   int status = QB_EXACT_OK;
-  if (idx != 0) {  // 2^e itself is exact
-    if (round_bit ? ((g1 | g0) == 0u) : ((g1 & g0) == 0xffffffffu)) status = QB_EXACT_AMBIGUOUS;
+  if (e_region < QB_EXACT_SMALL_E) {
+    // both roundings of the reference. mpfr_exp2 at p = 3 (e_region + 1) bits: the value has e + 1
+    // integer bits, so F = p - (e + 1) fractional bits survive, to nearest ...
+    const uint32_t F = 3 * (e_region + 1) - (e + 1);  // on [2 e_region + 1, 61]
+    const uint32_t rp = sh - F;                        // > 64: P - e >= 128 + emax - e
+    uint64_t frac = exact_table_bits64(T, c.tw, rp);   // low F bits: the fraction; above: integer bits
+    uint64_t whole = exact_table_bits64(T, c.tw, sh);  // the integer part (e + 1 <= 32 bits)
+    frac &= (F >= 64) ? ~0ull : ((1ull << F) - 1ull);
+    if (idx != 0) {  // 2^e itself is exact
+      if (exact_near_boundary(T, c.tw, rp)) status = QB_EXACT_AMBIGUOUS;
+      if (exact_table_bits(T, c.tw, rp - 1) & 1u) {
+        frac += 1;
+        if (frac >> F) {
+          frac = 0;
+          whole += 1;
+        }
+      }
+    }
+    // ... then mpfr_round: to the nearest integer, halves away from zero
+    if (F > 0 && (frac >> (F - 1)) != 0) whole += 1;
+    for (uint32_t i = 0; i < c.wa; i++) QB_L(out, i) = i == 0 ? (uint32_t)whole : (i == 1 ? (uint32_t)(whole >> 32) : 0u);
+    return status;
   }
-  uint32_t carry = round_bit;
+  // e_region >= 31: the reference's first rounding moves the value by at most 2^(-2 e - 3) < 2^-64, so
+  // round(2^(e + i/D)) is the reference's unless the value lies within 2^-64 of a half-integer
+  if (idx != 0 && exact_near_boundary(T, c.tw, sh)) status = QB_EXACT_AMBIGUOUS;
+  uint32_t carry = exact_table_bits(T, c.tw, sh - 1) & 1u;
   for (uint32_t i = 0; i < c.wa; i++) {
     const uint32_t v = exact_table_bits(T, c.tw, sh + 32u * i);
-    const uint32_t s = v + carry;
-    carry = (s < v) ? 1u : 0u;
-    QB_L(out, i) = s;
+    const uint32_t s2 = v + carry;
+    carry = (s2 < v) ? 1u : 0u;
+    QB_L(out, i) = s2;
   }
   return status;
 }
@@ -152,11 +194,18 @@ QHD uint32_t exact_bytes_for_bits(uint32_t bits) { return (bits + 64u + 8u) / 8u
 // ---- v mod M ---------------------------------------------------------------------------
 
 // V (nv limbs, strided, one more limb of room above) modulo M (wm limbs, top limb non-zero,
-// wm >= 2, one more limb of room above): Knuth's algorithm D (TAOCP 4.3.1) in 32-bit digits. The
-// remainder is left in V[0, wm); M is restored.
+// one more limb of room above): Knuth's algorithm D (TAOCP 4.3.1) in 32-bit digits. The
+// remainder is left in V[0, wm); M is restored. wm = 1: short division.
 template <int S>
 QHD void exact_mod(uint32_t* V, uint32_t nv, uint32_t* M, uint32_t wm) {
   if (nv < wm) return;
+  if (wm == 1) {  // a one-limb modulus (regions of slices at |log alpha| < ~40): short division
+    const uint64_t mod = QB_L(M, 0);
+    uint64_t rem = 0;
+    for (uint32_t i = nv; i-- > 0;) rem = ((rem << 32) | QB_L(V, i)) % mod;
+    QB_L(V, 0) = (uint32_t)rem;
+    return;
+  }
 #if defined(__CUDA_ARCH__)
   const uint32_t s = (uint32_t)__clz((int)QB_L(M, wm - 1));
 #else
@@ -220,14 +269,14 @@ template <int S>
 QHD uint32_t exact_region_modulus(const ExactConst& c, const ExactRegion& g, uint32_t* lo, uint32_t* M, int* status) {
   const uint32_t e = (uint32_t)(g.min_log_alpha < 0 ? -(int64_t)g.min_log_alpha : (int64_t)g.min_log_alpha);
   const uint32_t D = g.dimension;
-  if (g.min_log_alpha == 0 || e < 64 || e + 1 > c.emax || D == 0 || (D & (D - 1)) != 0 || D > c.table_dim ||
-      g.region >= D) {
+  // e < 8 (|alpha| < 256): the reference's precision of 3 (e + 1) bits no longer holds e + i / D itself
+  if (e < QB_EXACT_MIN_E || e + 1 > c.emax || D == 0 || (D & (D - 1)) != 0 || D > c.table_dim || g.region >= D) {
     *status = QB_EXACT_UNSUPPORTED;
     return 0;
   }
   const uint32_t step = c.table_dim / D;
-  const int s_lo = exact_bound<S>(c, e, g.region * step, lo);
-  const int s_hi = exact_bound<S>(c, e, (g.region + 1) * step, M);
+  const int s_lo = exact_bound<S>(c, e, e, g.region * step, lo);
+  const int s_hi = exact_bound<S>(c, e, e, (g.region + 1) * step, M);
   if (s_lo != QB_EXACT_OK || s_hi != QB_EXACT_OK) {
     *status = QB_EXACT_AMBIGUOUS;
     return 0;
@@ -239,8 +288,10 @@ QHD uint32_t exact_region_modulus(const ExactConst& c, const ExactRegion& g, uin
     borrow = (uint32_t)(t >> 63);
   }
   QB_L(M, c.wa) = 0;
-  *status = QB_EXACT_OK;
-  return limbs_bit_length<S>(M, c.wa);
+  const uint32_t bits = limbs_bit_length<S>(M, c.wa);
+  // max = min (tiny regions of a slice at |log alpha| < ~8): the reference divides by zero
+  *status = bits ? QB_EXACT_OK : QB_EXACT_UNSUPPORTED;
+  return bits;
 }
 
 // |alpha| (wa limbs at stride SO) of one sample; *negative = the sign. scratch:
@@ -269,7 +320,7 @@ QHD int exact_alpha(const ExactConst& c, const ExactRegion& g, uint32_t kappa, c
     }
     QB_L(V, i) = w;
   }
-  const uint32_t wm = (bits + 31) / 32;  // >= 2: bits >= 64 - log2(D) - 1
+  const uint32_t wm = (bits + 31) / 32;
   exact_mod<S>(V, nv, M, wm);             // src/random.c:179
   // alpha = min + v (src/sample.cpp:131), then the low kappa bits cleared (:133-144)
   uint32_t carry = 0;

@@ -113,8 +113,8 @@ inline int exact_prepare(int kind, uint32_t m, uint32_t l, uint32_t sigma, const
     return -2;
   }
   const uint32_t n = kind == QB_EXACT_KIND_DIAGONAL ? m + sigma : m + l;
-  if (m < 64 || n <= m || n > (1u << 15) || r.bit_length() > n || d.bit_length() > n) {
-    *err = "exact sampler: need m >= 64, l (sigma) > 0, m + l (m + sigma) <= 32768, d, r < 2^n";
+  if (m < 8 || n <= m || n > (1u << 15) || r.bit_length() > n || d.bit_length() > n) {
+    *err = "exact sampler: need m >= 8, l (sigma) > 0, m + l (m + sigma) <= 32768, d, r < 2^n";
     return -3;
   }
   if (dimension_max == 0 || (dimension_max & (dimension_max - 1)) != 0 || dimension_max > (1u << 14)) {
@@ -138,8 +138,8 @@ inline int exact_prepare(int kind, uint32_t m, uint32_t l, uint32_t sigma, const
   c.wk = (c.kbits + 31) / 32;
   if (emax == 0) emax = m + 64;
   if (emax > n) emax = n;
-  if (emax < 66) {
-    *err = "exact sampler: emax below 66";
+  if (emax < 8) {
+    *err = "exact sampler: emax below 8";
     return -3;
   }
   c.emax = emax;

@@ -249,7 +249,7 @@ int qb200_exact_region_bytes(const qb200_exact* s, int32_t min_log_alpha, uint32
   const uint32_t bits = exact_region_modulus<1>(c, g, lo.data(), M.data(), &st);
   *bytes = 0;
   if (st == QB_EXACT_UNSUPPORTED)
-    return set_error(-50, "exact sampler: region outside the sampler's range (|min_log_alpha| < 64 or above emax, "
+    return set_error(-50, "exact sampler: region outside the sampler's range (|min_log_alpha| < 8 or above emax, "
                           "dimension not a power of two up to the table's)");
   if (st != QB_EXACT_OK) return set_error(-51, "exact sampler: a bound within 2^-64 of a half-integer");
   *bytes = exact_bytes_for_bits(bits);

@@ -652,6 +652,14 @@ def test_tau_diagonal_dropin_host_logic_on_the_cpu_shim():
                 assert out["worst_tau_difference"] <= 2.0 ** -58
                 failed += out["failed_estimates"]
         assert failed > 40          # the replay path was taken
+    with tempfile.TemporaryDirectory() as t:
+        # m = 64: slices at |log alpha_r| from 34, where the bounds of a region carry the reference's own
+        # rounding of 2^x to 3 (e + 1) bits (exact.cuh, exact_bound)
+        dist = _generate_diagonal("ref", t, ["-dim", "128", "-eta-bound", "2", "-det", "64", "6", "2"], np_=9)
+        for seed, (n, est, db, eb) in enumerate([(2, 300, 1000, 2), (3, 200, 1, 1)]):
+            for batch in (1, 50):
+                out = _check(exe, dist, n, est, db, eb, seed + 1, batch)
+                assert out["worst_tau_difference"] <= 2.0 ** -58
 
 
 @pytest.mark.gpu
