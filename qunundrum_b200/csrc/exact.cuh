@@ -172,18 +172,20 @@ QHD int exact_bound(const ExactConst& c, uint32_t e_region, uint32_t e, uint32_t
   return status;
 }
 
+QHD uint32_t qb_clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)v);
+#else
+  return v ? (uint32_t)__builtin_clz(v) : 32u;
+#endif
+}
+
 // Bit length of a strided number of n limbs.
 template <int S>
 QHD uint32_t limbs_bit_length(const uint32_t* p, uint32_t n) {
   for (uint32_t i = n; i-- > 0;) {
     const uint32_t v = QB_L(p, i);
-    if (v) {
-#if defined(__CUDA_ARCH__)
-      return 32u * i + (32u - (uint32_t)__clz((int)v));
-#else
-      return 32u * i + (32u - (uint32_t)__builtin_clz(v));
-#endif
-    }
+    if (v) return 32u * i + (32u - qb_clz32(v));
   }
   return 0;
 }
@@ -193,79 +195,91 @@ QHD uint32_t exact_bytes_for_bits(uint32_t bits) { return (bits + 64u + 8u) / 8u
 
 // ---- v mod M ---------------------------------------------------------------------------
 
-// V (nv limbs, strided, one more limb of room above) modulo M (wm limbs, top limb non-zero,
-// one more limb of room above): Knuth's algorithm D (TAOCP 4.3.1) in 32-bit digits. The
-// remainder is left in V[0, wm); M is restored. wm = 1: short division.
+// The division steps of Knuth's algorithm D (TAOCP 4.3.1) in 32-bit digits. Vn: the dividend shifted
+// left by s, nv + 1 limbs (strided); M: the divisor, wm >= 2 limbs, top limb non-zero, s = clz(top
+// limb) -- M is read shifted on the fly (one load per limb, the previous one carried) and never
+// written. On return Vn[0, wm) holds the remainder shifted left by s and Vn[wm, nv] is zero.
 template <int S>
-QHD void exact_mod(uint32_t* V, uint32_t nv, uint32_t* M, uint32_t wm) {
+QHD void exact_div_core(uint32_t* Vn, uint32_t nv, const uint32_t* M, uint32_t wm, uint32_t s) {
   if (nv < wm) return;
-  if (wm == 1) {  // a one-limb modulus (regions of slices at |log alpha| < ~40): short division
+  const uint32_t m_top = QB_L(M, wm - 1), m_next = QB_L(M, wm - 2), m_third = wm >= 3 ? QB_L(M, wm - 3) : 0u;
+  const uint64_t vtop = s ? ((m_top << s) | (m_next >> (32u - s))) : m_top;
+  const uint64_t vnext = s ? ((m_next << s) | (m_third >> (32u - s))) : m_next;
+  for (uint32_t j = nv - wm + 1; j-- > 0;) {
+    const uint64_t num = ((uint64_t)QB_L(Vn, j + wm) << 32) | QB_L(Vn, j + wm - 1);
+    uint64_t qhat = num / vtop, rhat = num % vtop;
+    const uint64_t u2 = QB_L(Vn, j + wm - 2);
+    while ((qhat >> 32) != 0 || qhat * vnext > ((rhat << 32) | u2)) {
+      qhat--;
+      rhat += vtop;
+      if ((rhat >> 32) != 0) break;
+    }
+    if (qhat == 0) continue;
+    // Vn[j, j + wm] -= qhat (M << s)
+    uint64_t carry = 0;
+    uint32_t borrow = 0, prev = 0;
+    for (uint32_t i = 0; i < wm; i++) {
+      const uint32_t cur = QB_L(M, i);
+      const uint32_t mn = s ? ((cur << s) | (prev >> (32u - s))) : cur;
+      prev = cur;
+      const uint64_t p = qhat * (uint64_t)mn + carry;
+      carry = p >> 32;
+      const uint64_t t = (uint64_t)QB_L(Vn, i + j) - (uint32_t)p - borrow;
+      QB_L(Vn, i + j) = (uint32_t)t;
+      borrow = (uint32_t)(t >> 63);
+    }
+    const uint64_t t = (uint64_t)QB_L(Vn, j + wm) - carry - borrow;
+    QB_L(Vn, j + wm) = (uint32_t)t;
+    if (t >> 63) {  // qhat was one too large: add M << s back
+      uint64_t c2 = 0;
+      prev = 0;
+      for (uint32_t i = 0; i < wm; i++) {
+        const uint32_t cur = QB_L(M, i);
+        const uint32_t mn = s ? ((cur << s) | (prev >> (32u - s))) : cur;
+        prev = cur;
+        c2 += (uint64_t)QB_L(Vn, i + j) + mn;
+        QB_L(Vn, i + j) = (uint32_t)c2;
+        c2 >>= 32;
+      }
+      QB_L(Vn, j + wm) += (uint32_t)c2;
+    }
+  }
+}
+
+// V (nv limbs, strided, one more limb of room above) modulo M (wm limbs, top limb non-zero): the
+// remainder is left in V[0, wm). wm = 1: short division. (The general form, for the tests and for
+// callers that hold V unshifted; exact_alpha shifts while it imports the bytes.)
+template <int S>
+QHD void exact_mod(uint32_t* V, uint32_t nv, const uint32_t* M, uint32_t wm) {
+  if (nv < wm) return;
+  if (wm == 1) {  // a one-limb modulus (regions of slices at |log alpha| < ~40)
     const uint64_t mod = QB_L(M, 0);
     uint64_t rem = 0;
     for (uint32_t i = nv; i-- > 0;) rem = ((rem << 32) | QB_L(V, i)) % mod;
     QB_L(V, 0) = (uint32_t)rem;
     return;
   }
-#if defined(__CUDA_ARCH__)
-  const uint32_t s = (uint32_t)__clz((int)QB_L(M, wm - 1));
-#else
-  const uint32_t s = (uint32_t)__builtin_clz(QB_L(M, wm - 1));
-#endif
-  // normalise: M <<= s (top bit set), V <<= s (limb nv receives the bits shifted out)
+  const uint32_t s = qb_clz32(QB_L(M, wm - 1));
   if (s) {
-    for (uint32_t i = wm; i-- > 1;) QB_L(M, i) = (QB_L(M, i) << s) | (QB_L(M, i - 1) >> (32u - s));
-    QB_L(M, 0) <<= s;
     QB_L(V, nv) = QB_L(V, nv - 1) >> (32u - s);
     for (uint32_t i = nv; i-- > 1;) QB_L(V, i) = (QB_L(V, i) << s) | (QB_L(V, i - 1) >> (32u - s));
     QB_L(V, 0) <<= s;
   } else {
     QB_L(V, nv) = 0;
   }
-  const uint64_t vtop = QB_L(M, wm - 1), vnext = QB_L(M, wm - 2);
-  for (uint32_t j = nv - wm + 1; j-- > 0;) {
-    const uint64_t num = ((uint64_t)QB_L(V, j + wm) << 32) | QB_L(V, j + wm - 1);
-    uint64_t qhat = num / vtop, rhat = num % vtop;
-    const uint64_t u2 = QB_L(V, j + wm - 2);
-    while ((qhat >> 32) != 0 || qhat * vnext > ((rhat << 32) | u2)) {
-      qhat--;
-      rhat += vtop;
-      if ((rhat >> 32) != 0) break;
-    }
-    // V[j, j + wm] -= qhat M
-    uint64_t carry = 0;
-    uint32_t borrow = 0;
-    for (uint32_t i = 0; i < wm; i++) {
-      const uint64_t p = qhat * (uint64_t)QB_L(M, i) + carry;
-      carry = p >> 32;
-      const uint64_t t = (uint64_t)QB_L(V, i + j) - (uint32_t)p - borrow;
-      QB_L(V, i + j) = (uint32_t)t;
-      borrow = (uint32_t)(t >> 63);
-    }
-    const uint64_t t = (uint64_t)QB_L(V, j + wm) - carry - borrow;
-    QB_L(V, j + wm) = (uint32_t)t;
-    if (t >> 63) {  // qhat was one too large: add M back
-      uint64_t c2 = 0;
-      for (uint32_t i = 0; i < wm; i++) {
-        c2 += (uint64_t)QB_L(V, i + j) + QB_L(M, i);
-        QB_L(V, i + j) = (uint32_t)c2;
-        c2 >>= 32;
-      }
-      QB_L(V, j + wm) += (uint32_t)c2;
-    }
-  }
+  exact_div_core<S>(V, nv, M, wm, s);
   if (s) {
     for (uint32_t i = 0; i + 1 < wm; i++) QB_L(V, i) = (QB_L(V, i) >> s) | (QB_L(V, i + 1) << (32u - s));
     QB_L(V, wm - 1) >>= s;
-    for (uint32_t i = 0; i + 1 < wm; i++) QB_L(M, i) = (QB_L(M, i) >> s) | (QB_L(M, i + 1) << (32u - s));
-    QB_L(M, wm - 1) >>= s;
   }
 }
 
 // ---- alpha from a region (sample_alpha_from_region, src/sample.cpp:78-158) -----------------
 
-// bits(max - min) of a region, or 0 with *status set; M (wa + 1 limbs, strided) = max - min,
-// lo (wa limbs, strided) = min.
-template <int S>
+// bits(max - min) of a region, or 0 with *status set; M (wa + 1 limbs at stride S) = max - min,
+// lo (wa limbs at stride SL) = min. One pass: both table rows are read a word per limb (the previous
+// word carried), rounded, subtracted and stored.
+template <int S, int SL>
 QHD uint32_t exact_region_modulus(const ExactConst& c, const ExactRegion& g, uint32_t* lo, uint32_t* M, int* status) {
   const uint32_t e = (uint32_t)(g.min_log_alpha < 0 ? -(int64_t)g.min_log_alpha : (int64_t)g.min_log_alpha);
   const uint32_t D = g.dimension;
@@ -275,23 +289,71 @@ QHD uint32_t exact_region_modulus(const ExactConst& c, const ExactRegion& g, uin
     return 0;
   }
   const uint32_t step = c.table_dim / D;
-  const int s_lo = exact_bound<S>(c, e, e, g.region * step, lo);
-  const int s_hi = exact_bound<S>(c, e, e, (g.region + 1) * step, M);
-  if (s_lo != QB_EXACT_OK || s_hi != QB_EXACT_OK) {
-    *status = QB_EXACT_AMBIGUOUS;
-    return 0;
-  }
-  uint32_t borrow = 0;
-  for (uint32_t i = 0; i < c.wa; i++) {  // src/sample.cpp:126-128
-    const uint64_t t = (uint64_t)QB_L(M, i) - QB_L(lo, i) - borrow;
-    QB_L(M, i) = (uint32_t)t;
-    borrow = (uint32_t)(t >> 63);
+  uint32_t top_i = 0, top_v = 0;
+  if (e < QB_EXACT_SMALL_E) {
+    // toy sizes: the bounds one after the other, with both of the reference's roundings (exact_bound)
+    const int s_lo = exact_bound<SL>(c, e, e, g.region * step, lo);
+    const int s_hi = exact_bound<S>(c, e, e, (g.region + 1) * step, M);
+    if (s_lo != QB_EXACT_OK || s_hi != QB_EXACT_OK) {
+      *status = QB_EXACT_AMBIGUOUS;
+      return 0;
+    }
+    uint32_t borrow = 0;
+    for (uint32_t i = 0; i < c.wa; i++) {  // src/sample.cpp:126-128
+      const uint64_t t = (uint64_t)QB_L(M, i) - lo[(size_t)i * SL] - borrow;
+      QB_L(M, i) = (uint32_t)t;
+      borrow = (uint32_t)(t >> 63);
+      if ((uint32_t)t) {
+        top_i = i;
+        top_v = (uint32_t)t;
+      }
+    }
+  } else {
+    uint32_t idx_lo = g.region * step, idx_hi = (g.region + 1) * step, e_hi = e;
+    if (idx_hi == c.table_dim) {  // the bound 2^(e + 1)
+      e_hi = e + 1;
+      idx_hi = 0;
+    }
+    const uint32_t* Tl = c.table + (size_t)idx_lo * c.tw;
+    const uint32_t* Th = c.table + (size_t)idx_hi * c.tw;
+    const uint32_t sl = c.P - e, sh = c.P - e_hi;  // >= QB_EXACT_GUARD
+    if ((idx_lo != 0 && exact_near_boundary(Tl, c.tw, sl)) || (idx_hi != 0 && exact_near_boundary(Th, c.tw, sh))) {
+      *status = QB_EXACT_AMBIGUOUS;
+      return 0;
+    }
+    uint32_t cl = exact_table_bits(Tl, c.tw, sl - 1) & 1u, ch = exact_table_bits(Th, c.tw, sh - 1) & 1u;
+    const uint32_t wl = sl >> 5, ol = sl & 31u, wh = sh >> 5, oh = sh & 31u;
+    uint32_t pl = wl < c.tw ? Tl[wl] : 0u, ph = wh < c.tw ? Th[wh] : 0u;
+    uint32_t borrow = 0;
+    for (uint32_t i = 0; i < c.wa; i++) {
+      const uint32_t nl = wl + i + 1 < c.tw ? Tl[wl + i + 1] : 0u, nh = wh + i + 1 < c.tw ? Th[wh + i + 1] : 0u;
+      const uint32_t vl = ol ? ((pl >> ol) | (nl << (32u - ol))) : pl;
+      const uint32_t vh = oh ? ((ph >> oh) | (nh << (32u - oh))) : ph;
+      pl = nl;
+      ph = nh;
+      const uint32_t rl = vl + cl, rh = vh + ch;  // the rounding bits rippling up
+      cl = rl < vl ? 1u : 0u;
+      ch = rh < vh ? 1u : 0u;
+      lo[(size_t)i * SL] = rl;
+      const uint64_t t = (uint64_t)rh - rl - borrow;  // src/sample.cpp:126-128
+      QB_L(M, i) = (uint32_t)t;
+      borrow = (uint32_t)(t >> 63);
+      if ((uint32_t)t) {
+        top_i = i;
+        top_v = (uint32_t)t;
+      }
+    }
   }
   QB_L(M, c.wa) = 0;
-  const uint32_t bits = limbs_bit_length<S>(M, c.wa);
+  const uint32_t bits = top_v ? 32u * top_i + (32u - qb_clz32(top_v)) : 0u;
   // max = min (tiny regions of a slice at |log alpha| < ~8): the reference divides by zero
   *status = bits ? QB_EXACT_OK : QB_EXACT_UNSUPPORTED;
   return bits;
+}
+
+// The 32-bit limb whose most significant byte is p[0] (big-endian).
+QHD uint32_t exact_load_be32(const uint8_t* p) {
+  return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
 }
 
 // |alpha| (wa limbs at stride SO) of one sample; *negative = the sign. scratch:
@@ -303,29 +365,66 @@ QHD int exact_alpha(const ExactConst& c, const ExactRegion& g, uint32_t kappa, c
   uint32_t* M = scratch + (size_t)(c.wa + 5) * S;    // wa + 1 limbs
   *negative = g.min_log_alpha < 0 ? 1 : 0;
   int status = QB_EXACT_OK;
-  // min goes to alpha_out first (the strides differ: copy element-wise)
-  uint32_t* lo = V;  // borrowed: V is filled after the modulus is known
-  const uint32_t bits = exact_region_modulus<S>(c, g, lo, M, &status);
-  for (uint32_t i = 0; i < c.wa; i++) alpha_out[(size_t)i * SO] = (status == QB_EXACT_OK) ? QB_L(lo, i) : 0u;
-  if (status != QB_EXACT_OK) return status;
-  if (g.length != exact_bytes_for_bits(bits) || g.offset + g.length > stream_len) return QB_EXACT_LENGTH;
-  // v: big-endian bytes (mpz_import(value, length, 1, 1, 1, 0, buffer), src/random.c:178)
-  const uint32_t nv = (g.length + 3) / 4;  // <= wa + 3
-  const uint8_t* b = stream + g.offset;
-  for (uint32_t i = 0; i < nv; i++) {
-    uint32_t w = 0;
-    for (uint32_t k = 0; k < 4; k++) {
-      const uint32_t pos = 4 * i + k;  // significance in bytes
-      if (pos < g.length) w |= (uint32_t)b[g.length - 1 - pos] << (8 * k);
-    }
-    QB_L(V, i) = w;
+  const uint32_t bits = exact_region_modulus<S, SO>(c, g, alpha_out, M, &status);  // alpha_out = min
+  if (status == QB_EXACT_OK && (g.length != exact_bytes_for_bits(bits) || g.offset + g.length > stream_len))
+    status = QB_EXACT_LENGTH;
+  if (status != QB_EXACT_OK) {
+    for (uint32_t i = 0; i < c.wa; i++) alpha_out[(size_t)i * SO] = 0u;
+    return status;
   }
   const uint32_t wm = (bits + 31) / 32;
-  exact_mod<S>(V, nv, M, wm);             // src/random.c:179
-  // alpha = min + v (src/sample.cpp:131), then the low kappa bits cleared (:133-144)
+  const uint32_t s = wm >= 2 ? qb_clz32(QB_L(M, wm - 1)) : 0u;  // the one-limb division is not normalised
+  // v: big-endian bytes (mpz_import(value, length, 1, 1, 1, 0, buffer), src/random.c:178), stored shifted
+  // left by s as the division wants it. Limb i = the four bytes ending 4 i bytes before the end.
+  const uint32_t nv = (g.length + 3) / 4;  // <= wa + 3
+  const uint8_t* b = stream + g.offset;
+  const uint32_t full = g.length / 4;      // limbs with all four bytes
+  uint32_t prev = 0;
+#if defined(__CUDA_ARCH__)
+  // aligned 32-bit loads: limb i lies at the byte address q - 4 i, whose alignment is the same for
+  // every i -- one aligned word per limb, the other half carried (funnel shift), then a byte swap
+  const size_t q = (size_t)(b + g.length - 4);
+  const uint32_t mis = (uint32_t)(q & 3u) * 8u;
+  const uint32_t* aw = (const uint32_t*)(q & ~(size_t)3);
+  uint32_t upper = (mis && full) ? aw[1] : 0u;  // the word above limb 0's aligned word (inside the buffer: mis != 0)
+#endif
+  for (uint32_t i = 0; i < nv; i++) {
+    uint32_t w = 0;
+    if (i < full) {
+#if defined(__CUDA_ARCH__)
+      const uint32_t lower = *(aw - i);
+      w = __byte_perm(mis ? __funnelshift_r(lower, upper, mis) : lower, 0u, 0x0123);
+      upper = lower;
+#else
+      w = exact_load_be32(b + g.length - 4 - 4 * (size_t)i);
+#endif
+    } else {
+      for (uint32_t k = 0; k < g.length - 4 * full; k++) w |= (uint32_t)b[g.length - 4 * full - 1 - k] << (8 * k);
+    }
+    QB_L(V, i) = s ? ((w << s) | (prev >> (32u - s))) : w;
+    prev = w;
+  }
+  QB_L(V, nv) = s ? (prev >> (32u - s)) : 0u;
+  if (wm >= 2) {
+    exact_div_core<S>(V, nv, M, wm, s);  // src/random.c:179
+  } else {
+    const uint64_t mod = QB_L(M, 0);
+    uint64_t rem = 0;
+    for (uint32_t i = nv; i-- > 0;) rem = ((rem << 32) | QB_L(V, i)) % mod;
+    QB_L(V, 0) = (uint32_t)rem;
+    QB_L(V, 1) = 0;
+  }
+  // alpha = min + (remainder >> s) (src/sample.cpp:131), then the low kappa bits cleared (:133-144)
   uint32_t carry = 0;
+  uint32_t cur = QB_L(V, 0);
   for (uint32_t i = 0; i < c.wa; i++) {
-    const uint64_t t = (uint64_t)alpha_out[(size_t)i * SO] + (i < wm && i < nv ? QB_L(V, i) : 0u) + carry;
+    uint32_t rem = 0;
+    if (i < wm && i < nv) {
+      const uint32_t nxt = QB_L(V, i + 1);  // limb wm of the shifted remainder is zero
+      rem = s ? ((cur >> s) | (nxt << (32u - s))) : cur;
+      cur = nxt;
+    }
+    const uint64_t t = (uint64_t)alpha_out[(size_t)i * SO] + rem + carry;
     uint32_t v = (uint32_t)t;
     carry = (uint32_t)(t >> 32);
     if (32u * i < kappa) v &= (kappa - 32u * i >= 32u) ? 0u : ~((1u << (kappa - 32u * i)) - 1u);

@@ -124,7 +124,8 @@ int exact_device(const qb200_exact* s) { return s->device; }
 
 int exact_upload_stream(qb200_exact* s, const uint8_t* stream, uint64_t stream_len, const uint8_t** d_stream,
                         cudaStream_t st) {
-  if (s->bytes.reserve(stream_len ? stream_len : 1)) return -100;
+  // k_exact_alpha reads aligned 32-bit words: up to three bytes past the last sample's end
+  if (s->bytes.reserve(stream_len + 16)) return -100;
   if (stream_len) QD_CUDA(cudaMemcpyAsync(s->bytes.p, stream, stream_len, cudaMemcpyHostToDevice, st));
   *d_stream = s->bytes.as<uint8_t>();
   return 0;
@@ -246,7 +247,7 @@ int qb200_exact_region_bytes(const qb200_exact* s, int32_t min_log_alpha, uint32
   g.length = 0;
   g.offset = 0;
   int st = 0;
-  const uint32_t bits = exact_region_modulus<1>(c, g, lo.data(), M.data(), &st);
+  const uint32_t bits = exact_region_modulus<1, 1>(c, g, lo.data(), M.data(), &st);
   *bytes = 0;
   if (st == QB_EXACT_UNSUPPORTED)
     return set_error(-50, "exact sampler: region outside the sampler's range (|min_log_alpha| < 8 or above emax, "

@@ -349,6 +349,8 @@ struct Batch {
   std::vector<long double> tau;
   std::vector<uint8_t> ok;
   size_t next = 0;
+  Random_State state_after;  // the generator as the batch left it: a caller that re-seeds or draws from it
+                             // between calls gets a new batch, not stale estimates
 } g_batch;
 
 void compute_batch(const Diagonal_Distribution* distribution, Random_State* rs, uint32_t n,
@@ -456,7 +458,8 @@ bool tau_estimate_diagonal(const Diagonal_Distribution* const distribution, Rand
   g_stats.calls++;
   Batch& b = g_batch;
   if (!(b.next < b.ok.size() && b.distribution == distribution && b.rs == random_state && b.n == n &&
-        b.delta_bound == delta_bound && b.eta_bound == eta_bound)) {
+        b.delta_bound == delta_bound && b.eta_bound == eta_bound &&
+        0 == memcmp(random_state, &b.state_after, sizeof(Random_State)))) {
     setup_for(distribution);
     const int want = env_int("QB200_TAU_BATCH", 1000);
     compute_batch(distribution, random_state, n, delta_bound, eta_bound, (uint32_t)(want > 0 ? want : 1));
@@ -466,6 +469,7 @@ bool tau_estimate_diagonal(const Diagonal_Distribution* const distribution, Rand
     b.delta_bound = delta_bound;
     b.eta_bound = eta_bound;
     b.next = 0;
+    memcpy(&b.state_after, random_state, sizeof(Random_State));
   }
   tau = b.tau[b.next];
   return b.ok[b.next++] != 0;

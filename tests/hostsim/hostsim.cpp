@@ -838,7 +838,7 @@ uint32_t hostsim_exact_region_bytes(void* hh, int32_t min_log_alpha, uint32_t re
   g.length = 0;
   g.offset = 0;
   int st = 0;
-  const uint32_t bits = exact_region_modulus<1>(c, g, lo.data(), M.data(), &st);
+  const uint32_t bits = exact_region_modulus<1, 1>(c, g, lo.data(), M.data(), &st);
   *status = st;
   return st == QB_EXACT_OK ? exact_bytes_for_bits(bits) : 0;
 }
