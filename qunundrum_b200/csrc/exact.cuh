@@ -351,6 +351,38 @@ QHD uint32_t exact_region_modulus(const ExactConst& c, const ExactRegion& g, uin
   return bits;
 }
 
+// The second half of exact_alpha: V (nv + 1 limbs, the sample's integer shifted left by s) modulo M
+// (wm limbs), and alpha_out (holding min) += remainder >> s with the low kappa bits cleared.
+template <int S, int SO>
+QHD void exact_alpha_finish(const ExactConst& c, uint32_t* V, uint32_t nv, const uint32_t* M, uint32_t wm, uint32_t s,
+                            uint32_t kappa, uint32_t* alpha_out) {
+  if (wm >= 2) {
+    exact_div_core<S>(V, nv, M, wm, s);  // src/random.c:179
+  } else {
+    const uint64_t mod = QB_L(M, 0);
+    uint64_t rem = 0;
+    for (uint32_t i = nv; i-- > 0;) rem = ((rem << 32) | QB_L(V, i)) % mod;
+    QB_L(V, 0) = (uint32_t)rem;
+    QB_L(V, 1) = 0;
+  }
+  // alpha = min + (remainder >> s) (src/sample.cpp:131), then the low kappa bits cleared (:133-144)
+  uint32_t carry = 0;
+  uint32_t cur = QB_L(V, 0);
+  for (uint32_t i = 0; i < c.wa; i++) {
+    uint32_t rem = 0;
+    if (i < wm && i < nv) {
+      const uint32_t nxt = QB_L(V, i + 1);  // limb wm of the shifted remainder is zero
+      rem = s ? ((cur >> s) | (nxt << (32u - s))) : cur;
+      cur = nxt;
+    }
+    const uint64_t t = (uint64_t)alpha_out[(size_t)i * SO] + rem + carry;
+    uint32_t v = (uint32_t)t;
+    carry = (uint32_t)(t >> 32);
+    if (32u * i < kappa) v &= (kappa - 32u * i >= 32u) ? 0u : ~((1u << (kappa - 32u * i)) - 1u);
+    alpha_out[(size_t)i * SO] = v;
+  }
+}
+
 // The 32-bit limb whose most significant byte is p[0] (big-endian).
 QHD uint32_t exact_load_be32(const uint8_t* p) {
   return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
@@ -405,31 +437,7 @@ QHD int exact_alpha(const ExactConst& c, const ExactRegion& g, uint32_t kappa, c
     prev = w;
   }
   QB_L(V, nv) = s ? (prev >> (32u - s)) : 0u;
-  if (wm >= 2) {
-    exact_div_core<S>(V, nv, M, wm, s);  // src/random.c:179
-  } else {
-    const uint64_t mod = QB_L(M, 0);
-    uint64_t rem = 0;
-    for (uint32_t i = nv; i-- > 0;) rem = ((rem << 32) | QB_L(V, i)) % mod;
-    QB_L(V, 0) = (uint32_t)rem;
-    QB_L(V, 1) = 0;
-  }
-  // alpha = min + (remainder >> s) (src/sample.cpp:131), then the low kappa bits cleared (:133-144)
-  uint32_t carry = 0;
-  uint32_t cur = QB_L(V, 0);
-  for (uint32_t i = 0; i < c.wa; i++) {
-    uint32_t rem = 0;
-    if (i < wm && i < nv) {
-      const uint32_t nxt = QB_L(V, i + 1);  // limb wm of the shifted remainder is zero
-      rem = s ? ((cur >> s) | (nxt << (32u - s))) : cur;
-      cur = nxt;
-    }
-    const uint64_t t = (uint64_t)alpha_out[(size_t)i * SO] + rem + carry;
-    uint32_t v = (uint32_t)t;
-    carry = (uint32_t)(t >> 32);
-    if (32u * i < kappa) v &= (kappa - 32u * i >= 32u) ? 0u : ~((1u << (kappa - 32u * i)) - 1u);
-    alpha_out[(size_t)i * SO] = v;
-  }
+  exact_alpha_finish<S, SO>(c, V, nv, M, wm, s, kappa, alpha_out);
   return QB_EXACT_OK;
 }
 

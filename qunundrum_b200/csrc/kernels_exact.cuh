@@ -3,7 +3,14 @@
 //
 //   k_exact_alpha   one thread per sample: the region's bounds from the table of 2^(i/D), the
 //                   modulus, the sample's bytes modulo the modulus (at most four quotient digits),
-//                   alpha = min + remainder with the low kappa bits cleared.
+//                   alpha = min + remainder with the low kappa bits cleared. Every thread walks its
+//                   OWN two table rows and its own bytes (32 sectors per load instruction of a warp):
+//                   bound by those look-ups. Measured and dropped (B200, 303,104 samples at m = 2048,
+//                   profiles/r02_exact_alpha_staged_ab.txt): the warp fetching each sample's words with
+//                   one coalesced request and handing them over transposed through shared memory --
+//                   0.55 ms against 0.39 ms (70 registers and 34 KB of shared memory per CTA leave 32 %
+//                   occupancy, and the 32 load -> store hand-overs per chunk wait on each other:
+//                   long-scoreboard 20 cycles per instruction at 21 % issue).
 //   k_exact_jk      one thread per sample: j from alpha_r (one truncated product with the inverse
 //                   of r / 2^kappa_r modulo 2^n, staged in shared memory: every thread reads the
 //                   same limb), k from (alpha_d, j) (a truncated product with d), or j from

@@ -8,6 +8,7 @@
 // the caller needs BEFORE it can hand over a sample's bytes, and runs on the host.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
