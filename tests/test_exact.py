@@ -437,3 +437,61 @@ def test_diagonal_sample_from_bytes_to_k_gpu(gpu_ctx, m, sigma, kr, count):
     assert list(est) == [0] * count
     got = [(st in (0, 2), k if st in (0, 2) else 0) for st, k in zip(status, ks)]
     assert got == want
+
+
+def check_full_size_properties(factory, m=2048, s=1, kd=0, kr=3, D=256, n=6000, seed=5):
+    """The properties the reference's own unit tests state (src/test/test_sample.cpp:97-570), at full size
+    and without the reference in the loop: alpha lies in its region with the sign of the region and is
+    divisible by 2^kappa; {r j} modulo 2^(m+l) (centred) gives alpha_r back; alpha_d - d j - 2^m k is, modulo
+    2^(m+l), a non-negative number below 2^m (zero for an admissible pair); j < 2^(m+l), k < 2^l."""
+    g = np.random.default_rng(seed)
+    d, r = d_r_with_kappa(g, m, kd, kr)
+    l = -(-m // s)
+    ex = factory(0, m, l, 0, d, r, D)
+    nmod = 1 << (m + l)
+    stream = g.bytes(2 * n * ((ex.emax + 80) // 8 + 8))
+    regs, off = [], 0
+    for _ in range(2 * n):
+        e = int(g.integers(m - 30, m + 10))
+        sign = -1 if g.integers(2) else 1
+        reg = int(g.integers(0, D))
+        nb, st = ex.region_bytes(sign * e, reg, D)
+        assert st == 0
+        regs.append((sign * e, reg, D, off, nb))
+        off += nb
+    a_d, st_d = ex.alpha(regs[:n], kd, stream)
+    a_r, st_r = ex.alpha(regs[n:], kr, stream)
+    assert not st_d.any() and not st_r.any()
+    bounds = {}
+
+    def bound(e, i):
+        if (e, i) not in bounds:
+            with mp.workprec(e + 200):
+                bounds[(e, i)] = int(mp.nint(mp.mpf(2) ** (mp.mpf(e) + mp.mpf(i) / D)))
+        return bounds[(e, i)]
+
+    for alphas, rg, kap in ((a_d, regs[:n], kd), (a_r, regs[n:], kr)):
+        for a, (se, reg, _, _, _) in zip(alphas, rg):
+            assert (a < 0) == (se < 0)
+            lo, hi = bound(abs(se), reg), bound(abs(se), reg + 1)
+            # clearing the low kappa bits can take alpha below min by less than 2^kappa, as in the reference
+            assert lo - (1 << kap) < abs(a) < hi
+            assert abs(a) % (1 << kap) == 0
+    ts = [int(x) for x in g.integers(0, 1 << kr, n)] if kr else None
+    js, ks = ex.j_k_from_alpha_d_r(a_d, a_r, ts)
+    half = nmod >> 1
+    for ad, ar, j, k in zip(a_d, a_r, js, ks):
+        assert 0 <= j < nmod and 0 <= k < (1 << l)
+        v = (r * j) % nmod
+        assert (v - nmod if v >= half else v) == ar      # src/test/test_sample.cpp:519-527
+        assert (ad - d * j - (k << m)) % nmod < (1 << m)  # :507-516 for a pair that need not be admissible
+
+
+def test_full_size_properties_on_the_cpu_twin():
+    check_full_size_properties(twin_factory, n=300)
+
+
+@pytest.mark.gpu
+def test_full_size_properties_gpu(gpu_ctx):
+    check_full_size_properties(gpu_factory(gpu_ctx), n=6000)
+    check_full_size_properties(gpu_factory(gpu_ctx), m=2048, s=8, kd=2, kr=0, D=2048, n=3000, seed=6)
