@@ -22,11 +22,11 @@ struct DiagKHost {
 };
 
 // x as n limbs with the zero limbs mul_columns reads around a constant operand.
-inline std::vector<uint32_t> limbs32_padded(const BigUInt& x, size_t n) {
-  std::vector<uint32_t> out(n + 2 * QB_DIAGK_PAD, 0);
+inline std::vector<uint32_t> limbs32_padded(const BigUInt& x, size_t n, size_t pad = QB_DIAGK_PAD) {
+  std::vector<uint32_t> out(n + 2 * pad, 0);
   for (size_t i = 0; i < n; i++) {
     const size_t w = i / 2;
-    if (w < x.w.size()) out[QB_DIAGK_PAD + i] = (uint32_t)(x.w[w] >> (32 * (i % 2)));
+    if (w < x.w.size()) out[pad + i] = (uint32_t)(x.w[w] >> (32 * (i % 2)));
   }
   return out;
 }

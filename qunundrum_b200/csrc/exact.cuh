@@ -32,7 +32,7 @@
 //     mpz_mod is non-negative: bits [kappa_r, kappa_r + n) of the two's complement product).
 //   * k = floor((alpha_d - d j) / 2^m) mod 2^l: bits [m, m + l) of alpha_d - d j in two's
 //     complement, from the low m + l bits of d j: a second truncated product.
-// 32-bit limbs, products by mul_columns (diagk.cuh). Per-sample numbers are strided (S = 1 on the
+// 32-bit limbs, products by mul_columns_wide (diagk.cuh). Per-sample numbers are strided (S = 1 on the
 // host, the CTA's thread count on the device, see diagk.cuh). Integer arithmetic throughout: the
 // results are the reference's integers bit for bit.
 //
@@ -50,6 +50,9 @@ namespace qb200 {
 
 // Guard bits of the table below the rounding position of the largest bound.
 #define QB_EXACT_GUARD 128
+// Zero limbs the constant operands carry below index 0 and above their last limb (mul_columns_wide
+// with up to 8 columns at a time).
+#define QB_EXACT_PAD 7
 
 struct ExactConst {
   uint32_t m, l, sigma;
@@ -65,7 +68,7 @@ struct ExactConst {
   uint32_t table_log;  // log2(D_max)
   uint32_t tw;         // words per table entry
   uint32_t P;          // entry i = 2^(i / D_max) 2^P, truncated (error below 2 units): emax + QB_EXACT_GUARD bits
-  // each with QB_DIAGK_PAD zero limbs below index 0 and above its last limb (mul_columns):
+  // each with QB_EXACT_PAD zero limbs below index 0 and above its last limb (mul_columns_wide):
   const uint32_t* inv_r;  // wn limbs: (r / 2^kappa_r)^-1 mod 2^n
   const uint32_t* inv_d;  // wn limbs: (d / 2^kappa_d)^-1 mod 2^n
   const uint32_t* d;      // wd limbs
@@ -73,7 +76,7 @@ struct ExactConst {
 };
 
 // Words of the constants inv_r, inv_d, d with their zero limbs, in this order (shared-memory copy).
-QHD uint32_t exact_const_words(const ExactConst& c) { return 2 * (c.wn + 2 * QB_DIAGK_PAD) + (c.wd + 2 * QB_DIAGK_PAD); }
+QHD uint32_t exact_const_words(const ExactConst& c) { return 2 * (c.wn + 2 * QB_EXACT_PAD) + (c.wd + 2 * QB_EXACT_PAD); }
 
 // One region of a slice: |log alpha| on [e + region / dimension, e + (region + 1) / dimension],
 // e = |min_log_alpha| (the slice's coordinate), the sign that of min_log_alpha; the sample's bytes
@@ -498,28 +501,28 @@ QHD void exact_finish_j(const ExactConst& c, const uint32_t* P, uint32_t np, uin
 //      the first half of sample_j_k_from_alpha_d_r, :290-335, whose t_r is a multiple of
 //      2^kappa_t_r: the caller passes t already multiplied) ------------------------------------
 // a: |alpha_r|, wa limbs at stride SA. scratch: exact_jk_scratch_limbs words (strided by S).
-template <int S, int SA, int SO, int ST>
+template <int NC, int S, int SA, int SO, int ST>
 QHD void exact_j_from_alpha_r(const ExactConst& c, const uint32_t* a, int negative, const uint32_t* t,
                               uint32_t* scratch, uint32_t* j_out) {
   uint32_t* P = scratch;  // wn + 4 limbs
   const uint32_t cols = (c.n + c.kappa_r + 31) / 32;  // <= wn + ceil(kappa_r / 32)
   Acc96 acc;
   acc_zero(acc);
-  mul_columns<SA, 1, S>(a, c.wa, c.inv_r, c.wn, 0, cols - 1, 0, P, acc);  // :386-387 (low columns)
+  mul_columns_wide<NC, SA, 1, S>(a, c.wa, c.inv_r, c.wn, 0, cols - 1, 0, P, acc);  // :386-387 (low columns)
   if (negative) limbs_negate<S>(P, cols);
   exact_finish_j<S, SO, ST>(c, P, cols, c.kappa_r, c.kappa_r, t, j_out);    // :389-406
 }
 
 // ---- k from (alpha_d, j) (the second half of sample_j_k_from_alpha_d_r, src/sample.cpp:337-347) --
 // j: wn limbs at stride SJ; a: |alpha_d|, wa limbs at stride SA; k_out: wk limbs at stride SO.
-template <int S, int SA, int SJ, int SO>
+template <int NC, int S, int SA, int SJ, int SO>
 QHD void exact_k_from_alpha_d_j(const ExactConst& c, const uint32_t* a, int negative, const uint32_t* j,
                                 uint32_t* scratch, uint32_t* k_out) {
   uint32_t* P = scratch;  // wn + 4 limbs
   const uint32_t cols = (c.m + c.kbits + 31) / 32;  // = wn for the two-dimensional sampler
   Acc96 acc;
   acc_zero(acc);
-  mul_columns<SJ, 1, S>(j, c.wn, c.d, c.wd, 0, cols - 1, 0, P, acc);  // :338 (low columns)
+  mul_columns_wide<NC, SJ, 1, S>(j, c.wn, c.d, c.wd, 0, cols - 1, 0, P, acc);  // :338 (low columns)
   // P = alpha_d - d j modulo 2^(32 cols) (:339)
   uint32_t borrow = 0, ncarry = 1;
   for (uint32_t i = 0; i < cols; i++) {
@@ -542,7 +545,7 @@ QHD void exact_k_from_alpha_d_j(const ExactConst& c, const uint32_t* a, int nega
 // ---- j from (alpha_d, k) (sample_j_k_from_alpha_d, src/sample.cpp:210-273; k and t_d are drawn
 //      by the caller, :230-239) -------------------------------------------------------------
 // kk: k, wk limbs at stride SK.
-template <int S, int SA, int SK, int SO, int ST>
+template <int NC, int S, int SA, int SK, int SO, int ST>
 QHD void exact_j_from_alpha_d_k(const ExactConst& c, const uint32_t* a, int negative, const uint32_t* kk,
                                 const uint32_t* t, uint32_t* scratch, uint32_t* j_out) {
   uint32_t* X = scratch;                             // wn + 4 limbs
@@ -574,7 +577,7 @@ QHD void exact_j_from_alpha_d_k(const ExactConst& c, const uint32_t* a, int nega
   }
   Acc96 acc;
   acc_zero(acc);
-  mul_columns<S, 1, S>(X, c.wn, c.inv_d, c.wn, 0, c.wn - 1, 0, P, acc);  // :259 (low columns)
+  mul_columns_wide<NC, S, 1, S>(X, c.wn, c.inv_d, c.wn, 0, c.wn - 1, 0, P, acc);  // :259 (low columns)
   exact_finish_j<S, SO, ST>(c, P, c.wn, 0, c.kappa_d, t, j_out);           // :261-268
 }
 

@@ -26,7 +26,7 @@ namespace qb200 {
 #define QB_EXACT_MAX_KAPPA 64
 
 struct ExactHost {
-  std::vector<uint32_t> inv_r, inv_d, d;  // QB_DIAGK_PAD zero limbs, the number, QB_DIAGK_PAD zero limbs
+  std::vector<uint32_t> inv_r, inv_d, d;  // QB_EXACT_PAD zero limbs, the number, QB_EXACT_PAD zero limbs
   std::vector<uint32_t> table;
   ExactConst c;
 };
@@ -149,13 +149,13 @@ inline int exact_prepare(int kind, uint32_t m, uint32_t l, uint32_t sigma, const
   while ((1u << c.table_log) < dimension_max) c.table_log++;
   c.P = emax + QB_EXACT_GUARD;
   c.tw = (c.P + 1 + 31) / 32;
-  h->inv_r = limbs32_padded(big_inverse_mod_pow2(r.shr(c.kappa_r), n), c.wn);
-  h->inv_d = limbs32_padded(big_inverse_mod_pow2(d.shr(c.kappa_d), n), c.wn);
-  h->d = limbs32_padded(d, c.wd);
+  h->inv_r = limbs32_padded(big_inverse_mod_pow2(r.shr(c.kappa_r), n), c.wn, QB_EXACT_PAD);
+  h->inv_d = limbs32_padded(big_inverse_mod_pow2(d.shr(c.kappa_d), n), c.wn, QB_EXACT_PAD);
+  h->d = limbs32_padded(d, c.wd, QB_EXACT_PAD);
   exact_exp2_table(c.table_log, c.P, c.tw, &h->table);
-  c.inv_r = h->inv_r.data() + QB_DIAGK_PAD;
-  c.inv_d = h->inv_d.data() + QB_DIAGK_PAD;
-  c.d = h->d.data() + QB_DIAGK_PAD;
+  c.inv_r = h->inv_r.data() + QB_EXACT_PAD;
+  c.inv_d = h->inv_d.data() + QB_EXACT_PAD;
+  c.d = h->d.data() + QB_EXACT_PAD;
   c.table = h->table.data();
   return 0;
 }

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA) k_exact_alpha(ExactConst c, cons
 
 // tT: t tiles (tl words per sample; NULL when the kappa in question is 0). kT: k tiles, read in
 // mode 2, written in mode 1.
+template <int NC>
 __global__ void __launch_bounds__(QB_DIAGK_CTA) k_exact_jk(ExactConst c, int mode, const uint32_t* __restrict__ adT,
                                                           const int32_t* __restrict__ neg_d,
                                                           const uint32_t* __restrict__ arT,
@@ -95,12 +96,12 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA) k_exact_jk(ExactConst c, int mod
   extern __shared__ uint32_t sh[];
   // inv_r, inv_d, d with their zero limbs: contiguous in global memory (qb200_exact_create), inv_r first
   const uint32_t words = exact_const_words(c);
-  const uint32_t* src = c.inv_r - QB_DIAGK_PAD;
+  const uint32_t* src = c.inv_r - QB_EXACT_PAD;
   for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sh[i] = src[i];
   __syncthreads();
-  c.inv_r = sh + QB_DIAGK_PAD;
-  c.inv_d = sh + (c.wn + 2 * QB_DIAGK_PAD) + QB_DIAGK_PAD;
-  c.d = sh + 2 * (c.wn + 2 * QB_DIAGK_PAD) + QB_DIAGK_PAD;
+  c.inv_r = sh + QB_EXACT_PAD;
+  c.inv_d = sh + (c.wn + 2 * QB_EXACT_PAD) + QB_EXACT_PAD;
+  c.d = sh + 2 * (c.wn + 2 * QB_EXACT_PAD) + QB_EXACT_PAD;
   const uint32_t n_tiles = (B + QB_DIAGK_CTA - 1) / QB_DIAGK_CTA;
   uint32_t* mine = scratch + (size_t)blockIdx.x * QB_DIAGK_CTA * exact_jk_scratch_limbs(c) + threadIdx.x;
   constexpr int S = QB_DIAGK_CTA;
@@ -114,13 +115,13 @@ __global__ void __launch_bounds__(QB_DIAGK_CTA) k_exact_jk(ExactConst c, int mod
     }
     const uint32_t* t = tT ? tT + tile * tl + threadIdx.x : nullptr;
     if (mode == QB_EXACT_J_FROM_ALPHA_D_K) {
-      exact_j_from_alpha_d_k<S, S, S, S, S>(c, adT + tile * c.wa + threadIdx.x, neg_d[g],
+      exact_j_from_alpha_d_k<NC, S, S, S, S, S>(c, adT + tile * c.wa + threadIdx.x, neg_d[g],
                                             kT + tile * c.wk + threadIdx.x, t, mine, j_out);
       continue;
     }
-    exact_j_from_alpha_r<S, S, S, S>(c, arT + tile * c.wa + threadIdx.x, neg_r[g], t, mine, j_out);
+    exact_j_from_alpha_r<NC, S, S, S, S>(c, arT + tile * c.wa + threadIdx.x, neg_r[g], t, mine, j_out);
     if (mode == QB_EXACT_J_K_FROM_ALPHA_D_R)
-      exact_k_from_alpha_d_j<S, S, S, S>(c, adT + tile * c.wa + threadIdx.x, neg_d[g], j_out, mine,
+      exact_k_from_alpha_d_j<NC, S, S, S, S>(c, adT + tile * c.wa + threadIdx.x, neg_d[g], j_out, mine,
                                          kT + tile * c.wk + threadIdx.x);
   }
 }

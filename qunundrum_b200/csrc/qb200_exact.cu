@@ -34,6 +34,7 @@ struct qb200_exact {
   ExactConst dev;  // pointers into `consts` / `table`
   DBuf consts, table, regions, bytes, scratch, rows, a_d, a_r, neg_d, neg_r, status, t, k, j;
   uint32_t chunk = 0;
+  int columns = 8;  // columns per pass of the products (QB200_EXACT_COLUMNS=4: the narrower form, for the A/B)
   // CUDA events around the last k_exact_alpha [0, 1] and k_exact_jk [2, 3] launch (qb200_exact_kernel_ms)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timed[2] = {false, false};
@@ -106,8 +107,12 @@ int launch_jk(qb200_exact* s, int mode, uint32_t B, const uint32_t* adT, const i
   if (s->scratch.reserve((size_t)grid * QB_DIAGK_CTA * exact_jk_scratch_limbs(c) * 4)) return -100;
   const size_t shmem = (size_t)exact_const_words(c) * 4;
   QD_CUDA(cudaEventRecord(s->ev[2], st));
-  k_exact_jk<<<grid, QB_DIAGK_CTA, shmem, st>>>(s->dev, mode, adT, neg_d, arT, neg_r, tT, tl, kT, B,
-                                                s->scratch.as<uint32_t>(), jT);
+  if (s->columns == 8)
+    k_exact_jk<8><<<grid, QB_DIAGK_CTA, shmem, st>>>(s->dev, mode, adT, neg_d, arT, neg_r, tT, tl, kT, B,
+                                                     s->scratch.as<uint32_t>(), jT);
+  else
+    k_exact_jk<4><<<grid, QB_DIAGK_CTA, shmem, st>>>(s->dev, mode, adT, neg_d, arT, neg_r, tT, tl, kT, B,
+                                                     s->scratch.as<uint32_t>(), jT);
   QD_CUDA(cudaEventRecord(s->ev[3], st));
   s->timed[1] = true;
   *s->launches += 1;
@@ -188,7 +193,7 @@ int qb200_exact_create(qb200_context* ctx, const qb200_params* params, int kind,
   const uint32_t* dev_ptr[3];
   for (int i = 0; i < 3; i++) {
     QD_CUDA(cudaMemcpy(c + at, parts[i]->data(), parts[i]->size() * 4, cudaMemcpyHostToDevice));
-    dev_ptr[i] = c + at + QB_DIAGK_PAD;
+    dev_ptr[i] = c + at + QB_EXACT_PAD;
     at += parts[i]->size();
   }
   QD_CUDA(cudaMemcpy(s->table.p, s->host.table.data(), s->host.table.size() * 4, cudaMemcpyHostToDevice));
@@ -203,6 +208,10 @@ int qb200_exact_create(qb200_context* ctx, const qb200_params* params, int kind,
   while (b > 4096 && b * per > ((size_t)1 << 30)) b /= 2;
   s->chunk = (uint32_t)(b / QB_DIAGK_CTA * QB_DIAGK_CTA);
   for (int i = 0; i < 4; i++) QD_CUDA(cudaEventCreate(&s->ev[i]));
+  {
+    const char* v = getenv("QB200_EXACT_COLUMNS");
+    if (v && *v == '4') s->columns = 4;
+  }
   *out = s.release();
   return 0;
 }

@@ -823,7 +823,7 @@ void hostsim_exact_dims(void* hh, uint32_t* out9) {
 const uint32_t* hostsim_exact_table(void* hh) { return ((ExactHost*)hh)->table.data(); }
 const uint32_t* hostsim_exact_inverse(void* hh, int which) {
   ExactHost* h = (ExactHost*)hh;
-  return (which ? h->inv_d : h->inv_r).data() + QB_DIAGK_PAD;
+  return (which ? h->inv_d : h->inv_r).data() + QB_EXACT_PAD;
 }
 
 // The bytes random_generate_mpz reads for a region (0: see *status).
@@ -868,13 +868,13 @@ void hostsim_exact_jk(void* hh, int mode, uint32_t n, const uint32_t* alpha_d, c
     const uint32_t* ti = t ? t + (size_t)i * tl : nullptr;
     uint32_t* ji = j + (size_t)i * c.wn;
     if (mode == 2) {
-      exact_j_from_alpha_d_k<1, 1, 1, 1, 1>(c, alpha_d + (size_t)i * c.wa, neg_d[i], k + (size_t)i * c.wk, ti,
+      exact_j_from_alpha_d_k<8, 1, 1, 1, 1, 1>(c, alpha_d + (size_t)i * c.wa, neg_d[i], k + (size_t)i * c.wk, ti,
                                             scratch.data(), ji);
       continue;
     }
-    exact_j_from_alpha_r<1, 1, 1, 1>(c, alpha_r + (size_t)i * c.wa, neg_r[i], ti, scratch.data(), ji);
+    exact_j_from_alpha_r<8, 1, 1, 1, 1>(c, alpha_r + (size_t)i * c.wa, neg_r[i], ti, scratch.data(), ji);
     if (mode == 1)
-      exact_k_from_alpha_d_j<1, 1, 1, 1>(c, alpha_d + (size_t)i * c.wa, neg_d[i], ji, scratch.data(),
+      exact_k_from_alpha_d_j<8, 1, 1, 1, 1>(c, alpha_d + (size_t)i * c.wa, neg_d[i], ji, scratch.data(),
                                          k + (size_t)i * c.wk);
   }
 }
