@@ -70,6 +70,12 @@ from .host import (  # noqa: F401
     ExactSampler,
     diagonal_sample_drawn,
     pack_regions,
+    ByteStream,
+    sample_alpha_from_region,
+    sample_j_from_alpha_r,
+    sample_j_from_diagonal_alpha_r,
+    sample_j_k_from_alpha_d,
+    sample_j_k_from_alpha_d_r,
 )
 from . import host  # noqa: F401,E402
 

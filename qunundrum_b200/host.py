@@ -1245,3 +1245,110 @@ def diagonal_sample_drawn(diagk: DiagonalKSampler, exact: ExactSampler, regions,
            "qb200_diagk_sample_drawn")
     ks = [limbs_to_int(K[i]) for i in range(n)] if want_k else None
     return ks, np.stack([xh, xl], axis=1), delta, status, est
+
+
+# ---- the reference's own entry points (src/sample.h), one sample per call --------------------------
+
+class ByteStream:
+    """The random stream as random_generate (src/random.c:88-113) delivers it: bytes, in order."""
+
+    def __init__(self, data: bytes):
+        self.data = bytes(data)
+        self.pos = 0
+
+    def take(self, n: int) -> bytes:
+        if self.pos + n > len(self.data):
+            raise CriticalError("random_generate(): the random stream is exhausted")
+        out = self.data[self.pos:self.pos + n]
+        self.pos += n
+        return out
+
+    def mpz(self, modulus_bits: int, modulus: int) -> int:
+        """random_generate_mpz (src/random.c:158-181) for a modulus of the given bit length."""
+        return int.from_bytes(self.take((modulus_bits + 64 + 8) // 8), "big") % modulus
+
+
+_exact = {}
+
+
+def _exact_for(parameters, sampler=None, ctx=None):
+    """The ExactSampler of a parameter set (kept; any power-of-two dimension up to 16384), or the object
+    handed in (tests pass the CPU twin, which has the same methods)."""
+    if sampler is not None:
+        return sampler
+    key = (type(parameters).__name__, parameters.m, parameters.l, getattr(parameters, "sigma", 0), parameters.d,
+           parameters.r)
+    s = _exact.get(key)
+    if s is None:
+        s = _exact[key] = ExactSampler(parameters, 16384, 0, ctx)
+    return s
+
+
+def _region_of(min_log_alpha: float, max_log_alpha: float, who: str):
+    """(signed slice coordinate, region index, dimension) of a region given by its bounds as
+    distribution_slice_region_coordinates (src/distribution_slice.cpp:130-165) forms them."""
+    sgn = lambda x: -1 if x < 0 else 1  # sgn_d, src/math.cpp:32-34
+    if sgn(min_log_alpha) != sgn(max_log_alpha):
+        raise CriticalError(f"{who}(): Incompatible signs for min_log_alpha and max_log_alpha.")
+    lo, hi = abs(min_log_alpha), abs(max_log_alpha)
+    if lo >= hi:
+        raise CriticalError(f"{who}(): Incompatible absolute values for min_log_alpha and max_log_alpha.")
+    e = math.floor(lo)
+    dim = 1.0 / (hi - lo)
+    region = (lo - e) * dim
+    if dim != int(dim) or int(dim) & (int(dim) - 1) or region != int(region):
+        raise CriticalError(f"{who}(): [{min_log_alpha}, {max_log_alpha}] is not a region of a slice "
+                            "(e + i / D with a power of two D).")
+    return sgn(min_log_alpha) * e, int(region), int(dim)
+
+
+def sample_alpha_from_region(min_log_alpha: float, max_log_alpha: float, kappa: int, random_state: ByteStream,
+                             parameters=None, sampler=None, ctx=None) -> int:
+    """sample_alpha_from_region (src/sample.cpp:78-158): alpha, reading from random_state what the
+    reference reads."""
+    ex = _exact_for(parameters, sampler, ctx)
+    se, region, dim = _region_of(min_log_alpha, max_log_alpha, "sample_alpha_from_region")
+    nbytes, status = ex.region_bytes(se, region, dim)
+    if status:
+        raise CriticalError("sample_alpha_from_region(): the region is outside the sampler's range.")
+    vals, st = ex.alpha([(se, region, dim, 0, nbytes)], kappa, random_state.take(nbytes))
+    if st[0]:
+        raise CriticalError(f"sample_alpha_from_region(): status {int(st[0])}")
+    return vals[0]
+
+
+def _draw_t(kappa: int, random_state: ByteStream) -> int:
+    # random_generate_mpz(t, 2^kappa, random_state), src/sample.cpp:176-180: 2^kappa has kappa + 1 bits
+    return random_state.mpz(kappa + 1, 1 << kappa) if kappa > 0 else 0
+
+
+def sample_j_from_alpha_r(alpha_r: int, parameters, random_state: ByteStream, sampler=None, ctx=None) -> int:
+    """sample_j_from_alpha_r (src/sample.cpp:160-208)."""
+    ex = _exact_for(parameters, sampler, ctx)
+    return ex.j_from_alpha_r([alpha_r], [_draw_t(ex.kappa_r, random_state)])[0]
+
+
+def sample_j_from_diagonal_alpha_r(alpha_r: int, parameters, random_state: ByteStream, sampler=None, ctx=None) -> int:
+    """sample_j_from_diagonal_alpha_r (src/sample.cpp:354-410); parameters: Diagonal_Parameters."""
+    return sample_j_from_alpha_r(alpha_r, parameters, random_state, sampler, ctx)
+
+
+def sample_j_k_from_alpha_d(alpha_d: int, parameters, random_state: ByteStream, sampler=None, ctx=None):
+    """sample_j_k_from_alpha_d (src/sample.cpp:210-273): (j, k); t_d and k are drawn as the reference draws
+    them (:230-239)."""
+    ex = _exact_for(parameters, sampler, ctx)
+    t = _draw_t(ex.kappa_d, random_state)
+    k = random_state.mpz(parameters.l + 1, 1 << parameters.l)
+    return ex.j_from_alpha_d_k([alpha_d], [k], [t])[0], k
+
+
+def sample_j_k_from_alpha_d_r(alpha_d: int, alpha_r: int, parameters, random_state: ByteStream, sampler=None,
+                              ctx=None):
+    """sample_j_k_from_alpha_d_r (src/sample.cpp:275-352): (j, k); t_r a multiple of 2^kappa_t_r (:294-309)."""
+    ex = _exact_for(parameters, sampler, ctx)
+    kt = max(0, ex.kappa_r - ex.kappa_d - parameters.l)
+    t = 0
+    if ex.kappa_r > 0:
+        t = random_state.mpz(ex.kappa_r - kt + 1, 1 << (ex.kappa_r - kt)) << kt
+    js, ks = ex.j_k_from_alpha_d_r([alpha_d], [alpha_r], [t])
+    return js[0], ks[0]

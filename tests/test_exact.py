@@ -495,3 +495,80 @@ def test_full_size_properties_on_the_cpu_twin():
 def test_full_size_properties_gpu(gpu_ctx):
     check_full_size_properties(gpu_factory(gpu_ctx), n=6000)
     check_full_size_properties(gpu_factory(gpu_ctx), m=2048, s=8, kd=2, kr=0, D=2048, n=3000, seed=6)
+
+
+# ---- the reference's own unit tests, restated on the mirror of its interface -------------------------
+# src/test/test_sample.cpp:97-377 with the regions as a slice gives them (sixteenths of a unit of
+# log alpha instead of the tenths the reference's test uses: a slice's dimension is a power of two).
+
+def _centred(v, n):
+    v %= (1 << n)
+    return v - (1 << n) if v >= (1 << (n - 1)) else v   # mod_reduce / the explicit form of :339-343
+
+
+def reference_unit_tests(make_sampler, span=30, kappas=(0, 3, 9)):
+    from qunundrum_b200 import host as qb
+    g = np.random.default_rng(2048)
+    m, t = 2048, 30
+    l = m // 8
+    stream = qb.ByteStream(g.bytes(4 << 20))
+    # test_sample_alpha_from_region (:97-179)
+    d, r = d_r_with_kappa(g, m, 0, 0)
+    P = qb.Parameters(m=m, s=0, d=d, r=r, l=l, t=t)
+    S = make_sampler(P)
+    for kappa in kappas:
+        for i in range(m - span, m + span):
+            for j in range(0, 16, 5):
+                lo, hi = i + j / 16, i + (j + 1) / 16
+                for sign in (1, -1):
+                    alpha = qb.sample_alpha_from_region(sign * lo, sign * hi, kappa, stream, P, sampler=S)
+                    assert (alpha > 0) == (sign > 0) and alpha != 0           # "Incorrect sign."
+                    with mp.workprec(200):
+                        assert lo - 1e-9 <= float(mp.log(abs(alpha), 2)) <= hi  # "Incorrect magnitude."
+                    assert abs(alpha) % (1 << kappa) == 0                      # "Not divisible by 2^kappa."
+    # calling with the bounds in the wrong order is a critical error (:176)
+    with pytest.raises(qb.CriticalError):
+        qb.sample_alpha_from_region(m + 0.5, m, 0, stream, P, sampler=S)
+    with pytest.raises(qb.CriticalError):
+        qb.sample_alpha_from_region(-m, m + 0.5, 0, stream, P, sampler=S)
+    # test_sample_j_from_alpha_r (:181-264): d = r "by convention"; also an even r
+    for kr in (0, 4):
+        _, r = d_r_with_kappa(g, m, 0, kr)
+        P = qb.Parameters(m=m, s=0, d=r, r=r, l=l, t=t)
+        S = make_sampler(P)
+        for i in range(m - span, m + span):
+            for i2 in range(0, 16, 5):
+                for sign in (1, -1):
+                    alpha = qb.sample_alpha_from_region(sign * (i + i2 / 16), sign * (i + (i2 + 1) / 16), kr, stream, P,
+                                                        sampler=S)
+                    j = qb.sample_j_from_alpha_r(alpha, P, stream, sampler=S)
+                    assert _centred(j * r, m + l) == alpha                     # "Failed to correctly sample j."
+    # test_sample_j_k_from_alpha_d (:266-377)
+    for kd in (0, 2):
+        d, _ = d_r_with_kappa(g, m, kd, 0)
+        d |= 1 << (m - 1)
+        P = qb.Parameters(m=m, s=0, d=d, r=d, l=l, t=t)
+        S = make_sampler(P)
+        for i in range(m - span, m + span):
+            for i2 in range(0, 16, 5):
+                for sign in (1, -1):
+                    alpha = qb.sample_alpha_from_region(sign * (i + i2 / 16), sign * (i + (i2 + 1) / 16), kd, stream, P,
+                                                        sampler=S)
+                    j, k = qb.sample_j_k_from_alpha_d(alpha, P, stream, sampler=S)
+                    assert _centred(j * d + (k << m), m + l) == alpha          # "Failed to correctly sample (j, k)."
+    return stream.pos
+
+
+def test_the_references_unit_tests_on_the_cpu_twin():
+    def make(P):
+        return hs.Exact(0, P.m, P.l, 0, P.d, P.r, 16, P.m + 64)
+    assert reference_unit_tests(make, span=6, kappas=(0, 9)) > 0
+
+
+@pytest.mark.gpu
+def test_the_references_unit_tests_gpu(gpu_ctx):
+    from qunundrum_b200 import host as qb
+
+    def make(P):
+        return qb.ExactSampler(P, 16, 0, gpu_ctx)
+    assert reference_unit_tests(make, span=30, kappas=(0, 3, 9)) > 0
