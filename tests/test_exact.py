@@ -572,3 +572,33 @@ def test_the_references_unit_tests_gpu(gpu_ctx):
     def make(P):
         return qb.ExactSampler(P, 16, 0, gpu_ctx)
     assert reference_unit_tests(make, span=30, kappas=(0, 3, 9)) > 0
+
+
+def test_j_k_against_python_integers_over_random_sizes():
+    """Every (j, k) mode against the formulas in Python integers for random m on [8, 300), l on [1, m], kappa up to
+    59 and arguments of any size up to emax: operands shorter than a group of columns, n not a multiple of 32."""
+    g = np.random.default_rng(99)
+    done = 0
+    for _ in range(150):
+        m = int(g.integers(8, 300))
+        l = int(g.integers(1, m + 1))
+        kd = int(g.integers(0, min(60, m - 2))) if g.integers(3) == 0 else 0
+        kr = int(g.integers(0, min(60, m - 2))) if g.integers(3) == 0 else 0
+        d, r = d_r_with_kappa(g, m, kd, kr)
+        ex = hs.Exact(0, m, l, 0, d, r, 4)
+        n, N = m + l, 8
+        A_r = [(-1 if g.integers(2) else 1) * big(g, int(g.integers(1, ex.emax + 1))) for _ in range(N)]
+        A_d = [(-1 if g.integers(2) else 1) * big(g, int(g.integers(1, ex.emax + 1))) for _ in range(N)]
+        inv_r, inv_d = pow(r >> kr, -1, 1 << n), pow(d >> kd, -1, 1 << n)
+        tr = [big(g, kr) if kr else 0 for _ in range(N)]
+        td = [big(g, kd) if kd else 0 for _ in range(N)]
+        ks = [big(g, l) for _ in range(N)]
+        want_j = [(((inv_r * a) >> kr) + (t << (n - kr))) % (1 << n) for a, t in zip(A_r, tr)]     # :185-204
+        want_k = [((a - d * j) >> m) % (1 << l) for a, j in zip(A_d, want_j)]                       # :338-347
+        want_j2 = [(inv_d * ((a - (k << m)) >> kd) + (t << (n - kd))) % (1 << n)
+                   for a, k, t in zip(A_d, ks, td)]                                                 # :244-268
+        assert ex.j_from_alpha_r(A_r, tr) == want_j
+        assert ex.j_k_from_alpha_d_r(A_d, A_r, tr) == (want_j, want_k)
+        assert ex.j_from_alpha_d_k(A_d, ks, td) == want_j2
+        done += 1
+    assert done == 150
