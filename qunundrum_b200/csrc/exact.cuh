@@ -127,9 +127,10 @@ QHD bool exact_near_boundary(const uint32_t* T, uint32_t tw, uint32_t pos) {
 // the largest dimension): not supported. |alpha| < 256 there.
 #define QB_EXACT_MIN_E 8
 
-// out (wa limbs, strided) = round(2^(e + idx / D_max)) as the reference computes it, idx on
-// [0, D_max]. Returns QB_EXACT_OK or QB_EXACT_AMBIGUOUS. Requires e + 1 <= emax (idx = D_max: the
-// bound 2^(e + 1), at the precision of the region below it: `e_region` is the region's own e).
+// out (wa limbs, strided) = round(2^(e + idx / D_max)) as the reference computes it for a region at
+// e_region < QB_EXACT_SMALL_E, idx on [0, D_max] (idx = D_max: the bound 2^(e + 1), at the precision of
+// the region below it). Returns QB_EXACT_OK or QB_EXACT_AMBIGUOUS. Requires e + 1 <= emax. (Regions at
+// e_region >= 31 take the one-pass form inside exact_region_modulus.)
 template <int S>
 QHD int exact_bound(const ExactConst& c, uint32_t e_region, uint32_t e, uint32_t idx, uint32_t* out) {
   if (idx == c.table_dim) {
@@ -139,39 +140,26 @@ QHD int exact_bound(const ExactConst& c, uint32_t e_region, uint32_t e, uint32_t
   const uint32_t* T = c.table + (size_t)idx * c.tw;
   const uint32_t sh = c.P - e;  // >= QB_EXACT_GUARD: the integer part of T 2^(e - P) starts at bit sh
   int status = QB_EXACT_OK;
-  if (e_region < QB_EXACT_SMALL_E) {
-    // both roundings of the reference. mpfr_exp2 at p = 3 (e_region + 1) bits: the value has e + 1
-    // integer bits, so F = p - (e + 1) fractional bits survive, to nearest ...
-    const uint32_t F = 3 * (e_region + 1) - (e + 1);  // on [2 e_region + 1, 61]
-    const uint32_t rp = sh - F;                        // > 64: P - e >= 128 + emax - e
-    uint64_t frac = exact_table_bits64(T, c.tw, rp);   // low F bits: the fraction; above: integer bits
-    uint64_t whole = exact_table_bits64(T, c.tw, sh);  // the integer part (e + 1 <= 32 bits)
-    frac &= (F >= 64) ? ~0ull : ((1ull << F) - 1ull);
-    if (idx != 0) {  // 2^e itself is exact
-      if (exact_near_boundary(T, c.tw, rp)) status = QB_EXACT_AMBIGUOUS;
-      if (exact_table_bits(T, c.tw, rp - 1) & 1u) {
-        frac += 1;
-        if (frac >> F) {
-          frac = 0;
-          whole += 1;
-        }
+  // both roundings of the reference. mpfr_exp2 at p = 3 (e_region + 1) bits: the value has e + 1
+  // integer bits, so F = p - (e + 1) fractional bits survive, to nearest ...
+  const uint32_t F = 3 * (e_region + 1) - (e + 1);  // on [2 e_region + 1, 61]
+  const uint32_t rp = sh - F;                        // > 64: P - e >= 128 + emax - e
+  uint64_t frac = exact_table_bits64(T, c.tw, rp);   // low F bits: the fraction; above: integer bits
+  uint64_t whole = exact_table_bits64(T, c.tw, sh);  // the integer part (e + 1 <= 32 bits)
+  frac &= (1ull << F) - 1ull;
+  if (idx != 0) {  // 2^e itself is exact
+    if (exact_near_boundary(T, c.tw, rp)) status = QB_EXACT_AMBIGUOUS;
+    if (exact_table_bits(T, c.tw, rp - 1) & 1u) {
+      frac += 1;
+      if (frac >> F) {
+        frac = 0;
+        whole += 1;
       }
     }
-    // ... then mpfr_round: to the nearest integer, halves away from zero
-    if (F > 0 && (frac >> (F - 1)) != 0) whole += 1;
-    for (uint32_t i = 0; i < c.wa; i++) QB_L(out, i) = i == 0 ? (uint32_t)whole : (i == 1 ? (uint32_t)(whole >> 32) : 0u);
-    return status;
   }
-  // e_region >= 31: the reference's first rounding moves the value by at most 2^(-2 e - 3) < 2^-64, so
-  // round(2^(e + i/D)) is the reference's unless the value lies within 2^-64 of a half-integer
-  if (idx != 0 && exact_near_boundary(T, c.tw, sh)) status = QB_EXACT_AMBIGUOUS;
-  uint32_t carry = exact_table_bits(T, c.tw, sh - 1) & 1u;
-  for (uint32_t i = 0; i < c.wa; i++) {
-    const uint32_t v = exact_table_bits(T, c.tw, sh + 32u * i);
-    const uint32_t s2 = v + carry;
-    carry = (s2 < v) ? 1u : 0u;
-    QB_L(out, i) = s2;
-  }
+  // ... then mpfr_round: to the nearest integer, halves away from zero
+  if ((frac >> (F - 1)) != 0) whole += 1;
+  for (uint32_t i = 0; i < c.wa; i++) QB_L(out, i) = i == 0 ? (uint32_t)whole : (i == 1 ? (uint32_t)(whole >> 32) : 0u);
   return status;
 }
 
@@ -181,16 +169,6 @@ QHD uint32_t qb_clz32(uint32_t v) {
 #else
   return v ? (uint32_t)__builtin_clz(v) : 32u;
 #endif
-}
-
-// Bit length of a strided number of n limbs.
-template <int S>
-QHD uint32_t limbs_bit_length(const uint32_t* p, uint32_t n) {
-  for (uint32_t i = n; i-- > 0;) {
-    const uint32_t v = QB_L(p, i);
-    if (v) return 32u * i + (32u - qb_clz32(v));
-  }
-  return 0;
 }
 
 // The bytes random_generate_mpz reads for a modulus of `bits` bits (src/random.c:163-164).
