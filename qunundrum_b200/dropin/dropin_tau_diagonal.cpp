@@ -84,7 +84,7 @@ qb200_context* g_ctx = NULL;
 
 struct Stats {
   bool on = false;
-  unsigned long calls = 0, samples = 0, replays = 0, bounds = 0;
+  unsigned long calls = 0, samples = 0, replays = 0, regions = 0;
   double s_draw = 0, s_abi = 0, s_sum = 0;
 } g_stats;
 
@@ -97,9 +97,10 @@ double now_s() {
 void print_stats() {
   if (g_stats.on && g_stats.calls)
     fprintf(stderr,
-            "qunundrum_b200 diagonal tau drop-in: %lu estimates, %lu samples; %.3f s drawing (j, eta) on the host "
-            "(%lu mpfr_exp2 calls), %.3f s inside qb200_diagk_sample, %.3f s summing; %lu replays\n",
-            g_stats.calls, g_stats.samples, g_stats.s_draw, g_stats.bounds, g_stats.s_abi, g_stats.s_sum,
+            "qunundrum_b200 diagonal tau drop-in: %lu estimates, %lu samples; %.3f s choosing regions and reading the "
+            "stream on the host (%lu distinct regions), %.3f s inside qb200_diagk_sample_drawn, %.3f s summing; "
+            "%lu replays\n",
+            g_stats.calls, g_stats.samples, g_stats.s_draw, g_stats.regions, g_stats.s_abi, g_stats.s_sum,
             g_stats.replays);
 }
 
@@ -230,6 +231,7 @@ uint32_t bytes_of_region(int32_t min_log_alpha, uint32_t region, uint32_t dimens
     critical("tau_estimate_diagonal(): %s", qb200_last_error());
   }
   g.region_bytes[key] = n;
+  g_stats.regions++;
   return n;
 }
 

@@ -166,8 +166,8 @@ int qb200_sampler_tau_estimate(qb200_sampler* s, uint32_t n, uint32_t count, con
 }  // extern "C"
 
 // ---- diagonal k sampler entry points (TEST-ONLY, same purpose): the host logic of
-// qunundrum_b200/dropin/dropin_tau_diagonal.cpp -- the (j, eta) draws with the kept region bounds
-// and inverse, the replay after a failing sample, the MPFR sum -- runs in the GPU-less suite
+// qunundrum_b200/dropin/dropin_tau_diagonal.cpp -- the stream layout of the draws, the replay after a
+// failing sample, the MPFR sum -- runs in the GPU-less suite
 // inside integration/tools/tau_diagonal_check.cpp, next to the reference's own
 // tau_estimate_diagonal. k and alpha_phi come from the CPU compile of diagk.cuh.
 extern "C" {
