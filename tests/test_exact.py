@@ -602,3 +602,52 @@ def test_j_k_against_python_integers_over_random_sizes():
         assert ex.j_from_alpha_d_k(A_d, ks, td) == want_j2
         done += 1
     assert done == 150
+
+
+# ---- the committed golden vectors (tests/golden/exact.json, made by tests/golden/make_exact_golden.py from
+#      the reference): no reference needed at run time -------------------------------------------------
+
+def _golden_cases():
+    import json
+    import os
+    from tests.conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "exact.json")) as f:
+        return json.load(f)
+
+
+def check_golden(factory, case):
+    ih = lambda s: int(s, 16)
+    stream = bytes.fromhex(case["stream"])
+    ex = factory(case["kind"], case["m"], case["l"], case["sigma"], ih(case["d"]), ih(case["r"]), case["dimension"])
+    assert (ex.kappa_d, ex.kappa_r) == (case["kappa_d"], case["kappa_r"])
+    D = case["dimension"]
+    for which in ("d", "r"):
+        recs = [s[which] for s in case["samples"]]
+        regs = [(q["min_log_alpha"], q["region"], D, q["offset"], q["length"]) for q in recs]
+        for q in recs:
+            assert ex.region_bytes(q["min_log_alpha"], q["region"], D) == (q["length"], 0)   # the stream layout
+        got, st = ex.alpha(regs, recs[0]["kappa"], stream)
+        assert not st.any()
+        assert got == [ih(q["alpha"]) for q in recs], (case["name"], which)
+    a_d = [ih(s["d"]["alpha"]) for s in case["samples"]]
+    a_r = [ih(s["r"]["alpha"]) for s in case["samples"]]
+    S = case["samples"]
+    if case["kind"] == 1:
+        assert ex.j_from_alpha_r(a_r, [ih(s["t_r"]) for s in S]) == [ih(s["j_diagonal"]) for s in S]
+        return
+    assert ex.j_from_alpha_r(a_r, [ih(s["t_r"]) for s in S]) == [ih(s["j_from_alpha_r"]) for s in S]
+    js, ks = ex.j_k_from_alpha_d_r(a_d, a_r, [ih(s["t_r_scaled"]) for s in S])
+    assert [[format(j, "x"), format(k, "x")] for j, k in zip(js, ks)] == [s["j_k_from_alpha_d_r"] for s in S]
+    assert ex.j_from_alpha_d_k(a_d, [ih(s["k_drawn"]) for s in S], [ih(s["t_d"]) for s in S]) == \
+        [ih(s["j_from_alpha_d_k"]) for s in S]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_golden_vectors_on_the_cpu_twin(case):
+    check_golden(twin_factory, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_golden_vectors_gpu(gpu_ctx, case):
+    check_golden(gpu_factory(gpu_ctx), case)
